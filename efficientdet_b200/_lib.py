@@ -1,0 +1,112 @@
+"""ctypes binding of libeffdet_b200.so (the C ABI declared in include/effdet_b200.h).
+
+There is NO CPU fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libeffdet_b200.so")
+
+OK, E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED = 0, -1, -2, -3, -4
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_SWISH, ACT_SIGMOID = 0, 1, 2, 3
+
+
+class EffdetError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("effdet_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class CapacityError(EffdetError):
+    pass
+
+
+_lib = None
+
+c_void_p, c_int, c_size_t, c_float, c_double = (ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t,
+                                                ctypes.c_float, ctypes.c_double)
+_F4 = c_float * 4
+
+_SIGNATURES = {
+    "effdet_anchors_for_shape_host": [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                      c_void_p, c_int, c_void_p, c_size_t],
+    "effdet_compute_overlap": [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p],
+    "effdet_anchor_targets": [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                              c_void_p, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p],
+    "effdet_regress_boxes": [c_void_p, c_int, c_void_p, _F4, _F4, c_int, c_size_t, c_void_p,
+                             c_void_p],
+    "effdet_clip_boxes": [c_void_p, c_int, c_size_t, c_float, c_float, c_void_p, c_void_p],
+    "effdet_regress_clip_boxes": [c_void_p, c_int, c_void_p, _F4, _F4, c_int, c_size_t, c_float,
+                                  c_float, c_void_p, c_void_p],
+    "effdet_filter_detections": [c_void_p, c_void_p, c_int, c_size_t, c_int, c_float, c_float,
+                                 c_int, c_int, c_int, c_void_p, c_size_t, c_size_t, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+}
+
+
+def load():
+    """Loads the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "efficientdet_b200: %s is missing. Build it with `python -m efficientdet_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.effdet_last_error.restype = ctypes.c_char_p
+    lib.effdet_version.restype = c_int
+    lib.effdet_launch_count.restype = ctypes.c_longlong
+    lib.effdet_filter_detections_workspace_size.restype = c_size_t
+    lib.effdet_filter_detections_workspace_size.argtypes = [c_int, c_size_t, c_int, c_size_t, c_int]
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def register(name, argtypes, restype=c_int):
+    """Used by sibling modules to declare further entry points."""
+    _SIGNATURES[name] = argtypes
+    if _lib is not None:
+        fn = getattr(_lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+
+
+def check(code):
+    if code == OK:
+        return
+    msg = load().effdet_last_error().decode("utf-8", "replace")
+    if code == E_CAPACITY:
+        raise CapacityError(code, msg)
+    if code == E_INVALID:
+        raise ValueError("effdet_b200: " + msg)
+    raise EffdetError(code, msg)
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))
+
+
+def launch_count():
+    return int(load().effdet_launch_count())
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr()
+    return t.ctypes.data
+
+
+def stream_ptr(device=None):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream

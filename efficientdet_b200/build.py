@@ -1,0 +1,72 @@
+"""In-tree build of libeffdet_b200.so with nvcc for sm_100a (B200 only).
+
+    python -m efficientdet_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The .so lands next to this file so that it
+travels to the GPU box with the repo snapshot (it is git-ignored).
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_build")
+LIB = os.path.join(HERE, "libeffdet_b200.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INCLUDE]
+# translation units; "exact" ones are bit-exact integer/index/fp paths: no FMA contraction
+SOURCES = {
+    "core.cu": [],
+    "tail.cu": ["-fmad=false"],
+    "targets.cu": ["-fmad=false"],
+}
+
+
+def _discover():
+    srcs = dict(SOURCES)
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith(".cu") and f not in srcs:
+            srcs[f] = []
+    return srcs
+
+
+def _stale(out, deps):
+    if not os.path.exists(out):
+        return True
+    t = os.path.getmtime(out)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    nvcc = os.environ.get("NVCC", "nvcc")
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(INCLUDE, "effdet_b200.h"))
+    jobs, objs = [], []
+    for src, extra in _discover().items():
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src[:-3] + ".o")
+        objs.append(o)
+        if force or _stale(o, [s] + headers):
+            jobs.append([nvcc] + ARCH + COMMON + extra + ["-c", s, "-o", o])
+
+    def run(cmd):
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), r.stdout))
+        if verbose and r.stdout.strip():
+            print(r.stdout)
+
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        list(ex.map(run, jobs))
+    if force or jobs or _stale(LIB, objs):
+        run([nvcc] + ARCH + ["-shared", "-o", LIB] + objs)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,115 @@
+/* effdet_b200 -- C ABI of the B200-native EfficientDet hot path.
+ *
+ * Drop-in boundary for the path BASELINE.json names: the device work behind
+ * Ely-S/EfficientDet's Python layer API.  The reference has no native/FFI layer
+ * for this path (it is tf.keras Python; TensorFlow stock ops do the device work),
+ * so each entry point cites the reference *Python* interface it replaces
+ * (file:line under the reference tree) -- the host-side mirror in
+ * efficientdet_b200/*.py binds these through ctypes; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative EFFDET_E_* code;
+ *     effdet_last_error() gives a thread-local message.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - activations are NHWC; convolution kernels are Keras HWIO; depthwise HWC(1).
+ *   - dtype: EFFDET_F32 (accuracy mode) or EFFDET_BF16 (speed mode; fp32 accumulate).
+ *   - functions only enqueue work on `stream`; they never synchronise, so they
+ *     are CUDA-graph capturable (unless documented otherwise).
+ */
+#ifndef EFFDET_B200_H_
+#define EFFDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EFFDET_OK 0
+#define EFFDET_E_INVALID (-1)     /* bad argument */
+#define EFFDET_E_CUDA (-2)        /* CUDA runtime error (see effdet_last_error) */
+#define EFFDET_E_CAPACITY (-3)    /* caller-provided workspace too small */
+#define EFFDET_E_UNSUPPORTED (-4) /* shape / dtype combination not implemented */
+
+#define EFFDET_F32 0
+#define EFFDET_BF16 1
+
+#define EFFDET_ACT_NONE 0
+#define EFFDET_ACT_RELU 1
+#define EFFDET_ACT_SWISH 2
+#define EFFDET_ACT_SIGMOID 3
+
+const char *effdet_last_error(void);
+int effdet_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+long long effdet_launch_count(void);
+
+/* ---------------------------------------------------------------- geometry
+ * utils/anchors.py:372-403 generate_anchors, :339-369 shift, :296-336 anchors_for_shape.
+ * Host function: float64 table in level-major / cell-row-major / (ratio,scale) order.
+ * level_hw_host: n_levels x {H, W}.  ratios/scales are the float32-rounded values
+ * promoted to double (utils/anchors.py:46-52).  out_host: (sum H*W*nr*ns, 4) f64. */
+int effdet_anchors_for_shape_host(const int *level_hw_host, const int *sizes_host,
+                                  const int *strides_host, int n_levels,
+                                  const double *ratios_host, int n_ratios,
+                                  const double *scales_host, int n_scales,
+                                  double *out_host, size_t out_capacity_rows);
+
+/* utils/compute_overlap.pyx:13-53 -- IoU matrix (N,K) float64, "+1" convention. */
+int effdet_compute_overlap(const double *boxes, size_t N, const double *query, size_t K,
+                           double *overlaps, void *stream);
+
+/* utils/anchors.py:130-207 anchor_targets_bbox (+ :210-239, :406-439).
+ * anchors (N,4) f64; gt_boxes (B,Kmax,4) f64; gt_labels (B,Kmax) i32; gt_counts (B) i32;
+ * image_hw (B,2) f64 {H,W}, H<0 => skip the centre-outside-image rule.
+ * regression (B,N,5) f32 and labels (B,N,C+1) f32 are fully written (dense, reference
+ * layout).  compact_* (optional, may be NULL): state (B,N) i8 {-1,0,1}, cls (B,N) i32
+ * (class of the matched GT, -1 if not positive) -- the layout the fused loss consumes. */
+int effdet_anchor_targets(const double *anchors, size_t N, const double *gt_boxes,
+                          const int32_t *gt_labels, const int32_t *gt_counts, int B, int Kmax,
+                          const double *image_hw, int num_classes, double negative_overlap,
+                          double positive_overlap, float *regression, float *labels,
+                          int8_t *compact_state, int32_t *compact_cls, void *stream);
+
+/* ---------------------------------------------------------------- detection tail
+ * RegressBoxes.py:126-164 apply_bbox_deltas: out = a + (d*std + mean) * [w,h,w,h],
+ * each op individually rounded to float32 (no FMA contraction).
+ * anchors: (1,N,4) broadcast when anchors_per_image == 0, else (B,N,4). */
+int effdet_regress_boxes(const float *anchors, int anchors_per_image, const float *deltas,
+                         const float mean_host[4], const float std_host[4], int B, size_t N,
+                         float *out, void *stream);
+/* ClipBoxes.py:9-24: x in [0, W-1], y in [0, H-1]. in == out allowed. */
+int effdet_clip_boxes(const float *boxes, int B, size_t N, float height, float width, float *out,
+                      void *stream);
+/* the two fused (model.py:414-429): one read of anchors+deltas, one write. */
+int effdet_regress_clip_boxes(const float *anchors, int anchors_per_image, const float *deltas,
+                              const float mean_host[4], const float std_host[4], int B, size_t N,
+                              float height, float width, float *out, void *stream);
+
+/* FilterDetections.py:37-118 filter_detections mapped over the batch (:183-188).
+ * boxes (B,N,4) f32, classification (B,N,C) f32.
+ * Outputs: boxes (B,max_det,4) f32, scores (B,max_det) f32, labels (B,max_det) i32,
+ * padded with -1; out_indices (optional, may be NULL): (B,max_det) i32 anchor index of
+ * each detection.  nms == 0 reproduces `nms=False` (iou_threshold forced to 0 => no NMS,
+ * FilterDetections.py:170-171, :11).  class_specific == 0 reproduces :86-92.
+ * workspace: device scratch of effdet_filter_detections_workspace_size() bytes;
+ * cand_capacity = max number of (anchor,class) pairs above the threshold over the whole
+ * batch that the workspace can hold.  status (device int32[4]): [0] = 1 if the candidate
+ * list overflowed cand_capacity (outputs invalid, re-run with [1] = required capacity),
+ * [1] = total candidates, [2..3] reserved.  Bit-exact w.r.t. oracle/tail.py. */
+size_t effdet_filter_detections_workspace_size(int B, size_t N, int C, size_t cand_capacity,
+                                               int max_detections);
+int effdet_filter_detections(const float *boxes, const float *classification, int B, size_t N,
+                             int C, float score_threshold, float iou_threshold, int max_detections,
+                             int class_specific, int nms, void *workspace, size_t workspace_bytes,
+                             size_t cand_capacity, float *out_boxes, float *out_scores,
+                             int32_t *out_labels, int32_t *out_indices, int32_t *status,
+                             void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EFFDET_B200_H_ */
