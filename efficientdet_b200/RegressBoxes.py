@@ -31,7 +31,7 @@ def apply_bbox_deltas(boxes, deltas, mean=default_mean, std=default_std):
         raise ValueError("boxes %s incompatible with deltas %s" % (tuple(a.shape), tuple(d.shape)))
     out = torch.empty_like(d)
     _lib.call("effdet_regress_boxes", a.data_ptr(), int(a.shape[0] == B), d.data_ptr(), _f4(mean), _f4(std), B, N, out.data_ptr(), _lib.stream_ptr())
-    return give_back(out, host_d and host_a)
+    return give_back(out, host_d)
 
 
 class RegressBoxes(Layer):

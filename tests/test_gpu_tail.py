@@ -65,7 +65,7 @@ def test_regress_clip_bit_exact(B, N, shared):
     from efficientdet_b200 import RegressBoxes as RB, ClipBoxes as CB
     from oracle import tail
     rng = np.random.default_rng(B * 1000 + N)
-    anchors = _boxes(rng, (1 if shared else B) * N).reshape(-1, N, 4)
+    anchors = _boxes(rng, (1 if shared else B) * N).reshape((1 if shared else B), N, 4)
     deltas = rng.normal(0, 0.5, (B, N, 4)).astype(np.float32)
     got = RB.apply_bbox_deltas(anchors, deltas)
     want = tail.apply_bbox_deltas(np.broadcast_to(anchors, (B, N, 4)), deltas)
