@@ -41,10 +41,44 @@ _SIGNATURES = {
     "effdet_clip_boxes": [c_void_p, c_int, c_size_t, c_float, c_float, c_void_p, c_void_p],
     "effdet_regress_clip_boxes": [c_void_p, c_int, c_void_p, _F4, _F4, c_int, c_size_t, c_float,
                                   c_float, c_void_p, c_void_p],
+    "effdet_zero": [c_void_p, c_size_t, c_void_p],
+    "effdet_bn_fold": [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int,
+                       c_void_p],
+    "effdet_stem_conv": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                         c_int, c_int, c_void_p],
+    "effdet_conv2d": [c_void_p, c_void_p],
+    "effdet_dwconv": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                      c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "effdet_se_gate": [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                       c_int, c_int, c_void_p],
+    "effdet_wbifpn_add": [c_void_p, c_int, c_void_p, c_float, c_void_p, c_size_t, c_int, c_void_p],
+    "effdet_bifpn_node": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                          c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                          c_void_p],
     "effdet_filter_detections": [c_void_p, c_void_p, c_int, c_size_t, c_int, c_float, c_float,
                                  c_int, c_int, c_int, c_void_p, c_size_t, c_size_t, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
 }
+
+
+MAX_GROUPS = 5
+
+
+class ConvDesc(ctypes.Structure):
+    """Mirror of `effdet_conv_desc` (include/effdet_b200.h)."""
+    _fields_ = [
+        ("n_groups", c_int),
+        ("x", c_void_p * MAX_GROUPS), ("y", c_void_p * MAX_GROUPS),
+        ("residual", c_void_p * MAX_GROUPS),
+        ("H", c_int * MAX_GROUPS), ("W", c_int * MAX_GROUPS), ("ldc", c_int * MAX_GROUPS),
+        ("y_batch_stride", ctypes.c_longlong * MAX_GROUPS),
+        ("B", c_int), ("Cin", c_int), ("Cout", c_int), ("kh", c_int), ("kw", c_int),
+        ("stride", c_int),
+        ("weight", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("gate", c_void_p),
+        ("keep", c_void_p),
+        ("act", c_int), ("in_dtype", c_int), ("out_dtype", c_int),
+        ("weight_bf16", c_void_p), ("allow_tensor_core", c_int),
+    ]
 
 
 def load():

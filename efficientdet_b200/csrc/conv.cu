@@ -1,0 +1,312 @@
+// Dense convolutions, SIMT path (fp32 accumulate; activations fp32 or bf16).
+//   stem_conv_kernel     : efficientnet.py:413-423  Conv3x3 s2 (3 -> C0) + BN + swish
+//   conv_igemm_kernel    : implicit-GEMM 1x1 / 3x3 (stride 1/2, TF SAME padding) with fused
+//                          epilogue:  efficientnet.py:228-237 (expand), :289-304 (project + BN
+//                          [+ drop-connect scale] + residual, SE gate folded into the A load,
+//                          :255-286), model.py:71-90 (BiFPN ConvBlock), model.py:293-309 /
+//                          :324-351 (head trunk + final convs, grouped over pyramid levels and
+//                          written straight into the concatenated (B,N,4)/(B,N,C) outputs,
+//                          model.py:393-398)
+//   bn_fold_kernel       : BatchNormalization inference form -> per-channel scale/shift
+// This is the accuracy-mode (fp32) path and the fallback for shapes the tcgen05 kernel
+// (conv_tc.cu) does not take.
+#include "common.cuh"
+
+namespace effdet {
+
+// ------------------------------------------------------------------ BN fold
+__global__ void bn_fold_kernel(const float *__restrict__ gamma, const float *__restrict__ beta,
+                               const float *__restrict__ mean, const float *__restrict__ var,
+                               float eps, float *__restrict__ scale, float *__restrict__ shift,
+                               int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = gamma[c] / sqrtf(var[c] + eps);
+    scale[c] = s;
+    shift[c] = beta[c] - mean[c] * s;
+}
+
+// ------------------------------------------------------------------ stem
+// one thread = one output pixel x all C0 channels (C0 <= 64); weights broadcast from smem
+template <typename TO, int C0>
+__global__ void __launch_bounds__(128)
+stem_conv_kernel(const float *__restrict__ img, const float *__restrict__ w,
+                 const float *__restrict__ scale, const float *__restrict__ shift,
+                 TO *__restrict__ out, int B, int H, int W, int Ho, int Wo, int pad_t, int pad_l) {
+    __shared__ float sw[27 * C0];
+    __shared__ float ss[C0], sb[C0];
+    for (int i = threadIdx.x; i < 27 * C0; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < C0; i += blockDim.x) { ss[i] = scale[i]; sb[i] = shift[i]; }
+    __syncthreads();
+    const size_t total = (size_t)B * Ho * Wo;
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho), b = (int)(p / ((size_t)Wo * Ho));
+    float acc[C0];
+#pragma unroll
+    for (int c = 0; c < C0; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * 2 - pad_t + ky;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ox * 2 - pad_l + kx;
+            if (ix < 0 || ix >= W) continue;
+            const float *px = img + (((size_t)b * H + iy) * W + ix) * 3;
+            const float v0 = px[0], v1 = px[1], v2 = px[2];
+            const float *wk = sw + (ky * 3 + kx) * 3 * C0;
+#pragma unroll
+            for (int c = 0; c < C0; ++c)
+                acc[c] += v0 * wk[c] + v1 * wk[C0 + c] + v2 * wk[2 * C0 + c];
+        }
+    }
+    TO *o = out + p * C0;
+#pragma unroll
+    for (int c = 0; c < C0; ++c) o[c] = from_f<TO>(activate<EFFDET_ACT_SWISH>(acc[c] * ss[c] + sb[c]));
+}
+
+// ------------------------------------------------------------------ implicit GEMM
+constexpr int kMaxGroups = 5;
+struct ConvGroup {
+    const void *x;        // (B,H,W,Cin)
+    void *y;              // output base
+    const void *res;      // optional residual, same indexing as y
+    int H, W, Ho, Wo;
+    int tile_begin;       // first M tile of this group
+    long long y_batch_stride;   // elements between images in y
+    int ldc;              // elements between consecutive output pixels in y
+};
+struct ConvParams {
+    ConvGroup g[kMaxGroups];
+    int n_groups;
+    int B, Cin, Cout, kh, kw, stride;
+    const float *w;       // (kh*kw*Cin, Cout) == Keras HWIO
+    const float *scale;   // per-Cout multiplier (folded BN) or null
+    const float *shift;   // per-Cout addend (folded BN / bias) or null
+    const float *gate;    // (B,Cin) SE gate applied to the input, or null
+    const float *keep;    // (B) drop-connect scale applied before the residual add, or null
+    int act;
+};
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <typename TI> __device__ __forceinline__ void load4(const TI *p, bool vec, int n, float *v);
+template <> __device__ __forceinline__ void load4<float>(const float *p, bool vec, int n, float *v) {
+    if (vec && n >= 4) {
+        float4 t = *reinterpret_cast<const float4 *>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = i < n ? p[i] : 0.f;
+    }
+}
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16 *p, bool vec,
+                                                                   int n, float *v) {
+    if (vec && n >= 4) {
+        uint2 t = *reinterpret_cast<const uint2 *>(p);
+        __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162 *>(&t.x);
+        __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162 *>(&t.y);
+        v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = i < n ? __bfloat162float(p[i]) : 0.f;
+    }
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+conv_igemm_kernel(const ConvParams p) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN];
+    const int tid = threadIdx.x;
+    int gi = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxGroups; ++i)
+        if (i < p.n_groups && (int)blockIdx.x >= p.g[i].tile_begin) gi = i;
+    const ConvGroup G = p.g[gi];
+    const int HoWo = G.Ho * G.Wo;
+    const int M = p.B * HoWo;
+    const int m0 = ((int)blockIdx.x - G.tile_begin) * BM;
+    const int n0 = blockIdx.y * BN;
+    const int Cin = p.Cin, Cout = p.Cout;
+    const int pad_t = max((G.Ho - 1) * p.stride + p.kh - G.H, 0) / 2;   // TF SAME: before = total/2
+    const int pad_l = max((G.Wo - 1) * p.stride + p.kw - G.W, 0) / 2;
+
+    // A-load role: one row, 4 consecutive k
+    const int a_row = tid >> 2, a_k = (tid & 3) * 4;
+    const int am = m0 + a_row;
+    const bool a_ok = am < M;
+    int ab = 0, aoy = 0, aox = 0;
+    if (a_ok) { ab = am / HoWo; int r = am - ab * HoWo; aoy = r / G.Wo; aox = r - aoy * G.Wo; }
+    const bool a_vec = (Cin & 3) == 0;
+    // B-load role: one k row, 4 consecutive n
+    const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+    const bool b_vec = (Cout & 3) == 0;
+    // compute role
+    const int ty = tid >> 4, tx = tid & 15;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const TI *X = static_cast<const TI *>(G.x);
+    const int taps = p.kh * p.kw;
+    for (int tap = 0; tap < taps; ++tap) {
+        const int ky = tap / p.kw, kx = tap - ky * p.kw;
+        const int iy = aoy * p.stride - pad_t + ky, ix = aox * p.stride - pad_l + kx;
+        const bool pix_ok = a_ok && iy >= 0 && iy < G.H && ix >= 0 && ix < G.W;
+        const TI *src = X + (((size_t)ab * G.H + (pix_ok ? iy : 0)) * G.W + (pix_ok ? ix : 0)) * Cin;
+        const float *gsrc = p.gate ? p.gate + (size_t)ab * Cin : nullptr;
+        for (int c0 = 0; c0 < Cin; c0 += BK) {
+            float av[4] = {0.f, 0.f, 0.f, 0.f};
+            const int ck = c0 + a_k;
+            if (pix_ok && ck < Cin) {
+                load4<TI>(src + ck, a_vec, Cin - ck, av);
+                if (gsrc) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) if (ck + i < Cin) av[i] *= gsrc[ck + i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) As[a_k + i][a_row] = av[i];
+            float bv[4] = {0.f, 0.f, 0.f, 0.f};
+            const int kk = c0 + b_k, nn = n0 + b_n;
+            if (kk < Cin && nn < Cout)
+                load4<float>(p.w + ((size_t)tap * Cin + kk) * Cout + nn, b_vec, Cout - nn, bv);
+            *reinterpret_cast<float4 *>(&Bs[b_k][b_n]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < BK; ++k) {
+                const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+                const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+                const float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+
+    // epilogue
+    TO *Y = static_cast<TO *>(G.y);
+    const TO *R = static_cast<const TO *>(G.res);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+        const int b = m / HoWo, pix = m - b * HoWo;
+        const size_t base = (size_t)b * G.y_batch_stride + (size_t)pix * G.ldc;
+        const float kp = p.keep ? p.keep[b] : 1.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= Cout) continue;
+            float v = acc[i][j];
+            if (p.scale) v *= p.scale[n];
+            if (p.shift) v += p.shift[n];
+            v = activate_rt(v, p.act);
+            if (R) v = v * kp + to_f<TO>(R[base + n]);
+            Y[base + n] = from_f<TO>(v);
+        }
+    }
+}
+
+}  // namespace effdet
+
+using namespace effdet;
+
+extern "C" int effdet_bn_fold(const float *gamma, const float *beta, const float *mean,
+                              const float *var, float eps, float *scale, float *shift, int C,
+                              void *stream) {
+    EFFDET_REQUIRE(gamma && beta && mean && var && scale && shift && C > 0, "bad arguments");
+    bn_fold_kernel<<<cdiv(C, 128), 128, 0, as_stream(stream)>>>(gamma, beta, mean, var, eps, scale,
+                                                               shift, C);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+template <typename TO>
+static int launch_stem(const float *img, const float *w, const float *scale, const float *shift,
+                       void *out, int B, int H, int W, int C0, cudaStream_t st) {
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    const int pad_t = ((Ho - 1) * 2 + 3 - H > 0 ? (Ho - 1) * 2 + 3 - H : 0) / 2;
+    const int pad_l = ((Wo - 1) * 2 + 3 - W > 0 ? (Wo - 1) * 2 + 3 - W : 0) / 2;
+    const size_t total = (size_t)B * Ho * Wo;
+    dim3 grid(cdiv(total, 128));
+#define STEM_CASE(C)                                                                             \
+    case C:                                                                                      \
+        stem_conv_kernel<TO, C><<<grid, 128, 0, st>>>(img, w, scale, shift, static_cast<TO *>(out), \
+                                                      B, H, W, Ho, Wo, pad_t, pad_l);           \
+        break;
+    switch (C0) {
+        STEM_CASE(32) STEM_CASE(40) STEM_CASE(48) STEM_CASE(56) STEM_CASE(64) STEM_CASE(8) STEM_CASE(16)
+        default:
+            return fail(EFFDET_E_UNSUPPORTED, "effdet_stem_conv: %sunsupported C0=%lld", "", C0);
+    }
+#undef STEM_CASE
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+extern "C" int effdet_stem_conv(const float *images, const float *kernel, const float *scale,
+                                const float *shift, void *out, int B, int H, int W, int C0,
+                                int out_dtype, void *stream) {
+    EFFDET_REQUIRE(images && kernel && scale && shift && out, "null pointer");
+    EFFDET_REQUIRE(B > 0 && H > 0 && W > 0, "bad sizes");
+    if (out_dtype == EFFDET_F32)
+        return launch_stem<float>(images, kernel, scale, shift, out, B, H, W, C0, as_stream(stream));
+    if (out_dtype == EFFDET_BF16)
+        return launch_stem<__nv_bfloat16>(images, kernel, scale, shift, out, B, H, W, C0,
+                                          as_stream(stream));
+    return fail(EFFDET_E_INVALID, "effdet_stem_conv: bad dtype%s", "");
+}
+
+extern "C" int effdet_conv2d(const effdet_conv_desc *d, void *stream) {
+    EFFDET_REQUIRE(d, "null descriptor");
+    EFFDET_REQUIRE(d->n_groups >= 1 && d->n_groups <= kMaxGroups, "1..5 groups");
+    EFFDET_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0, "bad sizes");
+    EFFDET_REQUIRE((d->kh == 1 && d->kw == 1) || (d->kh == 3 && d->kw == 3), "kernel 1x1 or 3x3");
+    EFFDET_REQUIRE(d->stride == 1 || d->stride == 2, "stride 1 or 2");
+    EFFDET_REQUIRE(d->weight, "null weight");
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_groups = d->n_groups; p.B = d->B; p.Cin = d->Cin; p.Cout = d->Cout;
+    p.kh = d->kh; p.kw = d->kw; p.stride = d->stride;
+    p.w = d->weight; p.scale = d->scale; p.shift = d->shift; p.gate = d->gate; p.keep = d->keep;
+    p.act = d->act;
+    int tiles = 0;
+    const size_t in_es = d->in_dtype == EFFDET_BF16 ? 2 : 4;
+    for (int i = 0; i < d->n_groups; ++i) {
+        ConvGroup &g = p.g[i];
+        EFFDET_REQUIRE(d->x[i] && d->y[i] && d->H[i] > 0 && d->W[i] > 0, "bad group");
+        g.x = d->x[i]; g.y = d->y[i]; g.res = d->residual[i];
+        g.H = d->H[i]; g.W = d->W[i];
+        g.Ho = (d->H[i] + d->stride - 1) / d->stride;
+        g.Wo = (d->W[i] + d->stride - 1) / d->stride;
+        g.tile_begin = tiles;
+        g.ldc = d->ldc[i] ? d->ldc[i] : d->Cout;
+        g.y_batch_stride = d->y_batch_stride[i] ? d->y_batch_stride[i]
+                                                : (long long)g.Ho * g.Wo * g.ldc;
+        EFFDET_REQUIRE((reinterpret_cast<uintptr_t>(g.x) % (4 * in_es)) == 0,
+                       "input must be aligned to 4 elements");
+        tiles += (int)cdiv((size_t)d->B * g.Ho * g.Wo, BM);
+    }
+    EFFDET_REQUIRE((reinterpret_cast<uintptr_t>(d->weight) & 15) == 0, "weights must be 16B aligned");
+    dim3 grid(tiles, cdiv(d->Cout, BN));
+    cudaStream_t st = as_stream(stream);
+    if (d->in_dtype == EFFDET_F32 && d->out_dtype == EFFDET_F32)
+        conv_igemm_kernel<float, float><<<grid, 256, 0, st>>>(p);
+    else if (d->in_dtype == EFFDET_BF16 && d->out_dtype == EFFDET_BF16)
+        conv_igemm_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(p);
+    else if (d->in_dtype == EFFDET_BF16 && d->out_dtype == EFFDET_F32)
+        conv_igemm_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(p);
+    else
+        return fail(EFFDET_E_UNSUPPORTED, "effdet_conv2d: unsupported dtype combination%s", "");
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}

@@ -1,0 +1,397 @@
+// HBM-bound NHWC kernels of the backbone and BiFPN (fp32 math; fp32 or bf16 storage, 16-byte
+// vector accesses along C):
+//   dwconv_kernel      efficientnet.py:242-252  depthwise kxk + BN + swish (+ SE squeeze partial
+//                      sums, :259-260) ; also model.py:48-68 when used stand-alone
+//   se_gate_kernel     efficientnet.py:255-286  the two squeeze-excite FCs -> per-(b,c) gate
+//   wbifpn_add_kernel  layers.py:26-31          fast normalised fusion / keras Add
+//   bifpn_node_kernel  model.py:154-194, :226-266  upsample|maxpool-on-load + fusion +
+//                      DepthwiseConv3x3 + BN + ReLU in one pass (shared-memory halo tile)
+#include "common.cuh"
+
+namespace effdet {
+
+template <typename T, int CV> struct Vec;
+template <> struct Vec<float, 4> {
+    static __device__ __forceinline__ void load(const float *p, float *v) {
+        float4 t = *reinterpret_cast<const float4 *>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float *p, const float *v) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec<__nv_bfloat16, 8> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float *v) {
+        uint4 t = *reinterpret_cast<const uint4 *>(p);
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float *v) {
+        uint4 t;
+        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4 *>(p) = t;
+    }
+};
+template <int CV> __device__ __forceinline__ void loadf(const float *p, float *v) {
+#pragma unroll
+    for (int i = 0; i < CV; i += 4) {
+        float4 t = *reinterpret_cast<const float4 *>(p + i);
+        v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    }
+}
+
+// ------------------------------------------------------------------ depthwise conv
+// block = nvec x PY threads (nvec = C/CV channel vectors); a block covers `ppb` output pixels
+// of one image so the SE partial sums reduce in shared memory before one atomic per channel.
+template <typename T, int CV, int K>
+__global__ void dwconv_kernel(const T *__restrict__ x, const float *__restrict__ w,
+                              const float *__restrict__ scale, const float *__restrict__ shift,
+                              T *__restrict__ y, float *__restrict__ se_sum, int H, int W, int Ho,
+                              int Wo, int C, int stride, int pad_t, int pad_l, int ppb, int act) {
+    extern __shared__ float s_sum[];
+    const int nvec = C / CV;
+    const int PY = blockDim.x / nvec;
+    const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec;
+    const int b = blockIdx.y, c = cv * CV;
+    const int p0 = blockIdx.x * ppb, p1 = min(p0 + ppb, Ho * Wo);
+    if (se_sum) {
+        for (int i = threadIdx.x; i < C; i += blockDim.x) s_sum[i] = 0.f;
+        __syncthreads();
+    }
+    float sc[CV], sh[CV], tot[CV];
+    loadf<CV>(scale + c, sc);
+    loadf<CV>(shift + c, sh);
+#pragma unroll
+    for (int i = 0; i < CV; ++i) tot[i] = 0.f;
+    const T *xb = x + (size_t)b * H * W * C;
+    T *yb = y + (size_t)b * Ho * Wo * C;
+    if (py < PY) {
+        for (int p = p0 + py; p < p1; p += PY) {
+            const int oy = p / Wo, ox = p - oy * Wo;
+            float acc[CV];
+#pragma unroll
+            for (int i = 0; i < CV; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+                const int iy = oy * stride - pad_t + ky;
+                if (iy < 0 || iy >= H) continue;
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    const int ix = ox * stride - pad_l + kx;
+                    if (ix < 0 || ix >= W) continue;
+                    float v[CV], wk[CV];
+                    Vec<T, CV>::load(xb + ((size_t)iy * W + ix) * C + c, v);
+                    loadf<CV>(w + (size_t)(ky * K + kx) * C + c, wk);
+#pragma unroll
+                    for (int i = 0; i < CV; ++i) acc[i] = fmaf(v[i], wk[i], acc[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < CV; ++i) {
+                acc[i] = activate_rt(acc[i] * sc[i] + sh[i], act);
+                tot[i] += acc[i];
+            }
+            Vec<T, CV>::store(yb + (size_t)p * C + c, acc);
+        }
+    }
+    if (se_sum) {
+        if (py < PY) {
+#pragma unroll
+            for (int i = 0; i < CV; ++i) atomicAdd(&s_sum[c + i], tot[i]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&se_sum[(size_t)b * C + i], s_sum[i]);
+    }
+}
+
+// ------------------------------------------------------------------ squeeze-excite FCs
+__global__ void __launch_bounds__(256)
+se_gate_kernel(const float *__restrict__ se_sum, float inv_hw, const float *__restrict__ w1,
+               const float *__restrict__ b1, const float *__restrict__ w2,
+               const float *__restrict__ b2, float *__restrict__ gate, int C, int R) {
+    extern __shared__ float sm[];      // mean[C] | r[R]
+    float *mean = sm, *r = sm + C;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = tid; c < C; c += 256) mean[c] = se_sum[(size_t)b * C + c] * inv_hw;
+    __syncthreads();
+    for (int j = warp; j < R; j += 8) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(mean[c], w1[(size_t)c * R + j], s);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) r[j] = activate<EFFDET_ACT_SWISH>(s + b1[j]);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) {
+        float s = b2[c];
+        for (int j = 0; j < R; ++j) s = fmaf(r[j], w2[(size_t)j * C + c], s);
+        gate[(size_t)b * C + c] = activate<EFFDET_ACT_SIGMOID>(s);
+    }
+}
+
+// ------------------------------------------------------------------ fusion (stand-alone layer)
+struct FuseIn { const void *p[3]; };
+template <typename T, int CV>
+__global__ void __launch_bounds__(256)
+wbifpn_add_kernel(FuseIn in, int n, const float *__restrict__ w, float eps, T *__restrict__ out,
+                  size_t nvec) {
+    float w0 = 1.f, w1 = 1.f, w2 = 1.f, inv = 1.f;
+    if (w) {
+        w0 = fmaxf(w[0], 0.f); w1 = fmaxf(w[1], 0.f); w2 = n > 2 ? fmaxf(w[2], 0.f) : 0.f;
+        inv = w0 + w1 + w2 + eps;
+    }
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        float a[CV], b[CV], c[CV], o[CV];
+        Vec<T, CV>::load(static_cast<const T *>(in.p[0]) + i * CV, a);
+        Vec<T, CV>::load(static_cast<const T *>(in.p[1]) + i * CV, b);
+        if (n > 2) Vec<T, CV>::load(static_cast<const T *>(in.p[2]) + i * CV, c);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) {
+            if (w) {
+                float s = w0 * a[k] + w1 * b[k];
+                if (n > 2) s += w2 * c[k];
+                o[k] = s / inv;
+            } else {
+                float s = a[k] + b[k];
+                if (n > 2) s += c[k];
+                o[k] = s;
+            }
+        }
+        Vec<T, CV>::store(out + i * CV, o);
+    }
+}
+
+// ------------------------------------------------------------------ fused BiFPN node
+constexpr int kTile = 8;           // 8x8 output pixels per block
+constexpr int kHalo = kTile + 2;
+constexpr int kCB = 32;            // channels per block
+
+template <typename T, int CV>
+__global__ void __launch_bounds__(256)
+bifpn_node_kernel(const T *__restrict__ in0, int mode0, const T *__restrict__ in1,
+                  const T *__restrict__ in2, const float *__restrict__ fw, float eps,
+                  const float *__restrict__ dw, const float *__restrict__ scale,
+                  const float *__restrict__ shift, T *__restrict__ out, int H, int W, int C,
+                  int tiles_x) {
+    __shared__ __align__(16) float tile[kHalo * kHalo * kCB];
+    constexpr int NV = kCB / CV;
+    const int b = blockIdx.z, cb0 = blockIdx.y * kCB;
+    const int ty0 = (blockIdx.x / tiles_x) * kTile, tx0 = (blockIdx.x % tiles_x) * kTile;
+    float w0 = 1.f, w1 = 1.f, w2 = 1.f, inv = 1.f;
+    const bool weighted = fw != nullptr;
+    if (weighted) {
+        w0 = fmaxf(fw[0], 0.f); w1 = fmaxf(fw[1], 0.f); w2 = in2 ? fmaxf(fw[2], 0.f) : 0.f;
+        inv = w0 + w1 + w2 + eps;
+    }
+    const int H0 = mode0 == 1 ? H / 2 : (mode0 == 2 ? H * 2 : H);
+    const int W0 = mode0 == 1 ? W / 2 : (mode0 == 2 ? W * 2 : W);
+    const T *p0 = in0 + (size_t)b * H0 * W0 * C;
+    const T *p1 = in1 + (size_t)b * H * W * C;
+    const T *p2 = in2 ? in2 + (size_t)b * H * W * C : nullptr;
+
+    for (int item = threadIdx.x; item < kHalo * kHalo * NV; item += 256) {
+        const int v = item % NV, hp = item / NV;
+        const int hy = hp / kHalo, hx = hp - hy * kHalo;
+        const int yy = ty0 + hy - 1, xx = tx0 + hx - 1, c = cb0 + v * CV;
+        float f[CV];
+#pragma unroll
+        for (int k = 0; k < CV; ++k) f[k] = 0.f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W && c < C) {
+            float a[CV], bb[CV];
+            if (mode0 == 1) {
+                Vec<T, CV>::load(p0 + ((size_t)(yy >> 1) * W0 + (xx >> 1)) * C + c, a);
+            } else if (mode0 == 2) {
+                const T *q = p0 + ((size_t)(2 * yy) * W0 + 2 * xx) * C + c;
+                float t[CV];
+                Vec<T, CV>::load(q, a);
+                Vec<T, CV>::load(q + C, t);
+#pragma unroll
+                for (int k = 0; k < CV; ++k) a[k] = fmaxf(a[k], t[k]);
+                Vec<T, CV>::load(q + (size_t)W0 * C, t);
+#pragma unroll
+                for (int k = 0; k < CV; ++k) a[k] = fmaxf(a[k], t[k]);
+                Vec<T, CV>::load(q + (size_t)W0 * C + C, t);
+#pragma unroll
+                for (int k = 0; k < CV; ++k) a[k] = fmaxf(a[k], t[k]);
+            } else {
+                Vec<T, CV>::load(p0 + ((size_t)yy * W0 + xx) * C + c, a);
+            }
+            Vec<T, CV>::load(p1 + ((size_t)yy * W + xx) * C + c, bb);
+            if (weighted) {
+#pragma unroll
+                for (int k = 0; k < CV; ++k) f[k] = w0 * a[k] + w1 * bb[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < CV; ++k) f[k] = a[k] + bb[k];
+            }
+            if (p2) {
+                float cc[CV];
+                Vec<T, CV>::load(p2 + ((size_t)yy * W + xx) * C + c, cc);
+#pragma unroll
+                for (int k = 0; k < CV; ++k) f[k] += weighted ? w2 * cc[k] : cc[k];
+            }
+            if (weighted) {
+#pragma unroll
+                for (int k = 0; k < CV; ++k) f[k] = f[k] / inv;
+            }
+        }
+        float *dst = tile + (size_t)hp * kCB + v * CV;
+#pragma unroll
+        for (int k = 0; k < CV; k += 4)
+            *reinterpret_cast<float4 *>(dst + k) = make_float4(f[k], f[k + 1], f[k + 2], f[k + 3]);
+    }
+    __syncthreads();
+    T *ob = out + (size_t)b * H * W * C;
+    for (int item = threadIdx.x; item < kTile * kTile * NV; item += 256) {
+        const int v = item % NV, pp = item / NV;
+        const int py = pp / kTile, px = pp - py * kTile;
+        const int yy = ty0 + py, xx = tx0 + px, c = cb0 + v * CV;
+        if (yy >= H || xx >= W || c >= C) continue;
+        float acc[CV];
+#pragma unroll
+        for (int k = 0; k < CV; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float *src = tile + (size_t)((py + ky) * kHalo + px + kx) * kCB + v * CV;
+                float wk[CV];
+                loadf<CV>(dw + (size_t)(ky * 3 + kx) * C + c, wk);
+#pragma unroll
+                for (int k = 0; k < CV; ++k) acc[k] = fmaf(src[k], wk[k], acc[k]);
+            }
+        float sc[CV], sh[CV];
+        loadf<CV>(scale + c, sc);
+        loadf<CV>(shift + c, sh);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) acc[k] = fmaxf(acc[k] * sc[k] + sh[k], 0.f);
+        Vec<T, CV>::store(ob + ((size_t)yy * W + xx) * C + c, acc);
+    }
+}
+
+static bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename T, int CV>
+static int launch_dw(const void *x, const float *w, const float *scale, const float *shift, void *y,
+                     float *se_sum, int B, int H, int W, int C, int k, int stride, int act,
+                     cudaStream_t st) {
+    const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    const int pt = max((Ho - 1) * stride + k - H, 0) / 2, pl = max((Wo - 1) * stride + k - W, 0) / 2;
+    const int nvec = C / CV;
+    if (nvec > 1024) return fail(EFFDET_E_UNSUPPORTED, "effdet_dwconv: %sC=%lld too large", "", C);
+    int PY = 256 / nvec; if (PY < 1) PY = 1;
+    const int threads = nvec * PY;
+    // enough blocks to fill the machine, each with >= 4 pixels per thread-row when possible
+    int ppb = PY * 8;
+    const int HW = Ho * Wo;
+    while (ppb > PY && (size_t)B * cdiv(HW, ppb) < (size_t)kNumSMs * 4) ppb >>= 1;
+    dim3 grid(cdiv(HW, ppb), B);
+    const size_t sm = se_sum ? (size_t)C * sizeof(float) : 0;
+    if (k == 3)
+        dwconv_kernel<T, CV, 3><<<grid, threads, sm, st>>>(
+            static_cast<const T *>(x), w, scale, shift, static_cast<T *>(y), se_sum, H, W, Ho, Wo, C,
+            stride, pt, pl, ppb, act);
+    else
+        dwconv_kernel<T, CV, 5><<<grid, threads, sm, st>>>(
+            static_cast<const T *>(x), w, scale, shift, static_cast<T *>(y), se_sum, H, W, Ho, Wo, C,
+            stride, pt, pl, ppb, act);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+}  // namespace effdet
+
+using namespace effdet;
+
+extern "C" int effdet_dwconv(const void *x, const float *kernel, const float *scale,
+                             const float *shift, void *y, float *se_sum, int B, int H, int W, int C,
+                             int k, int stride, int act, int dtype, void *stream) {
+    EFFDET_REQUIRE(x && kernel && scale && shift && y, "null pointer");
+    EFFDET_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "bad sizes");
+    EFFDET_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+    EFFDET_REQUIRE(k == 3 || k == 5, "kernel size 3 or 5");
+    EFFDET_REQUIRE(stride == 1 || stride == 2, "stride 1 or 2");
+    EFFDET_REQUIRE(al16(x) && al16(y) && al16(kernel) && al16(scale) && al16(shift), "16B alignment");
+    if (dtype == EFFDET_F32)
+        return launch_dw<float, 4>(x, kernel, scale, shift, y, se_sum, B, H, W, C, k, stride, act,
+                                   as_stream(stream));
+    if (dtype == EFFDET_BF16)
+        return launch_dw<__nv_bfloat16, 8>(x, kernel, scale, shift, y, se_sum, B, H, W, C, k, stride,
+                                           act, as_stream(stream));
+    return fail(EFFDET_E_INVALID, "effdet_dwconv: bad dtype%s", "");
+}
+
+extern "C" int effdet_se_gate(const float *se_sum, float inv_hw, const float *w1, const float *b1,
+                              const float *w2, const float *b2, float *gate, int B, int C, int R,
+                              void *stream) {
+    EFFDET_REQUIRE(se_sum && w1 && b1 && w2 && b2 && gate, "null pointer");
+    EFFDET_REQUIRE(B > 0 && C > 0 && R > 0, "bad sizes");
+    const size_t sm = (size_t)(C + R) * sizeof(float);
+    EFFDET_REQUIRE(sm <= 48 * 1024, "C + R too large");
+    se_gate_kernel<<<B, 256, sm, as_stream(stream)>>>(se_sum, inv_hw, w1, b1, w2, b2, gate, C, R);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+extern "C" int effdet_wbifpn_add(const void *const *inputs, int n, const float *w, float eps,
+                                 void *out, size_t count, int dtype, void *stream) {
+    EFFDET_REQUIRE(inputs && out, "null pointer");
+    EFFDET_REQUIRE(n == 2 || n == 3, "2 or 3 inputs");
+    if (count == 0) return EFFDET_OK;
+    FuseIn in;
+    for (int i = 0; i < 3; ++i) {
+        in.p[i] = i < n ? inputs[i] : nullptr;
+        EFFDET_REQUIRE(i >= n || (in.p[i] && al16(in.p[i])), "inputs must be non-null, 16B aligned");
+    }
+    EFFDET_REQUIRE(al16(out), "output must be 16B aligned");
+    cudaStream_t st = as_stream(stream);
+    if (dtype == EFFDET_F32) {
+        EFFDET_REQUIRE(count % 4 == 0, "element count must be a multiple of 4");
+        size_t nv = count / 4;
+        unsigned blocks = cdiv(nv, 256); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        wbifpn_add_kernel<float, 4><<<blocks, 256, 0, st>>>(in, n, w, eps, static_cast<float *>(out), nv);
+    } else if (dtype == EFFDET_BF16) {
+        EFFDET_REQUIRE(count % 8 == 0, "element count must be a multiple of 8");
+        size_t nv = count / 8;
+        unsigned blocks = cdiv(nv, 256); if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        wbifpn_add_kernel<__nv_bfloat16, 8><<<blocks, 256, 0, st>>>(
+            in, n, w, eps, static_cast<__nv_bfloat16 *>(out), nv);
+    } else {
+        return fail(EFFDET_E_INVALID, "effdet_wbifpn_add: bad dtype%s", "");
+    }
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+extern "C" int effdet_bifpn_node(const void *in0, int mode0, const void *in1, const void *in2,
+                                 const float *w, float eps, const float *dw_kernel,
+                                 const float *scale, const float *shift, void *out, int B, int H,
+                                 int W, int C, int dtype, void *stream) {
+    EFFDET_REQUIRE(in0 && in1 && dw_kernel && scale && shift && out, "null pointer");
+    EFFDET_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad sizes (C % 8 == 0)");
+    EFFDET_REQUIRE(mode0 >= 0 && mode0 <= 2, "mode0 in {0,1,2}");
+    EFFDET_REQUIRE(mode0 != 1 || (H % 2 == 0 && W % 2 == 0), "upsample target must be even");
+    EFFDET_REQUIRE(al16(in0) && al16(in1) && (!in2 || al16(in2)) && al16(out) && al16(dw_kernel) &&
+                       al16(scale) && al16(shift), "16B alignment");
+    const int tx = (W + kTile - 1) / kTile, ty = (H + kTile - 1) / kTile;
+    dim3 grid(tx * ty, (C + kCB - 1) / kCB, B);
+    cudaStream_t st = as_stream(stream);
+    if (dtype == EFFDET_F32)
+        bifpn_node_kernel<float, 4><<<grid, 256, 0, st>>>(
+            static_cast<const float *>(in0), mode0, static_cast<const float *>(in1),
+            static_cast<const float *>(in2), w, eps, dw_kernel, scale, shift,
+            static_cast<float *>(out), H, W, C, tx);
+    else if (dtype == EFFDET_BF16)
+        bifpn_node_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(
+            static_cast<const __nv_bfloat16 *>(in0), mode0, static_cast<const __nv_bfloat16 *>(in1),
+            static_cast<const __nv_bfloat16 *>(in2), w, eps, dw_kernel, scale, shift,
+            static_cast<__nv_bfloat16 *>(out), H, W, C, tx);
+    else
+        return fail(EFFDET_E_INVALID, "effdet_bifpn_node: bad dtype%s", "");
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}

@@ -1,0 +1,347 @@
+"""Static launch plan for the EfficientDet forward pass on one GPU.
+
+model.efficientdet() describes the network (Keras layer names, shapes); this module lowers it
+for a fixed (batch, dtype) into a flat list of C-ABI kernel launches over preallocated NHWC
+buffers (liveness-based reuse), optionally captured in a CUDA graph.  torch provides device
+memory, streams and graph capture only -- every launch is a kernel of libeffdet_b200.so.
+
+Replaces the execution of the Keras graph built by the reference's model.py:356-452 /
+efficientnet.py:309-470 (call stack SURVEY.md section 3 (B)).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SWISH, BF16, F32
+
+TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16}
+BN_EPS_BACKBONE = 1e-3            # keras default (efficientnet.py:233-236 passes no epsilon)
+BN_EPS_BIFPN = 1e-4               # model.py:42-45
+BN_MOMENTUM_BIFPN = 0.997
+BN_MOMENTUM_BACKBONE = 0.99
+
+
+class Val:
+    """A planned activation tensor (NHWC)."""
+    __slots__ = ("shape", "dtype", "name", "keep", "t", "last_use")
+
+    def __init__(self, shape, dtype, name=None, keep=False):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = dtype
+        self.name = name
+        self.keep = keep          # never recycled (outputs, taps)
+        self.t = None
+        self.last_use = -1
+
+    @property
+    def nbytes(self):
+        n = 1
+        for s in self.shape:
+            n *= s
+        return n * (2 if self.dtype == BF16 else 4)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+
+class Op:
+    """One kernel launch.  `make` is called after buffers are assigned and returns a
+    zero-argument callable taking only the stream pointer."""
+
+    def __init__(self, kind, inputs, outputs, make, name=""):
+        self.kind, self.inputs, self.outputs, self.make, self.name = kind, inputs, outputs, make, name
+        self.fn = None
+
+
+def _call(name, *args):
+    fn = getattr(_lib.load(), name)
+
+    def run(stream):
+        rc = fn(*args, stream)
+        if rc != 0:
+            _lib.check(rc)
+    return run
+
+
+class Plan:
+    def __init__(self, net, batch, reuse_buffers=True, keep_taps=False):
+        self.net = net
+        self.B = int(batch)
+        self.dev = net.device
+        self.dtype = net.dtype
+        self.ops = []
+        self.vals = []
+        self.taps = {}
+        self.keep_taps = keep_taps
+        self.reuse = reuse_buffers and not keep_taps
+        self._keepalive = []
+        self.graph = None
+        self._build()
+        self._assign_buffers()
+        for op in self.ops:
+            op.fn = op.make()
+
+    # -------------------------------------------------------------- helpers
+    def val(self, shape, dtype=None, name=None, keep=False):
+        v = Val(shape, self.dtype if dtype is None else dtype, name, keep or self.keep_taps)
+        self.vals.append(v)
+        return v
+
+    def add(self, kind, inputs, outputs, make, name=""):
+        self.ops.append(Op(kind, [i for i in inputs if i is not None], outputs, make, name))
+
+    def w(self, key):
+        return self.net.weights[key]
+
+    def folded(self, bn_name):
+        return self.net.folded[bn_name]
+
+    # -------------------------------------------------------------- op emitters
+    def conv(self, xs, ys, weight_key, cin, cout, k=1, stride=1, scale=None, shift=None, act=ACT_NONE,
+             gate=None, keep=None, residuals=None, ldc=None, ybs=None, y_offsets=None,
+             in_dtype=None, out_dtype=None, name=""):
+        """xs / ys: lists of Vals (one per group).  y_offsets: byte offsets into ys[i]."""
+        n = len(xs)
+        residuals = residuals or [None] * n
+        wt = self.w(weight_key)
+        in_dt = self.dtype if in_dtype is None else in_dtype
+        out_dt = self.dtype if out_dtype is None else out_dtype
+
+        def make():
+            d = _lib.ConvDesc()
+            d.n_groups = n
+            for i in range(n):
+                d.x[i] = xs[i].ptr
+                d.y[i] = ys[i].ptr + (y_offsets[i] if y_offsets else 0)
+                d.residual[i] = residuals[i].ptr if residuals[i] is not None else None
+                d.H[i], d.W[i] = xs[i].shape[1], xs[i].shape[2]
+                d.ldc[i] = ldc[i] if ldc else 0
+                d.y_batch_stride[i] = ybs[i] if ybs else 0
+            d.B, d.Cin, d.Cout, d.kh, d.kw, d.stride = self.B, cin, cout, k, k, stride
+            d.weight = wt.data_ptr()
+            d.scale = scale.data_ptr() if scale is not None else None
+            d.shift = shift.data_ptr() if shift is not None else None
+            d.gate = gate.ptr if gate is not None else None
+            d.keep = keep.data_ptr() if keep is not None else None
+            d.act, d.in_dtype, d.out_dtype = act, in_dt, out_dt
+            d.weight_bf16 = None
+            d.allow_tensor_core = 1 if self.net.use_tensor_cores else 0
+            self._keepalive.append(d)
+            return _call("effdet_conv2d", ctypes.byref(d))
+        ins = list(xs) + [r for r in residuals if r is not None] + ([gate] if gate is not None else [])
+        self.add("conv", ins, list(ys), make, name)
+
+    # -------------------------------------------------------------- network lowering
+    def _build(self):
+        net, B, S = self.net, self.B, self.net.image_size
+        bb = net.backbone
+        self.images = self.val((B, S, S, 3), F32, "images", keep=True)
+        # one zero-initialised region for all squeeze-excite partial sums
+        se_total = sum(b.mid_filters for b in bb.blocks) * B
+        self.se_sums = self.val((se_total,), F32, "se_sums", keep=True)
+        self.add("memset", [], [self.se_sums],
+                 lambda: _call("effdet_zero", self.se_sums.ptr, self.se_sums.nbytes), "se_zero")
+        H = (S + 1) // 2
+        c0 = bb.stem_filters
+        x = self.val((B, H, H, c0), name="stem")
+        sc, sh = self.folded("stem_bn")
+        self.add("stem", [self.images], [x],
+                 lambda x=x: _call("effdet_stem_conv", self.images.ptr, self.w("stem_conv/kernel").data_ptr(),
+                                   sc.data_ptr(), sh.data_ptr(), x.ptr, B, S, S, c0, self.dtype),
+                 "stem_conv")
+        feats, se_off = [], 0
+        for bi, blk in enumerate(bb.blocks):
+            p = blk.prefix
+            inp, cin, cmid, cout = x, blk.input_filters, blk.mid_filters, blk.output_filters
+            if blk.expand_ratio != 1:
+                e = self.val((B, H, H, cmid), name=p + "expand")
+                s1, b1 = self.folded(p + "expand_bn")
+                self.conv([x], [e], p + "expand_conv/kernel", cin, cmid, scale=s1, shift=b1,
+                          act=ACT_SWISH, name=p + "expand_conv")
+                x = e
+            Ho = (H + blk.stride - 1) // blk.stride
+            d = self.val((B, Ho, Ho, cmid), name=p + "dw")
+            s2, b2 = self.folded(p + "bn")
+            se_ptr_off = se_off * 4
+            self.add("dwconv", [x], [d],
+                     lambda x=x, d=d, p=p, s2=s2, b2=b2, H=H, cmid=cmid, blk=blk, o=se_ptr_off:
+                     _call("effdet_dwconv", x.ptr, self.w(p + "dwconv/depthwise_kernel").data_ptr(),
+                           s2.data_ptr(), b2.data_ptr(), d.ptr, self.se_sums.ptr + o, B, H, H, cmid,
+                           blk.kernel_size, blk.stride, ACT_SWISH, self.dtype), p + "dwconv")
+            gate = self.val((B, cmid), F32, name=p + "gate")
+            self.add("se", [d], [gate],
+                     lambda p=p, gate=gate, Ho=Ho, cmid=cmid, blk=blk, o=se_ptr_off:
+                     _call("effdet_se_gate", self.se_sums.ptr + o, 1.0 / float(Ho * Ho),
+                           self.w(p + "se_reduce/kernel").data_ptr(), self.w(p + "se_reduce/bias").data_ptr(),
+                           self.w(p + "se_expand/kernel").data_ptr(), self.w(p + "se_expand/bias").data_ptr(),
+                           gate.ptr, B, cmid, blk.se_filters), p + "se")
+            se_off += B * cmid
+            y = self.val((B, Ho, Ho, cout), name=p + "out")
+            s3, b3 = self.folded(p + "project_bn")
+            keep = net.drop_scale.get(p) if blk.has_skip else None
+            self.conv([d], [y], p + "project_conv/kernel", cmid, cout, scale=s3, shift=b3,
+                      gate=gate, keep=keep, residuals=[inp] if blk.has_skip else None,
+                      name=p + "project_conv")
+            x, H = y, Ho
+            if bi in bb.feature_after:
+                x.keep = True
+                feats.append(x)
+                self.taps["C%d" % len(feats)] = x
+        self.features = feats
+        # ---- BiFPN
+        Wd = net.w_bifpn
+        for i in range(net.d_bifpn):
+            feats = self._bifpn_layer(feats, i, Wd)
+            for j, f in enumerate(feats):
+                self.taps["BiFPN_%d_P%d" % (i, j + 3)] = f
+        self.pyramid = feats
+        # ---- heads
+        self._heads(feats, Wd)
+
+    def _conv_block(self, x, name, cin, cout, k=1, stride=1):
+        B = self.B
+        Ho = (x.shape[1] + stride - 1) // stride
+        y = self.val((B, Ho, Ho, cout), name=name)
+        sc, sh = self.folded(name + "_bn")
+        self.conv([x], [y], name + "_conv/kernel", cin, cout, k=k, stride=stride, scale=sc, shift=sh,
+                  act=ACT_RELU, name=name + "_conv")
+        return y
+
+    def _node(self, in0, mode0, in1, in2, fuse_name, dw_name, C):
+        B, H = self.B, in1.shape[1]
+        out = self.val((B, H, H, C), name=dw_name)
+        sc, sh = self.folded(dw_name + "_bn")
+        fw = self.w(fuse_name + "/" + fuse_name) if self.net.weighted_bifpn else None
+        self.add("bifpn_node", [in0, in1, in2], [out],
+                 lambda: _call("effdet_bifpn_node", in0.ptr, mode0, in1.ptr,
+                               in2.ptr if in2 is not None else None,
+                               fw.data_ptr() if fw is not None else None, 1e-4,
+                               self.w(dw_name + "_dconv/depthwise_kernel").data_ptr(),
+                               sc.data_ptr(), sh.data_ptr(), out.ptr, B, H, H, C, self.dtype),
+                 dw_name)
+        return out
+
+    def _bifpn_layer(self, feats, i, Wd):
+        pre = "BiFPN_%d_" % i
+        if i == 0:
+            _, _, C3, C4, C5 = feats
+            P3 = self._conv_block(C3, pre + "P3", C3.shape[3], Wd)
+            P4 = self._conv_block(C4, pre + "P4", C4.shape[3], Wd)
+            P5 = self._conv_block(C5, pre + "P5", C5.shape[3], Wd)
+            P6 = self._conv_block(C5, pre + "P6", C5.shape[3], Wd, 3, 2)
+            P7 = self._conv_block(P6, pre + "P7", Wd, Wd, 3, 2)
+        else:
+            P3, P4, P5, P6, P7 = [self._conv_block(f, pre + "P%d" % (3 + j), Wd, Wd)
+                                  for j, f in enumerate(feats)]
+
+        def fn(j):
+            k = 8 * i + j
+            return "w_bi_fpn_add" if k == 0 else "w_bi_fpn_add_%d" % k
+        UP, DOWN = 1, 2
+        P6_td = self._node(P7, UP, P6, None, fn(0), pre + "U_P6", Wd)
+        P5_td = self._node(P6_td, UP, P5, None, fn(1), pre + "U_P5", Wd)
+        P4_td = self._node(P5_td, UP, P4, None, fn(2), pre + "U_P4", Wd)
+        P3_o = self._node(P4_td, UP, P3, None, fn(3), pre + "U_P3", Wd)
+        P4_o = self._node(P3_o, DOWN, P4_td, P4, fn(4), pre + "D_P4", Wd)
+        P5_o = self._node(P4_o, DOWN, P5_td, P5, fn(5), pre + "D_P5", Wd)
+        P6_o = self._node(P5_o, DOWN, P6_td, P6, fn(6), pre + "D_P6", Wd)
+        P7_o = self._node(P6_o, DOWN, P7, None, fn(7), pre + "D_P7", Wd)
+        return [P3_o, P4_o, P5_o, P6_o, P7_o]
+
+    def _heads(self, feats, Wd):
+        net, B = self.net, self.B
+        C, A = net.num_classes, 9
+        hw = [f.shape[1] * f.shape[2] for f in feats]
+        N = A * sum(hw)
+        self.N = N
+        self.regression = self.val((B, N, 4), F32, "regression", keep=True)
+        self.classification = self.val((B, N, C), F32, "classification", keep=True)
+        lvl_off = np.concatenate([[0], np.cumsum([A * h for h in hw])[:-1]])
+        for scope, fmt, final, out, per, act in (
+                ("box_head", "regress_head_conv_%d", "regress_head_conv_final", self.regression, 4,
+                 ACT_NONE),
+                ("class_head", "class_head_%d", "pyramid_classification", self.classification, C,
+                 ACT_SIGMOID)):
+            xs = list(feats)
+            for i in range(net.head_depth):
+                ys = [self.val(x.shape, name="%s_%d_l%d" % (scope, i, l)) for l, x in enumerate(xs)]
+                n = scope + "/" + fmt % i
+                self.conv(xs, ys, n + "/kernel", Wd, Wd, k=3, shift=self.w(n + "/bias"), act=ACT_RELU,
+                          name=n)
+                xs = ys
+            n = scope + "/" + final
+            self.conv(xs, [out] * len(xs), n + "/kernel", Wd, A * per, k=3, shift=self.w(n + "/bias"),
+                      act=act, ldc=[A * per] * len(xs), ybs=[N * per] * len(xs),
+                      y_offsets=[int(o) * per * 4 for o in lvl_off], out_dtype=F32, name=n)
+
+    # -------------------------------------------------------------- buffers
+    def _assign_buffers(self):
+        for idx, op in enumerate(self.ops):
+            for v in op.inputs + op.outputs:
+                v.last_use = max(v.last_use, idx)
+        free = {}
+        total = 0
+
+        def alloc(v):
+            nonlocal total
+            if self.reuse and not v.keep:
+                lst = free.get(v.nbytes)
+                if lst:
+                    v.t = lst.pop()
+                    return
+            v.t = torch.empty(max(v.nbytes, 16), dtype=torch.uint8, device=self.dev)
+            total += v.nbytes
+        done = set()
+        for v in self.vals:
+            if v.last_use < 0:            # e.g. images (only read) -- allocate anyway
+                alloc(v); done.add(id(v))
+        for idx, op in enumerate(self.ops):
+            for v in op.outputs:
+                if id(v) not in done:
+                    alloc(v); done.add(id(v))
+            for v in op.inputs:
+                if id(v) not in done:
+                    alloc(v); done.add(id(v))
+            if self.reuse:
+                for v in set(op.inputs + op.outputs):
+                    if v.last_use == idx and not v.keep and v.t is not None:
+                        free.setdefault(v.nbytes, []).append(v.t)
+        self.activation_bytes = total
+
+    def tensor(self, v):
+        """torch view of a planned value (for tests / outputs)."""
+        return v.t[:v.nbytes].view(TORCH_DTYPE[v.dtype]).view(v.shape)
+
+    # -------------------------------------------------------------- execution
+    def run(self):
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        for op in self.ops:
+            op.fn(stream)
+
+    def capture(self):
+        """Capture the launch list in a CUDA graph (replay with .replay())."""
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            self.run()              # warm-up outside capture
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run()
+        self.graph = g
+        return g
+
+    def replay(self):
+        if self.graph is None:
+            self.run()
+        else:
+            self.graph.replay()
+
+    def forward(self, images):
+        """images: (B,S,S,3) float32 CUDA tensor -> (regression, classification) views."""
+        self.tensor(self.images).copy_(images, non_blocking=True)
+        self.replay()
+        return self.tensor(self.regression), self.tensor(self.classification)

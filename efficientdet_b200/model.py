@@ -1,0 +1,373 @@
+"""efficientdet(phi, ...) builder -- mirror of the reference's model.py:356-452 public surface.
+
+Same signature and return convention (`model` or `(model, prediction_model)`); the returned
+objects expose the slice of the Keras Model API the reference's callers use
+(predict_on_batch, load_weights(by_name=True), layers[i].trainable, compile, fit /
+train_on_batch, summary, optimizer) and execute on the library's CUDA kernels through
+engine.Plan.  Extra keyword-only options of this build (popped before **bbkwargs reach the
+backbone builder): dtype ('fp32' accuracy mode | 'bf16' speed mode), image_size (override of
+model.py:29), seed (numpy default_rng seed of the random initialisation), device.
+"""
+import collections
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+from ._lib import BF16, F32
+from .efficientnet import (EfficientNetB0, EfficientNetB1, EfficientNetB2, EfficientNetB3,
+                           EfficientNetB4, EfficientNetB5, EfficientNetB6)
+from .initializers import PriorProbability
+
+w_bifpns = [64, 88, 112, 160, 224, 288, 384]
+image_sizes = [512, 640, 768, 896, 1024, 1280, 1408]
+backbones = [EfficientNetB0, EfficientNetB1, EfficientNetB2, EfficientNetB3, EfficientNetB4,
+             EfficientNetB5, EfficientNetB6]
+batchnorm_config = {"momentum": 0.997, "epsilon": 1e-4}     # model.py:42-45
+EFFICIENTNET_DEPTHS = [227, 329, 329, 374, 464, 566, 656]  # train_tpu.py:24
+
+
+def _fuse_name(k):
+    return "w_bi_fpn_add" if k == 0 else "w_bi_fpn_add_%d" % k
+
+
+class Network:
+    """Weights (Keras names, fp32 masters on the device) + derived tensors + plans."""
+
+    def __init__(self, phi, num_classes, weighted_bifpn, freeze_bn, backbone, image_size, dtype,
+                 seed, device):
+        self.phi, self.num_classes = phi, int(num_classes)
+        self.weighted_bifpn, self.freeze_bn = bool(weighted_bifpn), bool(freeze_bn)
+        self.backbone = backbone
+        self.image_size = int(image_size)
+        if self.image_size % 128 != 0:
+            raise ValueError("image size must be a multiple of 128 (5 pyramid levels, stride 128)")
+        self.dtype = {"fp32": F32, "float32": F32, "bf16": BF16, "bfloat16": BF16}[dtype]
+        self.device = device
+        self.w_bifpn = w_bifpns[phi]
+        self.d_bifpn = 2 + phi
+        self.head_depth = 3 + int(phi / 3)
+        self.use_tensor_cores = True
+        self.weights = collections.OrderedDict()
+        self.bn_layers = collections.OrderedDict()     # bn layer name -> (C, eps)
+        self.folded = {}
+        self.drop_scale = {}
+        self.frozen_layers = set()
+        self.plans = {}
+        self._init_weights(seed)
+        self.refresh()
+
+    # ---------------------------------------------------------------- initialisation
+    def _put(self, name, arr):
+        self.weights[name] = torch.from_numpy(np.ascontiguousarray(arr, np.float32)).to(self.device)
+
+    def _bn(self, name, C, eps):
+        self._put(name + "/gamma", np.ones(C))
+        self._put(name + "/beta", np.zeros(C))
+        self._put(name + "/moving_mean", np.zeros(C))
+        self._put(name + "/moving_variance", np.ones(C))
+        self.bn_layers[name] = (C, eps)
+        self.folded[name] = (torch.empty(C, dtype=torch.float32, device=self.device),
+                             torch.empty(C, dtype=torch.float32, device=self.device))
+
+    def _init_weights(self, seed):
+        rng = np.random.default_rng(seed)
+
+        def vs_normal(shape, fan_out):      # efficientnet.py:116-129 CONV_KERNEL_INITIALIZER
+            return rng.standard_normal(shape) * math.sqrt(2.0 / fan_out)
+
+        def glorot(shape, fan_in, fan_out):  # keras default kernel initializer (model.py:49-55,72-79)
+            lim = math.sqrt(6.0 / (fan_in + fan_out))
+            return rng.uniform(-lim, lim, shape)
+        bb = self.backbone
+        eps = engine.BN_EPS_BACKBONE
+        self._put("stem_conv/kernel", vs_normal((3, 3, 3, bb.stem_filters), 9 * bb.stem_filters))
+        self._bn("stem_bn", bb.stem_filters, eps)
+        for b in bb.blocks:
+            p, cin, cmid, cout, k = b.prefix, b.input_filters, b.mid_filters, b.output_filters, b.kernel_size
+            if b.expand_ratio != 1:
+                self._put(p + "expand_conv/kernel", vs_normal((1, 1, cin, cmid), cmid))
+                self._bn(p + "expand_bn", cmid, eps)
+            self._put(p + "dwconv/depthwise_kernel", vs_normal((k, k, cmid, 1), k * k))
+            self._bn(p + "bn", cmid, eps)
+            self._put(p + "se_reduce/kernel", vs_normal((1, 1, cmid, b.se_filters), b.se_filters))
+            self._put(p + "se_reduce/bias", np.zeros(b.se_filters))
+            self._put(p + "se_expand/kernel", vs_normal((1, 1, b.se_filters, cmid), cmid))
+            self._put(p + "se_expand/bias", np.zeros(cmid))
+            self._put(p + "project_conv/kernel", vs_normal((1, 1, cmid, cout), cout))
+            self._bn(p + "project_bn", cout, eps)
+        feat_ch = [bb.blocks[i].output_filters for i in bb.feature_after]
+        W, eps = self.w_bifpn, batchnorm_config["epsilon"]
+        for i in range(self.d_bifpn):
+            pre = "BiFPN_%d_" % i
+            for l in range(3, 8):
+                if i == 0:
+                    cin = feat_ch[l - 1] if l <= 5 else (feat_ch[4] if l == 6 else W)
+                    k = 1 if l <= 5 else 3
+                else:
+                    cin, k = W, 1
+                self._put(pre + "P%d_conv/kernel" % l, glorot((k, k, cin, W), k * k * cin, k * k * W))
+                self._bn(pre + "P%d_bn" % l, W, eps)
+            for j, nm in enumerate(["U_P6", "U_P5", "U_P4", "U_P3", "D_P4", "D_P5", "D_P6", "D_P7"]):
+                self._put(pre + nm + "_dconv/depthwise_kernel", glorot((3, 3, W, 1), 9 * W, 9))
+                self._bn(pre + nm + "_bn", W, eps)
+                if self.weighted_bifpn:
+                    n_in = 3 if nm in ("D_P4", "D_P5", "D_P6") else 2
+                    fn = _fuse_name(8 * i + j)
+                    self._put(fn + "/" + fn, np.full((n_in,), 1.0 / n_in))
+        A, C = 9, self.num_classes
+        for i in range(self.head_depth):
+            self._put("box_head/regress_head_conv_%d/kernel" % i, rng.normal(0, 0.01, (3, 3, W, W)))
+            self._put("box_head/regress_head_conv_%d/bias" % i, np.zeros(W))
+        self._put("box_head/regress_head_conv_final/kernel", rng.normal(0, 0.01, (3, 3, W, A * 4)))
+        self._put("box_head/regress_head_conv_final/bias", np.zeros(A * 4))
+        for i in range(self.head_depth):
+            self._put("class_head/class_head_%d/kernel" % i, rng.normal(0, 0.01, (3, 3, W, W)))
+            self._put("class_head/class_head_%d/bias" % i, np.zeros(W))
+        self._put("class_head/pyramid_classification/kernel", rng.normal(0, 0.01, (3, 3, W, A * C)))
+        self._put("class_head/pyramid_classification/bias", PriorProbability(0.01)((A * C,)))
+
+    # ---------------------------------------------------------------- derived tensors
+    def refresh(self):
+        """Re-derive folded BatchNorm scale/shift after the weights changed."""
+        st = _lib.stream_ptr(self.device)
+        for name, (C, eps) in self.bn_layers.items():
+            sc, sh = self.folded[name]
+            _lib.call("effdet_bn_fold", self.weights[name + "/gamma"].data_ptr(),
+                      self.weights[name + "/beta"].data_ptr(),
+                      self.weights[name + "/moving_mean"].data_ptr(),
+                      self.weights[name + "/moving_variance"].data_ptr(), float(eps),
+                      sc.data_ptr(), sh.data_ptr(), C, st)
+
+    def plan(self, batch, **kw):
+        key = (int(batch), tuple(sorted(kw.items())))
+        if key not in self.plans:
+            self.plans[key] = engine.Plan(self, batch, **kw)
+        return self.plans[key]
+
+    # ---------------------------------------------------------------- weight exchange
+    def get_weights_dict(self):
+        return {k: v.detach().cpu().numpy() for k, v in self.weights.items()}
+
+    def set_weights_dict(self, d, strict=False):
+        n = 0
+        for k, v in d.items():
+            k = k[:-2] if k.endswith(":0") else k
+            if k in self.weights:
+                t = self.weights[k]
+                a = np.asarray(v, np.float32)
+                if tuple(a.shape) != tuple(t.shape):
+                    raise ValueError("shape mismatch for %s: %s vs %s" % (k, a.shape, tuple(t.shape)))
+                t.copy_(torch.from_numpy(a))
+                n += 1
+            elif strict:
+                raise KeyError(k)
+        self.refresh()
+        return n
+
+
+class LayerRef:
+    """Handle returned by model.layers[i]: name + trainable flag (train.py:338-339)."""
+
+    def __init__(self, net, name):
+        self._net, self.name = net, name
+
+    @property
+    def trainable(self):
+        return self.name not in self._net.frozen_layers
+
+    @trainable.setter
+    def trainable(self, value):
+        if value:
+            self._net.frozen_layers.discard(self.name)
+        else:
+            self._net.frozen_layers.add(self.name)
+
+
+class Model:
+    """The slice of keras.Model the reference's callers use."""
+
+    def __init__(self, net, name, outputs, anchors=None, score_threshold=0.01, takes_anchors=False):
+        self.net, self.name, self._outputs = net, name, outputs
+        self._anchors = anchors            # baked (1,N,4) float32 CUDA tensor or None
+        self._takes_anchors = takes_anchors
+        self.score_threshold = score_threshold
+        self.output_names = {"train": ["regression", "classification"],
+                             "boxes": ["clipped_boxes", "classification"],
+                             "detections": ["filtered_detections"] * 3}[outputs]
+        self.optimizer = None
+        self.loss = None
+        self._trainer = None
+        self._pinned = {}
+        names = ["input_1"] + net.backbone.keras_layer_names()
+        for i in range(net.d_bifpn):
+            pre = "BiFPN_%d_" % i
+            for l in range(3, 8):
+                names += [pre + "P%d_conv" % l, pre + "P%d_bn" % l, pre + "P%d_relu" % l]
+            for j, nm in enumerate(["U_P6", "U_P5", "U_P4", "U_P3", "D_P4", "D_P5", "D_P6", "D_P7"]):
+                if net.weighted_bifpn:
+                    names.append(_fuse_name(8 * i + j))
+                names += [pre + nm + "_dconv", pre + nm + "_bn", pre + nm + "_relu"]
+        names += ["box_head", "class_head", "regression", "classification"]
+        if outputs != "train":
+            names += ["boxes", "clipped_boxes"] + (["filtered_detections"] if outputs == "detections" else [])
+        self.layers = [LayerRef(net, n) for n in names]
+
+    # ---------------------------------------------------------------- inference
+    def _stage(self, images):
+        """host numpy -> pinned staging buffer -> device (async)."""
+        if isinstance(images, torch.Tensor):
+            return images.to(self.net.device, torch.float32)
+        a = np.ascontiguousarray(images, np.float32)
+        key = a.shape
+        if key not in self._pinned:
+            self._pinned[key] = torch.empty(a.shape, dtype=torch.float32).pin_memory()
+        self._pinned[key].numpy()[...] = a
+        return self._pinned[key].to(self.net.device, non_blocking=True)
+
+    def predict_on_batch_device(self, x):
+        """Same as predict_on_batch but returns CUDA tensors (no device->host copy)."""
+        if isinstance(x, (list, tuple)):
+            images = x[0]
+            anchors = x[1] if len(x) > 1 else None
+        else:
+            images, anchors = x, None
+        net = self.net
+        S = net.image_size
+        if tuple(images.shape[1:]) != (S, S, 3):
+            raise ValueError("expected images of shape (B, %d, %d, 3), got %s" % (S, S, tuple(images.shape)))
+        B = int(images.shape[0])
+        plan = net.plan(B)
+        reg, cls = plan.forward(self._stage(images))
+        if self._outputs == "train":
+            return [reg, cls]
+        if self._takes_anchors:
+            if anchors is None:
+                raise ValueError("this model takes [images, anchors] (model.py:421-427)")
+            a = torch.as_tensor(anchors).to(net.device, torch.float32).contiguous()
+        else:
+            a = self._anchors
+        if a.dim() != 3 or a.shape[1] != plan.N or a.shape[0] not in (1, B):
+            raise ValueError("anchors must be (1 or B, %d, 4)" % plan.N)
+        boxes = torch.empty((B, plan.N, 4), dtype=torch.float32, device=net.device)
+        f4 = _lib.c_float * 4
+        _lib.call("effdet_regress_clip_boxes", a.data_ptr(), int(a.shape[0] == B and B > 1),
+                  reg.data_ptr(), f4(0, 0, 0, 0), f4(.2, .2, .2, .2), B, plan.N, float(S), float(S),
+                  boxes.data_ptr(), _lib.stream_ptr(net.device))
+        if self._outputs == "boxes":
+            return [boxes, cls]
+        from .FilterDetections import _run
+        return list(_run(boxes, cls, True, self.score_threshold, 300, 0.5, True))
+
+    def predict_on_batch(self, x):
+        outs = self.predict_on_batch_device(x)
+        return [o.cpu().numpy() for o in outs]
+
+    def predict(self, x, batch_size=32, **kw):
+        images = x[0] if isinstance(x, (list, tuple)) else x
+        rest = list(x[1:]) if isinstance(x, (list, tuple)) else []
+        outs = []
+        for i in range(0, len(images), batch_size):
+            outs.append(self.predict_on_batch([images[i:i + batch_size]] + rest))
+        return [np.concatenate([o[j] for o in outs], 0) for j in range(len(outs[0]))]
+
+    # ---------------------------------------------------------------- weights
+    def get_weights_dict(self):
+        return self.net.get_weights_dict()
+
+    def set_weights_dict(self, d, strict=False):
+        return self.net.set_weights_dict(d, strict)
+
+    def save_weights(self, path):
+        np.savez(path, **self.net.get_weights_dict())
+
+    def load_weights(self, path, by_name=True, skip_mismatch=False):
+        """Loads a .npz written by save_weights (keys = '<keras layer>/<weight>[:0]').
+        Keras .h5 files need h5py, which this image does not ship (SURVEY 8(f) 'next')."""
+        if str(path).endswith((".h5", ".hdf5")):
+            raise NotImplementedError("Keras .h5 reading needs h5py (not installed); export the "
+                                      "weights to .npz keyed '<layer>/<weight>'")
+        d = {(k[:-2] if k.endswith(":0") else k): v for k, v in dict(np.load(path)).items()}
+        if skip_mismatch:
+            d = {k: v for k, v in d.items() if k in self.net.weights and
+                 tuple(v.shape) == tuple(self.net.weights[k].shape)}
+        return self.net.set_weights_dict(d, strict=not by_name)
+
+    def summary(self, print_fn=print):
+        print_fn('Model: "%s"' % self.name)
+        tot = 0
+        for k, v in self.net.weights.items():
+            print_fn("%-60s %s" % (k, tuple(v.shape)))
+            tot += v.numel()
+        print_fn("Total params: {:,}".format(tot))
+
+    def count_params(self):
+        return sum(v.numel() for v in self.net.weights.values())
+
+    # ---------------------------------------------------------------- training (train.py)
+    def compile(self, optimizer=None, loss=None, **kw):
+        from . import train
+        self.optimizer, self.loss = optimizer, loss
+        self._trainer = train.Trainer(self, optimizer, loss)
+
+    def train_on_batch(self, x, y):
+        if self._trainer is None:
+            raise RuntimeError("compile() the model before training")
+        return self._trainer.step(x, y)
+
+    def fit(self, x=None, y=None, epochs=1, steps_per_epoch=None, batch_size=None, verbose=0, **kw):
+        """x: iterable of (images, (regression_targets, class_targets)) batches, or arrays."""
+        hist = []
+        for _ in range(epochs):
+            it = iter(x) if y is None else iter([(x, y)])
+            for step, (xb, yb) in enumerate(it):
+                if steps_per_epoch is not None and step >= steps_per_epoch:
+                    break
+                hist.append(self.train_on_batch(xb, yb))
+        return hist
+
+
+def efficientdet(phi, num_classes=20, weighted_bifpn=False, freeze_bn=False, score_threshold=0.01,
+                 no_filter=False, anchors=None, just_training_model=False, **bbkwargs):
+    """Builds EfficientDet-D{phi}.  Returns `model` if just_training_model else
+    `(model, prediction_model)` sharing weights (model.py:356-452)."""
+    assert phi in range(7)
+    dtype = bbkwargs.pop("dtype", "fp32")
+    image_size = bbkwargs.pop("image_size", None) or image_sizes[phi]
+    seed = bbkwargs.pop("seed", 2024)
+    device = bbkwargs.pop("device", None)
+    if device is None:
+        from ._tensor import device as _dev
+        device = _dev()
+    backbone = backbones[phi](input_tensor=None, freeze_bn=freeze_bn, **bbkwargs)
+    net = Network(phi, num_classes, weighted_bifpn, freeze_bn, backbone, image_size, dtype, seed,
+                  device)
+    model = Model(net, "efficientdet", "train")
+    if just_training_model:
+        return model
+    baked = None
+    if anchors is not None:
+        arr = np.expand_dims(np.asarray(anchors), axis=0).astype("float32")
+        baked = torch.from_numpy(arr).to(device)
+        net.weights["boxes/anchor_boxes_baked"] = baked
+    prediction_model = Model(net, "efficientdet_p", "boxes" if no_filter else "detections",
+                             anchors=baked, score_threshold=score_threshold,
+                             takes_anchors=anchors is None)
+    return model, prediction_model
+
+
+def _smoke():
+    """Tiny end-to-end check used by __graft_entry__.smoke(): D0 at 128x128, batch 2, against
+    the torch-CPU oracle (fp32, 1e-4 relative)."""
+    from oracle import graph
+    m, pm = efficientdet(0, num_classes=4, image_size=128, drop_connect_rate=0, score_threshold=0.3)
+    rng = np.random.default_rng(1234)
+    img = rng.standard_normal((2, 128, 128, 3)).astype(np.float32)
+    reg, cls = m.predict_on_batch(img)
+    W = m.get_weights_dict()
+    with torch.no_grad():
+        r0, c0 = graph.forward(W, img, 0, 4)
+    for got, want, nm in ((reg, r0.numpy(), "regression"), (cls, c0.numpy(), "classification")):
+        err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-12)
+        assert err < 1e-4, "%s mismatch vs oracle: %g" % (nm, err)

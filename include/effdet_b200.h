@@ -46,6 +46,8 @@ const char *effdet_last_error(void);
 int effdet_version(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 long long effdet_launch_count(void);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream` (zeroes accumulators inside captured graphs) */
+int effdet_zero(void *ptr, size_t bytes, void *stream);
 
 /* ---------------------------------------------------------------- geometry
  * utils/anchors.py:372-403 generate_anchors, :339-369 shift, :296-336 anchors_for_shape.
@@ -108,6 +110,79 @@ int effdet_filter_detections(const float *boxes, const float *classification, in
                              size_t cand_capacity, float *out_boxes, float *out_scores,
                              int32_t *out_labels, int32_t *out_indices, int32_t *status,
                              void *stream);
+
+/* ---------------------------------------------------------------- network forward
+ * BatchNormalization (inference form) folded to per-channel scale/shift:
+ * scale = gamma/sqrt(var+eps), shift = beta - mean*scale  (efficientnet.py:233-236 eps 1e-3;
+ * model.py:42-45 eps 1e-4). */
+int effdet_bn_fold(const float *gamma, const float *beta, const float *moving_mean,
+                   const float *moving_variance, float eps, float *scale, float *shift, int C,
+                   void *stream);
+
+/* efficientnet.py:413-423 stem: Conv3x3 stride 2 SAME (3 -> C0, kernel HWIO f32) + BN + swish.
+ * images (B,H,W,3) f32 -> out (B,ceil(H/2),ceil(W/2),C0) of out_dtype. */
+int effdet_stem_conv(const float *images, const float *kernel, const float *scale,
+                     const float *shift, void *out, int B, int H, int W, int C0, int out_dtype,
+                     void *stream);
+
+/* Dense convolution as implicit GEMM (1x1 or 3x3, stride 1 or 2, TF SAME padding) with fused
+ * epilogue  y = act(conv(x * gate) * scale + shift) [* keep[b] + residual].
+ * Replaces: efficientnet.py:228-237 expand_conv+bn+swish, :289-304 project_conv+bn(+drop)+add
+ * with the SE multiply (:286) folded into the input load; model.py:71-90 ConvBlock;
+ * model.py:293-309 / :324-351 head convs.  Up to 5 "groups" (pyramid levels) share the
+ * weights and run in ONE launch; each group may write with its own row stride (ldc) and
+ * per-image stride so the head outputs land directly in the concatenated (B,N,4)/(B,N,C)
+ * tensors (model.py:393-398) without a concat copy.  0 for ldc / y_batch_stride = dense. */
+#define EFFDET_MAX_GROUPS 5
+typedef struct effdet_conv_desc {
+    int n_groups;
+    const void *x[EFFDET_MAX_GROUPS];        /* (B,H,W,Cin) in_dtype */
+    void *y[EFFDET_MAX_GROUPS];              /* out_dtype */
+    const void *residual[EFFDET_MAX_GROUPS]; /* out_dtype, indexed like y; or NULL */
+    int H[EFFDET_MAX_GROUPS], W[EFFDET_MAX_GROUPS];
+    int ldc[EFFDET_MAX_GROUPS];
+    long long y_batch_stride[EFFDET_MAX_GROUPS];
+    int B, Cin, Cout, kh, kw, stride;
+    const float *weight;  /* (kh,kw,Cin,Cout) f32, Keras HWIO */
+    const float *scale;   /* (Cout) or NULL */
+    const float *shift;   /* (Cout) folded-BN shift or conv bias, or NULL */
+    const float *gate;    /* (B,Cin) f32 squeeze-excite gate, or NULL */
+    const float *keep;    /* (B) f32 drop-connect scale (FixedDropout, efficientnet.py:300-303) or NULL */
+    int act;              /* EFFDET_ACT_* */
+    int in_dtype, out_dtype;
+    const void *weight_bf16; /* optional (kh*kw, Cout_pad, Cin_pad) bf16 panel for the tcgen05 path */
+    int allow_tensor_core;   /* 0 = force the SIMT fp32-accumulate kernel */
+} effdet_conv_desc;
+int effdet_conv2d(const effdet_conv_desc *desc, void *stream);
+
+/* Depthwise kxk (k = 3 or 5, stride 1 or 2, SAME) + BN + activation; optionally accumulates
+ * the per-(image,channel) spatial SUM of the activated output into se_sum (B,C) f32 (must be
+ * zeroed by the caller) for squeeze-excite.  efficientnet.py:242-252 (+ :259-260 squeeze).
+ * kernel (k,k,C) f32 = Keras depthwise_kernel (k,k,C,1).  C % 8 == 0. */
+int effdet_dwconv(const void *x, const float *kernel, const float *scale, const float *shift,
+                  void *y, float *se_sum, int B, int H, int W, int C, int k, int stride, int act,
+                  int dtype, void *stream);
+
+/* Squeeze-excite FCs (efficientnet.py:255-286): mean = se_sum/(HW); r = swish(W1^T mean + b1);
+ * gate = sigmoid(W2^T r + b2).  w1 (C,R), w2 (R,C) f32 (Keras 1x1 conv kernels). gate (B,C) f32. */
+int effdet_se_gate(const float *se_sum, float inv_hw, const float *w1, const float *b1,
+                   const float *w2, const float *b2, float *gate, int B, int C, int R,
+                   void *stream);
+
+/* layers.py:11-39 wBiFPNAdd: out = sum_i relu(w_i) x_i / (sum_i relu(w_i) + eps); w == NULL
+ * gives keras.layers.Add (plain sum).  n_inputs 2 or 3, `count` elements of dtype. */
+int effdet_wbifpn_add(const void *const *inputs_host, int n_inputs, const float *w, float eps,
+                      void *out, size_t count, int dtype, void *stream);
+
+/* One fused BiFPN node (model.py:154-194 / :226-266): resample-on-load + (weighted) fusion +
+ * DepthwiseConv3x3 SAME + BN + ReLU.  in0 is the resampled input: mode 1 = nearest x2 upsample
+ * of a (B,H/2,W/2,C) tensor, mode 2 = 2x2/stride-2 max-pool of a (B,2H,2W,C) tensor, mode 0 =
+ * same resolution.  in1 / in2 (in2 may be NULL) are (B,H,W,C).  Weight order = input order
+ * (SURVEY Appendix D).  w NULL => unweighted Add. */
+int effdet_bifpn_node(const void *in0, int mode0, const void *in1, const void *in2,
+                      const float *w, float eps, const float *dw_kernel, const float *scale,
+                      const float *shift, void *out, int B, int H, int W, int C, int dtype,
+                      void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,247 @@
+"""GPU parity of the network forward kernels against the torch-CPU oracle.
+Tolerances (BASELINE.json north_star): <= 1e-4 relative in fp32 mode, <= 2e-2 in bf16 mode,
+relative = max|got - want| / max|want| per tensor."""
+import numpy as np
+import pytest
+import torch
+
+from util_model import perturb_weights, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL, BF16_TOL = 1e-4, 2e-2
+
+
+def _dev(a, dt=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dt)
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous().numpy()
+
+
+def _nchw(a):
+    return torch.from_numpy(a).permute(0, 3, 1, 2).contiguous()
+
+
+# ------------------------------------------------------------------ single kernels
+@pytest.mark.parametrize("k,stride,H,cin,cout,act", [
+    (1, 1, 16, 24, 144, 2), (1, 1, 8, 1152, 320, 0), (3, 1, 12, 64, 36, 0), (3, 2, 16, 320, 64, 1),
+    (3, 2, 8, 64, 64, 1), (3, 1, 4, 88, 810, 3), (1, 1, 9, 40, 240, 2)])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_conv2d(k, stride, H, cin, cout, act, dtype):
+    from efficientdet_b200 import _lib
+    from oracle import graph
+    import ctypes
+    rng = np.random.default_rng(k * 100 + cin)
+    B = 3
+    tdt = torch.float32 if dtype == "fp32" else torch.bfloat16
+    x = rng.standard_normal((B, H, H, cin)).astype(np.float32)
+    w = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+    sc = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    sh = rng.normal(0, 0.2, cout).astype(np.float32)
+    xd = _dev(x, tdt)
+    xq = xd.float().cpu().numpy()
+    Ho = (H + stride - 1) // stride
+    use_gate = k == 1
+    gate = rng.uniform(0.2, 1.0, (B, cin)).astype(np.float32)
+    res = rng.standard_normal((B, Ho, Ho, cout)).astype(np.float32)
+    keep = rng.uniform(0.5, 1.5, B).astype(np.float32)
+    resd = _dev(res, tdt)
+    out = torch.empty((B, Ho, Ho, cout), dtype=tdt, device="cuda")
+    wd, scd, shd, gd, kd = _dev(w), _dev(sc), _dev(sh), _dev(gate), _dev(keep)
+    d = _lib.ConvDesc()
+    d.n_groups = 1
+    d.x[0], d.y[0], d.residual[0] = xd.data_ptr(), out.data_ptr(), resd.data_ptr()
+    d.H[0], d.W[0] = H, H
+    d.B, d.Cin, d.Cout, d.kh, d.kw, d.stride = B, cin, cout, k, k, stride
+    d.weight, d.scale, d.shift = wd.data_ptr(), scd.data_ptr(), shd.data_ptr()
+    d.gate = gd.data_ptr() if use_gate else None
+    d.keep = kd.data_ptr()
+    d.act = act
+    d.in_dtype = d.out_dtype = _lib.F32 if dtype == "fp32" else _lib.BF16
+    d.allow_tensor_core = 0
+    _lib.call("effdet_conv2d", ctypes.byref(d), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    xin = torch.from_numpy(xq).double()
+    if use_gate:
+        xin = xin * torch.from_numpy(gate).double()[:, None, None, :]
+    y = graph.conv2d(xin.permute(0, 3, 1, 2), w.astype(np.float64), stride)
+    y = y * torch.from_numpy(sc).double().view(1, -1, 1, 1) + torch.from_numpy(sh).double().view(1, -1, 1, 1)
+    y = [lambda v: v, torch.relu, graph.swish, torch.sigmoid][act](y)
+    y = y * torch.from_numpy(keep).double().view(-1, 1, 1, 1) + _nchw(resd.float().cpu().numpy()).double()
+    err = rel_err(out.float().cpu().numpy(), _nhwc(y))
+    assert err < (1e-5 if dtype == "fp32" else 6e-3), err
+
+
+@pytest.mark.parametrize("k,stride,H,C", [(3, 1, 16, 32), (3, 2, 16, 96), (5, 2, 12, 144), (5, 1, 7, 240),
+                                          (3, 1, 5, 1152)])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_dwconv_and_se(k, stride, H, C, dtype):
+    from efficientdet_b200 import _lib
+    from oracle import graph
+    rng = np.random.default_rng(k * 10 + C)
+    B = 2
+    tdt = torch.float32 if dtype == "fp32" else torch.bfloat16
+    dt = _lib.F32 if dtype == "fp32" else _lib.BF16
+    x = rng.standard_normal((B, H, H, C)).astype(np.float32)
+    w = (rng.standard_normal((k, k, C, 1)) / k).astype(np.float32)
+    sc = rng.uniform(0.5, 1.5, C).astype(np.float32)
+    sh = rng.normal(0, 0.2, C).astype(np.float32)
+    xd = _dev(x, tdt)
+    Ho = (H + stride - 1) // stride
+    out = torch.empty((B, Ho, Ho, C), dtype=tdt, device="cuda")
+    se = torch.zeros((B, C), dtype=torch.float32, device="cuda")
+    wd, scd, shd = _dev(w), _dev(sc), _dev(sh)
+    _lib.call("effdet_dwconv", xd.data_ptr(), wd.data_ptr(), scd.data_ptr(), shd.data_ptr(),
+              out.data_ptr(), se.data_ptr(), B, H, H, C, k, stride, _lib.ACT_SWISH, dt, _lib.stream_ptr())
+    xin = _nchw(xd.float().cpu().numpy()).double()
+    y = graph.dwconv2d(xin, w.astype(np.float64), stride)
+    y = graph.swish(y * torch.from_numpy(sc).double().view(1, -1, 1, 1) + torch.from_numpy(sh).double().view(1, -1, 1, 1))
+    tol = 1e-5 if dtype == "fp32" else 6e-3
+    assert rel_err(out.float().cpu().numpy(), _nhwc(y)) < tol
+    want_sum = y.sum(dim=(2, 3)).numpy()
+    assert rel_err(se.cpu().numpy(), want_sum) < 1e-4
+    # SE FCs
+    R = max(1, C // 24)
+    w1 = (rng.standard_normal((C, R)) / np.sqrt(C)).astype(np.float32)
+    b1 = rng.normal(0, 0.1, R).astype(np.float32)
+    w2 = (rng.standard_normal((R, C)) / np.sqrt(R)).astype(np.float32)
+    b2 = rng.normal(0, 0.1, C).astype(np.float32)
+    gate = torch.empty((B, C), dtype=torch.float32, device="cuda")
+    _lib.call("effdet_se_gate", se.data_ptr(), 1.0 / (Ho * Ho), _dev(w1).data_ptr(), _dev(b1).data_ptr(),
+              _dev(w2).data_ptr(), _dev(b2).data_ptr(), gate.data_ptr(), B, C, R, _lib.stream_ptr())
+    mean = se.cpu().double().numpy() / (Ho * Ho)
+    r = mean @ w1.astype(np.float64) + b1
+    r = r / (1 + np.exp(-r))
+    g = 1 / (1 + np.exp(-(r @ w2.astype(np.float64) + b2)))
+    assert rel_err(gate.cpu().numpy(), g) < 1e-5
+
+
+@pytest.mark.parametrize("mode,three,weighted", [(1, False, True), (2, True, True), (2, False, False),
+                                                 (1, False, False), (2, True, False), (0, True, True)])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_bifpn_node(mode, three, weighted, dtype):
+    from efficientdet_b200 import _lib
+    from oracle import graph
+    rng = np.random.default_rng(mode * 7 + three)
+    B, H, C = 2, 12, 88
+    tdt = torch.float32 if dtype == "fp32" else torch.bfloat16
+    dt = _lib.F32 if dtype == "fp32" else _lib.BF16
+    H0 = {0: H, 1: H // 2, 2: H * 2}[mode]
+    a = _dev(rng.standard_normal((B, H0, H0, C)).astype(np.float32), tdt)
+    b = _dev(rng.standard_normal((B, H, H, C)).astype(np.float32), tdt)
+    c = _dev(rng.standard_normal((B, H, H, C)).astype(np.float32), tdt) if three else None
+    fw = np.array([0.7, -0.1, 0.4][:3 if three else 2], np.float32)
+    dw = (rng.standard_normal((3, 3, C, 1)) / 3).astype(np.float32)
+    sc = rng.uniform(0.5, 1.5, C).astype(np.float32)
+    sh = rng.normal(0, 0.2, C).astype(np.float32)
+    out = torch.empty((B, H, H, C), dtype=tdt, device="cuda")
+    fwd, dwd, scd, shd = _dev(fw), _dev(dw), _dev(sc), _dev(sh)
+    _lib.call("effdet_bifpn_node", a.data_ptr(), mode, b.data_ptr(), c.data_ptr() if three else None,
+              fwd.data_ptr() if weighted else None, 1e-4, dwd.data_ptr(), scd.data_ptr(), shd.data_ptr(),
+              out.data_ptr(), B, H, H, C, dt, _lib.stream_ptr())
+    ta = _nchw(a.float().cpu().numpy()).double()
+    if mode == 1:
+        ta = graph.upsample2(ta)
+    elif mode == 2:
+        ta = graph.maxpool2(ta)
+    ins = [ta, _nchw(b.float().cpu().numpy()).double()] + ([_nchw(c.float().cpu().numpy()).double()] if three else [])
+    f = graph.fuse(ins, {"f/f": fw.astype(np.float64)}, weighted, "f")
+    y = graph.dwconv2d(f, dw.astype(np.float64), 1)
+    y = torch.relu(y * torch.from_numpy(sc).double().view(1, -1, 1, 1) + torch.from_numpy(sh).double().view(1, -1, 1, 1))
+    assert rel_err(out.float().cpu().numpy(), _nhwc(y)) < (1e-5 if dtype == "fp32" else 6e-3)
+
+
+def test_wbifpn_add_layer():
+    from efficientdet_b200.layers import wBiFPNAdd
+    rng = np.random.default_rng(0)
+    xs = [rng.standard_normal((2, 8, 8, 16)).astype(np.float32) for _ in range(3)]
+    layer = wBiFPNAdd(name="w_bi_fpn_add_test")
+    out = layer(xs)
+    w = np.full(3, 1 / 3, np.float32)
+    want = (w[0] * xs[0] + w[1] * xs[1] + w[2] * xs[2]) / (w.sum() + np.float32(1e-4))
+    assert rel_err(out, want) < 1e-6
+    layer.set_weights([np.array([0.5, -1.0, 2.0], np.float32)])
+    out = layer(xs)
+    want = (0.5 * xs[0] + 2.0 * xs[2]) / (2.5 + 1e-4)
+    assert rel_err(out, want) < 1e-6
+    assert layer.get_config()["epsilon"] == 1e-4
+    assert layer.compute_output_shape([(2, 8, 8, 16)] * 3) == (2, 8, 8, 16)
+
+
+def test_stem():
+    from efficientdet_b200 import _lib
+    from oracle import graph
+    rng = np.random.default_rng(1)
+    B, S, C0 = 2, 34, 32
+    x = rng.standard_normal((B, S, S, 3)).astype(np.float32)
+    w = (rng.standard_normal((3, 3, 3, C0)) / 5).astype(np.float32)
+    sc = rng.uniform(0.5, 1.5, C0).astype(np.float32)
+    sh = rng.normal(0, 0.2, C0).astype(np.float32)
+    out = torch.empty((B, S // 2, S // 2, C0), dtype=torch.float32, device="cuda")
+    _lib.call("effdet_stem_conv", _dev(x).data_ptr(), _dev(w).data_ptr(), _dev(sc).data_ptr(),
+              _dev(sh).data_ptr(), out.data_ptr(), B, S, S, C0, _lib.F32, _lib.stream_ptr())
+    y = graph.conv2d(_nchw(x).double(), w.astype(np.float64), 2)
+    y = graph.swish(y * torch.from_numpy(sc).double().view(1, -1, 1, 1) + torch.from_numpy(sh).double().view(1, -1, 1, 1))
+    assert rel_err(out.cpu().numpy(), _nhwc(y)) < 1e-5
+
+
+# ------------------------------------------------------------------ whole network
+@pytest.mark.parametrize("phi,size,weighted,dtype,classes", [
+    (0, 128, False, "fp32", 20), (0, 256, True, "fp32", 90), (0, 256, True, "bf16", 20),
+    (1, 128, True, "fp32", 8), (2, 128, False, "bf16", 8)])
+def test_network_forward_per_level(phi, size, weighted, dtype, classes):
+    from efficientdet_b200.model import efficientdet
+    from oracle import graph
+    model = efficientdet(phi, num_classes=classes, weighted_bifpn=weighted, image_size=size,
+                         dtype=dtype, drop_connect_rate=0, just_training_model=True)
+    W = perturb_weights(model)
+    rng = np.random.default_rng(1234)
+    B = 2
+    img = rng.standard_normal((B, size, size, 3)).astype(np.float32)
+    plan = model.net.plan(B, keep_taps=True)
+    reg, cls = plan.forward(torch.from_numpy(img).cuda())
+    torch.cuda.synchronize()
+    taps = {}
+    with torch.no_grad():
+        r0, c0 = graph.forward(W, img, phi, classes, weighted, taps=taps)
+    tol = FP32_TOL if dtype == "fp32" else BF16_TOL
+    worst = {}
+    for name in ["C3", "C4", "C5"] + ["BiFPN_%d_P%d" % (i, l) for i in range(2 + phi) for l in range(3, 8)]:
+        got = plan.tensor(plan.taps[name]).float().cpu().numpy()
+        worst[name] = rel_err(got, taps[name].numpy())
+    worst["regression"] = rel_err(reg.cpu().numpy(), r0.numpy())
+    worst["classification"] = rel_err(cls.cpu().numpy(), c0.numpy())
+    bad = {k: v for k, v in worst.items() if not v < tol}
+    assert not bad, (bad, worst)
+    # model-level API returns the same numbers
+    r1, c1 = model.predict_on_batch(img)
+    assert np.array_equal(r1, reg.cpu().numpy()) or rel_err(r1, reg.cpu().numpy()) < 1e-6
+
+
+def test_prediction_model_end_to_end():
+    """efficientdet() -> prediction_model.predict_on_batch([images, anchors]) vs the oracle tail
+    applied to the oracle's own regression/classification is checked stage-wise: the GPU tail on
+    the GPU's head outputs must be bit-exact w.r.t. the oracle tail on the same inputs."""
+    from efficientdet_b200.model import efficientdet
+    from efficientdet_b200.utils.anchors import anchors_for_shape
+    from oracle import tail
+    size, classes = 256, 6
+    anchors = anchors_for_shape((size, size))
+    model, pmodel = efficientdet(0, num_classes=classes, image_size=size, score_threshold=0.4,
+                                 drop_connect_rate=0)
+    perturb_weights(model)
+    _, pbaked = efficientdet(0, num_classes=classes, image_size=size, score_threshold=0.4,
+                             drop_connect_rate=0, anchors=anchors)
+    pbaked.set_weights_dict({k: v for k, v in model.get_weights_dict().items()})
+    rng = np.random.default_rng(7)
+    img = rng.standard_normal((2, size, size, 3)).astype(np.float32)
+    reg, cls = model.predict_on_batch(img)
+    boxes, scores, labels = pmodel.predict_on_batch([img, anchors[None].astype(np.float32)])
+    b2, s2, l2 = pbaked.predict_on_batch([img])
+    wb = tail.clip_boxes((2, size, size, 3), tail.apply_bbox_deltas(anchors[None].astype(np.float32), reg))
+    ob, os_, ol = tail.filter_detections_batch(wb, cls, score_threshold=0.4)
+    assert np.array_equal(boxes, ob) and np.array_equal(scores, os_) and np.array_equal(labels, ol)
+    assert np.array_equal(b2, ob) and np.array_equal(s2, os_) and np.array_equal(l2, ol)
+    assert boxes.shape == (2, 300, 4) and labels.dtype == np.int32
