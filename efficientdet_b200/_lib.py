@@ -47,10 +47,11 @@ _SIGNATURES = {
     "effdet_stem_conv": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                          c_int, c_int, c_void_p],
     "effdet_conv2d": [c_void_p, c_void_p],
+    "effdet_dwconv_se_blocks": [c_int, c_int, c_int, c_int, c_int, c_int],
     "effdet_dwconv": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                      c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
-    "effdet_se_gate": [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                       c_int, c_int, c_void_p],
+                      c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "effdet_se_gate": [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                       c_int, c_int, c_int, c_void_p],
     "effdet_wbifpn_add": [c_void_p, c_int, c_void_p, c_float, c_void_p, c_size_t, c_int, c_void_p],
     "effdet_bifpn_node": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
                           c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -45,7 +45,9 @@ template <int CV> __device__ __forceinline__ void loadf(const float *p, float *v
 
 // ------------------------------------------------------------------ depthwise conv
 // block = nvec x PY threads (nvec = C/CV channel vectors); a block covers `ppb` output pixels
-// of one image so the SE partial sums reduce in shared memory before one atomic per channel.
+// of one image.  SE partial sums are reduced in a fixed order (registers -> shared rows ->
+// one (image, block, channel) partial in global memory; se_gate_kernel adds the blocks in
+// order), so the forward pass is bit-reproducible run to run -- no float atomics.
 template <typename T, int CV, int K>
 __global__ void dwconv_kernel(const T *__restrict__ x, const float *__restrict__ w,
                               const float *__restrict__ scale, const float *__restrict__ shift,
@@ -57,10 +59,6 @@ __global__ void dwconv_kernel(const T *__restrict__ x, const float *__restrict__
     const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec;
     const int b = blockIdx.y, c = cv * CV;
     const int p0 = blockIdx.x * ppb, p1 = min(p0 + ppb, Ho * Wo);
-    if (se_sum) {
-        for (int i = threadIdx.x; i < C; i += blockDim.x) s_sum[i] = 0.f;
-        __syncthreads();
-    }
     float sc[CV], sh[CV], tot[CV];
     loadf<CV>(scale + c, sc);
     loadf<CV>(shift + c, sh);
@@ -98,24 +96,33 @@ __global__ void dwconv_kernel(const T *__restrict__ x, const float *__restrict__
         }
     }
     if (se_sum) {
-        if (py < PY) {
 #pragma unroll
-            for (int i = 0; i < CV; ++i) atomicAdd(&s_sum[c + i], tot[i]);
-        }
+        for (int i = 0; i < CV; ++i) s_sum[(size_t)py * C + c + i] = tot[i];
         __syncthreads();
-        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&se_sum[(size_t)b * C + i], s_sum[i]);
+        float *dst = se_sum + ((size_t)b * gridDim.x + blockIdx.x) * C;
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            float t = 0.f;
+            for (int r = 0; r < PY; ++r) t += s_sum[(size_t)r * C + i];
+            dst[i] = t;
+        }
     }
 }
 
 // ------------------------------------------------------------------ squeeze-excite FCs
 __global__ void __launch_bounds__(256)
-se_gate_kernel(const float *__restrict__ se_sum, float inv_hw, const float *__restrict__ w1,
-               const float *__restrict__ b1, const float *__restrict__ w2,
-               const float *__restrict__ b2, float *__restrict__ gate, int C, int R) {
+se_gate_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_hw,
+               const float *__restrict__ w1, const float *__restrict__ b1,
+               const float *__restrict__ w2, const float *__restrict__ b2,
+               float *__restrict__ gate, int C, int R) {
     extern __shared__ float sm[];      // mean[C] | r[R]
     float *mean = sm, *r = sm + C;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int c = tid; c < C; c += 256) mean[c] = se_sum[(size_t)b * C + c] * inv_hw;
+    for (int c = tid; c < C; c += 256) {
+        const float *src = se_sum + (size_t)b * se_blocks * C + c;
+        float t = 0.f;
+        for (int k = 0; k < se_blocks; ++k) t += src[(size_t)k * C];
+        mean[c] = t * inv_hw;
+    }
     __syncthreads();
     for (int j = warp; j < R; j += 8) {
         float s = 0.f;
@@ -275,22 +282,31 @@ bifpn_node_kernel(const T *__restrict__ in0, int mode0, const T *__restrict__ in
 
 static bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+static int dw_default_blocks(int B, int HW, int PY) {
+    // enough blocks to fill the machine, each thread row handling up to 8 pixels
+    int ppb = PY * 8;
+    while (ppb > PY && (size_t)B * cdiv(HW, ppb) < (size_t)kNumSMs * 4) ppb >>= 1;
+    return (int)cdiv(HW, ppb);
+}
+
 template <typename T, int CV>
 static int launch_dw(const void *x, const float *w, const float *scale, const float *shift, void *y,
-                     float *se_sum, int B, int H, int W, int C, int k, int stride, int act,
-                     cudaStream_t st) {
+                     float *se_sum, int se_blocks, int B, int H, int W, int C, int k, int stride,
+                     int act, cudaStream_t st) {
     const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
     const int pt = max((Ho - 1) * stride + k - H, 0) / 2, pl = max((Wo - 1) * stride + k - W, 0) / 2;
     const int nvec = C / CV;
     if (nvec > 1024) return fail(EFFDET_E_UNSUPPORTED, "effdet_dwconv: %sC=%lld too large", "", C);
     int PY = 256 / nvec; if (PY < 1) PY = 1;
     const int threads = nvec * PY;
-    // enough blocks to fill the machine, each with >= 4 pixels per thread-row when possible
-    int ppb = PY * 8;
     const int HW = Ho * Wo;
-    while (ppb > PY && (size_t)B * cdiv(HW, ppb) < (size_t)kNumSMs * 4) ppb >>= 1;
-    dim3 grid(cdiv(HW, ppb), B);
-    const size_t sm = se_sum ? (size_t)C * sizeof(float) : 0;
+    int nblk = se_sum ? se_blocks : dw_default_blocks(B, HW, PY);
+    if (nblk < 1 || nblk > HW) return fail(EFFDET_E_INVALID, "effdet_dwconv: bad se_blocks%s", "");
+    const int ppb = (int)cdiv(HW, nblk);
+    if ((int)cdiv(HW, ppb) != nblk)
+        return fail(EFFDET_E_INVALID, "effdet_dwconv: se_blocks %smust come from effdet_dwconv_se_blocks", "");
+    dim3 grid(nblk, B);
+    const size_t sm = se_sum ? (size_t)PY * C * sizeof(float) : 0;
     if (k == 3)
         dwconv_kernel<T, CV, 3><<<grid, threads, sm, st>>>(
             static_cast<const T *>(x), w, scale, shift, static_cast<T *>(y), se_sum, H, W, Ho, Wo, C,
@@ -307,9 +323,21 @@ static int launch_dw(const void *x, const float *w, const float *scale, const fl
 
 using namespace effdet;
 
+extern "C" int effdet_dwconv_se_blocks(int B, int H, int W, int C, int stride, int dtype) {
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || stride < 1) return 0;
+    const int CV = dtype == EFFDET_BF16 ? 8 : 4;
+    const int nvec = C / CV;
+    int PY = 256 / (nvec > 0 ? nvec : 1); if (PY < 1) PY = 1;
+    const int HW = ((H + stride - 1) / stride) * ((W + stride - 1) / stride);
+    int nblk = dw_default_blocks(B, HW, PY);
+    const int ppb = (int)cdiv(HW, nblk);
+    return (int)cdiv(HW, ppb);
+}
+
 extern "C" int effdet_dwconv(const void *x, const float *kernel, const float *scale,
-                             const float *shift, void *y, float *se_sum, int B, int H, int W, int C,
-                             int k, int stride, int act, int dtype, void *stream) {
+                             const float *shift, void *y, float *se_sum, int se_blocks, int B,
+                             int H, int W, int C, int k, int stride, int act, int dtype,
+                             void *stream) {
     EFFDET_REQUIRE(x && kernel && scale && shift && y, "null pointer");
     EFFDET_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "bad sizes");
     EFFDET_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
@@ -317,22 +345,23 @@ extern "C" int effdet_dwconv(const void *x, const float *kernel, const float *sc
     EFFDET_REQUIRE(stride == 1 || stride == 2, "stride 1 or 2");
     EFFDET_REQUIRE(al16(x) && al16(y) && al16(kernel) && al16(scale) && al16(shift), "16B alignment");
     if (dtype == EFFDET_F32)
-        return launch_dw<float, 4>(x, kernel, scale, shift, y, se_sum, B, H, W, C, k, stride, act,
-                                   as_stream(stream));
+        return launch_dw<float, 4>(x, kernel, scale, shift, y, se_sum, se_blocks, B, H, W, C, k,
+                                   stride, act, as_stream(stream));
     if (dtype == EFFDET_BF16)
-        return launch_dw<__nv_bfloat16, 8>(x, kernel, scale, shift, y, se_sum, B, H, W, C, k, stride,
-                                           act, as_stream(stream));
+        return launch_dw<__nv_bfloat16, 8>(x, kernel, scale, shift, y, se_sum, se_blocks, B, H, W, C,
+                                           k, stride, act, as_stream(stream));
     return fail(EFFDET_E_INVALID, "effdet_dwconv: bad dtype%s", "");
 }
 
-extern "C" int effdet_se_gate(const float *se_sum, float inv_hw, const float *w1, const float *b1,
-                              const float *w2, const float *b2, float *gate, int B, int C, int R,
-                              void *stream) {
+extern "C" int effdet_se_gate(const float *se_sum, int se_blocks, float inv_hw, const float *w1,
+                              const float *b1, const float *w2, const float *b2, float *gate,
+                              int B, int C, int R, void *stream) {
     EFFDET_REQUIRE(se_sum && w1 && b1 && w2 && b2 && gate, "null pointer");
-    EFFDET_REQUIRE(B > 0 && C > 0 && R > 0, "bad sizes");
+    EFFDET_REQUIRE(B > 0 && C > 0 && R > 0 && se_blocks > 0, "bad sizes");
     const size_t sm = (size_t)(C + R) * sizeof(float);
     EFFDET_REQUIRE(sm <= 48 * 1024, "C + R too large");
-    se_gate_kernel<<<B, 256, sm, as_stream(stream)>>>(se_sum, inv_hw, w1, b1, w2, b2, gate, C, R);
+    se_gate_kernel<<<B, 256, sm, as_stream(stream)>>>(se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate,
+                                                      C, R);
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }

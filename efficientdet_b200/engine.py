@@ -51,9 +51,10 @@ class Op:
     """One kernel launch.  `make` is called after buffers are assigned and returns a
     zero-argument callable taking only the stream pointer."""
 
-    def __init__(self, kind, inputs, outputs, make, name=""):
+    def __init__(self, kind, inputs, outputs, make, name="", nbytes=0, flops=0):
         self.kind, self.inputs, self.outputs, self.make, self.name = kind, inputs, outputs, make, name
         self.fn = None
+        self.nbytes, self.flops = nbytes, flops     # algorithmic HBM bytes / FLOPs of the launch
 
 
 def _call(name, *args):
@@ -90,8 +91,10 @@ class Plan:
         self.vals.append(v)
         return v
 
-    def add(self, kind, inputs, outputs, make, name=""):
-        self.ops.append(Op(kind, [i for i in inputs if i is not None], outputs, make, name))
+    def add(self, kind, inputs, outputs, make, name="", flops=0, extra_bytes=0):
+        ins = [i for i in inputs if i is not None]
+        nbytes = sum(v.nbytes for v in ins) + sum(v.nbytes for v in outputs) + extra_bytes
+        self.ops.append(Op(kind, ins, outputs, make, name, nbytes, flops))
 
     def w(self, key):
         return self.net.weights[key]
@@ -132,18 +135,22 @@ class Plan:
             self._keepalive.append(d)
             return _call("effdet_conv2d", ctypes.byref(d))
         ins = list(xs) + [r for r in residuals if r is not None] + ([gate] if gate is not None else [])
-        self.add("conv", ins, list(ys), make, name)
+        out_es = 2 if out_dt == BF16 else 4
+        flops = nbytes = 0
+        for xv in xs:
+            ho, wo = -(-xv.shape[1] // stride), -(-xv.shape[2] // stride)
+            flops += 2 * self.B * ho * wo * cout * k * k * cin
+            nbytes += self.B * ho * wo * cout * out_es
+        nbytes += sum(v.nbytes for v in ins) + k * k * cin * cout * 4
+        kind = "conv%dx%d" % (k, k) + ("_head" if n > 1 else "")
+        self.ops.append(Op(kind, ins, list(dict.fromkeys(ys)), make, name, nbytes, flops))
 
     # -------------------------------------------------------------- network lowering
     def _build(self):
         net, B, S = self.net, self.B, self.net.image_size
         bb = net.backbone
         self.images = self.val((B, S, S, 3), F32, "images", keep=True)
-        # one zero-initialised region for all squeeze-excite partial sums
-        se_total = sum(b.mid_filters for b in bb.blocks) * B
-        self.se_sums = self.val((se_total,), F32, "se_sums", keep=True)
-        self.add("memset", [], [self.se_sums],
-                 lambda: _call("effdet_zero", self.se_sums.ptr, self.se_sums.nbytes), "se_zero")
+        lib = _lib.load()
         H = (S + 1) // 2
         c0 = bb.stem_filters
         x = self.val((B, H, H, c0), name="stem")
@@ -152,7 +159,7 @@ class Plan:
                  lambda x=x: _call("effdet_stem_conv", self.images.ptr, self.w("stem_conv/kernel").data_ptr(),
                                    sc.data_ptr(), sh.data_ptr(), x.ptr, B, S, S, c0, self.dtype),
                  "stem_conv")
-        feats, se_off = [], 0
+        feats = []
         for bi, blk in enumerate(bb.blocks):
             p = blk.prefix
             inp, cin, cmid, cout = x, blk.input_filters, blk.mid_filters, blk.output_filters
@@ -165,20 +172,21 @@ class Plan:
             Ho = (H + blk.stride - 1) // blk.stride
             d = self.val((B, Ho, Ho, cmid), name=p + "dw")
             s2, b2 = self.folded(p + "bn")
-            se_ptr_off = se_off * 4
-            self.add("dwconv", [x], [d],
-                     lambda x=x, d=d, p=p, s2=s2, b2=b2, H=H, cmid=cmid, blk=blk, o=se_ptr_off:
+            nblk = lib.effdet_dwconv_se_blocks(B, H, H, cmid, blk.stride, self.dtype)
+            part = self.val((B, nblk, cmid), F32, name=p + "se_partial")
+            self.add("dwconv", [x], [d, part],
+                     lambda x=x, d=d, p=p, s2=s2, b2=b2, H=H, cmid=cmid, blk=blk, part=part, nblk=nblk:
                      _call("effdet_dwconv", x.ptr, self.w(p + "dwconv/depthwise_kernel").data_ptr(),
-                           s2.data_ptr(), b2.data_ptr(), d.ptr, self.se_sums.ptr + o, B, H, H, cmid,
-                           blk.kernel_size, blk.stride, ACT_SWISH, self.dtype), p + "dwconv")
+                           s2.data_ptr(), b2.data_ptr(), d.ptr, part.ptr, nblk, B, H, H, cmid,
+                           blk.kernel_size, blk.stride, ACT_SWISH, self.dtype), p + "dwconv",
+                     flops=2 * blk.kernel_size ** 2 * B * Ho * Ho * cmid)
             gate = self.val((B, cmid), F32, name=p + "gate")
-            self.add("se", [d], [gate],
-                     lambda p=p, gate=gate, Ho=Ho, cmid=cmid, blk=blk, o=se_ptr_off:
-                     _call("effdet_se_gate", self.se_sums.ptr + o, 1.0 / float(Ho * Ho),
+            self.add("se", [part], [gate],
+                     lambda p=p, gate=gate, Ho=Ho, cmid=cmid, blk=blk, part=part, nblk=nblk:
+                     _call("effdet_se_gate", part.ptr, nblk, 1.0 / float(Ho * Ho),
                            self.w(p + "se_reduce/kernel").data_ptr(), self.w(p + "se_reduce/bias").data_ptr(),
                            self.w(p + "se_expand/kernel").data_ptr(), self.w(p + "se_expand/bias").data_ptr(),
                            gate.ptr, B, cmid, blk.se_filters), p + "se")
-            se_off += B * cmid
             y = self.val((B, Ho, Ho, cout), name=p + "out")
             s3, b3 = self.folded(p + "project_bn")
             keep = net.drop_scale.get(p) if blk.has_skip else None
@@ -221,7 +229,7 @@ class Plan:
                                fw.data_ptr() if fw is not None else None, 1e-4,
                                self.w(dw_name + "_dconv/depthwise_kernel").data_ptr(),
                                sc.data_ptr(), sh.data_ptr(), out.ptr, B, H, H, C, self.dtype),
-                 dw_name)
+                 dw_name, flops=(2 * 9 + 6) * B * H * H * C)
         return out
 
     def _bifpn_layer(self, feats, i, Wd):
@@ -339,6 +347,28 @@ class Plan:
             self.run()
         else:
             self.graph.replay()
+
+    def profile(self, iters=5):
+        """Per-launch device times (CUDA events on the launching stream, eager -- not the graph).
+        -> list of dicts {name, kind, ms, bytes, flops}."""
+        stream = torch.cuda.current_stream(self.dev)
+        sp = stream.cuda_stream
+        for op in self.ops:
+            op.fn(sp)
+        acc = [0.0] * len(self.ops)
+        for _ in range(iters):
+            evs = []
+            for op in self.ops:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                op.fn(sp)
+                b.record(stream)
+                evs.append((a, b))
+            torch.cuda.synchronize(self.dev)
+            for i, (a, b) in enumerate(evs):
+                acc[i] += a.elapsed_time(b)
+        return [dict(name=op.name, kind=op.kind, ms=acc[i] / iters, bytes=op.nbytes, flops=op.flops)
+                for i, op in enumerate(self.ops)]
 
     def forward(self, images):
         """images: (B,S,S,3) float32 CUDA tensor -> (regression, classification) views."""

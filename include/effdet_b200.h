@@ -155,19 +155,23 @@ typedef struct effdet_conv_desc {
 } effdet_conv_desc;
 int effdet_conv2d(const effdet_conv_desc *desc, void *stream);
 
-/* Depthwise kxk (k = 3 or 5, stride 1 or 2, SAME) + BN + activation; optionally accumulates
- * the per-(image,channel) spatial SUM of the activated output into se_sum (B,C) f32 (must be
- * zeroed by the caller) for squeeze-excite.  efficientnet.py:242-252 (+ :259-260 squeeze).
+/* Depthwise kxk (k = 3 or 5, stride 1 or 2, SAME) + BN + activation; optionally writes
+ * per-(image, block, channel) partial spatial SUMS of the activated output into se_sum
+ * (B, se_blocks, C) f32 for squeeze-excite (deterministic: no atomics; every cell is written).
+ * se_blocks must be effdet_dwconv_se_blocks(...) for the same arguments (ignored when se_sum
+ * is NULL).  efficientnet.py:242-252 (+ :259-260 squeeze).
  * kernel (k,k,C) f32 = Keras depthwise_kernel (k,k,C,1).  C % 8 == 0. */
+int effdet_dwconv_se_blocks(int B, int H, int W, int C, int stride, int dtype);
 int effdet_dwconv(const void *x, const float *kernel, const float *scale, const float *shift,
-                  void *y, float *se_sum, int B, int H, int W, int C, int k, int stride, int act,
-                  int dtype, void *stream);
+                  void *y, float *se_sum, int se_blocks, int B, int H, int W, int C, int k,
+                  int stride, int act, int dtype, void *stream);
 
-/* Squeeze-excite FCs (efficientnet.py:255-286): mean = se_sum/(HW); r = swish(W1^T mean + b1);
- * gate = sigmoid(W2^T r + b2).  w1 (C,R), w2 (R,C) f32 (Keras 1x1 conv kernels). gate (B,C) f32. */
-int effdet_se_gate(const float *se_sum, float inv_hw, const float *w1, const float *b1,
-                   const float *w2, const float *b2, float *gate, int B, int C, int R,
-                   void *stream);
+/* Squeeze-excite FCs (efficientnet.py:255-286): mean = sum_blocks(se_sum)/(HW);
+ * r = swish(W1^T mean + b1); gate = sigmoid(W2^T r + b2).  se_sum (B,se_blocks,C);
+ * w1 (C,R), w2 (R,C) f32 (Keras 1x1 conv kernels). gate (B,C) f32. */
+int effdet_se_gate(const float *se_sum, int se_blocks, float inv_hw, const float *w1,
+                   const float *b1, const float *w2, const float *b2, float *gate, int B, int C,
+                   int R, void *stream);
 
 /* layers.py:11-39 wBiFPNAdd: out = sum_i relu(w_i) x_i / (sum_i relu(w_i) + eps); w == NULL
  * gives keras.layers.Add (plain sum).  n_inputs 2 or 3, `count` elements of dtype. */
