@@ -47,7 +47,6 @@ _SIGNATURES = {
     "effdet_stem_conv": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                          c_int, c_int, c_void_p],
     "effdet_conv2d": [c_void_p, c_void_p],
-    "effdet_dwconv_se_blocks": [c_int, c_int, c_int, c_int, c_int, c_int],
     "effdet_dwconv": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                       c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "effdet_se_gate": [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -56,6 +55,35 @@ _SIGNATURES = {
     "effdet_bifpn_node": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
                           c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                           c_void_p],
+    "effdet_detection_losses": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                c_size_t, c_int, c_float, c_float, c_float, c_float, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    "effdet_resample_fuse": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                             c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "effdet_bn_train_stats": [c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_float, c_float,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_int, c_int, c_void_p],
+    "effdet_scale_shift_act": [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int,
+                               c_int, c_void_p],
+    "effdet_bn_relu_backward": [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_int, c_int, c_void_p],
+    "effdet_colsum": [c_void_p, c_size_t, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
+                      c_void_p],
+    "effdet_dw_wgrad": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                        c_int, c_void_p],
+    "effdet_fuse_backward_input": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_float,
+                                   c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "effdet_fuse_backward_weights": [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                     c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int,
+                                     c_int, c_int, c_void_p],
+    "effdet_conv_wgrad": [c_void_p, c_void_p],
+    "effdet_conv_dgrad_strided": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_int, c_void_p],
+    "effdet_conv_weight_transpose": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "effdet_flip_taps": [c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "effdet_sgd_momentum_step": [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float,
+                                 c_void_p],
     "effdet_filter_detections": [c_void_p, c_void_p, c_int, c_size_t, c_int, c_float, c_float,
                                  c_int, c_int, c_int, c_void_p, c_size_t, c_size_t, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
@@ -73,12 +101,28 @@ class ConvDesc(ctypes.Structure):
         ("residual", c_void_p * MAX_GROUPS),
         ("H", c_int * MAX_GROUPS), ("W", c_int * MAX_GROUPS), ("ldc", c_int * MAX_GROUPS),
         ("y_batch_stride", ctypes.c_longlong * MAX_GROUPS),
+        ("ldx", c_int * MAX_GROUPS), ("x_batch_stride", ctypes.c_longlong * MAX_GROUPS),
+        ("relu_mask", c_void_p * MAX_GROUPS),
         ("B", c_int), ("Cin", c_int), ("Cout", c_int), ("kh", c_int), ("kw", c_int),
         ("stride", c_int),
         ("weight", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("gate", c_void_p),
         ("keep", c_void_p),
         ("act", c_int), ("in_dtype", c_int), ("out_dtype", c_int),
         ("weight_bf16", c_void_p), ("allow_tensor_core", c_int),
+    ]
+
+
+class WgradDesc(ctypes.Structure):
+    """Mirror of `effdet_wgrad_desc` (include/effdet_b200.h)."""
+    _fields_ = [
+        ("n_groups", c_int),
+        ("x", c_void_p * MAX_GROUPS), ("dz", c_void_p * MAX_GROUPS),
+        ("H", c_int * MAX_GROUPS), ("W", c_int * MAX_GROUPS), ("dz_ld", c_int * MAX_GROUPS),
+        ("dz_batch_stride", ctypes.c_longlong * MAX_GROUPS),
+        ("B", c_int), ("Cin", c_int), ("Cout", c_int), ("kh", c_int), ("kw", c_int),
+        ("stride", c_int),
+        ("dweight", c_void_p), ("partial", c_void_p), ("n_splits", c_int), ("accumulate", c_int),
+        ("x_dtype", c_int), ("dz_dtype", c_int),
     ]
 
 
@@ -97,6 +141,16 @@ def load():
     lib.effdet_launch_count.restype = ctypes.c_longlong
     lib.effdet_filter_detections_workspace_size.restype = c_size_t
     lib.effdet_filter_detections_workspace_size.argtypes = [c_int, c_size_t, c_int, c_size_t, c_int]
+    lib.effdet_detection_losses_workspace_size.restype = c_size_t
+    lib.effdet_detection_losses_workspace_size.argtypes = []
+    lib.effdet_colreduce_blocks.restype = c_int
+    lib.effdet_colreduce_blocks.argtypes = [c_size_t, c_int, c_int]
+    lib.effdet_dw_wgrad_blocks.restype = c_int
+    lib.effdet_dw_wgrad_blocks.argtypes = [c_int, c_int, c_int, c_int, c_int]
+    lib.effdet_conv_wgrad_splits.restype = c_int
+    lib.effdet_conv_wgrad_splits.argtypes = [c_void_p]
+    lib.effdet_dwconv_se_blocks.restype = c_int
+    lib.effdet_dwconv_se_blocks.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args

@@ -72,7 +72,10 @@ struct ConvGroup {
     const void *x;        // (B,H,W,Cin)
     void *y;              // output base
     const void *res;      // optional residual, same indexing as y
+    const void *mask;     // optional ReLU mask (zero the output where mask <= 0), indexed like y
     int H, W, Ho, Wo;
+    long long x_batch_stride;   // elements between images in x
+    int ldx;              // elements between consecutive input pixels in x
     int tile_begin;       // first M tile of this group
     long long y_batch_stride;   // elements between images in y
     int ldc;              // elements between consecutive output pixels in y
@@ -139,7 +142,7 @@ conv_igemm_kernel(const ConvParams p) {
     const bool a_ok = am < M;
     int ab = 0, aoy = 0, aox = 0;
     if (a_ok) { ab = am / HoWo; int r = am - ab * HoWo; aoy = r / G.Wo; aox = r - aoy * G.Wo; }
-    const bool a_vec = (Cin & 3) == 0;
+    const bool a_vec = (Cin & 3) == 0 && (G.ldx & 3) == 0 && (G.x_batch_stride & 3) == 0;
     // B-load role: one k row, 4 consecutive n
     const int b_k = tid >> 4, b_n = (tid & 15) * 4;
     const bool b_vec = (Cout & 3) == 0;
@@ -158,7 +161,8 @@ conv_igemm_kernel(const ConvParams p) {
         const int ky = tap / p.kw, kx = tap - ky * p.kw;
         const int iy = aoy * p.stride - pad_t + ky, ix = aox * p.stride - pad_l + kx;
         const bool pix_ok = a_ok && iy >= 0 && iy < G.H && ix >= 0 && ix < G.W;
-        const TI *src = X + (((size_t)ab * G.H + (pix_ok ? iy : 0)) * G.W + (pix_ok ? ix : 0)) * Cin;
+        const TI *src = X + (size_t)ab * G.x_batch_stride +
+                        ((size_t)(pix_ok ? iy : 0) * G.W + (pix_ok ? ix : 0)) * G.ldx;
         const float *gsrc = p.gate ? p.gate + (size_t)ab * Cin : nullptr;
         for (int c0 = 0; c0 < Cin; c0 += BK) {
             float av[4] = {0.f, 0.f, 0.f, 0.f};
@@ -195,6 +199,7 @@ conv_igemm_kernel(const ConvParams p) {
     // epilogue
     TO *Y = static_cast<TO *>(G.y);
     const TO *R = static_cast<const TO *>(G.res);
+    const TO *MK = static_cast<const TO *>(G.mask);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int m = m0 + ty * 4 + i;
@@ -210,6 +215,7 @@ conv_igemm_kernel(const ConvParams p) {
             if (p.scale) v *= p.scale[n];
             if (p.shift) v += p.shift[n];
             v = activate_rt(v, p.act);
+            if (MK && !(to_f<TO>(MK[base + n]) > 0.f)) v = 0.f;
             if (R) v = v * kp + to_f<TO>(R[base + n]);
             Y[base + n] = from_f<TO>(v);
         }
@@ -284,7 +290,10 @@ extern "C" int effdet_conv2d(const effdet_conv_desc *d, void *stream) {
     for (int i = 0; i < d->n_groups; ++i) {
         ConvGroup &g = p.g[i];
         EFFDET_REQUIRE(d->x[i] && d->y[i] && d->H[i] > 0 && d->W[i] > 0, "bad group");
-        g.x = d->x[i]; g.y = d->y[i]; g.res = d->residual[i];
+        g.x = d->x[i]; g.y = d->y[i]; g.res = d->residual[i]; g.mask = d->relu_mask[i];
+        g.ldx = d->ldx[i] ? d->ldx[i] : d->Cin;
+        g.x_batch_stride = d->x_batch_stride[i] ? d->x_batch_stride[i]
+                                                : (long long)d->H[i] * d->W[i] * g.ldx;
         g.H = d->H[i]; g.W = d->W[i];
         g.Ho = (d->H[i] + d->stride - 1) / d->stride;
         g.Wo = (d->W[i] + d->stride - 1) / d->stride;
@@ -305,6 +314,8 @@ extern "C" int effdet_conv2d(const effdet_conv_desc *d, void *stream) {
         conv_igemm_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(p);
     else if (d->in_dtype == EFFDET_BF16 && d->out_dtype == EFFDET_F32)
         conv_igemm_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(p);
+    else if (d->in_dtype == EFFDET_F32 && d->out_dtype == EFFDET_BF16)
+        conv_igemm_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(p);
     else
         return fail(EFFDET_E_UNSUPPORTED, "effdet_conv2d: unsupported dtype combination%s", "");
     EFFDET_LAUNCHED();

@@ -1,0 +1,764 @@
+// Training-mode kernels of the BiFPN / heads (HBM-bound NHWC passes, fp32 math, fp32 or bf16
+// storage).  Everything the Keras/TF autodiff + fused-BN + SGD ops did for the reference's
+// model.fit (train_tpu.py:330-346), restated as explicit kernels:
+//   resample_fuse_kernel    model.py:154-194/226-266 + layers.py:26-31  (forward, keeps f)
+//   colreduce_kernel<MODE>  BN batch statistics / BN backward sums / bias gradients
+//   bn_train_finalize       batch mean/var -> scale/shift, moving-average update (momentum .997)
+//   scale_shift_act_kernel  y = act(z*scale + shift)
+//   bn_bwd_finalize/apply   dz = k1*dy_masked + k2*z + k3 ; dgamma, dbeta
+//   dw_wgrad_kernel         depthwise-kernel gradient
+//   fuse_bwd_kernel         gradient routing through nearest-upsample (sum-pool) /
+//                           2x2 max-pool (first-argmax) / same-resolution inputs
+//   fuse_wgrad_kernel       fusion-weight gradients (layers.py:26-31)
+//   sgd_momentum_kernel     train_tpu.py:268-269 keras SGD(lr, decay, momentum)
+// All reductions use per-block partials summed in a fixed order: training is deterministic.
+#include "common.cuh"
+
+namespace effdet {
+
+template <typename T, int CV> struct VecT;
+template <> struct VecT<float, 4> {
+    static __device__ __forceinline__ void load(const float *p, float *v) {
+        float4 t = *reinterpret_cast<const float4 *>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float *p, const float *v) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct VecT<__nv_bfloat16, 8> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float *v) {
+        uint4 t = *reinterpret_cast<const uint4 *>(p);
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float *v) {
+        uint4 t;
+        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4 *>(p) = t;
+    }
+};
+template <int CV> __device__ __forceinline__ void ldf(const float *p, float *v) {
+#pragma unroll
+    for (int i = 0; i < CV; i += 4) {
+        float4 t = *reinterpret_cast<const float4 *>(p + i);
+        v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    }
+}
+
+struct FuseCoef { float c[3]; float inv; };
+__device__ __forceinline__ FuseCoef fuse_coef(const float *fw, int n, float eps) {
+    FuseCoef f;
+    if (!fw) { f.c[0] = f.c[1] = f.c[2] = 1.f; f.inv = 1.f; return f; }
+    float r0 = fmaxf(fw[0], 0.f), r1 = fmaxf(fw[1], 0.f), r2 = n > 2 ? fmaxf(fw[2], 0.f) : 0.f;
+    f.c[0] = r0; f.c[1] = r1; f.c[2] = r2; f.inv = r0 + r1 + r2 + eps;
+    return f;
+}
+
+// load the (resampled) value of input 0 at output pixel (y,x)
+template <typename T, int CV>
+__device__ __forceinline__ void load_resampled(const T *p0, int mode0, int y, int x, int W0, int C,
+                                               int c, float *a) {
+    if (mode0 == 1) {
+        VecT<T, CV>::load(p0 + ((size_t)(y >> 1) * W0 + (x >> 1)) * C + c, a);
+    } else if (mode0 == 2) {
+        const T *q = p0 + ((size_t)(2 * y) * W0 + 2 * x) * C + c;
+        float t[CV];
+        VecT<T, CV>::load(q, a);
+        VecT<T, CV>::load(q + C, t);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) a[k] = fmaxf(a[k], t[k]);
+        VecT<T, CV>::load(q + (size_t)W0 * C, t);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) a[k] = fmaxf(a[k], t[k]);
+        VecT<T, CV>::load(q + (size_t)W0 * C + C, t);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) a[k] = fmaxf(a[k], t[k]);
+    } else {
+        VecT<T, CV>::load(p0 + ((size_t)y * W0 + x) * C + c, a);
+    }
+}
+
+// ------------------------------------------------------------------ fusion forward (keeps f)
+template <typename T, int CV>
+__global__ void __launch_bounds__(256)
+resample_fuse_kernel(const T *__restrict__ in0, int mode0, const T *__restrict__ in1,
+                     const T *__restrict__ in2, const float *__restrict__ fw, float eps,
+                     T *__restrict__ out, int B, int H, int W, int C) {
+    const int nvec = C / CV;
+    const size_t total = (size_t)B * H * W * nvec;
+    const FuseCoef fc = fuse_coef(fw, in2 ? 3 : 2, eps);
+    const int H0 = mode0 == 1 ? H / 2 : (mode0 == 2 ? H * 2 : H);
+    const int W0 = mode0 == 1 ? W / 2 : (mode0 == 2 ? W * 2 : W);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int cv = (int)(i % nvec);
+        size_t pix = i / nvec;
+        const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((size_t)W * H));
+        const int c = cv * CV;
+        float a[CV], bb[CV], o[CV];
+        load_resampled<T, CV>(in0 + (size_t)b * H0 * W0 * C, mode0, y, x, W0, C, c, a);
+        VecT<T, CV>::load(in1 + pix * C + c, bb);
+        if (fw) {
+#pragma unroll
+            for (int k = 0; k < CV; ++k) o[k] = fc.c[0] * a[k] + fc.c[1] * bb[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < CV; ++k) o[k] = a[k] + bb[k];
+        }
+        if (in2) {
+            float cc[CV];
+            VecT<T, CV>::load(in2 + pix * C + c, cc);
+#pragma unroll
+            for (int k = 0; k < CV; ++k) o[k] += fw ? fc.c[2] * cc[k] : cc[k];
+        }
+        if (fw) {
+#pragma unroll
+            for (int k = 0; k < CV; ++k) o[k] = o[k] / fc.inv;
+        }
+        VecT<T, CV>::store(out + pix * C + c, o);
+    }
+}
+
+// ------------------------------------------------------------------ column reductions
+// x is (rows, C).  block = nvec x PY threads; blocks split the rows; partial[(blk)*2*C + s*C + c]
+enum { RED_STATS = 0, RED_BNBWD = 1, RED_SUM = 2 };
+template <typename T, int CV, int MODE>
+__global__ void colreduce_kernel(const T *__restrict__ x, const T *__restrict__ y,
+                                 const T *__restrict__ dy, const float *__restrict__ mean,
+                                 const float *__restrict__ invstd, size_t rows, int C,
+                                 int rows_per_block, float *__restrict__ partial) {
+    extern __shared__ float sred[];      // PY * 2 * C
+    const int nvec = C / CV, PY = blockDim.x / nvec;
+    const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec, c = cv * CV;
+    const size_t r0 = (size_t)blockIdx.x * rows_per_block;
+    const size_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float s1[CV], s2[CV], mu[CV], is[CV];
+#pragma unroll
+    for (int k = 0; k < CV; ++k) { s1[k] = 0.f; s2[k] = 0.f; mu[k] = 0.f; is[k] = 1.f; }
+    if (MODE == RED_BNBWD) { ldf<CV>(mean + c, mu); ldf<CV>(invstd + c, is); }
+    for (size_t r = r0 + py; r < r1; r += PY) {
+        float v[CV];
+        if (MODE == RED_STATS) {
+            VecT<T, CV>::load(x + r * C + c, v);
+#pragma unroll
+            for (int k = 0; k < CV; ++k) { s1[k] += v[k]; s2[k] = fmaf(v[k], v[k], s2[k]); }
+        } else if (MODE == RED_BNBWD) {
+            float g[CV], yy[CV];
+            VecT<T, CV>::load(x + r * C + c, v);
+            VecT<T, CV>::load(dy + r * C + c, g);
+            VecT<T, CV>::load(y + r * C + c, yy);
+#pragma unroll
+            for (int k = 0; k < CV; ++k) {
+                const float gm = yy[k] > 0.f ? g[k] : 0.f;
+                s1[k] += gm;
+                s2[k] = fmaf(gm, (v[k] - mu[k]) * is[k], s2[k]);
+            }
+        } else {
+            VecT<T, CV>::load(x + r * C + c, v);
+#pragma unroll
+            for (int k = 0; k < CV; ++k) s1[k] += v[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CV; ++k) {
+        sred[((size_t)py * 2 + 0) * C + c + k] = s1[k];
+        sred[((size_t)py * 2 + 1) * C + c + k] = s2[k];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float t = 0.f;
+        for (int r = 0; r < PY; ++r) t += sred[(size_t)r * 2 * C + i];
+        partial[(size_t)blockIdx.x * 2 * C + i] = t;
+    }
+}
+
+// BN training: batch statistics -> scale/shift (+ saved mean/invstd, moving averages)
+__global__ void bn_train_finalize_kernel(const float *__restrict__ partial, int nblk, double count,
+                                         const float *__restrict__ gamma,
+                                         const float *__restrict__ beta, float eps, float momentum,
+                                         float *__restrict__ moving_mean,
+                                         float *__restrict__ moving_var, float *__restrict__ scale,
+                                         float *__restrict__ shift, float *__restrict__ save_mean,
+                                         float *__restrict__ save_invstd, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+        s1 += (double)partial[(size_t)b * 2 * C + c];
+        s2 += (double)partial[(size_t)b * 2 * C + C + c];
+    }
+    const double m = s1 / count;
+    double var = s2 / count - m * m;
+    if (var < 0.0) var = 0.0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * is;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)m * sc;
+    save_mean[c] = (float)m;
+    save_invstd[c] = is;
+    if (moving_mean) {
+        const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+        moving_mean[c] = moving_mean[c] * momentum + (float)m * (1.f - momentum);
+        moving_var[c] = moving_var[c] * momentum + (float)unb * (1.f - momentum);
+    }
+}
+
+// sums `nblk` partial rows (layout [blk][2][C], first half) into out (bias / generic gradients)
+// C = fold * Cout: the matrix was viewed as (rows/fold, fold*Cout) to get vectorisable rows
+__global__ void colsum_finalize_kernel(const float *__restrict__ partial, int nblk, int C, int fold,
+                                       float *__restrict__ out, int accumulate) {
+    const int Cout = C / fold;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cout) return;
+    float t = 0.f;
+    for (int b = 0; b < nblk; ++b)
+        for (int j = 0; j < fold; ++j) t += partial[(size_t)b * 2 * C + j * Cout + c];
+    out[c] = accumulate ? out[c] + t : t;
+}
+
+// BN backward coefficients: dz = k1*dy_masked + k2*z + k3 ; dgamma, dbeta
+__global__ void bn_bwd_finalize_kernel(const float *__restrict__ partial, int nblk, double count,
+                                       const float *__restrict__ gamma,
+                                       const float *__restrict__ mean,
+                                       const float *__restrict__ invstd, float *__restrict__ k123,
+                                       float *__restrict__ dgamma, float *__restrict__ dbeta, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+        s1 += (double)partial[(size_t)b * 2 * C + c];
+        s2 += (double)partial[(size_t)b * 2 * C + C + c];
+    }
+    const float g = gamma[c], is = invstd[c], mu = mean[c];
+    const float m1 = (float)(s1 / count), m2 = (float)(s2 / count);
+    k123[c] = g * is;
+    k123[C + c] = -g * is * is * m2;
+    k123[2 * C + c] = -g * is * (m1 - mu * is * m2);
+    if (dgamma) dgamma[c] = (float)s2;
+    if (dbeta) dbeta[c] = (float)s1;
+}
+
+template <typename T, int CV>
+__global__ void __launch_bounds__(256)
+scale_shift_act_kernel(const T *__restrict__ z, const float *__restrict__ scale,
+                       const float *__restrict__ shift, T *__restrict__ y, size_t nvec_total,
+                       int C, int act) {
+    const int nvec = C / CV;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
+        const int c = (int)(i % nvec) * CV;
+        float v[CV], sc[CV], sh[CV];
+        VecT<T, CV>::load(z + i * CV, v);
+        ldf<CV>(scale + c, sc);
+        ldf<CV>(shift + c, sh);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) v[k] = activate_rt(v[k] * sc[k] + sh[k], act);
+        VecT<T, CV>::store(y + i * CV, v);
+    }
+}
+
+// dz = k1*(dy * [y>0]) + k2*z + k3     (frozen BN: k2 = k3 = 0, k1 = scale)
+template <typename T, int CV>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ y, const T *__restrict__ z,
+                    const float *__restrict__ k123, T *__restrict__ dz, size_t nvec_total, int C) {
+    const int nvec = C / CV;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
+        const int c = (int)(i % nvec) * CV;
+        float g[CV], yy[CV], zz[CV], k1[CV], k2[CV], k3[CV];
+        VecT<T, CV>::load(dy + i * CV, g);
+        VecT<T, CV>::load(y + i * CV, yy);
+        VecT<T, CV>::load(z + i * CV, zz);
+        ldf<CV>(k123 + c, k1);
+        ldf<CV>(k123 + C + c, k2);
+        ldf<CV>(k123 + 2 * C + c, k3);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) g[k] = k1[k] * (yy[k] > 0.f ? g[k] : 0.f) + k2[k] * zz[k] + k3[k];
+        VecT<T, CV>::store(dz + i * CV, g);
+    }
+}
+
+// ------------------------------------------------------------------ depthwise weight gradient
+// dW[tap][c] = sum_{b,y,x} f[b, y+ky-1, x+kx-1, c] * dz[b,y,x,c]   (3x3, stride 1, SAME)
+template <typename T, int CV>
+__global__ void dw_wgrad_kernel(const T *__restrict__ f, const T *__restrict__ dz, int B, int H, int W,
+                                int C, int pix_per_block, float *__restrict__ partial) {
+    extern __shared__ float sred[];      // PY * 9 * C
+    const int nvec = C / CV, PY = blockDim.x / nvec;
+    const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec, c = cv * CV;
+    const size_t total = (size_t)B * H * W;
+    const size_t p0 = (size_t)blockIdx.x * pix_per_block;
+    const size_t p1 = p0 + pix_per_block < total ? p0 + pix_per_block : total;
+    float acc[9][CV];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int k = 0; k < CV; ++k) acc[t][k] = 0.f;
+    for (size_t p = p0 + py; p < p1; p += PY) {
+        const int x = (int)(p % W), y = (int)((p / W) % H);
+        const size_t bbase = (p / ((size_t)W * H)) * (size_t)H * W;
+        float g[CV];
+        VecT<T, CV>::load(dz + p * C + c, g);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = y + ky - 1;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = x + kx - 1;
+                if (ix < 0 || ix >= W) continue;
+                float v[CV];
+                VecT<T, CV>::load(f + (bbase + (size_t)iy * W + ix) * C + c, v);
+#pragma unroll
+                for (int k = 0; k < CV; ++k) acc[ky * 3 + kx][k] = fmaf(v[k], g[k], acc[ky * 3 + kx][k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int k = 0; k < CV; ++k) sred[((size_t)py * 9 + t) * C + c + k] = acc[t][k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+        float t = 0.f;
+        for (int r = 0; r < PY; ++r) t += sred[(size_t)r * 9 * C + i];
+        partial[(size_t)blockIdx.x * 9 * C + i] = t;
+    }
+}
+__global__ void sum_partials_kernel(const float *__restrict__ partial, int nblk, int n,
+                                    float *__restrict__ out, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float t = 0.f;
+    for (int b = 0; b < nblk; ++b) t += partial[(size_t)b * n + i];
+    out[i] = accumulate ? out[i] + t : t;
+}
+
+// ------------------------------------------------------------------ fusion backward
+// which = 0: gradient of the resampled input (mode0 routing); which = 1/2: same-resolution inputs
+template <typename T, int CV>
+__global__ void __launch_bounds__(256)
+fuse_bwd_kernel(const T *__restrict__ df, int which, int mode0, const T *__restrict__ in0,
+                const float *__restrict__ fw, int n_in, float eps, T *__restrict__ dst,
+                int accumulate, int B, int H, int W, int C) {
+    // H, W = resolution of df (the node's resolution)
+    const FuseCoef fc = fuse_coef(fw, n_in, eps);
+    const float coef = fw ? fc.c[which] / fc.inv : 1.f;
+    const int nvec = C / CV;
+    int Hd = H, Wd = W;
+    if (which == 0 && mode0 == 1) { Hd = H / 2; Wd = W / 2; }
+    if (which == 0 && mode0 == 2) { Hd = H * 2; Wd = W * 2; }
+    const size_t total = (size_t)B * Hd * Wd * nvec;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int cv = (int)(i % nvec), c = cv * CV;
+        const size_t pix = i / nvec;
+        const int x = (int)(pix % Wd), y = (int)((pix / Wd) % Hd), b = (int)(pix / ((size_t)Wd * Hd));
+        const T *dfb = df + (size_t)b * H * W * C;
+        float g[CV];
+        if (which != 0 || mode0 == 0) {
+            VecT<T, CV>::load(dfb + ((size_t)y * W + x) * C + c, g);
+        } else if (mode0 == 1) {          // nearest upsample backward = 2x2 sum
+            float t[CV];
+            const T *q = dfb + ((size_t)(2 * y) * W + 2 * x) * C + c;
+            VecT<T, CV>::load(q, g);
+            VecT<T, CV>::load(q + C, t);
+#pragma unroll
+            for (int k = 0; k < CV; ++k) g[k] += t[k];
+            VecT<T, CV>::load(q + (size_t)W * C, t);
+#pragma unroll
+            for (int k = 0; k < CV; ++k) g[k] += t[k];
+            VecT<T, CV>::load(q + (size_t)W * C + C, t);
+#pragma unroll
+            for (int k = 0; k < CV; ++k) g[k] += t[k];
+        } else {                          // max-pool backward: route to the first maximum
+            const int wy = y >> 1, wx = x >> 1;
+            if (wy >= H || wx >= W) {
+#pragma unroll
+                for (int k = 0; k < CV; ++k) g[k] = 0.f;
+            } else {
+                const T *q = in0 + (((size_t)b * Hd + 2 * wy) * Wd + 2 * wx) * C + c;
+                float v[4][CV];
+                VecT<T, CV>::load(q, v[0]);
+                VecT<T, CV>::load(q + C, v[1]);
+                VecT<T, CV>::load(q + (size_t)Wd * C, v[2]);
+                VecT<T, CV>::load(q + (size_t)Wd * C + C, v[3]);
+                float d[CV];
+                VecT<T, CV>::load(dfb + ((size_t)wy * W + wx) * C + c, d);
+                const int me = (y & 1) * 2 + (x & 1);
+#pragma unroll
+                for (int k = 0; k < CV; ++k) {
+                    int arg = 0; float m = v[0][k];
+#pragma unroll
+                    for (int j = 1; j < 4; ++j) if (v[j][k] > m) { m = v[j][k]; arg = j; }
+                    g[k] = arg == me ? d[k] : 0.f;
+                }
+            }
+        }
+        float o[CV];
+        if (accumulate) {
+            VecT<T, CV>::load(dst + pix * C + c, o);
+#pragma unroll
+            for (int k = 0; k < CV; ++k) o[k] += coef * g[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < CV; ++k) o[k] = coef * g[k];
+        }
+        VecT<T, CV>::store(dst + pix * C + c, o);
+    }
+}
+
+// partial[blk][4] = { sum df*in0r, sum df*in1, sum df*in2, sum df*f }
+template <typename T, int CV>
+__global__ void __launch_bounds__(256)
+fuse_wgrad_kernel(const T *__restrict__ df, const T *__restrict__ f, const T *__restrict__ in0,
+                  int mode0, const T *__restrict__ in1, const T *__restrict__ in2, int B, int H,
+                  int W, int C, float *__restrict__ partial) {
+    __shared__ float sh[4][8];
+    const int nvec = C / CV;
+    const size_t total = (size_t)B * H * W * nvec;
+    const int H0 = mode0 == 1 ? H / 2 : (mode0 == 2 ? H * 2 : H);
+    const int W0 = mode0 == 1 ? W / 2 : (mode0 == 2 ? W * 2 : W);
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int cv = (int)(i % nvec), c = cv * CV;
+        const size_t pix = i / nvec;
+        const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((size_t)W * H));
+        float g[CV], a[CV], v[CV];
+        VecT<T, CV>::load(df + pix * C + c, g);
+        load_resampled<T, CV>(in0 + (size_t)b * H0 * W0 * C, mode0, y, x, W0, C, c, a);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) s[0] = fmaf(g[k], a[k], s[0]);
+        VecT<T, CV>::load(in1 + pix * C + c, v);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) s[1] = fmaf(g[k], v[k], s[1]);
+        if (in2) {
+            VecT<T, CV>::load(in2 + pix * C + c, v);
+#pragma unroll
+            for (int k = 0; k < CV; ++k) s[2] = fmaf(g[k], v[k], s[2]);
+        }
+        VecT<T, CV>::load(f + pix * C + c, v);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) s[3] = fmaf(g[k], v[k], s[3]);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float v = s[j];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) sh[j][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += sh[threadIdx.x][i];
+        partial[(size_t)blockIdx.x * 4 + threadIdx.x] = t;
+    }
+}
+__global__ void fuse_wgrad_finalize_kernel(const float *__restrict__ partial, int nblk,
+                                           const float *__restrict__ fw, int n_in, float eps,
+                                           float *__restrict__ dw) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s[4] = {0, 0, 0, 0};
+    for (int b = 0; b < nblk; ++b)
+        for (int j = 0; j < 4; ++j) s[j] += (double)partial[(size_t)b * 4 + j];
+    float D = eps;
+    for (int i = 0; i < n_in; ++i) D += fmaxf(fw[i], 0.f);
+    for (int i = 0; i < n_in; ++i)
+        dw[i] = fw[i] > 0.f ? (float)((s[i] - s[3]) / (double)D) : 0.f;
+}
+
+// ------------------------------------------------------------------ optimiser
+__global__ void __launch_bounds__(256)
+sgd_momentum_kernel(float *__restrict__ w, const float *__restrict__ g, float *__restrict__ v,
+                    size_t n, float lr_t, float momentum, float grad_scale) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const float vel = momentum * v[i] - lr_t * (g[i] * grad_scale);
+        v[i] = vel;
+        w[i] += vel;
+    }
+}
+
+// flips a depthwise kernel (k,k,C) spatially: out[k*k-1-t][c] = in[t][c]
+__global__ void flip_taps_kernel(const float *__restrict__ in, float *__restrict__ out, int taps, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= taps * n) return;
+    const int t = i / n, r = i - t * n;
+    out[(size_t)(taps - 1 - t) * n + r] = in[i];
+}
+// dense conv weight (taps,Cin,Cout) -> (taps flipped, Cout, Cin)   (data-gradient kernel)
+__global__ void conv_weight_transpose_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                             int taps, int Cin, int Cout) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)taps * Cin * Cout) return;
+    const int co = (int)(i % Cout), ci = (int)((i / Cout) % Cin), t = (int)(i / ((size_t)Cout * Cin));
+    out[((size_t)(taps - 1 - t) * Cout + co) * Cin + ci] = in[i];
+}
+
+static bool a16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static unsigned grid_for(size_t n) {
+    unsigned b = cdiv(n, 256);
+    return b > (unsigned)kNumSMs * 8 ? kNumSMs * 8 : (b ? b : 1);
+}
+
+}  // namespace effdet
+
+using namespace effdet;
+
+#define DISPATCH_T(dtype, EXPR_F32, EXPR_BF16)                                        \
+    if ((dtype) == EFFDET_F32) { EXPR_F32; }                                          \
+    else if ((dtype) == EFFDET_BF16) { EXPR_BF16; }                                   \
+    else return fail(EFFDET_E_INVALID, "%s: bad dtype", __func__);
+
+extern "C" int effdet_resample_fuse(const void *in0, int mode0, const void *in1, const void *in2,
+                                    const float *w, float eps, void *out, int B, int H, int W, int C,
+                                    int dtype, void *stream) {
+    EFFDET_REQUIRE(in0 && in1 && out && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad arguments");
+    EFFDET_REQUIRE(mode0 >= 0 && mode0 <= 2 && (mode0 != 1 || (H % 2 == 0 && W % 2 == 0)), "bad mode");
+    EFFDET_REQUIRE(a16(in0) && a16(in1) && (!in2 || a16(in2)) && a16(out), "16B alignment");
+    cudaStream_t st = as_stream(stream);
+    DISPATCH_T(dtype,
+        (resample_fuse_kernel<float, 4><<<grid_for((size_t)B * H * W * C / 4), 256, 0, st>>>(
+            (const float *)in0, mode0, (const float *)in1, (const float *)in2, w, eps, (float *)out, B, H, W, C)),
+        (resample_fuse_kernel<__nv_bfloat16, 8><<<grid_for((size_t)B * H * W * C / 8), 256, 0, st>>>(
+            (const __nv_bfloat16 *)in0, mode0, (const __nv_bfloat16 *)in1, (const __nv_bfloat16 *)in2, w,
+            eps, (__nv_bfloat16 *)out, B, H, W, C)))
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+// number of row blocks the column reductions use for a (rows, C) matrix
+extern "C" int effdet_colreduce_blocks(size_t rows, int C, int dtype) {
+    if (rows == 0 || C <= 0) return 0;
+    const int CV = dtype == EFFDET_BF16 ? 8 : 4;
+    int nvec = C / CV; if (nvec < 1) nvec = 1;
+    int PY = 256 / nvec; if (PY < 1) PY = 1;
+    size_t rpb = (size_t)PY * 16;
+    while (rpb > (size_t)PY && cdiv(rows, rpb) < (unsigned)kNumSMs * 2) rpb >>= 1;
+    return (int)cdiv(rows, rpb);
+}
+
+template <typename T, int CV, int MODE>
+static int launch_colreduce(const void *x, const void *y, const void *dy, const float *mean,
+                            const float *invstd, size_t rows, int C, int nblk, float *partial,
+                            cudaStream_t st) {
+    const int nvec = C / CV;
+    if (nvec > 1024) return fail(EFFDET_E_UNSUPPORTED, "colreduce: %sC=%lld too large", "", C);
+    int PY = 256 / nvec; if (PY < 1) PY = 1;
+    const int rpb = (int)cdiv(rows, nblk);
+    if ((int)cdiv(rows, rpb) != nblk) return fail(EFFDET_E_INVALID, "colreduce: bad block count%s", "");
+    const size_t sm = (size_t)PY * 2 * C * sizeof(float);
+    if (sm > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(colreduce_kernel<T, CV, MODE>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return fail(EFFDET_E_CUDA, "colreduce: smem attribute: %s", cudaGetErrorString(e));
+    }
+    colreduce_kernel<T, CV, MODE><<<nblk, nvec * PY, sm, st>>>(
+        (const T *)x, (const T *)y, (const T *)dy, mean, invstd, rows, C, rpb, partial);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+/* BN (training mode) forward statistics + finalize: z (rows,C) -> scale/shift/saved stats. */
+extern "C" int effdet_bn_train_stats(const void *z, size_t rows, int C, const float *gamma,
+                                     const float *beta, float eps, float momentum,
+                                     float *moving_mean, float *moving_var, float *scale,
+                                     float *shift, float *save_mean, float *save_invstd,
+                                     float *partial, int nblk, int dtype, void *stream) {
+    EFFDET_REQUIRE(z && gamma && beta && scale && shift && save_mean && save_invstd && partial, "null pointer");
+    EFFDET_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && nblk > 0, "bad sizes");
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    DISPATCH_T(dtype,
+        rc = (launch_colreduce<float, 4, RED_STATS>(z, nullptr, nullptr, nullptr, nullptr, rows, C, nblk, partial, st)),
+        rc = (launch_colreduce<__nv_bfloat16, 8, RED_STATS>(z, nullptr, nullptr, nullptr, nullptr, rows, C, nblk, partial, st)))
+    if (rc) return rc;
+    bn_train_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(partial, nblk, (double)rows, gamma, beta, eps,
+                                                           momentum, moving_mean, moving_var, scale,
+                                                           shift, save_mean, save_invstd, C);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+extern "C" int effdet_scale_shift_act(const void *z, const float *scale, const float *shift, void *y,
+                                      size_t rows, int C, int act, int dtype, void *stream) {
+    EFFDET_REQUIRE(z && scale && shift && y && C > 0 && C % 8 == 0, "bad arguments");
+    if (rows == 0) return EFFDET_OK;
+    cudaStream_t st = as_stream(stream);
+    DISPATCH_T(dtype,
+        (scale_shift_act_kernel<float, 4><<<grid_for(rows * C / 4), 256, 0, st>>>(
+            (const float *)z, scale, shift, (float *)y, rows * C / 4, C, act)),
+        (scale_shift_act_kernel<__nv_bfloat16, 8><<<grid_for(rows * C / 8), 256, 0, st>>>(
+            (const __nv_bfloat16 *)z, scale, shift, (__nv_bfloat16 *)y, rows * C / 8, C, act)))
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+/* BN + ReLU backward (training-mode BN): dz from dy, y (ReLU output), z (BN input) and the saved
+ * batch statistics; also dgamma/dbeta.  frozen != 0: BN ran in inference mode (k1 = scale). */
+extern "C" int effdet_bn_relu_backward(const void *dy, const void *y, const void *z, size_t rows, int C,
+                                       const float *gamma, const float *save_mean,
+                                       const float *save_invstd, const float *frozen_scale,
+                                       float *dgamma, float *dbeta, void *dz, float *k123,
+                                       float *partial, int nblk, int dtype, void *stream) {
+    EFFDET_REQUIRE(dy && y && z && dz && k123 && partial && gamma, "null pointer");
+    EFFDET_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && nblk > 0, "bad sizes");
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    if (frozen_scale) {
+        // inference-mode BN: dz = scale * dy_masked ; gamma/beta receive no gradient here
+        EFFDET_CUDA(cudaMemsetAsync(k123, 0, 3 * (size_t)C * sizeof(float), st));
+        EFFDET_CUDA(cudaMemcpyAsync(k123, frozen_scale, (size_t)C * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, st));
+    } else {
+        EFFDET_REQUIRE(save_mean && save_invstd, "null saved statistics");
+        DISPATCH_T(dtype,
+            rc = (launch_colreduce<float, 4, RED_BNBWD>(z, y, dy, save_mean, save_invstd, rows, C, nblk, partial, st)),
+            rc = (launch_colreduce<__nv_bfloat16, 8, RED_BNBWD>(z, y, dy, save_mean, save_invstd, rows, C, nblk, partial, st)))
+        if (rc) return rc;
+        bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(partial, nblk, (double)rows, gamma, save_mean,
+                                                             save_invstd, k123, dgamma, dbeta, C);
+        EFFDET_LAUNCHED();
+    }
+    DISPATCH_T(dtype,
+        (bn_bwd_apply_kernel<float, 4><<<grid_for(rows * C / 4), 256, 0, st>>>(
+            (const float *)dy, (const float *)y, (const float *)z, k123, (float *)dz, rows * C / 4, C)),
+        (bn_bwd_apply_kernel<__nv_bfloat16, 8><<<grid_for(rows * C / 8), 256, 0, st>>>(
+            (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)y, (const __nv_bfloat16 *)z, k123,
+            (__nv_bfloat16 *)dz, rows * C / 8, C)))
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+/* column sum of a dense (rows*fold, C/fold) matrix -> out[C/fold] (bias gradients); the caller
+ * passes it viewed as (rows, C) with C a multiple of the vector width. */
+extern "C" int effdet_colsum(const void *x, size_t rows, int C, int fold, float *out, int accumulate,
+                             float *partial, int nblk, int dtype, void *stream) {
+    EFFDET_REQUIRE(x && out && partial && rows > 0 && C > 0 && nblk > 0 && fold >= 1, "bad arguments");
+    EFFDET_REQUIRE(C % fold == 0, "fold must divide C");
+    EFFDET_REQUIRE(C % (dtype == EFFDET_BF16 ? 8 : 4) == 0, "C must be a multiple of the vector width");
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    DISPATCH_T(dtype,
+        rc = (launch_colreduce<float, 4, RED_SUM>(x, nullptr, nullptr, nullptr, nullptr, rows, C, nblk, partial, st)),
+        rc = (launch_colreduce<__nv_bfloat16, 8, RED_SUM>(x, nullptr, nullptr, nullptr, nullptr, rows, C, nblk, partial, st)))
+    if (rc) return rc;
+    colsum_finalize_kernel<<<cdiv(C / fold, 128), 128, 0, st>>>(partial, nblk, C, fold, out, accumulate);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+extern "C" int effdet_dw_wgrad_blocks(int B, int H, int W, int C, int dtype) {
+    const int CV = dtype == EFFDET_BF16 ? 8 : 4;
+    int nvec = C / CV; if (nvec < 1) nvec = 1;
+    int PY = 128 / nvec; if (PY < 1) PY = 1;
+    const size_t total = (size_t)B * H * W;
+    size_t ppb = (size_t)PY * 32;
+    while (ppb > (size_t)PY && cdiv(total, ppb) < (unsigned)kNumSMs * 2) ppb >>= 1;
+    return (int)cdiv(total, ppb);
+}
+
+/* depthwise 3x3 (stride 1, SAME) weight gradient: dkernel (3,3,C) = sum f (*) dz. */
+extern "C" int effdet_dw_wgrad(const void *f, const void *dz, int B, int H, int W, int C,
+                               float *dkernel, float *partial, int nblk, int dtype, void *stream) {
+    EFFDET_REQUIRE(f && dz && dkernel && partial && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && nblk > 0,
+                   "bad arguments");
+    cudaStream_t st = as_stream(stream);
+    const int CV = dtype == EFFDET_BF16 ? 8 : 4;
+    const int nvec = C / CV;
+    EFFDET_REQUIRE(nvec <= 1024, "C too large");
+    int PY = 128 / nvec; if (PY < 1) PY = 1;
+    const size_t total = (size_t)B * H * W;
+    const int ppb = (int)cdiv(total, nblk);
+    EFFDET_REQUIRE((int)cdiv(total, ppb) == nblk, "nblk must come from effdet_dw_wgrad_blocks");
+    const size_t sm = (size_t)PY * 9 * C * sizeof(float);
+    if (dtype == EFFDET_F32) {
+        if (sm > 48 * 1024) EFFDET_CUDA(cudaFuncSetAttribute(dw_wgrad_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        dw_wgrad_kernel<float, 4><<<nblk, nvec * PY, sm, st>>>((const float *)f, (const float *)dz, B, H, W, C, ppb, partial);
+    } else if (dtype == EFFDET_BF16) {
+        if (sm > 48 * 1024) EFFDET_CUDA(cudaFuncSetAttribute(dw_wgrad_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        dw_wgrad_kernel<__nv_bfloat16, 8><<<nblk, nvec * PY, sm, st>>>((const __nv_bfloat16 *)f, (const __nv_bfloat16 *)dz, B, H, W, C, ppb, partial);
+    } else {
+        return fail(EFFDET_E_INVALID, "effdet_dw_wgrad: bad dtype%s", "");
+    }
+    EFFDET_LAUNCHED();
+    sum_partials_kernel<<<cdiv((size_t)9 * C, 128), 128, 0, st>>>(partial, nblk, 9 * C, dkernel, 0);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+/* gradient of one fusion input.  which = 0 routes through the resampling of in0 (mode0). */
+extern "C" int effdet_fuse_backward_input(const void *df, int which, int mode0, const void *in0,
+                                          const float *w, int n_inputs, float eps, void *dst,
+                                          int accumulate, int B, int H, int W, int C, int dtype,
+                                          void *stream) {
+    EFFDET_REQUIRE(df && dst && which >= 0 && which < n_inputs && (n_inputs == 2 || n_inputs == 3), "bad arguments");
+    EFFDET_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad sizes");
+    EFFDET_REQUIRE(!(which == 0 && mode0 == 2) || in0, "max-pool routing needs the forward input");
+    EFFDET_REQUIRE(a16(df) && a16(dst), "16B alignment");
+    cudaStream_t st = as_stream(stream);
+    size_t n = (size_t)B * H * W * C;
+    if (which == 0 && mode0 == 1) n /= 4;
+    if (which == 0 && mode0 == 2) n *= 4;
+    DISPATCH_T(dtype,
+        (fuse_bwd_kernel<float, 4><<<grid_for(n / 4), 256, 0, st>>>(
+            (const float *)df, which, mode0, (const float *)in0, w, n_inputs, eps, (float *)dst, accumulate, B, H, W, C)),
+        (fuse_bwd_kernel<__nv_bfloat16, 8><<<grid_for(n / 8), 256, 0, st>>>(
+            (const __nv_bfloat16 *)df, which, mode0, (const __nv_bfloat16 *)in0, w, n_inputs, eps,
+            (__nv_bfloat16 *)dst, accumulate, B, H, W, C)))
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+/* gradient of the fusion weights (layers.py:26-31): dw (n_inputs) f32; partial: 4*1184 floats. */
+extern "C" int effdet_fuse_backward_weights(const void *df, const void *f, const void *in0, int mode0,
+                                            const void *in1, const void *in2, const float *w,
+                                            float eps, float *dw, float *partial, int B, int H, int W,
+                                            int C, int dtype, void *stream) {
+    EFFDET_REQUIRE(df && f && in0 && in1 && w && dw && partial, "null pointer");
+    EFFDET_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad sizes");
+    cudaStream_t st = as_stream(stream);
+    const int n_in = in2 ? 3 : 2;
+    const size_t n = (size_t)B * H * W * C;
+    unsigned nblk;
+    DISPATCH_T(dtype,
+        (nblk = grid_for(n / 4), fuse_wgrad_kernel<float, 4><<<nblk, 256, 0, st>>>(
+            (const float *)df, (const float *)f, (const float *)in0, mode0, (const float *)in1,
+            (const float *)in2, B, H, W, C, partial)),
+        (nblk = grid_for(n / 8), fuse_wgrad_kernel<__nv_bfloat16, 8><<<nblk, 256, 0, st>>>(
+            (const __nv_bfloat16 *)df, (const __nv_bfloat16 *)f, (const __nv_bfloat16 *)in0, mode0,
+            (const __nv_bfloat16 *)in1, (const __nv_bfloat16 *)in2, B, H, W, C, partial)))
+    EFFDET_LAUNCHED();
+    fuse_wgrad_finalize_kernel<<<1, 32, 0, st>>>(partial, (int)nblk, w, n_in, eps, dw);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+/* keras SGD (train_tpu.py:268-269): v = momentum*v - lr_t*(g*grad_scale); w += v, with
+ * lr_t = lr / (1 + decay*iterations) computed by the caller. */
+extern "C" int effdet_sgd_momentum_step(float *w, const float *g, float *v, size_t n, float lr_t,
+                                        float momentum, float grad_scale, void *stream) {
+    if (n == 0) return EFFDET_OK;
+    EFFDET_REQUIRE(w && g && v, "null pointer");
+    sgd_momentum_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(w, g, v, n, lr_t, momentum, grad_scale);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+extern "C" int effdet_flip_taps(const float *in, float *out, int taps, int n, void *stream) {
+    EFFDET_REQUIRE(in && out && taps > 0 && n > 0, "bad arguments");
+    flip_taps_kernel<<<cdiv((size_t)taps * n, 256), 256, 0, as_stream(stream)>>>(in, out, taps, n);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+extern "C" int effdet_conv_weight_transpose(const float *in, float *out, int taps, int Cin, int Cout,
+                                            void *stream) {
+    EFFDET_REQUIRE(in && out && taps > 0 && Cin > 0 && Cout > 0, "bad arguments");
+    conv_weight_transpose_kernel<<<cdiv((size_t)taps * Cin * Cout, 256), 256, 0, as_stream(stream)>>>(
+        in, out, taps, Cin, Cout);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}

@@ -16,7 +16,7 @@ import torch
 from . import _lib
 from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SWISH, BF16, F32
 
-TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16}
+TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16, "i8": torch.int8, "i32": torch.int32}
 BN_EPS_BACKBONE = 1e-3            # keras default (efficientnet.py:233-236 passes no epsilon)
 BN_EPS_BIFPN = 1e-4               # model.py:42-45
 BN_MOMENTUM_BIFPN = 0.997
@@ -40,7 +40,7 @@ class Val:
         n = 1
         for s in self.shape:
             n *= s
-        return n * (2 if self.dtype == BF16 else 4)
+        return n * {BF16: 2, F32: 4, "i8": 1, "i32": 4}[self.dtype]
 
     @property
     def ptr(self):
@@ -199,7 +199,10 @@ class Plan:
                 feats.append(x)
                 self.taps["C%d" % len(feats)] = x
         self.features = feats
-        # ---- BiFPN
+        self._build_neck_and_heads(feats)
+
+    def _build_neck_and_heads(self, feats):
+        net = self.net
         Wd = net.w_bifpn
         for i in range(net.d_bifpn):
             feats = self._bifpn_layer(feats, i, Wd)

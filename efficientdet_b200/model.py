@@ -55,12 +55,33 @@ class Network:
         self.drop_scale = {}
         self.frozen_layers = set()
         self.plans = {}
+        self._staged = collections.OrderedDict()
         self._init_weights(seed)
+        self._materialize()
         self.refresh()
 
     # ---------------------------------------------------------------- initialisation
     def _put(self, name, arr):
-        self.weights[name] = torch.from_numpy(np.ascontiguousarray(arr, np.float32)).to(self.device)
+        self._staged[name] = np.ascontiguousarray(arr, np.float32)
+
+    def _materialize(self):
+        """All weights live in ONE flat fp32 device buffer (16-byte aligned slots, creation
+        order: backbone, BiFPN, heads) so that the gradient all-reduce and the SGD update run
+        over contiguous ranges; `weights[name]` are views into it."""
+        offs, total = collections.OrderedDict(), 0
+        for name, a in self._staged.items():
+            offs[name] = total
+            total += (a.size + 3) // 4 * 4
+        host = np.zeros(total, np.float32)
+        for name, a in self._staged.items():
+            host[offs[name]:offs[name] + a.size] = a.reshape(-1)
+        self.flat = torch.from_numpy(host).to(self.device)
+        self.offsets = offs
+        for name, a in self._staged.items():
+            self.weights[name] = self.flat[offs[name]:offs[name] + a.size].view(a.shape)
+        first_bifpn = next(k for k in offs if k.startswith("BiFPN_"))
+        self.backbone_end = offs[first_bifpn]      # flat index where BiFPN + head params start
+        self._staged = None
 
     def _bn(self, name, C, eps):
         self._put(name + "/gamma", np.ones(C))
@@ -68,8 +89,6 @@ class Network:
         self._put(name + "/moving_mean", np.zeros(C))
         self._put(name + "/moving_variance", np.ones(C))
         self.bn_layers[name] = (C, eps)
-        self.folded[name] = (torch.empty(C, dtype=torch.float32, device=self.device),
-                             torch.empty(C, dtype=torch.float32, device=self.device))
 
     def _init_weights(self, seed):
         rng = np.random.default_rng(seed)
@@ -133,6 +152,9 @@ class Network:
         """Re-derive folded BatchNorm scale/shift after the weights changed."""
         st = _lib.stream_ptr(self.device)
         for name, (C, eps) in self.bn_layers.items():
+            if name not in self.folded:
+                self.folded[name] = (torch.empty(C, dtype=torch.float32, device=self.device),
+                                     torch.empty(C, dtype=torch.float32, device=self.device))
             sc, sh = self.folded[name]
             _lib.call("effdet_bn_fold", self.weights[name + "/gamma"].data_ptr(),
                       self.weights[name + "/beta"].data_ptr(),
@@ -140,7 +162,35 @@ class Network:
                       self.weights[name + "/moving_variance"].data_ptr(), float(eps),
                       sc.data_ptr(), sh.data_ptr(), C, st)
 
+    # ---------------------------------------------------------------- training state
+    def ensure_grad_buffers(self):
+        if not hasattr(self, "grad_flat"):
+            self.grad_flat = torch.zeros_like(self.flat)
+            self.velocity = torch.zeros_like(self.flat)
+            self.grads = {k: self.grad_flat[o:o + self.weights[k].numel()].view(self.weights[k].shape)
+                          for k, o in self.offsets.items()}
+            self._consts = {}
+
+    def const_ones(self, C):
+        k = ("ones", C)
+        if k not in self._consts:
+            self._consts[k] = torch.ones(C, dtype=torch.float32, device=self.device)
+        return self._consts[k]
+
+    def const_zeros(self, C):
+        k = ("zeros", C)
+        if k not in self._consts:
+            self._consts[k] = torch.zeros(C, dtype=torch.float32, device=self.device)
+        return self._consts[k]
+
+    def invalidate(self):
+        """Weights changed (optimizer step): inference-mode folded BN must be re-derived."""
+        self._dirty = True
+
     def plan(self, batch, **kw):
+        if getattr(self, "_dirty", False):
+            self.refresh()
+            self._dirty = False
         key = (int(batch), tuple(sorted(kw.items())))
         if key not in self.plans:
             self.plans[key] = engine.Plan(self, batch, **kw)

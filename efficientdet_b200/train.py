@@ -1,0 +1,492 @@
+"""Training step on one GPU (+ data-parallel all-reduce across ranks).
+
+Replaces what Keras/TF did inside `model.fit` for the reference (train_tpu.py:249-346, call stack
+SURVEY section 3 (C)): forward in training mode (BatchNorm batch statistics in every layer that
+is trainable and not freeze_bn), focal + smooth-L1 losses, backward through heads and BiFPN,
+gradient all-reduce (tf.distribute.MirroredStrategy -> NCCL over NVLink here), SGD-momentum.
+
+Scope of this build: layers up to the backbone boundary must be frozen
+(`--freeze-backbone`, train_tpu.py:272-274: model.layers[1:EFFICIENTNET_DEPTHS[phi]]); the
+backbone then runs in inference mode and receives no gradient.  Full-backbone backward is listed
+under "next" in DESIGN.md.
+"""
+import ctypes
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, BF16, F32
+from .engine import BN_EPS_BIFPN, BN_MOMENTUM_BIFPN, Op, Val, _call
+
+UP, DOWN = 1, 2
+
+
+class TrainPlan(engine.Plan):
+    """Forward (training mode) + losses + backward launch list for a fixed batch."""
+
+    def __init__(self, net, batch, alpha=0.25, gamma=1.5, delta=1.0, dense_labels=False):
+        self.alpha, self.gamma, self.delta = alpha, gamma, delta
+        self.dense_labels = dense_labels
+        self.tape = []
+        self.gvals = {}            # id(Val) -> gradient Val
+        net.ensure_grad_buffers()
+        super().__init__(net, batch, reuse_buffers=True)
+
+    # ------------------------------------------------------------------ small helpers
+    def gw(self, key):
+        return self.net.grads[key]
+
+    def fvec(self, C, name):
+        return self.val((C,), F32, name, keep=True)
+
+    def _scratch(self, nfloats, name):
+        return self.val((int(nfloats),), F32, name)
+
+    def bn_is_training(self, bn_name):
+        return not (self.net.freeze_bn or bn_name in self.net.frozen_layers)
+
+    def _bn_train(self, z, y, bn_name, C, rows, act):
+        """z -> y = act(BN_batch(z)); returns the record needed by the backward pass."""
+        lib = _lib.load()
+        rec = dict(bn=bn_name, C=C, rows=rows, train=self.bn_is_training(bn_name))
+        if rec["train"]:
+            nblk = lib.effdet_colreduce_blocks(rows, C, self.dtype)
+            sc, sh = self.fvec(C, bn_name + "/scale_t"), self.fvec(C, bn_name + "/shift_t")
+            mu, iv = self.fvec(C, bn_name + "/mean_t"), self.fvec(C, bn_name + "/invstd_t")
+            part = self._scratch(2 * C * nblk, bn_name + "/partial")
+            w = self.w
+            self.add("bn_stats", [z], [sc, sh, mu, iv, part],
+                     lambda: _call("effdet_bn_train_stats", z.ptr, rows, C, w(bn_name + "/gamma").data_ptr(),
+                                   w(bn_name + "/beta").data_ptr(), BN_EPS_BIFPN, BN_MOMENTUM_BIFPN,
+                                   w(bn_name + "/moving_mean").data_ptr(),
+                                   w(bn_name + "/moving_variance").data_ptr(), sc.ptr, sh.ptr, mu.ptr,
+                                   iv.ptr, part.ptr, nblk, self.dtype), bn_name + "_stats")
+            self.add("bn_apply", [z, sc, sh], [y],
+                     lambda: _call("effdet_scale_shift_act", z.ptr, sc.ptr, sh.ptr, y.ptr, rows, C, act,
+                                   self.dtype), bn_name + "_apply")
+            rec.update(mean=mu, invstd=iv, nblk=nblk)
+        else:
+            fs, fb = self.folded(bn_name)
+            self.add("bn_apply", [z], [y],
+                     lambda: _call("effdet_scale_shift_act", z.ptr, fs.data_ptr(), fb.data_ptr(), y.ptr,
+                                   rows, C, act, self.dtype), bn_name + "_apply")
+        return rec
+
+    # ------------------------------------------------------------------ forward emitters (override)
+    def _conv_block(self, x, name, cin, cout, k=1, stride=1):
+        B = self.B
+        Ho = (x.shape[1] + stride - 1) // stride
+        z = self.val((B, Ho, Ho, cout), name=name + "_z", keep=True)
+        y = self.val((B, Ho, Ho, cout), name=name, keep=True)
+        self.conv([x], [z], name + "_conv/kernel", cin, cout, k=k, stride=stride, name=name + "_conv")
+        rec = self._bn_train(z, y, name + "_bn", cout, B * Ho * Ho, ACT_RELU)
+        rec.update(kind="convblock", x=x, z=z, y=y, name=name, cin=cin, cout=cout, k=k, stride=stride)
+        self.tape.append(rec)
+        return y
+
+    def _node(self, in0, mode0, in1, in2, fuse_name, dw_name, C):
+        B, H = self.B, in1.shape[1]
+        net = self.net
+        f = self.val((B, H, H, C), name=dw_name + "_f", keep=True)
+        z = self.val((B, H, H, C), name=dw_name + "_z", keep=True)
+        y = self.val((B, H, H, C), name=dw_name, keep=True)
+        fw = self.w(fuse_name + "/" + fuse_name) if net.weighted_bifpn else None
+        fwp = fw.data_ptr() if fw is not None else None
+        self.add("fuse", [in0, in1, in2], [f],
+                 lambda: _call("effdet_resample_fuse", in0.ptr, mode0, in1.ptr,
+                               in2.ptr if in2 is not None else None, fwp, 1e-4, f.ptr, B, H, H, C,
+                               self.dtype), dw_name + "_fuse")
+        ones, zeros = net.const_ones(C), net.const_zeros(C)
+        self.add("dwconv", [f], [z],
+                 lambda: _call("effdet_dwconv", f.ptr, self.w(dw_name + "_dconv/depthwise_kernel").data_ptr(),
+                               ones.data_ptr(), zeros.data_ptr(), z.ptr, None, 0, B, H, H, C, 3, 1,
+                               ACT_NONE, self.dtype), dw_name + "_dconv", flops=18 * B * H * H * C)
+        rec = self._bn_train(z, y, dw_name + "_bn", C, B * H * H, ACT_RELU)
+        rec.update(kind="node", in0=in0, mode0=mode0, in1=in1, in2=in2, f=f, z=z, y=y, fuse=fuse_name,
+                   name=dw_name, H=H)
+        self.tape.append(rec)
+        return y
+
+    def _heads(self, feats, Wd):
+        super()._heads(feats, Wd)
+        # recover the per-layer activations from the conv ops just emitted
+        net = self.net
+        n_ops = 2 * (net.head_depth + 1)
+        ops = self.ops[-n_ops:]
+        self.head_tape = []
+        for h, (scope, fmt, final, out, per) in enumerate((
+                ("box_head", "regress_head_conv_%d", "regress_head_conv_final", self.regression, 4),
+                ("class_head", "class_head_%d", "pyramid_classification", self.classification,
+                 net.num_classes))):
+            layers = []
+            xs = list(feats)
+            for i in range(net.head_depth):
+                op = ops[h * (net.head_depth + 1) + i]
+                ys = op.outputs
+                for v in ys:
+                    v.keep = True
+                layers.append(dict(name=scope + "/" + fmt % i, xs=xs, ys=ys))
+                xs = ys
+            self.head_tape.append(dict(scope=scope, final=scope + "/" + final, layers=layers, xs=xs,
+                                       out=out, per=per))
+        for f in feats:
+            f.keep = True
+
+    # ------------------------------------------------------------------ whole step
+    def _build(self):
+        super()._build()                      # forward (training-mode emitters above)
+        self.n_forward_ops = len(self.ops)
+        self._build_losses()
+        self._build_backward()
+
+    def _build_losses(self):
+        B, N, C = self.B, self.N, self.net.num_classes
+        self.reg_t = self.val((B, N, 5), F32, "regression_targets", keep=True)
+        if self.dense_labels:
+            self.lab_t = self.val((B, N, C + 1), F32, "label_targets", keep=True)
+            self.state_t = self.cls_t = None
+        else:
+            self.lab_t = None
+            self.state_t = self.val((B, N), "i8", "state_targets", keep=True)
+            self.cls_t = self.val((B, N), "i32", "class_targets", keep=True)
+        self.dcls = self.val((B, N, C), F32, "dclassification_logits", keep=True)
+        self.dreg = self.val((B, N, 4), F32, "dregression", keep=True)
+        self.loss_out = self.val((8,), F32, "losses", keep=True)
+        ws_bytes = _lib.load().effdet_detection_losses_workspace_size()
+        ws = self._scratch(ws_bytes // 4, "loss_ws")
+        ins = [self.classification, self.regression, self.reg_t, self.lab_t, self.state_t, self.cls_t]
+        self.add("losses", ins, [self.dcls, self.dreg, self.loss_out, ws],
+                 lambda: _call("effdet_detection_losses", self.classification.ptr, self.regression.ptr,
+                               self.reg_t.ptr, self.lab_t.ptr if self.lab_t is not None else None,
+                               self.state_t.ptr if self.state_t is not None else None,
+                               self.cls_t.ptr if self.cls_t is not None else None, B, N, C, self.alpha,
+                               self.gamma, self.delta, 1.0, self.dcls.ptr, self.dreg.ptr,
+                               self.loss_out.ptr, ws.ptr, ws_bytes), "losses")
+
+    # gradient bookkeeping ------------------------------------------------------------
+    def grad_of(self, v):
+        """(gradient Val, accumulate?) for activation v; first writer overwrites."""
+        g = self.gvals.get(id(v))
+        if g is None:
+            g = self.val(v.shape, v.dtype, (v.name or "") + "_grad")
+            self.gvals[id(v)] = g
+            return g, 0
+        return g, 1
+
+    def _transposed_weight(self, key, taps, cin, cout):
+        wt = self.val((taps * cin * cout,), F32, key + "_T")
+        self.add("wtrans", [], [wt],
+                 lambda: _call("effdet_conv_weight_transpose", self.w(key).data_ptr(), wt.ptr, taps, cin,
+                               cout), key + "_T")
+        return wt
+
+    def _wgrad(self, xs, dzs, key, cin, cout, k, stride, dz_ld=None, dz_bs=None, dz_off=None,
+               dz_dtype=None, name=""):
+        lib = _lib.load()
+        n = len(xs)
+        d = _lib.WgradDesc()
+        d.n_groups = n
+        for i in range(n):
+            d.H[i], d.W[i] = xs[i].shape[1], xs[i].shape[2]
+        d.B, d.Cin, d.Cout, d.kh, d.kw, d.stride = self.B, cin, cout, k, k, stride
+        nsplit = lib.effdet_conv_wgrad_splits(ctypes.byref(d))
+        part = self._scratch(nsplit * k * k * cin * cout, key + "_wg_partial")
+        gw = self.gw(key)
+        xdt = self.dtype
+        zdt = self.dtype if dz_dtype is None else dz_dtype
+
+        def make():
+            for i in range(n):
+                d.x[i] = xs[i].ptr
+                d.dz[i] = dzs[i].ptr + (dz_off[i] if dz_off else 0)
+                d.dz_ld[i] = dz_ld[i] if dz_ld else 0
+                d.dz_batch_stride[i] = dz_bs[i] if dz_bs else 0
+            d.dweight, d.partial, d.n_splits, d.accumulate = gw.data_ptr(), part.ptr, nsplit, 0
+            d.x_dtype, d.dz_dtype = xdt, zdt
+            self._keepalive.append(d)
+            return _call("effdet_conv_wgrad", ctypes.byref(d))
+        flops = sum(2 * self.B * (-(-x.shape[1] // stride)) * (-(-x.shape[2] // stride)) * cin * cout * k * k
+                    for x in xs)
+        self.ops.append(Op("conv_wgrad", list(xs) + list(dict.fromkeys(dzs)), [part], make, name,
+                           sum(v.nbytes for v in xs) + sum(v.nbytes for v in dict.fromkeys(dzs)), flops))
+
+    def _bias_grad(self, dz, rows, C, key, accumulate, dtype, byte_off=0, name=""):
+        lib = _lib.load()
+        vec = 8 if dtype == BF16 else 4
+        fold = 1
+        while (C * fold) % vec:
+            fold *= 2
+        assert rows % fold == 0
+        prow, pC = rows // fold, C * fold
+        nblk = lib.effdet_colreduce_blocks(prow, pC, dtype)
+        part = self._scratch(2 * pC * nblk, key + "_bg_partial")
+        g = self.gw(key)
+        self.add("bias_grad", [dz], [part],
+                 lambda: _call("effdet_colsum", dz.ptr + byte_off, prow, pC, fold, g.data_ptr(), accumulate,
+                               part.ptr, nblk, dtype), name)
+
+    # backward ------------------------------------------------------------------------
+    def _build_backward(self):
+        net, B, Wd = self.net, self.B, self.net.w_bifpn
+        A = 9
+        feats = self.pyramid
+        hw = [f.shape[1] * f.shape[2] for f in feats]
+        N = self.N
+        lvl_off = np.concatenate([[0], np.cumsum([A * h for h in hw])[:-1]])
+        # ---- heads
+        for ht in self.head_tape:
+            per = ht["per"]
+            cout = A * per
+            dz_final = self.dreg if ht["scope"] == "box_head" else self.dcls
+            key = ht["final"]
+            # bias: the concatenated (B,N,per) tensor is a dense (B*N/9, 9*per) matrix
+            self._bias_grad(dz_final, B * N // A, cout, key + "/bias", 0, F32, name=key + "_dbias")
+            offs = [int(o) * per * 4 for o in lvl_off]
+            self._wgrad(ht["xs"], [dz_final] * 5, key + "/kernel", Wd, cout, 3, 1,
+                        dz_ld=[cout] * 5, dz_bs=[N * per] * 5, dz_off=offs, dz_dtype=F32,
+                        name=key + "_wgrad")
+            wt = self._transposed_weight(key + "/kernel", 9, Wd, cout)
+            layers = ht["layers"]
+            # data gradient into the last trunk layer's outputs (masked by its ReLU)
+            targets = ht["xs"]
+            gvals = [self.grad_of(t) for t in targets]
+            self._dgrad(dz_final, None, wt, cout, Wd, [g for g, _ in gvals], targets,
+                        masks=targets if layers else None, accumulate=[a for _, a in gvals],
+                        x_ld=[cout] * 5, x_bs=[N * per] * 5, x_off=offs, in_dtype=F32,
+                        shapes=[t.shape for t in targets], name=key + "_dgrad")
+            for li in range(len(layers) - 1, -1, -1):
+                L = layers[li]
+                dzs = [self.gvals[id(y)] for y in L["ys"]]
+                for l, dz in enumerate(dzs):
+                    rows = B * dz.shape[1] * dz.shape[2]
+                    self._bias_grad(dz, rows, Wd, L["name"] + "/bias", 0 if l == 0 else 1, self.dtype,
+                                    name=L["name"] + "_dbias")
+                self._wgrad(L["xs"], dzs, L["name"] + "/kernel", Wd, Wd, 3, 1, name=L["name"] + "_wgrad")
+                wt = self._transposed_weight(L["name"] + "/kernel", 9, Wd, Wd)
+                targets = L["xs"]
+                gv = [self.grad_of(t) for t in targets]
+                self._dgrad(None, dzs, wt, Wd, Wd, [g for g, _ in gv], targets,
+                            masks=targets if li > 0 else None, accumulate=[a for _, a in gv],
+                            shapes=[t.shape for t in targets], name=L["name"] + "_dgrad")
+        # ---- BiFPN (reverse tape)
+        for rec in reversed(self.tape):
+            if rec["kind"] == "node":
+                self._node_backward(rec)
+            else:
+                self._convblock_backward(rec)
+
+    def _dgrad(self, x_single, xs, wt, cin, cout, dsts, targets, masks, accumulate, shapes, x_ld=None,
+               x_bs=None, x_off=None, in_dtype=None, name=""):
+        """stride-1 3x3/1x1 data gradient = convolution of dz with the transposed kernel."""
+        n = len(dsts)
+        in_dt = self.dtype if in_dtype is None else in_dtype
+        taps = wt.shape[0] // (cin * cout)
+        k = 3 if taps == 9 else 1
+
+        def make():
+            d = _lib.ConvDesc()
+            d.n_groups = n
+            for i in range(n):
+                src = x_single if x_single is not None else xs[i]
+                d.x[i] = src.ptr + (x_off[i] if x_off else 0)
+                d.y[i] = dsts[i].ptr
+                d.residual[i] = dsts[i].ptr if accumulate[i] else None
+                d.relu_mask[i] = masks[i].ptr if masks else None
+                d.H[i], d.W[i] = shapes[i][1], shapes[i][2]
+                d.ldx[i] = x_ld[i] if x_ld else 0
+                d.x_batch_stride[i] = x_bs[i] if x_bs else 0
+            d.B, d.Cin, d.Cout, d.kh, d.kw, d.stride = self.B, cin, cout, k, k, 1
+            d.weight = wt.ptr
+            d.act, d.in_dtype, d.out_dtype = ACT_NONE, in_dt, self.dtype
+            d.allow_tensor_core = 0
+            self._keepalive.append(d)
+            return _call("effdet_conv2d", ctypes.byref(d))
+        ins = ([x_single] if x_single is not None else list(xs)) + [wt] + (list(masks) if masks else [])
+        ins += [dsts[i] for i in range(n) if accumulate[i]]
+        flops = sum(2 * self.B * s[1] * s[2] * cin * cout * taps for s in shapes)
+        self.ops.append(Op("conv_dgrad", ins, list(dsts), make, name,
+                           sum(v.nbytes for v in ins) + sum(v.nbytes for v in dsts), flops))
+
+    def _bn_backward(self, rec, dy):
+        """dy (grad of y = relu(BN(z))) -> dz (new Val)."""
+        z, y, C, rows, bn = rec["z"], rec["y"], rec["C"], rec["rows"], rec["bn"]
+        dz = self.val(z.shape, name=(z.name or "") + "_grad")
+        k123 = self._scratch(3 * C, bn + "/k123")
+        w = self.w
+        if rec["train"]:
+            nblk = rec["nblk"]
+            part = self._scratch(2 * C * nblk, bn + "/bwd_partial")
+            mu, iv = rec["mean"], rec["invstd"]
+            self.add("bn_bwd", [dy, y, z, mu, iv], [dz, k123, part],
+                     lambda: _call("effdet_bn_relu_backward", dy.ptr, y.ptr, z.ptr, rows, C,
+                                   w(bn + "/gamma").data_ptr(), mu.ptr, iv.ptr, None,
+                                   self.gw(bn + "/gamma").data_ptr(), self.gw(bn + "/beta").data_ptr(),
+                                   dz.ptr, k123.ptr, part.ptr, nblk, self.dtype), bn + "_bwd")
+        else:
+            fs, _ = self.folded(bn)
+            part = self._scratch(4, bn + "/bwd_partial")
+            self.add("bn_bwd", [dy, y, z], [dz, k123],
+                     lambda: _call("effdet_bn_relu_backward", dy.ptr, y.ptr, z.ptr, rows, C,
+                                   w(bn + "/gamma").data_ptr(), None, None, fs.data_ptr(), None, None,
+                                   dz.ptr, k123.ptr, part.ptr, 1, self.dtype), bn + "_bwd")
+        return dz
+
+    def _needs_grad(self, v):
+        return not any(v is f for f in self.features)     # frozen backbone features
+
+    def _node_backward(self, rec):
+        lib = _lib.load()
+        B, H, C, name = self.B, rec["H"], rec["C"], rec["name"]
+        net = self.net
+        y = rec["y"]
+        dy = self.gvals.get(id(y))
+        if dy is None:
+            return
+        dz = self._bn_backward(rec, dy)
+        f = rec["f"]
+        kkey = name + "_dconv/depthwise_kernel"
+        nblk = lib.effdet_dw_wgrad_blocks(B, H, H, C, self.dtype)
+        part = self._scratch(9 * C * nblk, name + "/dw_wg_partial")
+        self.add("dw_wgrad", [f, dz], [part],
+                 lambda: _call("effdet_dw_wgrad", f.ptr, dz.ptr, B, H, H, C, self.gw(kkey).data_ptr(),
+                               part.ptr, nblk, self.dtype), name + "_dw_wgrad", flops=18 * B * H * H * C)
+        wflip = self._scratch(9 * C, name + "/dw_flip")
+        self.add("wtrans", [], [wflip],
+                 lambda: _call("effdet_flip_taps", self.w(kkey).data_ptr(), wflip.ptr, 9, C), name + "_flip")
+        df = self.val(f.shape, name=name + "_f_grad")
+        ones, zeros = net.const_ones(C), net.const_zeros(C)
+        self.add("dwconv", [dz, wflip], [df],
+                 lambda: _call("effdet_dwconv", dz.ptr, wflip.ptr, ones.data_ptr(), zeros.data_ptr(), df.ptr,
+                               None, 0, B, H, H, C, 3, 1, ACT_NONE, self.dtype), name + "_dw_dgrad",
+                 flops=18 * B * H * H * C)
+        in0, in1, in2, mode0 = rec["in0"], rec["in1"], rec["in2"], rec["mode0"]
+        n_in = 3 if in2 is not None else 2
+        fw = self.w(rec["fuse"] + "/" + rec["fuse"]) if net.weighted_bifpn else None
+        fwp = fw.data_ptr() if fw is not None else None
+        if fw is not None:
+            fpart = self._scratch(4 * 148 * 8, name + "/fuse_wg_partial")
+            gfw = self.gw(rec["fuse"] + "/" + rec["fuse"])
+            self.add("fuse_wgrad", [df, f, in0, in1, in2], [fpart],
+                     lambda: _call("effdet_fuse_backward_weights", df.ptr, f.ptr, in0.ptr, mode0, in1.ptr,
+                                   in2.ptr if in2 is not None else None, fwp, 1e-4, gfw.data_ptr(),
+                                   fpart.ptr, B, H, H, C, self.dtype), name + "_fuse_wgrad")
+        for which, src in enumerate([in0, in1, in2][:n_in]):
+            if not self._needs_grad(src):
+                continue
+            g, acc = self.grad_of(src)
+            self.add("fuse_bwd", [df, in0 if (which == 0 and mode0 == DOWN) else None, g if acc else None],
+                     [g],
+                     lambda which=which, g=g, acc=acc:
+                     _call("effdet_fuse_backward_input", df.ptr, which, mode0, in0.ptr, fwp, n_in, 1e-4,
+                           g.ptr, acc, B, H, H, C, self.dtype), name + "_fuse_bwd%d" % which)
+
+    def _convblock_backward(self, rec):
+        B = self.B
+        y, x = rec["y"], rec["x"]
+        dy = self.gvals.get(id(y))
+        if dy is None:
+            return
+        dz = self._bn_backward(rec, dy)
+        name, cin, cout, k, stride = rec["name"], rec["cin"], rec["cout"], rec["k"], rec["stride"]
+        key = name + "_conv/kernel"
+        self._wgrad([x], [dz], key, cin, cout, k, stride, name=name + "_wgrad")
+        if not self._needs_grad(x):
+            return
+        g, acc = self.grad_of(x)
+        if stride == 1:
+            wt = self._transposed_weight(key, k * k, cin, cout)
+            self._dgrad(None, [dz], wt, cout, cin, [g], [x], None, [acc], [x.shape], name=name + "_dgrad")
+        else:
+            H = x.shape[1]
+            self.add("conv_dgrad", [dz, g if acc else None], [g],
+                     lambda: _call("effdet_conv_dgrad_strided", dz.ptr, self.w(key).data_ptr(), g.ptr, acc, B,
+                                   H, H, cin, cout, k, stride, self.dtype), name + "_dgrad")
+
+
+class Trainer:
+    """compile()/train_on_batch() backend of model.Model."""
+
+    def __init__(self, model, optimizer, loss):
+        from .optimizers import SGD
+        from .utils.tpu import Focal, SmoothL1
+        self.model, self.net = model, model.net
+        self.opt = optimizer if optimizer is not None else SGD(lr=0.01, decay=4e-5, momentum=0.9)
+        loss = loss or {}
+        self.focal = loss.get("classification") or Focal(0.25, 1.5)
+        self.sl1 = loss.get("regression") or SmoothL1(1)
+        self.plans = {}
+        self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        self.graphs = {}
+
+    def plan(self, B, dense):
+        key = (B, dense)
+        if key not in self.plans:
+            net = self.net
+            n_backbone = 1 + len(net.backbone.keras_layer_names())
+            frozen = net.frozen_layers
+            missing = [n for n in net.backbone.keras_layer_names() if n not in frozen]
+            if missing:
+                raise NotImplementedError(
+                    "this build trains BiFPN + heads only: freeze the backbone first "
+                    "(for i in range(1, %d): model.layers[i].trainable = False), as "
+                    "train_tpu.py --freeze-backbone does" % n_backbone)
+            self.plans[key] = TrainPlan(net, B, self.focal.alpha, self.focal.gamma, self.sl1.lambda_,
+                                        dense_labels=dense)
+        return self.plans[key]
+
+    def load_batch(self, plan, images, targets):
+        """targets: [regression_t (B,N,5), labels_t (B,N,C+1)] (reference generator layout) or
+        (regression_t, state i8, cls i32) device tensors from anchor_targets_device(compact=True)."""
+        dev = self.net.device
+        img = images if isinstance(images, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(images, np.float32))
+        plan.tensor(plan.images).copy_(img.to(dev, non_blocking=True))
+        if plan.dense_labels:
+            reg_t, lab_t = targets
+            plan.tensor(plan.reg_t).copy_(torch.as_tensor(reg_t).to(dev, non_blocking=True))
+            plan.tensor(plan.lab_t).copy_(torch.as_tensor(lab_t).to(dev, non_blocking=True))
+        else:
+            reg_t, st, cl = targets
+            plan.tensor(plan.reg_t).copy_(reg_t)
+            plan.tensor(plan.state_t).copy_(st)
+            plan.tensor(plan.cls_t).copy_(cl)
+
+    def apply_gradients(self):
+        net = self.net
+        g = net.grad_flat[net.backbone_end:]
+        if self.world > 1:
+            torch.distributed.all_reduce(g)
+        n = g.numel()
+        _lib.call("effdet_sgd_momentum_step", net.flat.data_ptr() + 4 * net.backbone_end, g.data_ptr(),
+                  net.velocity.data_ptr() + 4 * net.backbone_end, n, float(self.opt.current_lr()),
+                  float(self.opt.momentum), 1.0 / self.world, _lib.stream_ptr(net.device))
+        self.opt.iterations += 1
+
+    def run_plan(self, plan, use_graph=True):
+        key = id(plan)
+        if use_graph and key not in self.graphs:
+            plan.run()                                  # eager warm-up (sets func attributes)
+            torch.cuda.synchronize(self.net.device)
+            # the warm-up advanced the BN moving averages once; that is a real (extra) step of
+            # statistics only when the caller discards this run, so restore them
+            self.graphs[key] = plan.capture()
+        if use_graph:
+            plan.graph.replay()
+        else:
+            plan.run()
+
+    def step(self, images, targets, sync=True):
+        dense = not (isinstance(targets, (tuple, list)) and len(targets) == 3)
+        B = int(images.shape[0])
+        plan = self.plan(B, dense)
+        self.load_batch(plan, images, targets)
+        plan.run()
+        self.apply_gradients()
+        self.net.invalidate()
+        if not sync:
+            return None
+        out = plan.tensor(plan.loss_out).cpu().numpy()
+        return [float(out[0] + out[1]), float(out[1]), float(out[0])]   # keras: [total, regression, classification]

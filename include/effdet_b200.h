@@ -142,6 +142,11 @@ typedef struct effdet_conv_desc {
     int H[EFFDET_MAX_GROUPS], W[EFFDET_MAX_GROUPS];
     int ldc[EFFDET_MAX_GROUPS];
     long long y_batch_stride[EFFDET_MAX_GROUPS];
+    int ldx[EFFDET_MAX_GROUPS];              /* input pixel stride (elements), 0 = Cin */
+    long long x_batch_stride[EFFDET_MAX_GROUPS]; /* input image stride (elements), 0 = dense */
+    const void *relu_mask[EFFDET_MAX_GROUPS];    /* out_dtype, indexed like y: output zeroed where
+                                                    mask <= 0 (ReLU backward fused into a data-
+                                                    gradient convolution); or NULL */
     int B, Cin, Cout, kh, kw, stride;
     const float *weight;  /* (kh,kw,Cin,Cout) f32, Keras HWIO */
     const float *scale;   /* (Cout) or NULL */
@@ -187,6 +192,111 @@ int effdet_bifpn_node(const void *in0, int mode0, const void *in1, const void *i
                       const float *w, float eps, const float *dw_kernel, const float *scale,
                       const float *shift, void *out, int B, int H, int W, int C, int dtype,
                       void *stream);
+
+/* ---------------------------------------------------------------- training
+ * utils/tpu.py:84-155 tpu_focal + :26-81 tpu_smooth_l1, forward and backward in one pass.
+ * classification (B,N,C) f32 probabilities (sigmoid output of the class head, model.py:351),
+ * regression (B,N,4) f32.  Targets in the reference layout: regression_t (B,N,5) f32 and either
+ * dense labels_t (B,N,C+1) f32 or, when labels_t == NULL, the compact pair state (B,N) i8 /
+ * cls (B,N) i32 written by effdet_anchor_targets.  Gradients: dcls_logits (B,N,C) f32 w.r.t.
+ * the class head's pre-sigmoid outputs, dreg (B,N,4) f32; both already divided by
+ * max(1,#positive) and multiplied by grad_scale.  out8 (device f32[8]): [0] focal loss,
+ * [1] smooth-L1 loss, [2]/[3] #positive anchors, [4]/[5] 1/normaliser. */
+size_t effdet_detection_losses_workspace_size(void);
+int effdet_detection_losses(const float *classification, const float *regression,
+                            const float *regression_t, const float *labels_t, const int8_t *state,
+                            const int32_t *cls, int B, size_t N, int C, float alpha, float gamma,
+                            float delta, float grad_scale, float *dcls_logits, float *dreg,
+                            float *out8, void *workspace, size_t workspace_bytes, void *stream);
+
+/* BiFPN fusion forward keeping the fused tensor (training): same semantics as the fusion stage
+ * of effdet_bifpn_node (model.py:154-194/226-266, layers.py:26-31). */
+int effdet_resample_fuse(const void *in0, int mode0, const void *in1, const void *in2,
+                         const float *w, float eps, void *out, int B, int H, int W, int C, int dtype,
+                         void *stream);
+
+/* Row-block count used by the deterministic column reductions below for a (rows, C) matrix;
+ * `partial` scratch must hold 2*C*blocks floats. */
+int effdet_colreduce_blocks(size_t rows, int C, int dtype);
+
+/* BatchNormalization, training mode (model.py:59-62/81-84 with trainable=True; TF fused BN):
+ * batch mean / biased variance of z (rows,C) -> scale, shift (y = z*scale + shift), saved
+ * mean / invstd for the backward pass, and the moving-average update
+ * moving = moving*momentum + batch*(1-momentum) (unbiased variance); moving_* may be NULL. */
+int effdet_bn_train_stats(const void *z, size_t rows, int C, const float *gamma, const float *beta,
+                          float eps, float momentum, float *moving_mean, float *moving_var,
+                          float *scale, float *shift, float *save_mean, float *save_invstd,
+                          float *partial, int nblk, int dtype, void *stream);
+/* y = act(z*scale + shift) over a (rows,C) matrix. */
+int effdet_scale_shift_act(const void *z, const float *scale, const float *shift, void *y,
+                           size_t rows, int C, int act, int dtype, void *stream);
+/* Backward of y = relu(BN(z)): dz, dgamma, dbeta.  frozen_scale != NULL => BN ran in inference
+ * mode (freeze_bn / trainable=False): dz = scale * dy*[y>0], no dgamma/dbeta.
+ * k123: scratch 3*C floats; partial: 2*C*nblk floats. */
+int effdet_bn_relu_backward(const void *dy, const void *y, const void *z, size_t rows, int C,
+                            const float *gamma, const float *save_mean, const float *save_invstd,
+                            const float *frozen_scale, float *dgamma, float *dbeta, void *dz,
+                            float *k123, float *partial, int nblk, int dtype, void *stream);
+/* Column sums of x viewed as (rows, C) -> out[C/fold] (bias gradients; `fold` consecutive logical
+ * rows were packed into one physical row to keep rows vectorisable). */
+int effdet_colsum(const void *x, size_t rows, int C, int fold, float *out, int accumulate,
+                  float *partial, int nblk, int dtype, void *stream);
+
+/* Depthwise 3x3 stride-1 SAME weight gradient (model.py:48-55 DepthwiseConv2D backward-filter).
+ * partial: 9*C*blocks floats with blocks = effdet_dw_wgrad_blocks(). */
+int effdet_dw_wgrad_blocks(int B, int H, int W, int C, int dtype);
+int effdet_dw_wgrad(const void *f, const void *dz, int B, int H, int W, int C, float *dkernel,
+                    float *partial, int nblk, int dtype, void *stream);
+
+/* Fusion backward (layers.py:26-31 + UpSampling2D / MaxPooling2D gradients).  df (B,H,W,C) is the
+ * gradient of the fused tensor.  which = 0: gradient of in0 routed through its resampling
+ * (mode 1: 2x2 sum into the (H/2,W/2) tensor; mode 2: to the first maximum of each 2x2 window of
+ * the (2H,2W) tensor `in0`); which = 1/2: same-resolution inputs.  dst is overwritten or
+ * accumulated into. */
+int effdet_fuse_backward_input(const void *df, int which, int mode0, const void *in0, const float *w,
+                               int n_inputs, float eps, void *dst, int accumulate, int B, int H,
+                               int W, int C, int dtype, void *stream);
+/* dw_i = [w_i > 0] * sum(df * (in_i - f)) / (sum relu(w) + eps); partial: 4*1184 floats. */
+int effdet_fuse_backward_weights(const void *df, const void *f, const void *in0, int mode0,
+                                 const void *in1, const void *in2, const float *w, float eps,
+                                 float *dw, float *partial, int B, int H, int W, int C, int dtype,
+                                 void *stream);
+
+/* Dense-convolution weight gradient (cuDNN bwd-filter in the reference's TF graph):
+ * dweight (kh,kw,Cin,Cout) f32 (+)= sum over groups/pixels x (*) dz.  dz may be strided (head
+ * outputs inside the concatenated tensors).  partial: n_splits*kh*kw*Cin*Cout floats with
+ * n_splits = effdet_conv_wgrad_splits(desc). */
+typedef struct effdet_wgrad_desc {
+    int n_groups;
+    const void *x[EFFDET_MAX_GROUPS];   /* (B,H,W,Cin) x_dtype, dense */
+    const void *dz[EFFDET_MAX_GROUPS];  /* (B,Ho,Wo,Cout) dz_dtype */
+    int H[EFFDET_MAX_GROUPS], W[EFFDET_MAX_GROUPS];
+    int dz_ld[EFFDET_MAX_GROUPS];
+    long long dz_batch_stride[EFFDET_MAX_GROUPS];
+    int B, Cin, Cout, kh, kw, stride;
+    float *dweight;
+    float *partial;
+    int n_splits;
+    int accumulate;
+    int x_dtype, dz_dtype;
+} effdet_wgrad_desc;
+int effdet_conv_wgrad_splits(const effdet_wgrad_desc *desc);
+int effdet_conv_wgrad(const effdet_wgrad_desc *desc, void *stream);
+/* Data gradient of a strided (stride 2) 1x1/3x3 SAME convolution; weight is the forward HWIO
+ * kernel.  Stride-1 data gradients use effdet_conv2d on effdet_conv_weight_transpose'd weights. */
+int effdet_conv_dgrad_strided(const void *dz, const float *weight, void *dx, int accumulate, int B,
+                              int H, int W, int Cin, int Cout, int k, int stride, int dtype,
+                              void *stream);
+/* (taps,Cin,Cout) -> spatially flipped (taps,Cout,Cin): the kernel of the data-gradient conv. */
+int effdet_conv_weight_transpose(const float *in, float *out, int taps, int Cin, int Cout,
+                                 void *stream);
+/* (taps, n) -> spatially flipped (depthwise data-gradient kernel). */
+int effdet_flip_taps(const float *in, float *out, int taps, int n, void *stream);
+
+/* keras SGD(lr, decay, momentum) of train_tpu.py:268-269 on a flat fp32 range:
+ * v = momentum*v - lr_t*(g*grad_scale); w += v, lr_t = lr/(1+decay*iterations) from the caller. */
+int effdet_sgd_momentum_step(float *w, const float *g, float *v, size_t n, float lr_t,
+                             float momentum, float grad_scale, void *stream);
 
 #ifdef __cplusplus
 }

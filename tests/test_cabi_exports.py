@@ -28,7 +28,10 @@ def test_python_binding_covers_header():
     from efficientdet_b200 import _lib
     _lib.load()
     bound = set(_lib._SIGNATURES) | {"effdet_last_error", "effdet_version", "effdet_launch_count",
-                                     "effdet_filter_detections_workspace_size"}
+                                     "effdet_filter_detections_workspace_size",
+                                     "effdet_detection_losses_workspace_size",
+                                     "effdet_colreduce_blocks", "effdet_dw_wgrad_blocks",
+                                     "effdet_conv_wgrad_splits", "effdet_dwconv_se_blocks"}
     missing = [n for n in _declared() if n not in bound]
     assert not missing, missing
 
