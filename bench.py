@@ -29,7 +29,7 @@ WORKLOADS = {
     "d0_train_b32": ("train", 0, 32, 20, "bf16", False),
     "d4_train_b8": ("train", 4, 8, 90, "bf16", False),
 }
-DEFAULT_WORKLOAD = "d0_infer_b32"
+DEFAULT_WORKLOAD = "d0_train_b32"   # BASELINE.json configs[1]
 
 
 def peaks():

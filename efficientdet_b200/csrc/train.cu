@@ -409,7 +409,8 @@ fuse_bwd_kernel(const T *__restrict__ df, int which, int mode0, const T *__restr
     }
 }
 
-// partial[blk][4] = { sum df*in0r, sum df*in1, sum df*in2, sum df*f }
+// partial[blk][4] = { sum df*(in0r - f), sum df*(in1 - f), sum df*(in2 - f), unused }
+// (the difference is formed per element: subtracting two large sums would cancel badly)
 template <typename T, int CV>
 __global__ void __launch_bounds__(256)
 fuse_wgrad_kernel(const T *__restrict__ df, const T *__restrict__ f, const T *__restrict__ in0,
@@ -425,22 +426,20 @@ fuse_wgrad_kernel(const T *__restrict__ df, const T *__restrict__ f, const T *__
         const int cv = (int)(i % nvec), c = cv * CV;
         const size_t pix = i / nvec;
         const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((size_t)W * H));
-        float g[CV], a[CV], v[CV];
+        float g[CV], a[CV], v[CV], ff[CV];
         VecT<T, CV>::load(df + pix * C + c, g);
+        VecT<T, CV>::load(f + pix * C + c, ff);
         load_resampled<T, CV>(in0 + (size_t)b * H0 * W0 * C, mode0, y, x, W0, C, c, a);
 #pragma unroll
-        for (int k = 0; k < CV; ++k) s[0] = fmaf(g[k], a[k], s[0]);
+        for (int k = 0; k < CV; ++k) s[0] = fmaf(g[k], a[k] - ff[k], s[0]);
         VecT<T, CV>::load(in1 + pix * C + c, v);
 #pragma unroll
-        for (int k = 0; k < CV; ++k) s[1] = fmaf(g[k], v[k], s[1]);
+        for (int k = 0; k < CV; ++k) s[1] = fmaf(g[k], v[k] - ff[k], s[1]);
         if (in2) {
             VecT<T, CV>::load(in2 + pix * C + c, v);
 #pragma unroll
-            for (int k = 0; k < CV; ++k) s[2] = fmaf(g[k], v[k], s[2]);
+            for (int k = 0; k < CV; ++k) s[2] = fmaf(g[k], v[k] - ff[k], s[2]);
         }
-        VecT<T, CV>::load(f + pix * C + c, v);
-#pragma unroll
-        for (int k = 0; k < CV; ++k) s[3] = fmaf(g[k], v[k], s[3]);
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -466,8 +465,7 @@ __global__ void fuse_wgrad_finalize_kernel(const float *__restrict__ partial, in
         for (int j = 0; j < 4; ++j) s[j] += (double)partial[(size_t)b * 4 + j];
     float D = eps;
     for (int i = 0; i < n_in; ++i) D += fmaxf(fw[i], 0.f);
-    for (int i = 0; i < n_in; ++i)
-        dw[i] = fw[i] > 0.f ? (float)((s[i] - s[3]) / (double)D) : 0.f;
+    for (int i = 0; i < n_in; ++i) dw[i] = fw[i] > 0.f ? (float)(s[i] / (double)D) : 0.f;
 }
 
 // ------------------------------------------------------------------ optimiser

@@ -264,6 +264,17 @@ class Model:
             names += ["boxes", "clipped_boxes"] + (["filtered_detections"] if outputs == "detections" else [])
         self.layers = [LayerRef(net, n) for n in names]
 
+    @property
+    def backbone_depth(self):
+        """Index one past the last backbone layer in `layers` (== EFFICIENTNET_DEPTHS[phi] for the
+        default drop_connect_rate; smaller when drop_connect_rate=0 removes the `*_drop` layers)."""
+        return 1 + len(self.net.backbone.keras_layer_names())
+
+    def freeze_backbone(self):
+        """train_tpu.py:272-274 / train.py:336-339 `--freeze-backbone`."""
+        for i in range(1, self.backbone_depth):
+            self.layers[i].trainable = False
+
     # ---------------------------------------------------------------- inference
     def _stage(self, images):
         """host numpy -> pinned staging buffer -> device (async)."""

@@ -41,7 +41,7 @@ def loss_and_grads(W, images, reg_t, lab_t, phi, num_classes, weighted=False, fr
     sl = losses.smooth_l1(torch.as_tensor(reg_t).to(dtype), reg)
     (fl + sl).backward()
     grads = {k: Wt[k].grad.detach().numpy() for k in keys if Wt[k].grad is not None}
-    return float(fl), float(sl), grads, {k: (m.numpy(), v.numpy()) for k, (m, v) in stats.items()}
+    return float(fl.detach()), float(sl.detach()), grads, {k: (m.numpy(), v.numpy()) for k, (m, v) in stats.items()}
 
 
 def sgd_step(W, grads, velocity, lr=0.01, decay=4e-5, momentum=0.9, iteration=0):

@@ -65,22 +65,256 @@ def test_losses_fwd_bwd():
         assert abs(o[1] - float(sl)) / float(sl) < 1e-4
         assert o[2] == (state == 1).sum()
         g = dcls.cpu().numpy()
-        skip = np.zeros_like(g, bool); skip[0, :4, 0] = True      # clip boundary points
+        # clip boundary points, and p == 0.5 exactly where autograd's sub-gradient of max/abs at
+        # z = 0 differs from the analytic derivative
+        skip = np.zeros_like(g, bool); skip[0, :5, 0] = True
         assert rel_err(g[~skip], want_dlogit[~skip]) < 1e-4
         assert rel_err(dreg.cpu().numpy(), rt.grad.numpy()) < 1e-5
 
 
+def _d(a, dt=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dt)
+
+
+def _nchw(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).permute(0, 3, 1, 2).contiguous().double()
+
+
+# ------------------------------------------------------------------ backward kernels, one by one
+def test_conv_wgrad_grouped_and_strided_dz():
+    import ctypes
+    from efficientdet_b200 import _lib
+    from oracle import graph
+    rng = np.random.default_rng(0)
+    lib = _lib.load()
+    for (k, stride, cin, cout, Hs, B) in [(3, 1, 64, 36, [8, 4, 2], 3), (1, 1, 40, 64, [6], 2),
+                                           (3, 2, 64, 64, [8], 2), (3, 1, 24, 810, [4, 2], 2)]:
+        w = torch.zeros((k, k, cin, cout), dtype=torch.float64, requires_grad=True)
+        xs, dzs, total = [], [], 0
+        for H in Hs:
+            Ho = (H + stride - 1) // stride
+            xs.append(rng.standard_normal((B, H, H, cin)).astype(np.float32))
+            dzs.append(rng.standard_normal((B, Ho, Ho, cout)).astype(np.float32))
+            y = graph.conv2d(_nchw(xs[-1]), w, stride)
+            total = total + (y * _nchw(dzs[-1])).sum()
+        total.backward()
+        # dz packed like the concatenated head outputs: (B, sum HoWo, cout)
+        cat = np.concatenate([z.reshape(B, -1, cout) for z in dzs], 1)
+        catd = _d(cat)
+        d = _lib.WgradDesc()
+        d.n_groups = len(Hs)
+        keep, off = [], 0
+        for i, H in enumerate(Hs):
+            xd = _d(xs[i]); keep.append(xd)
+            Ho = (H + stride - 1) // stride
+            d.x[i] = xd.data_ptr(); d.dz[i] = catd.data_ptr() + off * cout * 4
+            d.H[i] = d.W[i] = H
+            d.dz_ld[i] = cout; d.dz_batch_stride[i] = cat.shape[1] * cout
+            off += Ho * Ho
+        d.B, d.Cin, d.Cout, d.kh, d.kw, d.stride = B, cin, cout, k, k, stride
+        ns = lib.effdet_conv_wgrad_splits(ctypes.byref(d))
+        assert ns > 0
+        part = torch.empty(ns * k * k * cin * cout, device="cuda")
+        out = torch.full((k, k, cin, cout), float("nan"), device="cuda")
+        d.dweight, d.partial, d.n_splits, d.accumulate = out.data_ptr(), part.data_ptr(), ns, 0
+        d.x_dtype = d.dz_dtype = _lib.F32
+        _lib.call("effdet_conv_wgrad", ctypes.byref(d), _lib.stream_ptr())
+        assert rel_err(out.cpu().numpy(), w.grad.numpy()) < 1e-5, (k, stride, cin, cout)
+
+
+def test_conv_dgrad_via_transposed_weights_and_strided():
+    import ctypes
+    from efficientdet_b200 import _lib
+    from oracle import graph
+    rng = np.random.default_rng(1)
+    B = 3
+    for (k, stride, cin, cout, H) in [(3, 1, 64, 64, 8), (1, 1, 64, 88, 5), (3, 2, 64, 64, 8),
+                                      (3, 2, 320, 64, 4)]:
+        w = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+        Ho = (H + stride - 1) // stride
+        dz = rng.standard_normal((B, Ho, Ho, cout)).astype(np.float32)
+        x = torch.tensor(rng.standard_normal((B, cin, H, H)), dtype=torch.float64, requires_grad=True)
+        graph.conv2d(x, w.astype(np.float64), stride).backward(_nchw(dz))
+        want = x.grad.permute(0, 2, 3, 1).numpy()
+        wd, dzd = _d(w), _d(dz)
+        prev = rng.standard_normal((B, H, H, cin)).astype(np.float32)
+        mask = rng.standard_normal((B, H, H, cin)).astype(np.float32)
+        if stride == 1:
+            wt = torch.empty(k * k * cin * cout, device="cuda")
+            _lib.call("effdet_conv_weight_transpose", wd.data_ptr(), wt.data_ptr(), k * k, cin, cout,
+                      _lib.stream_ptr())
+            out, md = _d(prev), _d(mask)
+            d = _lib.ConvDesc()
+            d.n_groups = 1
+            d.x[0], d.y[0], d.residual[0], d.relu_mask[0] = dzd.data_ptr(), out.data_ptr(), out.data_ptr(), md.data_ptr()
+            d.H[0] = d.W[0] = H
+            d.B, d.Cin, d.Cout, d.kh, d.kw, d.stride = B, cout, cin, k, k, 1
+            d.weight = wt.data_ptr()
+            d.in_dtype = d.out_dtype = _lib.F32
+            _lib.call("effdet_conv2d", ctypes.byref(d), _lib.stream_ptr())
+            assert rel_err(out.cpu().numpy(), want * (mask > 0) + prev) < 1e-5
+        else:
+            out = _d(prev)
+            _lib.call("effdet_conv_dgrad_strided", dzd.data_ptr(), wd.data_ptr(), out.data_ptr(), 1, B, H, H,
+                      cin, cout, k, stride, _lib.F32, _lib.stream_ptr())
+            assert rel_err(out.cpu().numpy(), want + prev) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_bn_train_forward_backward(dtype):
+    from efficientdet_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(2)
+    rows, C = 4 * 12 * 12, 88
+    tdt = torch.float32 if dtype == "fp32" else torch.bfloat16
+    dt = _lib.F32 if dtype == "fp32" else _lib.BF16
+    zd = _d(rng.standard_normal((rows, C)).astype(np.float32) * 1.5 + 0.3, tdt)
+    dyd = _d(rng.standard_normal((rows, C)).astype(np.float32), tdt)
+    gamma = rng.uniform(0.5, 1.5, C).astype(np.float32); beta = rng.normal(0, 0.2, C).astype(np.float32)
+    mm0 = rng.normal(0, 0.1, C).astype(np.float32); mv0 = rng.uniform(0.5, 1.5, C).astype(np.float32)
+    g_, b_, mm, mv = _d(gamma), _d(beta), _d(mm0), _d(mv0)
+    sc, sh, mu, iv = (torch.empty(C, device="cuda") for _ in range(4))
+    nblk = lib.effdet_colreduce_blocks(rows, C, dt)
+    part = torch.empty(2 * C * nblk, device="cuda")
+    _lib.call("effdet_bn_train_stats", zd.data_ptr(), rows, C, g_.data_ptr(), b_.data_ptr(), 1e-4, 0.997,
+              mm.data_ptr(), mv.data_ptr(), sc.data_ptr(), sh.data_ptr(), mu.data_ptr(), iv.data_ptr(),
+              part.data_ptr(), nblk, dt, _lib.stream_ptr())
+    yd = torch.empty_like(zd)
+    _lib.call("effdet_scale_shift_act", zd.data_ptr(), sc.data_ptr(), sh.data_ptr(), yd.data_ptr(), rows, C,
+              _lib.ACT_RELU, dt, _lib.stream_ptr())
+    z = zd.double().cpu().requires_grad_(True)
+    gt, bt = torch.tensor(gamma, dtype=torch.float64, requires_grad=True), torch.tensor(beta, dtype=torch.float64, requires_grad=True)
+    m, v = z.mean(0), z.var(0, unbiased=False)
+    y = torch.relu((z - m) / torch.sqrt(v + 1e-4) * gt + bt)
+    tol = 1e-5 if dtype == "fp32" else 1e-2
+    assert rel_err(yd.double().cpu().numpy(), y.detach().numpy()) < tol
+    assert rel_err(mm.cpu().numpy(), mm0 * 0.997 + m.detach().numpy() * 0.003) < 1e-5
+    assert rel_err(mv.cpu().numpy(), mv0 * 0.997 + z.var(0, unbiased=True).detach().numpy() * 0.003) < 1e-5
+    # backward uses the GPU's own y as the ReLU mask (no mask flips between implementations)
+    ymask = (yd.double().cpu() > 0).double()
+    ((z - m) / torch.sqrt(v + 1e-4) * gt + bt).backward(dyd.double().cpu() * ymask)
+    dz = torch.empty_like(zd); k123 = torch.empty(3 * C, device="cuda")
+    dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    _lib.call("effdet_bn_relu_backward", dyd.data_ptr(), yd.data_ptr(), zd.data_ptr(), rows, C, g_.data_ptr(),
+              mu.data_ptr(), iv.data_ptr(), None, dg.data_ptr(), db.data_ptr(), dz.data_ptr(), k123.data_ptr(),
+              part.data_ptr(), nblk, dt, _lib.stream_ptr())
+    assert rel_err(dz.double().cpu().numpy(), z.grad.numpy()) < (1e-4 if dtype == "fp32" else 2e-2)
+    assert rel_err(dg.cpu().numpy(), gt.grad.numpy()) < (1e-4 if dtype == "fp32" else 2e-2)
+    assert rel_err(db.cpu().numpy(), bt.grad.numpy()) < (1e-4 if dtype == "fp32" else 2e-2)
+    # frozen (inference-mode) BN: dz = scale * dy * [y > 0]
+    _lib.call("effdet_bn_relu_backward", dyd.data_ptr(), yd.data_ptr(), zd.data_ptr(), rows, C, g_.data_ptr(),
+              None, None, sc.data_ptr(), None, None, dz.data_ptr(), k123.data_ptr(), part.data_ptr(), 1, dt,
+              _lib.stream_ptr())
+    want = dyd.double().cpu() * ymask * sc.double().cpu()
+    assert rel_err(dz.double().cpu().numpy(), want.numpy()) < (1e-6 if dtype == "fp32" else 1e-2)
+
+
+@pytest.mark.parametrize("mode,three,weighted", [(1, False, True), (2, True, True), (2, False, False),
+                                                 (1, False, False), (2, True, False)])
+def test_fusion_and_depthwise_backward(mode, three, weighted):
+    from efficientdet_b200 import _lib
+    from oracle import graph
+    lib = _lib.load()
+    rng = np.random.default_rng(3 + mode)
+    B, H, C = 2, 8, 88
+    H0 = {1: H // 2, 2: H * 2}[mode]
+    a = torch.tensor(rng.standard_normal((B, C, H0, H0)), dtype=torch.float64, requires_grad=True)
+    b = torch.tensor(rng.standard_normal((B, C, H, H)), dtype=torch.float64, requires_grad=True)
+    c = torch.tensor(rng.standard_normal((B, C, H, H)), dtype=torch.float64, requires_grad=True) if three else None
+    fw = torch.tensor([0.7, -0.1, 0.4][:3 if three else 2], dtype=torch.float64, requires_grad=True)
+    dw = torch.tensor(rng.standard_normal((3, 3, C, 1)) / 3, dtype=torch.float64, requires_grad=True)
+    ra = graph.upsample2(a) if mode == 1 else graph.maxpool2(a)
+    f = graph.fuse([ra, b] + ([c] if three else []), {"f/f": fw}, weighted, "f")
+    f.retain_grad()
+    z = graph.dwconv2d(f, dw, 1)
+    dzn = rng.standard_normal((B, H, H, C)).astype(np.float32)
+    z.backward(_nchw(dzn))
+    nhwc = lambda t: t.detach().permute(0, 2, 3, 1).contiguous().numpy().astype(np.float32)
+    ad, bd, cd = _d(nhwc(a)), _d(nhwc(b)), (_d(nhwc(c)) if three else None)
+    fwd_ = _d(fw.detach().numpy().astype(np.float32))
+    fwp = fwd_.data_ptr() if weighted else None
+    fd = torch.empty((B, H, H, C), device="cuda")
+    _lib.call("effdet_resample_fuse", ad.data_ptr(), mode, bd.data_ptr(), cd.data_ptr() if three else None, fwp,
+              1e-4, fd.data_ptr(), B, H, H, C, _lib.F32, _lib.stream_ptr())
+    assert rel_err(fd.cpu().numpy(), nhwc(f)) < 1e-6
+    dzd = _d(dzn)
+    # depthwise weight gradient
+    nblk = lib.effdet_dw_wgrad_blocks(B, H, H, C, _lib.F32)
+    part = torch.empty(9 * C * nblk, device="cuda"); dk = torch.empty((3, 3, C), device="cuda")
+    _lib.call("effdet_dw_wgrad", fd.data_ptr(), dzd.data_ptr(), B, H, H, C, dk.data_ptr(), part.data_ptr(), nblk,
+              _lib.F32, _lib.stream_ptr())
+    assert rel_err(dk.cpu().numpy(), dw.grad.numpy()[..., 0]) < 1e-5
+    # depthwise data gradient = depthwise conv with the flipped kernel
+    dwd = _d(dw.detach().numpy().astype(np.float32)); flip = torch.empty(9 * C, device="cuda")
+    _lib.call("effdet_flip_taps", dwd.data_ptr(), flip.data_ptr(), 9, C, _lib.stream_ptr())
+    ones, zeros = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+    dfd = torch.empty((B, H, H, C), device="cuda")
+    _lib.call("effdet_dwconv", dzd.data_ptr(), flip.data_ptr(), ones.data_ptr(), zeros.data_ptr(), dfd.data_ptr(),
+              None, 0, B, H, H, C, 3, 1, _lib.ACT_NONE, _lib.F32, _lib.stream_ptr())
+    assert rel_err(dfd.cpu().numpy(), nhwc(f.grad)) < 1e-5
+    # fusion weights
+    if weighted:
+        fpart = torch.empty(4 * 148 * 8, device="cuda"); dfw = torch.empty(3, device="cuda")
+        _lib.call("effdet_fuse_backward_weights", dfd.data_ptr(), fd.data_ptr(), ad.data_ptr(), mode, bd.data_ptr(),
+                  cd.data_ptr() if three else None, fwp, 1e-4, dfw.data_ptr(), fpart.data_ptr(), B, H, H, C,
+                  _lib.F32, _lib.stream_ptr())
+        n_in = 3 if three else 2
+        # with one active weight in_0 - f is a difference of nearly equal numbers: fp32 leaves
+        # ~1e-3 relative accuracy in that (tiny) gradient
+        assert rel_err(dfw.cpu().numpy()[:n_in], fw.grad.numpy()) < 2e-3
+    # inputs (overwrite, then accumulate on top of existing content)
+    n_in = 3 if three else 2
+    for which, src in enumerate([a, b, c][:n_in]):
+        want = nhwc(src.grad)
+        dst = torch.full(want.shape, float("nan"), device="cuda")
+        args = (dfd.data_ptr(), which, mode, ad.data_ptr(), fwp, n_in, 1e-4, dst.data_ptr())
+        _lib.call("effdet_fuse_backward_input", *args, 0, B, H, H, C, _lib.F32, _lib.stream_ptr())
+        assert rel_err(dst.cpu().numpy(), want) < 1e-5, which
+        _lib.call("effdet_fuse_backward_input", *args, 1, B, H, H, C, _lib.F32, _lib.stream_ptr())
+        assert rel_err(dst.cpu().numpy(), 2 * want) < 1e-5, which
+
+
+def test_colsum_fold_and_sgd():
+    from efficientdet_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((600, 810)).astype(np.float32)          # 810 % 4 != 0 -> fold 2
+    xd = _d(x)
+    nblk = lib.effdet_colreduce_blocks(300, 1620, _lib.F32)
+    part = torch.empty(2 * 1620 * nblk, device="cuda"); out = torch.ones(810, device="cuda")
+    _lib.call("effdet_colsum", xd.data_ptr(), 300, 1620, 2, out.data_ptr(), 1, part.data_ptr(), nblk, _lib.F32,
+              _lib.stream_ptr())
+    assert rel_err(out.cpu().numpy(), 1 + x.astype(np.float64).sum(0)) < 1e-5
+    n = 100003
+    w, g, v = (rng.standard_normal(n).astype(np.float32) for _ in range(3))
+    wd, gd, vd = _d(w), _d(g), _d(v)
+    _lib.call("effdet_sgd_momentum_step", wd.data_ptr(), gd.data_ptr(), vd.data_ptr(), n, 0.01 / (1 + 4e-5 * 7), 0.9,
+              0.5, _lib.stream_ptr())
+    from oracle import losses
+    wt, vt = torch.tensor(w, dtype=torch.float64), torch.tensor(v, dtype=torch.float64)
+    losses.sgd_momentum_step(wt, torch.tensor(g, dtype=torch.float64) * 0.5, vt, 0.01, 4e-5, 0.9, 7)
+    assert rel_err(wd.cpu().numpy(), wt.numpy()) < 1e-6 and rel_err(vd.cpu().numpy(), vt.numpy()) < 1e-6
+
+
+# ------------------------------------------------------------------ whole step
 @pytest.mark.parametrize("weighted,freeze_bn", [(False, False), (True, False), (True, True)])
 def test_training_step_gradients(weighted, freeze_bn):
+    """End to end against the fp64 autograd oracle.  Per-tensor relative L2 <= 5e-2: the oracle
+    itself moves by up to ~1e-2 (L2) between fp32 and fp64 on this network because a handful of the
+    ~10^7 ReLU units sit within rounding distance of zero and the detection gradients are carried
+    by few positive anchors (measured in scratch/dbg_cond.py); the kernels themselves are pinned
+    much tighter by the single-kernel tests above, which share the ReLU masks."""
     from efficientdet_b200.model import efficientdet, EFFICIENTNET_DEPTHS
     from efficientdet_b200.optimizers import SGD
     from efficientdet_b200.utils.tpu import tpu_focal, tpu_smooth_l1
     from oracle import train as otrain
-    size, C, B, phi = 128, 5, 4, 0
+    from util_model import rel_l2
+    size, C, B, phi = 256, 5, 8, 0
     model = efficientdet(phi, num_classes=C, weighted_bifpn=weighted, freeze_bn=freeze_bn,
                          image_size=size, dtype="fp32", drop_connect_rate=0, just_training_model=True)
     W0 = perturb_weights(model)
-    for i in range(1, EFFICIENTNET_DEPTHS[phi]):
+    assert EFFICIENTNET_DEPTHS[phi] == 227
+    for i in range(1, model.backbone_depth):     # == EFFICIENTNET_DEPTHS minus the *_drop layers
         model.layers[i].trainable = False
     model.compile(optimizer=SGD(lr=0.01, decay=4e-5, momentum=0.9),
                   loss={"regression": tpu_smooth_l1(), "classification": tpu_focal(alpha=0.25, gamma=1.5)})
@@ -89,37 +323,40 @@ def test_training_step_gradients(weighted, freeze_bn):
     img = rng.standard_normal((B, size, size, 3)).astype(np.float32)
     total, l_reg, l_cls = model.train_on_batch(img, [reg_t, lab_t])
     fl, sl, grads, stats = otrain.loss_and_grads(W0, img, reg_t, lab_t, phi, C, weighted, freeze_bn)
-    assert abs(l_cls - fl) / fl < 1e-3, (l_cls, fl)
-    assert abs(l_reg - sl) / max(sl, 1e-9) < 1e-3, (l_reg, sl)
+    assert abs(l_cls - fl) / fl < 1e-4, (l_cls, fl)
+    assert abs(l_reg - sl) / max(sl, 1e-9) < 1e-4, (l_reg, sl)
     net = model.net
     bad = {}
     for k, g in grads.items():
         got = net.grads[k].cpu().numpy()
-        scale = max(np.abs(g).max(), 1e-12)
-        e = np.abs(got - g).max() / scale
-        if not e < 2e-3:
-            bad[k] = (float(e), float(scale))
+        if np.abs(g).max() < 1e-12:
+            continue
+        e = rel_l2(got, g)
+        # fusion-weight gradients are global sums with heavy cancellation: looser bound
+        if not e < (0.2 if k.startswith("w_bi_fpn_add") else 5e-2):
+            bad[k] = float(e)
     assert not bad, bad
-    # SGD: w1 = w0 + v, v = -lr*g (first step, zero velocity)
+    # SGD: first step from zero velocity: w1 = w0 - lr * g  (checked with the GPU's own gradients)
     W1 = model.get_weights_dict()
-    for k in list(grads)[:50]:
-        want = W0[k] - 0.01 * grads[k]
-        assert rel_err(W1[k], want) < 1e-4, k
+    for k in list(grads)[:60]:
+        want = W0[k].astype(np.float64) - 0.01 * net.grads[k].cpu().numpy()
+        assert rel_err(W1[k], want) < 1e-5, k
     # BN moving averages follow momentum .997 with the batch statistics (training-mode BN only)
     if not freeze_bn:
-        for name, (m, v) in list(stats.items())[:10]:
+        for name, (m, v) in list(stats.items())[:12]:
             want_m = W0[name + "/moving_mean"] * 0.997 + m * 0.003
             want_v = W0[name + "/moving_variance"] * 0.997 + v * 0.003
             assert rel_err(W1[name + "/moving_mean"], want_m) < 1e-4, name
             assert rel_err(W1[name + "/moving_variance"], want_v) < 1e-4, name
+    else:
+        assert np.array_equal(W1["BiFPN_0_P3_bn/gamma"], W0["BiFPN_0_P3_bn/gamma"])
     # backbone untouched
     assert np.array_equal(W1["stem_conv/kernel"], W0["stem_conv/kernel"])
-    # compact device targets give the same step
+    # compact device targets give the same step (bit-identical: the step is deterministic)
     model2 = efficientdet(phi, num_classes=C, weighted_bifpn=weighted, freeze_bn=freeze_bn,
                           image_size=size, dtype="fp32", drop_connect_rate=0, just_training_model=True)
     model2.set_weights_dict(W0)
-    for i in range(1, EFFICIENTNET_DEPTHS[phi]):
-        model2.layers[i].trainable = False
+    model2.freeze_backbone()
     model2.compile(optimizer=SGD(lr=0.01, decay=4e-5, momentum=0.9))
     from efficientdet_b200.utils.anchors import anchor_targets_device
     r, _, st, cl = anchor_targets_device(anchors, [(size, size, 3)] * B, ann, C, dense_labels=False,
