@@ -47,6 +47,8 @@ _SIGNATURES = {
     "effdet_stem_conv": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                          c_int, c_int, c_void_p],
     "effdet_conv2d": [c_void_p, c_void_p],
+    "effdet_conv_weight_panel": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                 c_void_p],
     "effdet_dwconv": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                       c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "effdet_se_gate": [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -108,7 +110,7 @@ class ConvDesc(ctypes.Structure):
         ("weight", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("gate", c_void_p),
         ("keep", c_void_p),
         ("act", c_int), ("in_dtype", c_int), ("out_dtype", c_int),
-        ("weight_bf16", c_void_p), ("allow_tensor_core", c_int),
+        ("weight_bf16", c_void_p), ("allow_tensor_core", c_int), ("weight_per_sample", c_int),
     ]
 
 
@@ -149,6 +151,10 @@ def load():
     lib.effdet_dw_wgrad_blocks.argtypes = [c_int, c_int, c_int, c_int, c_int]
     lib.effdet_conv_wgrad_splits.restype = c_int
     lib.effdet_conv_wgrad_splits.argtypes = [c_void_p]
+    lib.effdet_conv_tc_block_n.restype = c_int
+    lib.effdet_conv_tc_block_n.argtypes = [c_int]
+    lib.effdet_conv_weight_panel_elems.restype = c_size_t
+    lib.effdet_conv_weight_panel_elems.argtypes = [c_int, c_int, c_int]
     lib.effdet_dwconv_se_blocks.restype = c_int
     lib.effdet_dwconv_se_blocks.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int]
     for name, args in _SIGNATURES.items():

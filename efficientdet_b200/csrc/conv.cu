@@ -272,13 +272,20 @@ extern "C" int effdet_stem_conv(const float *images, const float *kernel, const 
     return fail(EFFDET_E_INVALID, "effdet_stem_conv: bad dtype%s", "");
 }
 
+int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream);     // conv_tc.cu
+
 extern "C" int effdet_conv2d(const effdet_conv_desc *d, void *stream) {
     EFFDET_REQUIRE(d, "null descriptor");
     EFFDET_REQUIRE(d->n_groups >= 1 && d->n_groups <= kMaxGroups, "1..5 groups");
     EFFDET_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0, "bad sizes");
     EFFDET_REQUIRE((d->kh == 1 && d->kw == 1) || (d->kh == 3 && d->kw == 3), "kernel 1x1 or 3x3");
     EFFDET_REQUIRE(d->stride == 1 || d->stride == 2, "stride 1 or 2");
-    EFFDET_REQUIRE(d->weight, "null weight");
+    EFFDET_REQUIRE(d->weight || d->weight_bf16, "null weight");
+    if (d->allow_tensor_core && d->weight_bf16) {
+        const int rc = effdet_conv2d_tc(d, stream);
+        if (rc != EFFDET_E_UNSUPPORTED) return rc;
+    }
+    EFFDET_REQUIRE(d->weight, "shape not supported by the tensor-core path and no fp32 weight given");
     ConvParams p;
     memset(&p, 0, sizeof(p));
     p.n_groups = d->n_groups; p.B = d->B; p.Cin = d->Cin; p.Cout = d->Cout;

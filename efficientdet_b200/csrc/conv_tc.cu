@@ -1,0 +1,463 @@
+// Tensor-core convolution for sm_100a: implicit GEMM on tcgen05.mma with the accumulator in
+// TMEM, operands staged in shared memory by TMA (SWIZZLE_128B), warp-specialised
+// producer / MMA-issuer / epilogue roles synchronised with mbarriers.
+//
+//   D[M = 128 pixels, N = Cout tile] += A[128 pixels, 64 channels] * B[Cout tile, 64 channels]^T
+//
+// A tile  = one TMA box of a 4-D NHWC tensor map (C, W, H, B): box (64, Wt, Ht, Bt), Wt*Ht*Bt = 128.
+//           For a 3x3 convolution the box origin is shifted by the tap offset; TMA's out-of-bounds
+//           zero fill IS the TF "SAME" zero padding, so there is no im2col buffer.  The K loop
+//           runs over taps x 64-channel blocks.
+// B tile  = TMA box (64, BLOCK_N, 1) of the bf16 weight panel (Kpad, Npad, taps | samples).
+// Epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> scale/shift (folded BN or bias),
+//           activation, ReLU-mask (data-gradient use), drop-connect scale + residual ->
+//           bf16 / fp32 stores at per-group row / image strides (concat-free head outputs).
+//
+// Replaces the cuDNN calls behind efficientnet.py:228-237/289-304 (1x1 expand / project),
+// model.py:71-90 (BiFPN 1x1 laterals), model.py:293-309/324-351 (3x3 head convs, all five pyramid
+// levels in one launch) and their data gradients.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace effdet {
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                            int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+          "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
+                                            int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+          "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+// rows are 128-byte lines (64 bf16), 8-row groups are 1024 bytes apart (SBO), LBO = 1 (unused).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+constexpr int kTcMaxGroups = 5;
+constexpr int kTileM = 128, kTileK = 64;
+constexpr int kATileBytes = kTileM * kTileK * 2;   // 16 KiB
+
+struct TcGroup {
+    void *y;
+    const void *res;
+    const void *mask;
+    long long y_batch_stride;
+    int ldc;
+    int H, W;
+    int Wt, Ht, Bt;           // tile extent (Wt*Ht*Bt == 128)
+    int tiles_x, tiles_y, tiles_b;
+    int tile_begin;
+};
+struct alignas(64) TcParams {
+    CUtensorMap a_map[kTcMaxGroups];
+    CUtensorMap b_map;
+    TcGroup g[kTcMaxGroups];
+    int n_groups, B, Cout, ksize, kblocks_per_tap, block_n, stages, tmem_cols;
+    int act, out_f32, b_per_sample;
+    const float *scale, *shift, *keep;
+};
+
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_tile_bytes = p.block_n * kTileK * 2;
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + (size_t)p.stages * kATileBytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sB + (size_t)p.stages * b_tile_bytes);
+    uint64_t *empty = full + p.stages;
+    uint64_t *tmem_full = empty + p.stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- which group / tile
+    int gi = 0;
+#pragma unroll
+    for (int i = 1; i < kTcMaxGroups; ++i)
+        if (i < p.n_groups && (int)blockIdx.x >= p.g[i].tile_begin) gi = i;
+    const TcGroup &G = p.g[gi];
+    int t = (int)blockIdx.x - G.tile_begin;
+    const int tx = t % G.tiles_x; t /= G.tiles_x;
+    const int ty = t % G.tiles_y; t /= G.tiles_y;
+    const int tb = t;
+    const int x0 = tx * G.Wt, y0 = ty * G.Ht, b0 = tb * G.Bt;
+    const int n0 = blockIdx.y * p.block_n;
+    const int pad = p.ksize / 2;
+    const int taps = p.ksize * p.ksize;
+    const int num_k = taps * p.kblocks_per_tap;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer
+            const CUtensorMap *amap = &p.a_map[gi];
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % p.stages, ph = (kb / p.stages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const int tap = kb / p.kblocks_per_tap, kc = (kb - tap * p.kblocks_per_tap) * kTileK;
+                const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+                mbar_expect_tx(&full[s], (uint32_t)(kATileBytes + b_tile_bytes));
+                tma_load_4d(sA + (size_t)s * kATileBytes, amap, &full[s], kc, x0 + kx - pad, y0 + ky - pad, b0);
+                tma_load_3d(sB + (size_t)s * b_tile_bytes, &p.b_map, &full[s], kc, n0,
+                            p.b_per_sample ? b0 : tap);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer (single thread)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+                                   ((uint32_t)(kTileM >> 4) << 24);
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % p.stages, ph = (kb / p.stages) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + (size_t)s * kATileBytes));
+                const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + (size_t)s * b_tile_bytes));
+#pragma unroll
+                for (int k = 0; k < kTileK / 16; ++k)      // UMMA_K = 16 bf16 = 32 bytes: +2 in the address field
+                    umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                              (kb | k) ? 1u : 0u);
+                umma_commit(&empty[s]);                     // frees the smem slot when the MMAs retire
+            }
+            umma_commit(tmem_full);                         // accumulator complete
+        }
+    } else {
+        // ===== epilogue: 4 warps, each owns the TMEM lane quarter (warp % 4)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                      // tile row == TMEM lane
+        const int xx = row % G.Wt, yy = (row / G.Wt) % G.Ht, bb = row / (G.Wt * G.Ht);
+        const int x = x0 + xx, y = y0 + yy, b = b0 + bb;
+        const bool row_ok = x < G.W && y < G.H && b < p.B;
+        const size_t base = (size_t)b * G.y_batch_stride + ((size_t)y * G.W + x) * G.ldc;
+        const float kp = (p.keep && row_ok) ? p.keep[b] : 1.f;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+            uint32_t r[32];
+            __syncwarp();                                   // tcgen05.ld is warp-collective
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            const int nbase = n0 + c0;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int n = nbase + j;
+                float a = __uint_as_float(r[j]);
+                if (n < p.Cout) {
+                    if (p.scale) a *= p.scale[n];
+                    if (p.shift) a += p.shift[n];
+                    a = activate_rt(a, p.act);
+                }
+                v[j] = a;
+            }
+            const int nvalid = row_ok ? min(32, min(p.Cout, n0 + p.block_n) - nbase) : 0;
+            if (nvalid <= 0) {
+                // nothing to store for this thread / chunk
+            } else if (p.out_f32) {
+                float *Y = static_cast<float *>(G.y) + base + nbase;
+                const float *R = G.res ? static_cast<const float *>(G.res) + base + nbase : nullptr;
+                const float *MK = G.mask ? static_cast<const float *>(G.mask) + base + nbase : nullptr;
+                for (int j = 0; j < nvalid; ++j) {
+                    float a = v[j];
+                    if (MK && !(MK[j] > 0.f)) a = 0.f;
+                    if (R) a = a * kp + R[j];
+                    Y[j] = a;
+                }
+            } else {
+                __nv_bfloat16 *Y = static_cast<__nv_bfloat16 *>(G.y) + base + nbase;
+                const __nv_bfloat16 *R = G.res ? static_cast<const __nv_bfloat16 *>(G.res) + base + nbase : nullptr;
+                const __nv_bfloat16 *MK = G.mask ? static_cast<const __nv_bfloat16 *>(G.mask) + base + nbase : nullptr;
+                const bool vec = nvalid == 32 && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
+                                 (!R || (reinterpret_cast<uintptr_t>(R) & 15) == 0) &&
+                                 (!MK || (reinterpret_cast<uintptr_t>(MK) & 15) == 0);
+                if (vec) {
+#pragma unroll
+                    for (int j8 = 0; j8 < 32; j8 += 8) {
+                        float o[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o[j] = v[j8 + j];
+                        if (MK) {
+                            uint4 mv = *reinterpret_cast<const uint4 *>(MK + j8);
+                            const __nv_bfloat162 *mh = reinterpret_cast<const __nv_bfloat162 *>(&mv);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (!(__low2float(mh[j]) > 0.f)) o[2 * j] = 0.f;
+                                if (!(__high2float(mh[j]) > 0.f)) o[2 * j + 1] = 0.f;
+                            }
+                        }
+                        if (R) {
+                            uint4 rv = *reinterpret_cast<const uint4 *>(R + j8);
+                            const __nv_bfloat162 *rh = reinterpret_cast<const __nv_bfloat162 *>(&rv);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                o[2 * j] = o[2 * j] * kp + __low2float(rh[j]);
+                                o[2 * j + 1] = o[2 * j + 1] * kp + __high2float(rh[j]);
+                            }
+                        }
+                        uint4 ov;
+                        __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&ov);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+                        *reinterpret_cast<uint4 *>(Y + j8) = ov;
+                    }
+                } else {
+                    for (int j = 0; j < nvalid; ++j) {
+                        float a = v[j];
+                        if (MK && !(__bfloat162float(MK[j]) > 0.f)) a = 0.f;
+                        if (R) a = a * kp + __bfloat162float(R[j]);
+                        Y[j] = __float2bfloat16_rn(a);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------ weight panels
+// mode 0 (forward):       panel[t][n = co][k = ci] = w[t][ci][co]
+// mode 1 (data gradient): panel[t][n = ci][k = co] = w[taps-1-t][ci][co]
+// gate != NULL (forward 1x1 only): per-sample panels panel[b][co][ci] = w[ci][co] * gate[b][ci]
+// (the squeeze-excite multiply of efficientnet.py:286 folded into the weights of project_conv)
+__global__ void __launch_bounds__(256)
+weight_panel_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ panel, int taps, int Cin,
+                    int Cout, int Kpad, int Npad, int mode, const float *__restrict__ gate, int nb) {
+    const size_t per = (size_t)Npad * Kpad;
+    const size_t total = (size_t)(gate ? nb : taps) * per;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int k = (int)(i % Kpad), n = (int)((i / Kpad) % Npad), z = (int)(i / per);
+        float v = 0.f;
+        if (mode == 0) {
+            if (k < Cin && n < Cout) {
+                if (gate) v = w[(size_t)k * Cout + n] * gate[(size_t)z * Cin + k];
+                else v = w[((size_t)z * Cin + k) * Cout + n];
+            }
+        } else {
+            if (k < Cout && n < Cin) v = w[((size_t)(taps - 1 - z) * Cin + n) * Cout + k];
+        }
+        panel[i] = __float2bfloat16_rn(v);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// picks (Wt, Ht, Bt) with Wt*Ht*Bt == 128 minimising the number of tiles
+static void pick_tile(int W, int H, int B, int *Wt, int *Ht, int *Bt) {
+    static const int cand[][3] = {{16, 8, 1}, {8, 16, 1}, {32, 4, 1}, {4, 32, 1}, {8, 8, 2}, {4, 8, 4}, {8, 4, 4},
+                                  {4, 4, 8}, {2, 4, 16}, {4, 2, 16}, {2, 2, 32}, {1, 2, 64}, {2, 1, 64},
+                                  {1, 1, 128}, {16, 4, 2}, {4, 16, 2}, {16, 2, 4}, {2, 16, 4}, {64, 2, 1}, {128, 1, 1}};
+    long best = -1;
+    for (auto &c : cand) {
+        long n = (long)cdiv(W, c[0]) * cdiv(H, c[1]) * cdiv(B, c[2]);
+        if (best < 0 || n < best) { best = n; *Wt = c[0]; *Ht = c[1]; *Bt = c[2]; }
+    }
+}
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+}  // namespace effdet
+
+using namespace effdet;
+
+extern "C" int effdet_conv_tc_block_n(int n) {
+    // N tile: whole N (rounded to 16) when <= 256, else 128-wide tiles
+    const int n16 = round_up(n, 16);
+    return n16 <= 256 ? n16 : 128;
+}
+
+extern "C" size_t effdet_conv_weight_panel_elems(int taps_or_samples, int K, int N) {
+    const int bn = effdet_conv_tc_block_n(N);
+    return (size_t)taps_or_samples * round_up(N, bn) * round_up(K, kTileK);
+}
+
+extern "C" int effdet_conv_weight_panel(const float *w, void *panel, int taps, int Cin, int Cout, int mode,
+                                        const float *gate, int B, void *stream) {
+    EFFDET_REQUIRE(w && panel && taps > 0 && Cin > 0 && Cout > 0, "bad arguments");
+    EFFDET_REQUIRE(mode == 0 || mode == 1, "mode 0 (forward) or 1 (data gradient)");
+    EFFDET_REQUIRE(!gate || (mode == 0 && taps == 1 && B > 0), "gate only for forward 1x1");
+    const int K = mode == 0 ? Cin : Cout, N = mode == 0 ? Cout : Cin;
+    const int bn = effdet_conv_tc_block_n(N);
+    const int Kpad = round_up(K, kTileK), Npad = round_up(N, bn);
+    const size_t total = (size_t)(gate ? B : taps) * Npad * Kpad;
+    unsigned blocks = cdiv(total, 256);
+    if (blocks > (unsigned)kNumSMs * 16) blocks = kNumSMs * 16;
+    weight_panel_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, static_cast<__nv_bfloat16 *>(panel), taps, Cin,
+                                                               Cout, Kpad, Npad, mode, gate, B);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+// Called by effdet_conv2d when the descriptor qualifies.  Returns EFFDET_E_UNSUPPORTED (without
+// touching the error string of a real failure) when the shape cannot take this path.
+int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
+    if (!d->weight_bf16 || d->in_dtype != EFFDET_BF16 || d->stride != 1) return EFFDET_E_UNSUPPORTED;
+    if (d->Cin % 8 != 0 || d->kh != d->kw) return EFFDET_E_UNSUPPORTED;
+    if (d->gate && !d->weight_per_sample) return EFFDET_E_UNSUPPORTED;
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return fail(EFFDET_E_CUDA, "effdet_conv2d: cuTensorMapEncodeTiled unavailable%s", "");
+    static TcParams p;      // large; filled per call (single-threaded use per the ABI contract)
+    memset(&p, 0, sizeof(p));
+    const int bn = effdet_conv_tc_block_n(d->Cout);
+    const int Kpad = round_up(d->Cin, kTileK), Npad = round_up(d->Cout, bn);
+    p.n_groups = d->n_groups; p.B = d->B; p.Cout = d->Cout; p.ksize = d->kh;
+    p.kblocks_per_tap = Kpad / kTileK; p.block_n = bn;
+    p.tmem_cols = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
+    p.act = d->act; p.out_f32 = d->out_dtype == EFFDET_F32; p.b_per_sample = d->weight_per_sample ? 1 : 0;
+    p.scale = d->scale; p.shift = d->shift; p.keep = d->keep;
+    const int b_tile_bytes = bn * kTileK * 2;
+    // <= 4 stages: with 64..128-wide N tiles two CTAs stay resident per SM, so one CTA's
+    // epilogue overlaps the other's main loop
+    int stages = (200 * 1024) / (kATileBytes + b_tile_bytes);
+    if (stages > 4) stages = 4;
+    const int num_k = d->kh * d->kw * p.kblocks_per_tap;
+    if (stages > num_k) stages = num_k;
+    if (stages < 1) stages = 1;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * (kATileBytes + b_tile_bytes) + (2 * stages + 1) * 8 + 16 + 1024;
+    int tiles = 0;
+    for (int i = 0; i < d->n_groups; ++i) {
+        TcGroup &g = p.g[i];
+        g.y = d->y[i]; g.res = d->residual[i]; g.mask = d->relu_mask[i];
+        g.H = d->H[i]; g.W = d->W[i];
+        g.ldc = d->ldc[i] ? d->ldc[i] : d->Cout;
+        g.y_batch_stride = d->y_batch_stride[i] ? d->y_batch_stride[i] : (long long)g.H * g.W * g.ldc;
+        if (d->weight_per_sample) { g.Bt = 1; pick_tile(g.W, g.H, 1, &g.Wt, &g.Ht, &g.Bt); if (g.Bt != 1) { g.Wt = 16; g.Ht = 8; g.Bt = 1; } }
+        else pick_tile(g.W, g.H, d->B, &g.Wt, &g.Ht, &g.Bt);
+        g.tiles_x = cdiv(g.W, g.Wt); g.tiles_y = cdiv(g.H, g.Ht); g.tiles_b = cdiv(d->B, g.Bt);
+        g.tile_begin = tiles;
+        tiles += g.tiles_x * g.tiles_y * g.tiles_b;
+        const long long ldx = d->ldx[i] ? d->ldx[i] : d->Cin;
+        const long long xbs = d->x_batch_stride[i] ? d->x_batch_stride[i] : (long long)g.H * g.W * ldx;
+        if ((ldx * 2) % 16 || (xbs * 2) % 16 || (reinterpret_cast<uintptr_t>(d->x[i]) & 15)) return EFFDET_E_UNSUPPORTED;
+        cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)d->B};
+        cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * g.W, (cuuint64_t)xbs * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kTileK, (cuuint32_t)g.Wt, (cuuint32_t)g.Ht, (cuuint32_t)g.Bt};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = encode(&p.a_map[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d->x[i]), dims,
+                            strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_conv2d: cuTensorMapEncodeTiled(A) failed %s(%lld)", "", (long long)r);
+    }
+    {
+        const int nz = d->weight_per_sample ? d->B : d->kh * d->kw;
+        cuuint64_t dims[3] = {(cuuint64_t)Kpad, (cuuint64_t)Npad, (cuuint64_t)nz};
+        cuuint64_t strides[2] = {(cuuint64_t)Kpad * 2, (cuuint64_t)Kpad * 2 * Npad};
+        cuuint32_t box[3] = {(cuuint32_t)kTileK, (cuuint32_t)bn, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = encode(&p.b_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(d->weight_bf16), dims,
+                            strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_conv2d: cuTensorMapEncodeTiled(B) failed %s(%lld)", "", (long long)r);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        EFFDET_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(tiles, Npad / bn);
+    conv_tc_kernel<<<grid, 192, smem, as_stream(stream)>>>(p);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}

@@ -155,10 +155,23 @@ typedef struct effdet_conv_desc {
     const float *keep;    /* (B) f32 drop-connect scale (FixedDropout, efficientnet.py:300-303) or NULL */
     int act;              /* EFFDET_ACT_* */
     int in_dtype, out_dtype;
-    const void *weight_bf16; /* optional (kh*kw, Cout_pad, Cin_pad) bf16 panel for the tcgen05 path */
+    const void *weight_bf16; /* optional bf16 panel from effdet_conv_weight_panel for the tcgen05 path */
     int allow_tensor_core;   /* 0 = force the SIMT fp32-accumulate kernel */
+    int weight_per_sample;   /* weight_bf16 holds one panel per image (SE gate folded in) */
 } effdet_conv_desc;
 int effdet_conv2d(const effdet_conv_desc *desc, void *stream);
+
+/* bf16 weight panels for the tcgen05 path of effdet_conv2d (stride 1, bf16 activations):
+ * mode 0: forward, panel[tap][Cout_pad][Cin_pad] = kernel[tap][ci][co];
+ * mode 1: data gradient, panel[tap][Cin_pad][Cout_pad] = kernel[flipped tap][ci][co] (use with
+ *         Cin/Cout swapped in the descriptor);
+ * gate != NULL (mode 0, 1x1): one panel per image with the squeeze-excite gate (B,Cin) folded
+ *         into the weights (efficientnet.py:286) -- set weight_per_sample in the descriptor.
+ * effdet_conv_weight_panel_elems(taps or B, K, N) gives the bf16 element count to allocate. */
+int effdet_conv_tc_block_n(int n);
+size_t effdet_conv_weight_panel_elems(int taps_or_samples, int K, int N);
+int effdet_conv_weight_panel(const float *kernel, void *panel, int taps, int Cin, int Cout, int mode,
+                             const float *gate, int B, void *stream);
 
 /* Depthwise kxk (k = 3 or 5, stride 1 or 2, SAME) + BN + activation; optionally writes
  * per-(image, block, channel) partial spatial SUMS of the activated output into se_sum

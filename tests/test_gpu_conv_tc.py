@@ -1,0 +1,156 @@
+"""GPU parity of the tcgen05/TMA implicit-GEMM convolution (bf16 operands, fp32 accumulate in
+TMEM) against the fp64 oracle convolution evaluated on the SAME bf16-rounded inputs/weights."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from util_model import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _d(a, dt=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dt)
+
+
+def _bf(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).float().numpy()
+
+
+def _panel(w, mode, gate=None, B=0):
+    from efficientdet_b200 import _lib
+    lib = _lib.load()
+    k = w.shape[0]
+    taps, cin, cout = k * k, w.shape[2], w.shape[3]
+    K, N = (cin, cout) if mode == 0 else (cout, cin)
+    n = lib.effdet_conv_weight_panel_elems(B if gate is not None else taps, K, N)
+    panel = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    wd = _d(w)
+    gd = _d(gate) if gate is not None else None
+    _lib.call("effdet_conv_weight_panel", wd.data_ptr(), panel.data_ptr(), taps, cin, cout, mode,
+              gd.data_ptr() if gate is not None else None, B, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    return panel
+
+
+def _run(xs, panel, cin, cout, k, B, out_dtype, act=0, scale=None, shift=None, res=None, mask=None,
+         keep=None, per_sample=False, ys=None, ldc=None, ybs=None, gate=None):
+    from efficientdet_b200 import _lib
+    d = _lib.ConvDesc()
+    d.n_groups = len(xs)
+    outs = []
+    for i, x in enumerate(xs):
+        H = x.shape[1]
+        if ys is None:
+            y = torch.full((B, H, H, cout), float("nan"), device="cuda",
+                           dtype=torch.float32 if out_dtype == _lib.F32 else torch.bfloat16)
+        else:
+            y = ys[i]
+        outs.append(y)
+        d.x[i], d.y[i] = x.data_ptr(), y.data_ptr()
+        d.residual[i] = res[i].data_ptr() if res else None
+        d.relu_mask[i] = mask[i].data_ptr() if mask else None
+        d.H[i] = d.W[i] = H
+        if ldc:
+            d.ldc[i], d.y_batch_stride[i] = ldc[i], ybs[i]
+    d.B, d.Cin, d.Cout, d.kh, d.kw, d.stride = B, cin, cout, k, k, 1
+    d.weight = None
+    d.scale = scale.data_ptr() if scale is not None else None
+    d.shift = shift.data_ptr() if shift is not None else None
+    d.keep = keep.data_ptr() if keep is not None else None
+    d.gate = gate.data_ptr() if gate is not None else None
+    d.act, d.in_dtype, d.out_dtype = act, _lib.BF16, out_dtype
+    d.weight_bf16, d.allow_tensor_core, d.weight_per_sample = panel.data_ptr(), 1, int(per_sample)
+    _lib.call("effdet_conv2d", ctypes.byref(d), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    return outs
+
+
+def _ref(x_bf, w, act=0, scale=None, shift=None):
+    from oracle import graph
+    y = graph.conv2d(torch.from_numpy(x_bf).double().permute(0, 3, 1, 2), _bf(w).astype(np.float64), 1)
+    if scale is not None:
+        y = y * torch.from_numpy(scale).double().view(1, -1, 1, 1)
+    if shift is not None:
+        y = y + torch.from_numpy(shift).double().view(1, -1, 1, 1)
+    y = [lambda v: v, torch.relu, graph.swish, torch.sigmoid][act](y)
+    return y.permute(0, 2, 3, 1).numpy()
+
+
+@pytest.mark.parametrize("cin,cout,H,B,act", [(64, 64, 16, 2, 1), (24, 144, 16, 3, 2), (320, 64, 8, 2, 1),
+                                              (1152, 320, 4, 2, 0), (40, 240, 20, 1, 2), (88, 88, 10, 5, 1)])
+def test_conv1x1_tc(cin, cout, H, B, act):
+    from efficientdet_b200 import _lib
+    rng = np.random.default_rng(cin + cout)
+    x = rng.standard_normal((B, H, H, cin)).astype(np.float32)
+    w = (rng.standard_normal((1, 1, cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    sc = rng.uniform(0.5, 1.5, cout).astype(np.float32); sh = rng.normal(0, 0.2, cout).astype(np.float32)
+    xd = _d(x, torch.bfloat16)
+    res = rng.standard_normal((B, H, H, cout)).astype(np.float32)
+    keep = rng.uniform(0.5, 1.5, B).astype(np.float32)
+    resd, keepd = _d(res, torch.bfloat16), _d(keep)
+    y, = _run([xd], _panel(w, 0), cin, cout, 1, B, _lib.BF16, act, _d(sc), _d(sh), res=[resd], keep=keepd)
+    want = _ref(xd.float().cpu().numpy(), w, act, sc, sh) * keep[:, None, None, None] + resd.float().cpu().numpy()
+    assert rel_err(y.float().cpu().numpy(), want) < 6e-3
+
+
+def test_conv1x1_tc_per_sample_gate():
+    from efficientdet_b200 import _lib
+    rng = np.random.default_rng(9)
+    B, H, cin, cout = 3, 16, 144, 40
+    x = rng.standard_normal((B, H, H, cin)).astype(np.float32)
+    w = (rng.standard_normal((1, 1, cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    gate = rng.uniform(0.1, 1.0, (B, cin)).astype(np.float32)
+    xd, gd = _d(x, torch.bfloat16), _d(gate)
+    y, = _run([xd], _panel(w, 0, gate, B), cin, cout, 1, B, _lib.BF16, per_sample=True, gate=gd)
+    xq = xd.float().cpu().numpy().astype(np.float64)
+    wq = np.stack([_bf(w[0, 0] * gate[b][:, None]) for b in range(B)]).astype(np.float64)
+    want = np.einsum("bhwc,bcn->bhwn", xq, wq)
+    assert rel_err(y.float().cpu().numpy(), want) < 6e-3
+
+
+@pytest.mark.parametrize("W,cout,out_f32,B,sizes", [(64, 64, False, 4, [16, 8, 4, 2, 1]),
+                                                    (64, 36, True, 2, [16, 8, 4, 2, 1]),
+                                                    (88, 180, True, 2, [20, 10, 5]),
+                                                    (112, 810, True, 1, [12, 6, 3])])
+def test_conv3x3_head_tc_grouped(W, cout, out_f32, B, sizes):
+    """All pyramid levels in one launch; fp32 outputs land in the concatenated (B, N, per) layout."""
+    from efficientdet_b200 import _lib
+    rng = np.random.default_rng(W + cout)
+    w = (rng.standard_normal((3, 3, W, cout)) / np.sqrt(9 * W)).astype(np.float32)
+    bias = rng.normal(0, 0.2, cout).astype(np.float32)
+    xs = [_d(rng.standard_normal((B, s, s, W)).astype(np.float32), torch.bfloat16) for s in sizes]
+    act = 3 if out_f32 and cout != 36 else (0 if out_f32 else 1)
+    if out_f32:
+        rows = sum(s * s for s in sizes)
+        out = torch.full((B, rows, cout), float("nan"), device="cuda")
+        offs = np.concatenate([[0], np.cumsum([s * s for s in sizes])[:-1]])
+        ys = [out.view(-1)[int(o) * cout:] for o in offs]
+        _run(xs, _panel(w, 0), W, cout, 3, B, _lib.F32, act, None, _d(bias), ys=ys, ldc=[cout] * len(sizes),
+             ybs=[rows * cout] * len(sizes))
+        got = out.cpu().numpy()
+        want = np.concatenate([_ref(x.float().cpu().numpy(), w, act, None, bias).reshape(B, -1, cout) for x in xs], 1)
+        assert rel_err(got, want) < 6e-3
+    else:
+        ys = _run(xs, _panel(w, 0), W, cout, 3, B, _lib.BF16, act, None, _d(bias))
+        for x, y in zip(xs, ys):
+            assert rel_err(y.float().cpu().numpy(), _ref(x.float().cpu().numpy(), w, act, None, bias)) < 6e-3
+
+
+def test_conv3x3_dgrad_tc_with_relu_mask_and_accumulate():
+    from efficientdet_b200 import _lib
+    from oracle import graph
+    rng = np.random.default_rng(3)
+    B, H, cin, cout = 2, 12, 64, 64
+    w = (rng.standard_normal((3, 3, cin, cout)) / np.sqrt(9 * cin)).astype(np.float32)
+    dz = _d(rng.standard_normal((B, H, H, cout)).astype(np.float32), torch.bfloat16)
+    mask = _d(rng.standard_normal((B, H, H, cin)).astype(np.float32), torch.bfloat16)
+    prev = _d(rng.standard_normal((B, H, H, cin)).astype(np.float32), torch.bfloat16)
+    x = torch.zeros((B, cin, H, H), dtype=torch.float64, requires_grad=True)
+    graph.conv2d(x, _bf(w).astype(np.float64), 1).backward(dz.double().cpu().permute(0, 3, 1, 2))
+    want = x.grad.permute(0, 2, 3, 1).numpy() * (mask.float().cpu().numpy() > 0) + prev.float().cpu().numpy()
+    out = prev.clone()
+    _run([dz], _panel(w, 1), cout, cin, 3, B, _lib.BF16, res=[out], mask=[mask], ys=[out])
+    assert rel_err(out.float().cpu().numpy(), want) < 6e-3
