@@ -99,6 +99,11 @@ class Plan:
     def w(self, key):
         return self.net.weights[key]
 
+    def panel_for(self, key, taps, cin, cout, mode):
+        """bf16 weight panel of the tensor-core path.  Inference: static (rebuilt by
+        Network.refresh() when weights change)."""
+        return self.net.static_panel(key, taps, cin, cout, mode)
+
     def folded(self, bn_name):
         return self.net.folded[bn_name]
 
@@ -112,6 +117,18 @@ class Plan:
         wt = self.w(weight_key)
         in_dt = self.dtype if in_dtype is None else in_dtype
         out_dt = self.dtype if out_dtype is None else out_dtype
+        # tcgen05 path: bf16 activations, stride 1, channel count a multiple of 8 (TMA strides)
+        use_tc = (self.net.use_tensor_cores and in_dt == BF16 and stride == 1 and cin % 8 == 0)
+        panel = gate_panel = None
+        if use_tc and gate is not None:
+            lib = _lib.load()
+            gate_panel = self.val((lib.effdet_conv_weight_panel_elems(self.B, cin, cout),), BF16,
+                                  name + "_gated_panel")
+            self.add("panel", [gate], [gate_panel],
+                     lambda: _call("effdet_conv_weight_panel", wt.data_ptr(), gate_panel.ptr, 1, cin, cout,
+                                   0, gate.ptr, self.B), name + "_panel")
+        elif use_tc:
+            panel = self.panel_for(weight_key, k * k, cin, cout, 0)
 
         def make():
             d = _lib.ConvDesc()
@@ -130,11 +147,21 @@ class Plan:
             d.gate = gate.ptr if gate is not None else None
             d.keep = keep.data_ptr() if keep is not None else None
             d.act, d.in_dtype, d.out_dtype = act, in_dt, out_dt
-            d.weight_bf16 = None
-            d.allow_tensor_core = 1 if self.net.use_tensor_cores else 0
+            if gate_panel is not None:
+                d.weight_bf16, d.weight_per_sample = gate_panel.ptr, 1
+            elif panel is not None:
+                d.weight_bf16, d.weight_per_sample = (panel.ptr if isinstance(panel, Val)
+                                                      else panel.data_ptr()), 0
+            else:
+                d.weight_bf16 = None
+            d.allow_tensor_core = 1 if use_tc else 0
             self._keepalive.append(d)
             return _call("effdet_conv2d", ctypes.byref(d))
         ins = list(xs) + [r for r in residuals if r is not None] + ([gate] if gate is not None else [])
+        if gate_panel is not None:
+            ins.append(gate_panel)
+        if isinstance(panel, Val):
+            ins.append(panel)
         out_es = 2 if out_dt == BF16 else 4
         flops = nbytes = 0
         for xv in xs:
@@ -142,7 +169,7 @@ class Plan:
             flops += 2 * self.B * ho * wo * cout * k * k * cin
             nbytes += self.B * ho * wo * cout * out_es
         nbytes += sum(v.nbytes for v in ins) + k * k * cin * cout * 4
-        kind = "conv%dx%d" % (k, k) + ("_head" if n > 1 else "")
+        kind = "conv%dx%d" % (k, k) + ("_head" if n > 1 else "") + ("_tc" if use_tc else "")
         self.ops.append(Op(kind, ins, list(dict.fromkeys(ys)), make, name, nbytes, flops))
 
     # -------------------------------------------------------------- network lowering

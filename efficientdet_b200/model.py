@@ -6,7 +6,8 @@ objects expose the slice of the Keras Model API the reference's callers use
 train_on_batch, summary, optimizer) and execute on the library's CUDA kernels through
 engine.Plan.  Extra keyword-only options of this build (popped before **bbkwargs reach the
 backbone builder): dtype ('fp32' accuracy mode | 'bf16' speed mode), image_size (override of
-model.py:29), seed (numpy default_rng seed of the random initialisation), device.
+model.py:29), seed (numpy default_rng seed of the random initialisation), device,
+tensor_cores (bf16 mode: False forces the SIMT convolution kernels).
 """
 import collections
 import math
@@ -36,7 +37,7 @@ class Network:
     """Weights (Keras names, fp32 masters on the device) + derived tensors + plans."""
 
     def __init__(self, phi, num_classes, weighted_bifpn, freeze_bn, backbone, image_size, dtype,
-                 seed, device):
+                 seed, device, tensor_cores=True):
         self.phi, self.num_classes = phi, int(num_classes)
         self.weighted_bifpn, self.freeze_bn = bool(weighted_bifpn), bool(freeze_bn)
         self.backbone = backbone
@@ -48,7 +49,7 @@ class Network:
         self.w_bifpn = w_bifpns[phi]
         self.d_bifpn = 2 + phi
         self.head_depth = 3 + int(phi / 3)
-        self.use_tensor_cores = True
+        self.use_tensor_cores = bool(tensor_cores)   # bf16 mode: tcgen05 convolutions
         self.weights = collections.OrderedDict()
         self.bn_layers = collections.OrderedDict()     # bn layer name -> (C, eps)
         self.folded = {}
@@ -161,6 +162,8 @@ class Network:
                       self.weights[name + "/moving_mean"].data_ptr(),
                       self.weights[name + "/moving_variance"].data_ptr(), float(eps),
                       sc.data_ptr(), sh.data_ptr(), C, st)
+        for k in getattr(self, "_panels", {}):
+            self._build_panel(k)
 
     # ---------------------------------------------------------------- training state
     def ensure_grad_buffers(self):
@@ -186,6 +189,24 @@ class Network:
     def invalidate(self):
         """Weights changed (optimizer step): inference-mode folded BN must be re-derived."""
         self._dirty = True
+
+    def static_panel(self, key, taps, cin, cout, mode):
+        """bf16 weight panel for the tcgen05 convolution, cached per (weight, mode)."""
+        if not hasattr(self, "_panels"):
+            self._panels = {}
+        k = (key, mode)
+        if k not in self._panels:
+            n = _lib.load().effdet_conv_weight_panel_elems(taps, cin if mode == 0 else cout,
+                                                           cout if mode == 0 else cin)
+            t = torch.empty(n, dtype=torch.bfloat16, device=self.device)
+            self._panels[k] = (t, taps, cin, cout)
+            self._build_panel(k)
+        return self._panels[k][0]
+
+    def _build_panel(self, k):
+        t, taps, cin, cout = self._panels[k]
+        _lib.call("effdet_conv_weight_panel", self.weights[k[0]].data_ptr(), t.data_ptr(), taps, cin, cout,
+                  k[1], None, 0, _lib.stream_ptr(self.device))
 
     def plan(self, batch, **kw):
         if getattr(self, "_dirty", False):
@@ -398,12 +419,13 @@ def efficientdet(phi, num_classes=20, weighted_bifpn=False, freeze_bn=False, sco
     image_size = bbkwargs.pop("image_size", None) or image_sizes[phi]
     seed = bbkwargs.pop("seed", 2024)
     device = bbkwargs.pop("device", None)
+    tensor_cores = bbkwargs.pop("tensor_cores", True)
     if device is None:
         from ._tensor import device as _dev
         device = _dev()
     backbone = backbones[phi](input_tensor=None, freeze_bn=freeze_bn, **bbkwargs)
     net = Network(phi, num_classes, weighted_bifpn, freeze_bn, backbone, image_size, dtype, seed,
-                  device)
+                  device, tensor_cores)
     model = Model(net, "efficientdet", "train")
     if just_training_model:
         return model

@@ -76,6 +76,25 @@ class TrainPlan(engine.Plan):
                                    rows, C, act, self.dtype), bn_name + "_apply")
         return rec
 
+    def panel_for(self, key, taps, cin, cout, mode):
+        """Trainable weights change every step: their bf16 panels are rebuilt inside the step;
+        frozen-backbone panels stay static."""
+        net = self.net
+        if net.offsets[key] < net.backbone_end:
+            return net.static_panel(key, taps, cin, cout, mode)
+        ck = (key, mode)
+        if not hasattr(self, "_step_panels"):
+            self._step_panels = {}
+        if ck not in self._step_panels:
+            n = _lib.load().effdet_conv_weight_panel_elems(taps, cin if mode == 0 else cout,
+                                                           cout if mode == 0 else cin)
+            pv = self.val((n,), BF16, key + "_panel%d" % mode, keep=True)
+            self.add("panel", [], [pv],
+                     lambda: _call("effdet_conv_weight_panel", self.w(key).data_ptr(), pv.ptr, taps, cin,
+                                   cout, mode, None, 0), key + "_panel%d" % mode)
+            self._step_panels[ck] = pv
+        return self._step_panels[ck]
+
     # ------------------------------------------------------------------ forward emitters (override)
     def _conv_block(self, x, name, cin, cout, k=1, stride=1):
         B = self.B
@@ -112,11 +131,13 @@ class TrainPlan(engine.Plan):
         return y
 
     def _heads(self, feats, Wd):
+        start = len(self.ops)
         super()._heads(feats, Wd)
         # recover the per-layer activations from the conv ops just emitted
         net = self.net
         n_ops = 2 * (net.head_depth + 1)
-        ops = self.ops[-n_ops:]
+        ops = [op for op in self.ops[start:] if op.kind.startswith("conv")]
+        assert len(ops) == n_ops
         self.head_tape = []
         for h, (scope, fmt, final, out, per) in enumerate((
                 ("box_head", "regress_head_conv_%d", "regress_head_conv_final", self.regression, 4),
@@ -271,7 +292,8 @@ class TrainPlan(engine.Plan):
                 gv = [self.grad_of(t) for t in targets]
                 self._dgrad(None, dzs, wt, Wd, Wd, [g for g, _ in gv], targets,
                             masks=targets if li > 0 else None, accumulate=[a for _, a in gv],
-                            shapes=[t.shape for t in targets], name=L["name"] + "_dgrad")
+                            shapes=[t.shape for t in targets], name=L["name"] + "_dgrad",
+                            key=L["name"] + "/kernel")
         # ---- BiFPN (reverse tape)
         for rec in reversed(self.tape):
             if rec["kind"] == "node":
@@ -280,12 +302,16 @@ class TrainPlan(engine.Plan):
                 self._convblock_backward(rec)
 
     def _dgrad(self, x_single, xs, wt, cin, cout, dsts, targets, masks, accumulate, shapes, x_ld=None,
-               x_bs=None, x_off=None, in_dtype=None, name=""):
-        """stride-1 3x3/1x1 data gradient = convolution of dz with the transposed kernel."""
+               x_bs=None, x_off=None, in_dtype=None, name="", key=None):
+        """stride-1 3x3/1x1 data gradient = convolution of dz with the transposed kernel.
+        cin/cout are those of THIS convolution (= forward Cout/Cin)."""
         n = len(dsts)
         in_dt = self.dtype if in_dtype is None else in_dtype
         taps = wt.shape[0] // (cin * cout)
         k = 3 if taps == 9 else 1
+        use_tc = (self.net.use_tensor_cores and in_dt == BF16 and self.dtype == BF16 and key is not None
+                  and cin % 8 == 0)
+        panel = self.panel_for(key, taps, cout, cin, 1) if use_tc else None
 
         def make():
             d = _lib.ConvDesc()
@@ -302,13 +328,19 @@ class TrainPlan(engine.Plan):
             d.B, d.Cin, d.Cout, d.kh, d.kw, d.stride = self.B, cin, cout, k, k, 1
             d.weight = wt.ptr
             d.act, d.in_dtype, d.out_dtype = ACT_NONE, in_dt, self.dtype
-            d.allow_tensor_core = 0
+            if panel is not None:
+                d.weight_bf16 = panel.ptr if isinstance(panel, Val) else panel.data_ptr()
+                d.allow_tensor_core = 1
+            else:
+                d.allow_tensor_core = 0
             self._keepalive.append(d)
             return _call("effdet_conv2d", ctypes.byref(d))
         ins = ([x_single] if x_single is not None else list(xs)) + [wt] + (list(masks) if masks else [])
         ins += [dsts[i] for i in range(n) if accumulate[i]]
+        if isinstance(panel, Val):
+            ins.append(panel)
         flops = sum(2 * self.B * s[1] * s[2] * cin * cout * taps for s in shapes)
-        self.ops.append(Op("conv_dgrad", ins, list(dsts), make, name,
+        self.ops.append(Op("conv_dgrad_tc" if use_tc else "conv_dgrad", ins, list(dsts), make, name,
                            sum(v.nbytes for v in ins) + sum(v.nbytes for v in dsts), flops))
 
     def _bn_backward(self, rec, dy):
@@ -399,7 +431,8 @@ class TrainPlan(engine.Plan):
         g, acc = self.grad_of(x)
         if stride == 1:
             wt = self._transposed_weight(key, k * k, cin, cout)
-            self._dgrad(None, [dz], wt, cout, cin, [g], [x], None, [acc], [x.shape], name=name + "_dgrad")
+            self._dgrad(None, [dz], wt, cout, cin, [g], [x], None, [acc], [x.shape], name=name + "_dgrad",
+                        key=key)
         else:
             H = x.shape[1]
             self.add("conv_dgrad", [dz, g if acc else None], [g],
