@@ -369,33 +369,37 @@ def test_training_step_gradients(weighted, freeze_bn):
 
 def test_training_step_bf16_tensor_cores_matches_simt():
     """bf16 speed mode: the tcgen05 convolution path and the SIMT path agree on losses and
-    gradients (same bf16 activations, different summation order)."""
+    gradients up to the noise floor of bf16 training on this problem.  The floor is measured, not
+    assumed: a third (SIMT) run on inputs perturbed by 1e-3 relative noise moves the gradients by
+    20-60 % (relative L2) in the deep BiFPN layers, because activations and activation gradients
+    are stored in bf16; the tensor-core run must not move them more than 1.5x that (+0.05)."""
     from efficientdet_b200.model import efficientdet
     from efficientdet_b200.optimizers import SGD
     from util_model import rel_l2
     size, C, B, phi = 256, 5, 4, 0
     anchors, ann, reg_t, lab_t = _targets(size, B, C)
     img = np.random.default_rng(5).standard_normal((B, size, size, 3)).astype(np.float32)
+    img_noisy = img * (1 + 1e-3 * np.random.default_rng(1).standard_normal(img.shape).astype(np.float32))
     res = {}
-    for tc in (False, True):
+    for tag, tc, x in (("simt", False, img), ("tc", True, img), ("noise", False, img_noisy)):
         model = efficientdet(phi, num_classes=C, weighted_bifpn=True, image_size=size, dtype="bf16",
                              drop_connect_rate=0, just_training_model=True, tensor_cores=tc)
         perturb_weights(model)
         model.freeze_backbone()
         model.compile(optimizer=SGD(lr=0.01, decay=4e-5, momentum=0.9))
-        loss = model.train_on_batch(img, [reg_t, lab_t])
+        loss = model.train_on_batch(x, [reg_t, lab_t])
         kinds = {op.kind for op in list(model._trainer.plans.values())[0].ops}
         assert any(k.endswith("_tc") for k in kinds) == tc
-        res[tc] = (loss, {k: v.cpu().numpy().copy() for k, v in model.net.grads.items()
-                          if k.startswith(("BiFPN_", "box_head", "class_head"))})
-    assert abs(res[True][0][0] - res[False][0][0]) / res[False][0][0] < 2e-2
+        res[tag] = (loss, {k: v.cpu().numpy().copy() for k, v in model.net.grads.items()
+                           if k.startswith(("BiFPN_", "box_head", "class_head"))})
+    assert abs(res["tc"][0][0] - res["simt"][0][0]) / res["simt"][0][0] < 1e-2
     bad = {}
-    for k, g in res[False][1].items():
+    for k, g in res["simt"][1].items():
         if k.endswith(("moving_mean", "moving_variance")) or np.abs(g).max() < 1e-10:
             continue
-        e = rel_l2(res[True][1][k], g)
-        if not e < 0.1:
-            bad[k] = float(e)
+        e, floor = rel_l2(res["tc"][1][k], g), rel_l2(res["noise"][1][k], g)
+        if not e < 1.5 * floor + 0.05:
+            bad[k] = (float(e), float(floor))
     assert not bad, bad
 
 
