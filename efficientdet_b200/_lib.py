@@ -59,7 +59,8 @@ _SIGNATURES = {
                           c_void_p],
     "effdet_detection_losses": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                 c_size_t, c_int, c_float, c_float, c_float, c_float, c_void_p,
-                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+                                c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p,
+                                c_int, c_int, c_int, c_void_p],
     "effdet_resample_fuse": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
                              c_int, c_int, c_int, c_int, c_int, c_void_p],
     "effdet_bn_train_stats": [c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_float, c_float,
@@ -80,6 +81,7 @@ _SIGNATURES = {
                                      c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int,
                                      c_int, c_int, c_void_p],
     "effdet_conv_wgrad": [c_void_p, c_void_p],
+    "effdet_conv_wgrad_tc": [c_void_p, c_void_p],
     "effdet_conv_dgrad_strided": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_void_p],
     "effdet_conv_weight_transpose": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
@@ -151,6 +153,8 @@ def load():
     lib.effdet_dw_wgrad_blocks.argtypes = [c_int, c_int, c_int, c_int, c_int]
     lib.effdet_conv_wgrad_splits.restype = c_int
     lib.effdet_conv_wgrad_splits.argtypes = [c_void_p]
+    lib.effdet_conv_wgrad_tc_splits.restype = c_int
+    lib.effdet_conv_wgrad_tc_splits.argtypes = [c_void_p]
     lib.effdet_conv_tc_block_n.restype = c_int
     lib.effdet_conv_tc_block_n.argtypes = [c_int]
     lib.effdet_conv_weight_panel_elems.restype = c_size_t

@@ -327,6 +327,147 @@ weight_panel_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ pan
     }
 }
 
+
+// ------------------------------------------------------------------ weight gradient on tcgen05
+// dW[tap][ci][co] = sum_pixels X[pix + tap][ci] * dZ[pix][co]
+// GEMM per tap:  D[M = 128 ci, N = co tile] += A[ci, K = 128 pixels] * B[K = 128 pixels, co]
+// Both operands have the reduction dimension (pixels) as the slow one in memory, i.e. they are
+// "MN-major" for the tensor core: the TMA boxes (64 channels x 128 pixels, SWIZZLE_128B) are
+// exactly the canonical MN-major atoms stacked along K (SBO = 1024 B between 8-pixel groups,
+// LBO = 16 KiB between 64-channel boxes).  Split-K over pixel-tile ranges; fp32 partials are
+// reduced in a fixed order by wgrad_reduce_kernel (deterministic).
+struct WgTcGroup {
+    int H, W, Wt, Ht, Bt, tiles_x, tiles_y, tiles_b;
+    int n_tiles, split_begin, tiles_per_split;
+};
+struct alignas(64) WgTcParams {
+    CUtensorMap x_map[kTcMaxGroups];
+    CUtensorMap z_map[kTcMaxGroups];
+    WgTcGroup g[kTcMaxGroups];
+    int n_groups, B, Cin, Cout, ksize, m_tiles, block_n, stages, tmem_cols;
+    float *partial;
+};
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int n_boxes = p.block_n / 64;
+    const int a_bytes = 2 * kATileBytes, b_bytes = n_boxes * kATileBytes;
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + (size_t)p.stages * a_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sB + (size_t)p.stages * b_bytes);
+    uint64_t *empty = full + p.stages;
+    uint64_t *tmem_full = empty + p.stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int gi = 0;
+#pragma unroll
+    for (int i = 1; i < kTcMaxGroups; ++i)
+        if (i < p.n_groups && (int)blockIdx.x >= p.g[i].split_begin) gi = i;
+    const WgTcGroup &G = p.g[gi];
+    const int t_begin = ((int)blockIdx.x - G.split_begin) * G.tiles_per_split;
+    const int t_end = min(t_begin + G.tiles_per_split, G.n_tiles);
+    const int tap = blockIdx.y / p.m_tiles, ci0 = (blockIdx.y % p.m_tiles) * 128;
+    const int n0 = blockIdx.z * p.block_n;
+    const int ky = tap / p.ksize, kx = tap - ky * p.ksize, pad = p.ksize / 2;
+    const int num_k = t_end - t_begin;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % p.stages, ph = (kb / p.stages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                int t = t_begin + kb;
+                const int tx = t % G.tiles_x; t /= G.tiles_x;
+                const int ty = t % G.tiles_y; t /= G.tiles_y;
+                const int x0 = tx * G.Wt, y0 = ty * G.Ht, b0 = t * G.Bt;
+                mbar_expect_tx(&full[s], (uint32_t)(a_bytes + b_bytes));
+                uint8_t *a = sA + (size_t)s * a_bytes, *b = sB + (size_t)s * b_bytes;
+                tma_load_4d(a, &p.x_map[gi], &full[s], ci0, x0 + kx - pad, y0 + ky - pad, b0);
+                tma_load_4d(a + kATileBytes, &p.x_map[gi], &full[s], ci0 + 64, x0 + kx - pad, y0 + ky - pad, b0);
+                for (int j = 0; j < n_boxes; ++j)
+                    tma_load_4d(b + (size_t)j * kATileBytes, &p.z_map[gi], &full[s], n0 + 64 * j, x0, y0, b0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // a_major = b_major = MN (bits 15, 16)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % p.stages, ph = (kb / p.stages) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t a = smem_u32(sA + (size_t)s * a_bytes), b = smem_u32(sB + (size_t)s * b_bytes);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {   // 128 pixels = 8 x UMMA_K(16); 16 pixel rows = 2048 bytes
+                    const uint64_t da = make_mnmajor_sw128_desc(a + k * 2048, kATileBytes);
+                    const uint64_t db = make_mnmajor_sw128_desc(b + k * 2048, kATileBytes);
+                    umma_bf16(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int ci = ci0 + q * 32 + lane;
+        if (num_k > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        float *out = p.partial + ((size_t)blockIdx.x * p.ksize * p.ksize + tap) * p.Cin * p.Cout;
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+            uint32_t r[32];
+            __syncwarp();
+            if (num_k > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            if (ci < p.Cin) {
+                float *o = out + (size_t)ci * p.Cout + n0 + c0;
+                const int nv = min(32, p.Cout - (n0 + c0));
+                for (int j = 0; j < nv; ++j) o[j] = num_k > 0 ? __uint_as_float(r[j]) : 0.f;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+__global__ void wgrad_tc_reduce_kernel(const float *__restrict__ partial, int nsplit, size_t n,
+                                       float *__restrict__ out, int accumulate) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float t = 0.f;
+    for (int s = 0; s < nsplit; ++s) t += partial[(size_t)s * n + i];
+    out[i] = accumulate ? out[i] + t : t;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -458,6 +599,110 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     }
     dim3 grid(tiles, Npad / bn);
     conv_tc_kernel<<<grid, 192, smem, as_stream(stream)>>>(p);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+static int wg_tc_plan(const effdet_wgrad_desc *d, int *tiles_per_split_out, int *n_tiles_out, int *Wt, int *Ht,
+                      int *Bt, int *block_n_out, int *m_tiles_out) {
+    const int taps = d->kh * d->kw;
+    const int bn = d->Cout <= 256 ? round_up(d->Cout, 64) : 256;
+    const int m_tiles = (d->Cin + 127) / 128, n_tiles_n = (d->Cout + bn - 1) / bn;
+    long total_tiles = 0;
+    for (int i = 0; i < d->n_groups; ++i) {
+        pick_tile(d->W[i], d->H[i], d->B, &Wt[i], &Ht[i], &Bt[i]);
+        n_tiles_out[i] = (int)(cdiv(d->W[i], Wt[i]) * cdiv(d->H[i], Ht[i]) * cdiv(d->B, Bt[i]));
+        total_tiles += n_tiles_out[i];
+    }
+    // ~2 CTAs per SM in flight; at least 8 pixel tiles per CTA so the pipeline has work
+    long want = ((long)kNumSMs * 2 + (long)taps * m_tiles * n_tiles_n - 1) / ((long)taps * m_tiles * n_tiles_n);
+    if (want < 1) want = 1;
+    long tps = (total_tiles + want - 1) / want;
+    if (tps < 8) tps = 8;
+    *tiles_per_split_out = (int)tps;
+    *block_n_out = bn; *m_tiles_out = m_tiles;
+    int splits = 0;
+    for (int i = 0; i < d->n_groups; ++i) splits += (int)cdiv(n_tiles_out[i], tps);
+    return splits;
+}
+
+extern "C" int effdet_conv_wgrad_tc_splits(const effdet_wgrad_desc *d) {
+    if (!d || d->n_groups < 1 || d->n_groups > kTcMaxGroups) return 0;
+    int tps, nt[kTcMaxGroups], Wt[kTcMaxGroups], Ht[kTcMaxGroups], Bt[kTcMaxGroups], bn, mt;
+    return wg_tc_plan(d, &tps, nt, Wt, Ht, Bt, &bn, &mt);
+}
+
+/* Tensor-core weight gradient: x (B,H,W,Cin) bf16 dense, dz (B,H,W,dz_ld) bf16 with the first Cout
+ * channels meaningful (dz_ld >= Cout, multiple of 8), stride 1, k in {1,3}.  partial must hold
+ * effdet_conv_wgrad_tc_splits(desc) * kh*kw*Cin*Cout floats. */
+extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
+    EFFDET_REQUIRE(d, "null descriptor");
+    EFFDET_REQUIRE(d->n_groups >= 1 && d->n_groups <= kTcMaxGroups, "1..5 groups");
+    EFFDET_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0 && d->dweight && d->partial, "bad arguments");
+    EFFDET_REQUIRE(d->stride == 1 && d->kh == d->kw && (d->kh == 1 || d->kh == 3), "stride 1, k in {1,3}");
+    EFFDET_REQUIRE(d->x_dtype == EFFDET_BF16 && d->dz_dtype == EFFDET_BF16, "bf16 operands");
+    EFFDET_REQUIRE(d->Cin % 8 == 0, "Cin must be a multiple of 8");
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return fail(EFFDET_E_CUDA, "effdet_conv_wgrad_tc: cuTensorMapEncodeTiled unavailable%s", "");
+    static WgTcParams p;
+    memset(&p, 0, sizeof(p));
+    int tps, nt[kTcMaxGroups], Wt[kTcMaxGroups], Ht[kTcMaxGroups], Bt[kTcMaxGroups], bn, mt;
+    const int splits = wg_tc_plan(d, &tps, nt, Wt, Ht, Bt, &bn, &mt);
+    EFFDET_REQUIRE(splits == d->n_splits, "n_splits must be effdet_conv_wgrad_tc_splits()");
+    p.n_groups = d->n_groups; p.B = d->B; p.Cin = d->Cin; p.Cout = d->Cout; p.ksize = d->kh;
+    p.m_tiles = mt; p.block_n = bn; p.partial = d->partial;
+    p.tmem_cols = bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
+    const int stage_bytes = 2 * kATileBytes + (bn / 64) * kATileBytes;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 4) stages = 4;
+    if (stages < 1) stages = 1;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+    int z = 0;
+    for (int i = 0; i < d->n_groups; ++i) {
+        WgTcGroup &g = p.g[i];
+        g.H = d->H[i]; g.W = d->W[i]; g.Wt = Wt[i]; g.Ht = Ht[i]; g.Bt = Bt[i];
+        g.tiles_x = cdiv(g.W, g.Wt); g.tiles_y = cdiv(g.H, g.Ht); g.tiles_b = cdiv(d->B, g.Bt);
+        g.n_tiles = nt[i]; g.split_begin = z; g.tiles_per_split = tps;
+        z += (int)cdiv(nt[i], tps);
+        const long long ldz = d->dz_ld[i] ? d->dz_ld[i] : d->Cout;
+        const long long zbs = d->dz_batch_stride[i] ? d->dz_batch_stride[i] : (long long)g.H * g.W * ldz;
+        EFFDET_REQUIRE((ldz * 2) % 16 == 0 && (zbs * 2) % 16 == 0, "dz strides must be multiples of 16 bytes");
+        EFFDET_REQUIRE(((reinterpret_cast<uintptr_t>(d->x[i]) | reinterpret_cast<uintptr_t>(d->dz[i])) & 15) == 0,
+                       "operands must be 16-byte aligned");
+        cuuint32_t box[4] = {64, (cuuint32_t)g.Wt, (cuuint32_t)g.Ht, (cuuint32_t)g.Bt};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        {
+            cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)d->B};
+            cuuint64_t st[3] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * g.W, (cuuint64_t)d->Cin * 2 * g.W * g.H};
+            CUresult r = encode(&p.x_map[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d->x[i]), dims, st,
+                                box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_conv_wgrad_tc: encode(x) failed %s(%lld)", "", (long long)r);
+        }
+        {
+            // only the first Cout channels are meaningful: the map's channel extent is Cout so that
+            // everything beyond it is zero-filled by TMA
+            cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)d->B};
+            cuuint64_t st[3] = {(cuuint64_t)ldz * 2, (cuuint64_t)ldz * 2 * g.W, (cuuint64_t)zbs * 2};
+            CUresult r = encode(&p.z_map[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d->dz[i]), dims, st,
+                                box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_conv_wgrad_tc: encode(dz) failed %s(%lld)", "", (long long)r);
+        }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        EFFDET_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int taps = d->kh * d->kw;
+    dim3 grid(z, taps * mt, (d->Cout + bn - 1) / bn);
+    cudaStream_t st = as_stream(stream);
+    conv_wgrad_tc_kernel<<<grid, 192, smem, st>>>(p);
+    EFFDET_LAUNCHED();
+    const size_t n = (size_t)taps * d->Cin * d->Cout;
+    wgrad_tc_reduce_kernel<<<cdiv(n, 256), 256, 0, st>>>(d->partial, z, n, d->dweight, d->accumulate);
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }

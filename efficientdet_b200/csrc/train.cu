@@ -175,6 +175,20 @@ __global__ void colreduce_kernel(const T *__restrict__ x, const T *__restrict__ 
     }
 }
 
+
+// Sum over `nblk` partial rows for one channel with a whole warp: lane l adds blocks l, l+32, ...
+// (fixed order), then a fixed-shape shuffle tree -> deterministic, and ~32x less serial latency
+// than one thread walking all blocks.
+__device__ __forceinline__ double warp_block_sum(const float *__restrict__ partial, int nblk,
+                                                 size_t stride, size_t offset) {
+    const int lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int b = lane; b < nblk; b += 32) s += (double)partial[(size_t)b * stride + offset];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    return s;
+}
+
 // BN training: batch statistics -> scale/shift (+ saved mean/invstd, moving averages)
 __global__ void bn_train_finalize_kernel(const float *__restrict__ partial, int nblk, double count,
                                          const float *__restrict__ gamma,
@@ -183,13 +197,11 @@ __global__ void bn_train_finalize_kernel(const float *__restrict__ partial, int 
                                          float *__restrict__ moving_var, float *__restrict__ scale,
                                          float *__restrict__ shift, float *__restrict__ save_mean,
                                          float *__restrict__ save_invstd, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per channel
     if (c >= C) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < nblk; ++b) {
-        s1 += (double)partial[(size_t)b * 2 * C + c];
-        s2 += (double)partial[(size_t)b * 2 * C + C + c];
-    }
+    const double s1 = warp_block_sum(partial, nblk, 2 * (size_t)C, c);
+    const double s2 = warp_block_sum(partial, nblk, 2 * (size_t)C, (size_t)C + c);
+    if (threadIdx.x & 31) return;
     const double m = s1 / count;
     double var = s2 / count - m * m;
     if (var < 0.0) var = 0.0;
@@ -211,12 +223,12 @@ __global__ void bn_train_finalize_kernel(const float *__restrict__ partial, int 
 __global__ void colsum_finalize_kernel(const float *__restrict__ partial, int nblk, int C, int fold,
                                        float *__restrict__ out, int accumulate) {
     const int Cout = C / fold;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per channel
     if (c >= Cout) return;
-    float t = 0.f;
-    for (int b = 0; b < nblk; ++b)
-        for (int j = 0; j < fold; ++j) t += partial[(size_t)b * 2 * C + j * Cout + c];
-    out[c] = accumulate ? out[c] + t : t;
+    double t = 0.0;
+    for (int j = 0; j < fold; ++j) t += warp_block_sum(partial, nblk, 2 * (size_t)C, (size_t)j * Cout + c);
+    if (threadIdx.x & 31) return;
+    out[c] = accumulate ? out[c] + (float)t : (float)t;
 }
 
 // BN backward coefficients: dz = k1*dy_masked + k2*z + k3 ; dgamma, dbeta
@@ -225,13 +237,11 @@ __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partial, int nb
                                        const float *__restrict__ mean,
                                        const float *__restrict__ invstd, float *__restrict__ k123,
                                        float *__restrict__ dgamma, float *__restrict__ dbeta, int C) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per channel
     if (c >= C) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < nblk; ++b) {
-        s1 += (double)partial[(size_t)b * 2 * C + c];
-        s2 += (double)partial[(size_t)b * 2 * C + C + c];
-    }
+    const double s1 = warp_block_sum(partial, nblk, 2 * (size_t)C, c);
+    const double s2 = warp_block_sum(partial, nblk, 2 * (size_t)C, (size_t)C + c);
+    if (threadIdx.x & 31) return;
     const float g = gamma[c], is = invstd[c], mu = mean[c];
     const float m1 = (float)(s1 / count), m2 = (float)(s2 / count);
     k123[c] = g * is;
@@ -329,11 +339,11 @@ __global__ void dw_wgrad_kernel(const T *__restrict__ f, const T *__restrict__ d
 }
 __global__ void sum_partials_kernel(const float *__restrict__ partial, int nblk, int n,
                                     float *__restrict__ out, int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per element
     if (i >= n) return;
-    float t = 0.f;
-    for (int b = 0; b < nblk; ++b) t += partial[(size_t)b * n + i];
-    out[i] = accumulate ? out[i] + t : t;
+    const double t = warp_block_sum(partial, nblk, (size_t)n, (size_t)i);
+    if (threadIdx.x & 31) return;
+    out[i] = accumulate ? out[i] + (float)t : (float)t;
 }
 
 // ------------------------------------------------------------------ fusion backward
@@ -573,7 +583,7 @@ extern "C" int effdet_bn_train_stats(const void *z, size_t rows, int C, const fl
         rc = (launch_colreduce<float, 4, RED_STATS>(z, nullptr, nullptr, nullptr, nullptr, rows, C, nblk, partial, st)),
         rc = (launch_colreduce<__nv_bfloat16, 8, RED_STATS>(z, nullptr, nullptr, nullptr, nullptr, rows, C, nblk, partial, st)))
     if (rc) return rc;
-    bn_train_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(partial, nblk, (double)rows, gamma, beta, eps,
+    bn_train_finalize_kernel<<<cdiv((size_t)C * 32, 256), 256, 0, st>>>(partial, nblk, (double)rows, gamma, beta, eps,
                                                            momentum, moving_mean, moving_var, scale,
                                                            shift, save_mean, save_invstd, C);
     EFFDET_LAUNCHED();
@@ -616,7 +626,7 @@ extern "C" int effdet_bn_relu_backward(const void *dy, const void *y, const void
             rc = (launch_colreduce<float, 4, RED_BNBWD>(z, y, dy, save_mean, save_invstd, rows, C, nblk, partial, st)),
             rc = (launch_colreduce<__nv_bfloat16, 8, RED_BNBWD>(z, y, dy, save_mean, save_invstd, rows, C, nblk, partial, st)))
         if (rc) return rc;
-        bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, st>>>(partial, nblk, (double)rows, gamma, save_mean,
+        bn_bwd_finalize_kernel<<<cdiv((size_t)C * 32, 256), 256, 0, st>>>(partial, nblk, (double)rows, gamma, save_mean,
                                                              save_invstd, k123, dgamma, dbeta, C);
         EFFDET_LAUNCHED();
     }
@@ -643,7 +653,7 @@ extern "C" int effdet_colsum(const void *x, size_t rows, int C, int fold, float 
         rc = (launch_colreduce<float, 4, RED_SUM>(x, nullptr, nullptr, nullptr, nullptr, rows, C, nblk, partial, st)),
         rc = (launch_colreduce<__nv_bfloat16, 8, RED_SUM>(x, nullptr, nullptr, nullptr, nullptr, rows, C, nblk, partial, st)))
     if (rc) return rc;
-    colsum_finalize_kernel<<<cdiv(C / fold, 128), 128, 0, st>>>(partial, nblk, C, fold, out, accumulate);
+    colsum_finalize_kernel<<<cdiv((size_t)(C / fold) * 32, 256), 256, 0, st>>>(partial, nblk, C, fold, out, accumulate);
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -682,7 +692,7 @@ extern "C" int effdet_dw_wgrad(const void *f, const void *dz, int B, int H, int 
         return fail(EFFDET_E_INVALID, "effdet_dw_wgrad: bad dtype%s", "");
     }
     EFFDET_LAUNCHED();
-    sum_partials_kernel<<<cdiv((size_t)9 * C, 128), 128, 0, st>>>(partial, nblk, 9 * C, dkernel, 0);
+    sum_partials_kernel<<<cdiv((size_t)9 * C * 32, 256), 256, 0, st>>>(partial, nblk, 9 * C, dkernel, 0);
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }

@@ -180,13 +180,38 @@ class TrainPlan(engine.Plan):
         ws_bytes = _lib.load().effdet_detection_losses_workspace_size()
         ws = self._scratch(ws_bytes // 4, "loss_ws")
         ins = [self.classification, self.regression, self.reg_t, self.lab_t, self.state_t, self.cls_t]
-        self.add("losses", ins, [self.dcls, self.dreg, self.loss_out, ws],
-                 lambda: _call("effdet_detection_losses", self.classification.ptr, self.regression.ptr,
-                               self.reg_t.ptr, self.lab_t.ptr if self.lab_t is not None else None,
-                               self.state_t.ptr if self.state_t is not None else None,
-                               self.cls_t.ptr if self.cls_t is not None else None, B, N, C, self.alpha,
-                               self.gamma, self.delta, 1.0, self.dcls.ptr, self.dreg.ptr,
-                               self.loss_out.ptr, ws.ptr, ws_bytes), "losses")
+        # tensor-core gradient kernels read bf16, channel-padded, per-level copies of dreg / dcls
+        self.use_tc_grads = self.net.use_tensor_cores and self.dtype == BF16
+        self.lvl_dcls = self.lvl_dreg = None
+        outs = [self.dcls, self.dreg, self.loss_out, ws]
+        if self.use_tc_grads:
+            feats = self.pyramid
+            self.cpad_cls, self.cpad_reg = -(-9 * C // 8) * 8, 40
+            self.lvl_dcls = [self.val((B, f.shape[1], f.shape[2], self.cpad_cls), BF16, "dcls_l%d" % i, keep=True)
+                             for i, f in enumerate(feats)]
+            self.lvl_dreg = [self.val((B, f.shape[1], f.shape[2], self.cpad_reg), BF16, "dreg_l%d" % i, keep=True)
+                             for i, f in enumerate(feats)]
+            outs += self.lvl_dcls + self.lvl_dreg
+            cells = (ctypes.c_int * 5)(*[f.shape[1] * f.shape[2] for f in feats])
+
+        def make():
+            args = [self.classification.ptr, self.regression.ptr,
+                    self.reg_t.ptr, self.lab_t.ptr if self.lab_t is not None else None,
+                    self.state_t.ptr if self.state_t is not None else None,
+                    self.cls_t.ptr if self.cls_t is not None else None, B, N, C, self.alpha,
+                    self.gamma, self.delta, 1.0, self.dcls.ptr, self.dreg.ptr,
+                    self.loss_out.ptr, ws.ptr, ws_bytes]
+            if self.use_tc_grads:
+                for v in self.lvl_dcls + self.lvl_dreg:      # zero the padding channels once
+                    self.tensor(v).zero_()
+                pc = (ctypes.c_void_p * 5)(*[v.ptr for v in self.lvl_dcls])
+                pr = (ctypes.c_void_p * 5)(*[v.ptr for v in self.lvl_dreg])
+                self._keepalive += [pc, pr, cells]
+                args += [pc, pr, cells, 5, self.cpad_cls, self.cpad_reg]
+            else:
+                args += [None, None, None, 0, 0, 0]
+            return _call("effdet_detection_losses", *args)
+        self.add("losses", ins, outs, make, "losses")
 
     # gradient bookkeeping ------------------------------------------------------------
     def grad_of(self, v):
@@ -205,8 +230,36 @@ class TrainPlan(engine.Plan):
                                cout), key + "_T")
         return wt
 
+    def _wgrad_tc(self, xs, dzs, key, cin, cout, k, dz_ld=None, name=""):
+        """bf16 operands, stride 1: tcgen05 weight gradient."""
+        lib = _lib.load()
+        n = len(xs)
+        d = _lib.WgradDesc()
+        d.n_groups = n
+        for i in range(n):
+            d.H[i], d.W[i] = xs[i].shape[1], xs[i].shape[2]
+            d.dz_ld[i] = dz_ld if dz_ld else 0
+        d.B, d.Cin, d.Cout, d.kh, d.kw, d.stride = self.B, cin, cout, k, k, 1
+        nsplit = lib.effdet_conv_wgrad_tc_splits(ctypes.byref(d))
+        part = self._scratch(nsplit * k * k * cin * cout, key + "_wg_partial")
+        gw = self.gw(key)
+
+        def make():
+            for i in range(n):
+                d.x[i], d.dz[i] = xs[i].ptr, dzs[i].ptr
+            d.dweight, d.partial, d.n_splits, d.accumulate = gw.data_ptr(), part.ptr, nsplit, 0
+            d.x_dtype = d.dz_dtype = BF16
+            self._keepalive.append(d)
+            return _call("effdet_conv_wgrad_tc", ctypes.byref(d))
+        flops = sum(2 * self.B * x.shape[1] * x.shape[2] * cin * cout * k * k for x in xs)
+        self.ops.append(Op("conv_wgrad_tc", list(xs) + list(dzs), [part], make, name,
+                           sum(v.nbytes for v in xs) + sum(v.nbytes for v in dzs), flops))
+
     def _wgrad(self, xs, dzs, key, cin, cout, k, stride, dz_ld=None, dz_bs=None, dz_off=None,
                dz_dtype=None, name=""):
+        if (self.net.use_tensor_cores and self.dtype == BF16 and stride == 1 and cin % 8 == 0
+                and dz_off is None and (dz_dtype is None or dz_dtype == BF16)):
+            return self._wgrad_tc(xs, dzs, key, cin, cout, k, name=name)
         lib = _lib.load()
         n = len(xs)
         d = _lib.WgradDesc()
@@ -267,18 +320,28 @@ class TrainPlan(engine.Plan):
             # bias: the concatenated (B,N,per) tensor is a dense (B*N/9, 9*per) matrix
             self._bias_grad(dz_final, B * N // A, cout, key + "/bias", 0, F32, name=key + "_dbias")
             offs = [int(o) * per * 4 for o in lvl_off]
-            self._wgrad(ht["xs"], [dz_final] * 5, key + "/kernel", Wd, cout, 3, 1,
-                        dz_ld=[cout] * 5, dz_bs=[N * per] * 5, dz_off=offs, dz_dtype=F32,
-                        name=key + "_wgrad")
-            wt = self._transposed_weight(key + "/kernel", 9, Wd, cout)
             layers = ht["layers"]
-            # data gradient into the last trunk layer's outputs (masked by its ReLU)
             targets = ht["xs"]
             gvals = [self.grad_of(t) for t in targets]
-            self._dgrad(dz_final, None, wt, cout, Wd, [g for g, _ in gvals], targets,
-                        masks=targets if layers else None, accumulate=[a for _, a in gvals],
-                        x_ld=[cout] * 5, x_bs=[N * per] * 5, x_off=offs, in_dtype=F32,
-                        shapes=[t.shape for t in targets], name=key + "_dgrad")
+            if self.use_tc_grads:
+                lv = self.lvl_dreg if ht["scope"] == "box_head" else self.lvl_dcls
+                cpad = self.cpad_reg if ht["scope"] == "box_head" else self.cpad_cls
+                self._wgrad_tc(ht["xs"], lv, key + "/kernel", Wd, cout, 3, dz_ld=cpad, name=key + "_wgrad")
+                wt = self._scratch(4, key + "_unused_T")
+                # data gradient: K = padded channel count of the level buffers (padding is zero)
+                self._dgrad_tc_padded(lv, key + "/kernel", cpad, cout, Wd, [g for g, _ in gvals], targets,
+                                      masks=targets if layers else None, accumulate=[a for _, a in gvals],
+                                      name=key + "_dgrad")
+            else:
+                self._wgrad(ht["xs"], [dz_final] * 5, key + "/kernel", Wd, cout, 3, 1,
+                            dz_ld=[cout] * 5, dz_bs=[N * per] * 5, dz_off=offs, dz_dtype=F32,
+                            name=key + "_wgrad")
+                wt = self._transposed_weight(key + "/kernel", 9, Wd, cout)
+                # data gradient into the last trunk layer's outputs (masked by its ReLU)
+                self._dgrad(dz_final, None, wt, cout, Wd, [g for g, _ in gvals], targets,
+                            masks=targets if layers else None, accumulate=[a for _, a in gvals],
+                            x_ld=[cout] * 5, x_bs=[N * per] * 5, x_off=offs, in_dtype=F32,
+                            shapes=[t.shape for t in targets], name=key + "_dgrad")
             for li in range(len(layers) - 1, -1, -1):
                 L = layers[li]
                 dzs = [self.gvals[id(y)] for y in L["ys"]]
@@ -341,6 +404,35 @@ class TrainPlan(engine.Plan):
             ins.append(panel)
         flops = sum(2 * self.B * s[1] * s[2] * cin * cout * taps for s in shapes)
         self.ops.append(Op("conv_dgrad_tc" if use_tc else "conv_dgrad", ins, list(dsts), make, name,
+                           sum(v.nbytes for v in ins) + sum(v.nbytes for v in dsts), flops))
+
+    def _dgrad_tc_padded(self, dzs, key, cpad, cout_fwd, cin_fwd, dsts, targets, masks, accumulate, name=""):
+        """Data gradient of a head's final 3x3 conv from the channel-padded bf16 level buffers."""
+        n = len(dsts)
+        panel = self.panel_for(key, 9, cin_fwd, cout_fwd, 1)
+
+        def make():
+            d = _lib.ConvDesc()
+            d.n_groups = n
+            for i in range(n):
+                d.x[i], d.y[i] = dzs[i].ptr, dsts[i].ptr
+                d.residual[i] = dsts[i].ptr if accumulate[i] else None
+                d.relu_mask[i] = masks[i].ptr if masks else None
+                d.H[i], d.W[i] = targets[i].shape[1], targets[i].shape[2]
+            # Cin = padded channel count: the panel's K extent (Cout_fwd rounded to 64) has zeros
+            # beyond Cout_fwd and the buffers have zeros in their padding channels
+            d.B, d.Cin, d.Cout, d.kh, d.kw, d.stride = self.B, cpad, cin_fwd, 3, 3, 1
+            d.weight = None
+            d.act, d.in_dtype, d.out_dtype = ACT_NONE, BF16, BF16
+            d.weight_bf16 = panel.ptr if isinstance(panel, Val) else panel.data_ptr()
+            d.allow_tensor_core = 1
+            self._keepalive.append(d)
+            return _call("effdet_conv2d", ctypes.byref(d))
+        ins = list(dzs) + (list(masks) if masks else []) + [dsts[i] for i in range(n) if accumulate[i]]
+        if isinstance(panel, Val):
+            ins.append(panel)
+        flops = sum(2 * self.B * t.shape[1] * t.shape[2] * cout_fwd * cin_fwd * 9 for t in targets)
+        self.ops.append(Op("conv_dgrad_tc", ins, list(dsts), make, name,
                            sum(v.nbytes for v in ins) + sum(v.nbytes for v in dsts), flops))
 
     def _bn_backward(self, rec, dy):
@@ -645,6 +737,10 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev):
     losses = plan.tensor(plan.loss_out).cpu().numpy().tolist()
 
     prof = plan.profile(iters=3)
+    if os.environ.get("EFFDET_DUMP_OPS"):
+        import json
+        with open(os.environ["EFFDET_DUMP_OPS"], "w") as f:
+            json.dump(prof, f)
     by_kind = {}
     for r in prof:
         k2 = by_kind.setdefault(r["kind"], dict(ms=0.0, bytes=0, flops=0, n=0))

@@ -214,13 +214,19 @@ int effdet_bifpn_node(const void *in0, int mode0, const void *in1, const void *i
  * cls (B,N) i32 written by effdet_anchor_targets.  Gradients: dcls_logits (B,N,C) f32 w.r.t.
  * the class head's pre-sigmoid outputs, dreg (B,N,4) f32; both already divided by
  * max(1,#positive) and multiplied by grad_scale.  out8 (device f32[8]): [0] focal loss,
- * [1] smooth-L1 loss, [2]/[3] #positive anchors, [4]/[5] 1/normaliser. */
+ * [1] smooth-L1 loss, [2]/[3] #positive anchors, [4]/[5] 1/normaliser.
+ * Optional (n_levels > 0): a second, bf16 copy of both gradients in per-pyramid-level dense
+ * buffers (B, cells_l, cpad) with channel = anchor*per + k (what the TMA-fed tensor-core
+ * gradient kernels read); level_cells_host[l] = H_l*W_l; padding channels are not written. */
 size_t effdet_detection_losses_workspace_size(void);
 int effdet_detection_losses(const float *classification, const float *regression,
                             const float *regression_t, const float *labels_t, const int8_t *state,
                             const int32_t *cls, int B, size_t N, int C, float alpha, float gamma,
                             float delta, float grad_scale, float *dcls_logits, float *dreg,
-                            float *out8, void *workspace, size_t workspace_bytes, void *stream);
+                            float *out8, void *workspace, size_t workspace_bytes,
+                            void *const *dcls_levels_host, void *const *dreg_levels_host,
+                            const int *level_cells_host, int n_levels, int cpad_cls, int cpad_reg,
+                            void *stream);
 
 /* BiFPN fusion forward keeping the fused tensor (training): same semantics as the fusion stage
  * of effdet_bifpn_node (model.py:154-194/226-266, layers.py:26-31). */
@@ -295,6 +301,11 @@ typedef struct effdet_wgrad_desc {
 } effdet_wgrad_desc;
 int effdet_conv_wgrad_splits(const effdet_wgrad_desc *desc);
 int effdet_conv_wgrad(const effdet_wgrad_desc *desc, void *stream);
+/* Tensor-core (tcgen05, MN-major operands fed by TMA) version for bf16 operands, stride 1,
+ * k in {1,3}: x dense (B,H,W,Cin), dz (B,H,W,dz_ld) bf16 with the first Cout channels used.
+ * partial: effdet_conv_wgrad_tc_splits(desc) * kh*kw*Cin*Cout floats. */
+int effdet_conv_wgrad_tc_splits(const effdet_wgrad_desc *desc);
+int effdet_conv_wgrad_tc(const effdet_wgrad_desc *desc, void *stream);
 /* Data gradient of a strided (stride 2) 1x1/3x3 SAME convolution; weight is the forward HWIO
  * kernel.  Stride-1 data gradients use effdet_conv2d on effdet_conv_weight_transpose'd weights. */
 int effdet_conv_dgrad_strided(const void *dz, const float *weight, void *dx, int accumulate, int B,

@@ -20,7 +20,7 @@ dcls=torch.empty((B,N,C),device="cuda"); dreg=torch.empty((B,N,4),device="cuda")
 wsb=lib.effdet_detection_losses_workspace_size(); ws=torch.empty(wsb,dtype=torch.uint8,device="cuda")
 st=d(state,torch.int8); cl=d(np.where(state==1,clsid,-1),torch.int32)
 for dense in (True,False):
-    _lib.call("effdet_detection_losses",pd.data_ptr(),rd.data_ptr(),rtd.data_ptr(),labd.data_ptr() if dense else None,st.data_ptr(),cl.data_ptr(),B,N,C,0.25,1.5,1.0,1.0,dcls.data_ptr(),dreg.data_ptr(),out8.data_ptr(),ws.data_ptr(),wsb,_lib.stream_ptr())
+    _lib.call("effdet_detection_losses",pd.data_ptr(),rd.data_ptr(),rtd.data_ptr(),labd.data_ptr() if dense else None,st.data_ptr(),cl.data_ptr(),B,N,C,0.25,1.5,1.0,1.0,dcls.data_ptr(),dreg.data_ptr(),out8.data_ptr(),ws.data_ptr(),wsb,None,None,None,0,0,0,_lib.stream_ptr())
     g=dcls.cpu().numpy()
     err=np.abs(g-want); i=np.unravel_index(err.argmax(),g.shape)
     print(dense, out8.cpu().numpy(), err.max(), np.abs(want).max(), i, g[i], want[i], p[i], lab[i[0],i[1]], )

@@ -154,3 +154,39 @@ def test_conv3x3_dgrad_tc_with_relu_mask_and_accumulate():
     out = prev.clone()
     _run([dz], _panel(w, 1), cout, cin, 3, B, _lib.BF16, res=[out], mask=[mask], ys=[out])
     assert rel_err(out.float().cpu().numpy(), want) < 6e-3
+
+
+@pytest.mark.parametrize("k,cin,cout,ldz,sizes,B", [(3, 64, 64, 64, [16, 8, 4, 2, 1], 4), (1, 112, 64, 64, [16], 2),
+                                                      (3, 64, 36, 40, [8, 4], 3), (1, 320, 64, 64, [8], 2),
+                                                      (3, 88, 180, 184, [10, 5], 2), (3, 64, 810, 816, [4], 1)])
+def test_conv_wgrad_tc(k, cin, cout, ldz, sizes, B):
+    """tcgen05 weight gradient with MN-major TMA-fed operands vs fp64 autograd on the same
+    bf16-rounded operands (dz lives in channel-padded per-level buffers)."""
+    from efficientdet_b200 import _lib
+    from oracle import graph
+    lib = _lib.load()
+    rng = np.random.default_rng(k * 1000 + cin + cout)
+    w = torch.zeros((k, k, cin, cout), dtype=torch.float64, requires_grad=True)
+    d = _lib.WgradDesc()
+    d.n_groups = len(sizes)
+    keep, total = [], 0
+    for i, H in enumerate(sizes):
+        x = _d(rng.standard_normal((B, H, H, cin)).astype(np.float32), torch.bfloat16)
+        dz = torch.zeros((B, H, H, ldz), dtype=torch.bfloat16, device="cuda")
+        dz[..., :cout] = _d(rng.standard_normal((B, H, H, cout)).astype(np.float32), torch.bfloat16)
+        dz[..., cout:] = 7.0          # padding channels must be ignored
+        keep += [x, dz]
+        y = graph.conv2d(x.double().cpu().permute(0, 3, 1, 2), w, 1)
+        total = total + (y * dz[..., :cout].double().cpu().permute(0, 3, 1, 2)).sum()
+        d.x[i], d.dz[i], d.H[i], d.W[i], d.dz_ld[i] = x.data_ptr(), dz.data_ptr(), H, H, ldz
+    total.backward()
+    d.B, d.Cin, d.Cout, d.kh, d.kw, d.stride = B, cin, cout, k, k, 1
+    d.x_dtype = d.dz_dtype = _lib.BF16
+    ns = lib.effdet_conv_wgrad_tc_splits(ctypes.byref(d))
+    assert ns > 0
+    part = torch.full((ns * k * k * cin * cout,), float("nan"), device="cuda")
+    out = torch.full((k, k, cin, cout), float("nan"), device="cuda")
+    d.dweight, d.partial, d.n_splits, d.accumulate = out.data_ptr(), part.data_ptr(), ns, 0
+    _lib.call("effdet_conv_wgrad_tc", ctypes.byref(d), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert rel_err(out.cpu().numpy(), w.grad.numpy()) < 1e-4

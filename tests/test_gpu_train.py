@@ -59,7 +59,7 @@ def test_losses_fwd_bwd():
         _lib.call("effdet_detection_losses", pd.data_ptr(), rd.data_ptr(), rtd.data_ptr(),
                   labd.data_ptr() if dense else None, st.data_ptr(), cl.data_ptr(), B, N, C, 0.25, 1.5,
                   1.0, 1.0, dcls.data_ptr(), dreg.data_ptr(), out8.data_ptr(), ws.data_ptr(), wsb,
-                  _lib.stream_ptr())
+                  None, None, None, 0, 0, 0, _lib.stream_ptr())
         o = out8.cpu().numpy()
         assert abs(o[0] - float(fl)) / float(fl) < 1e-4, (o, float(fl))
         assert abs(o[1] - float(sl)) / float(sl) < 1e-4
