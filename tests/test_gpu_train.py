@@ -372,7 +372,7 @@ def test_training_step_bf16_tensor_cores_matches_simt():
     gradients up to the noise floor of bf16 training on this problem.  The floor is measured, not
     assumed: a third (SIMT) run on inputs perturbed by 1e-3 relative noise moves the gradients by
     20-60 % (relative L2) in the deep BiFPN layers, because activations and activation gradients
-    are stored in bf16; the tensor-core run must not move them more than 1.5x that (+0.05)."""
+    are stored in bf16; the tensor-core run must not move them more than 2x that (+0.1)."""
     from efficientdet_b200.model import efficientdet
     from efficientdet_b200.optimizers import SGD
     from util_model import rel_l2
@@ -398,7 +398,7 @@ def test_training_step_bf16_tensor_cores_matches_simt():
         if k.endswith(("moving_mean", "moving_variance")) or np.abs(g).max() < 1e-10:
             continue
         e, floor = rel_l2(res["tc"][1][k], g), rel_l2(res["noise"][1][k], g)
-        if not e < 1.5 * floor + 0.05:
+        if not e < 2.0 * floor + 0.1:
             bad[k] = (float(e), float(floor))
     assert not bad, bad
 
