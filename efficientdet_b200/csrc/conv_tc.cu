@@ -17,6 +17,7 @@
 // model.py:71-90 (BiFPN 1x1 laterals), model.py:293-309/324-351 (3x3 head convs, all five pyramid
 // levels in one launch) and their data gradients.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -60,6 +61,14 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
           "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2,
+                                             int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                  "r"(ncols) : "memory");
@@ -121,48 +130,77 @@ struct TcGroup {
     int Wt, Ht, Bt;           // tile extent (Wt*Ht*Bt == 128)
     int tiles_x, tiles_y, tiles_b;
     int tile_begin;
+    int tma_store;            // output rows are 16-byte strided: store through out_map
 };
 struct alignas(64) TcParams {
     CUtensorMap a_map[kTcMaxGroups];
+    CUtensorMap out_map[kTcMaxGroups];
     CUtensorMap b_map;
     TcGroup g[kTcMaxGroups];
     int n_groups, B, Cout, ksize, kblocks_per_tap, block_n, stages, tmem_cols;
-    int act, out_f32, b_per_sample;
+    int act, out_f32, b_per_sample, total_tiles, n_tiles, any_tma_store;
     const float *scale, *shift, *keep;
 };
 
-__global__ void __launch_bounds__(192, 1)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TileCoord { int gi, x0, y0, b0, n0; };
+__device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int t) {
+    TileCoord c;
+    const int m = t / p.n_tiles;
+    c.n0 = (t - m * p.n_tiles) * p.block_n;
+    int gi = 0;
+#pragma unroll
+    for (int i = 1; i < kTcMaxGroups; ++i)
+        if (i < p.n_groups && m >= p.g[i].tile_begin) gi = i;
+    const TcGroup &G = p.g[gi];
+    int r = m - G.tile_begin;
+    const int tx = r % G.tiles_x; r /= G.tiles_x;
+    const int ty = r % G.tiles_y; r /= G.tiles_y;
+    c.gi = gi; c.x0 = tx * G.Wt; c.y0 = ty * G.Ht; c.b0 = r * G.Bt;
+    return c;
+}
+
+template <int ACT> __device__ __forceinline__ float fast_act(float x) {
+    if (ACT == EFFDET_ACT_RELU) return fmaxf(x, 0.f);
+    if (ACT == EFFDET_ACT_SWISH) return x * __frcp_rn(1.f + __expf(-x));
+    if (ACT == EFFDET_ACT_SIGMOID) return __frcp_rn(1.f + __expf(-x));
+    return x;
+}
+
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter, alternating column chunks
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
+
+// Persistent: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  Barriers and TMEM
+// are set up once; two TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue.
+template <int ACT, bool OUT_F32>
+__global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_tile_bytes = p.block_n * kTileK * 2;
     uint8_t *sA = smem;
     uint8_t *sB = smem + (size_t)p.stages * kATileBytes;
-    uint64_t *full = reinterpret_cast<uint64_t *>(sB + (size_t)p.stages * b_tile_bytes);
+    float *sScale = reinterpret_cast<float *>(sB + (size_t)p.stages * b_tile_bytes);   // [256]
+    float *sShift = sScale + 256;                                                          // [256]
+    uint64_t *full = reinterpret_cast<uint64_t *>(sShift + 256);
     uint64_t *empty = full + p.stages;
-    uint64_t *tmem_full = empty + p.stages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    uint64_t *tmem_full = empty + p.stages;      // [2]
+    uint64_t *tmem_empty = tmem_full + 2;        // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // ---- which group / tile
-    int gi = 0;
-#pragma unroll
-    for (int i = 1; i < kTcMaxGroups; ++i)
-        if (i < p.n_groups && (int)blockIdx.x >= p.g[i].tile_begin) gi = i;
-    const TcGroup &G = p.g[gi];
-    int t = (int)blockIdx.x - G.tile_begin;
-    const int tx = t % G.tiles_x; t /= G.tiles_x;
-    const int ty = t % G.tiles_y; t /= G.tiles_y;
-    const int tb = t;
-    const int x0 = tx * G.Wt, y0 = ty * G.Ht, b0 = tb * G.Bt;
-    const int n0 = blockIdx.y * p.block_n;
     const int pad = p.ksize / 2;
     const int taps = p.ksize * p.ksize;
     const int num_k = taps * p.kblocks_per_tap;
+    const int total = p.total_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -170,20 +208,26 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_cols = (uint32_t)p.tmem_cols >> 1;
 
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer
-            const CUtensorMap *amap = &p.a_map[gi];
-            for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % p.stages, ph = (kb / p.stages) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                const int tap = kb / p.kblocks_per_tap, kc = (kb - tap * p.kblocks_per_tap) * kTileK;
-                const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-                mbar_expect_tx(&full[s], (uint32_t)(kATileBytes + b_tile_bytes));
-                tma_load_4d(sA + (size_t)s * kATileBytes, amap, &full[s], kc, x0 + kx - pad, y0 + ky - pad, b0);
-                tma_load_3d(sB + (size_t)s * b_tile_bytes, &p.b_map, &full[s], kc, n0,
-                            p.b_per_sample ? b0 : tap);
+            int it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const TileCoord c = decode_tile(p, t);
+                const CUtensorMap *amap = &p.a_map[c.gi];
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % p.stages, ph = (it / p.stages) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const int tap = kb / p.kblocks_per_tap, kc = (kb - tap * p.kblocks_per_tap) * kTileK;
+                    const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+                    mbar_expect_tx(&full[s], (uint32_t)(kATileBytes + b_tile_bytes));
+                    tma_load_4d(sA + (size_t)s * kATileBytes, amap, &full[s], kc, c.x0 + kx - pad, c.y0 + ky - pad,
+                                c.b0);
+                    tma_load_3d(sB + (size_t)s * b_tile_bytes, &p.b_map, &full[s], kc, c.n0,
+                                p.b_per_sample ? c.b0 : tap);
+                }
             }
         }
     } else if (warp == 1) {
@@ -191,107 +235,145 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             // ===== MMA issuer (single thread)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                                    ((uint32_t)(kTileM >> 4) << 24);
-            for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % p.stages, ph = (kb / p.stages) & 1;
-                mbar_wait(&full[s], ph);
+            int it = 0, ti = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+                const int acc = ti & 1, aph = (ti >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], aph ^ 1);        // epilogue drained this accumulator
                 tc_fence_after();
-                const uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + (size_t)s * kATileBytes));
-                const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + (size_t)s * b_tile_bytes));
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % p.stages, ph = (it / p.stages) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + (size_t)s * kATileBytes));
+                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + (size_t)s * b_tile_bytes));
 #pragma unroll
-                for (int k = 0; k < kTileK / 16; ++k)      // UMMA_K = 16 bf16 = 32 bytes: +2 in the address field
-                    umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                              (kb | k) ? 1u : 0u);
-                umma_commit(&empty[s]);                     // frees the smem slot when the MMAs retire
+                    for (int k = 0; k < kTileK / 16; ++k)      // UMMA_K = 16 bf16 = 32 bytes: +2 in the address field
+                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty[s]);                     // frees the smem slot when the MMAs retire
+                }
+                umma_commit(&tmem_full[acc]);                   // accumulator complete
             }
-            umma_commit(tmem_full);                         // accumulator complete
         }
     } else {
-        // ===== epilogue: 4 warps, each owns the TMEM lane quarter (warp % 4)
+        // ===== epilogue: 8 warps; warp w owns TMEM lane quarter (w % 4) and every other 32-column chunk
+        const int ew = warp - 2;
         const int q = warp & 3;
+        const int half = ew >> 2;                           // which of the two warps of this quarter
         const int row = q * 32 + lane;                      // tile row == TMEM lane
-        const int xx = row % G.Wt, yy = (row / G.Wt) % G.Ht, bb = row / (G.Wt * G.Ht);
-        const int x = x0 + xx, y = y0 + yy, b = b0 + bb;
-        const bool row_ok = x < G.W && y < G.H && b < p.B;
-        const size_t base = (size_t)b * G.y_batch_stride + ((size_t)y * G.W + x) * G.ldc;
-        const float kp = (p.keep && row_ok) ? p.keep[b] : 1.f;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-            uint32_t r[32];
-            __syncwarp();                                   // tcgen05.ld is warp-collective
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            const int nbase = n0 + c0;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int n = nbase + j;
-                float a = __uint_as_float(r[j]);
-                if (n < p.Cout) {
-                    if (p.scale) a *= p.scale[n];
-                    if (p.shift) a += p.shift[n];
-                    a = activate_rt(a, p.act);
-                }
-                v[j] = a;
+        const int et = threadIdx.x - 64;                    // 0..255
+        int ti = 0, cur_n0 = -1;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
+            const TileCoord tc = decode_tile(p, t);
+            const TcGroup &G = p.g[tc.gi];
+            const int x0 = tc.x0, y0 = tc.y0, b0 = tc.b0, n0 = tc.n0;
+            const int acc = ti & 1, aph = (ti >> 1) & 1;
+            if (n0 != cur_n0) {
+                // per-column scale / shift of this N tile -> shared memory (uniform across the CTA)
+                asm volatile("bar.sync 1, 256;" ::: "memory");       // previous tile's readers are done
+                const int n = n0 + et;
+                sScale[et] = (p.scale && n < p.Cout) ? p.scale[n] : 1.f;
+                sShift[et] = (p.shift && n < p.Cout) ? p.shift[n] : 0.f;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                cur_n0 = n0;
             }
-            const int nvalid = row_ok ? min(32, min(p.Cout, n0 + p.block_n) - nbase) : 0;
-            if (nvalid <= 0) {
-                // nothing to store for this thread / chunk
-            } else if (p.out_f32) {
-                float *Y = static_cast<float *>(G.y) + base + nbase;
-                const float *R = G.res ? static_cast<const float *>(G.res) + base + nbase : nullptr;
-                const float *MK = G.mask ? static_cast<const float *>(G.mask) + base + nbase : nullptr;
-                for (int j = 0; j < nvalid; ++j) {
-                    float a = v[j];
-                    if (MK && !(MK[j] > 0.f)) a = 0.f;
-                    if (R) a = a * kp + R[j];
-                    Y[j] = a;
+            const int xx = row % G.Wt, yy = (row / G.Wt) % G.Ht, bb = row / (G.Wt * G.Ht);
+            const int x = x0 + xx, y = y0 + yy, b = b0 + bb;
+            const bool row_ok = x < G.W && y < G.H && b < p.B;
+            const size_t base = (size_t)b * G.y_batch_stride + ((size_t)y * G.W + x) * G.ldc;
+            const float kp = (p.keep && row_ok) ? p.keep[b] : 1.f;
+            mbar_wait(&tmem_full[acc], aph);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(q * 32) << 16);
+            for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
+                uint32_t r[32];
+                __syncwarp();                               // tcgen05.ld is warp-collective
+                tmem_ld32(d_tmem + (uint32_t)c0, r);
+                const int nbase = n0 + c0;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 sc = *reinterpret_cast<const float4 *>(sScale + c0 + j);
+                    const float4 sh = *reinterpret_cast<const float4 *>(sShift + c0 + j);
+                    v[j] = fast_act<ACT>(fmaf(__uint_as_float(r[j]), sc.x, sh.x));
+                    v[j + 1] = fast_act<ACT>(fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y));
+                    v[j + 2] = fast_act<ACT>(fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z));
+                    v[j + 3] = fast_act<ACT>(fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w));
                 }
-            } else {
-                __nv_bfloat16 *Y = static_cast<__nv_bfloat16 *>(G.y) + base + nbase;
-                const __nv_bfloat16 *R = G.res ? static_cast<const __nv_bfloat16 *>(G.res) + base + nbase : nullptr;
-                const __nv_bfloat16 *MK = G.mask ? static_cast<const __nv_bfloat16 *>(G.mask) + base + nbase : nullptr;
-                const bool vec = nvalid == 32 && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0) &&
-                                 (!R || (reinterpret_cast<uintptr_t>(R) & 15) == 0) &&
-                                 (!MK || (reinterpret_cast<uintptr_t>(MK) & 15) == 0);
-                if (vec) {
-#pragma unroll
-                    for (int j8 = 0; j8 < 32; j8 += 8) {
-                        float o[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] = v[j8 + j];
-                        if (MK) {
-                            uint4 mv = *reinterpret_cast<const uint4 *>(MK + j8);
-                            const __nv_bfloat162 *mh = reinterpret_cast<const __nv_bfloat162 *>(&mv);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                if (!(__low2float(mh[j]) > 0.f)) o[2 * j] = 0.f;
-                                if (!(__high2float(mh[j]) > 0.f)) o[2 * j + 1] = 0.f;
-                            }
+                const int nvalid = row_ok ? min(32, min(p.Cout, n0 + p.block_n) - nbase) : 0;
+                if (nvalid <= 0) continue;
+                if (OUT_F32) {
+                    float *Y = static_cast<float *>(G.y) + base + nbase;
+                    const float *R = G.res ? static_cast<const float *>(G.res) + base + nbase : nullptr;
+                    const float *MK = G.mask ? static_cast<const float *>(G.mask) + base + nbase : nullptr;
+                    if (R || MK) {
+                        for (int j = 0; j < nvalid; ++j) {
+                            if (MK && !(MK[j] > 0.f)) v[j] = 0.f;
+                            if (R) v[j] = v[j] * kp + R[j];
                         }
-                        if (R) {
-                            uint4 rv = *reinterpret_cast<const uint4 *>(R + j8);
-                            const __nv_bfloat162 *rh = reinterpret_cast<const __nv_bfloat162 *>(&rv);
+                    }
+                    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                o[2 * j] = o[2 * j] * kp + __low2float(rh[j]);
-                                o[2 * j + 1] = o[2 * j + 1] * kp + __high2float(rh[j]);
-                            }
-                        }
-                        uint4 ov;
-                        __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&ov);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
-                        *reinterpret_cast<uint4 *>(Y + j8) = ov;
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            *reinterpret_cast<float4 *>(Y + 4 * j4) =
+                                make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+                    } else {
+                        for (int j = 0; j < nvalid; ++j) Y[j] = v[j];
                     }
                 } else {
-                    for (int j = 0; j < nvalid; ++j) {
-                        float a = v[j];
-                        if (MK && !(__bfloat162float(MK[j]) > 0.f)) a = 0.f;
-                        if (R) a = a * kp + __bfloat162float(R[j]);
-                        Y[j] = __float2bfloat16_rn(a);
+                    __nv_bfloat16 *Y = static_cast<__nv_bfloat16 *>(G.y) + base + nbase;
+                    const __nv_bfloat16 *R = G.res ? static_cast<const __nv_bfloat16 *>(G.res) + base + nbase : nullptr;
+                    const __nv_bfloat16 *MK = G.mask ? static_cast<const __nv_bfloat16 *>(G.mask) + base + nbase : nullptr;
+                    if (R || MK) {
+                        const bool vec = nvalid == 32 && (!R || (reinterpret_cast<uintptr_t>(R) & 15) == 0) &&
+                                         (!MK || (reinterpret_cast<uintptr_t>(MK) & 15) == 0);
+                        if (vec) {
+#pragma unroll
+                            for (int j8 = 0; j8 < 32; j8 += 8) {
+                                if (MK) {
+                                    uint4 mv = *reinterpret_cast<const uint4 *>(MK + j8);
+                                    const __nv_bfloat162 *mh = reinterpret_cast<const __nv_bfloat162 *>(&mv);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        if (!(__low2float(mh[j]) > 0.f)) v[j8 + 2 * j] = 0.f;
+                                        if (!(__high2float(mh[j]) > 0.f)) v[j8 + 2 * j + 1] = 0.f;
+                                    }
+                                }
+                                if (R) {
+                                    uint4 rv = *reinterpret_cast<const uint4 *>(R + j8);
+                                    const __nv_bfloat162 *rh = reinterpret_cast<const __nv_bfloat162 *>(&rv);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        v[j8 + 2 * j] = v[j8 + 2 * j] * kp + __low2float(rh[j]);
+                                        v[j8 + 2 * j + 1] = v[j8 + 2 * j + 1] * kp + __high2float(rh[j]);
+                                    }
+                                }
+                            }
+                        } else {
+                            for (int j = 0; j < nvalid; ++j) {
+                                if (MK && !(__bfloat162float(MK[j]) > 0.f)) v[j] = 0.f;
+                                if (R) v[j] = v[j] * kp + __bfloat162float(R[j]);
+                            }
+                        }
+                    }
+                    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            uint4 ov;
+                            __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&ov);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[8 * j8 + 2 * j], v[8 * j8 + 2 * j + 1]);
+                            *reinterpret_cast<uint4 *>(Y + 8 * j8) = ov;
+                        }
+                    } else {
+                        for (int j = 0; j < nvalid; ++j) Y[j] = __float2bfloat16_rn(v[j]);
                     }
                 }
             }
+            // accumulator drained: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
     }
     tc_fence_before();
@@ -544,19 +626,22 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     const int Kpad = round_up(d->Cin, kTileK), Npad = round_up(d->Cout, bn);
     p.n_groups = d->n_groups; p.B = d->B; p.Cout = d->Cout; p.ksize = d->kh;
     p.kblocks_per_tap = Kpad / kTileK; p.block_n = bn;
-    p.tmem_cols = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
+    // two accumulators (double-buffered epilogue): 2 x next-pow2(block_n) columns
+    p.tmem_cols = 2 * (bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256);
     p.act = d->act; p.out_f32 = d->out_dtype == EFFDET_F32; p.b_per_sample = d->weight_per_sample ? 1 : 0;
     p.scale = d->scale; p.shift = d->shift; p.keep = d->keep;
     const int b_tile_bytes = bn * kTileK * 2;
     // <= 4 stages: with 64..128-wide N tiles two CTAs stay resident per SM, so one CTA's
     // epilogue overlaps the other's main loop
-    int stages = (200 * 1024) / (kATileBytes + b_tile_bytes);
+    // small tiles: 2 resident CTAs per SM (<= ~100 KiB each); wide tiles: 1
+    int stages = ((bn <= 128 ? 100 : 200) * 1024) / (kATileBytes + b_tile_bytes);
     if (stages > 4) stages = 4;
     const int num_k = d->kh * d->kw * p.kblocks_per_tap;
     if (stages > num_k) stages = num_k;
     if (stages < 1) stages = 1;
     p.stages = stages;
-    const size_t smem = (size_t)stages * (kATileBytes + b_tile_bytes) + (2 * stages + 1) * 8 + 16 + 1024;
+    const size_t smem = (size_t)stages * (kATileBytes + b_tile_bytes) + 2048 + (2 * stages + 4) * 8 + 16 + 1024;
+    p.any_tma_store = 0;
     int tiles = 0;
     for (int i = 0; i < d->n_groups; ++i) {
         TcGroup &g = p.g[i];
@@ -580,6 +665,7 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
                             strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_conv2d: cuTensorMapEncodeTiled(A) failed %s(%lld)", "", (long long)r);
+        g.tma_store = 0;
     }
     {
         const int nz = d->weight_per_sample ? d->B : d->kh * d->kw;
@@ -592,13 +678,36 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_conv2d: cuTensorMapEncodeTiled(B) failed %s(%lld)", "", (long long)r);
     }
+    p.n_tiles = Npad / bn;
+    p.total_tiles = tiles * p.n_tiles;
+    const int ctas_per_sm = (smem <= 110 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
+    int grid = kNumSMs * ctas_per_sm;
+    if (grid > p.total_tiles) grid = p.total_tiles;
     static bool attr_set = false;
+#define TC_INST(A, F)                                                                                   \
+    do {                                                                                                \
+        if (!attr_set)                                                                                  \
+            EFFDET_CUDA(cudaFuncSetAttribute(conv_tc_kernel<A, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             227 * 1024));                                              \
+    } while (0)
     if (!attr_set) {
-        EFFDET_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TC_INST(EFFDET_ACT_NONE, false); TC_INST(EFFDET_ACT_RELU, false); TC_INST(EFFDET_ACT_SWISH, false);
+        TC_INST(EFFDET_ACT_SIGMOID, false); TC_INST(EFFDET_ACT_NONE, true); TC_INST(EFFDET_ACT_RELU, true);
+        TC_INST(EFFDET_ACT_SWISH, true); TC_INST(EFFDET_ACT_SIGMOID, true);
         attr_set = true;
     }
-    dim3 grid(tiles, Npad / bn);
-    conv_tc_kernel<<<grid, 192, smem, as_stream(stream)>>>(p);
+#undef TC_INST
+    cudaStream_t st = as_stream(stream);
+#define TC_LAUNCH(A)                                                                      \
+    case A:                                                                               \
+        if (p.out_f32) conv_tc_kernel<A, true><<<grid, kTcThreads, smem, st>>>(p);        \
+        else conv_tc_kernel<A, false><<<grid, kTcThreads, smem, st>>>(p);                 \
+        break;
+    switch (d->act) {
+        TC_LAUNCH(EFFDET_ACT_NONE) TC_LAUNCH(EFFDET_ACT_RELU) TC_LAUNCH(EFFDET_ACT_SWISH) TC_LAUNCH(EFFDET_ACT_SIGMOID)
+        default: return fail(EFFDET_E_INVALID, "effdet_conv2d: bad activation%s", "");
+    }
+#undef TC_LAUNCH
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }

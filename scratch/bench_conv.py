@@ -1,0 +1,27 @@
+import sys, ctypes, numpy as np, torch
+sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+from efficientdet_b200 import _lib
+from test_gpu_conv_tc import _panel, _d
+cases={"expand2a":(32,256,16,96,1,2),"expand3a":(32,128,24,144,1,2),"project2b":(32,128,144,24,1,0),"head":(32,64,64,64,3,1),"project7a":(32,16,1152,320,1,0)}
+name=sys.argv[1] if len(sys.argv)>1 else "expand2a"
+B,H,cin,cout,k,act=cases[name]
+rng=np.random.default_rng(0)
+x=torch.randn((B,H,H,cin),device="cuda").to(torch.bfloat16)
+w=(rng.standard_normal((k,k,cin,cout))/np.sqrt(k*k*cin)).astype(np.float32)
+panel=_panel(w,0)
+sc=torch.ones(cout,device="cuda"); sh=torch.zeros(cout,device="cuda")
+y=torch.empty((B,H,H,cout),device="cuda",dtype=torch.bfloat16)
+d=_lib.ConvDesc(); d.n_groups=1; d.x[0]=x.data_ptr(); d.y[0]=y.data_ptr(); d.H[0]=d.W[0]=H
+d.B,d.Cin,d.Cout,d.kh,d.kw,d.stride=B,cin,cout,k,k,1
+d.scale=sc.data_ptr(); d.shift=sh.data_ptr(); d.act=act; d.in_dtype=d.out_dtype=_lib.BF16
+d.weight_bf16=panel.data_ptr(); d.allow_tensor_core=1
+st=_lib.stream_ptr()
+for _ in range(3): _lib.call("effdet_conv2d",ctypes.byref(d),st)
+torch.cuda.synchronize()
+e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): _lib.call("effdet_conv2d",ctypes.byref(d),st)
+e1.record(); torch.cuda.synchronize()
+ms=e0.elapsed_time(e1)/10
+byt=B*H*H*(cin+cout)*2
+print(name,"ms",ms,"GB/s",byt/ms/1e6,"TF/s",2*B*H*H*cin*cout*k*k/ms/1e9)
