@@ -108,6 +108,147 @@ __global__ void dwconv_kernel(const T *__restrict__ x, const float *__restrict__
     }
 }
 
+// ------------------------------------------------------------------ depthwise conv, tiled
+// Shared-memory version: one block = 8 x 16 output pixels x CB channels.  The input tile
+// (with its k-1 halo, zero-filled outside the image == TF SAME padding) is staged once with
+// 16-byte cp.async copies, the k*k*CB weights sit next to it, and every thread produces a strip
+// of 4 horizontally adjacent outputs for one 16-byte channel vector, so an input vector is read
+// from shared memory once per kernel ROW and reused across the strip.  Lanes run along the
+// channel vectors, so shared and global accesses of a warp are contiguous 128-byte lines.
+constexpr int kDwTW = 16, kDwTH = 8, kDwStrip = 4;
+
+__device__ __forceinline__ void cp_async16_zfill(void *dst, const void *src, bool valid) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+template <typename T, int CV, int K, int S, int NCV, int ACT>
+__global__ void __launch_bounds__(NCV * (kDwTW / kDwStrip) * kDwTH)
+dwconv_tiled_kernel(const T *__restrict__ x, const float *__restrict__ w, const float *__restrict__ scale,
+                    const float *__restrict__ shift, T *__restrict__ y, float *__restrict__ se_sum, int H,
+                    int W, int Ho, int Wo, int C, int pad_t, int pad_l, int tiles_x) {
+    constexpr int CB = NCV * CV;
+    constexpr int IH = (kDwTH - 1) * S + K, IW = (kDwTW - 1) * S + K;
+    constexpr int NT = NCV * (kDwTW / kDwStrip) * kDwTH;
+    constexpr int NIN = (kDwStrip - 1) * S + K;            // input vectors per strip and kernel row
+    extern __shared__ __align__(16) uint8_t dsm[];
+    T *sIn = reinterpret_cast<T *>(dsm);                                   // [IH][IW][CB]
+    float *sW = reinterpret_cast<float *>(dsm + (size_t)IH * IW * CB * sizeof(T));   // [K*K][CB]
+    float *sRed = sW + K * K * CB;                                         // [strips][CB] (SE only)
+
+    const int b = blockIdx.z, cb0 = blockIdx.y * CB;
+    const int ty0 = (blockIdx.x / tiles_x) * kDwTH, tx0 = (blockIdx.x % tiles_x) * kDwTW;
+    const int iy0 = ty0 * S - pad_t, ix0 = tx0 * S - pad_l;
+    const T *xb = x + (size_t)b * H * W * C;
+    // ---- stage input tile
+    for (int i = threadIdx.x; i < IH * IW * NCV; i += NT) {
+        const int v = i % NCV, pix = i / NCV;
+        const int py = pix / IW, px = pix - py * IW;
+        const int gy = iy0 + py, gx = ix0 + px, c = cb0 + v * CV;
+        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W && c < C;
+        const T *src = ok ? xb + ((size_t)gy * W + gx) * C + c : xb;
+        cp_async16_zfill(sIn + (size_t)pix * CB + v * CV, src, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int i = threadIdx.x; i < K * K * CB; i += NT) {
+        const int c = cb0 + i % CB;
+        sW[i] = c < C ? w[(size_t)(i / CB) * C + c] : 0.f;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const int v = threadIdx.x % NCV, strip = threadIdx.x / NCV;
+    const int sy = strip / (kDwTW / kDwStrip), sx = strip % (kDwTW / kDwStrip);
+    const int c = cb0 + v * CV;
+    float acc[kDwStrip][CV];
+#pragma unroll
+    for (int o = 0; o < kDwStrip; ++o)
+#pragma unroll
+        for (int k = 0; k < CV; ++k) acc[o][k] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+        float in[NIN][CV];
+        const T *rowp = sIn + ((size_t)(sy * S + ky) * IW + sx * kDwStrip * S) * CB + v * CV;
+#pragma unroll
+        for (int j = 0; j < NIN; ++j) Vec<T, CV>::load(rowp + (size_t)j * CB, in[j]);
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+            float wk[CV];
+            loadf<CV>(sW + (ky * K + kx) * CB + v * CV, wk);
+#pragma unroll
+            for (int o = 0; o < kDwStrip; ++o)
+#pragma unroll
+                for (int k = 0; k < CV; ++k) acc[o][k] = fmaf(in[o * S + kx][k], wk[k], acc[o][k]);
+        }
+    }
+    float tot[CV];
+#pragma unroll
+    for (int k = 0; k < CV; ++k) tot[k] = 0.f;
+    if (c < C) {
+        float sc[CV], sh[CV];
+        loadf<CV>(scale + c, sc);
+        loadf<CV>(shift + c, sh);
+        const int oy = ty0 + sy;
+        T *yb = y + (size_t)b * Ho * Wo * C;
+#pragma unroll
+        for (int o = 0; o < kDwStrip; ++o) {
+            const int ox = tx0 + sx * kDwStrip + o;
+            if (oy < Ho && ox < Wo) {
+#pragma unroll
+                for (int k = 0; k < CV; ++k) {
+                    acc[o][k] = activate<ACT>(acc[o][k] * sc[k] + sh[k]);
+                    tot[k] += acc[o][k];
+                }
+                Vec<T, CV>::store(yb + ((size_t)oy * Wo + ox) * C + c, acc[o]);
+            }
+        }
+    }
+    if (se_sum) {
+        // deterministic: strip partials -> shared rows -> fixed-order sum -> (image, tile, channel)
+#pragma unroll
+        for (int k = 0; k < CV; ++k) sRed[(size_t)strip * CB + v * CV + k] = tot[k];
+        __syncthreads();
+        constexpr int NS = (kDwTW / kDwStrip) * kDwTH;
+        float *dst = se_sum + ((size_t)b * gridDim.x + blockIdx.x) * C;
+        for (int i = threadIdx.x; i < CB; i += NT) {
+            if (cb0 + i < C) {
+                float t = 0.f;
+                for (int r = 0; r < NS; ++r) t += sRed[(size_t)r * CB + i];
+                dst[cb0 + i] = t;
+            }
+        }
+    }
+}
+
+template <typename T, int CV, int K, int S, int NCV>
+static int launch_dw_tiled(const void *x, const float *w, const float *scale, const float *shift, void *y,
+                           float *se_sum, int B, int H, int W, int C, int act, cudaStream_t st) {
+    constexpr int CB = NCV * CV;
+    constexpr int IH = (kDwTH - 1) * S + K, IW = (kDwTW - 1) * S + K;
+    constexpr int NT = NCV * (kDwTW / kDwStrip) * kDwTH;
+    const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S;
+    const int pt = max((Ho - 1) * S + K - H, 0) / 2, pl = max((Wo - 1) * S + K - W, 0) / 2;
+    const int tx = (Wo + kDwTW - 1) / kDwTW, ty = (Ho + kDwTH - 1) / kDwTH;
+    const size_t smem = (size_t)IH * IW * CB * sizeof(T) + (size_t)K * K * CB * 4 +
+                        (size_t)(kDwTW / kDwStrip) * kDwTH * CB * 4;
+    dim3 grid(tx * ty, (C + CB - 1) / CB, B);
+#define DW_LAUNCH(A)                                                                                       \
+    {                                                                                                      \
+        auto kern = dwconv_tiled_kernel<T, CV, K, S, NCV, A>;                                              \
+        if (smem > 48 * 1024) EFFDET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, NT, smem, st>>>(static_cast<const T *>(x), w, scale, shift, static_cast<T *>(y), se_sum, H, W, \
+                                     Ho, Wo, C, pt, pl, tx);                                               \
+    }
+    if (act == EFFDET_ACT_SWISH) DW_LAUNCH(EFFDET_ACT_SWISH)
+    else if (act == EFFDET_ACT_RELU) DW_LAUNCH(EFFDET_ACT_RELU)
+    else if (act == EFFDET_ACT_NONE) DW_LAUNCH(EFFDET_ACT_NONE)
+    else return fail(EFFDET_E_UNSUPPORTED, "effdet_dwconv: unsupported activation%s", "");
+#undef DW_LAUNCH
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
 // ------------------------------------------------------------------ squeeze-excite FCs
 __global__ void __launch_bounds__(256)
 se_gate_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_hw,
@@ -325,6 +466,10 @@ using namespace effdet;
 
 extern "C" int effdet_dwconv_se_blocks(int B, int H, int W, int C, int stride, int dtype) {
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || stride < 1) return 0;
+    {   // tiled kernel: one partial per 8x16 output tile
+        const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+        return ((Wo + kDwTW - 1) / kDwTW) * ((Ho + kDwTH - 1) / kDwTH);
+    }
     const int CV = dtype == EFFDET_BF16 ? 8 : 4;
     const int nvec = C / CV;
     int PY = 256 / (nvec > 0 ? nvec : 1); if (PY < 1) PY = 1;
@@ -344,12 +489,23 @@ extern "C" int effdet_dwconv(const void *x, const float *kernel, const float *sc
     EFFDET_REQUIRE(k == 3 || k == 5, "kernel size 3 or 5");
     EFFDET_REQUIRE(stride == 1 || stride == 2, "stride 1 or 2");
     EFFDET_REQUIRE(al16(x) && al16(y) && al16(kernel) && al16(scale) && al16(shift), "16B alignment");
-    if (dtype == EFFDET_F32)
-        return launch_dw<float, 4>(x, kernel, scale, shift, y, se_sum, se_blocks, B, H, W, C, k,
-                                   stride, act, as_stream(stream));
-    if (dtype == EFFDET_BF16)
-        return launch_dw<__nv_bfloat16, 8>(x, kernel, scale, shift, y, se_sum, se_blocks, B, H, W, C,
-                                           k, stride, act, as_stream(stream));
+    if (se_sum)
+        EFFDET_REQUIRE(se_blocks == effdet_dwconv_se_blocks(B, H, W, C, stride, dtype),
+                       "se_blocks must come from effdet_dwconv_se_blocks");
+    cudaStream_t st = as_stream(stream);
+#define DW_CASE(T, CV, K, S, NCV) return launch_dw_tiled<T, CV, K, S, NCV>(x, kernel, scale, shift, y, se_sum, B, H, W, C, act, st)
+    if (dtype == EFFDET_BF16) {
+        if (k == 3 && stride == 1) DW_CASE(__nv_bfloat16, 8, 3, 1, 8);
+        if (k == 5 && stride == 1) DW_CASE(__nv_bfloat16, 8, 5, 1, 8);
+        if (k == 3 && stride == 2) DW_CASE(__nv_bfloat16, 8, 3, 2, 4);
+        if (k == 5 && stride == 2) DW_CASE(__nv_bfloat16, 8, 5, 2, 4);
+    } else if (dtype == EFFDET_F32) {
+        if (k == 3 && stride == 1) DW_CASE(float, 4, 3, 1, 8);
+        if (k == 5 && stride == 1) DW_CASE(float, 4, 5, 1, 8);
+        if (k == 3 && stride == 2) DW_CASE(float, 4, 3, 2, 4);
+        if (k == 5 && stride == 2) DW_CASE(float, 4, 5, 2, 4);
+    }
+#undef DW_CASE
     return fail(EFFDET_E_INVALID, "effdet_dwconv: bad dtype%s", "");
 }
 
