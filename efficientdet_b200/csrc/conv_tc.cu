@@ -177,7 +177,7 @@ constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 // are set up once; two TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue.
 template <int ACT, bool OUT_F32>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 2)      // <= 96 registers: two CTAs (16 epilogue warps) per SM
 conv_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -307,9 +307,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                     const float *R = G.res ? static_cast<const float *>(G.res) + base + nbase : nullptr;
                     const float *MK = G.mask ? static_cast<const float *>(G.mask) + base + nbase : nullptr;
                     if (R || MK) {
-                        for (int j = 0; j < nvalid; ++j) {
-                            if (MK && !(MK[j] > 0.f)) v[j] = 0.f;
-                            if (R) v[j] = v[j] * kp + R[j];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (j < nvalid) {
+                                if (MK && !(MK[j] > 0.f)) v[j] = 0.f;
+                                if (R) v[j] = v[j] * kp + R[j];
+                            }
                         }
                     }
                     if (nvalid == 32 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
@@ -318,7 +321,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                             *reinterpret_cast<float4 *>(Y + 4 * j4) =
                                 make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
                     } else {
-                        for (int j = 0; j < nvalid; ++j) Y[j] = v[j];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < nvalid) Y[j] = v[j];
                     }
                 } else {
                     __nv_bfloat16 *Y = static_cast<__nv_bfloat16 *>(G.y) + base + nbase;
@@ -350,9 +354,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                                 }
                             }
                         } else {
-                            for (int j = 0; j < nvalid; ++j) {
-                                if (MK && !(__bfloat162float(MK[j]) > 0.f)) v[j] = 0.f;
-                                if (R) v[j] = v[j] * kp + __bfloat162float(R[j]);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (j < nvalid) {
+                                    if (MK && !(__bfloat162float(MK[j]) > 0.f)) v[j] = 0.f;
+                                    if (R) v[j] = v[j] * kp + __bfloat162float(R[j]);
+                                }
                             }
                         }
                     }
@@ -366,7 +373,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                             *reinterpret_cast<uint4 *>(Y + 8 * j8) = ov;
                         }
                     } else {
-                        for (int j = 0; j < nvalid; ++j) Y[j] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (j < nvalid) Y[j] = __float2bfloat16_rn(v[j]);
                     }
                 }
             }
@@ -529,7 +537,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
             if (ci < p.Cin) {
                 float *o = out + (size_t)ci * p.Cout + n0 + c0;
                 const int nv = min(32, p.Cout - (n0 + c0));
-                for (int j = 0; j < nv; ++j) o[j] = num_k > 0 ? __uint_as_float(r[j]) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < nv) o[j] = num_k > 0 ? __uint_as_float(r[j]) : 0.f;
             }
         }
     }

@@ -495,6 +495,10 @@ extern "C" int effdet_dwconv(const void *x, const float *kernel, const float *sc
     cudaStream_t st = as_stream(stream);
 #define DW_CASE(T, CV, K, S, NCV) return launch_dw_tiled<T, CV, K, S, NCV>(x, kernel, scale, shift, y, se_sum, B, H, W, C, act, st)
     if (dtype == EFFDET_BF16) {
+        if (C % 64 != 0 && C <= 32) {       // narrow layers: do not idle half of the lanes
+            if (k == 3 && stride == 1) DW_CASE(__nv_bfloat16, 8, 3, 1, 4);
+            if (k == 5 && stride == 1) DW_CASE(__nv_bfloat16, 8, 5, 1, 4);
+        }
         if (k == 3 && stride == 1) DW_CASE(__nv_bfloat16, 8, 3, 1, 8);
         if (k == 5 && stride == 1) DW_CASE(__nv_bfloat16, 8, 5, 1, 8);
         if (k == 3 && stride == 2) DW_CASE(__nv_bfloat16, 8, 3, 2, 4);
