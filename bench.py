@@ -339,6 +339,20 @@ def run_reference(args, rank, world):
     }
 
 
+def _claim_stdout():
+    """Libraries (NCCL prints its version, torchrun banners) may write to fd 1; the contract is ONE
+    JSON line on stdout, so everything else is sent to stderr and the line is written to the saved fd."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(saved_fd, obj):
+    sys.stdout.flush()
+    os.write(saved_fd, (json.dumps(obj) + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -349,9 +363,10 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    out_fd = _claim_stdout()
     if args.impl == "reference":
         if rank == 0:
-            print(json.dumps(run_reference(args, rank, world)), flush=True)
+            _emit(out_fd, run_reference(args, rank, world))
         return 0
     if world > 1:
         import torch
@@ -360,7 +375,7 @@ def main():
         dist.init_process_group("nccl")
     out = run_ours(args, rank, world)
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        _emit(out_fd, out)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
