@@ -595,9 +595,12 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 using namespace effdet;
 
 extern "C" int effdet_conv_tc_block_n(int n) {
-    // N tile: whole N (rounded to 16) when <= 256, else 128-wide tiles
+    // N tile <= 128 columns: two accumulators of <= 128 TMEM columns each leave room for two CTAs
+    // (16 epilogue warps) per SM; N is split into equal tiles rounded up to 16.
     const int n16 = round_up(n, 16);
-    return n16 <= 256 ? n16 : 128;
+    if (n16 <= 128) return n16;
+    const int tiles = (n16 + 127) / 128;
+    return round_up((n16 + tiles - 1) / tiles, 16);
 }
 
 extern "C" size_t effdet_conv_weight_panel_elems(int taps_or_samples, int K, int N) {
