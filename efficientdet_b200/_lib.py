@@ -88,6 +88,18 @@ _SIGNATURES = {
     "effdet_flip_taps": [c_void_p, c_void_p, c_int, c_int, c_void_p],
     "effdet_sgd_momentum_step": [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float,
                                  c_void_p],
+    "effdet_bn_act_backward": [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_int, c_int, c_void_p],
+    "effdet_spatial_sum": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "effdet_se_apply": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "effdet_se_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                           c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "effdet_dw_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                           c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "effdet_stem_wgrad": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                          c_void_p],
     "effdet_filter_detections": [c_void_p, c_void_p, c_int, c_size_t, c_int, c_float, c_float,
                                  c_int, c_int, c_int, c_void_p, c_size_t, c_size_t, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
@@ -159,6 +171,12 @@ def load():
     lib.effdet_conv_tc_block_n.argtypes = [c_int]
     lib.effdet_conv_weight_panel_elems.restype = c_size_t
     lib.effdet_conv_weight_panel_elems.argtypes = [c_int, c_int, c_int]
+    lib.effdet_se_backward_blocks.restype = c_int
+    lib.effdet_se_backward_blocks.argtypes = [c_int, c_int, c_int]
+    lib.effdet_dw_backward_blocks.restype = c_int
+    lib.effdet_dw_backward_blocks.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, c_int]
+    lib.effdet_stem_wgrad_blocks.restype = c_int
+    lib.effdet_stem_wgrad_blocks.argtypes = [c_int, c_int, c_int]
     lib.effdet_dwconv_se_blocks.restype = c_int
     lib.effdet_dwconv_se_blocks.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int]
     for name, args in _SIGNATURES.items():

@@ -1,0 +1,644 @@
+// Training-mode kernels needed only when the EfficientNet backbone itself is trained
+// (train_tpu.py without --freeze-backbone; BASELINE config 4): backward of
+//   efficientnet.py:228-237  expand conv + BN + swish          -> bn_act_backward (swish')
+//   efficientnet.py:242-252  depthwise k3/k5, stride 1/2       -> dw_wgrad_general, dw_dgrad_strided
+//   efficientnet.py:255-286  squeeze-excite                    -> se_apply, se_bwd_reduce, se_fc_backward,
+//                                                                 se_bwd_finish
+//   efficientnet.py:413-423  stem conv                         -> stem_wgrad
+// Same conventions as train.cu: NHWC, fp32 math, 16-byte vectors along C, deterministic
+// fixed-order reductions.
+#include "common.cuh"
+
+namespace effdet {
+
+template <typename T, int CV> struct VecB;
+template <> struct VecB<float, 4> {
+    static __device__ __forceinline__ void load(const float *p, float *v) {
+        float4 t = *reinterpret_cast<const float4 *>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float *p, const float *v) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct VecB<__nv_bfloat16, 8> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float *v) {
+        uint4 t = *reinterpret_cast<const uint4 *>(p);
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float *v) {
+        uint4 t;
+        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4 *>(p) = t;
+    }
+};
+template <int CV> __device__ __forceinline__ void ldv(const float *p, float *v) {
+#pragma unroll
+    for (int i = 0; i < CV; i += 4) {
+        float4 t = *reinterpret_cast<const float4 *>(p + i);
+        v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    }
+}
+
+// derivative of the activation applied to u = BN(z), as a factor on the incoming gradient
+__device__ __forceinline__ float act_grad(float u, int act) {
+    if (act == EFFDET_ACT_RELU) return u > 0.f ? 1.f : 0.f;
+    if (act == EFFDET_ACT_SWISH) {
+        const float s = 1.f / (1.f + __expf(-u));
+        return s * (1.f + u * (1.f - s));
+    }
+    return 1.f;
+}
+
+// ------------------------------------------------------------------ BN + activation backward
+// u = z*a + b with a = gamma*invstd, b = beta - mean*a (training) or the folded inference scale/shift.
+// pass 1: partial[blk][0][c] = sum dy*act'(u), partial[blk][1][c] = sum dy*act'(u)*xhat
+template <typename T, int CV>
+__global__ void bn_act_bwd_reduce_kernel(const T *__restrict__ z, const T *__restrict__ dy,
+                                         const float *__restrict__ ua, const float *__restrict__ ub,
+                                         const float *__restrict__ mean, const float *__restrict__ invstd,
+                                         size_t rows, int C, int rows_per_block, int act,
+                                         float *__restrict__ partial) {
+    extern __shared__ float sred[];
+    const int nvec = C / CV, PY = blockDim.x / nvec;
+    const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec, c = cv * CV;
+    const size_t r0 = (size_t)blockIdx.x * rows_per_block;
+    const size_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    float s1[CV], s2[CV], a[CV], b[CV], mu[CV], is[CV];
+    ldv<CV>(ua + c, a); ldv<CV>(ub + c, b); ldv<CV>(mean + c, mu); ldv<CV>(invstd + c, is);
+#pragma unroll
+    for (int k = 0; k < CV; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+    for (size_t r = r0 + py; r < r1; r += PY) {
+        float zz[CV], g[CV];
+        VecB<T, CV>::load(z + r * C + c, zz);
+        VecB<T, CV>::load(dy + r * C + c, g);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) {
+            const float gm = g[k] * act_grad(zz[k] * a[k] + b[k], act);
+            s1[k] += gm;
+            s2[k] = fmaf(gm, (zz[k] - mu[k]) * is[k], s2[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CV; ++k) {
+        sred[((size_t)py * 2 + 0) * C + c + k] = s1[k];
+        sred[((size_t)py * 2 + 1) * C + c + k] = s2[k];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float t = 0.f;
+        for (int r = 0; r < PY; ++r) t += sred[(size_t)r * 2 * C + i];
+        partial[(size_t)blockIdx.x * 2 * C + i] = t;
+    }
+}
+__global__ void bn_act_bwd_finalize_kernel(const float *__restrict__ partial, int nblk, double count,
+                                           const float *__restrict__ gamma, const float *__restrict__ mean,
+                                           const float *__restrict__ invstd, float *__restrict__ k123,
+                                           float *__restrict__ dgamma, float *__restrict__ dbeta, int C) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= C) return;
+    const int lane = threadIdx.x & 31;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = lane; b < nblk; b += 32) {
+        s1 += (double)partial[(size_t)b * 2 * C + c];
+        s2 += (double)partial[(size_t)b * 2 * C + C + c];
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    }
+    if (lane) return;
+    const float g = gamma[c], is = invstd[c], mu = mean[c];
+    const float m1 = (float)(s1 / count), m2 = (float)(s2 / count);
+    k123[c] = g * is;
+    k123[C + c] = -g * is * is * m2;
+    k123[2 * C + c] = -g * is * (m1 - mu * is * m2);
+    if (dgamma) dgamma[c] = (float)s2;
+    if (dbeta) dbeta[c] = (float)s1;
+}
+// pass 2: dz = k1*(dy*act'(u)) + k2*z + k3
+template <typename T, int CV>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ z, const float *__restrict__ ua,
+                        const float *__restrict__ ub, const float *__restrict__ k123, T *__restrict__ dz,
+                        size_t nvec_total, int C, int act) {
+    const int nvec = C / CV;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
+        const int c = (int)(i % nvec) * CV;
+        float g[CV], zz[CV], a[CV], b[CV], k1[CV], k2[CV], k3[CV];
+        VecB<T, CV>::load(dy + i * CV, g);
+        VecB<T, CV>::load(z + i * CV, zz);
+        ldv<CV>(ua + c, a); ldv<CV>(ub + c, b);
+        ldv<CV>(k123 + c, k1); ldv<CV>(k123 + C + c, k2); ldv<CV>(k123 + 2 * C + c, k3);
+#pragma unroll
+        for (int k = 0; k < CV; ++k)
+            g[k] = k1[k] * (g[k] * act_grad(zz[k] * a[k] + b[k], act)) + k2[k] * zz[k] + k3[k];
+        VecB<T, CV>::store(dz + i * CV, g);
+    }
+}
+
+// ------------------------------------------------------------------ squeeze-excite
+// yg = y * gate[b][c]
+template <typename T, int CV>
+__global__ void __launch_bounds__(256)
+se_apply_kernel(const T *__restrict__ y, const float *__restrict__ gate, T *__restrict__ out, int HW, int C,
+                size_t nvec_total) {
+    const int nvec = C / CV;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
+        const int c = (int)(i % nvec) * CV;
+        const size_t b = i / ((size_t)nvec * HW);
+        float v[CV], g[CV];
+        VecB<T, CV>::load(y + i * CV, v);
+        ldv<CV>(gate + b * C + c, g);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) v[k] *= g[k];
+        VecB<T, CV>::store(out + i * CV, v);
+    }
+}
+// partial[b][blk][c] = sum over the block's pixels of dyg * y     (d gate before the sigmoid);
+// y == NULL: plain spatial sum of dyg (the squeeze of the forward pass)
+template <typename T, int CV>
+__global__ void se_bwd_reduce_kernel(const T *__restrict__ dyg, const T *__restrict__ y, int HW, int C,
+                                     int rows_per_block, float *__restrict__ partial) {
+    extern __shared__ float sred[];
+    const int nvec = C / CV, PY = blockDim.x / nvec;
+    const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec, c = cv * CV;
+    const int b = blockIdx.y;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
+    const T *pa = dyg + (size_t)b * HW * C, *pb = y ? y + (size_t)b * HW * C : nullptr;
+    float s[CV];
+#pragma unroll
+    for (int k = 0; k < CV; ++k) s[k] = 0.f;
+    for (int r = r0 + py; r < r1; r += PY) {
+        float a[CV], v[CV];
+        VecB<T, CV>::load(pa + (size_t)r * C + c, a);
+        if (pb) {
+            VecB<T, CV>::load(pb + (size_t)r * C + c, v);
+#pragma unroll
+            for (int k = 0; k < CV; ++k) s[k] = fmaf(a[k], v[k], s[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < CV; ++k) s[k] += a[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CV; ++k) sred[(size_t)py * C + c + k] = s[k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        float t = 0.f;
+        for (int r = 0; r < PY; ++r) t += sred[(size_t)r * C + i];
+        partial[((size_t)b * gridDim.x + blockIdx.x) * C + i] = t;
+    }
+}
+// One block per image: recompute the SE forward from the squeeze sums, back-propagate through
+// sigmoid / FC2 / swish / FC1; per-image weight gradients go to scratch (summed over images later),
+// dmean (B,C) is the gradient of the squeezed mean.
+__global__ void __launch_bounds__(256)
+se_fc_backward_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_hw,
+                      const float *__restrict__ dgate_partial, int dg_blocks, const float *__restrict__ w1,
+                      const float *__restrict__ b1, const float *__restrict__ w2, const float *__restrict__ b2,
+                      int C, int R, float *__restrict__ dmean, float *__restrict__ scratch) {
+    extern __shared__ float sm[];       // mean[C] | ds2[C] | s1[R] | r[R] | ds1[R]
+    float *mean = sm, *ds2 = sm + C, *s1 = ds2 + C, *rr = s1 + R, *ds1 = rr + R;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int c = tid; c < C; c += 256) {
+        const float *src = se_sum + (size_t)b * se_blocks * C + c;
+        float t = 0.f;
+        for (int k = 0; k < se_blocks; ++k) t += src[(size_t)k * C];
+        mean[c] = t * inv_hw;
+    }
+    __syncthreads();
+    for (int j = warp; j < R; j += 8) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(mean[c], w1[(size_t)c * R + j], s);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) { s1[j] = s + b1[j]; rr[j] = (s + b1[j]) / (1.f + __expf(-(s + b1[j]))); }
+    }
+    __syncthreads();
+    const size_t per = (size_t)2 * C * R + R + C;        // dW1 | dW2 | db1 | db2 per image
+    float *dW1 = scratch + (size_t)b * per, *dW2 = dW1 + (size_t)C * R, *db1 = dW2 + (size_t)R * C, *db2 = db1 + R;
+    for (int c = tid; c < C; c += 256) {
+        float s = b2[c];
+        for (int j = 0; j < R; ++j) s = fmaf(rr[j], w2[(size_t)j * C + c], s);
+        const float g = 1.f / (1.f + __expf(-s));
+        const float *src = dgate_partial + (size_t)b * dg_blocks * C + c;
+        float dg = 0.f;
+        for (int k = 0; k < dg_blocks; ++k) dg += src[(size_t)k * C];
+        const float d = dg * g * (1.f - g);
+        ds2[c] = d;
+        db2[c] = d;
+        for (int j = 0; j < R; ++j) dW2[(size_t)j * C + c] = rr[j] * d;
+    }
+    __syncthreads();
+    for (int j = warp; j < R; j += 8) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(ds2[c], w2[(size_t)j * C + c], s);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (lane == 0) {
+            const float u = s1[j], sg = 1.f / (1.f + __expf(-u));
+            ds1[j] = s * sg * (1.f + u * (1.f - sg));
+            db1[j] = ds1[j];
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) {
+        float s = 0.f;
+        for (int j = 0; j < R; ++j) {
+            const float d = ds1[j];
+            s = fmaf(w1[(size_t)c * R + j], d, s);
+            dW1[(size_t)c * R + j] = mean[c] * d;
+        }
+        dmean[(size_t)b * C + c] = s;
+    }
+}
+__global__ void sum_over_images_kernel(const float *__restrict__ scratch, int B, size_t per,
+                                       float *__restrict__ dw1, float *__restrict__ dw2, float *__restrict__ db1,
+                                       float *__restrict__ db2, int C, int R) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per) return;
+    float t = 0.f;
+    for (int b = 0; b < B; ++b) t += scratch[(size_t)b * per + i];
+    const size_t cr = (size_t)C * R;
+    if (i < cr) dw1[i] = t;
+    else if (i < 2 * cr) dw2[i - cr] = t;
+    else if (i < 2 * cr + R) db1[i - 2 * cr] = t;
+    else db2[i - 2 * cr - R] = t;
+}
+// dy = dyg * gate + dmean * inv_hw
+template <typename T, int CV>
+__global__ void __launch_bounds__(256)
+se_bwd_finish_kernel(const T *__restrict__ dyg, const float *__restrict__ gate, const float *__restrict__ dmean,
+                     float inv_hw, T *__restrict__ dy, int HW, int C, size_t nvec_total) {
+    const int nvec = C / CV;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
+        const int c = (int)(i % nvec) * CV;
+        const size_t b = i / ((size_t)nvec * HW);
+        float v[CV], g[CV], m[CV];
+        VecB<T, CV>::load(dyg + i * CV, v);
+        ldv<CV>(gate + b * C + c, g);
+        ldv<CV>(dmean + b * C + c, m);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) v[k] = fmaf(v[k], g[k], m[k] * inv_hw);
+        VecB<T, CV>::store(dy + i * CV, v);
+    }
+}
+
+// ------------------------------------------------------------------ depthwise backward (general)
+// dW[tap][c] = sum_{b,oy,ox} x[b, oy*s - pad + ky, ox*s - pad + kx, c] * dz[b,oy,ox,c]
+template <typename T, int CV, int K>
+__global__ void dw_wgrad_general_kernel(const T *__restrict__ x, const T *__restrict__ dz, int B, int H, int W,
+                                        int Ho, int Wo, int C, int stride, int pad_t, int pad_l,
+                                        int pix_per_block, float *__restrict__ partial) {
+    extern __shared__ float sred[];      // PY * K*K * C
+    const int nvec = C / CV, PY = blockDim.x / nvec;
+    const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec, c = cv * CV;
+    const size_t total = (size_t)B * Ho * Wo;
+    const size_t p0 = (size_t)blockIdx.x * pix_per_block;
+    const size_t p1 = p0 + pix_per_block < total ? p0 + pix_per_block : total;
+    float acc[K * K][CV];
+#pragma unroll
+    for (int t = 0; t < K * K; ++t)
+#pragma unroll
+        for (int k = 0; k < CV; ++k) acc[t][k] = 0.f;
+    for (size_t p = p0 + py; p < p1; p += PY) {
+        const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho);
+        const size_t b = p / ((size_t)Wo * Ho);
+        float g[CV];
+        VecB<T, CV>::load(dz + p * C + c, g);
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const int iy = oy * stride - pad_t + ky;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const int ix = ox * stride - pad_l + kx;
+                if (ix < 0 || ix >= W) continue;
+                float v[CV];
+                VecB<T, CV>::load(x + ((b * H + iy) * (size_t)W + ix) * C + c, v);
+#pragma unroll
+                for (int k = 0; k < CV; ++k) acc[ky * K + kx][k] = fmaf(v[k], g[k], acc[ky * K + kx][k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < K * K; ++t)
+#pragma unroll
+        for (int k = 0; k < CV; ++k) sred[((size_t)py * K * K + t) * C + c + k] = acc[t][k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) {
+        float t = 0.f;
+        for (int r = 0; r < PY; ++r) t += sred[(size_t)r * K * K * C + i];
+        partial[(size_t)blockIdx.x * K * K * C + i] = t;
+    }
+}
+__global__ void sum_partials_warp_kernel(const float *__restrict__ partial, int nblk, int n,
+                                         float *__restrict__ out) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int b = lane; b < nblk; b += 32) s += (double)partial[(size_t)b * n + i];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) out[i] = (float)s;
+}
+// data gradient of a depthwise conv (any stride): gather form
+template <typename T, int CV, int K>
+__global__ void __launch_bounds__(256)
+dw_dgrad_kernel(const T *__restrict__ dz, const float *__restrict__ w, T *__restrict__ dx, int B, int H, int W,
+                int Ho, int Wo, int C, int stride, int pad_t, int pad_l) {
+    const int nvec = C / CV;
+    const size_t total = (size_t)B * H * W * nvec;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int c = (int)(i % nvec) * CV;
+        const size_t pix = i / nvec;
+        const int ix = (int)(pix % W), iy = (int)((pix / W) % H);
+        const size_t b = pix / ((size_t)W * H);
+        float acc[CV];
+#pragma unroll
+        for (int k = 0; k < CV; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const int ny = iy + pad_t - ky;
+            if (ny < 0 || ny % stride) continue;
+            const int oy = ny / stride;
+            if (oy >= Ho) continue;
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const int nx = ix + pad_l - kx;
+                if (nx < 0 || nx % stride) continue;
+                const int ox = nx / stride;
+                if (ox >= Wo) continue;
+                float g[CV], wk[CV];
+                VecB<T, CV>::load(dz + ((b * Ho + oy) * (size_t)Wo + ox) * C + c, g);
+                ldv<CV>(w + (size_t)(ky * K + kx) * C + c, wk);
+#pragma unroll
+                for (int k = 0; k < CV; ++k) acc[k] = fmaf(g[k], wk[k], acc[k]);
+            }
+        }
+        VecB<T, CV>::store(dx + pix * C + c, acc);
+    }
+}
+
+// ------------------------------------------------------------------ stem weight gradient
+// dW[ky][kx][ci][co] = sum_{b,oy,ox} img[b, 2oy - pad + ky, 2ox - pad + kx, ci] * dz[b,oy,ox,co]
+// block = 27 x C0 threads-worth of outputs over a pixel range; partial[blk][27*C0]
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(const float *__restrict__ img, const T *__restrict__ dz, int B, int H, int W, int Ho, int Wo,
+                  int C0, int pad_t, int pad_l, int pix_per_block, float *__restrict__ partial) {
+    const int n_out = 27 * C0;
+    const size_t total = (size_t)B * Ho * Wo;
+    const size_t p0 = (size_t)blockIdx.x * pix_per_block;
+    const size_t p1 = p0 + pix_per_block < total ? p0 + pix_per_block : total;
+    for (int o = threadIdx.x; o < n_out; o += 256) {
+        const int co = o % C0, ci = (o / C0) % 3, tap = o / (3 * C0);
+        const int ky = tap / 3, kx = tap % 3;
+        float acc = 0.f;
+        for (size_t p = p0; p < p1; ++p) {
+            const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho);
+            const size_t b = p / ((size_t)Wo * Ho);
+            const int iy = oy * 2 - pad_t + ky, ix = ox * 2 - pad_l + kx;
+            if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+            acc = fmaf(img[((b * H + iy) * (size_t)W + ix) * 3 + ci], to_f<T>(dz[p * C0 + co]), acc);
+        }
+        partial[(size_t)blockIdx.x * n_out + o] = acc;
+    }
+}
+
+static unsigned grid_for_n(size_t n) {
+    unsigned b = cdiv(n, 256);
+    return b > (unsigned)kNumSMs * 8 ? kNumSMs * 8 : (b ? b : 1);
+}
+
+}  // namespace effdet
+
+using namespace effdet;
+
+#define DISPATCH_TB(dtype, EXPR_F32, EXPR_BF16)                                       \
+    if ((dtype) == EFFDET_F32) { EXPR_F32; }                                          \
+    else if ((dtype) == EFFDET_BF16) { EXPR_BF16; }                                   \
+    else return fail(EFFDET_E_INVALID, "%s: bad dtype", __func__);
+
+/* Backward of y = act(BN(z)) for act in {none, relu, swish}.  ua/ub: the affine map u = z*ua + ub the
+ * forward applied (training: gamma*invstd, beta - mean*gamma*invstd; frozen BN: folded scale/shift).
+ * frozen != 0: inference-mode BN (dz = ua * dy*act'(u); no dgamma/dbeta). */
+extern "C" int effdet_bn_act_backward(const void *dy, const void *z, size_t rows, int C, const float *gamma,
+                                      const float *save_mean, const float *save_invstd, const float *ua,
+                                      const float *ub, int frozen, int act, float *dgamma, float *dbeta,
+                                      void *dz, float *k123, float *partial, int nblk, int dtype, void *stream) {
+    EFFDET_REQUIRE(dy && z && dz && k123 && ua && ub, "null pointer");
+    EFFDET_REQUIRE(rows > 0 && C > 0 && C % 8 == 0 && nblk > 0, "bad sizes");
+    cudaStream_t st = as_stream(stream);
+    if (frozen) {
+        EFFDET_CUDA(cudaMemsetAsync(k123, 0, 3 * (size_t)C * sizeof(float), st));
+        EFFDET_CUDA(cudaMemcpyAsync(k123, ua, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+        EFFDET_REQUIRE(gamma && save_mean && save_invstd && partial, "null statistics");
+        const int CV = dtype == EFFDET_BF16 ? 8 : 4;
+        const int nvec = C / CV;
+        EFFDET_REQUIRE(nvec <= 1024, "C too large");
+        int PY = 256 / nvec; if (PY < 1) PY = 1;
+        const int rpb = (int)cdiv(rows, nblk);
+        EFFDET_REQUIRE((int)cdiv(rows, rpb) == nblk, "nblk must come from effdet_colreduce_blocks");
+        const size_t sm = (size_t)PY * 2 * C * sizeof(float);
+        DISPATCH_TB(dtype,
+            (bn_act_bwd_reduce_kernel<float, 4><<<nblk, nvec * PY, sm, st>>>(
+                (const float *)z, (const float *)dy, ua, ub, save_mean, save_invstd, rows, C, rpb, act, partial)),
+            (bn_act_bwd_reduce_kernel<__nv_bfloat16, 8><<<nblk, nvec * PY, sm, st>>>(
+                (const __nv_bfloat16 *)z, (const __nv_bfloat16 *)dy, ua, ub, save_mean, save_invstd, rows, C, rpb,
+                act, partial)))
+        EFFDET_LAUNCHED();
+        bn_act_bwd_finalize_kernel<<<cdiv((size_t)C * 32, 256), 256, 0, st>>>(partial, nblk, (double)rows, gamma,
+                                                                            save_mean, save_invstd, k123, dgamma,
+                                                                            dbeta, C);
+        EFFDET_LAUNCHED();
+    }
+    DISPATCH_TB(dtype,
+        (bn_act_bwd_apply_kernel<float, 4><<<grid_for_n(rows * C / 4), 256, 0, st>>>(
+            (const float *)dy, (const float *)z, ua, ub, k123, (float *)dz, rows * C / 4, C, act)),
+        (bn_act_bwd_apply_kernel<__nv_bfloat16, 8><<<grid_for_n(rows * C / 8), 256, 0, st>>>(
+            (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)z, ua, ub, k123, (__nv_bfloat16 *)dz, rows * C / 8, C,
+            act)))
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+extern "C" int effdet_se_apply(const void *y, const float *gate, void *out, int B, int HW, int C, int dtype,
+                               void *stream) {
+    EFFDET_REQUIRE(y && gate && out && B > 0 && HW > 0 && C > 0 && C % 8 == 0, "bad arguments");
+    cudaStream_t st = as_stream(stream);
+    const size_t n = (size_t)B * HW * C;
+    DISPATCH_TB(dtype,
+        (se_apply_kernel<float, 4><<<grid_for_n(n / 4), 256, 0, st>>>((const float *)y, gate, (float *)out, HW, C, n / 4)),
+        (se_apply_kernel<__nv_bfloat16, 8><<<grid_for_n(n / 8), 256, 0, st>>>(
+            (const __nv_bfloat16 *)y, gate, (__nv_bfloat16 *)out, HW, C, n / 8)))
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+/* Per-(image, block, channel) spatial sums of y (B,HW,C): the SE squeeze when the depthwise
+ * output is produced by a separate BN/activation pass (training mode).  partial (B, nblk, C) with
+ * nblk = effdet_se_backward_blocks(). */
+extern "C" int effdet_se_backward_blocks(int HW, int C, int dtype);
+extern "C" int effdet_spatial_sum(const void *y, float *partial, int nblk, int B, int HW, int C, int dtype,
+                                  void *stream) {
+    EFFDET_REQUIRE(y && partial && B > 0 && HW > 0 && C > 0 && C % 8 == 0, "bad arguments");
+    EFFDET_REQUIRE(nblk == effdet_se_backward_blocks(HW, C, dtype), "nblk must come from effdet_se_backward_blocks");
+    cudaStream_t st = as_stream(stream);
+    const int CV = dtype == EFFDET_BF16 ? 8 : 4;
+    const int nvec = C / CV;
+    EFFDET_REQUIRE(nvec <= 1024, "C too large");
+    int PY = 256 / nvec; if (PY < 1) PY = 1;
+    const int rpb = (int)cdiv(HW, nblk);
+    const size_t sm = (size_t)PY * C * sizeof(float);
+    dim3 grid(nblk, B);
+    DISPATCH_TB(dtype,
+        (se_bwd_reduce_kernel<float, 4><<<grid, nvec * PY, sm, st>>>((const float *)y, nullptr, HW, C, rpb, partial)),
+        (se_bwd_reduce_kernel<__nv_bfloat16, 8><<<grid, nvec * PY, sm, st>>>((const __nv_bfloat16 *)y, nullptr, HW, C,
+                                                                              rpb, partial)))
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+extern "C" int effdet_se_backward_blocks(int HW, int C, int dtype) {
+    const int CV = dtype == EFFDET_BF16 ? 8 : 4;
+    int nvec = C / CV; if (nvec < 1) nvec = 1;
+    int PY = 256 / nvec; if (PY < 1) PY = 1;
+    int rpb = PY * 16;
+    while (rpb > PY && cdiv(HW, rpb) < 8) rpb >>= 1;
+    return (int)cdiv(HW, rpb);
+}
+
+/* Squeeze-excite backward (efficientnet.py:255-286).  dyg: gradient of the gated tensor y*gate.
+ * Outputs: dy (B,HW,C) gradient of y (both the direct path and the path through the squeeze),
+ * gradients of se_reduce / se_expand kernels and biases.  Scratch sizes (floats):
+ * dg_partial B*effdet_se_backward_blocks()*C ; fc_scratch B*(2*C*R + R + C) ; dmean B*C. */
+extern "C" int effdet_se_backward(const void *dyg, const void *y, const float *gate, const float *se_sum,
+                                  int se_blocks, const float *w1, const float *b1, const float *w2,
+                                  const float *b2, void *dy, float *dw1, float *db1, float *dw2, float *db2,
+                                  float *dg_partial, int dg_blocks, float *fc_scratch, float *dmean, int B, int HW,
+                                  int C, int R, int dtype, void *stream) {
+    EFFDET_REQUIRE(dyg && y && gate && se_sum && w1 && b1 && w2 && b2 && dy && dw1 && db1 && dw2 && db2 &&
+                       dg_partial && fc_scratch && dmean, "null pointer");
+    EFFDET_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && R > 0 && se_blocks > 0, "bad sizes");
+    EFFDET_REQUIRE(dg_blocks == effdet_se_backward_blocks(HW, C, dtype), "dg_blocks must come from effdet_se_backward_blocks");
+    cudaStream_t st = as_stream(stream);
+    const int CV = dtype == EFFDET_BF16 ? 8 : 4;
+    const int nvec = C / CV;
+    EFFDET_REQUIRE(nvec <= 1024, "C too large");
+    int PY = 256 / nvec; if (PY < 1) PY = 1;
+    const int rpb = (int)cdiv(HW, dg_blocks);
+    const size_t sm = (size_t)PY * C * sizeof(float);
+    dim3 grid(dg_blocks, B);
+    DISPATCH_TB(dtype,
+        (se_bwd_reduce_kernel<float, 4><<<grid, nvec * PY, sm, st>>>((const float *)dyg, (const float *)y, HW, C, rpb, dg_partial)),
+        (se_bwd_reduce_kernel<__nv_bfloat16, 8><<<grid, nvec * PY, sm, st>>>(
+            (const __nv_bfloat16 *)dyg, (const __nv_bfloat16 *)y, HW, C, rpb, dg_partial)))
+    EFFDET_LAUNCHED();
+    const size_t sm2 = (size_t)(2 * C + 3 * R) * sizeof(float);
+    EFFDET_REQUIRE(sm2 <= 48 * 1024, "C + R too large");
+    se_fc_backward_kernel<<<B, 256, sm2, st>>>(se_sum, se_blocks, 1.f / (float)HW, dg_partial, dg_blocks, w1, b1, w2,
+                                               b2, C, R, dmean, fc_scratch);
+    EFFDET_LAUNCHED();
+    const size_t per = (size_t)2 * C * R + R + C;
+    sum_over_images_kernel<<<cdiv(per, 256), 256, 0, st>>>(fc_scratch, B, per, dw1, dw2, db1, db2, C, R);
+    EFFDET_LAUNCHED();
+    const size_t n = (size_t)B * HW * C;
+    DISPATCH_TB(dtype,
+        (se_bwd_finish_kernel<float, 4><<<grid_for_n(n / 4), 256, 0, st>>>(
+            (const float *)dyg, gate, dmean, 1.f / (float)HW, (float *)dy, HW, C, n / 4)),
+        (se_bwd_finish_kernel<__nv_bfloat16, 8><<<grid_for_n(n / 8), 256, 0, st>>>(
+            (const __nv_bfloat16 *)dyg, gate, dmean, 1.f / (float)HW, (__nv_bfloat16 *)dy, HW, C, n / 8)))
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+extern "C" int effdet_dw_backward_blocks(int B, int H, int W, int C, int k, int stride, int dtype) {
+    const int CV = dtype == EFFDET_BF16 ? 8 : 4;
+    int nvec = C / CV; if (nvec < 1) nvec = 1;
+    int PY = (k == 5 ? 64 : 128) / nvec; if (PY < 1) PY = 1;
+    const size_t total = (size_t)B * ((H + stride - 1) / stride) * ((W + stride - 1) / stride);
+    size_t ppb = (size_t)PY * 32;
+    while (ppb > (size_t)PY && cdiv(total, ppb) < (unsigned)kNumSMs * 2) ppb >>= 1;
+    return (int)cdiv(total, ppb);
+}
+
+/* Depthwise conv backward for k in {3,5}, stride in {1,2} (efficientnet.py:242-252):
+ * dkernel (k,k,C) f32 and dx (B,H,W,C).  partial: k*k*C*effdet_dw_backward_blocks() floats. */
+extern "C" int effdet_dw_backward(const void *x, const void *dz, const float *kernel, void *dx, float *dkernel,
+                                  float *partial, int nblk, int B, int H, int W, int C, int k, int stride,
+                                  int dtype, void *stream) {
+    EFFDET_REQUIRE(x && dz && kernel && dkernel && partial, "null pointer");
+    EFFDET_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad sizes");
+    EFFDET_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2), "k in {3,5}, stride in {1,2}");
+    EFFDET_REQUIRE(nblk == effdet_dw_backward_blocks(B, H, W, C, k, stride, dtype), "nblk must come from effdet_dw_backward_blocks");
+    cudaStream_t st = as_stream(stream);
+    const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    const int pt = max((Ho - 1) * stride + k - H, 0) / 2, pl = max((Wo - 1) * stride + k - W, 0) / 2;
+    const int CV = dtype == EFFDET_BF16 ? 8 : 4;
+    const int nvec = C / CV;
+    EFFDET_REQUIRE(nvec <= 1024, "C too large");
+    int PY = (k == 5 ? 64 : 128) / nvec; if (PY < 1) PY = 1;
+    const size_t total = (size_t)B * Ho * Wo;
+    const int ppb = (int)cdiv(total, nblk);
+    const size_t sm = (size_t)PY * k * k * C * sizeof(float);
+#define DWG(T, CVV, KK)                                                                                        \
+    {                                                                                                          \
+        auto kern = dw_wgrad_general_kernel<T, CVV, KK>;                                                       \
+        if (sm > 48 * 1024) EFFDET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        kern<<<nblk, nvec * PY, sm, st>>>((const T *)x, (const T *)dz, B, H, W, Ho, Wo, C, stride, pt, pl, ppb, partial); \
+    }
+    if (dtype == EFFDET_F32) { if (k == 3) DWG(float, 4, 3) else DWG(float, 4, 5) }
+    else if (dtype == EFFDET_BF16) { if (k == 3) DWG(__nv_bfloat16, 8, 3) else DWG(__nv_bfloat16, 8, 5) }
+    else return fail(EFFDET_E_INVALID, "effdet_dw_backward: bad dtype%s", "");
+#undef DWG
+    EFFDET_LAUNCHED();
+    sum_partials_warp_kernel<<<cdiv((size_t)k * k * C * 32, 256), 256, 0, st>>>(partial, nblk, k * k * C, dkernel);
+    EFFDET_LAUNCHED();
+    if (dx) {
+        const size_t n = (size_t)B * H * W * C;
+#define DWD(T, CVV, KK) dw_dgrad_kernel<T, CVV, KK><<<grid_for_n(n / CVV), 256, 0, st>>>( \
+            (const T *)dz, kernel, (T *)dx, B, H, W, Ho, Wo, C, stride, pt, pl)
+        if (dtype == EFFDET_F32) { if (k == 3) DWD(float, 4, 3); else DWD(float, 4, 5); }
+        else { if (k == 3) DWD(__nv_bfloat16, 8, 3); else DWD(__nv_bfloat16, 8, 5); }
+#undef DWD
+        EFFDET_LAUNCHED();
+    }
+    return EFFDET_OK;
+}
+
+extern "C" int effdet_stem_wgrad_blocks(int B, int H, int W) {
+    const size_t total = (size_t)B * ((H + 1) / 2) * ((W + 1) / 2);
+    size_t ppb = 2048;
+    while (ppb > 64 && cdiv(total, ppb) < (unsigned)kNumSMs * 4) ppb >>= 1;
+    return (int)cdiv(total, ppb);
+}
+
+/* Stem conv (3x3, stride 2, 3 -> C0) weight gradient; dz is the gradient of the conv output
+ * (B, H/2, W/2, C0).  partial: 27*C0*effdet_stem_wgrad_blocks() floats. */
+extern "C" int effdet_stem_wgrad(const float *images, const void *dz, float *dkernel, float *partial, int nblk,
+                                 int B, int H, int W, int C0, int dtype, void *stream) {
+    EFFDET_REQUIRE(images && dz && dkernel && partial && B > 0 && H > 0 && W > 0 && C0 > 0, "bad arguments");
+    EFFDET_REQUIRE(nblk == effdet_stem_wgrad_blocks(B, H, W), "nblk must come from effdet_stem_wgrad_blocks");
+    cudaStream_t st = as_stream(stream);
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    const int pt = max((Ho - 1) * 2 + 3 - H, 0) / 2, pl = max((Wo - 1) * 2 + 3 - W, 0) / 2;
+    const size_t total = (size_t)B * Ho * Wo;
+    const int ppb = (int)cdiv(total, nblk);
+    DISPATCH_TB(dtype,
+        (stem_wgrad_kernel<float><<<nblk, 256, 0, st>>>(images, (const float *)dz, B, H, W, Ho, Wo, C0, pt, pl, ppb, partial)),
+        (stem_wgrad_kernel<__nv_bfloat16><<<nblk, 256, 0, st>>>(images, (const __nv_bfloat16 *)dz, B, H, W, Ho, Wo, C0,
+                                                                  pt, pl, ppb, partial)))
+    EFFDET_LAUNCHED();
+    sum_partials_warp_kernel<<<cdiv((size_t)27 * C0 * 32, 256), 256, 0, st>>>(partial, nblk, 27 * C0, dkernel);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}

@@ -177,56 +177,65 @@ class Plan:
         net, B, S = self.net, self.B, self.net.image_size
         bb = net.backbone
         self.images = self.val((B, S, S, 3), F32, "images", keep=True)
-        lib = _lib.load()
-        H = (S + 1) // 2
-        c0 = bb.stem_filters
-        x = self.val((B, H, H, c0), name="stem")
-        sc, sh = self.folded("stem_bn")
-        self.add("stem", [self.images], [x],
-                 lambda x=x: _call("effdet_stem_conv", self.images.ptr, self.w("stem_conv/kernel").data_ptr(),
-                                   sc.data_ptr(), sh.data_ptr(), x.ptr, B, S, S, c0, self.dtype),
-                 "stem_conv")
+        x, H = self._stem()
         feats = []
         for bi, blk in enumerate(bb.blocks):
-            p = blk.prefix
-            inp, cin, cmid, cout = x, blk.input_filters, blk.mid_filters, blk.output_filters
-            if blk.expand_ratio != 1:
-                e = self.val((B, H, H, cmid), name=p + "expand")
-                s1, b1 = self.folded(p + "expand_bn")
-                self.conv([x], [e], p + "expand_conv/kernel", cin, cmid, scale=s1, shift=b1,
-                          act=ACT_SWISH, name=p + "expand_conv")
-                x = e
-            Ho = (H + blk.stride - 1) // blk.stride
-            d = self.val((B, Ho, Ho, cmid), name=p + "dw")
-            s2, b2 = self.folded(p + "bn")
-            nblk = lib.effdet_dwconv_se_blocks(B, H, H, cmid, blk.stride, self.dtype)
-            part = self.val((B, nblk, cmid), F32, name=p + "se_partial")
-            self.add("dwconv", [x], [d, part],
-                     lambda x=x, d=d, p=p, s2=s2, b2=b2, H=H, cmid=cmid, blk=blk, part=part, nblk=nblk:
-                     _call("effdet_dwconv", x.ptr, self.w(p + "dwconv/depthwise_kernel").data_ptr(),
-                           s2.data_ptr(), b2.data_ptr(), d.ptr, part.ptr, nblk, B, H, H, cmid,
-                           blk.kernel_size, blk.stride, ACT_SWISH, self.dtype), p + "dwconv",
-                     flops=2 * blk.kernel_size ** 2 * B * Ho * Ho * cmid)
-            gate = self.val((B, cmid), F32, name=p + "gate")
-            self.add("se", [part], [gate],
-                     lambda p=p, gate=gate, Ho=Ho, cmid=cmid, blk=blk, part=part, nblk=nblk:
-                     _call("effdet_se_gate", part.ptr, nblk, 1.0 / float(Ho * Ho),
-                           self.w(p + "se_reduce/kernel").data_ptr(), self.w(p + "se_reduce/bias").data_ptr(),
-                           self.w(p + "se_expand/kernel").data_ptr(), self.w(p + "se_expand/bias").data_ptr(),
-                           gate.ptr, B, cmid, blk.se_filters), p + "se")
-            y = self.val((B, Ho, Ho, cout), name=p + "out")
-            s3, b3 = self.folded(p + "project_bn")
-            keep = net.drop_scale.get(p) if blk.has_skip else None
-            self.conv([d], [y], p + "project_conv/kernel", cmid, cout, scale=s3, shift=b3,
-                      gate=gate, keep=keep, residuals=[inp] if blk.has_skip else None,
-                      name=p + "project_conv")
-            x, H = y, Ho
+            x, H = self._mbconv(x, blk, H)
             if bi in bb.feature_after:
                 x.keep = True
                 feats.append(x)
                 self.taps["C%d" % len(feats)] = x
         self.features = feats
         self._build_neck_and_heads(feats)
+
+    def _stem(self):
+        net, B, S = self.net, self.B, self.net.image_size
+        H = (S + 1) // 2
+        c0 = net.backbone.stem_filters
+        x = self.val((B, H, H, c0), name="stem")
+        sc, sh = self.folded("stem_bn")
+        self.add("stem", [self.images], [x],
+                 lambda: _call("effdet_stem_conv", self.images.ptr, self.w("stem_conv/kernel").data_ptr(),
+                               sc.data_ptr(), sh.data_ptr(), x.ptr, B, S, S, c0, self.dtype),
+                 "stem_conv")
+        return x, H
+
+    def _mbconv(self, x, blk, H):
+        """One MBConv block (efficientnet.py:210-306), inference form: BN folded into the conv /
+        depthwise epilogues, SE gate folded into the project conv."""
+        B = self.B
+        lib = _lib.load()
+        p = blk.prefix
+        inp, cin, cmid, cout = x, blk.input_filters, blk.mid_filters, blk.output_filters
+        if blk.expand_ratio != 1:
+            e = self.val((B, H, H, cmid), name=p + "expand")
+            s1, b1 = self.folded(p + "expand_bn")
+            self.conv([x], [e], p + "expand_conv/kernel", cin, cmid, scale=s1, shift=b1,
+                      act=ACT_SWISH, name=p + "expand_conv")
+            x = e
+        Ho = (H + blk.stride - 1) // blk.stride
+        d = self.val((B, Ho, Ho, cmid), name=p + "dw")
+        s2, b2 = self.folded(p + "bn")
+        nblk = lib.effdet_dwconv_se_blocks(B, H, H, cmid, blk.stride, self.dtype)
+        part = self.val((B, nblk, cmid), F32, name=p + "se_partial")
+        self.add("dwconv", [x], [d, part],
+                 lambda: _call("effdet_dwconv", x.ptr, self.w(p + "dwconv/depthwise_kernel").data_ptr(),
+                               s2.data_ptr(), b2.data_ptr(), d.ptr, part.ptr, nblk, B, H, H, cmid,
+                               blk.kernel_size, blk.stride, ACT_SWISH, self.dtype), p + "dwconv",
+                 flops=2 * blk.kernel_size ** 2 * B * Ho * Ho * cmid)
+        gate = self.val((B, cmid), F32, name=p + "gate")
+        self.add("se", [part], [gate],
+                 lambda: _call("effdet_se_gate", part.ptr, nblk, 1.0 / float(Ho * Ho),
+                               self.w(p + "se_reduce/kernel").data_ptr(), self.w(p + "se_reduce/bias").data_ptr(),
+                               self.w(p + "se_expand/kernel").data_ptr(), self.w(p + "se_expand/bias").data_ptr(),
+                               gate.ptr, B, cmid, blk.se_filters), p + "se")
+        y = self.val((B, Ho, Ho, cout), name=p + "out")
+        s3, b3 = self.folded(p + "project_bn")
+        keep = self.net.drop_scale.get(p) if blk.has_skip else None
+        self.conv([d], [y], p + "project_conv/kernel", cmid, cout, scale=s3, shift=b3,
+                  gate=gate, keep=keep, residuals=[inp] if blk.has_skip else None,
+                  name=p + "project_conv")
+        return y, Ho
 
     def _build_neck_and_heads(self, feats):
         net = self.net

@@ -18,8 +18,9 @@ import numpy as np
 import torch
 
 from . import _lib, engine
-from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, BF16, F32
-from .engine import BN_EPS_BIFPN, BN_MOMENTUM_BIFPN, Op, Val, _call
+from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SWISH, BF16, F32
+from .engine import (BN_EPS_BACKBONE, BN_EPS_BIFPN, BN_MOMENTUM_BACKBONE, BN_MOMENTUM_BIFPN, Op, Val,
+                     _call)
 
 UP, DOWN = 1, 2
 
@@ -28,10 +29,12 @@ class TrainPlan(engine.Plan):
     """Forward (training mode) + losses + backward launch list for a fixed batch."""
 
     def __init__(self, net, batch, alpha=0.25, gamma=1.5, delta=1.0, dense_labels=False,
-                 reuse_buffers=True):
+                 reuse_buffers=True, train_backbone=False):
         self.alpha, self.gamma, self.delta = alpha, gamma, delta
         self.dense_labels = dense_labels
+        self.train_backbone = train_backbone
         self.tape = []
+        self.bb_tape = []
         self.gvals = {}            # id(Val) -> gradient Val
         net.ensure_grad_buffers()
         super().__init__(net, batch, reuse_buffers=reuse_buffers)
@@ -52,7 +55,10 @@ class TrainPlan(engine.Plan):
     def _bn_train(self, z, y, bn_name, C, rows, act):
         """z -> y = act(BN_batch(z)); returns the record needed by the backward pass."""
         lib = _lib.load()
-        rec = dict(bn=bn_name, C=C, rows=rows, train=self.bn_is_training(bn_name))
+        is_bifpn = bn_name.startswith("BiFPN_")
+        eps = BN_EPS_BIFPN if is_bifpn else BN_EPS_BACKBONE
+        mom = BN_MOMENTUM_BIFPN if is_bifpn else BN_MOMENTUM_BACKBONE
+        rec = dict(bn=bn_name, C=C, rows=rows, train=self.bn_is_training(bn_name), act=act)
         if rec["train"]:
             nblk = lib.effdet_colreduce_blocks(rows, C, self.dtype)
             sc, sh = self.fvec(C, bn_name + "/scale_t"), self.fvec(C, bn_name + "/shift_t")
@@ -61,14 +67,14 @@ class TrainPlan(engine.Plan):
             w = self.w
             self.add("bn_stats", [z], [sc, sh, mu, iv, part],
                      lambda: _call("effdet_bn_train_stats", z.ptr, rows, C, w(bn_name + "/gamma").data_ptr(),
-                                   w(bn_name + "/beta").data_ptr(), BN_EPS_BIFPN, BN_MOMENTUM_BIFPN,
+                                   w(bn_name + "/beta").data_ptr(), eps, mom,
                                    w(bn_name + "/moving_mean").data_ptr(),
                                    w(bn_name + "/moving_variance").data_ptr(), sc.ptr, sh.ptr, mu.ptr,
                                    iv.ptr, part.ptr, nblk, self.dtype), bn_name + "_stats")
             self.add("bn_apply", [z, sc, sh], [y],
                      lambda: _call("effdet_scale_shift_act", z.ptr, sc.ptr, sh.ptr, y.ptr, rows, C, act,
                                    self.dtype), bn_name + "_apply")
-            rec.update(mean=mu, invstd=iv, nblk=nblk)
+            rec.update(mean=mu, invstd=iv, nblk=nblk, ua=sc, ub=sh)
         else:
             fs, fb = self.folded(bn_name)
             self.add("bn_apply", [z], [y],
@@ -363,9 +369,15 @@ class TrainPlan(engine.Plan):
                 self._node_backward(rec)
             else:
                 self._convblock_backward(rec)
+        # ---- backbone (only when it is trained)
+        for rec in reversed(self.bb_tape):
+            if rec["kind"] == "mbconv":
+                self._mbconv_backward(rec)
+            else:
+                self._stem_backward(rec)
 
     def _dgrad(self, x_single, xs, wt, cin, cout, dsts, targets, masks, accumulate, shapes, x_ld=None,
-               x_bs=None, x_off=None, in_dtype=None, name="", key=None):
+               x_bs=None, x_off=None, in_dtype=None, name="", key=None, extra_residual=None):
         """stride-1 3x3/1x1 data gradient = convolution of dz with the transposed kernel.
         cin/cout are those of THIS convolution (= forward Cout/Cin)."""
         n = len(dsts)
@@ -383,7 +395,8 @@ class TrainPlan(engine.Plan):
                 src = x_single if x_single is not None else xs[i]
                 d.x[i] = src.ptr + (x_off[i] if x_off else 0)
                 d.y[i] = dsts[i].ptr
-                d.residual[i] = dsts[i].ptr if accumulate[i] else None
+                d.residual[i] = dsts[i].ptr if accumulate[i] else (
+                    extra_residual.ptr if extra_residual is not None else None)
                 d.relu_mask[i] = masks[i].ptr if masks else None
                 d.H[i], d.W[i] = shapes[i][1], shapes[i][2]
                 d.ldx[i] = x_ld[i] if x_ld else 0
@@ -400,6 +413,8 @@ class TrainPlan(engine.Plan):
             return _call("effdet_conv2d", ctypes.byref(d))
         ins = ([x_single] if x_single is not None else list(xs)) + [wt] + (list(masks) if masks else [])
         ins += [dsts[i] for i in range(n) if accumulate[i]]
+        if extra_residual is not None:
+            ins.append(extra_residual)
         if isinstance(panel, Val):
             ins.append(panel)
         flops = sum(2 * self.B * s[1] * s[2] * cin * cout * taps for s in shapes)
@@ -435,6 +450,194 @@ class TrainPlan(engine.Plan):
         self.ops.append(Op("conv_dgrad_tc", ins, list(dsts), make, name,
                            sum(v.nbytes for v in ins) + sum(v.nbytes for v in dsts), flops))
 
+
+    # ------------------------------------------------------------------ backbone in training mode
+    def _stem(self):
+        if not self.train_backbone:
+            return super()._stem()
+        net, B, S = self.net, self.B, self.net.image_size
+        H = (S + 1) // 2
+        c0 = net.backbone.stem_filters
+        z = self.val((B, H, H, c0), name="stem_z", keep=True)
+        y = self.val((B, H, H, c0), name="stem", keep=True)
+        ones, zeros = net.const_ones(c0), net.const_zeros(c0)
+        # raw conv: identity scale/shift; swish is applied after the batch-norm pass, so the
+        # stem kernel's built-in swish cannot be used -> run it through the generic conv (Cin = 3)
+        self.conv([self.images], [z], "stem_conv/kernel", 3, c0, k=3, stride=2, in_dtype=F32, name="stem_conv")
+        rec = self._bn_train(z, y, "stem_bn", c0, B * H * H, ACT_SWISH)
+        rec.update(kind="stem", z=z, y=y, H=H, c0=c0)
+        self.bb_tape.append(rec)
+        return y, H
+
+    def _mbconv(self, x, blk, H):
+        if not self.train_backbone:
+            return super()._mbconv(x, blk, H)
+        B, net = self.B, self.net
+        lib = _lib.load()
+        p = blk.prefix
+        inp, cin, cmid, cout = x, blk.input_filters, blk.mid_filters, blk.output_filters
+        rec = dict(kind="mbconv", blk=blk, inp=inp, H=H)
+        xin = x
+        if blk.expand_ratio != 1:
+            z_e = self.val((B, H, H, cmid), name=p + "expand_z", keep=True)
+            y_e = self.val((B, H, H, cmid), name=p + "expand", keep=True)
+            self.conv([x], [z_e], p + "expand_conv/kernel", cin, cmid, name=p + "expand_conv")
+            rec["bn_e"] = self._bn_train(z_e, y_e, p + "expand_bn", cmid, B * H * H, ACT_SWISH)
+            rec.update(z_e=z_e, y_e=y_e)
+            xin = y_e
+        Ho = (H + blk.stride - 1) // blk.stride
+        z_d = self.val((B, Ho, Ho, cmid), name=p + "dw_z", keep=True)
+        y_d = self.val((B, Ho, Ho, cmid), name=p + "dw", keep=True)
+        ones, zeros = net.const_ones(cmid), net.const_zeros(cmid)
+        self.add("dwconv", [xin], [z_d],
+                 lambda: _call("effdet_dwconv", xin.ptr, self.w(p + "dwconv/depthwise_kernel").data_ptr(),
+                               ones.data_ptr(), zeros.data_ptr(), z_d.ptr, None, 0, B, H, H, cmid,
+                               blk.kernel_size, blk.stride, ACT_NONE, self.dtype), p + "dwconv",
+                 flops=2 * blk.kernel_size ** 2 * B * Ho * Ho * cmid)
+        rec["bn_d"] = self._bn_train(z_d, y_d, p + "bn", cmid, B * Ho * Ho, ACT_SWISH)
+        HW = Ho * Ho
+        nblk = lib.effdet_se_backward_blocks(HW, cmid, self.dtype)
+        part = self.val((B, nblk, cmid), F32, name=p + "se_partial", keep=True)
+        self.add("se_squeeze", [y_d], [part],
+                 lambda: _call("effdet_spatial_sum", y_d.ptr, part.ptr, nblk, B, HW, cmid, self.dtype),
+                 p + "se_squeeze")
+        gate = self.val((B, cmid), F32, name=p + "gate", keep=True)
+        self.add("se", [part], [gate],
+                 lambda: _call("effdet_se_gate", part.ptr, nblk, 1.0 / float(HW),
+                               self.w(p + "se_reduce/kernel").data_ptr(), self.w(p + "se_reduce/bias").data_ptr(),
+                               self.w(p + "se_expand/kernel").data_ptr(), self.w(p + "se_expand/bias").data_ptr(),
+                               gate.ptr, B, cmid, blk.se_filters), p + "se")
+        yg = self.val((B, Ho, Ho, cmid), name=p + "se_excite", keep=True)
+        self.add("se_apply", [y_d, gate], [yg],
+                 lambda: _call("effdet_se_apply", y_d.ptr, gate.ptr, yg.ptr, B, HW, cmid, self.dtype),
+                 p + "se_excite")
+        z_p = self.val((B, Ho, Ho, cout), name=p + "project_z", keep=True)
+        y_p = self.val((B, Ho, Ho, cout), name=p + "project", keep=True)
+        self.conv([yg], [z_p], p + "project_conv/kernel", cmid, cout, name=p + "project_conv")
+        rec["bn_p"] = self._bn_train(z_p, y_p, p + "project_bn", cout, B * HW, ACT_NONE)
+        out = y_p
+        if blk.has_skip:
+            out = self.val((B, Ho, Ho, cout), name=p + "add", keep=True)
+            ptrs = lambda: (ctypes.c_void_p * 3)(y_p.ptr, inp.ptr, None)
+
+            def make_add():
+                arr = ptrs()
+                self._keepalive.append(arr)
+                return _call("effdet_wbifpn_add", arr, 2, None, 0.0, out.ptr, B * HW * cout, self.dtype)
+            self.add("add", [y_p, inp], [out], make_add, p + "add")
+        rec.update(xin=xin, z_d=z_d, y_d=y_d, part=part, nblk=nblk, gate=gate, yg=yg, z_p=z_p, y_p=y_p,
+                   out=out, Ho=Ho)
+        self.bb_tape.append(rec)
+        return out, Ho
+
+    def _bn_act_backward(self, rec, dy, name):
+        """dy (gradient of act(BN(z))) -> dz, for act in {none, relu, swish}."""
+        z, C, rows, bn, act = rec["z"], rec["C"], rec["rows"], rec["bn"], rec["act"]
+        dz = self.val(z.shape, name=name + "_dz")
+        k123 = self._scratch(3 * C, bn + "/k123")
+        w = self.w
+        if rec["train"]:
+            nblk = rec["nblk"]
+            part = self._scratch(2 * C * nblk, bn + "/bwd_partial")
+            mu, iv, ua, ub = rec["mean"], rec["invstd"], rec["ua"], rec["ub"]
+            self.add("bn_bwd", [dy, z, mu, iv, ua, ub], [dz, k123, part],
+                     lambda: _call("effdet_bn_act_backward", dy.ptr, z.ptr, rows, C, w(bn + "/gamma").data_ptr(),
+                                   mu.ptr, iv.ptr, ua.ptr, ub.ptr, 0, act, self.gw(bn + "/gamma").data_ptr(),
+                                   self.gw(bn + "/beta").data_ptr(), dz.ptr, k123.ptr, part.ptr, nblk,
+                                   self.dtype), bn + "_bwd")
+        else:
+            fs, fb = self.folded(bn)
+            self.add("bn_bwd", [dy, z], [dz, k123],
+                     lambda: _call("effdet_bn_act_backward", dy.ptr, z.ptr, rows, C, w(bn + "/gamma").data_ptr(),
+                                   None, None, fs.data_ptr(), fb.data_ptr(), 1, act, None, None, dz.ptr,
+                                   k123.ptr, None, 1, self.dtype), bn + "_bwd")
+        return dz
+
+    def _mbconv_backward(self, rec):
+        lib = _lib.load()
+        B, blk = self.B, rec["blk"]
+        p = blk.prefix
+        cin, cmid, cout, H, Ho = blk.input_filters, blk.mid_filters, blk.output_filters, rec["H"], rec["Ho"]
+        HW = Ho * Ho
+        d_out = self.gvals.get(id(rec["out"]))
+        if d_out is None:
+            return
+        # project BN (linear) -> project conv
+        bn_p = dict(rec["bn_p"]); bn_p["z"] = rec["z_p"]
+        dz_p = self._bn_act_backward(bn_p, d_out, p + "project")
+        pkey = p + "project_conv/kernel"
+        yg = rec["yg"]
+        self._wgrad([yg], [dz_p], pkey, cmid, cout, 1, 1, name=p + "project_wgrad")
+        dyg = self.val(yg.shape, name=p + "se_excite_grad")
+        wt = self._transposed_weight(pkey, 1, cmid, cout)
+        self._dgrad(None, [dz_p], wt, cout, cmid, [dyg], [yg], None, [0], [yg.shape], name=p + "project_dgrad",
+                    key=pkey)
+        # squeeze-excite
+        y_d, gate, part, nblk = rec["y_d"], rec["gate"], rec["part"], rec["nblk"]
+        R = blk.se_filters
+        dy_d = self.val(y_d.shape, name=p + "dw_grad")
+        dgb = lib.effdet_se_backward_blocks(HW, cmid, self.dtype)
+        dgp = self._scratch(B * dgb * cmid, p + "se_dg_partial")
+        fcs = self._scratch(B * (2 * cmid * R + R + cmid), p + "se_fc_scratch")
+        dmean = self._scratch(B * cmid, p + "se_dmean")
+        w, gw = self.w, self.gw
+        self.add("se_bwd", [dyg, y_d, gate, part], [dy_d, dgp, fcs, dmean],
+                 lambda: _call("effdet_se_backward", dyg.ptr, y_d.ptr, gate.ptr, part.ptr, nblk,
+                               w(p + "se_reduce/kernel").data_ptr(), w(p + "se_reduce/bias").data_ptr(),
+                               w(p + "se_expand/kernel").data_ptr(), w(p + "se_expand/bias").data_ptr(),
+                               dy_d.ptr, gw(p + "se_reduce/kernel").data_ptr(), gw(p + "se_reduce/bias").data_ptr(),
+                               gw(p + "se_expand/kernel").data_ptr(), gw(p + "se_expand/bias").data_ptr(),
+                               dgp.ptr, dgb, fcs.ptr, dmean.ptr, B, HW, cmid, R, self.dtype), p + "se_bwd")
+        # depthwise BN + swish -> depthwise conv
+        bn_d = dict(rec["bn_d"]); bn_d["z"] = rec["z_d"]
+        dz_d = self._bn_act_backward(bn_d, dy_d, p + "dw")
+        xin = rec["xin"]
+        k, st = blk.kernel_size, blk.stride
+        nb = lib.effdet_dw_backward_blocks(B, H, H, cmid, k, st, self.dtype)
+        dwp = self._scratch(k * k * cmid * nb, p + "dw_partial")
+        dkey = p + "dwconv/depthwise_kernel"
+        inp = rec["inp"]
+        if blk.expand_ratio != 1:
+            d_xin = self.val(xin.shape, name=p + "expand_grad")
+        else:
+            d_xin, acc = self.grad_of(inp)
+            assert acc == 0, "block without expansion must be the only consumer of its input"
+        self.add("dw_bwd", [xin, dz_d], [d_xin, dwp],
+                 lambda: _call("effdet_dw_backward", xin.ptr, dz_d.ptr, w(dkey).data_ptr(), d_xin.ptr,
+                               gw(dkey).data_ptr(), dwp.ptr, nb, B, H, H, cmid, k, st, self.dtype), p + "dw_bwd",
+                 flops=4 * k * k * B * Ho * Ho * cmid)
+        if blk.expand_ratio == 1:
+            return
+        bn_e = dict(rec["bn_e"]); bn_e["z"] = rec["z_e"]
+        dz_e = self._bn_act_backward(bn_e, d_xin, p + "expand")
+        ekey = p + "expand_conv/kernel"
+        self._wgrad([inp], [dz_e], ekey, cin, cmid, 1, 1, name=p + "expand_wgrad")
+        if not self._needs_grad(inp):
+            return
+        g, acc = self.grad_of(inp)
+        extra = None
+        if blk.has_skip:
+            if acc:
+                raise NotImplementedError("skip block whose input already has a gradient")
+            extra = d_out                     # residual branch: d(inp) = d(out) + dgrad(expand)
+        wt = self._transposed_weight(ekey, 1, cin, cmid)
+        self._dgrad(None, [dz_e], wt, cmid, cin, [g], [inp], None, [acc], [inp.shape], name=p + "expand_dgrad",
+                    key=ekey, extra_residual=extra)
+
+    def _stem_backward(self, rec):
+        lib = _lib.load()
+        B, S = self.B, self.net.image_size
+        dy = self.gvals.get(id(rec["y"]))
+        if dy is None:
+            return
+        dz = self._bn_act_backward(rec, dy, "stem")
+        nb = lib.effdet_stem_wgrad_blocks(B, S, S)
+        c0 = rec["c0"]
+        part = self._scratch(27 * c0 * nb, "stem_wg_partial")
+        self.add("stem_wgrad", [self.images, dz], [part],
+                 lambda: _call("effdet_stem_wgrad", self.images.ptr, dz.ptr, self.gw("stem_conv/kernel").data_ptr(),
+                               part.ptr, nb, B, S, S, c0, self.dtype), "stem_wgrad")
+
     def _bn_backward(self, rec, dy):
         """dy (grad of y = relu(BN(z))) -> dz (new Val)."""
         z, y, C, rows, bn = rec["z"], rec["y"], rec["C"], rec["rows"], rec["bn"]
@@ -460,6 +663,8 @@ class TrainPlan(engine.Plan):
         return dz
 
     def _needs_grad(self, v):
+        if self.train_backbone:
+            return v is not self.images
         return not any(v is f for f in self.features)     # frozen backbone features
 
     def _node_backward(self, rec):
@@ -551,17 +756,22 @@ class Trainer:
         key = (B, dense)
         if key not in self.plans:
             net = self.net
-            n_backbone = 1 + len(net.backbone.keras_layer_names())
+            names = net.backbone.keras_layer_names()
             frozen = net.frozen_layers
-            missing = [n for n in net.backbone.keras_layer_names() if n not in frozen]
-            if missing:
+            n_frozen = sum(1 for n in names if n in frozen)
+            if 0 < n_frozen < len(names):
                 raise NotImplementedError(
-                    "this build trains BiFPN + heads only: freeze the backbone first "
-                    "(for i in range(1, %d): model.layers[i].trainable = False), as "
-                    "train_tpu.py --freeze-backbone does" % n_backbone)
+                    "partially frozen backbones are not supported: freeze all of it "
+                    "(model.freeze_backbone(), train_tpu.py --freeze-backbone) or none of it")
+            self.train_backbone = n_frozen == 0
+            if self.train_backbone and any(b.drop_rate and b.drop_rate > 0 and b.has_skip
+                                           for b in net.backbone.blocks):
+                raise NotImplementedError("stochastic depth while training the backbone is not "
+                                          "implemented: build with drop_connect_rate=0")
             self.plans[key] = TrainPlan(net, B, self.focal.alpha, self.focal.gamma, self.sl1.lambda_,
                                         dense_labels=dense,
-                                        reuse_buffers=os.environ.get("EFFDET_NO_REUSE") != "1")
+                                        reuse_buffers=os.environ.get("EFFDET_NO_REUSE") != "1",
+                                        train_backbone=self.train_backbone)
         return self.plans[key]
 
     def load_batch(self, plan, images, targets):
@@ -583,14 +793,15 @@ class Trainer:
 
     def apply_gradients(self):
         net = self.net
-        g = net.grad_flat[net.backbone_end:]
+        start = 0 if getattr(self, "train_backbone", False) else net.backbone_end
+        g = net.grad_flat[start:]
         for k in self._frozen_keys():          # layers.trainable = False outside the backbone
             net.grads[k].zero_()
         from . import parallel
         scale = parallel.allreduce_gradients_(g)      # SUM over replicas (NCCL); 1/replicas below
         n = g.numel()
-        _lib.call("effdet_sgd_momentum_step", net.flat.data_ptr() + 4 * net.backbone_end, g.data_ptr(),
-                  net.velocity.data_ptr() + 4 * net.backbone_end, n, float(self.opt.current_lr()),
+        _lib.call("effdet_sgd_momentum_step", net.flat.data_ptr() + 4 * start, g.data_ptr(),
+                  net.velocity.data_ptr() + 4 * start, n, float(self.opt.current_lr()),
                   float(self.opt.momentum), float(scale), _lib.stream_ptr(net.device))
         self.opt.iterations += 1
 

@@ -322,6 +322,41 @@ int effdet_flip_taps(const float *in, float *out, int taps, int n, void *stream)
 int effdet_sgd_momentum_step(float *w, const float *g, float *v, size_t n, float lr_t,
                              float momentum, float grad_scale, void *stream);
 
+/* ---------------------------------------------------------------- training the backbone
+ * (train_tpu.py without --freeze-backbone; BASELINE config 4).
+ * Backward of y = act(BN(z)), act in {none, relu, swish} (efficientnet.py:228-252,289-296).
+ * ua/ub: the affine map u = z*ua + ub applied in the forward pass (training-mode BN: the scale /
+ * shift written by effdet_bn_train_stats; frozen BN: the folded inference scale/shift, frozen=1,
+ * no dgamma/dbeta).  k123: 3*C floats scratch; partial: 2*C*nblk floats. */
+int effdet_bn_act_backward(const void *dy, const void *z, size_t rows, int C, const float *gamma,
+                           const float *save_mean, const float *save_invstd, const float *ua,
+                           const float *ub, int frozen, int act, float *dgamma, float *dbeta, void *dz,
+                           float *k123, float *partial, int nblk, int dtype, void *stream);
+/* Per-(image, block, channel) spatial sums of y (B,HW,C) -> partial (B, nblk, C) with
+ * nblk = effdet_se_backward_blocks(): the SE squeeze (efficientnet.py:259-260) in training mode. */
+int effdet_spatial_sum(const void *y, float *partial, int nblk, int B, int HW, int C, int dtype,
+                       void *stream);
+/* out = y * gate[b][c]  (efficientnet.py:286 se_excite, materialised in training mode). */
+int effdet_se_apply(const void *y, const float *gate, void *out, int B, int HW, int C, int dtype,
+                    void *stream);
+/* Squeeze-excite backward (efficientnet.py:255-286): dy (gradient of the SE input, both the direct
+ * path and the path through GlobalAveragePooling), gradients of se_reduce / se_expand. */
+int effdet_se_backward_blocks(int HW, int C, int dtype);
+int effdet_se_backward(const void *dyg, const void *y, const float *gate, const float *se_sum,
+                       int se_blocks, const float *w1, const float *b1, const float *w2, const float *b2,
+                       void *dy, float *dw1, float *db1, float *dw2, float *db2, float *dg_partial,
+                       int dg_blocks, float *fc_scratch, float *dmean, int B, int HW, int C, int R,
+                       int dtype, void *stream);
+/* Depthwise conv backward, k in {3,5}, stride in {1,2}: dkernel (k,k,C) and (optional) dx. */
+int effdet_dw_backward_blocks(int B, int H, int W, int C, int k, int stride, int dtype);
+int effdet_dw_backward(const void *x, const void *dz, const float *kernel, void *dx, float *dkernel,
+                       float *partial, int nblk, int B, int H, int W, int C, int k, int stride, int dtype,
+                       void *stream);
+/* Stem conv weight gradient (efficientnet.py:413-418). */
+int effdet_stem_wgrad_blocks(int B, int H, int W);
+int effdet_stem_wgrad(const float *images, const void *dz, float *dkernel, float *partial, int nblk, int B,
+                      int H, int W, int C0, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

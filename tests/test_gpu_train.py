@@ -403,10 +403,56 @@ def test_training_step_bf16_tensor_cores_matches_simt():
     assert not bad, bad
 
 
-def test_training_requires_frozen_backbone():
+@pytest.mark.parametrize("weighted,freeze_bn", [(True, False), (False, True)])
+def test_full_training_step_with_backbone(weighted, freeze_bn):
+    """Nothing frozen (BASELINE config 4 shape of step): gradients of EVERY weight, backbone included
+    (MBConv expand / depthwise / squeeze-excite / project, stem), against the fp64 autograd oracle."""
     from efficientdet_b200.model import efficientdet
-    model = efficientdet(0, num_classes=3, image_size=128, just_training_model=True)
+    from efficientdet_b200.optimizers import SGD
+    from oracle import train as otrain
+    from util_model import rel_l2
+    size, C, B, phi = 256, 5, 8, 0
+    model = efficientdet(phi, num_classes=C, weighted_bifpn=weighted, freeze_bn=freeze_bn, image_size=size,
+                         dtype="fp32", drop_connect_rate=0, just_training_model=True)
+    W0 = perturb_weights(model)
+    model.compile(optimizer=SGD(lr=0.01, decay=4e-5, momentum=0.9))
+    anchors, ann, reg_t, lab_t = _targets(size, B, C)
+    img = np.random.default_rng(5).standard_normal((B, size, size, 3)).astype(np.float32)
+    total, l_reg, l_cls = model.train_on_batch(img, [reg_t, lab_t])
+    fl, sl, grads, stats = otrain.loss_and_grads(W0, img, reg_t, lab_t, phi, C, weighted, freeze_bn,
+                                                 freeze_backbone=False)
+    assert abs(l_cls - fl) / fl < 2e-4, (l_cls, fl)
+    assert abs(l_reg - sl) / max(sl, 1e-9) < 2e-4, (l_reg, sl)
+    assert any(k.startswith("block") for k in grads) and "stem_conv/kernel" in grads
+    net = model.net
+    bad = {}
+    for k, g in grads.items():
+        if np.abs(g).max() < 1e-12:
+            continue
+        e = rel_l2(net.grads[k].cpu().numpy(), g)
+        if not e < (0.25 if k.startswith("w_bi_fpn_add") else 8e-2):
+            bad[k] = float(e)
+    assert not bad, bad
+    W1 = model.get_weights_dict()
+    for k in ("stem_conv/kernel", "block3b_se_reduce/kernel", "block5a_dwconv/depthwise_kernel"):
+        want = W0[k].astype(np.float64) - 0.01 * net.grads[k].cpu().numpy()
+        assert rel_err(W1[k], want) < 1e-5, k
+    if not freeze_bn:
+        for name in ("stem_bn", "block2a_expand_bn", "block4b_bn", "block7a_project_bn"):
+            m, v = stats[name]
+            assert rel_err(W1[name + "/moving_mean"], W0[name + "/moving_mean"] * 0.99 + m * 0.01) < 1e-4, name
+            assert rel_err(W1[name + "/moving_variance"], W0[name + "/moving_variance"] * 0.99 + v * 0.01) < 1e-4
+
+
+def test_partial_backbone_freeze_and_stochastic_depth_are_rejected():
+    from efficientdet_b200.model import efficientdet
+    z = lambda *s: np.zeros(s, np.float32)
+    model = efficientdet(0, num_classes=3, image_size=128, just_training_model=True, drop_connect_rate=0)
+    model.layers[5].trainable = False
     model.compile()
     with pytest.raises(NotImplementedError):
-        model.train_on_batch(np.zeros((1, 128, 128, 3), np.float32),
-                             [np.zeros((1, 3069, 5), np.float32), np.zeros((1, 3069, 4), np.float32)])
+        model.train_on_batch(z(1, 128, 128, 3), [z(1, 3069, 5), z(1, 3069, 4)])
+    model = efficientdet(0, num_classes=3, image_size=128, just_training_model=True)   # drop_connect 0.2
+    model.compile()
+    with pytest.raises(NotImplementedError):
+        model.train_on_batch(z(1, 128, 128, 3), [z(1, 3069, 5), z(1, 3069, 4)])
