@@ -26,9 +26,10 @@ WORKLOADS = {
     "d0_infer_b1": ("infer", 0, 1, 90, "bf16", False),
     "d0_infer_b32": ("infer", 0, 32, 20, "bf16", False),
     "d2_infer_b64": ("infer", 2, 64, 90, "bf16", False),
-    "d0_train_b32": ("train", 0, 32, 20, "bf16", False),
-    "d4_train_b8": ("train", 4, 8, 90, "bf16", False),
+    "d0_train_b32": ("train", 0, 32, 20, "bf16", False),          # BASELINE configs[1] (frozen backbone)
+    "d4_train_b8": ("train", 4, 8, 90, "bf16", False),            # BASELINE configs[3] (nothing frozen)
 }
+FREEZE_BACKBONE = {"d0_train_b32": True, "d4_train_b8": False}
 DEFAULT_WORKLOAD = "d0_train_b32"   # BASELINE.json configs[1]
 
 
@@ -106,7 +107,8 @@ def run_ours(args, rank, world):
     hbm, tflops, peak_src = peaks()
     if kind == "train":
         from efficientdet_b200 import train as T
-        return T.bench_train(args, rank, world, phi, B, C, dtype, weighted, dev)
+        return T.bench_train(args, rank, world, phi, B, C, dtype, weighted, dev,
+                             freeze_backbone=FREEZE_BACKBONE[args.workload])
 
     S = [512, 640, 768, 896, 1024, 1280, 1408][phi]
     anchors = anchors_for_shape((S, S))
@@ -303,7 +305,7 @@ def run_reference(args, rank, world):
     torch.set_num_threads(os.cpu_count())
     if kind == "train":
         from efficientdet_b200 import train as T
-        return T.bench_train_reference(args, phi, B, C, weighted)
+        return T.bench_train_reference(args, phi, B, C, weighted, FREEZE_BACKBONE[args.workload])
     W = _random_weights(phi, C, weighted)
     anchors = oa.anchors_for_shape((S, S)).astype(np.float32)
     sample = max(1, min(B, 2))

@@ -867,7 +867,7 @@ def _synthetic_gt(B, S, C, seed):
     return ann
 
 
-def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev):
+def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev, freeze_backbone=True):
     import bench as bench_mod
     from .model import efficientdet
     from .optimizers import SGD
@@ -877,7 +877,8 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev):
     hbm, tflops, peak_src = bench_mod.peaks()
     model = efficientdet(phi, num_classes=C, weighted_bifpn=weighted, dtype=dtype, drop_connect_rate=0,
                          just_training_model=True, seed=2024)
-    model.freeze_backbone()
+    if freeze_backbone:
+        model.freeze_backbone()
     model.compile(optimizer=SGD(lr=0.01, decay=4e-5, momentum=0.9),
                   loss={"regression": tpu_smooth_l1(), "classification": tpu_focal(alpha=0.25, gamma=1.5)})
     tr = model._trainer
@@ -969,7 +970,7 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev):
     roof.update(traffic=None, kernel=dom_kind, launches=dom["n"], share_of_step=dom["ms"] / total_ms,
                 peak_source=peak_src,
                 per_kind_ms={k_: round(v["ms"], 4) for k_, v in sorted(by_kind.items())})
-    cpu = cpu_baseline_train(phi, C, weighted, S) if rank == 0 else None
+    cpu = cpu_baseline_train(phi, C, weighted, S, freeze_backbone=freeze_backbone) if rank == 0 else None
     imgs = B * world * args.steps
     h2d = B * S * S * 3 * 4 + sum(t.numel() * t.element_size() for t in gts[0]["host"])
     return {
@@ -979,13 +980,16 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev):
         "data": "synthetic (numpy default_rng images + VOC-shaped boxes, random-init weights)",
         "config": {"workload": args.workload, "phi": phi, "image_size": S, "batch_per_gpu": B,
                    "global_batch": B * world, "num_classes": C, "weighted_bifpn": weighted,
-                   "freeze_backbone": True, "optimizer": "SGD(lr=.01, decay=4e-5, momentum=.9)",
-                   "step": "device anchor targets -> forward (BN batch stats in BiFPN) -> focal + "
-                           "smooth-L1 -> backward (heads + BiFPN) -> grad all-reduce -> SGD",
+                   "freeze_backbone": freeze_backbone, "optimizer": "SGD(lr=.01, decay=4e-5, momentum=.9)",
+                   "step": "device anchor targets -> forward (BN batch stats in %s) -> focal + "
+                           "smooth-L1 -> backward (%s) -> grad all-reduce -> SGD"
+                           % (("BiFPN", "heads + BiFPN") if freeze_backbone else
+                              ("every layer", "heads + BiFPN + backbone")),
                    "l2": "inputs rotate over %d image sets (%.0f MB) > 126 MB L2; activations %.0f MB"
                          % (n_sets, n_sets * B * S * S * 12 / 1e6, plan.activation_bytes / 1e6),
                    "parallelism": "dp%d (NCCL all-reduce of %.1f MB fp32 gradients)"
-                                  % (world, 4 * (model.net.flat.numel() - model.net.backbone_end) / 1e6),
+                                  % (world, 4 * (model.net.flat.numel() -
+                                                 (model.net.backbone_end if freeze_backbone else 0)) / 1e6),
                    "final_losses": losses[:2]},
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 32},
@@ -994,7 +998,7 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev):
     }
 
 
-def _cpu_train_step_fn(phi, C, weighted, S, batch):
+def _cpu_train_step_fn(phi, C, weighted, S, batch, freeze_backbone=True):
     import bench as bench_mod
     from oracle import anchors as oa, train as otrain
     W = bench_mod._random_weights(phi, C, weighted)
@@ -1007,14 +1011,14 @@ def _cpu_train_step_fn(phi, C, weighted, S, batch):
         from oracle import overlap_c
         reg_t, lab_t = overlap_c.anchor_targets_bbox(anchors, [(S, S, 3)] * batch, ann, C)
         _, _, grads, _ = otrain.loss_and_grads(W, img, reg_t, lab_t, phi, C, weighted, False,
-                                               dtype=torch.float32)
+                                               dtype=torch.float32, freeze_backbone=freeze_backbone)
         otrain.sgd_step(W, grads, vel)
     return step
 
 
-def cpu_baseline_train(phi, C, weighted, S, budget_s=20.0, batch=2):
+def cpu_baseline_train(phi, C, weighted, S, budget_s=20.0, batch=2, freeze_backbone=True):
     torch.set_num_threads(os.cpu_count())
-    step = _cpu_train_step_fn(phi, C, weighted, S, batch)
+    step = _cpu_train_step_fn(phi, C, weighted, S, batch, freeze_backbone)
     n, t0 = 0, time.perf_counter()
     while True:
         step()
@@ -1024,15 +1028,15 @@ def cpu_baseline_train(phi, C, weighted, S, budget_s=20.0, batch=2):
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
             "sample": "%d image(s): the same training step (C target assignment + torch-CPU fp32 autograd "
-                      "of the reference graph, frozen backbone, SGD) in batches of %d, %.1f s"
-                      % (n, batch, dt)}
+                      "of the reference graph, %s, SGD) in batches of %d, %.1f s"
+                      % (n, "frozen backbone" if freeze_backbone else "nothing frozen", batch, dt)}
 
 
-def bench_train_reference(args, phi, B, C, weighted):
+def bench_train_reference(args, phi, B, C, weighted, freeze_backbone=True):
     S = [512, 640, 768, 896, 1024, 1280, 1408][phi]
     torch.set_num_threads(os.cpu_count())
     batch = max(1, min(B, 2))
-    step = _cpu_train_step_fn(phi, C, weighted, S, batch)
+    step = _cpu_train_step_fn(phi, C, weighted, S, batch, freeze_backbone)
     for _ in range(min(args.warmup, 1)):
         step()
     steps = max(1, min(args.steps, 4))
@@ -1047,7 +1051,7 @@ def bench_train_reference(args, phi, B, C, weighted):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (numpy default_rng images + VOC-shaped boxes, random-init weights)",
         "config": {"workload": args.workload, "phi": phi, "image_size": S, "batch_per_gpu": B,
-                   "num_classes": C, "weighted_bifpn": weighted, "freeze_backbone": True},
+                   "num_classes": C, "weighted_bifpn": weighted, "freeze_backbone": freeze_backbone},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": "%d-image training steps on torch-CPU fp32 (reference graph restated; "
                                    "TensorFlow not installable)" % batch},
