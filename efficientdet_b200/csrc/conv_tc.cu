@@ -34,16 +34,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    return done != 0;
+}
+// Spinning waiters share the SM's issue slots with the epilogue warps (the busy ones in the
+// HBM-bound layers): back off between probes.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(a), "r"(parity) : "memory");
-    }
+    if (mbar_try(a, parity)) return;
+    while (!mbar_try(a, parity)) __nanosleep(32);
 }
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
                                             int c1, int c2, int c3) {
@@ -68,7 +73,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void 
         ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// at most n of this thread's bulk stores may still be READING their shared-memory source
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                  "r"(ncols) : "memory");
@@ -131,6 +141,7 @@ struct TcGroup {
     int tiles_x, tiles_y, tiles_b;
     int tile_begin;
     int tma_store;            // output rows are 16-byte strided: store through out_map
+    int lw, lh;               // log2(Wt), log2(Ht): tile extents are powers of two
 };
 struct alignas(64) TcParams {
     CUtensorMap a_map[kTcMaxGroups];
@@ -163,10 +174,26 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int t) {
     return c;
 }
 
-template <int ACT> __device__ __forceinline__ float fast_act(float x) {
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+// HALF_IN: the caller passes z/2 (the 1/2 is folded into the per-channel scale / shift), so that
+// swish(z) = z * sigmoid(z) = (z/2) * (1 + tanh(z/2)) costs one MUFU and one FMA.  The special
+// function unit is the co-limiter of the HBM-bound expand convolutions (one output element per
+// 2 bytes written); bf16 outputs only -- tanh.approx is good to ~2^-11 absolute.
+template <int ACT, bool HALF_IN> __device__ __forceinline__ float fast_act(float x) {
     if (ACT == EFFDET_ACT_RELU) return fmaxf(x, 0.f);
-    if (ACT == EFFDET_ACT_SWISH) return x * __frcp_rn(1.f + __expf(-x));
-    if (ACT == EFFDET_ACT_SIGMOID) return __frcp_rn(1.f + __expf(-x));
+    if (ACT == EFFDET_ACT_SWISH) {
+        if (HALF_IN) return fmaf(x, tanh_approx(x), x);
+        return x * rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x));
+    }
+    if (ACT == EFFDET_ACT_SIGMOID) return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x));
     return x;
 }
 
@@ -191,6 +218,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     uint64_t *tmem_full = empty + p.stages;      // [2]
     uint64_t *tmem_empty = tmem_full + 2;        // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    // epilogue staging (TMA-store path): per warp two [32 rows][32 columns] swizzled buffers
+    constexpr int kStageBytes = 32 * 32 * (OUT_F32 ? 4 : 2);
+    uint8_t *sStage = reinterpret_cast<uint8_t *>(
+        (reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pad = p.ksize / 2;
@@ -262,7 +293,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         const int half = ew >> 2;                           // which of the two warps of this quarter
         const int row = q * 32 + lane;                      // tile row == TMEM lane
         const int et = threadIdx.x - 64;                    // 0..255
-        int ti = 0, cur_n0 = -1;
+        constexpr bool kHalfIn = (ACT == EFFDET_ACT_SWISH) && !OUT_F32;
+        int ti = 0, cur_n0 = -1, sbuf = 0;
+        uint8_t *my_stage = sStage + (size_t)ew * 2 * kStageBytes;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
             const TileCoord tc = decode_tile(p, t);
             const TcGroup &G = p.g[tc.gi];
@@ -272,36 +305,44 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                 // per-column scale / shift of this N tile -> shared memory (uniform across the CTA)
                 asm volatile("bar.sync 1, 256;" ::: "memory");       // previous tile's readers are done
                 const int n = n0 + et;
-                sScale[et] = (p.scale && n < p.Cout) ? p.scale[n] : 1.f;
-                sShift[et] = (p.shift && n < p.Cout) ? p.shift[n] : 0.f;
+                const float pre = kHalfIn ? 0.5f : 1.f;
+                sScale[et] = pre * ((p.scale && n < p.Cout) ? p.scale[n] : 1.f);
+                sShift[et] = pre * ((p.shift && n < p.Cout) ? p.shift[n] : 0.f);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 cur_n0 = n0;
             }
-            const int xx = row % G.Wt, yy = (row / G.Wt) % G.Ht, bb = row / (G.Wt * G.Ht);
+            const int xx = row & (G.Wt - 1), yy = (row >> G.lw) & (G.Ht - 1), bb = row >> (G.lw + G.lh);
             const int x = x0 + xx, y = y0 + yy, b = b0 + bb;
             const bool row_ok = x < G.W && y < G.H && b < p.B;
             const size_t base = (size_t)b * G.y_batch_stride + ((size_t)y * G.W + x) * G.ldc;
             const float kp = (p.keep && row_ok) ? p.keep[b] : 1.f;
+            // origin of this warp's 32-row box (rows 32q .. 32q+31 of the tile) for the TMA store
+            const int r0 = q * 32;
+            const int sx = x0 + (r0 & (G.Wt - 1)), sy = y0 + ((r0 >> G.lw) & (G.Ht - 1)), sb = b0 + (r0 >> (G.lw + G.lh));
+            const bool tma_out = G.tma_store != 0;
             mbar_wait(&tmem_full[acc], aph);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(q * 32) << 16);
-            for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
+            // 32-column chunks alternate between the two warps of a lane quarter; the starting warp
+            // flips every tile so that an odd chunk count (N = 96: 3 chunks) balances over two tiles
+            for (int c0 = ((half ^ ti) & 1) * 32; c0 < p.block_n; c0 += 64) {
+                const int nbase = n0 + c0;
+                const int ncols = min(32, min(p.Cout, n0 + p.block_n) - nbase);   // warp-uniform
+                if (ncols <= 0) break;
                 uint32_t r[32];
                 __syncwarp();                               // tcgen05.ld is warp-collective
                 tmem_ld32(d_tmem + (uint32_t)c0, r);
-                const int nbase = n0 + c0;
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 sc = *reinterpret_cast<const float4 *>(sScale + c0 + j);
                     const float4 sh = *reinterpret_cast<const float4 *>(sShift + c0 + j);
-                    v[j] = fast_act<ACT>(fmaf(__uint_as_float(r[j]), sc.x, sh.x));
-                    v[j + 1] = fast_act<ACT>(fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y));
-                    v[j + 2] = fast_act<ACT>(fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z));
-                    v[j + 3] = fast_act<ACT>(fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w));
+                    v[j] = fast_act<ACT, kHalfIn>(fmaf(__uint_as_float(r[j]), sc.x, sh.x));
+                    v[j + 1] = fast_act<ACT, kHalfIn>(fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y));
+                    v[j + 2] = fast_act<ACT, kHalfIn>(fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z));
+                    v[j + 3] = fast_act<ACT, kHalfIn>(fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w));
                 }
-                const int nvalid = row_ok ? min(32, min(p.Cout, n0 + p.block_n) - nbase) : 0;
-                if (nvalid <= 0) continue;
+                const int nvalid = row_ok ? ncols : 0;
                 if (OUT_F32) {
                     float *Y = static_cast<float *>(G.y) + base + nbase;
                     const float *R = G.res ? static_cast<const float *>(G.res) + base + nbase : nullptr;
@@ -315,7 +356,21 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                             }
                         }
                     }
-                    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
+                    if (tma_out) {
+                        // [32 rows][128 B] SWIZZLE_128B: 16-byte chunk index ^= row & 7 (bank-conflict free)
+                        tma_store_wait_read<1>();           // the store that last read this buffer is done
+                        __syncwarp();
+                        uint8_t *dst = my_stage + (size_t)sbuf * kStageBytes + lane * 128;
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            *reinterpret_cast<float4 *>(dst + ((j4 ^ (lane & 7)) << 4)) =
+                                make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0)
+                            tma_store_4d(&p.out_map[tc.gi], my_stage + (size_t)sbuf * kStageBytes, nbase, sx, sy, sb);
+                        sbuf ^= 1;
+                    } else if (nvalid == 32 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4)
                             *reinterpret_cast<float4 *>(Y + 4 * j4) =
@@ -328,7 +383,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                     __nv_bfloat16 *Y = static_cast<__nv_bfloat16 *>(G.y) + base + nbase;
                     const __nv_bfloat16 *R = G.res ? static_cast<const __nv_bfloat16 *>(G.res) + base + nbase : nullptr;
                     const __nv_bfloat16 *MK = G.mask ? static_cast<const __nv_bfloat16 *>(G.mask) + base + nbase : nullptr;
-                    if (R || MK) {
+                    if ((R || MK) && nvalid > 0) {
                         const bool vec = nvalid == 32 && (!R || (reinterpret_cast<uintptr_t>(R) & 15) == 0) &&
                                          (!MK || (reinterpret_cast<uintptr_t>(MK) & 15) == 0);
                         if (vec) {
@@ -363,7 +418,25 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                             }
                         }
                     }
-                    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
+                    if (tma_out) {
+                        // [32 rows][64 B] SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3 (bank-conflict free)
+                        tma_store_wait_read<1>();
+                        __syncwarp();
+                        uint8_t *dst = my_stage + (size_t)sbuf * kStageBytes + lane * 64;
+#pragma unroll
+                        for (int j8 = 0; j8 < 4; ++j8) {
+                            uint4 ov;
+                            __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&ov);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[8 * j8 + 2 * j], v[8 * j8 + 2 * j + 1]);
+                            *reinterpret_cast<uint4 *>(dst + ((j8 ^ ((lane >> 1) & 3)) << 4)) = ov;
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0)
+                            tma_store_4d(&p.out_map[tc.gi], my_stage + (size_t)sbuf * kStageBytes, nbase, sx, sy, sb);
+                        sbuf ^= 1;
+                    } else if (nvalid == 32 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
 #pragma unroll
                         for (int j8 = 0; j8 < 4; ++j8) {
                             uint4 ov;
@@ -383,6 +456,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // outstanding TMA stores land before exit
     }
     tc_fence_before();
     __syncthreads();
@@ -599,8 +673,9 @@ extern "C" int effdet_conv_tc_block_n(int n) {
     // (16 epilogue warps) per SM; N is split into equal tiles rounded up to 16.
     const int n16 = round_up(n, 16);
     if (n16 <= 128) return n16;
+    // several N tiles: multiples of 32 so that no 32-column epilogue chunk straddles two tiles
     const int tiles = (n16 + 127) / 128;
-    return round_up((n16 + tiles - 1) / tiles, 16);
+    return round_up((n16 + tiles - 1) / tiles, 32);
 }
 
 extern "C" size_t effdet_conv_weight_panel_elems(int taps_or_samples, int K, int N) {
@@ -647,13 +722,15 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     // <= 4 stages: with 64..128-wide N tiles two CTAs stay resident per SM, so one CTA's
     // epilogue overlaps the other's main loop
     // small tiles: 2 resident CTAs per SM (<= ~100 KiB each); wide tiles: 1
-    int stages = ((bn <= 128 ? 100 : 200) * 1024) / (kATileBytes + b_tile_bytes);
+    const int stage_out_bytes = kEpiWarps * 2 * 32 * 32 * (p.out_f32 ? 4 : 2);
+    int stages = ((bn <= 128 ? 108 : 216) * 1024 - stage_out_bytes) / (kATileBytes + b_tile_bytes);
     if (stages > 4) stages = 4;
-    const int num_k = d->kh * d->kw * p.kblocks_per_tap;
-    if (stages > num_k) stages = num_k;
-    if (stages < 1) stages = 1;
+    // persistent kernel: the ring runs ahead ACROSS tiles, so its depth does not depend on the
+    // number of K blocks of one tile (a 1x1 convolution with Cin <= 64 has a single K block)
+    if (stages < 2) stages = 2;
     p.stages = stages;
-    const size_t smem = (size_t)stages * (kATileBytes + b_tile_bytes) + 2048 + (2 * stages + 4) * 8 + 16 + 1024;
+    const size_t smem = (size_t)stages * (kATileBytes + b_tile_bytes) + 2048 + (2 * stages + 4) * 8 + 16 + 1024 +
+                        1024 + stage_out_bytes;
     p.any_tma_store = 0;
     int tiles = 0;
     for (int i = 0; i < d->n_groups; ++i) {
@@ -665,6 +742,7 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
         if (d->weight_per_sample) { g.Bt = 1; pick_tile(g.W, g.H, 1, &g.Wt, &g.Ht, &g.Bt); if (g.Bt != 1) { g.Wt = 16; g.Ht = 8; g.Bt = 1; } }
         else pick_tile(g.W, g.H, d->B, &g.Wt, &g.Ht, &g.Bt);
         g.tiles_x = cdiv(g.W, g.Wt); g.tiles_y = cdiv(g.H, g.Ht); g.tiles_b = cdiv(d->B, g.Bt);
+        g.lw = 31 - __builtin_clz(g.Wt); g.lh = 31 - __builtin_clz(g.Ht);
         g.tile_begin = tiles;
         tiles += g.tiles_x * g.tiles_y * g.tiles_b;
         const long long ldx = d->ldx[i] ? d->ldx[i] : d->Cin;
@@ -678,7 +756,27 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
                             strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_conv2d: cuTensorMapEncodeTiled(A) failed %s(%lld)", "", (long long)r);
-        g.tma_store = 0;
+        // coalesced output: the epilogue stages 32-row x 32-column pieces in shared memory and TMA
+        // stores them (rows / channels outside the tensor are clipped by the tensor map)
+        const int es_out = p.out_f32 ? 4 : 2;
+        g.tma_store = ((long long)g.ldc * es_out) % 16 == 0 && (g.y_batch_stride * es_out) % 16 == 0 &&
+                      (reinterpret_cast<uintptr_t>(g.y) & 15) == 0;
+        if (g.tma_store) {
+            cuuint32_t obox[4];
+            obox[0] = 32;
+            if (g.Wt >= 32) { obox[1] = 32; obox[2] = 1; obox[3] = 1; }
+            else if (g.Wt * g.Ht >= 32) { obox[1] = g.Wt; obox[2] = 32 / g.Wt; obox[3] = 1; }
+            else { obox[1] = g.Wt; obox[2] = g.Ht; obox[3] = 32 / (g.Wt * g.Ht); }
+            cuuint64_t odims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)d->B};
+            cuuint64_t ostr[3] = {(cuuint64_t)g.ldc * es_out, (cuuint64_t)g.ldc * es_out * g.W,
+                                  (cuuint64_t)g.y_batch_stride * es_out};
+            CUresult ro = encode(&p.out_map[i], p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                                 4, g.y, odims, ostr, obox, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 p.out_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (ro != CUDA_SUCCESS) g.tma_store = 0;
+            else p.any_tma_store = 1;
+        }
     }
     {
         const int nz = d->weight_per_sample ? d->B : d->kh * d->kw;
@@ -693,7 +791,7 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     }
     p.n_tiles = Npad / bn;
     p.total_tiles = tiles * p.n_tiles;
-    const int ctas_per_sm = (smem <= 110 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
+    const int ctas_per_sm = (smem <= 113 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
     int grid = kNumSMs * ctas_per_sm;
     if (grid > p.total_tiles) grid = p.total_tiles;
     static bool attr_set = false;

@@ -2,7 +2,8 @@ import sys, ctypes, numpy as np, torch
 sys.path.insert(0,'.'); sys.path.insert(0,'tests')
 from efficientdet_b200 import _lib
 from test_gpu_conv_tc import _panel, _d
-cases={"expand2a":(32,256,16,96,1,2),"expand3a":(32,128,24,144,1,2),"project2b":(32,128,144,24,1,0),"head":(32,64,64,64,3,1),"project7a":(32,16,1152,320,1,0)}
+cases={"expand2a":(32,256,16,96,1,2),"expand3a":(32,128,24,144,1,2),"project2b":(32,128,144,24,1,0),"head":(32,64,64,64,3,1),"project7a":(32,16,1152,320,1,0),
+"expand3b":(32,64,40,240,1,2),"expand4b":(32,32,80,480,1,2),"expand5b":(32,32,112,672,1,2),"project5b":(32,32,672,112,1,0),"expand6b":(32,16,192,1152,1,2),"project1a":(32,256,32,16,1,0)}
 name=sys.argv[1] if len(sys.argv)>1 else "expand2a"
 B,H,cin,cout,k,act=cases[name]
 rng=np.random.default_rng(0)
