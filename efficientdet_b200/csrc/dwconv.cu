@@ -255,14 +255,33 @@ se_gate_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_hw,
                const float *__restrict__ w1, const float *__restrict__ b1,
                const float *__restrict__ w2, const float *__restrict__ b2,
                float *__restrict__ gate, int C, int R) {
-    extern __shared__ float sm[];      // mean[C] | r[R]
-    float *mean = sm, *r = sm + C;
+    extern __shared__ float sm[];      // mean[C] | r[R] | part[256]
+    float *mean = sm, *r = sm + C, *part = sm + C + R;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int c = tid; c < C; c += 256) {
-        const float *src = se_sum + (size_t)b * se_blocks * C + c;
-        float t = 0.f;
-        for (int k = 0; k < se_blocks; ++k) t += src[(size_t)k * C];
-        mean[c] = t * inv_hw;
+    if (C >= 256 || se_blocks < 8) {
+        for (int c = tid; c < C; c += 256) {
+            const float *src = se_sum + (size_t)b * se_blocks * C + c;
+            float t = 0.f;
+            for (int k = 0; k < se_blocks; ++k) t += src[(size_t)k * C];
+            mean[c] = t * inv_hw;
+        }
+    } else {
+        // few channels, many tile partials (early stages): KS threads per channel each add every
+        // KS-th partial, then the KS slices are added in order -- still a fixed summation order
+        const int KS = 256 / C;
+        const int c = tid % C, slice = tid / C;
+        if (slice < KS) {
+            const float *src = se_sum + (size_t)b * se_blocks * C + c;
+            float t = 0.f;
+            for (int k = slice; k < se_blocks; k += KS) t += src[(size_t)k * C];
+            part[slice * C + c] = t;
+        }
+        __syncthreads();
+        if (tid < C) {
+            float t = 0.f;
+            for (int s2 = 0; s2 < KS; ++s2) t += part[s2 * C + tid];
+            mean[tid] = t * inv_hw;
+        }
     }
     __syncthreads();
     for (int j = warp; j < R; j += 8) {
@@ -460,12 +479,18 @@ static int launch_dw(const void *x, const float *w, const float *scale, const fl
     return EFFDET_OK;
 }
 
+// dwconv_tma.cu: TMA-fed persistent kernel (bf16)
+int dwconv_bf16_tma(const void *x, const float *w, const float *scale, const float *shift, void *y, float *se_sum,
+                    int B, int H, int W, int C, int k, int stride, int act, cudaStream_t st);
+int dwconv_bf16_tma_se_blocks(int H, int W, int stride);
+
 }  // namespace effdet
 
 using namespace effdet;
 
 extern "C" int effdet_dwconv_se_blocks(int B, int H, int W, int C, int stride, int dtype) {
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || stride < 1) return 0;
+    if (dtype == EFFDET_BF16) return dwconv_bf16_tma_se_blocks(H, W, stride);
     {   // tiled kernel: one partial per 8x16 output tile
         const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
         return ((Wo + kDwTW - 1) / kDwTW) * ((Ho + kDwTH - 1) / kDwTH);
@@ -495,14 +520,7 @@ extern "C" int effdet_dwconv(const void *x, const float *kernel, const float *sc
     cudaStream_t st = as_stream(stream);
 #define DW_CASE(T, CV, K, S, NCV) return launch_dw_tiled<T, CV, K, S, NCV>(x, kernel, scale, shift, y, se_sum, B, H, W, C, act, st)
     if (dtype == EFFDET_BF16) {
-        if (C % 64 != 0 && C <= 32) {       // narrow layers: do not idle half of the lanes
-            if (k == 3 && stride == 1) DW_CASE(__nv_bfloat16, 8, 3, 1, 4);
-            if (k == 5 && stride == 1) DW_CASE(__nv_bfloat16, 8, 5, 1, 4);
-        }
-        if (k == 3 && stride == 1) DW_CASE(__nv_bfloat16, 8, 3, 1, 8);
-        if (k == 5 && stride == 1) DW_CASE(__nv_bfloat16, 8, 5, 1, 8);
-        if (k == 3 && stride == 2) DW_CASE(__nv_bfloat16, 8, 3, 2, 4);
-        if (k == 5 && stride == 2) DW_CASE(__nv_bfloat16, 8, 5, 2, 4);
+        return dwconv_bf16_tma(x, kernel, scale, shift, y, se_sum, B, H, W, C, k, stride, act, st);
     } else if (dtype == EFFDET_F32) {
         if (k == 3 && stride == 1) DW_CASE(float, 4, 3, 1, 8);
         if (k == 5 && stride == 1) DW_CASE(float, 4, 5, 1, 8);
@@ -518,7 +536,7 @@ extern "C" int effdet_se_gate(const float *se_sum, int se_blocks, float inv_hw, 
                               int B, int C, int R, void *stream) {
     EFFDET_REQUIRE(se_sum && w1 && b1 && w2 && b2 && gate, "null pointer");
     EFFDET_REQUIRE(B > 0 && C > 0 && R > 0 && se_blocks > 0, "bad sizes");
-    const size_t sm = (size_t)(C + R) * sizeof(float);
+    const size_t sm = (size_t)(C + R + 256) * sizeof(float);
     EFFDET_REQUIRE(sm <= 48 * 1024, "C + R too large");
     se_gate_kernel<<<B, 256, sm, as_stream(stream)>>>(se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate,
                                                       C, R);

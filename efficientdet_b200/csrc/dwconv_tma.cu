@@ -1,0 +1,286 @@
+// Depthwise k x k convolution + folded BN + activation (+ squeeze-excite partial sums) for bf16
+// NHWC tensors on sm_100a -- the HBM-bound half of every MBConv block (efficientnet.py:242-260)
+// and the BiFPN DepthwiseConvBlock (model.py:48-68).  SURVEY section 8(a) row 4.
+//
+// Persistent blocks walk (x tile, y tile, channel block, image) tiles.  One elected thread feeds a
+// two-deep shared-memory ring with TMA: the (8*S+K-S) x (16*S+K-S) x CB input patch of the next tile
+// (out-of-image rows / columns / channels are zero-filled by the tensor map == TF "SAME"
+// padding, asymmetric for stride 2) and its K*K x CB weight slice land while the current tile
+// is being computed, so a block always has one tile of loads in flight and two resident blocks
+// per SM keep ~60-170 KB per SM outstanding.
+// A thread owns ONE channel pair (a bf16x2 word == one packed fp32x2 FFMA2 operand) and a 2 x 4
+// register tile of outputs; its K*K weights live in registers for the whole tile, every input
+// word is read from shared memory once and feeds up to 2*K FFMA2s, so the kernel needs ~12 bytes
+// of shared-memory traffic per output element instead of ~45 for a vector-per-thread layout
+// (which measured smem/LSU-bound: ncu short_scoreboard + mio_throttle, profiles/).  Lanes run
+// along the channel pairs: a warp reads / writes whole 64..128-byte pixel rows.
+// SE partial sums are reduced in a fixed order (registers -> shared rows -> one (image, tile,
+// channel) partial) so the result is bit-reproducible run to run.
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace effdet {
+
+constexpr int kRtH = 2, kRtW = 4;          // outputs per thread (register tile)
+
+struct alignas(64) DwTmaParams {
+    CUtensorMap x_map;                     // (C, W, H, B) bf16, box (CB, IW, IH, 1)
+    CUtensorMap w_map;                     // (C, K*K) f32,      box (CB, K*K)
+    const float *scale, *shift;
+    __nv_bfloat16 *y;
+    float *se_sum;
+    int Ho, Wo, C, pad_t, pad_l, tiles_x, tiles_y, cblocks, total_tiles;
+};
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ float tanh_approx_f(float x) {
+    float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+
+// S = 1: 8 x 16 output tile, two register-tile passes per thread; S = 2: 8 x 8 tile, one pass
+template <int K, int S, int CP> struct DwCfg {
+    static constexpr int TH = 8, TW = S == 1 ? 16 : 8;
+    static constexpr int CB = CP * 2;
+    static constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
+    static constexpr int NRT = (TH / kRtH) * (TW / kRtW);              // register tiles per tile
+    static constexpr int PASSES = NRT / 8;
+    static constexpr int NT = CP * 8;
+    static constexpr int IR = (kRtH - 1) * S + K, NIN = (kRtW - 1) * S + K;
+    static constexpr int IN_BYTES = IH * IW * CB * 2;
+    static constexpr int IN_PAD = ((IN_BYTES + 127) / 128) * 128;       // TMA destinations are 128-byte aligned
+    static constexpr int W_BYTES = K * K * CB * 4;
+    static constexpr int STAGE_BYTES = ((IN_PAD + W_BYTES + 127) / 128) * 128;
+    static constexpr size_t SMEM = 2 * (size_t)STAGE_BYTES + 2 * 8 * CB * 4 + 64 + 128;
+};
+
+template <int K, int S, int CP, int ACT>
+__global__ void __launch_bounds__(DwCfg<K, S, CP>::NT, 2)
+dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
+    using Cfg = DwCfg<K, S, CP>;
+    constexpr int CB = Cfg::CB, IW = Cfg::IW, NIN = Cfg::NIN, IR = Cfg::IR, TW = Cfg::TW, TH = Cfg::TH;
+    extern __shared__ uint8_t dsm_raw[];
+    // pointer arithmetic on the __shared__ array (not through uintptr_t) keeps LDS/STS addressing
+    uint8_t *dsm = dsm_raw + ((128u - (smem_u32(dsm_raw) & 127u)) & 127u);
+    float *sRed = reinterpret_cast<float *>(dsm + 2 * Cfg::STAGE_BYTES);      // [2][8][CB]
+    uint64_t *full = reinterpret_cast<uint64_t *>(sRed + 2 * 8 * CB);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int t, int stage) {
+        int r = t;
+        const int tx = r % p.tiles_x; r /= p.tiles_x;
+        const int ty = r % p.tiles_y; r /= p.tiles_y;
+        const int cb = r % p.cblocks; const int b = r / p.cblocks;
+        uint8_t *dst = dsm + (size_t)stage * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full[stage], (uint32_t)(Cfg::IN_BYTES + Cfg::W_BYTES));
+        tma_load_4d(dst, &p.x_map, &full[stage], cb * CB, tx * TW * S - p.pad_l, ty * TH * S - p.pad_t, b);
+        tma_load_2d(dst + Cfg::IN_PAD, &p.w_map, &full[stage], cb * CB, 0);
+    };
+
+    const int pair = tid % CP, slot = tid / CP;        // slot 0..7: which register tile of a pass
+
+    if (tid == 0 && (int)blockIdx.x < p.total_tiles) issue(blockIdx.x, 0);
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const int stage = it & 1;
+        if (tid == 0 && t + (int)gridDim.x < p.total_tiles) issue(t + gridDim.x, stage ^ 1);
+        int r = t;
+        const int tx = r % p.tiles_x; r /= p.tiles_x;
+        const int ty = r % p.tiles_y; r /= p.tiles_y;
+        const int cb = r % p.cblocks; const int b = r / p.cblocks;
+        const int c = cb * CB + pair * 2;
+        const bool c_ok = c < p.C;
+        // per-channel epilogue constants (swish: the 1/2 of z/2 * (1 + tanh(z/2)) is folded in)
+        float2 sc = make_float2(0.f, 0.f), sh = make_float2(0.f, 0.f);
+        if (c_ok) {
+            const float pre = ACT == EFFDET_ACT_SWISH ? 0.5f : 1.f;
+            sc = *reinterpret_cast<const float2 *>(p.scale + c);
+            sh = *reinterpret_cast<const float2 *>(p.shift + c);
+            sc.x *= pre; sc.y *= pre; sh.x *= pre; sh.y *= pre;
+        }
+        const uint8_t *sIn = dsm + (size_t)stage * Cfg::STAGE_BYTES;
+        const float *sW = reinterpret_cast<const float *>(sIn + Cfg::IN_PAD);
+        mbar_wait(&full[stage], (it >> 1) & 1);
+
+        float2 wk[K * K];
+#pragma unroll
+        for (int i = 0; i < K * K; ++i) wk[i] = *reinterpret_cast<const float2 *>(sW + i * CB + pair * 2);
+
+        float2 tot = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int pass = 0; pass < Cfg::PASSES; ++pass) {
+            const int rt = pass * 8 + slot;
+            const int ry = (rt / (TW / kRtW)) * kRtH, rx = (rt % (TW / kRtW)) * kRtW;   // output origin in the tile
+            float2 acc[kRtH][kRtW];
+#pragma unroll
+            for (int i = 0; i < kRtH; ++i)
+#pragma unroll
+                for (int j = 0; j < kRtW; ++j) acc[i][j] = make_float2(0.f, 0.f);
+            const uint8_t *base = sIn + ((size_t)((ry * S) * IW + rx * S) * CB + pair * 2) * 2;
+#pragma unroll
+            for (int rr = 0; rr < IR; ++rr) {
+                float2 in[NIN];
+#pragma unroll
+                for (int j = 0; j < NIN; ++j) {
+                    const uint32_t w2 = *reinterpret_cast<const uint32_t *>(base + (size_t)(rr * IW + j) * CB * 2);
+                    in[j] = make_float2(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u));
+                }
+#pragma unroll
+                for (int orow = 0; orow < kRtH; ++orow) {
+                    const int ky = rr - orow * S;
+                    if (ky < 0 || ky >= K) continue;
+#pragma unroll
+                    for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                        for (int oc = 0; oc < kRtW; ++oc)
+                            acc[orow][oc] = __ffma2_rn(in[oc * S + kx], wk[ky * K + kx], acc[orow][oc]);
+                }
+            }
+            if (c_ok) {
+#pragma unroll
+                for (int orow = 0; orow < kRtH; ++orow) {
+                    const int oy = ty * TH + ry + orow;
+                    if (oy >= p.Ho) continue;
+                    __nv_bfloat16 *yrow = p.y + (((size_t)b * p.Ho + oy) * p.Wo) * p.C + c;
+#pragma unroll
+                    for (int oc = 0; oc < kRtW; ++oc) {
+                        const int ox = tx * TW + rx + oc;
+                        if (ox < p.Wo) {
+                            float2 z = __ffma2_rn(acc[orow][oc], sc, sh);
+                            if (ACT == EFFDET_ACT_SWISH) {
+                                z.x = fmaf(z.x, tanh_approx_f(z.x), z.x);
+                                z.y = fmaf(z.y, tanh_approx_f(z.y), z.y);
+                            } else if (ACT == EFFDET_ACT_RELU) {
+                                z.x = fmaxf(z.x, 0.f); z.y = fmaxf(z.y, 0.f);
+                            }
+                            tot.x += z.x; tot.y += z.y;
+                            *reinterpret_cast<__nv_bfloat162 *>(yrow + (size_t)ox * p.C) = __floats2bfloat162_rn(z.x, z.y);
+                        }
+                    }
+                }
+            }
+        }
+        if (p.se_sum) {
+            float *red = sRed + (size_t)(it & 1) * 8 * CB;
+            *reinterpret_cast<float2 *>(red + slot * CB + pair * 2) = tot;
+            __syncthreads();
+            if (tid < CB && cb * CB + tid < p.C) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s += red[w * CB + tid];
+                p.se_sum[((size_t)b * p.tiles_x * p.tiles_y + (size_t)ty * p.tiles_x + tx) * p.C + cb * CB + tid] = s;
+            }
+        } else {
+            __syncthreads();        // everyone is done reading this stage before it is refilled
+        }
+    }
+}
+
+template <int K, int S, int CP>
+static int launch_dw_tma(const void *x, const float *w, const float *scale, const float *shift, void *y,
+                         float *se_sum, int B, int H, int W, int C, int act, cudaStream_t st) {
+    using Cfg = DwCfg<K, S, CP>;
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return fail(EFFDET_E_CUDA, "effdet_dwconv: cuTensorMapEncodeTiled unavailable%s", "");
+    DwTmaParams p;
+    memset(&p, 0, sizeof(p));
+    const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S;
+    p.Ho = Ho; p.Wo = Wo; p.C = C;
+    p.pad_t = max((Ho - 1) * S + K - H, 0) / 2;
+    p.pad_l = max((Wo - 1) * S + K - W, 0) / 2;
+    p.tiles_x = (Wo + Cfg::TW - 1) / Cfg::TW; p.tiles_y = (Ho + Cfg::TH - 1) / Cfg::TH;
+    p.cblocks = (C + Cfg::CB - 1) / Cfg::CB;
+    p.total_tiles = p.tiles_x * p.tiles_y * p.cblocks * B;
+    p.scale = scale; p.shift = shift; p.y = static_cast<__nv_bfloat16 *>(y); p.se_sum = se_sum;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+        cuuint32_t box[4] = {(cuuint32_t)Cfg::CB, (cuuint32_t)Cfg::IW, (cuuint32_t)Cfg::IH, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = encode(&p.x_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(x), dims, strides, box,
+                            es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_dwconv: cuTensorMapEncodeTiled(x) failed %s(%lld)", "", (long long)r);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)(K * K)};
+        cuuint64_t strides[1] = {(cuuint64_t)C * 4};
+        cuuint32_t box[2] = {(cuuint32_t)Cfg::CB, (cuuint32_t)(K * K)};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = encode(&p.w_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(w), dims, strides, box,
+                            es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_dwconv: cuTensorMapEncodeTiled(w) failed %s(%lld)", "", (long long)r);
+    }
+#define DWT_LAUNCH(A)                                                                                      \
+    {                                                                                                      \
+        auto kern = dwconv_tma_kernel<K, S, CP, A>;                                                        \
+        static int per_sm = 0;                                                                             \
+        if (!per_sm) {                                                                                     \
+            EFFDET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM)); \
+            int nb = 0;                                                                                    \
+            EFFDET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::NT, Cfg::SMEM));     \
+            per_sm = nb < 1 ? 1 : nb;                                                                      \
+        }                                                                                                  \
+        int grid = kNumSMs * per_sm;                                                                       \
+        if (grid > p.total_tiles) grid = p.total_tiles;                                                    \
+        kern<<<grid, Cfg::NT, Cfg::SMEM, st>>>(p);                                                         \
+    }
+    if (act == EFFDET_ACT_SWISH) DWT_LAUNCH(EFFDET_ACT_SWISH)
+    else if (act == EFFDET_ACT_RELU) DWT_LAUNCH(EFFDET_ACT_RELU)
+    else if (act == EFFDET_ACT_NONE) DWT_LAUNCH(EFFDET_ACT_NONE)
+    else return fail(EFFDET_E_UNSUPPORTED, "effdet_dwconv: unsupported activation%s", "");
+#undef DWT_LAUNCH
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+// channel pairs per block: the largest of 32 / 24 / 16 (64 / 48 / 32 channels) that divides C,
+// else the one wasting the fewest lanes
+static int pick_cp(int C) {
+    const int cand[3] = {32, 24, 16};
+    for (int cp : cand) if (C % (2 * cp) == 0) return cp;
+    int best = 32; long waste = -1;
+    for (int cp : cand) {
+        const long w = (long)((C + 2 * cp - 1) / (2 * cp)) * 2 * cp - C;
+        if (waste < 0 || w < waste) { waste = w; best = cp; }
+    }
+    return best;
+}
+
+// SE partials: one per output tile (8 x 16 for stride 1, 8 x 8 for stride 2)
+int dwconv_bf16_tma_se_blocks(int H, int W, int stride) {
+    const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    const int tw = stride == 1 ? 16 : 8;
+    return ((Wo + tw - 1) / tw) * ((Ho + 7) / 8);
+}
+
+// bf16 entry used by effdet_dwconv (dwconv.cu)
+int dwconv_bf16_tma(const void *x, const float *w, const float *scale, const float *shift, void *y, float *se_sum,
+                    int B, int H, int W, int C, int k, int stride, int act, cudaStream_t st) {
+    const int cp = pick_cp(C);
+#define DWT_CASE(K_, S_)                                                                                   \
+    if (k == K_ && stride == S_) {                                                                         \
+        if (cp == 32) return launch_dw_tma<K_, S_, 32>(x, w, scale, shift, y, se_sum, B, H, W, C, act, st); \
+        if (cp == 24) return launch_dw_tma<K_, S_, 24>(x, w, scale, shift, y, se_sum, B, H, W, C, act, st); \
+        return launch_dw_tma<K_, S_, 16>(x, w, scale, shift, y, se_sum, B, H, W, C, act, st);              \
+    }
+    DWT_CASE(3, 1) DWT_CASE(5, 1) DWT_CASE(3, 2) DWT_CASE(5, 2)
+#undef DWT_CASE
+    return fail(EFFDET_E_INVALID, "effdet_dwconv: bad kernel / stride%s", "");
+}
+
+}  // namespace effdet
