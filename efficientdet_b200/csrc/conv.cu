@@ -66,6 +66,97 @@ stem_conv_kernel(const float *__restrict__ img, const float *__restrict__ w,
     for (int c = 0; c < C0; ++c) o[c] = from_f<TO>(activate<EFFDET_ACT_SWISH>(acc[c] * ss[c] + sb[c]));
 }
 
+
+// bf16-output stem, tiled: one block = 4 x 32 output pixels of one image.  The fp32 RGB patch
+// (9 x 65 pixels) is staged with coalesced row copies, the 27 x C0 weights sit next to it; a thread
+// owns 8 output channels x a strip of 4 horizontally adjacent pixels (weights read once per tap
+// and reused over the strip, packed FFMA2 math), and writes 16-byte bf16 vectors: the warp's
+// stores are whole 64-byte pixel rows.  HBM-bound: 12 B in + 2*C0 B out per output pixel.
+constexpr int kStemTW = 32, kStemTH = 4, kStemStrip = 4;
+constexpr int kStemIW = 2 * kStemTW + 1, kStemIH = 2 * kStemTH + 1;
+
+template <int C0, int ACT>
+__global__ void __launch_bounds__((C0 / 8) * (kStemTW / kStemStrip) * kStemTH)
+stem_conv_tiled_kernel(const float *__restrict__ img, const float *__restrict__ w,
+                       const float *__restrict__ scale, const float *__restrict__ shift,
+                       __nv_bfloat16 *__restrict__ out, int H, int W, int Ho, int Wo, int pad_t, int pad_l,
+                       int tiles_x) {
+    constexpr int NO = C0 / 8;
+    constexpr int NT = NO * (kStemTW / kStemStrip) * kStemTH;
+    constexpr int ROW = kStemIW * 3;
+    __shared__ __align__(16) float sw[27 * C0];
+    __shared__ float sin_[kStemIH * ROW];
+    const int b = blockIdx.y;
+    const int ty0 = (blockIdx.x / tiles_x) * kStemTH, tx0 = (blockIdx.x % tiles_x) * kStemTW;
+    const int iy0 = ty0 * 2 - pad_t, ix0 = tx0 * 2 - pad_l;
+    for (int i = threadIdx.x; i < 27 * C0 / 4; i += NT)
+        reinterpret_cast<float4 *>(sw)[i] = reinterpret_cast<const float4 *>(w)[i];
+    const float *ib = img + (size_t)b * H * W * 3;
+    for (int i = threadIdx.x; i < kStemIH * ROW; i += NT) {
+        const int r = i / ROW, cidx = i - r * ROW;
+        const int gy = iy0 + r, g3 = ix0 * 3 + cidx;
+        sin_[i] = (gy >= 0 && gy < H && g3 >= 0 && g3 < W * 3) ? ib[(size_t)gy * W * 3 + g3] : 0.f;
+    }
+    __syncthreads();
+    const int oct = threadIdx.x % NO, strip = threadIdx.x / NO;
+    const int sy = strip / (kStemTW / kStemStrip), sx = (strip % (kStemTW / kStemStrip)) * kStemStrip;
+    float2 acc[kStemStrip][4];
+#pragma unroll
+    for (int o = 0; o < kStemStrip; ++o)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[o][k] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const float *rowp = sin_ + (sy * 2 + ky) * ROW + sx * 2 * 3;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                const float *wp = sw + ((ky * 3 + kx) * 3 + ci) * C0 + oct * 8;
+                const float4 wa = *reinterpret_cast<const float4 *>(wp);
+                const float4 wb = *reinterpret_cast<const float4 *>(wp + 4);
+                const float2 wk[4] = {make_float2(wa.x, wa.y), make_float2(wa.z, wa.w), make_float2(wb.x, wb.y),
+                                      make_float2(wb.z, wb.w)};
+#pragma unroll
+                for (int o = 0; o < kStemStrip; ++o) {
+                    const float v = rowp[(o * 2 + kx) * 3 + ci];
+                    const float2 vv = make_float2(v, v);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[o][k] = __ffma2_rn(vv, wk[k], acc[o][k]);
+                }
+            }
+    }
+    const int oy = ty0 + sy;
+    if (oy >= Ho) return;
+    const float pre = ACT == EFFDET_ACT_SWISH ? 0.5f : 1.f;
+    float2 sc[4], sh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        sc[k] = *reinterpret_cast<const float2 *>(scale + oct * 8 + 2 * k);
+        sh[k] = *reinterpret_cast<const float2 *>(shift + oct * 8 + 2 * k);
+        sc[k].x *= pre; sc[k].y *= pre; sh[k].x *= pre; sh[k].y *= pre;
+    }
+#pragma unroll
+    for (int o = 0; o < kStemStrip; ++o) {
+        const int ox = tx0 + sx + o;
+        if (ox >= Wo) continue;
+        uint4 ov;
+        __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&ov);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float2 z = __ffma2_rn(acc[o][k], sc[k], sh[k]);
+            if (ACT == EFFDET_ACT_SWISH) {
+                float tx, ty;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(tx) : "f"(z.x));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(ty) : "f"(z.y));
+                z.x = fmaf(z.x, tx, z.x); z.y = fmaf(z.y, ty, z.y);
+            }
+            oh[k] = __floats2bfloat162_rn(z.x, z.y);
+        }
+        *reinterpret_cast<uint4 *>(out + (((size_t)b * Ho + oy) * Wo + ox) * C0 + oct * 8) = ov;
+    }
+}
+
 // ------------------------------------------------------------------ implicit GEMM
 constexpr int kMaxGroups = 5;
 struct ConvGroup {
@@ -259,6 +350,27 @@ static int launch_stem(const float *img, const float *w, const float *scale, con
     return EFFDET_OK;
 }
 
+static int launch_stem_bf16(const float *img, const float *w, const float *scale, const float *shift,
+                            void *out, int B, int H, int W, int C0, cudaStream_t st) {
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    const int pad_t = ((Ho - 1) * 2 + 3 - H > 0 ? (Ho - 1) * 2 + 3 - H : 0) / 2;
+    const int pad_l = ((Wo - 1) * 2 + 3 - W > 0 ? (Wo - 1) * 2 + 3 - W : 0) / 2;
+    const int tx = (Wo + kStemTW - 1) / kStemTW, ty = (Ho + kStemTH - 1) / kStemTH;
+    dim3 grid(tx * ty, B);
+#define STEM_T(C)                                                                                          \
+    case C:                                                                                                \
+        stem_conv_tiled_kernel<C, EFFDET_ACT_SWISH><<<grid, (C / 8) * (kStemTW / kStemStrip) * kStemTH, 0, st>>>( \
+            img, w, scale, shift, static_cast<__nv_bfloat16 *>(out), H, W, Ho, Wo, pad_t, pad_l, tx);      \
+        break;
+    switch (C0) {
+        STEM_T(32) STEM_T(40) STEM_T(48) STEM_T(56) STEM_T(64)
+        default: return launch_stem<__nv_bfloat16>(img, w, scale, shift, out, B, H, W, C0, st);
+    }
+#undef STEM_T
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
 extern "C" int effdet_stem_conv(const float *images, const float *kernel, const float *scale,
                                 const float *shift, void *out, int B, int H, int W, int C0,
                                 int out_dtype, void *stream) {
@@ -267,8 +379,7 @@ extern "C" int effdet_stem_conv(const float *images, const float *kernel, const 
     if (out_dtype == EFFDET_F32)
         return launch_stem<float>(images, kernel, scale, shift, out, B, H, W, C0, as_stream(stream));
     if (out_dtype == EFFDET_BF16)
-        return launch_stem<__nv_bfloat16>(images, kernel, scale, shift, out, B, H, W, C0,
-                                          as_stream(stream));
+        return launch_stem_bf16(images, kernel, scale, shift, out, B, H, W, C0, as_stream(stream));
     return fail(EFFDET_E_INVALID, "effdet_stem_conv: bad dtype%s", "");
 }
 

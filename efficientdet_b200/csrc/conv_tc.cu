@@ -96,6 +96,7 @@ struct alignas(64) TcParams {
     TcGroup g[kTcMaxGroups];
     int n_groups, B, Cout, ksize, kblocks_per_tap, block_n, stages, tmem_cols;
     int act, out_f32, b_per_sample, total_tiles, n_tiles, any_tma_store;
+    int stride, pad_t[kTcMaxGroups], pad_l[kTcMaxGroups];   // stride 2: TMA element strides sample every other pixel
     const float *scale, *shift, *keep;
 };
 
@@ -170,7 +171,6 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         (reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pad = p.ksize / 2;
     const int taps = p.ksize * p.ksize;
     const int num_k = taps * p.kblocks_per_tap;
     const int total = p.total_tiles;
@@ -200,8 +200,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                     const int tap = kb / p.kblocks_per_tap, kc = (kb - tap * p.kblocks_per_tap) * kTileK;
                     const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
                     mbar_expect_tx(&full[s], (uint32_t)(kATileBytes + b_tile_bytes));
-                    tma_load_4d(sA + (size_t)s * kATileBytes, amap, &full[s], kc, c.x0 + kx - pad, c.y0 + ky - pad,
-                                c.b0);
+                    tma_load_4d(sA + (size_t)s * kATileBytes, amap, &full[s], kc, c.x0 * p.stride + kx - p.pad_l[c.gi],
+                                c.y0 * p.stride + ky - p.pad_t[c.gi], c.b0);
                     tma_load_3d(sB + (size_t)s * b_tile_bytes, &p.b_map, &full[s], kc, c.n0,
                                 p.b_per_sample ? c.b0 : tap);
                 }
@@ -420,10 +420,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 __global__ void __launch_bounds__(256)
 weight_panel_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ panel, int taps, int Cin,
                     int Cout, int Kpad, int Npad, int mode, const float *__restrict__ gate, int nb) {
-    const size_t per = (size_t)Npad * Kpad;
-    const size_t total = (size_t)(gate ? nb : taps) * per;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-        const int k = (int)(i % Kpad), n = (int)((i / Kpad) % Npad), z = (int)(i / per);
+    const unsigned per = (unsigned)Npad * Kpad;
+    const unsigned total = (unsigned)(gate ? nb : taps) * per;
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+        const unsigned z = i / per, rem = i - z * per;
+        const int n = (int)(rem / Kpad), k = (int)(rem - (unsigned)n * Kpad);
         float v = 0.f;
         if (mode == 0) {
             if (k < Cin && n < Cout) {
@@ -437,6 +438,32 @@ weight_panel_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ pan
     }
 }
 
+// Per-sample gated panels of a 1x1 convolution: panel[b][n][k] = w[k][n] * gate[b][k].
+// One block transposes a 32(k) x 32(n) tile of w through shared memory once (coalesced reads
+// along n) and streams it out for every sample with k fastest (coalesced 64-byte rows).
+__global__ void __launch_bounds__(256)
+gated_panel_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ panel, int Cin, int Cout,
+                   int Kpad, int Npad, const float *__restrict__ gate, int nb) {
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, n = n0 + tx;
+        tile[r][tx] = (k < Cin && n < Cout) ? w[(size_t)k * Cout + n] : 0.f;
+    }
+    __syncthreads();
+    const int k = k0 + tx;
+    for (int b = blockIdx.z; b < nb; b += gridDim.z) {
+        const float g = k < Cin ? gate[(size_t)b * Cin + k] : 0.f;
+        __nv_bfloat16 *dst = panel + (size_t)b * Npad * Kpad;
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            const int n = n0 + r;
+            if (n < Npad && k < Kpad) dst[(size_t)n * Kpad + k] = __float2bfloat16_rn(tile[tx][r] * g);
+        }
+    }
+}
 
 // ------------------------------------------------------------------ weight gradient on tcgen05
 // dW[tap][ci][co] = sum_pixels X[pix + tap][ci] * dZ[pix][co]
@@ -622,6 +649,15 @@ extern "C" int effdet_conv_weight_panel(const float *w, void *panel, int taps, i
     const int bn = effdet_conv_tc_block_n(N);
     const int Kpad = round_up(K, kTileK), Npad = round_up(N, bn);
     const size_t total = (size_t)(gate ? B : taps) * Npad * Kpad;
+    EFFDET_REQUIRE(total < 0xffffffffull, "panel too large");
+    if (gate) {
+        int zs = B < 8 ? B : 8;             // samples per block column: enough blocks to fill the machine
+        dim3 grid(Kpad / 32, (Npad + 31) / 32, zs);
+        gated_panel_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, static_cast<__nv_bfloat16 *>(panel), Cin, Cout,
+                                                                Kpad, Npad, gate, B);
+        EFFDET_LAUNCHED();
+        return EFFDET_OK;
+    }
     unsigned blocks = cdiv(total, 256);
     if (blocks > (unsigned)kNumSMs * 16) blocks = kNumSMs * 16;
     weight_panel_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, static_cast<__nv_bfloat16 *>(panel), taps, Cin,
@@ -633,7 +669,8 @@ extern "C" int effdet_conv_weight_panel(const float *w, void *panel, int taps, i
 // Called by effdet_conv2d when the descriptor qualifies.  Returns EFFDET_E_UNSUPPORTED (without
 // touching the error string of a real failure) when the shape cannot take this path.
 int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
-    if (!d->weight_bf16 || d->in_dtype != EFFDET_BF16 || d->stride != 1) return EFFDET_E_UNSUPPORTED;
+    if (!d->weight_bf16 || d->in_dtype != EFFDET_BF16 || (d->stride != 1 && d->stride != 2)) return EFFDET_E_UNSUPPORTED;
+    if (d->stride == 2 && (d->relu_mask[0] || d->weight_per_sample)) return EFFDET_E_UNSUPPORTED;
     if (d->Cin % 8 != 0 || d->kh != d->kw) return EFFDET_E_UNSUPPORTED;
     if (d->gate && !d->weight_per_sample) return EFFDET_E_UNSUPPORTED;
     EncodeTiledFn encode = get_encode();
@@ -642,7 +679,7 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     memset(&p, 0, sizeof(p));
     const int bn = effdet_conv_tc_block_n(d->Cout);
     const int Kpad = round_up(d->Cin, kTileK), Npad = round_up(d->Cout, bn);
-    p.n_groups = d->n_groups; p.B = d->B; p.Cout = d->Cout; p.ksize = d->kh;
+    p.n_groups = d->n_groups; p.B = d->B; p.Cout = d->Cout; p.ksize = d->kh; p.stride = d->stride;
     p.kblocks_per_tap = Kpad / kTileK; p.block_n = bn;
     // two accumulators (double-buffered epilogue): 2 x next-pow2(block_n) columns
     p.tmem_cols = 2 * (bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256);
@@ -666,7 +703,11 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     for (int i = 0; i < d->n_groups; ++i) {
         TcGroup &g = p.g[i];
         g.y = d->y[i]; g.res = d->residual[i]; g.mask = d->relu_mask[i];
-        g.H = d->H[i]; g.W = d->W[i];
+        // g.H / g.W are OUTPUT extents; stride 2 reads every other input pixel (TMA element strides)
+        const int Hin = d->H[i], Win = d->W[i], sd = d->stride;
+        g.H = (Hin + sd - 1) / sd; g.W = (Win + sd - 1) / sd;
+        p.pad_t[i] = max((g.H - 1) * sd + d->kh - Hin, 0) / 2;      // TF SAME: before = total / 2
+        p.pad_l[i] = max((g.W - 1) * sd + d->kw - Win, 0) / 2;
         g.ldc = d->ldc[i] ? d->ldc[i] : d->Cout;
         g.y_batch_stride = d->y_batch_stride[i] ? d->y_batch_stride[i] : (long long)g.H * g.W * g.ldc;
         if (d->weight_per_sample) { g.Bt = 1; pick_tile(g.W, g.H, 1, &g.Wt, &g.Ht, &g.Bt); if (g.Bt != 1) { g.Wt = 16; g.Ht = 8; g.Bt = 1; } }
@@ -676,14 +717,16 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
         g.tile_begin = tiles;
         tiles += g.tiles_x * g.tiles_y * g.tiles_b;
         const long long ldx = d->ldx[i] ? d->ldx[i] : d->Cin;
-        const long long xbs = d->x_batch_stride[i] ? d->x_batch_stride[i] : (long long)g.H * g.W * ldx;
+        const long long xbs = d->x_batch_stride[i] ? d->x_batch_stride[i] : (long long)Hin * Win * ldx;
         if ((ldx * 2) % 16 || (xbs * 2) % 16 || (reinterpret_cast<uintptr_t>(d->x[i]) & 15)) return EFFDET_E_UNSUPPORTED;
-        cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)d->B};
-        cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * g.W, (cuuint64_t)xbs * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kTileK, (cuuint32_t)g.Wt, (cuuint32_t)g.Ht, (cuuint32_t)g.Bt};
+        if (g.Wt * sd > 256 || g.Ht * sd > 256) return EFFDET_E_UNSUPPORTED;
+        cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)d->B};
+        cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * Win, (cuuint64_t)xbs * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kTileK, (cuuint32_t)(g.Wt * sd), (cuuint32_t)(g.Ht * sd), (cuuint32_t)g.Bt};
+        cuuint32_t es_in[4] = {1, (cuuint32_t)sd, (cuuint32_t)sd, 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = encode(&p.a_map[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d->x[i]), dims,
-                            strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            strides, box, es_in, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_conv2d: cuTensorMapEncodeTiled(A) failed %s(%lld)", "", (long long)r);
         // coalesced output: the epilogue stages 32-row x 32-column pieces in shared memory and TMA

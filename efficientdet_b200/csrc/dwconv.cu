@@ -284,12 +284,30 @@ se_gate_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_hw,
         }
     }
     __syncthreads();
-    for (int j = warp; j < R; j += 8) {
-        float s = 0.f;
-        for (int c = lane; c < C; c += 32) s = fmaf(mean[c], w1[(size_t)c * R + j], s);
+    // FC1: lanes run along the R outputs (w1 is (C, R) row-major: coalesced), G = 256 / R thread
+    // groups split the C reduction; the G partial sums are added in a fixed order
+    if (R <= 256) {
+        const int G = 256 / R;
+        const int j = tid % R, cg = tid / R;
+        if (cg < G) {
+            float s = 0.f;
+            for (int c = cg; c < C; c += G) s = fmaf(mean[c], w1[(size_t)c * R + j], s);
+            part[cg * R + j] = s;
+        }
+        __syncthreads();
+        if (tid < R) {
+            float s = 0.f;
+            for (int g = 0; g < G; ++g) s += part[g * R + tid];
+            r[tid] = activate<EFFDET_ACT_SWISH>(s + b1[tid]);
+        }
+    } else {
+        for (int j = warp; j < R; j += 8) {
+            float s = 0.f;
+            for (int c = lane; c < C; c += 32) s = fmaf(mean[c], w1[(size_t)c * R + j], s);
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (lane == 0) r[j] = activate<EFFDET_ACT_SWISH>(s + b1[j]);
+            for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+            if (lane == 0) r[j] = activate<EFFDET_ACT_SWISH>(s + b1[j]);
+        }
     }
     __syncthreads();
     for (int c = tid; c < C; c += 256) {

@@ -78,70 +78,109 @@ struct LevelGrads {
     int n_levels, cpad_cls, cpad_reg;
     unsigned N;
 };
-__device__ __forceinline__ void level_store(const LevelGrads &L, bool is_cls, size_t r, int k, int per,
-                                            float v) {
-    const unsigned b = (unsigned)(r / L.N);
-    unsigned n = (unsigned)(r - (size_t)b * L.N);
+// (image, level, cell, anchor) of concatenated row r
+struct LevelPos { int l; size_t cell_index; unsigned a; };
+__device__ __forceinline__ LevelPos level_pos(const LevelGrads &L, unsigned b, unsigned n) {
     int l = 0;
     while (l + 1 < L.n_levels && n >= 9u * (unsigned)L.cells[l]) { n -= 9u * (unsigned)L.cells[l]; ++l; }
-    const unsigned cell = n / 9u, a = n - cell * 9u;
-    const int cpad = is_cls ? L.cpad_cls : L.cpad_reg;
-    __nv_bfloat16 *dst = is_cls ? L.cls[l] : L.reg[l];
-    dst[((size_t)b * L.cells[l] + cell) * cpad + a * per + k] = __float2bfloat16_rn(v);
+    const unsigned cell = n / 9u;
+    LevelPos q;
+    q.l = l; q.a = n - cell * 9u; q.cell_index = (size_t)b * L.cells[l] + cell;
+    return q;
 }
 
+// focal loss of one element + its gradient w.r.t. the logit.  t in {0, 1}:
+//   keras binary_crossentropy (clip -> logit -> sigmoid CE) == -log(pc) | -log(1 - pc), evaluated
+//   with logf / log1pf (the three-transcendental form max(z,0) - z t + log1p(exp(-|z|)) of
+//   utils/tpu.py:135 is the same number); (1-p_t)^gamma by sqrt for the reference's gamma = 1.5.
+template <int GMODE>   // 0: generic gamma, 1: gamma == 1.5, 2: gamma == 2
+__device__ __forceinline__ float focal_elem(float p, bool fg, float mask, float alpha, float gamma,
+                                            float gscale, float &loss_acc) {
+    const float af = fg ? alpha : 1.f - alpha;
+    const float fw = fg ? 1.f - p : p;
+    const float pc = fminf(fmaxf(p, 1e-7f), 1.f - 1e-7f);
+    const float bce = fg ? -logf(pc) : -log1pf(-pc);
+    float fwg, dfwg_abs;                       // fw^gamma, gamma * fw^(gamma-1)
+    if (GMODE == 1) { const float sq = sqrtf(fw); fwg = fw * sq; dfwg_abs = 1.5f * sq; }
+    else if (GMODE == 2) { fwg = fw * fw; dfwg_abs = 2.f * fw; }
+    else { fwg = powf(fw, gamma); dfwg_abs = fw > 0.f ? gamma * powf(fw, gamma - 1.f) : 0.f; }
+    loss_acc += af * fwg * bce * mask;
+    const float dfwg = fg ? -dfwg_abs : dfwg_abs;
+    const bool in_range = p > 1e-7f && p < 1.f - 1e-7f;
+    // d/dlogit = dL/dp * p (1-p);  dbce/dp * p (1-p) = (p - t) inside the clip range, 0 outside
+    const float t = fg ? 1.f : 0.f;
+    const float g = af * (dfwg * bce * p * (1.f - p) + (in_range ? fwg * (p - t) : 0.f));
+    return g * mask * gscale;
+}
+
+template <int VEC, int GMODE>
 __global__ void __launch_bounds__(256)
 focal_kernel(const float *__restrict__ p_, const float *__restrict__ labels_t,
-             const int8_t *__restrict__ state, const int32_t *__restrict__ cls, size_t rows, int C,
+             const int8_t *__restrict__ state, const int32_t *__restrict__ cls, unsigned rows, int C,
              float alpha, float gamma, float grad_scale, const float *__restrict__ norm,
              float *__restrict__ dlogit, float *__restrict__ partial, const LevelGrads L) {
     __shared__ float sh[8];
-    const float inv_norm = norm[5];
-    const size_t total = rows * (size_t)C;
+    const float gscale = norm[5] * grad_scale;
+    const unsigned vpr = (unsigned)C / VEC;                // vectors per row
+    const unsigned total = rows * vpr;
     float acc = 0.f;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
-        const size_t r = i / C;
-        const int c = (int)(i - r * C);
-        float t, st;
+    for (unsigned v = blockIdx.x * 256u + threadIdx.x; v < total; v += gridDim.x * 256u) {
+        const unsigned r = v / vpr;
+        const int c0 = (int)(v - r * vpr) * VEC;
+        float p[VEC], t[VEC], st;
+        const float *src = p_ + (size_t)r * C + c0;
+        if (VEC == 4) { const float4 q = *reinterpret_cast<const float4 *>(src); p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w; }
+        else if (VEC == 2) { const float2 q = *reinterpret_cast<const float2 *>(src); p[0] = q.x; p[1] = q.y; }
+        else p[0] = src[0];
         if (labels_t) {
-            t = labels_t[r * (size_t)(C + 1) + c];
-            st = labels_t[r * (size_t)(C + 1) + C];
+            const float *lt = labels_t + (size_t)r * (C + 1);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) t[k] = lt[c0 + k];
+            st = lt[C];
         } else {
-            t = (cls[r] == c) ? 1.f : 0.f;
+            const int cl = cls[r];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) t[k] = (cl == c0 + k) ? 1.f : 0.f;
             st = (float)state[r];
         }
-        const float p = p_[i];
-        const bool fg = t == 1.f;
-        const float af = fg ? alpha : 1.f - alpha;
-        const float fw = fg ? 1.f - p : p;
-        const float pc = fminf(fmaxf(p, 1e-7f), 1.f - 1e-7f);
-        const float z = logf(pc / (1.f - pc));
-        const float bce = fmaxf(z, 0.f) - z * t + log1pf(expf(-fabsf(z)));
-        const float fwg = powf(fw, gamma);
         const float mask = st != -1.f ? 1.f : 0.f;
-        acc += af * fwg * bce * mask;
-        const float dbce = (p > 1e-7f && p < 1.f - 1e-7f) ? (pc - t) / (pc * (1.f - pc)) : 0.f;
-        const float dfw = fg ? -1.f : 1.f;
-        const float dfwg = fw > 0.f ? gamma * powf(fw, gamma - 1.f) * dfw : 0.f;
-        const float dLdp = af * (dfwg * bce + fwg * dbce);
-        const float gout = dLdp * p * (1.f - p) * mask * inv_norm * grad_scale;
-        dlogit[i] = gout;
-        if (L.n_levels) level_store(L, true, r, c, C, gout);
+        float g[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) g[k] = focal_elem<GMODE>(p[k], t[k] == 1.f, mask, alpha, gamma, gscale, acc);
+        float *dst = dlogit + (size_t)r * C + c0;
+        if (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(g[0], g[1], g[2], g[3]);
+        else if (VEC == 2) *reinterpret_cast<float2 *>(dst) = make_float2(g[0], g[1]);
+        else dst[0] = g[0];
+        if (L.n_levels) {
+            const unsigned b = r / L.N;
+            const LevelPos q = level_pos(L, b, r - b * L.N);
+            __nv_bfloat16 *o = L.cls[q.l] + q.cell_index * L.cpad_cls + q.a * C + c0;
+            if (VEC == 4) {
+                uint2 pk;
+                *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(g[0], g[1]);
+                *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(g[2], g[3]);
+                *reinterpret_cast<uint2 *>(o) = pk;
+            } else if (VEC == 2) {
+                *reinterpret_cast<__nv_bfloat162 *>(o) = __floats2bfloat162_rn(g[0], g[1]);
+            } else {
+                o[0] = __float2bfloat16_rn(g[0]);
+            }
+        }
     }
     float t = block_sum_256(acc, sh);
     if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 
 __global__ void __launch_bounds__(256)
-smooth_l1_kernel(const float *__restrict__ pred, const float *__restrict__ reg_t, size_t rows,
+smooth_l1_kernel(const float *__restrict__ pred, const float *__restrict__ reg_t, unsigned rows,
                  float delta, float grad_scale, const float *__restrict__ norm,
                  float *__restrict__ dreg, float *__restrict__ partial, const LevelGrads L) {
     __shared__ float sh[8];
     const float inv_norm = norm[4];
     float acc = 0.f;
-    for (size_t r = (size_t)blockIdx.x * 256 + threadIdx.x; r < rows; r += (size_t)gridDim.x * 256) {
-        const float4 pr = *reinterpret_cast<const float4 *>(pred + r * 4);
-        const float *tg = reg_t + r * 5;
+    for (unsigned r = blockIdx.x * 256u + threadIdx.x; r < rows; r += gridDim.x * 256u) {
+        const float4 pr = *reinterpret_cast<const float4 *>(pred + (size_t)r * 4);
+        const float *tg = reg_t + (size_t)r * 5;
         const bool fg = tg[4] == 1.f;
         const float pv[4] = {pr.x, pr.y, pr.z, pr.w};
         float g[4];
@@ -153,24 +192,34 @@ smooth_l1_kernel(const float *__restrict__ pred, const float *__restrict__ reg_t
             acc += fg ? l : 0.f;
             g[k] = fg ? gd * inv_norm * grad_scale : 0.f;
         }
-        *reinterpret_cast<float4 *>(dreg + r * 4) = make_float4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<float4 *>(dreg + (size_t)r * 4) = make_float4(g[0], g[1], g[2], g[3]);
         if (L.n_levels) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) level_store(L, false, r, k, 4, g[k]);
+            const unsigned b = r / L.N;
+            const LevelPos q = level_pos(L, b, r - b * L.N);
+            uint2 pk;
+            *reinterpret_cast<__nv_bfloat162 *>(&pk.x) = __floats2bfloat162_rn(g[0], g[1]);
+            *reinterpret_cast<__nv_bfloat162 *>(&pk.y) = __floats2bfloat162_rn(g[2], g[3]);
+            *reinterpret_cast<uint2 *>(L.reg[q.l] + q.cell_index * L.cpad_reg + q.a * 4) = pk;
         }
     }
     float t = block_sum_256(acc, sh);
     if (threadIdx.x == 0) partial[blockIdx.x] = t;
 }
 
-__global__ void finalize_losses_kernel(const float *__restrict__ pf, int nf, const float *__restrict__ ps,
-                                       int ns, float *__restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        float a = 0.f, b = 0.f;
-        for (int i = 0; i < nf; ++i) a += pf[i];
-        for (int i = 0; i < ns; ++i) b += ps[i];
-        out[0] = a * out[5];     // focal
-        out[1] = b * out[4];     // smooth L1
+// fixed-order parallel sums of the per-block partials (deterministic)
+__global__ void __launch_bounds__(256)
+finalize_losses_kernel(const float *__restrict__ pf, int nf, const float *__restrict__ ps,
+                       int ns, float *__restrict__ out) {
+    __shared__ float sh[8];
+    float a = 0.f, b = 0.f;
+    for (int i = threadIdx.x; i < nf; i += 256) a += pf[i];
+    for (int i = threadIdx.x; i < ns; i += 256) b += ps[i];
+    const float ta = block_sum_256(a, sh);
+    __syncthreads();
+    const float tb = block_sum_256(b, sh);
+    if (threadIdx.x == 0) {
+        out[0] = ta * out[5];     // focal
+        out[1] = tb * out[4];     // smooth L1
     }
 }
 
@@ -223,15 +272,26 @@ extern "C" int effdet_detection_losses(const float *classification, const float 
     EFFDET_LAUNCHED();
     count_pos_finalize_kernel<<<1, 256, 0, st>>>(cnt, nc, out8);
     EFFDET_LAUNCHED();
-    int nf = (int)cdiv(rows * C, 256 * 8); if (nf > kLossBlocks) nf = kLossBlocks; if (nf < 1) nf = 1;
-    focal_kernel<<<nf, 256, 0, st>>>(classification, labels_t, state, cls, rows, C, alpha, gamma,
-                                     grad_scale, out8, dcls_logits, pf, L);
+    EFFDET_REQUIRE(rows * (size_t)C < 0xffffffffull, "B*N*C must fit 32 bits");
+    const bool al = (reinterpret_cast<uintptr_t>(classification) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(dcls_logits) & 15) == 0 && (n_levels == 0 || cpad_cls % 4 == 0);
+    const int vec = (C % 4 == 0 && al) ? 4 : (C % 2 == 0 && al) ? 2 : 1;
+    const int gmode = gamma == 1.5f ? 1 : gamma == 2.f ? 2 : 0;
+    int nf = (int)cdiv(rows * C / vec, 256 * 4); if (nf > kLossBlocks) nf = kLossBlocks; if (nf < 1) nf = 1;
+#define FOCAL(V, G)                                                                                      \
+    focal_kernel<V, G><<<nf, 256, 0, st>>>(classification, labels_t, state, cls, (unsigned)rows, C, alpha, gamma, \
+                                           grad_scale, out8, dcls_logits, pf, L)
+#define FOCAL_G(V)                                                                                       \
+    do { if (gmode == 1) FOCAL(V, 1); else if (gmode == 2) FOCAL(V, 2); else FOCAL(V, 0); } while (0)
+    if (vec == 4) FOCAL_G(4); else if (vec == 2) FOCAL_G(2); else FOCAL_G(1);
+#undef FOCAL_G
+#undef FOCAL
     EFFDET_LAUNCHED();
     int ns = (int)cdiv(rows, 256 * 4); if (ns > kLossBlocks) ns = kLossBlocks; if (ns < 1) ns = 1;
-    smooth_l1_kernel<<<ns, 256, 0, st>>>(regression, regression_t, rows, delta, grad_scale, out8,
+    smooth_l1_kernel<<<ns, 256, 0, st>>>(regression, regression_t, (unsigned)rows, delta, grad_scale, out8,
                                          dreg, ps, L);
     EFFDET_LAUNCHED();
-    finalize_losses_kernel<<<1, 32, 0, st>>>(pf, nf, ps, ns, out8);
+    finalize_losses_kernel<<<1, 256, 0, st>>>(pf, nf, ps, ns, out8);
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }

@@ -117,8 +117,10 @@ class Plan:
         wt = self.w(weight_key)
         in_dt = self.dtype if in_dtype is None else in_dtype
         out_dt = self.dtype if out_dtype is None else out_dtype
-        # tcgen05 path: bf16 activations, stride 1, channel count a multiple of 8 (TMA strides)
-        use_tc = (self.net.use_tensor_cores and in_dt == BF16 and stride == 1 and cin % 8 == 0)
+        # tcgen05 path: bf16 activations, channel count a multiple of 8 (TMA strides); stride 2
+        # (BiFPN P6/P7 laterals) samples every other pixel through the tensor map's element strides
+        use_tc = (self.net.use_tensor_cores and in_dt == BF16 and cin % 8 == 0 and
+                  (stride == 1 or (stride == 2 and gate is None)))
         panel = gate_panel = None
         if use_tc and gate is not None:
             lib = _lib.load()

@@ -96,6 +96,39 @@ def test_conv1x1_tc(cin, cout, H, B, act):
     assert rel_err(y.float().cpu().numpy(), want) < 6e-3
 
 
+@pytest.mark.parametrize("cin,cout,H,B,k", [(320, 64, 16, 3, 3), (64, 64, 8, 2, 3), (64, 64, 9, 2, 3), (40, 48, 14, 2, 1)])
+def test_conv_stride2_tc(cin, cout, H, B, k):
+    """BiFPN P6/P7 laterals (model.py:205-211): stride 2, TF SAME padding (asymmetric on even inputs),
+    sampled through the input tensor map's element strides."""
+    from efficientdet_b200 import _lib
+    from oracle import graph
+    rng = np.random.default_rng(cin + H)
+    x = rng.standard_normal((B, H, H, cin)).astype(np.float32)
+    w = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(k * k * cin)).astype(np.float32)
+    sc = rng.uniform(0.5, 1.5, cout).astype(np.float32); sh = rng.normal(0, 0.2, cout).astype(np.float32)
+    xd = _d(x, torch.bfloat16)
+    Ho = (H + 1) // 2
+    y = torch.full((B, Ho, Ho, cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    d = _lib.ConvDesc()
+    d.n_groups = 1
+    d.x[0], d.y[0] = xd.data_ptr(), y.data_ptr()
+    d.H[0] = d.W[0] = H
+    d.B, d.Cin, d.Cout, d.kh, d.kw, d.stride = B, cin, cout, k, k, 2
+    scd, shd = _d(sc), _d(sh)
+    d.scale, d.shift = scd.data_ptr(), shd.data_ptr()
+    d.act, d.in_dtype, d.out_dtype = 1, _lib.BF16, _lib.BF16
+    panel = _panel(w, 0)
+    d.weight_bf16, d.allow_tensor_core = panel.data_ptr(), 1
+    n0 = _lib.launch_count()
+    _lib.call("effdet_conv2d", ctypes.byref(d), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == n0 + 1
+    ref = graph.conv2d(xd.float().cpu().double().permute(0, 3, 1, 2), _bf(w).astype(np.float64), 2)
+    ref = torch.relu(ref * torch.from_numpy(sc).double().view(1, -1, 1, 1) +
+                     torch.from_numpy(sh).double().view(1, -1, 1, 1)).permute(0, 2, 3, 1).numpy()
+    assert rel_err(y.float().cpu().numpy(), ref) < 6e-3
+
+
 def test_conv1x1_tc_per_sample_gate():
     from efficientdet_b200 import _lib
     rng = np.random.default_rng(9)
