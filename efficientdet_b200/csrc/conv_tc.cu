@@ -96,6 +96,8 @@ struct alignas(64) TcParams {
     TcGroup g[kTcMaxGroups];
     int n_groups, B, Cout, ksize, kblocks_per_tap, block_n, stages, tmem_cols;
     int act, out_f32, b_per_sample, total_tiles, n_tiles, any_tma_store;
+    int acc_bufs;        // TMEM accumulators per CTA: 2 (epilogue of tile i overlaps the MMAs of i+1) or 1
+    int b_resident;      // all K blocks of the (single) weight tile stay in shared memory for the CTA's lifetime
     int stride, pad_t[kTcMaxGroups], pad_l[kTcMaxGroups];   // stride 2: TMA element strides sample every other pixel
     const float *scale, *shift, *keep;
 };
@@ -105,21 +107,47 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 
 struct TileCoord { int gi, x0, y0, b0, n0; };
-__device__ __forceinline__ TileCoord decode_tile(const TcParams &p, int t) {
-    TileCoord c;
-    const int m = t / p.n_tiles;
-    c.n0 = (t - m * p.n_tiles) * p.block_n;
-    int gi = 0;
-#pragma unroll
-    for (int i = 1; i < kTcMaxGroups; ++i)
-        if (i < p.n_groups && m >= p.g[i].tile_begin) gi = i;
-    const TcGroup &G = p.g[gi];
-    int r = m - G.tile_begin;
-    const int tx = r % G.tiles_x; r /= G.tiles_x;
-    const int ty = r % G.tiles_y; r /= G.tiles_y;
-    c.gi = gi; c.x0 = tx * G.Wt; c.y0 = ty * G.Ht; c.b0 = r * G.Bt;
-    return c;
+// Each CTA walks a CONTIGUOUS range of tiles; after the one-time decode the coordinates advance
+// by increments (no integer divisions in the per-tile path of the three roles).
+// fp32 pair -> packed bf16x2, round-half-away (differs from RNE only on exact ties).  Three
+// ALU-pipe instructions instead of one F2FP: F2FP shares the 16-lane/clk XU pipe with MUFU.TANH,
+// which is the co-limiter of the swish epilogue (ncu: xu pipe 43 % busy, MUFU only 2/3 of it).
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
 }
+
+struct TileIter {
+    int gi, tx, ty, tb, nt;
+    __device__ __forceinline__ void init(const TcParams &p, int t) {
+        const int m = t / p.n_tiles;
+        nt = t - m * p.n_tiles;
+        gi = 0;
+#pragma unroll
+        for (int i = 1; i < kTcMaxGroups; ++i)
+            if (i < p.n_groups && m >= p.g[i].tile_begin) gi = i;
+        const TcGroup &G = p.g[gi];
+        int r = m - G.tile_begin;
+        tx = r % G.tiles_x; r /= G.tiles_x;
+        ty = r % G.tiles_y; tb = r / G.tiles_y;
+    }
+    __device__ __forceinline__ void next(const TcParams &p) {
+        if (++nt < p.n_tiles) return;
+        nt = 0;
+        const TcGroup &G = p.g[gi];
+        if (++tx < G.tiles_x) return;
+        tx = 0;
+        if (++ty < G.tiles_y) return;
+        ty = 0;
+        if (++tb < G.tiles_b) return;
+        tb = 0; ++gi;
+    }
+    __device__ __forceinline__ TileCoord coord(const TcParams &p) const {
+        const TcGroup &G = p.g[gi];
+        TileCoord c;
+        c.gi = gi; c.x0 = tx * G.Wt; c.y0 = ty * G.Ht; c.b0 = tb * G.Bt; c.n0 = nt * p.block_n;
+        return c;
+    }
+};
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
@@ -154,30 +182,36 @@ template <int ACT, bool OUT_F32>
 __global__ void __launch_bounds__(kTcThreads, 2)      // <= 96 registers: two CTAs (16 epilogue warps) per SM
 conv_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // (pointer arithmetic on the __shared__ array, not through uintptr_t, keeps LDS/STS addressing)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int b_tile_bytes = p.block_n * kTileK * 2;
     uint8_t *sA = smem;
     uint8_t *sB = smem + (size_t)p.stages * kATileBytes;
-    float *sScale = reinterpret_cast<float *>(sB + (size_t)p.stages * b_tile_bytes);   // [256]
+    // ring B tiles, or (b_resident) one slot per K block filled once
+    const int num_k_all = p.ksize * p.ksize * p.kblocks_per_tap;
+    float *sScale = reinterpret_cast<float *>(sB + (size_t)(p.b_resident ? num_k_all : p.stages) * b_tile_bytes);   // [256]
     float *sShift = sScale + 256;                                                          // [256]
     uint64_t *full = reinterpret_cast<uint64_t *>(sShift + 256);
     uint64_t *empty = full + p.stages;
     uint64_t *tmem_full = empty + p.stages;      // [2]
     uint64_t *tmem_empty = tmem_full + 2;        // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    uint64_t *b_full = tmem_empty + 2;           // [1] resident weights landed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_full + 1);
     // epilogue staging (TMA-store path): per warp two [32 rows][32 columns] swizzled buffers
     constexpr int kStageBytes = 32 * 32 * (OUT_F32 ? 4 : 2);
-    uint8_t *sStage = reinterpret_cast<uint8_t *>(
-        (reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sStage = reinterpret_cast<uint8_t *>(tmem_slot + 4);
+    sStage += (1024u - (smem_u32(sStage) & 1023u)) & 1023u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int taps = p.ksize * p.ksize;
     const int num_k = taps * p.kblocks_per_tap;
-    const int total = p.total_tiles;
+    const int t_begin = (int)(((long long)blockIdx.x * p.total_tiles) / gridDim.x);
+    const int t_end = (int)(((long long)(blockIdx.x + 1) * p.total_tiles) / gridDim.x);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], kEpiWarps); }
+        mbar_init(b_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -185,25 +219,35 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t acc_cols = (uint32_t)p.tmem_cols >> 1;
+    const uint32_t acc_cols = (uint32_t)p.tmem_cols / (uint32_t)p.acc_bufs;
+    const int two_acc = p.acc_bufs == 2;
 
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer
             int it = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const TileCoord c = decode_tile(p, t);
+            if (p.b_resident && t_begin < t_end) {
+                mbar_expect_tx(b_full, (uint32_t)(num_k * b_tile_bytes));
+                for (int kb = 0; kb < num_k; ++kb)
+                    tma_load_3d(sB + (size_t)kb * b_tile_bytes, &p.b_map, b_full, (kb % p.kblocks_per_tap) * kTileK, 0,
+                                kb / p.kblocks_per_tap);
+            }
+            TileIter ti_;
+            ti_.init(p, t_begin);
+            for (int t = t_begin; t < t_end; ++t, ti_.next(p)) {
+                const TileCoord c = ti_.coord(p);
                 const CUtensorMap *amap = &p.a_map[c.gi];
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
                     const int s = it % p.stages, ph = (it / p.stages) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_wait_backoff(&empty[s], ph ^ 1, 256);
                     const int tap = kb / p.kblocks_per_tap, kc = (kb - tap * p.kblocks_per_tap) * kTileK;
                     const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-                    mbar_expect_tx(&full[s], (uint32_t)(kATileBytes + b_tile_bytes));
+                    mbar_expect_tx(&full[s], (uint32_t)(kATileBytes + (p.b_resident ? 0 : b_tile_bytes)));
                     tma_load_4d(sA + (size_t)s * kATileBytes, amap, &full[s], kc, c.x0 * p.stride + kx - p.pad_l[c.gi],
                                 c.y0 * p.stride + ky - p.pad_t[c.gi], c.b0);
-                    tma_load_3d(sB + (size_t)s * b_tile_bytes, &p.b_map, &full[s], kc, c.n0,
-                                p.b_per_sample ? c.b0 : tap);
+                    if (!p.b_resident)
+                        tma_load_3d(sB + (size_t)s * b_tile_bytes, &p.b_map, &full[s], kc, c.n0,
+                                    p.b_per_sample ? c.b0 : tap);
                 }
             }
         }
@@ -213,8 +257,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                                    ((uint32_t)(kTileM >> 4) << 24);
             int it = 0, ti = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
-                const int acc = ti & 1, aph = (ti >> 1) & 1;
+            if (p.b_resident && t_begin < t_end) { mbar_wait(b_full, 0); tc_fence_after(); }
+            for (int t = t_begin; t < t_end; ++t, ++ti) {
+                const int acc = two_acc ? (ti & 1) : 0, aph = (two_acc ? (ti >> 1) : ti) & 1;
                 mbar_wait(&tmem_empty[acc], aph ^ 1);        // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
@@ -223,7 +268,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint64_t da = make_kmajor_sw128_desc(smem_u32(sA + (size_t)s * kATileBytes));
-                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + (size_t)s * b_tile_bytes));
+                    const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + (size_t)(p.b_resident ? kb : s) * b_tile_bytes));
 #pragma unroll
                     for (int k = 0; k < kTileK / 16; ++k)      // UMMA_K = 16 bf16 = 32 bytes: +2 in the address field
                         umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
@@ -242,11 +287,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         constexpr bool kHalfIn = (ACT == EFFDET_ACT_SWISH) && !OUT_F32;
         int ti = 0, cur_n0 = -1, sbuf = 0;
         uint8_t *my_stage = sStage + (size_t)ew * 2 * kStageBytes;
-        for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
-            const TileCoord tc = decode_tile(p, t);
+        TileIter tit;
+        tit.init(p, t_begin);
+        for (int t = t_begin; t < t_end; ++t, ++ti, tit.next(p)) {
+            const TileCoord tc = tit.coord(p);
             const TcGroup &G = p.g[tc.gi];
             const int x0 = tc.x0, y0 = tc.y0, b0 = tc.b0, n0 = tc.n0;
-            const int acc = ti & 1, aph = (ti >> 1) & 1;
+            const int acc = two_acc ? (ti & 1) : 0, aph = (two_acc ? (ti >> 1) : ti) & 1;
             if (n0 != cur_n0) {
                 // per-column scale / shift of this N tile -> shared memory (uniform across the CTA)
                 asm volatile("bar.sync 1, 256;" ::: "memory");       // previous tile's readers are done
@@ -257,15 +304,22 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 cur_n0 = n0;
             }
-            const int xx = row & (G.Wt - 1), yy = (row >> G.lw) & (G.Ht - 1), bb = row >> (G.lw + G.lh);
-            const int x = x0 + xx, y = y0 + yy, b = b0 + bb;
-            const bool row_ok = x < G.W && y < G.H && b < p.B;
-            const size_t base = (size_t)b * G.y_batch_stride + ((size_t)y * G.W + x) * G.ldc;
-            const float kp = (p.keep && row_ok) ? p.keep[b] : 1.f;
+            // per-row addressing is only needed for direct stores / residual / mask reads: the TMA
+            // store clips rows outside the tensor by itself
+            const bool tma_out = G.tma_store != 0;
+            bool row_ok = true;
+            size_t base = 0;
+            float kp = 1.f;
+            if (!tma_out || G.res || G.mask) {
+                const int xx = row & (G.Wt - 1), yy = (row >> G.lw) & (G.Ht - 1), bb = row >> (G.lw + G.lh);
+                const int x = x0 + xx, y = y0 + yy, b = b0 + bb;
+                row_ok = x < G.W && y < G.H && b < p.B;
+                base = (size_t)b * G.y_batch_stride + ((size_t)y * G.W + x) * G.ldc;
+                kp = (p.keep && row_ok) ? p.keep[b] : 1.f;
+            }
             // origin of this warp's 32-row box (rows 32q .. 32q+31 of the tile) for the TMA store
             const int r0 = q * 32;
             const int sx = x0 + (r0 & (G.Wt - 1)), sy = y0 + ((r0 >> G.lw) & (G.Ht - 1)), sb = b0 + (r0 >> (G.lw + G.lh));
-            const bool tma_out = G.tma_store != 0;
             mbar_wait(&tmem_full[acc], aph);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(q * 32) << 16);
@@ -372,9 +426,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 #pragma unroll
                         for (int j8 = 0; j8 < 4; ++j8) {
                             uint4 ov;
-                            __nv_bfloat162 *oh = reinterpret_cast<__nv_bfloat162 *>(&ov);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(v[8 * j8 + 2 * j], v[8 * j8 + 2 * j + 1]);
+                            ov.x = pack_bf16x2(v[8 * j8], v[8 * j8 + 1]);
+                            ov.y = pack_bf16x2(v[8 * j8 + 2], v[8 * j8 + 3]);
+                            ov.z = pack_bf16x2(v[8 * j8 + 4], v[8 * j8 + 5]);
+                            ov.w = pack_bf16x2(v[8 * j8 + 6], v[8 * j8 + 7]);
                             *reinterpret_cast<uint4 *>(dst + ((j8 ^ ((lane >> 1) & 3)) << 4)) = ov;
                         }
                         fence_proxy_async();
@@ -628,8 +683,10 @@ using namespace effdet;
 extern "C" int effdet_conv_tc_block_n(int n) {
     // N tile <= 128 columns: two accumulators of <= 128 TMEM columns each leave room for two CTAs
     // (16 epilogue warps) per SM; N is split into equal tiles rounded up to 16.
+    // up to 256 columns: one N tile (the activations are read once); the launcher picks one or two
+    // TMEM accumulators per CTA from the K extent
     const int n16 = round_up(n, 16);
-    if (n16 <= 128) return n16;
+    if (n16 <= 256) return n16;
     // several N tiles: multiples of 32 so that no 32-column epilogue chunk straddles two tiles
     const int tiles = (n16 + 127) / 128;
     return round_up((n16 + tiles - 1) / tiles, 32);
@@ -681,8 +738,14 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     const int Kpad = round_up(d->Cin, kTileK), Npad = round_up(d->Cout, bn);
     p.n_groups = d->n_groups; p.B = d->B; p.Cout = d->Cout; p.ksize = d->kh; p.stride = d->stride;
     p.kblocks_per_tap = Kpad / kTileK; p.block_n = bn;
-    // two accumulators (double-buffered epilogue): 2 x next-pow2(block_n) columns
-    p.tmem_cols = 2 * (bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256);
+    const int num_k = d->kh * d->kw * p.kblocks_per_tap;
+    const int acc_pow2 = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
+    // two accumulators (epilogue of tile i overlaps the MMAs of tile i+1) unless the tile is wide
+    // AND shallow (HBM-bound expand convolutions): then one accumulator and two CTAs per SM
+    p.acc_bufs = (acc_pow2 == 256 && num_k <= 4) ? 1 : 2;
+    p.tmem_cols = p.acc_bufs * acc_pow2;
+    // weights resident in shared memory: single N tile, shared by all samples, <= 48 KiB
+    p.b_resident = (Npad == bn && !d->weight_per_sample && (size_t)num_k * bn * kTileK * 2 <= 48 * 1024) ? 1 : 0;
     p.act = d->act; p.out_f32 = d->out_dtype == EFFDET_F32; p.b_per_sample = d->weight_per_sample ? 1 : 0;
     p.scale = d->scale; p.shift = d->shift; p.keep = d->keep;
     const int b_tile_bytes = bn * kTileK * 2;
@@ -690,14 +753,17 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     // epilogue overlaps the other's main loop
     // small tiles: 2 resident CTAs per SM (<= ~100 KiB each); wide tiles: 1
     const int stage_out_bytes = kEpiWarps * 2 * 32 * 32 * (p.out_f32 ? 4 : 2);
-    int stages = ((bn <= 128 ? 108 : 216) * 1024 - stage_out_bytes) / (kATileBytes + b_tile_bytes);
-    if (stages > 4) stages = 4;
+    const int two_ctas = p.tmem_cols <= 256;
+    const int ring_bytes = kATileBytes + (p.b_resident ? 0 : b_tile_bytes);
+    const int fixed_bytes = stage_out_bytes + (p.b_resident ? num_k * b_tile_bytes : 0) + 6 * 1024;
+    int stages = ((two_ctas ? 113 : 226) * 1024 - fixed_bytes) / ring_bytes;
+    if (stages > (p.b_resident ? 6 : 4)) stages = p.b_resident ? 6 : 4;
     // persistent kernel: the ring runs ahead ACROSS tiles, so its depth does not depend on the
     // number of K blocks of one tile (a 1x1 convolution with Cin <= 64 has a single K block)
     if (stages < 2) stages = 2;
     p.stages = stages;
-    const size_t smem = (size_t)stages * (kATileBytes + b_tile_bytes) + 2048 + (2 * stages + 4) * 8 + 16 + 1024 +
-                        1024 + stage_out_bytes;
+    const size_t smem = (size_t)stages * ring_bytes + (p.b_resident ? (size_t)num_k * b_tile_bytes : 0) + 2048 +
+                        (2 * stages + 5) * 8 + 16 + 1024 + 1024 + stage_out_bytes;
     p.any_tma_store = 0;
     int tiles = 0;
     for (int i = 0; i < d->n_groups; ++i) {

@@ -250,16 +250,60 @@ static int launch_dw_tiled(const void *x, const float *w, const float *scale, co
 }
 
 // ------------------------------------------------------------------ squeeze-excite FCs
-__global__ void __launch_bounds__(256)
+// One block per image.  The two FCs are tiny (C x R, R x C) but every step is a round trip to
+// L2 / HBM, so the kernel is organised to keep many wide loads in flight per thread and few
+// dependent rounds: 16-byte (8-byte when R % 4 != 0) weight loads, 4-8 independent accumulator
+// chains, fixed summation orders (bit-reproducible).
+constexpr int kSeThreads = 512;
+
+template <int VW>
+__device__ __forceinline__ void se_fc1(const float *__restrict__ mean, const float *__restrict__ w1, float *part,
+                                       int C, int R, int tid) {
+    const int JV = R / VW, G = kSeThreads / JV;
+    const int jv = tid % JV, cg = tid / JV;
+    if (cg >= G) return;
+    float s[4][VW];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < VW; ++k) s[u][k] = 0.f;
+    int c = cg;
+    for (; c + 3 * G < C; c += 4 * G) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float m = mean[c + u * G];
+            const float *wp = w1 + (size_t)(c + u * G) * R + jv * VW;
+            if (VW == 4) {
+                const float4 q = *reinterpret_cast<const float4 *>(wp);
+                s[u][0] = fmaf(m, q.x, s[u][0]); s[u][1 % VW] = fmaf(m, q.y, s[u][1 % VW]);
+                s[u][2 % VW] = fmaf(m, q.z, s[u][2 % VW]); s[u][3 % VW] = fmaf(m, q.w, s[u][3 % VW]);
+            } else if (VW == 2) {
+                const float2 q = *reinterpret_cast<const float2 *>(wp);
+                s[u][0] = fmaf(m, q.x, s[u][0]); s[u][1 % VW] = fmaf(m, q.y, s[u][1 % VW]);
+            } else {
+                s[u][0] = fmaf(m, wp[0], s[u][0]);
+            }
+        }
+    }
+    for (int u = 0; c < C; c += G, ++u) {
+        const float m = mean[c];
+#pragma unroll
+        for (int k = 0; k < VW; ++k) s[u][k] = fmaf(m, w1[(size_t)c * R + jv * VW + k], s[u][k]);
+    }
+#pragma unroll
+    for (int k = 0; k < VW; ++k) part[cg * R + jv * VW + k] = (s[0][k] + s[1][k]) + (s[2][k] + s[3][k]);
+}
+
+__global__ void __launch_bounds__(kSeThreads)
 se_gate_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_hw,
                const float *__restrict__ w1, const float *__restrict__ b1,
                const float *__restrict__ w2, const float *__restrict__ b2,
                float *__restrict__ gate, int C, int R) {
-    extern __shared__ float sm[];      // mean[C] | r[R] | part[256]
+    extern __shared__ float sm[];      // mean[C] | r[R] | part[4 * kSeThreads]
     float *mean = sm, *r = sm + C, *part = sm + C + R;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (C >= 256 || se_blocks < 8) {
-        for (int c = tid; c < C; c += 256) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (C >= kSeThreads || se_blocks < 8) {
+        for (int c = tid; c < C; c += kSeThreads) {
             const float *src = se_sum + (size_t)b * se_blocks * C + c;
             float t = 0.f;
             for (int k = 0; k < se_blocks; ++k) t += src[(size_t)k * C];
@@ -268,13 +312,18 @@ se_gate_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_hw,
     } else {
         // few channels, many tile partials (early stages): KS threads per channel each add every
         // KS-th partial, then the KS slices are added in order -- still a fixed summation order
-        const int KS = 256 / C;
+        const int KS = kSeThreads / C;
         const int c = tid % C, slice = tid / C;
         if (slice < KS) {
             const float *src = se_sum + (size_t)b * se_blocks * C + c;
-            float t = 0.f;
-            for (int k = slice; k < se_blocks; k += KS) t += src[(size_t)k * C];
-            part[slice * C + c] = t;
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+            int k = slice;
+            for (; k + 3 * KS < se_blocks; k += 4 * KS) {
+                t0 += src[(size_t)k * C]; t1 += src[(size_t)(k + KS) * C];
+                t2 += src[(size_t)(k + 2 * KS) * C]; t3 += src[(size_t)(k + 3 * KS) * C];
+            }
+            for (; k < se_blocks; k += KS) t0 += src[(size_t)k * C];
+            part[slice * C + c] = (t0 + t1) + (t2 + t3);
         }
         __syncthreads();
         if (tid < C) {
@@ -284,36 +333,50 @@ se_gate_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_hw,
         }
     }
     __syncthreads();
-    // FC1: lanes run along the R outputs (w1 is (C, R) row-major: coalesced), G = 256 / R thread
-    // groups split the C reduction; the G partial sums are added in a fixed order
-    if (R <= 256) {
-        const int G = 256 / R;
-        const int j = tid % R, cg = tid / R;
-        if (cg < G) {
-            float s = 0.f;
-            for (int c = cg; c < C; c += G) s = fmaf(mean[c], w1[(size_t)c * R + j], s);
-            part[cg * R + j] = s;
-        }
-        __syncthreads();
-        if (tid < R) {
-            float s = 0.f;
-            for (int g = 0; g < G; ++g) s += part[g * R + tid];
-            r[tid] = activate<EFFDET_ACT_SWISH>(s + b1[tid]);
-        }
-    } else {
-        for (int j = warp; j < R; j += 8) {
-            float s = 0.f;
-            for (int c = lane; c < C; c += 32) s = fmaf(mean[c], w1[(size_t)c * R + j], s);
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-            if (lane == 0) r[j] = activate<EFFDET_ACT_SWISH>(s + b1[j]);
-        }
+    // FC1 + swish: lanes along the R outputs (w1 is (C, R) row-major), thread groups split C
+    const bool v4 = (R % 4 == 0) && ((reinterpret_cast<uintptr_t>(w1) & 15) == 0);
+    const bool v2 = (R % 2 == 0) && ((reinterpret_cast<uintptr_t>(w1) & 7) == 0);
+    int G;
+    if (v4) { se_fc1<4>(mean, w1, part, C, R, tid); G = kSeThreads / (R / 4); }
+    else if (v2) { se_fc1<2>(mean, w1, part, C, R, tid); G = kSeThreads / (R / 2); }
+    else { se_fc1<1>(mean, w1, part, C, R, tid); G = kSeThreads / R; }
+    __syncthreads();
+    if (tid < R) {
+        float s = 0.f;
+        for (int g = 0; g < G; ++g) s += part[g * R + tid];
+        r[tid] = activate<EFFDET_ACT_SWISH>(s + b1[tid]);
     }
     __syncthreads();
-    for (int c = tid; c < C; c += 256) {
-        float s = b2[c];
-        for (int j = 0; j < R; ++j) s = fmaf(r[j], w2[(size_t)j * C + c], s);
-        gate[(size_t)b * C + c] = activate<EFFDET_ACT_SIGMOID>(s);
+    // FC2 + sigmoid: a thread owns 4 consecutive channels (w2 is (R, C) row-major: 16-byte loads)
+    for (int c = tid * 4; c < C; c += kSeThreads * 4) {
+        float s[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s[u][k] = 0.f;
+        int j = 0;
+        for (; j + 3 < R; j += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 q = *reinterpret_cast<const float4 *>(w2 + (size_t)(j + u) * C + c);
+                const float rj = r[j + u];
+                s[u][0] = fmaf(rj, q.x, s[u][0]); s[u][1] = fmaf(rj, q.y, s[u][1]);
+                s[u][2] = fmaf(rj, q.z, s[u][2]); s[u][3] = fmaf(rj, q.w, s[u][3]);
+            }
+        }
+        for (; j < R; ++j) {
+            const float4 q = *reinterpret_cast<const float4 *>(w2 + (size_t)j * C + c);
+            const float rj = r[j];
+            s[0][0] = fmaf(rj, q.x, s[0][0]); s[0][1] = fmaf(rj, q.y, s[0][1]);
+            s[0][2] = fmaf(rj, q.z, s[0][2]); s[0][3] = fmaf(rj, q.w, s[0][3]);
+        }
+        const float4 bb = *reinterpret_cast<const float4 *>(b2 + c);
+        float4 o;
+        o.x = activate<EFFDET_ACT_SIGMOID>(bb.x + ((s[0][0] + s[1][0]) + (s[2][0] + s[3][0])));
+        o.y = activate<EFFDET_ACT_SIGMOID>(bb.y + ((s[0][1] + s[1][1]) + (s[2][1] + s[3][1])));
+        o.z = activate<EFFDET_ACT_SIGMOID>(bb.z + ((s[0][2] + s[1][2]) + (s[2][2] + s[3][2])));
+        o.w = activate<EFFDET_ACT_SIGMOID>(bb.w + ((s[0][3] + s[1][3]) + (s[2][3] + s[3][3])));
+        *reinterpret_cast<float4 *>(gate + (size_t)b * C + c) = o;
     }
 }
 
@@ -554,9 +617,12 @@ extern "C" int effdet_se_gate(const float *se_sum, int se_blocks, float inv_hw, 
                               int B, int C, int R, void *stream) {
     EFFDET_REQUIRE(se_sum && w1 && b1 && w2 && b2 && gate, "null pointer");
     EFFDET_REQUIRE(B > 0 && C > 0 && R > 0 && se_blocks > 0, "bad sizes");
-    const size_t sm = (size_t)(C + R + 256) * sizeof(float);
+    EFFDET_REQUIRE(C % 4 == 0 && R <= kSeThreads, "C must be a multiple of 4, R <= 512");
+    EFFDET_REQUIRE(((reinterpret_cast<uintptr_t>(w2) | reinterpret_cast<uintptr_t>(b2) |
+                     reinterpret_cast<uintptr_t>(gate)) & 15) == 0, "w2 / b2 / gate must be 16B aligned");
+    const size_t sm = (size_t)(C + R + 4 * kSeThreads) * sizeof(float);
     EFFDET_REQUIRE(sm <= 48 * 1024, "C + R too large");
-    se_gate_kernel<<<B, 256, sm, as_stream(stream)>>>(se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate,
+    se_gate_kernel<<<B, kSeThreads, sm, as_stream(stream)>>>(se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate,
                                                       C, R);
     EFFDET_LAUNCHED();
     return EFFDET_OK;

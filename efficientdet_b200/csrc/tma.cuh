@@ -34,6 +34,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (mbar_try(a, parity)) return;
     while (!mbar_try(a, parity)) __nanosleep(32);
 }
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, unsigned ns) {
+    const uint32_t a = smem_u32(bar);
+    if (mbar_try(a, parity)) return;
+    while (!mbar_try(a, parity)) __nanosleep(ns);
+}
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
                                             int c1, int c2, int c3) {
     asm volatile(
