@@ -537,6 +537,7 @@ struct alignas(64) WgTcParams {
     CUtensorMap z_map[kTcMaxGroups];
     WgTcGroup g[kTcMaxGroups];
     int n_groups, B, Cin, Cout, ksize, m_tiles, block_n, stages, tmem_cols;
+    int pair_taps;       // Cin <= 64: the two 64-channel halves of the M = 128 tile hold two different taps
     float *partial;
 };
 
@@ -571,9 +572,16 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
     const WgTcGroup &G = p.g[gi];
     const int t_begin = ((int)blockIdx.x - G.split_begin) * G.tiles_per_split;
     const int t_end = min(t_begin + G.tiles_per_split, G.n_tiles);
-    const int tap = blockIdx.y / p.m_tiles, ci0 = (blockIdx.y % p.m_tiles) * 128;
+    const int taps_all = p.ksize * p.ksize;
+    // pair_taps: rows 0..63 of the accumulator = tap 2*blockIdx.y, rows 64..127 = the next tap (both
+    // over input channels 0..63), sharing one dz tile -- halves the operand traffic of the 64-channel
+    // head convolutions
+    const int tap = p.pair_taps ? 2 * (int)blockIdx.y : (int)blockIdx.y / p.m_tiles;
+    const int tap2 = p.pair_taps ? min(tap + 1, taps_all - 1) : tap;
+    const int ci0 = p.pair_taps ? 0 : ((int)blockIdx.y % p.m_tiles) * 128;
     const int n0 = blockIdx.z * p.block_n;
     const int ky = tap / p.ksize, kx = tap - ky * p.ksize, pad = p.ksize / 2;
+    const int ky2 = tap2 / p.ksize, kx2 = tap2 - ky2 * p.ksize;
     const int num_k = t_end - t_begin;
 
     if (threadIdx.x == 0) {
@@ -599,7 +607,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
                 mbar_expect_tx(&full[s], (uint32_t)(a_bytes + b_bytes));
                 uint8_t *a = sA + (size_t)s * a_bytes, *b = sB + (size_t)s * b_bytes;
                 tma_load_4d(a, &p.x_map[gi], &full[s], ci0, x0 + kx - pad, y0 + ky - pad, b0);
-                tma_load_4d(a + kATileBytes, &p.x_map[gi], &full[s], ci0 + 64, x0 + kx - pad, y0 + ky - pad, b0);
+                if (p.pair_taps) tma_load_4d(a + kATileBytes, &p.x_map[gi], &full[s], 0, x0 + kx2 - pad, y0 + ky2 - pad, b0);
+                else tma_load_4d(a + kATileBytes, &p.x_map[gi], &full[s], ci0 + 64, x0 + kx - pad, y0 + ky - pad, b0);
                 for (int j = 0; j < n_boxes; ++j)
                     tma_load_4d(b + (size_t)j * kATileBytes, &p.z_map[gi], &full[s], n0 + 64 * j, x0, y0, b0);
             }
@@ -626,17 +635,20 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
         }
     } else {
         const int q = warp & 3;
-        const int ci = ci0 + q * 32 + lane;
+        const int row = q * 32 + lane;
+        const int ci = p.pair_taps ? (row & 63) : ci0 + row;
+        const int otap = p.pair_taps ? tap + (row >> 6) : tap;
         if (num_k > 0) {
             mbar_wait(tmem_full, 0);
             tc_fence_after();
         }
-        float *out = p.partial + ((size_t)blockIdx.x * p.ksize * p.ksize + tap) * p.Cin * p.Cout;
+        float *out = p.partial + ((size_t)blockIdx.x * taps_all + min(otap, taps_all - 1)) * p.Cin * p.Cout;
+        const bool row_ok = ci < p.Cin && otap < taps_all;
         for (int c0 = 0; c0 < p.block_n; c0 += 32) {
             uint32_t r[32];
             __syncwarp();
             if (num_k > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            if (ci < p.Cin) {
+            if (row_ok) {
                 float *o = out + (size_t)ci * p.Cout + n0 + c0;
                 const int nv = min(32, p.Cout - (n0 + c0));
 #pragma unroll
@@ -874,7 +886,8 @@ static int wg_tc_plan(const effdet_wgrad_desc *d, int *tiles_per_split_out, int 
         total_tiles += n_tiles_out[i];
     }
     // ~2 CTAs per SM in flight; at least 8 pixel tiles per CTA so the pipeline has work
-    long want = ((long)kNumSMs * 2 + (long)taps * m_tiles * n_tiles_n - 1) / ((long)taps * m_tiles * n_tiles_n);
+    const long yz = (long)((d->Cin <= 64 && taps > 1) ? (taps + 1) / 2 : taps * m_tiles) * n_tiles_n;
+    long want = ((long)kNumSMs * 2 + yz - 1) / yz;
     if (want < 1) want = 1;
     long tps = (total_tiles + want - 1) / want;
     if (tps < 8) tps = 8;
@@ -910,6 +923,7 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
     EFFDET_REQUIRE(splits == d->n_splits, "n_splits must be effdet_conv_wgrad_tc_splits()");
     p.n_groups = d->n_groups; p.B = d->B; p.Cin = d->Cin; p.Cout = d->Cout; p.ksize = d->kh;
     p.m_tiles = mt; p.block_n = bn; p.partial = d->partial;
+    p.pair_taps = (d->Cin <= 64 && d->kh * d->kw > 1) ? 1 : 0;
     p.tmem_cols = bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
     const int stage_bytes = 2 * kATileBytes + (bn / 64) * kATileBytes;
     int stages = (200 * 1024) / stage_bytes;
@@ -956,7 +970,7 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
         attr_set = true;
     }
     const int taps = d->kh * d->kw;
-    dim3 grid(z, taps * mt, (d->Cout + bn - 1) / bn);
+    dim3 grid(z, p.pair_taps ? (taps + 1) / 2 : taps * mt, (d->Cout + bn - 1) / bn);
     cudaStream_t st = as_stream(stream);
     conv_wgrad_tc_kernel<<<grid, 192, smem, st>>>(p);
     EFFDET_LAUNCHED();

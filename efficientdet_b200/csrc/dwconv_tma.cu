@@ -248,6 +248,163 @@ static int launch_dw_tma(const void *x, const float *w, const float *scale, cons
     return EFFDET_OK;
 }
 
+// ------------------------------------------------------------------ depthwise weight gradient
+// dW[ky][kx][c] = sum_{b,oy,ox} x[b, oy*S - pad + ky, ox*S - pad + kx, c] * dz[b,oy,ox,c]
+// Same tiling and thread layout as the forward kernel: block (split, channel block) walks spatial
+// tiles split, split + nsplit, ...; TMA double-buffers the x patch (with halo, zero padded) and the
+// dz tile (zero filled outside the tensor, so edge tiles need no masks); a thread keeps the K*K
+// partial sums of its channel pair in registers over ALL its tiles.  Partials are written per
+// split in a fixed order and summed by sum_partials_warp_kernel (deterministic).
+struct alignas(64) DwWgParams {
+    CUtensorMap x_map;                     // (C, W, H, B) bf16, box (CB, IW, IH, 1)
+    CUtensorMap z_map;                     // (C, Wo, Ho, B) bf16, box (CB, TW, TH, 1)
+    float *partial;                        // [nsplit][K*K][C]
+    int C, pad_t, pad_l, tiles_x, tiles_y, spatial_tiles;
+};
+
+template <int K, int S, int CP>
+__global__ void __launch_bounds__(DwCfg<K, S, CP>::NT, 2)
+dw_wgrad_tma_kernel(const __grid_constant__ DwWgParams p) {
+    using Cfg = DwCfg<K, S, CP>;
+    constexpr int CB = Cfg::CB, IW = Cfg::IW, NIN = Cfg::NIN, IR = Cfg::IR, TW = Cfg::TW, TH = Cfg::TH;
+    constexpr int Z_BYTES = TH * TW * CB * 2;
+    constexpr int STAGE = ((Cfg::IN_PAD + Z_BYTES + 127) / 128) * 128;
+    extern __shared__ uint8_t dsm_raw[];
+    uint8_t *dsm = dsm_raw + ((128u - (smem_u32(dsm_raw) & 127u)) & 127u);
+    uint64_t *full = reinterpret_cast<uint64_t *>(dsm + 2 * STAGE);
+    float *sRed = reinterpret_cast<float *>(dsm);          // reused after the main loop: [8][K*K][CB]
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int cb = blockIdx.y;
+    auto issue = [&](int t, int stage) {
+        int r = t;
+        const int tx = r % p.tiles_x; r /= p.tiles_x;
+        const int ty = r % p.tiles_y; const int b = r / p.tiles_y;
+        uint8_t *dst = dsm + (size_t)stage * STAGE;
+        mbar_expect_tx(&full[stage], (uint32_t)(Cfg::IN_BYTES + Z_BYTES));
+        tma_load_4d(dst, &p.x_map, &full[stage], cb * CB, tx * TW * S - p.pad_l, ty * TH * S - p.pad_t, b);
+        tma_load_4d(dst + Cfg::IN_PAD, &p.z_map, &full[stage], cb * CB, tx * TW, ty * TH, b);
+    };
+    const int pair = tid % CP, slot = tid / CP;
+    float2 acc[K * K];
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) acc[i] = make_float2(0.f, 0.f);
+
+    if (tid == 0 && (int)blockIdx.x < p.spatial_tiles) issue(blockIdx.x, 0);
+    int it = 0;
+    for (int t = blockIdx.x; t < p.spatial_tiles; t += gridDim.x, ++it) {
+        const int stage = it & 1;
+        if (tid == 0 && t + (int)gridDim.x < p.spatial_tiles) issue(t + gridDim.x, stage ^ 1);
+        const uint8_t *sIn = dsm + (size_t)stage * STAGE;
+        const uint8_t *sZ = sIn + Cfg::IN_PAD;
+        mbar_wait(&full[stage], (it >> 1) & 1);
+#pragma unroll 1
+        for (int pass = 0; pass < Cfg::PASSES; ++pass) {
+            const int rt = pass * 8 + slot;
+            const int ry = (rt / (TW / kRtW)) * kRtH, rx = (rt % (TW / kRtW)) * kRtW;
+            float2 dzv[kRtH][kRtW];
+#pragma unroll
+            for (int i = 0; i < kRtH; ++i)
+#pragma unroll
+                for (int j = 0; j < kRtW; ++j) {
+                    const uint32_t w2 = *reinterpret_cast<const uint32_t *>(
+                        sZ + ((size_t)((ry + i) * TW + rx + j) * CB + pair * 2) * 2);
+                    dzv[i][j] = make_float2(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u));
+                }
+            const uint8_t *base = sIn + ((size_t)((ry * S) * IW + rx * S) * CB + pair * 2) * 2;
+#pragma unroll
+            for (int rr = 0; rr < IR; ++rr) {
+                float2 in[NIN];
+#pragma unroll
+                for (int j = 0; j < NIN; ++j) {
+                    const uint32_t w2 = *reinterpret_cast<const uint32_t *>(base + (size_t)(rr * IW + j) * CB * 2);
+                    in[j] = make_float2(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u));
+                }
+#pragma unroll
+                for (int orow = 0; orow < kRtH; ++orow) {
+                    const int ky = rr - orow * S;
+                    if (ky < 0 || ky >= K) continue;
+#pragma unroll
+                    for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                        for (int oc = 0; oc < kRtW; ++oc)
+                            acc[ky * K + kx] = __ffma2_rn(in[oc * S + kx], dzv[orow][oc], acc[ky * K + kx]);
+                }
+            }
+        }
+        __syncthreads();            // everyone is done reading this stage before it is refilled
+    }
+    // block reduction over the 8 register-tile slots (fixed order), then one partial row per split
+#pragma unroll
+    for (int i = 0; i < K * K; ++i)
+        *reinterpret_cast<float2 *>(sRed + ((size_t)slot * K * K + i) * CB + pair * 2) = acc[i];
+    __syncthreads();
+    for (int i = tid; i < K * K * CB; i += Cfg::NT) {
+        const int c = cb * CB + i % CB;
+        if (c < p.C) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += sRed[(size_t)w * K * K * CB + i];
+            p.partial[((size_t)blockIdx.x * K * K + i / CB) * p.C + c] = s;
+        }
+    }
+}
+
+template <int K, int S, int CP>
+static int launch_dw_wgrad_tma(const void *x, const void *dz, float *partial, int nsplit, int B, int H, int W,
+                               int C, cudaStream_t st) {
+    using Cfg = DwCfg<K, S, CP>;
+    constexpr int Z_BYTES = Cfg::TH * Cfg::TW * Cfg::CB * 2;
+    constexpr int STAGE = ((Cfg::IN_PAD + Z_BYTES + 127) / 128) * 128;
+    constexpr size_t RED = (size_t)8 * K * K * Cfg::CB * 4;
+    constexpr size_t SMEM = (2 * (size_t)STAGE > RED ? 2 * (size_t)STAGE : RED) + 64 + 128;
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return fail(EFFDET_E_CUDA, "effdet_dw_backward: cuTensorMapEncodeTiled unavailable%s", "");
+    DwWgParams p;
+    memset(&p, 0, sizeof(p));
+    const int Ho = (H + S - 1) / S, Wo = (W + S - 1) / S;
+    p.C = C; p.partial = partial;
+    p.pad_t = max((Ho - 1) * S + K - H, 0) / 2;
+    p.pad_l = max((Wo - 1) * S + K - W, 0) / 2;
+    p.tiles_x = (Wo + Cfg::TW - 1) / Cfg::TW; p.tiles_y = (Ho + Cfg::TH - 1) / Cfg::TH;
+    p.spatial_tiles = p.tiles_x * p.tiles_y * B;
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+        cuuint32_t box[4] = {(cuuint32_t)Cfg::CB, (cuuint32_t)Cfg::IW, (cuuint32_t)Cfg::IH, 1};
+        CUresult r = encode(&p.x_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(x), dims, strides, box,
+                            es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_dw_backward: encode(x) failed %s(%lld)", "", (long long)r);
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * Wo, (cuuint64_t)C * 2 * Wo * Ho};
+        cuuint32_t box[4] = {(cuuint32_t)Cfg::CB, (cuuint32_t)Cfg::TW, (cuuint32_t)Cfg::TH, 1};
+        CUresult r = encode(&p.z_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(dz), dims, strides, box,
+                            es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_dw_backward: encode(dz) failed %s(%lld)", "", (long long)r);
+    }
+    auto kern = dw_wgrad_tma_kernel<K, S, CP>;
+    static bool attr = false;
+    if (!attr) {
+        EFFDET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        attr = true;
+    }
+    dim3 grid(nsplit, (C + Cfg::CB - 1) / Cfg::CB);
+    kern<<<grid, Cfg::NT, SMEM, st>>>(p);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
 // channel pairs per block: the largest of 32 / 24 / 16 (64 / 48 / 32 channels) that divides C,
 // else the one wasting the fewest lanes
 static int pick_cp(int C) {
@@ -281,6 +438,33 @@ int dwconv_bf16_tma(const void *x, const float *w, const float *scale, const flo
     DWT_CASE(3, 1) DWT_CASE(5, 1) DWT_CASE(3, 2) DWT_CASE(5, 2)
 #undef DWT_CASE
     return fail(EFFDET_E_INVALID, "effdet_dwconv: bad kernel / stride%s", "");
+}
+
+// number of spatial splits (partial rows) of the bf16 depthwise weight gradient
+int dw_wgrad_bf16_splits(int B, int H, int W, int C, int stride) {
+    const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    const int tw = stride == 1 ? 16 : 8;
+    const long tiles = (long)((Wo + tw - 1) / tw) * ((Ho + 7) / 8) * B;
+    const int cp = pick_cp(C);
+    const int cblocks = (C + 2 * cp - 1) / (2 * cp);
+    long ns = (2L * kNumSMs + cblocks - 1) / cblocks;
+    if (ns < 2) ns = 2;
+    if (ns > tiles) ns = tiles < 2 ? 2 : tiles;
+    return (int)ns;
+}
+
+int dw_wgrad_bf16_tma(const void *x, const void *dz, float *partial, int nsplit, int B, int H, int W, int C, int k,
+                      int stride, cudaStream_t st) {
+    const int cp = pick_cp(C);
+#define DWW_CASE(K_, S_)                                                                                   \
+    if (k == K_ && stride == S_) {                                                                         \
+        if (cp == 32) return launch_dw_wgrad_tma<K_, S_, 32>(x, dz, partial, nsplit, B, H, W, C, st);       \
+        if (cp == 24) return launch_dw_wgrad_tma<K_, S_, 24>(x, dz, partial, nsplit, B, H, W, C, st);       \
+        return launch_dw_wgrad_tma<K_, S_, 16>(x, dz, partial, nsplit, B, H, W, C, st);                    \
+    }
+    DWW_CASE(3, 1) DWW_CASE(5, 1) DWW_CASE(3, 2) DWW_CASE(5, 2)
+#undef DWW_CASE
+    return fail(EFFDET_E_INVALID, "effdet_dw_backward: bad kernel / stride%s", "");
 }
 
 }  // namespace effdet

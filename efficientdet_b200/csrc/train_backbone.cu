@@ -413,6 +413,22 @@ stem_wgrad_kernel(const float *__restrict__ img, const T *__restrict__ dz, int B
     }
 }
 
+// flipped depthwise kernel (the data gradient of a stride-1 depthwise conv is the same conv with
+// the taps reversed) followed by C ones and C zeros (identity scale / shift of the epilogue)
+__global__ void dw_flip_kernel(const float *__restrict__ w, float *__restrict__ out, int taps, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < taps * C) out[i] = w[(size_t)(taps - 1 - i / C) * C + i % C];
+    else if (i < (taps + 1) * C) out[i] = 1.f;
+    else if (i < (taps + 2) * C) out[i] = 0.f;
+}
+
+// dwconv_tma.cu
+int dwconv_bf16_tma(const void *x, const float *w, const float *scale, const float *shift, void *y, float *se_sum,
+                    int B, int H, int W, int C, int k, int stride, int act, cudaStream_t st);
+int dw_wgrad_bf16_splits(int B, int H, int W, int C, int stride);
+int dw_wgrad_bf16_tma(const void *x, const void *dz, float *partial, int nsplit, int B, int H, int W, int C, int k,
+                      int stride, cudaStream_t st);
+
 static unsigned grid_for_n(size_t n) {
     unsigned b = cdiv(n, 256);
     return b > (unsigned)kNumSMs * 8 ? kNumSMs * 8 : (b ? b : 1);
@@ -562,6 +578,7 @@ extern "C" int effdet_se_backward(const void *dyg, const void *y, const float *g
 }
 
 extern "C" int effdet_dw_backward_blocks(int B, int H, int W, int C, int k, int stride, int dtype) {
+    if (dtype == EFFDET_BF16) return dw_wgrad_bf16_splits(B, H, W, C, stride);
     const int CV = dtype == EFFDET_BF16 ? 8 : 4;
     int nvec = C / CV; if (nvec < 1) nvec = 1;
     int PY = (k == 5 ? 64 : 128) / nvec; if (PY < 1) PY = 1;
@@ -583,6 +600,29 @@ extern "C" int effdet_dw_backward(const void *x, const void *dz, const float *ke
     cudaStream_t st = as_stream(stream);
     const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
     const int pt = max((Ho - 1) * stride + k - H, 0) / 2, pl = max((Wo - 1) * stride + k - W, 0) / 2;
+    if (dtype == EFFDET_BF16) {
+        // TMA-tiled weight gradient (dwconv_tma.cu), partial rows summed in a fixed order
+        int rc = dw_wgrad_bf16_tma(x, dz, partial, nblk, B, H, W, C, k, stride, st);
+        if (rc) return rc;
+        sum_partials_warp_kernel<<<cdiv((size_t)k * k * C * 32, 256), 256, 0, st>>>(partial, nblk, k * k * C, dkernel);
+        EFFDET_LAUNCHED();
+        if (dx && stride == 1) {
+            // data gradient == the forward kernel on dz with reversed taps (scratch: partial is free now)
+            dw_flip_kernel<<<cdiv((size_t)(k * k + 2) * C, 256), 256, 0, st>>>(kernel, partial, k * k, C);
+            EFFDET_LAUNCHED();
+            return dwconv_bf16_tma(dz, partial, partial + (size_t)k * k * C, partial + (size_t)(k * k + 1) * C, dx,
+                                   nullptr, B, H, W, C, k, 1, EFFDET_ACT_NONE, st);
+        }
+        if (dx) {
+            const size_t n = (size_t)B * H * W * C;
+            if (k == 3) dw_dgrad_kernel<__nv_bfloat16, 8, 3><<<grid_for_n(n / 8), 256, 0, st>>>(
+                    (const __nv_bfloat16 *)dz, kernel, (__nv_bfloat16 *)dx, B, H, W, Ho, Wo, C, stride, pt, pl);
+            else dw_dgrad_kernel<__nv_bfloat16, 8, 5><<<grid_for_n(n / 8), 256, 0, st>>>(
+                    (const __nv_bfloat16 *)dz, kernel, (__nv_bfloat16 *)dx, B, H, W, Ho, Wo, C, stride, pt, pl);
+            EFFDET_LAUNCHED();
+        }
+        return EFFDET_OK;
+    }
     const int CV = dtype == EFFDET_BF16 ? 8 : 4;
     const int nvec = C / CV;
     EFFDET_REQUIRE(nvec <= 1024, "C too large");

@@ -444,6 +444,36 @@ def test_full_training_step_with_backbone(weighted, freeze_bn):
             assert rel_err(W1[name + "/moving_variance"], W0[name + "/moving_variance"] * 0.99 + v * 0.01) < 1e-4
 
 
+@pytest.mark.parametrize("k,stride,C,H,B", [(3, 1, 48, 20, 3), (5, 1, 144, 17, 2), (3, 2, 96, 16, 2), (5, 2, 240, 18, 2),
+                                            (5, 1, 64, 8, 5), (3, 1, 32, 33, 1)])
+def test_depthwise_backward_bf16_tma(k, stride, C, H, B):
+    """bf16 depthwise backward (efficientnet.py:242-252): TMA-tiled weight gradient and the data gradient
+    (forward kernel on dz with reversed taps for stride 1, gather form for stride 2) against autograd
+    on the same bf16-rounded operands."""
+    from efficientdet_b200 import _lib
+    from oracle import graph
+    lib = _lib.load()
+    rng = np.random.default_rng(k * 100 + C)
+    Ho = (H + stride - 1) // stride
+    x = torch.from_numpy(rng.standard_normal((B, H, H, C)).astype(np.float32)).cuda().to(torch.bfloat16)
+    dz = torch.from_numpy(rng.standard_normal((B, Ho, Ho, C)).astype(np.float32)).cuda().to(torch.bfloat16)
+    w = torch.from_numpy((rng.standard_normal((k, k, C)) * 0.3).astype(np.float32)).cuda()
+    dx = torch.full((B, H, H, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dw = torch.zeros((k, k, C), device="cuda")
+    nb = lib.effdet_dw_backward_blocks(B, H, H, C, k, stride, _lib.BF16)
+    part = torch.empty(k * k * C * nb, device="cuda")
+    _lib.call("effdet_dw_backward", x.data_ptr(), dz.data_ptr(), w.data_ptr(), dx.data_ptr(), dw.data_ptr(),
+              part.data_ptr(), nb, B, H, H, C, k, stride, _lib.BF16, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    xr = x.float().cpu().double().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.cpu().double().requires_grad_(True)
+    wt = wr.permute(2, 0, 1)[:, None]
+    y = torch.nn.functional.conv2d(graph.same_pad(xr, k, stride), wt, None, stride=stride, groups=C)
+    y.backward(dz.float().cpu().double().permute(0, 3, 1, 2))
+    assert rel_err(dw.cpu().numpy(), wr.grad.numpy()) < 2e-5
+    assert rel_err(dx.float().cpu().numpy(), xr.grad.permute(0, 2, 3, 1).numpy()) < 6e-3
+
+
 def test_partial_backbone_freeze_and_stochastic_depth_are_rejected():
     from efficientdet_b200.model import efficientdet
     z = lambda *s: np.zeros(s, np.float32)
