@@ -86,6 +86,8 @@ _SIGNATURES = {
                                   c_int, c_int, c_int, c_int, c_void_p],
     "effdet_conv_weight_transpose": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "effdet_flip_taps": [c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "effdet_zero_insert": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                           c_void_p],
     "effdet_sgd_momentum_step": [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float,
                                  c_void_p],
     "effdet_bn_act_backward": [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

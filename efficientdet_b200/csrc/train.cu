@@ -505,6 +505,30 @@ __global__ void conv_weight_transpose_kernel(const float *__restrict__ in, float
     out[((size_t)(taps - 1 - t) * Cout + co) * Cin + ci] = in[i];
 }
 
+
+// out (B,H,W,C) = dz (B,Ho,Wo,C) placed at (2*oy + ay, 2*ox + ax), zeros elsewhere.  The data gradient of
+// a stride-2 convolution is then the stride-1 data gradient (tensor-core path) of this tensor.
+template <typename T, int CV>
+__global__ void __launch_bounds__(256)
+zero_insert_kernel(const T *__restrict__ dz, T *__restrict__ out, int B, int Ho, int Wo, int C, int H, int W,
+                   int ay, int ax) {
+    const int nvec = C / CV;
+    const size_t total = (size_t)B * H * W * nvec;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int c = (int)(i % nvec) * CV;
+        const size_t pix = i / nvec;
+        const int x = (int)(pix % W), y = (int)((pix / W) % H);
+        const size_t b = pix / ((size_t)W * H);
+        const int ny = y - ay, nx = x - ax;
+        float v[CV];
+#pragma unroll
+        for (int k = 0; k < CV; ++k) v[k] = 0.f;
+        if (ny >= 0 && nx >= 0 && !(ny & 1) && !(nx & 1) && (ny >> 1) < Ho && (nx >> 1) < Wo)
+            VecT<T, CV>::load(dz + ((b * Ho + (ny >> 1)) * (size_t)Wo + (nx >> 1)) * C + c, v);
+        VecT<T, CV>::store(out + pix * C + c, v);
+    }
+}
+
 static bool a16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static unsigned grid_for(size_t n) {
     unsigned b = cdiv(n, 256);
@@ -746,6 +770,21 @@ extern "C" int effdet_fuse_backward_weights(const void *df, const void *f, const
 
 /* keras SGD (train_tpu.py:268-269): v = momentum*v - lr_t*(g*grad_scale); w += v, with
  * lr_t = lr / (1 + decay*iterations) computed by the caller. */
+/* Zero insertion for the data gradient of a stride-2 convolution: out (B,H,W,C) holds dz (B,Ho,Wo,C) at
+ * rows 2*oy + ay / columns 2*ox + ax and zeros elsewhere (ay = (k-1)/2 - pad_top of the forward conv). */
+extern "C" int effdet_zero_insert(const void *dz, void *out, int B, int Ho, int Wo, int C, int H, int W, int ay,
+                                  int ax, int dtype, void *stream) {
+    EFFDET_REQUIRE(dz && out && B > 0 && Ho > 0 && Wo > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad arguments");
+    EFFDET_REQUIRE(a16(dz) && a16(out), "16B alignment");
+    cudaStream_t st = as_stream(stream);
+    const size_t n = (size_t)B * H * W * C;
+    DISPATCH_T(dtype,
+        (zero_insert_kernel<float, 4><<<grid_for(n / 4), 256, 0, st>>>((const float *)dz, (float *)out, B, Ho, Wo, C, H, W, ay, ax)),
+        (zero_insert_kernel<__nv_bfloat16, 8><<<grid_for(n / 8), 256, 0, st>>>((const __nv_bfloat16 *)dz, (__nv_bfloat16 *)out, B, Ho, Wo, C, H, W, ay, ax)))
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
 extern "C" int effdet_sgd_momentum_step(float *w, const float *g, float *v, size_t n, float lr_t,
                                         float momentum, float grad_scale, void *stream) {
     if (n == 0) return EFFDET_OK;

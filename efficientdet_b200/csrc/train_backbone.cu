@@ -429,6 +429,76 @@ int dw_wgrad_bf16_splits(int B, int H, int W, int C, int stride);
 int dw_wgrad_bf16_tma(const void *x, const void *dz, float *partial, int nsplit, int B, int H, int W, int C, int k,
                       int stride, cudaStream_t st);
 
+// bf16 dz, tiled: block walks 4 x 32 output-pixel tiles (tile = blockIdx.x, += gridDim.x), staging
+// the fp32 RGB patch (9 x 65 pixels, coalesced rows) and the dz tile in shared memory; a thread owns
+// one output-channel PAIR and TPG of the 27 (tap, ci) rows and keeps their partial sums in
+// registers over all its tiles (packed FFMA2), so the kernel is a streaming pass over images + dz.
+constexpr int kSwTW = 32, kSwTH = 4, kSwIW = 2 * kSwTW + 1, kSwIH = 2 * kSwTH + 1;
+template <int C0>
+__global__ void __launch_bounds__(256)
+stem_wgrad_tiled_kernel(const float *__restrict__ img, const __nv_bfloat16 *__restrict__ dz, int B, int H, int W,
+                        int Ho, int Wo, int pad_t, int pad_l, int tiles_x, int tiles_y,
+                        float *__restrict__ partial) {
+    constexpr int CPn = C0 / 2, G = 256 / CPn, TPG = (27 + G - 1) / G, ROW = kSwIW * 3, NPIX = kSwTW * kSwTH;
+    __shared__ float sin_[kSwIH * ROW];
+    __shared__ __align__(16) uint32_t sdz[NPIX * CPn];
+    const int cp = threadIdx.x % CPn, g = threadIdx.x / CPn;
+    const bool active = g < G;
+    int off[TPG];
+#pragma unroll
+    for (int j = 0; j < TPG; ++j) {
+        const int tc = min(g * TPG + j, 26);
+        const int tap = tc / 3, ci = tc - tap * 3;
+        off[j] = (tap / 3) * ROW + (tap % 3) * 3 + ci;
+    }
+    float2 acc[TPG];
+#pragma unroll
+    for (int j = 0; j < TPG; ++j) acc[j] = make_float2(0.f, 0.f);
+    const int total_tiles = tiles_x * tiles_y * B;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int r = t;
+        const int tx = r % tiles_x; r /= tiles_x;
+        const int ty = r % tiles_y; const int b = r / tiles_y;
+        const int ty0 = ty * kSwTH, tx0 = tx * kSwTW;
+        const int iy0 = ty0 * 2 - pad_t, ix0 = tx0 * 2 - pad_l;
+        const float *ib = img + (size_t)b * H * W * 3;
+        __syncthreads();                // previous tile fully consumed
+        for (int i = threadIdx.x; i < kSwIH * ROW; i += 256) {
+            const int rr = i / ROW, cidx = i - rr * ROW;
+            const int gy = iy0 + rr, g3 = ix0 * 3 + cidx;
+            sin_[i] = (gy >= 0 && gy < H && g3 >= 0 && g3 < W * 3) ? ib[(size_t)gy * W * 3 + g3] : 0.f;
+        }
+        for (int i = threadIdx.x; i < NPIX * CPn; i += 256) {
+            const int pix = i / CPn, c2 = i - pix * CPn;
+            const int oy = ty0 + pix / kSwTW, ox = tx0 + pix % kSwTW;
+            sdz[i] = (oy < Ho && ox < Wo)
+                ? reinterpret_cast<const uint32_t *>(dz + (((size_t)b * Ho + oy) * Wo + ox) * C0)[c2] : 0u;
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll 4
+            for (int pix = 0; pix < NPIX; ++pix) {
+                const uint32_t w2 = sdz[pix * CPn + cp];
+                const float2 dzv = make_float2(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u));
+                const float *base = sin_ + (pix / kSwTW) * 2 * ROW + (pix % kSwTW) * 6;
+#pragma unroll
+                for (int j = 0; j < TPG; ++j) {
+                    const float v = base[off[j]];
+                    acc[j] = __ffma2_rn(make_float2(v, v), dzv, acc[j]);
+                }
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < TPG; ++j) {
+            const int tc = g * TPG + j;
+            if (tc < 27)
+                *reinterpret_cast<float2 *>(partial + (size_t)blockIdx.x * 27 * C0 + (size_t)tc * C0 + cp * 2) = acc[j];
+        }
+    }
+}
+
 static unsigned grid_for_n(size_t n) {
     unsigned b = cdiv(n, 256);
     return b > (unsigned)kNumSMs * 8 ? kNumSMs * 8 : (b ? b : 1);
@@ -673,6 +743,18 @@ extern "C" int effdet_stem_wgrad(const float *images, const void *dz, float *dke
     const int pt = max((Ho - 1) * 2 + 3 - H, 0) / 2, pl = max((Wo - 1) * 2 + 3 - W, 0) / 2;
     const size_t total = (size_t)B * Ho * Wo;
     const int ppb = (int)cdiv(total, nblk);
+    if (dtype == EFFDET_BF16 && (C0 == 32 || C0 == 40 || C0 == 48 || C0 == 56 || C0 == 64) &&
+        (reinterpret_cast<uintptr_t>(dz) & 3) == 0) {
+        const int tx = (Wo + kSwTW - 1) / kSwTW, ty = (Ho + kSwTH - 1) / kSwTH;
+        int grid = nblk < kNumSMs * 4 ? nblk : kNumSMs * 4;
+#define SWG(C) case C: stem_wgrad_tiled_kernel<C><<<grid, 256, 0, st>>>(images, (const __nv_bfloat16 *)dz, B, H, W, Ho, Wo, pt, pl, tx, ty, partial); break;
+        switch (C0) { SWG(32) SWG(40) SWG(48) SWG(56) SWG(64) }
+#undef SWG
+        EFFDET_LAUNCHED();
+        sum_partials_warp_kernel<<<cdiv((size_t)27 * C0 * 32, 256), 256, 0, st>>>(partial, grid, 27 * C0, dkernel);
+        EFFDET_LAUNCHED();
+        return EFFDET_OK;
+    }
     DISPATCH_TB(dtype,
         (stem_wgrad_kernel<float><<<nblk, 256, 0, st>>>(images, (const float *)dz, B, H, W, Ho, Wo, C0, pt, pl, ppb, partial)),
         (stem_wgrad_kernel<__nv_bfloat16><<<nblk, 256, 0, st>>>(images, (const __nv_bfloat16 *)dz, B, H, W, Ho, Wo, C0,

@@ -730,6 +730,17 @@ class TrainPlan(engine.Plan):
             wt = self._transposed_weight(key, k * k, cin, cout)
             self._dgrad(None, [dz], wt, cout, cin, [g], [x], None, [acc], [x.shape], name=name + "_dgrad",
                         key=key)
+        elif self.net.use_tensor_cores and self.dtype == BF16 and stride == 2 and cout % 8 == 0:
+            # stride 2: zero-insert dz to the input's extent, then the stride-1 tensor-core data gradient
+            H, Ho = x.shape[1], dz.shape[1]
+            a = (k - 1) // 2 - max((Ho - 1) * 2 + k - H, 0) // 2
+            dzs = self.val((B, H, H, cout), name=name + "_dz_up")
+            self.add("zero_insert", [dz], [dzs],
+                     lambda: _call("effdet_zero_insert", dz.ptr, dzs.ptr, B, Ho, Ho, cout, H, H, a, a, self.dtype),
+                     name + "_dz_up")
+            wt = self._transposed_weight(key, k * k, cin, cout)
+            self._dgrad(None, [dzs], wt, cout, cin, [g], [x], None, [acc], [x.shape], name=name + "_dgrad",
+                        key=key)
         else:
             H = x.shape[1]
             self.add("conv_dgrad", [dz, g if acc else None], [g],

@@ -317,6 +317,12 @@ int effdet_conv_weight_transpose(const float *in, float *out, int taps, int Cin,
 /* (taps, n) -> spatially flipped (depthwise data-gradient kernel). */
 int effdet_flip_taps(const float *in, float *out, int taps, int n, void *stream);
 
+/* Zero insertion for the data gradient of a stride-2 convolution (implicit in model.fit, train_tpu.py:330;
+ * forward: model.py:205-211 BiFPN P6/P7 laterals): out (B,H,W,C) holds dz (B,Ho,Wo,C) at rows 2*oy + ay,
+ * columns 2*ox + ax and zeros elsewhere, so that the stride-1 tensor-core data gradient applies. */
+int effdet_zero_insert(const void *dz, void *out, int B, int Ho, int Wo, int C, int H, int W, int ay, int ax,
+                       int dtype, void *stream);
+
 /* keras SGD(lr, decay, momentum) of train_tpu.py:268-269 on a flat fp32 range:
  * v = momentum*v - lr_t*(g*grad_scale); w += v, lr_t = lr/(1+decay*iterations) from the caller. */
 int effdet_sgd_momentum_step(float *w, const float *g, float *v, size_t n, float lr_t,

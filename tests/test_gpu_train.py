@@ -474,6 +474,29 @@ def test_depthwise_backward_bf16_tma(k, stride, C, H, B):
     assert rel_err(dx.float().cpu().numpy(), xr.grad.permute(0, 2, 3, 1).numpy()) < 6e-3
 
 
+@pytest.mark.parametrize("C0,H,B", [(32, 64, 2), (48, 70, 3), (40, 33, 1)])
+def test_stem_weight_gradient_bf16(C0, H, B):
+    """Stem conv (efficientnet.py:413-423: 3x3, stride 2, 3 -> C0) weight gradient from bf16 dz (tiled
+    kernel) against autograd on the same operands."""
+    from efficientdet_b200 import _lib
+    from oracle import graph
+    lib = _lib.load()
+    rng = np.random.default_rng(C0 + H)
+    Ho = (H + 1) // 2
+    img = torch.from_numpy(rng.standard_normal((B, H, H, 3)).astype(np.float32)).cuda()
+    dz = torch.from_numpy(rng.standard_normal((B, Ho, Ho, C0)).astype(np.float32)).cuda().to(torch.bfloat16)
+    dw = torch.zeros((3, 3, 3, C0), device="cuda")
+    nb = lib.effdet_stem_wgrad_blocks(B, H, H)
+    part = torch.empty(27 * C0 * nb, device="cuda")
+    _lib.call("effdet_stem_wgrad", img.data_ptr(), dz.data_ptr(), dw.data_ptr(), part.data_ptr(), nb, B, H, H, C0,
+              _lib.BF16, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    w = torch.zeros((C0, 3, 3, 3), dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(graph.same_pad(img.cpu().double().permute(0, 3, 1, 2), 3, 2), w, None, stride=2)
+    y.backward(dz.float().cpu().double().permute(0, 3, 1, 2))
+    assert rel_err(dw.cpu().numpy(), w.grad.permute(2, 3, 1, 0).numpy()) < 2e-5
+
+
 def test_partial_backbone_freeze_and_stochastic_depth_are_rejected():
     from efficientdet_b200.model import efficientdet
     z = lambda *s: np.zeros(s, np.float32)
