@@ -83,4 +83,36 @@ __device__ __forceinline__ float activate_rt(float x, int act) {
     }
 }
 
+// ---- storage-type aware activations: bf16 tensors take the one-MUFU tanh forms (error ~2^-11 absolute,
+//      below the bf16 rounding of the stored result); fp32 tensors keep the exact forms
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+template <typename T> __device__ __forceinline__ float activate_io(float x, int act) { return activate_rt(x, act); }
+template <> __device__ __forceinline__ float activate_io<__nv_bfloat16>(float x, int act) {
+    switch (act) {
+        case EFFDET_ACT_RELU: return fmaxf(x, 0.f);
+        case EFFDET_ACT_SWISH: { const float h = 0.5f * x; return fmaf(h, tanh_fast(h), h); }
+        case EFFDET_ACT_SIGMOID: return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f);
+        default: return x;
+    }
+}
+// derivative of the activation applied to u, as a factor on the incoming gradient
+template <typename T> __device__ __forceinline__ float act_grad_io(float u, int act) {
+    if (act == EFFDET_ACT_RELU) return u > 0.f ? 1.f : 0.f;
+    if (act == EFFDET_ACT_SWISH) {
+        const float s = 1.f / (1.f + __expf(-u));
+        return s * (1.f + u * (1.f - s));
+    }
+    return 1.f;
+}
+template <> __device__ __forceinline__ float act_grad_io<__nv_bfloat16>(float u, int act) {
+    if (act == EFFDET_ACT_RELU) return u > 0.f ? 1.f : 0.f;
+    if (act == EFFDET_ACT_SWISH) {
+        const float s = fmaf(0.5f, tanh_fast(0.5f * u), 0.5f);
+        return s * fmaf(u, 1.f - s, 1.f);
+    }
+    return 1.f;
+}
+
 }  // namespace effdet

@@ -256,15 +256,15 @@ __global__ void __launch_bounds__(256)
 scale_shift_act_kernel(const T *__restrict__ z, const float *__restrict__ scale,
                        const float *__restrict__ shift, T *__restrict__ y, size_t nvec_total,
                        int C, int act) {
-    const int nvec = C / CV;
+    const unsigned nvec = C / CV;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
-        const int c = (int)(i % nvec) * CV;
+        const int c = (int)((unsigned)i % nvec) * CV;        // nvec_total < 2^32 (checked by the launcher)
         float v[CV], sc[CV], sh[CV];
         VecT<T, CV>::load(z + i * CV, v);
         ldf<CV>(scale + c, sc);
         ldf<CV>(shift + c, sh);
 #pragma unroll
-        for (int k = 0; k < CV; ++k) v[k] = activate_rt(v[k] * sc[k] + sh[k], act);
+        for (int k = 0; k < CV; ++k) v[k] = activate_io<T>(fmaf(v[k], sc[k], sh[k]), act);
         VecT<T, CV>::store(y + i * CV, v);
     }
 }
@@ -274,9 +274,9 @@ template <typename T, int CV>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ y, const T *__restrict__ z,
                     const float *__restrict__ k123, T *__restrict__ dz, size_t nvec_total, int C) {
-    const int nvec = C / CV;
+    const unsigned nvec = C / CV;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
-        const int c = (int)(i % nvec) * CV;
+        const int c = (int)((unsigned)i % nvec) * CV;
         float g[CV], yy[CV], zz[CV], k1[CV], k2[CV], k3[CV];
         VecT<T, CV>::load(dy + i * CV, g);
         VecT<T, CV>::load(y + i * CV, yy);
@@ -567,8 +567,9 @@ extern "C" int effdet_colreduce_blocks(size_t rows, int C, int dtype) {
     const int CV = dtype == EFFDET_BF16 ? 8 : 4;
     int nvec = C / CV; if (nvec < 1) nvec = 1;
     int PY = 256 / nvec; if (PY < 1) PY = 1;
-    size_t rpb = (size_t)PY * 16;
-    while (rpb > (size_t)PY && cdiv(rows, rpb) < (unsigned)kNumSMs * 2) rpb >>= 1;
+    // up to 64 rows per thread (fewer partial rows for the finalize kernels), but at least ~6 blocks per SM
+    size_t rpb = (size_t)PY * 64;
+    while (rpb > (size_t)PY && cdiv(rows, rpb) < (unsigned)kNumSMs * 6) rpb >>= 1;
     return (int)cdiv(rows, rpb);
 }
 
@@ -617,6 +618,7 @@ extern "C" int effdet_bn_train_stats(const void *z, size_t rows, int C, const fl
 extern "C" int effdet_scale_shift_act(const void *z, const float *scale, const float *shift, void *y,
                                       size_t rows, int C, int act, int dtype, void *stream) {
     EFFDET_REQUIRE(z && scale && shift && y && C > 0 && C % 8 == 0, "bad arguments");
+    EFFDET_REQUIRE(rows * (size_t)C / 4 < 0xffffffffull, "tensor too large");
     if (rows == 0) return EFFDET_OK;
     cudaStream_t st = as_stream(stream);
     DISPATCH_T(dtype,

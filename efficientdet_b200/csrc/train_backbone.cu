@@ -44,16 +44,6 @@ template <int CV> __device__ __forceinline__ void ldv(const float *p, float *v) 
     }
 }
 
-// derivative of the activation applied to u = BN(z), as a factor on the incoming gradient
-__device__ __forceinline__ float act_grad(float u, int act) {
-    if (act == EFFDET_ACT_RELU) return u > 0.f ? 1.f : 0.f;
-    if (act == EFFDET_ACT_SWISH) {
-        const float s = 1.f / (1.f + __expf(-u));
-        return s * (1.f + u * (1.f - s));
-    }
-    return 1.f;
-}
-
 // ------------------------------------------------------------------ BN + activation backward
 // u = z*a + b with a = gamma*invstd, b = beta - mean*a (training) or the folded inference scale/shift.
 // pass 1: partial[blk][0][c] = sum dy*act'(u), partial[blk][1][c] = sum dy*act'(u)*xhat
@@ -78,7 +68,7 @@ __global__ void bn_act_bwd_reduce_kernel(const T *__restrict__ z, const T *__res
         VecB<T, CV>::load(dy + r * C + c, g);
 #pragma unroll
         for (int k = 0; k < CV; ++k) {
-            const float gm = g[k] * act_grad(zz[k] * a[k] + b[k], act);
+            const float gm = g[k] * act_grad_io<T>(fmaf(zz[k], a[k], b[k]), act);
             s1[k] += gm;
             s2[k] = fmaf(gm, (zz[k] - mu[k]) * is[k], s2[k]);
         }
@@ -127,9 +117,9 @@ __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ z, const float *__restrict__ ua,
                         const float *__restrict__ ub, const float *__restrict__ k123, T *__restrict__ dz,
                         size_t nvec_total, int C, int act) {
-    const int nvec = C / CV;
+    const unsigned nvec = C / CV;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
-        const int c = (int)(i % nvec) * CV;
+        const int c = (int)((unsigned)i % nvec) * CV;
         float g[CV], zz[CV], a[CV], b[CV], k1[CV], k2[CV], k3[CV];
         VecB<T, CV>::load(dy + i * CV, g);
         VecB<T, CV>::load(z + i * CV, zz);
@@ -137,7 +127,7 @@ bn_act_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ z, const
         ldv<CV>(k123 + c, k1); ldv<CV>(k123 + C + c, k2); ldv<CV>(k123 + 2 * C + c, k3);
 #pragma unroll
         for (int k = 0; k < CV; ++k)
-            g[k] = k1[k] * (g[k] * act_grad(zz[k] * a[k] + b[k], act)) + k2[k] * zz[k] + k3[k];
+            g[k] = k1[k] * (g[k] * act_grad_io<T>(fmaf(zz[k], a[k], b[k]), act)) + k2[k] * zz[k] + k3[k];
         VecB<T, CV>::store(dz + i * CV, g);
     }
 }
@@ -195,81 +185,149 @@ __global__ void se_bwd_reduce_kernel(const T *__restrict__ dyg, const T *__restr
         partial[((size_t)b * gridDim.x + blockIdx.x) * C + i] = t;
     }
 }
-// One block per image: recompute the SE forward from the squeeze sums, back-propagate through
-// sigmoid / FC2 / swish / FC1; per-image weight gradients go to scratch (summed over images later),
-// dmean (B,C) is the gradient of the squeezed mean.
-__global__ void __launch_bounds__(256)
-se_fc_backward_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_hw,
-                      const float *__restrict__ dgate_partial, int dg_blocks, const float *__restrict__ w1,
-                      const float *__restrict__ b1, const float *__restrict__ w2, const float *__restrict__ b2,
-                      int C, int R, float *__restrict__ dmean, float *__restrict__ scratch) {
-    extern __shared__ float sm[];       // mean[C] | ds2[C] | s1[R] | r[R] | ds1[R]
-    float *mean = sm, *ds2 = sm + C, *s1 = ds2 + C, *rr = s1 + R, *ds1 = rr + R;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int c = tid; c < C; c += 256) {
+// SE FC backward in four short, wide phases (the old one-block-per-image kernel spent its time in
+// serial chains of L2 round trips).  Scratch layout (floats), S = B*(C+R):
+//   mean[B][C] | s1[B][R] | rr[B][R] | ds2[B][C] | ds1[B][R] | ds1p[B][nch][R]
+// phase 1 (grid B): squeeze mean, FC1 pre-activation s1 and rr = swish(s1)        (forward recompute)
+__global__ void __launch_bounds__(512)
+se_bwd_phase1_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_hw, const float *__restrict__ w1,
+                     const float *__restrict__ b1, int C, int R, float *__restrict__ mean_o,
+                     float *__restrict__ s1_o, float *__restrict__ rr_o) {
+    extern __shared__ float sm[];       // mean[C] | part[512]
+    float *mean = sm, *part = sm + C;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int c = tid; c < C; c += 512) {
         const float *src = se_sum + (size_t)b * se_blocks * C + c;
         float t = 0.f;
         for (int k = 0; k < se_blocks; ++k) t += src[(size_t)k * C];
         mean[c] = t * inv_hw;
+        mean_o[(size_t)b * C + c] = t * inv_hw;
     }
     __syncthreads();
-    for (int j = warp; j < R; j += 8) {
-        float s = 0.f;
-        for (int c = lane; c < C; c += 32) s = fmaf(mean[c], w1[(size_t)c * R + j], s);
+    const int G = 512 / R;              // R <= 512
+    const int j = tid % R, cg = tid / R;
+    if (cg < G) {
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        int c = cg;
+        for (; c + 3 * G < C; c += 4 * G) {
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (lane == 0) { s1[j] = s + b1[j]; rr[j] = (s + b1[j]) / (1.f + __expf(-(s + b1[j]))); }
+            for (int u = 0; u < 4; ++u) s4[u] = fmaf(mean[c + u * G], w1[(size_t)(c + u * G) * R + j], s4[u]);
+        }
+        for (int u = 0; c < C; c += G, ++u) s4[u] = fmaf(mean[c], w1[(size_t)c * R + j], s4[u]);
+        part[cg * R + j] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     }
     __syncthreads();
-    const size_t per = (size_t)2 * C * R + R + C;        // dW1 | dW2 | db1 | db2 per image
-    float *dW1 = scratch + (size_t)b * per, *dW2 = dW1 + (size_t)C * R, *db1 = dW2 + (size_t)R * C, *db2 = db1 + R;
-    for (int c = tid; c < C; c += 256) {
-        float s = b2[c];
-        for (int j = 0; j < R; ++j) s = fmaf(rr[j], w2[(size_t)j * C + c], s);
-        const float g = 1.f / (1.f + __expf(-s));
+    if (tid < R) {
+        float s = b1[tid];
+        for (int g = 0; g < G; ++g) s += part[g * R + tid];
+        s1_o[(size_t)b * R + tid] = s;
+        rr_o[(size_t)b * R + tid] = s / (1.f + __expf(-s));
+    }
+}
+// phase 2 (grid nch x B, 256 threads = 256 channels): gate pre-activation, ds2 = dgate * g (1-g),
+// partial sums over the chunk of ds1_pre[j] = sum_c ds2[c] * w2[j][c]
+__global__ void __launch_bounds__(256)
+se_bwd_phase2_kernel(const float *__restrict__ rr_g, const float *__restrict__ dgate_partial, int dg_blocks,
+                     const float *__restrict__ w2, const float *__restrict__ b2, int C, int R,
+                     float *__restrict__ ds2_o, float *__restrict__ ds1p) {
+    extern __shared__ float sm[];       // rr[R] | red[8][R]
+    float *rr = sm, *red = sm + R;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x * 256 + tid;
+    for (int j = tid; j < R; j += 256) rr[j] = rr_g[(size_t)b * R + j];
+    __syncthreads();
+    float d = 0.f;
+    if (c < C) {
+        float s4[4] = {b2[c], 0.f, 0.f, 0.f};
+        int j = 0;
+        for (; j + 3 < R; j += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s4[u] = fmaf(rr[j + u], w2[(size_t)(j + u) * C + c], s4[u]);
+        }
+        for (; j < R; ++j) s4[0] = fmaf(rr[j], w2[(size_t)j * C + c], s4[0]);
+        const float sg = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        const float g = 1.f / (1.f + __expf(-sg));
         const float *src = dgate_partial + (size_t)b * dg_blocks * C + c;
         float dg = 0.f;
         for (int k = 0; k < dg_blocks; ++k) dg += src[(size_t)k * C];
-        const float d = dg * g * (1.f - g);
-        ds2[c] = d;
-        db2[c] = d;
-        for (int j = 0; j < R; ++j) dW2[(size_t)j * C + c] = rr[j] * d;
+        d = dg * g * (1.f - g);
+        ds2_o[(size_t)b * C + c] = d;
     }
-    __syncthreads();
-    for (int j = warp; j < R; j += 8) {
-        float s = 0.f;
-        for (int c = lane; c < C; c += 32) s = fmaf(ds2[c], w2[(size_t)j * C + c], s);
+    // ds1 partial of this chunk: for each j, sum over the block's 256 channels (warp shuffle + 8 rows)
+    for (int j = 0; j < R; ++j) {
+        float v = c < C ? d * w2[(size_t)j * C + c] : 0.f;
 #pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-        if (lane == 0) {
-            const float u = s1[j], sg = 1.f / (1.f + __expf(-u));
-            ds1[j] = s * sg * (1.f + u * (1.f - sg));
-            db1[j] = ds1[j];
-        }
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp * R + j] = v;
     }
     __syncthreads();
-    for (int c = tid; c < C; c += 256) {
-        float s = 0.f;
-        for (int j = 0; j < R; ++j) {
-            const float d = ds1[j];
-            s = fmaf(w1[(size_t)c * R + j], d, s);
-            dW1[(size_t)c * R + j] = mean[c] * d;
-        }
-        dmean[(size_t)b * C + c] = s;
+    for (int j = tid; j < R; j += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w * R + j];
+        ds1p[((size_t)b * gridDim.x + blockIdx.x) * R + j] = t;
     }
 }
-__global__ void sum_over_images_kernel(const float *__restrict__ scratch, int B, size_t per,
-                                       float *__restrict__ dw1, float *__restrict__ dw2, float *__restrict__ db1,
-                                       float *__restrict__ db2, int C, int R) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= per) return;
-    float t = 0.f;
-    for (int b = 0; b < B; ++b) t += scratch[(size_t)b * per + i];
+// phase 3 (grid nch x B): ds1 = (sum of chunk partials) * swish'(s1); dmean[c] = sum_j w1[c][j] ds1[j]
+__global__ void __launch_bounds__(256)
+se_bwd_phase3_kernel(const float *__restrict__ ds1p, int nch, const float *__restrict__ s1_g,
+                     const float *__restrict__ w1, int C, int R, float *__restrict__ ds1_o,
+                     float *__restrict__ dmean) {
+    extern __shared__ float sm[];       // ds1[R]
+    float *ds1 = sm;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    for (int j = tid; j < R; j += 256) {
+        float t = 0.f;
+        for (int k = 0; k < nch; ++k) t += ds1p[((size_t)b * nch + k) * R + j];
+        const float u = s1_g[(size_t)b * R + j], sg = 1.f / (1.f + __expf(-u));
+        const float v = t * sg * (1.f + u * (1.f - sg));
+        ds1[j] = v;
+        if (blockIdx.x == 0) ds1_o[(size_t)b * R + j] = v;
+    }
+    __syncthreads();
+    const int c = blockIdx.x * 256 + tid;
+    if (c < C) {
+        const float *wr = w1 + (size_t)c * R;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        int j = 0;
+        for (; j + 3 < R; j += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s4[u] = fmaf(wr[j + u], ds1[j + u], s4[u]);
+        }
+        for (; j < R; ++j) s4[0] = fmaf(wr[j], ds1[j], s4[0]);
+        dmean[(size_t)b * C + c] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    }
+}
+// phase 4: weight / bias gradients summed over images in image order (deterministic)
+//   dW1[c][j] = sum_b mean[b][c] ds1[b][j];  dW2[j][c] = sum_b rr[b][j] ds2[b][c];  db1 = sum_b ds1;  db2 = sum_b ds2
+__global__ void __launch_bounds__(256)
+se_bwd_phase4_kernel(const float *__restrict__ mean, const float *__restrict__ rr, const float *__restrict__ ds2,
+                     const float *__restrict__ ds1, int B, int C, int R, float *__restrict__ dw1,
+                     float *__restrict__ dw2, float *__restrict__ db1, float *__restrict__ db2) {
     const size_t cr = (size_t)C * R;
-    if (i < cr) dw1[i] = t;
-    else if (i < 2 * cr) dw2[i - cr] = t;
-    else if (i < 2 * cr + R) db1[i - 2 * cr] = t;
-    else db2[i - 2 * cr - R] = t;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < cr) {
+        const int c = (int)(i / R), j = (int)(i % R);
+        float t = 0.f;
+        for (int b = 0; b < B; ++b) t = fmaf(mean[(size_t)b * C + c], ds1[(size_t)b * R + j], t);
+        dw1[i] = t;
+    } else if (i < 2 * cr) {
+        const size_t k = i - cr;
+        const int j = (int)(k / C), c = (int)(k % C);
+        float t = 0.f;
+        for (int b = 0; b < B; ++b) t = fmaf(rr[(size_t)b * R + j], ds2[(size_t)b * C + c], t);
+        dw2[k] = t;
+    } else if (i < 2 * cr + R) {
+        const int j = (int)(i - 2 * cr);
+        float t = 0.f;
+        for (int b = 0; b < B; ++b) t += ds1[(size_t)b * R + j];
+        db1[j] = t;
+    } else if (i < 2 * cr + R + C) {
+        const int c = (int)(i - 2 * cr - R);
+        float t = 0.f;
+        for (int b = 0; b < B; ++b) t += ds2[(size_t)b * C + c];
+        db2[c] = t;
+    }
 }
 // dy = dyg * gate + dmean * inv_hw
 template <typename T, int CV>
@@ -629,14 +687,26 @@ extern "C" int effdet_se_backward(const void *dyg, const void *y, const float *g
         (se_bwd_reduce_kernel<__nv_bfloat16, 8><<<grid, nvec * PY, sm, st>>>(
             (const __nv_bfloat16 *)dyg, (const __nv_bfloat16 *)y, HW, C, rpb, dg_partial)))
     EFFDET_LAUNCHED();
-    const size_t sm2 = (size_t)(2 * C + 3 * R) * sizeof(float);
-    EFFDET_REQUIRE(sm2 <= 48 * 1024, "C + R too large");
-    se_fc_backward_kernel<<<B, 256, sm2, st>>>(se_sum, se_blocks, 1.f / (float)HW, dg_partial, dg_blocks, w1, b1, w2,
-                                               b2, C, R, dmean, fc_scratch);
-    EFFDET_LAUNCHED();
-    const size_t per = (size_t)2 * C * R + R + C;
-    sum_over_images_kernel<<<cdiv(per, 256), 256, 0, st>>>(fc_scratch, B, per, dw1, dw2, db1, db2, C, R);
-    EFFDET_LAUNCHED();
+    {
+        EFFDET_REQUIRE(R <= 512, "R too large");
+        const int nch = (C + 255) / 256;
+        const size_t per = (size_t)2 * C * R + R + C;
+        EFFDET_REQUIRE((size_t)B * (2 * C + 3 * R + (size_t)nch * R) <= (size_t)B * per, "fc_scratch too small");
+        float *mean_g = fc_scratch, *s1_g = mean_g + (size_t)B * C, *rr_g = s1_g + (size_t)B * R;
+        float *ds2_g = rr_g + (size_t)B * R, *ds1_g = ds2_g + (size_t)B * C, *ds1p = ds1_g + (size_t)B * R;
+        const size_t sm1 = (size_t)(C + 512) * sizeof(float);
+        EFFDET_REQUIRE(sm1 <= 48 * 1024, "C too large");
+        se_bwd_phase1_kernel<<<B, 512, sm1, st>>>(se_sum, se_blocks, 1.f / (float)HW, w1, b1, C, R, mean_g, s1_g, rr_g);
+        EFFDET_LAUNCHED();
+        dim3 g2(nch, B);
+        se_bwd_phase2_kernel<<<g2, 256, (size_t)9 * R * sizeof(float), st>>>(rr_g, dg_partial, dg_blocks, w2, b2, C, R,
+                                                                             ds2_g, ds1p);
+        EFFDET_LAUNCHED();
+        se_bwd_phase3_kernel<<<g2, 256, (size_t)R * sizeof(float), st>>>(ds1p, nch, s1_g, w1, C, R, ds1_g, dmean);
+        EFFDET_LAUNCHED();
+        se_bwd_phase4_kernel<<<cdiv(per, 256), 256, 0, st>>>(mean_g, rr_g, ds2_g, ds1_g, B, C, R, dw1, dw2, db1, db2);
+        EFFDET_LAUNCHED();
+    }
     const size_t n = (size_t)B * HW * C;
     DISPATCH_TB(dtype,
         (se_bwd_finish_kernel<float, 4><<<grid_for_n(n / 4), 256, 0, st>>>(
