@@ -46,6 +46,8 @@ _SIGNATURES = {
                        c_void_p],
     "effdet_stem_conv": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                          c_int, c_int, c_void_p],
+    "effdet_stem_conv_act": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                             c_int, c_int, c_void_p],
     "effdet_conv2d": [c_void_p, c_void_p],
     "effdet_conv_weight_panel": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                  c_void_p],

@@ -351,7 +351,7 @@ static int launch_stem(const float *img, const float *w, const float *scale, con
 }
 
 static int launch_stem_bf16(const float *img, const float *w, const float *scale, const float *shift,
-                            void *out, int B, int H, int W, int C0, cudaStream_t st) {
+                            void *out, int B, int H, int W, int C0, int act, cudaStream_t st) {
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     const int pad_t = ((Ho - 1) * 2 + 3 - H > 0 ? (Ho - 1) * 2 + 3 - H : 0) / 2;
     const int pad_l = ((Wo - 1) * 2 + 3 - W > 0 ? (Wo - 1) * 2 + 3 - W : 0) / 2;
@@ -359,12 +359,18 @@ static int launch_stem_bf16(const float *img, const float *w, const float *scale
     dim3 grid(tx * ty, B);
 #define STEM_T(C)                                                                                          \
     case C:                                                                                                \
-        stem_conv_tiled_kernel<C, EFFDET_ACT_SWISH><<<grid, (C / 8) * (kStemTW / kStemStrip) * kStemTH, 0, st>>>( \
-            img, w, scale, shift, static_cast<__nv_bfloat16 *>(out), H, W, Ho, Wo, pad_t, pad_l, tx);      \
+        if (act == EFFDET_ACT_SWISH)                                                                       \
+            stem_conv_tiled_kernel<C, EFFDET_ACT_SWISH><<<grid, (C / 8) * (kStemTW / kStemStrip) * kStemTH, 0, st>>>( \
+                img, w, scale, shift, static_cast<__nv_bfloat16 *>(out), H, W, Ho, Wo, pad_t, pad_l, tx);  \
+        else                                                                                               \
+            stem_conv_tiled_kernel<C, EFFDET_ACT_NONE><<<grid, (C / 8) * (kStemTW / kStemStrip) * kStemTH, 0, st>>>( \
+                img, w, scale, shift, static_cast<__nv_bfloat16 *>(out), H, W, Ho, Wo, pad_t, pad_l, tx);  \
         break;
     switch (C0) {
         STEM_T(32) STEM_T(40) STEM_T(48) STEM_T(56) STEM_T(64)
-        default: return launch_stem<__nv_bfloat16>(img, w, scale, shift, out, B, H, W, C0, st);
+        default:
+            if (act != EFFDET_ACT_SWISH) return fail(EFFDET_E_UNSUPPORTED, "effdet_stem_conv_act: %sunsupported C0=%lld", "", C0);
+            return launch_stem<__nv_bfloat16>(img, w, scale, shift, out, B, H, W, C0, st);
     }
 #undef STEM_T
     EFFDET_LAUNCHED();
@@ -379,8 +385,19 @@ extern "C" int effdet_stem_conv(const float *images, const float *kernel, const 
     if (out_dtype == EFFDET_F32)
         return launch_stem<float>(images, kernel, scale, shift, out, B, H, W, C0, as_stream(stream));
     if (out_dtype == EFFDET_BF16)
-        return launch_stem_bf16(images, kernel, scale, shift, out, B, H, W, C0, as_stream(stream));
+        return launch_stem_bf16(images, kernel, scale, shift, out, B, H, W, C0, EFFDET_ACT_SWISH, as_stream(stream));
     return fail(EFFDET_E_INVALID, "effdet_stem_conv: bad dtype%s", "");
+}
+
+/* bf16 stem with a selectable epilogue: act = EFFDET_ACT_SWISH (inference, folded BN in scale/shift) or
+ * EFFDET_ACT_NONE (training: raw convolution output z, scale = 1, shift = 0; BN runs on batch statistics). */
+extern "C" int effdet_stem_conv_act(const float *images, const float *kernel, const float *scale,
+                                    const float *shift, void *out, int B, int H, int W, int C0, int act,
+                                    void *stream) {
+    EFFDET_REQUIRE(images && kernel && scale && shift && out, "null pointer");
+    EFFDET_REQUIRE(B > 0 && H > 0 && W > 0, "bad sizes");
+    EFFDET_REQUIRE(act == EFFDET_ACT_SWISH || act == EFFDET_ACT_NONE, "act must be swish or none");
+    return launch_stem_bf16(images, kernel, scale, shift, out, B, H, W, C0, act, as_stream(stream));
 }
 
 int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream);     // conv_tc.cu

@@ -684,7 +684,14 @@ extern "C" int effdet_colsum(const void *x, size_t rows, int C, int fold, float 
     return EFFDET_OK;
 }
 
+namespace effdet {      // dwconv_tma.cu
+int dw_wgrad_bf16_splits(int B, int H, int W, int C, int stride);
+int dw_wgrad_bf16_tma(const void *x, const void *dz, float *partial, int nsplit, int B, int H, int W, int C, int k,
+                      int stride, cudaStream_t st);
+}
+
 extern "C" int effdet_dw_wgrad_blocks(int B, int H, int W, int C, int dtype) {
+    if (dtype == EFFDET_BF16) return dw_wgrad_bf16_splits(B, H, W, C, 1);
     const int CV = dtype == EFFDET_BF16 ? 8 : 4;
     int nvec = C / CV; if (nvec < 1) nvec = 1;
     int PY = 128 / nvec; if (PY < 1) PY = 1;
@@ -700,6 +707,15 @@ extern "C" int effdet_dw_wgrad(const void *f, const void *dz, int B, int H, int 
     EFFDET_REQUIRE(f && dz && dkernel && partial && B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && nblk > 0,
                    "bad arguments");
     cudaStream_t st = as_stream(stream);
+    if (dtype == EFFDET_BF16) {
+        // TMA-tiled kernel shared with the backbone's depthwise backward (dwconv_tma.cu)
+        EFFDET_REQUIRE(nblk == effdet_dw_wgrad_blocks(B, H, W, C, dtype), "nblk must come from effdet_dw_wgrad_blocks");
+        const int rc = dw_wgrad_bf16_tma(f, dz, partial, nblk, B, H, W, C, 3, 1, st);
+        if (rc) return rc;
+        sum_partials_kernel<<<cdiv((size_t)9 * C * 32, 256), 256, 0, st>>>(partial, nblk, 9 * C, dkernel, 0);
+        EFFDET_LAUNCHED();
+        return EFFDET_OK;
+    }
     const int CV = dtype == EFFDET_BF16 ? 8 : 4;
     const int nvec = C / CV;
     EFFDET_REQUIRE(nvec <= 1024, "C too large");

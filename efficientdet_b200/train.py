@@ -463,7 +463,13 @@ class TrainPlan(engine.Plan):
         ones, zeros = net.const_ones(c0), net.const_zeros(c0)
         # raw conv: identity scale/shift; swish is applied after the batch-norm pass, so the
         # stem kernel's built-in swish cannot be used -> run it through the generic conv (Cin = 3)
-        self.conv([self.images], [z], "stem_conv/kernel", 3, c0, k=3, stride=2, in_dtype=F32, name="stem_conv")
+        if self.dtype == BF16 and c0 in (32, 40, 48, 56, 64):
+            self.add("stem", [self.images], [z],
+                     lambda: _call("effdet_stem_conv_act", self.images.ptr, self.w("stem_conv/kernel").data_ptr(),
+                                   ones.data_ptr(), zeros.data_ptr(), z.ptr, B, S, S, c0, ACT_NONE), "stem_conv",
+                     flops=2 * 27 * B * H * H * c0)
+        else:
+            self.conv([self.images], [z], "stem_conv/kernel", 3, c0, k=3, stride=2, in_dtype=F32, name="stem_conv")
         rec = self._bn_train(z, y, "stem_bn", c0, B * H * H, ACT_SWISH)
         rec.update(kind="stem", z=z, y=y, H=H, c0=c0)
         self.bb_tape.append(rec)

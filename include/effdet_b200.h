@@ -124,6 +124,12 @@ int effdet_bn_fold(const float *gamma, const float *beta, const float *moving_me
 int effdet_stem_conv(const float *images, const float *kernel, const float *scale,
                      const float *shift, void *out, int B, int H, int W, int C0, int out_dtype,
                      void *stream);
+/* Same stem, bf16 output, selectable epilogue: act = EFFDET_ACT_SWISH (as above) or EFFDET_ACT_NONE
+ * (training mode: the raw convolution z with scale = 1 / shift = 0; BatchNormalization then runs on batch
+ * statistics, efficientnet.py:413-423 with trainable BN). */
+int effdet_stem_conv_act(const float *images, const float *kernel, const float *scale, const float *shift,
+                         void *out, int B, int H, int W, int C0, int act, void *stream);
+
 
 /* Dense convolution as implicit GEMM (1x1 or 3x3, stride 1 or 2, TF SAME padding) with fused
  * epilogue  y = act(conv(x * gate) * scale + shift) [* keep[b] + residual].
