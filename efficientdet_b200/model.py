@@ -346,6 +346,43 @@ class Model:
         outs = self.predict_on_batch_device(x)
         return [o.cpu().numpy() for o in outs]
 
+    def predict_generator(self, batches):
+        """keras Model.predict_generator over an iterable of HOST image batches ((B,S,S,3) float32 torch
+        tensors, ideally pinned): the host->device copy of batch i+1 runs on a copy stream while batch i
+        is computed (what the reference gets from keras' generator queue / tf.data prefetch).  Yields
+        the outputs of predict_on_batch (numpy) per batch."""
+        dev = self.net.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._slots = {}
+        cs = self._copy_stream
+
+        def stage(slot, xb):
+            xb = torch.as_tensor(xb)
+            key = (slot, tuple(xb.shape))
+            if key not in self._slots:
+                self._slots[key] = torch.empty(xb.shape, dtype=torch.float32, device=dev)
+            d = self._slots[key]
+            with torch.cuda.stream(cs):
+                d.copy_(xb, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            return d, ev
+        it = iter(batches)
+        first = next(it, None)
+        nxt = stage(0, first) if first is not None else None
+        i = 0
+        while nxt is not None:
+            cur, ev = nxt
+            b = next(it, None)
+            # slot (i+1)%2 was last read by batch i-1, which has completed (its outputs were copied out)
+            nxt = stage((i + 1) % 2, b) if b is not None else None
+            main.wait_event(ev)
+            outs = self.predict_on_batch_device([cur])
+            yield [o.cpu().numpy() for o in outs]
+            i += 1
+
     def predict(self, x, batch_size=32, **kw):
         images = x[0] if isinstance(x, (list, tuple)) else x
         rest = list(x[1:]) if isinstance(x, (list, tuple)) else []

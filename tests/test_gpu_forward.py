@@ -251,3 +251,23 @@ def test_prediction_model_end_to_end():
     assert np.array_equal(boxes, ob) and np.array_equal(scores, os_) and np.array_equal(labels, ol)
     assert np.array_equal(b2, ob) and np.array_equal(s2, os_) and np.array_equal(l2, ol)
     assert boxes.shape == (2, 300, 4) and labels.dtype == np.int32
+
+
+def test_predict_generator_matches_predict_on_batch():
+    """The prefetching pipeline (host->device copy of batch i+1 on a copy stream while batch i runs)
+    returns, batch by batch, exactly what predict_on_batch returns."""
+    from efficientdet_b200.model import efficientdet
+    from efficientdet_b200.utils.anchors import anchors_for_shape
+    size, classes = 128, 4
+    anchors = anchors_for_shape((size, size))
+    model, pmodel = efficientdet(0, num_classes=classes, image_size=size, score_threshold=0.3,
+                                 drop_connect_rate=0, anchors=anchors, dtype="bf16")
+    perturb_weights(model)
+    rng = np.random.default_rng(3)
+    batches = [rng.standard_normal((3, size, size, 3)).astype(np.float32) for _ in range(5)]
+    want = [pmodel.predict_on_batch([b]) for b in batches]
+    got = list(pmodel.predict_generator(torch.from_numpy(b).pin_memory() for b in batches))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            assert np.array_equal(a, b)

@@ -543,3 +543,51 @@ def test_partial_backbone_freeze_and_stochastic_depth_are_rejected():
     model.compile()
     with pytest.raises(NotImplementedError):
         model.train_on_batch(z(1, 128, 128, 3), [z(1, 3069, 5), z(1, 3069, 4)])
+
+
+def test_fit_prefetched_matches_stepwise_training():
+    """Trainer.fit_prefetched (copy stream + device target assignment + captured graph) produces the same
+    losses, step after step, as train_on_batch with host-computed dense targets (fp32 mode)."""
+    from efficientdet_b200.model import efficientdet
+    from efficientdet_b200.optimizers import SGD
+    from efficientdet_b200.utils.anchors import _pack_annotations, anchors_for_shape
+    from oracle import anchors as oa
+    size, C, B, phi, steps = 128, 4, 2, 0, 3
+    anchors = anchors_for_shape((size, size))
+    rng = np.random.default_rng(11)
+    data = []
+    for s in range(steps):
+        ann = []
+        for _ in range(B):
+            n = int(rng.integers(1, 4))
+            wh = rng.uniform(16, 60, (n, 2)); xy = rng.uniform(0, size - 64, (n, 2))
+            ann.append({"bboxes": np.concatenate([xy, xy + wh], 1).astype(np.float32),
+                        "labels": rng.integers(0, C, n).astype(np.float32)})
+        data.append((rng.standard_normal((B, size, size, 3)).astype(np.float32), ann))
+    losses = {}
+    for mode in ("stepwise", "prefetched"):
+        model = efficientdet(phi, num_classes=C, image_size=size, dtype="fp32", drop_connect_rate=0,
+                             just_training_model=True)
+        perturb_weights(model)
+        model.freeze_backbone()
+        model.compile(optimizer=SGD(lr=0.01, decay=4e-5, momentum=0.9))
+        if mode == "stepwise":
+            out = []
+            for img, ann in data:
+                reg_t, lab_t = oa.anchor_targets_bbox(anchors, [(size, size, 3)] * B, ann, C)
+                tot, l_reg, l_cls = model.train_on_batch(img, [reg_t, lab_t])
+                out.append((l_cls, l_reg))
+        else:
+            tr = model._trainer
+            plan = tr.plan(B, dense=False)
+            anchors_d = torch.from_numpy(anchors).cuda()
+            def gen():
+                for img, ann in data:
+                    gt, gl, cnt, kmax = _pack_annotations(ann)
+                    hw = np.tile(np.array([[float(size), float(size)]]), (B, 1))
+                    yield (torch.from_numpy(img).pin_memory(),
+                           [torch.from_numpy(a).pin_memory() for a in (gt, gl, cnt, hw)], kmax)
+            out = [(float(o[0]), float(o[1])) for o in tr.fit_prefetched(plan, anchors_d, gen())]
+        losses[mode] = out
+    for a, b in zip(losses["stepwise"], losses["prefetched"]):
+        assert abs(a[0] - b[0]) / max(abs(a[0]), 1e-9) < 1e-4 and abs(a[1] - b[1]) / max(abs(a[1]), 1e-9) < 1e-4, losses
