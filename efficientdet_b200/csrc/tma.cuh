@@ -27,17 +27,29 @@ __device__ __forceinline__ bool mbar_try(uint32_t a, uint32_t parity) {
         : "=r"(done) : "r"(a), "r"(parity) : "memory");
     return done != 0;
 }
-// Spinning waiters share the SM's issue slots with the epilogue warps (the busy ones in the
-// HBM-bound layers): back off between probes.
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or
+// ~hint_ns elapse, so a waiting role does not burn issue slots (ncu: the polling loops of the
+// producer / MMA / starved epilogue warps were ~18 % of all executed instructions of the
+// HBM-bound layers, which are issue-limited in the epilogue).
+__device__ __forceinline__ bool mbar_try_suspend(uint32_t a, uint32_t parity, uint32_t hint_ns) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(a), "r"(parity), "r"(hint_ns) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
     if (mbar_try(a, parity)) return;
-    while (!mbar_try(a, parity)) __nanosleep(32);
+    while (!mbar_try_suspend(a, parity, 2000u)) { }
 }
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity, unsigned ns) {
     const uint32_t a = smem_u32(bar);
     if (mbar_try(a, parity)) return;
-    while (!mbar_try(a, parity)) __nanosleep(ns);
+    while (!mbar_try_suspend(a, parity, 4000u)) { }
+    (void)ns;
 }
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0,
                                             int c1, int c2, int c3) {
