@@ -28,7 +28,12 @@ WORKLOADS = {
     "d2_infer_b64": ("infer", 2, 64, 90, "bf16", False),
     "d0_train_b32": ("train", 0, 32, 20, "bf16", False),          # BASELINE configs[1] (frozen backbone)
     "d4_train_b8": ("train", 4, 8, 90, "bf16", False),            # BASELINE configs[3] (nothing frozen)
+    # BASELINE configs[4]: D6, batch 16, weighted BiFPN.  phi=6 is 1408x1408 in the reference
+    # (model.py:29); the config's wording says 1280, so both are runnable
+    "d6_infer_b16": ("infer", 6, 16, 90, "bf16", True),
+    "d6_infer_b16_1280": ("infer", 6, 16, 90, "bf16", True),
 }
+IMAGE_SIZE_OVERRIDE = {"d6_infer_b16_1280": 1280}
 FREEZE_BACKBONE = {"d0_train_b32": True, "d4_train_b8": False}
 DEFAULT_WORKLOAD = "d0_train_b32"   # BASELINE.json configs[1]
 
@@ -110,10 +115,10 @@ def run_ours(args, rank, world):
         return T.bench_train(args, rank, world, phi, B, C, dtype, weighted, dev,
                              freeze_backbone=FREEZE_BACKBONE[args.workload])
 
-    S = [512, 640, 768, 896, 1024, 1280, 1408][phi]
+    S = IMAGE_SIZE_OVERRIDE.get(args.workload, [512, 640, 768, 896, 1024, 1280, 1408][phi])
     anchors = anchors_for_shape((S, S))
     model, pmodel = efficientdet(phi, num_classes=C, weighted_bifpn=weighted, dtype=dtype,
-                                 anchors=anchors, drop_connect_rate=0, seed=2024 + rank)
+                                 anchors=anchors, drop_connect_rate=0, seed=2024 + rank, image_size=S)
     net = model.net
     plan = net.plan(B)
     n_sets = max(2, min(8, int(400e6 // (B * S * S * 12)) + 1))      # > L2 (126 MB) of inputs in rotation
@@ -300,7 +305,7 @@ def run_reference(args, rank, world):
     import numpy as np
     import torch
     kind, phi, B, C, dtype, weighted = WORKLOADS[args.workload]
-    S = [512, 640, 768, 896, 1024, 1280, 1408][phi]
+    S = IMAGE_SIZE_OVERRIDE.get(args.workload, [512, 640, 768, 896, 1024, 1280, 1408][phi])
     from oracle import graph, tail, anchors as oa
     torch.set_num_threads(os.cpu_count())
     if kind == "train":
