@@ -389,26 +389,43 @@ class Plan:
         else:
             self.graph.replay()
 
-    def profile(self, iters=5):
-        """Per-launch device times (CUDA events on the launching stream, eager -- not the graph).
-        -> list of dicts {name, kind, ms, bytes, flops}."""
+    def profile(self, iters=3, repeat=8):
+        """Per-launch device times -> list of dicts {name, kind, ms, bytes, flops}.
+        Every launch is captured `repeat` times back to back into its own small CUDA graph and the
+        graph is replayed between two CUDA events on the launching stream: the interval holds only
+        device time (kernel + the inter-node gap it also has inside the plan's graph), not the host
+        work of building descriptors / tensor maps, which an eager event pair around a 3-microsecond
+        kernel would mostly measure.  Large launches stream more bytes than L2 holds; small ones
+        are L2-resident here as they are in the real step (their producer just wrote their input)."""
         stream = torch.cuda.current_stream(self.dev)
-        sp = stream.cuda_stream
+        for op in self.ops:                      # warm (kernel attributes, lazy allocations)
+            op.fn(stream.cuda_stream)
+        torch.cuda.synchronize(self.dev)
+        graphs = []
+        side = torch.cuda.Stream(self.dev)
         for op in self.ops:
-            op.fn(sp)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                sp = torch.cuda.current_stream(self.dev).cuda_stream
+                for _ in range(repeat):
+                    op.fn(sp)
+            graphs.append(g)
         acc = [0.0] * len(self.ops)
+        for g in graphs:
+            g.replay()
+        torch.cuda.synchronize(self.dev)
         for _ in range(iters):
             evs = []
-            for op in self.ops:
+            for g in graphs:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream)
-                op.fn(sp)
+                g.replay()
                 b.record(stream)
                 evs.append((a, b))
             torch.cuda.synchronize(self.dev)
             for i, (a, b) in enumerate(evs):
                 acc[i] += a.elapsed_time(b)
-        return [dict(name=op.name, kind=op.kind, ms=acc[i] / iters, bytes=op.nbytes, flops=op.flops)
+        return [dict(name=op.name, kind=op.kind, ms=acc[i] / (iters * repeat), bytes=op.nbytes, flops=op.flops)
                 for i, op in enumerate(self.ops)]
 
     def forward(self, images):
