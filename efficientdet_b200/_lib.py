@@ -142,7 +142,7 @@ class WgradDesc(ctypes.Structure):
         ("B", c_int), ("Cin", c_int), ("Cout", c_int), ("kh", c_int), ("kw", c_int),
         ("stride", c_int),
         ("dweight", c_void_p), ("partial", c_void_p), ("n_splits", c_int), ("accumulate", c_int),
-        ("x_dtype", c_int), ("dz_dtype", c_int),
+        ("x_dtype", c_int), ("dz_dtype", c_int), ("dbias", c_void_p),
     ]
 
 

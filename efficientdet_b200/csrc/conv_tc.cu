@@ -539,6 +539,7 @@ struct alignas(64) WgTcParams {
     int n_groups, B, Cin, Cout, ksize, m_tiles, block_n, stages, tmem_cols;
     int pair_taps;       // Cin <= 64: the two 64-channel halves of the M = 128 tile hold two different taps
     float *partial;
+    float *bias_partial; // [split][Cout] or NULL: the spare half of the last pair multiplies ones -> sum of dz
 };
 
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
@@ -582,6 +583,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
     const int n0 = blockIdx.z * p.block_n;
     const int ky = tap / p.ksize, kx = tap - ky * p.ksize, pad = p.ksize / 2;
     const int ky2 = tap2 / p.ksize, kx2 = tap2 - ky2 * p.ksize;
+    // last pair of an odd tap count: its second half is free.  With a bias gradient requested it holds
+    // bf16 ones (written once, never touched by TMA), so accumulator rows 64..127 = sum over pixels of dz.
+    const bool ones_half = p.pair_taps && p.bias_partial && tap + 1 >= taps_all;
     const int num_k = t_end - t_begin;
 
     if (threadIdx.x == 0) {
@@ -590,6 +594,14 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (ones_half) {
+        for (int s = 0; s < p.stages; ++s) {
+            uint4 *dst = reinterpret_cast<uint4 *>(sA + (size_t)s * a_bytes + kATileBytes);
+            for (int i = threadIdx.x; i < kATileBytes / 16; i += blockDim.x)
+                dst[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+        }
+        fence_proxy_async();              // generic writes -> visible to the tensor core's async proxy
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -604,10 +616,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
                 const int tx = t % G.tiles_x; t /= G.tiles_x;
                 const int ty = t % G.tiles_y; t /= G.tiles_y;
                 const int x0 = tx * G.Wt, y0 = ty * G.Ht, b0 = t * G.Bt;
-                mbar_expect_tx(&full[s], (uint32_t)(a_bytes + b_bytes));
+                mbar_expect_tx(&full[s], (uint32_t)(a_bytes + b_bytes - (ones_half ? kATileBytes : 0)));
                 uint8_t *a = sA + (size_t)s * a_bytes, *b = sB + (size_t)s * b_bytes;
                 tma_load_4d(a, &p.x_map[gi], &full[s], ci0, x0 + kx - pad, y0 + ky - pad, b0);
-                if (p.pair_taps) tma_load_4d(a + kATileBytes, &p.x_map[gi], &full[s], 0, x0 + kx2 - pad, y0 + ky2 - pad, b0);
+                if (ones_half) { }
+                else if (p.pair_taps) tma_load_4d(a + kATileBytes, &p.x_map[gi], &full[s], 0, x0 + kx2 - pad, y0 + ky2 - pad, b0);
                 else tma_load_4d(a + kATileBytes, &p.x_map[gi], &full[s], ci0 + 64, x0 + kx - pad, y0 + ky - pad, b0);
                 for (int j = 0; j < n_boxes; ++j)
                     tma_load_4d(b + (size_t)j * kATileBytes, &p.z_map[gi], &full[s], n0 + 64 * j, x0, y0, b0);
@@ -655,6 +668,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
                 for (int j = 0; j < 32; ++j)
                     if (j < nv) o[j] = num_k > 0 ? __uint_as_float(r[j]) : 0.f;
             }
+            if (ones_half && row == 64) {
+                float *o = p.bias_partial + (size_t)blockIdx.x * p.Cout + n0 + c0;
+                const int nv = min(32, p.Cout - (n0 + c0));
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < nv) o[j] = num_k > 0 ? __uint_as_float(r[j]) : 0.f;
+            }
         }
     }
     tc_fence_before();
@@ -666,12 +686,20 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
 }
 
 __global__ void wgrad_tc_reduce_kernel(const float *__restrict__ partial, int nsplit, size_t n,
-                                       float *__restrict__ out, int accumulate) {
+                                       float *__restrict__ out, int accumulate,
+                                       const float *__restrict__ bias_partial, int n_bias,
+                                       float *__restrict__ dbias) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float t = 0.f;
-    for (int s = 0; s < nsplit; ++s) t += partial[(size_t)s * n + i];
-    out[i] = accumulate ? out[i] + t : t;
+    if (i < n) {
+        float t = 0.f;
+        for (int s = 0; s < nsplit; ++s) t += partial[(size_t)s * n + i];
+        out[i] = accumulate ? out[i] + t : t;
+    } else if (i < n + (size_t)n_bias) {
+        const size_t j = i - n;
+        float t = 0.f;
+        for (int s = 0; s < nsplit; ++s) t += bias_partial[(size_t)s * n_bias + j];
+        dbias[j] = t;
+    }
 }
 
 // picks (Wt, Ht, Bt) with Wt*Ht*Bt == 128 minimising the number of tiles
@@ -898,6 +926,10 @@ static int wg_tc_plan(const effdet_wgrad_desc *d, int *tiles_per_split_out, int 
     return splits;
 }
 
+extern "C" int effdet_conv_wgrad_tc_fuses_bias(const effdet_wgrad_desc *d) {
+    return d && d->Cin <= 64 && d->kh == d->kw && ((d->kh * d->kw) & 1) && d->kh * d->kw > 1;
+}
+
 extern "C" int effdet_conv_wgrad_tc_splits(const effdet_wgrad_desc *d) {
     if (!d || d->n_groups < 1 || d->n_groups > kTcMaxGroups) return 0;
     int tps, nt[kTcMaxGroups], Wt[kTcMaxGroups], Ht[kTcMaxGroups], Bt[kTcMaxGroups], bn, mt;
@@ -923,7 +955,9 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
     EFFDET_REQUIRE(splits == d->n_splits, "n_splits must be effdet_conv_wgrad_tc_splits()");
     p.n_groups = d->n_groups; p.B = d->B; p.Cin = d->Cin; p.Cout = d->Cout; p.ksize = d->kh;
     p.m_tiles = mt; p.block_n = bn; p.partial = d->partial;
+    p.bias_partial = d->dbias ? d->partial + (size_t)splits * d->kh * d->kw * d->Cin * d->Cout : nullptr;
     p.pair_taps = (d->Cin <= 64 && d->kh * d->kw > 1) ? 1 : 0;
+    EFFDET_REQUIRE(!d->dbias || effdet_conv_wgrad_tc_fuses_bias(d), "dbias only when effdet_conv_wgrad_tc_fuses_bias()");
     p.tmem_cols = bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
     const int stage_bytes = 2 * kATileBytes + (bn / 64) * kATileBytes;
     int stages = (200 * 1024) / stage_bytes;
@@ -975,7 +1009,9 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
     conv_wgrad_tc_kernel<<<grid, 192, smem, st>>>(p);
     EFFDET_LAUNCHED();
     const size_t n = (size_t)taps * d->Cin * d->Cout;
-    wgrad_tc_reduce_kernel<<<cdiv(n, 256), 256, 0, st>>>(d->partial, z, n, d->dweight, d->accumulate);
+    const int n_bias = d->dbias ? d->Cout : 0;
+    wgrad_tc_reduce_kernel<<<cdiv(n + n_bias, 256), 256, 0, st>>>(d->partial, z, n, d->dweight, d->accumulate,
+                                                                 p.bias_partial, n_bias, d->dbias);
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }

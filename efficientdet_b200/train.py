@@ -236,8 +236,14 @@ class TrainPlan(engine.Plan):
                                cout), key + "_T")
         return wt
 
-    def _wgrad_tc(self, xs, dzs, key, cin, cout, k, dz_ld=None, name=""):
-        """bf16 operands, stride 1: tcgen05 weight gradient."""
+    def wgrad_fuses_bias(self, cin, k):
+        """True when the tensor-core weight gradient of a (k x k, cin -> *) convolution also produces the
+        bias gradient (effdet_conv_wgrad_tc_fuses_bias)."""
+        return bool(self.net.use_tensor_cores and self.dtype == BF16 and cin <= 64 and cin % 8 == 0 and k == 3)
+
+    def _wgrad_tc(self, xs, dzs, key, cin, cout, k, dz_ld=None, name="", bias_key=None):
+        """bf16 operands, stride 1: tcgen05 weight gradient (+ the bias gradient when bias_key is given
+        and the kernel can fuse it)."""
         lib = _lib.load()
         n = len(xs)
         d = _lib.WgradDesc()
@@ -247,13 +253,18 @@ class TrainPlan(engine.Plan):
             d.dz_ld[i] = dz_ld if dz_ld else 0
         d.B, d.Cin, d.Cout, d.kh, d.kw, d.stride = self.B, cin, cout, k, k, 1
         nsplit = lib.effdet_conv_wgrad_tc_splits(ctypes.byref(d))
-        part = self._scratch(nsplit * k * k * cin * cout, key + "_wg_partial")
+        if bias_key is not None:
+            assert lib.effdet_conv_wgrad_tc_fuses_bias(ctypes.byref(d))
+        part = self._scratch(nsplit * (k * k * cin * cout + (cout if bias_key is not None else 0)),
+                             key + "_wg_partial")
         gw = self.gw(key)
+        gb = self.gw(bias_key) if bias_key is not None else None
 
         def make():
             for i in range(n):
                 d.x[i], d.dz[i] = xs[i].ptr, dzs[i].ptr
             d.dweight, d.partial, d.n_splits, d.accumulate = gw.data_ptr(), part.ptr, nsplit, 0
+            d.dbias = gb.data_ptr() if gb is not None else None
             d.x_dtype = d.dz_dtype = BF16
             self._keepalive.append(d)
             return _call("effdet_conv_wgrad_tc", ctypes.byref(d))
@@ -262,10 +273,11 @@ class TrainPlan(engine.Plan):
                            sum(v.nbytes for v in xs) + sum(v.nbytes for v in dzs), flops))
 
     def _wgrad(self, xs, dzs, key, cin, cout, k, stride, dz_ld=None, dz_bs=None, dz_off=None,
-               dz_dtype=None, name=""):
+               dz_dtype=None, name="", bias_key=None):
         if (self.net.use_tensor_cores and self.dtype == BF16 and stride == 1 and cin % 8 == 0
                 and dz_off is None and (dz_dtype is None or dz_dtype == BF16)):
-            return self._wgrad_tc(xs, dzs, key, cin, cout, k, name=name)
+            return self._wgrad_tc(xs, dzs, key, cin, cout, k, name=name, bias_key=bias_key)
+        assert bias_key is None
         lib = _lib.load()
         n = len(xs)
         d = _lib.WgradDesc()
@@ -323,8 +335,10 @@ class TrainPlan(engine.Plan):
             cout = A * per
             dz_final = self.dreg if ht["scope"] == "box_head" else self.dcls
             key = ht["final"]
-            # bias: the concatenated (B,N,per) tensor is a dense (B*N/9, 9*per) matrix
-            self._bias_grad(dz_final, B * N // A, cout, key + "/bias", 0, F32, name=key + "_dbias")
+            fuse_bias = self.use_tc_grads and self.wgrad_fuses_bias(Wd, 3)
+            if not fuse_bias:
+                # bias: the concatenated (B,N,per) tensor is a dense (B*N/9, 9*per) matrix
+                self._bias_grad(dz_final, B * N // A, cout, key + "/bias", 0, F32, name=key + "_dbias")
             offs = [int(o) * per * 4 for o in lvl_off]
             layers = ht["layers"]
             targets = ht["xs"]
@@ -332,7 +346,8 @@ class TrainPlan(engine.Plan):
             if self.use_tc_grads:
                 lv = self.lvl_dreg if ht["scope"] == "box_head" else self.lvl_dcls
                 cpad = self.cpad_reg if ht["scope"] == "box_head" else self.cpad_cls
-                self._wgrad_tc(ht["xs"], lv, key + "/kernel", Wd, cout, 3, dz_ld=cpad, name=key + "_wgrad")
+                self._wgrad_tc(ht["xs"], lv, key + "/kernel", Wd, cout, 3, dz_ld=cpad, name=key + "_wgrad",
+                               bias_key=key + "/bias" if fuse_bias else None)
                 wt = self._scratch(4, key + "_unused_T")
                 # data gradient: K = padded channel count of the level buffers (padding is zero)
                 self._dgrad_tc_padded(lv, key + "/kernel", cpad, cout, Wd, [g for g, _ in gvals], targets,
@@ -351,11 +366,14 @@ class TrainPlan(engine.Plan):
             for li in range(len(layers) - 1, -1, -1):
                 L = layers[li]
                 dzs = [self.gvals[id(y)] for y in L["ys"]]
-                for l, dz in enumerate(dzs):
-                    rows = B * dz.shape[1] * dz.shape[2]
-                    self._bias_grad(dz, rows, Wd, L["name"] + "/bias", 0 if l == 0 else 1, self.dtype,
-                                    name=L["name"] + "_dbias")
-                self._wgrad(L["xs"], dzs, L["name"] + "/kernel", Wd, Wd, 3, 1, name=L["name"] + "_wgrad")
+                fuse_l = self.wgrad_fuses_bias(Wd, 3)       # bias gradient comes out of the wgrad launch
+                if not fuse_l:
+                    for l, dz in enumerate(dzs):
+                        rows = B * dz.shape[1] * dz.shape[2]
+                        self._bias_grad(dz, rows, Wd, L["name"] + "/bias", 0 if l == 0 else 1, self.dtype,
+                                        name=L["name"] + "_dbias")
+                self._wgrad(L["xs"], dzs, L["name"] + "/kernel", Wd, Wd, 3, 1, name=L["name"] + "_wgrad",
+                            bias_key=L["name"] + "/bias" if fuse_l else None)
                 wt = self._transposed_weight(L["name"] + "/kernel", 9, Wd, Wd)
                 targets = L["xs"]
                 gv = [self.grad_of(t) for t in targets]

@@ -304,6 +304,11 @@ typedef struct effdet_wgrad_desc {
     int n_splits;
     int accumulate;
     int x_dtype, dz_dtype;
+    /* effdet_conv_wgrad_tc only, optional: bias gradient dbias[Cout] = sum over pixels of dz, produced by
+     * the same launch when effdet_conv_wgrad_tc_fuses_bias(desc) != 0 (3x3, Cin <= 64: the spare half of
+     * the last tap pair's M tile multiplies a block of ones).  partial then needs n_splits * Cout more
+     * floats.  Ignored (must be NULL) otherwise. */
+    float *dbias;
 } effdet_wgrad_desc;
 int effdet_conv_wgrad_splits(const effdet_wgrad_desc *desc);
 int effdet_conv_wgrad(const effdet_wgrad_desc *desc, void *stream);
@@ -311,6 +316,7 @@ int effdet_conv_wgrad(const effdet_wgrad_desc *desc, void *stream);
  * k in {1,3}: x dense (B,H,W,Cin), dz (B,H,W,dz_ld) bf16 with the first Cout channels used.
  * partial: effdet_conv_wgrad_tc_splits(desc) * kh*kw*Cin*Cout floats. */
 int effdet_conv_wgrad_tc_splits(const effdet_wgrad_desc *desc);
+int effdet_conv_wgrad_tc_fuses_bias(const effdet_wgrad_desc *desc);
 int effdet_conv_wgrad_tc(const effdet_wgrad_desc *desc, void *stream);
 /* Data gradient of a strided (stride 2) 1x1/3x3 SAME convolution; weight is the forward HWIO
  * kernel.  Stride-1 data gradients use effdet_conv2d on effdet_conv_weight_transpose'd weights. */

@@ -217,9 +217,17 @@ def test_conv_wgrad_tc(k, cin, cout, ldz, sizes, B):
     d.x_dtype = d.dz_dtype = _lib.BF16
     ns = lib.effdet_conv_wgrad_tc_splits(ctypes.byref(d))
     assert ns > 0
-    part = torch.full((ns * k * k * cin * cout,), float("nan"), device="cuda")
+    fuse_bias = bool(lib.effdet_conv_wgrad_tc_fuses_bias(ctypes.byref(d)))
+    assert fuse_bias == (k == 3 and cin <= 64)
+    part = torch.full((ns * (k * k * cin * cout + (cout if fuse_bias else 0)),), float("nan"), device="cuda")
     out = torch.full((k, k, cin, cout), float("nan"), device="cuda")
+    dbias = torch.full((cout,), float("nan"), device="cuda")
     d.dweight, d.partial, d.n_splits, d.accumulate = out.data_ptr(), part.data_ptr(), ns, 0
+    d.dbias = dbias.data_ptr() if fuse_bias else None
     _lib.call("effdet_conv_wgrad_tc", ctypes.byref(d), _lib.stream_ptr())
     torch.cuda.synchronize()
     assert rel_err(out.cpu().numpy(), w.grad.numpy()) < 1e-4
+    if fuse_bias:
+        # bias gradient from the same launch (ones block in the spare half of the last tap pair)
+        want = sum(keep[2 * i + 1][..., :cout].double().sum((0, 1, 2)) for i in range(len(sizes))).cpu().numpy()
+        assert rel_err(dbias.cpu().numpy(), want) < 1e-4
