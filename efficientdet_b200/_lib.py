@@ -68,6 +68,9 @@ _SIGNATURES = {
     "effdet_bn_train_stats": [c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_float, c_float,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int, c_int, c_void_p],
+    "effdet_dwconv_bn_stats": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                               c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "effdet_scale_shift_act": [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int,
                                c_int, c_void_p],
     "effdet_bn_relu_backward": [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p,

@@ -562,7 +562,7 @@ static int launch_dw(const void *x, const float *w, const float *scale, const fl
 
 // dwconv_tma.cu: TMA-fed persistent kernel (bf16)
 int dwconv_bf16_tma(const void *x, const float *w, const float *scale, const float *shift, void *y, float *se_sum,
-                    int B, int H, int W, int C, int k, int stride, int act, cudaStream_t st);
+                    int B, int H, int W, int C, int k, int stride, int act, cudaStream_t st, float *stats = nullptr);
 int dwconv_bf16_tma_se_blocks(int H, int W, int stride);
 
 }  // namespace effdet

@@ -28,7 +28,9 @@ struct alignas(64) DwTmaParams {
     CUtensorMap w_map;                     // (C, K*K) f32,      box (CB, K*K)
     const float *scale, *shift;
     __nv_bfloat16 *y;
-    float *se_sum;
+    float *se_sum;                         // [image][tile][C] sums of the outputs (SE squeeze), or NULL
+    float *stats;                          // [image*tile][2][C] sum / sum of squares of the outputs (BN batch
+                                           // statistics of the following BatchNormalization), or NULL
     int Ho, Wo, C, pad_t, pad_l, tiles_x, tiles_y, cblocks, total_tiles;
 };
 
@@ -57,7 +59,7 @@ template <int K, int S, int CP> struct DwCfg {
     static constexpr int IN_PAD = ((IN_BYTES + 127) / 128) * 128;       // TMA destinations are 128-byte aligned
     static constexpr int W_BYTES = K * K * CB * 4;
     static constexpr int STAGE_BYTES = ((IN_PAD + W_BYTES + 127) / 128) * 128;
-    static constexpr size_t SMEM = 2 * (size_t)STAGE_BYTES + 2 * 8 * CB * 4 + 64 + 128;
+    static constexpr size_t SMEM = 2 * (size_t)STAGE_BYTES + 2 * 2 * 8 * CB * 4 + 64 + 128;
 };
 
 template <int K, int S, int CP, int ACT>
@@ -68,8 +70,8 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
     extern __shared__ uint8_t dsm_raw[];
     // pointer arithmetic on the __shared__ array (not through uintptr_t) keeps LDS/STS addressing
     uint8_t *dsm = dsm_raw + ((128u - (smem_u32(dsm_raw) & 127u)) & 127u);
-    float *sRed = reinterpret_cast<float *>(dsm + 2 * Cfg::STAGE_BYTES);      // [2][8][CB]
-    uint64_t *full = reinterpret_cast<uint64_t *>(sRed + 2 * 8 * CB);
+    float *sRed = reinterpret_cast<float *>(dsm + 2 * Cfg::STAGE_BYTES);      // [2 parities][2 moments][8][CB]
+    uint64_t *full = reinterpret_cast<uint64_t *>(sRed + 2 * 2 * 8 * CB);
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -119,7 +121,7 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
 #pragma unroll
         for (int i = 0; i < K * K; ++i) wk[i] = *reinterpret_cast<const float2 *>(sW + i * CB + pair * 2);
 
-        float2 tot = make_float2(0.f, 0.f);
+        float2 tot = make_float2(0.f, 0.f), tot2 = make_float2(0.f, 0.f);
 #pragma unroll 1
         for (int pass = 0; pass < Cfg::PASSES; ++pass) {
             const int rt = pass * 8 + slot;
@@ -167,21 +169,26 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
                                 z.x = fmaxf(z.x, 0.f); z.y = fmaxf(z.y, 0.f);
                             }
                             tot.x += z.x; tot.y += z.y;
+                            tot2 = __ffma2_rn(z, z, tot2);
                             *reinterpret_cast<__nv_bfloat162 *>(yrow + (size_t)ox * p.C) = __floats2bfloat162_rn(z.x, z.y);
                         }
                     }
                 }
             }
         }
-        if (p.se_sum) {
-            float *red = sRed + (size_t)(it & 1) * 8 * CB;
+        if (p.se_sum || p.stats) {
+            float *red = sRed + (size_t)(it & 1) * 2 * 8 * CB;
             *reinterpret_cast<float2 *>(red + slot * CB + pair * 2) = tot;
+            if (p.stats) *reinterpret_cast<float2 *>(red + (8 + slot) * CB + pair * 2) = tot2;
             __syncthreads();
-            if (tid < CB && cb * CB + tid < p.C) {
+            const int moment = tid / CB, ch = tid - moment * CB;        // NT = 4 * CB threads
+            if (moment < (p.stats ? 2 : 1) && cb * CB + ch < p.C) {
                 float s = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) s += red[w * CB + tid];
-                p.se_sum[((size_t)b * p.tiles_x * p.tiles_y + (size_t)ty * p.tiles_x + tx) * p.C + cb * CB + tid] = s;
+                for (int w = 0; w < 8; ++w) s += red[(moment * 8 + w) * CB + ch];
+                const size_t row = (size_t)b * p.tiles_x * p.tiles_y + (size_t)ty * p.tiles_x + tx;
+                if (p.stats) p.stats[(row * 2 + moment) * p.C + cb * CB + ch] = s;
+                else p.se_sum[row * p.C + cb * CB + ch] = s;
             }
         } else {
             __syncthreads();        // everyone is done reading this stage before it is refilled
@@ -191,7 +198,7 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
 
 template <int K, int S, int CP>
 static int launch_dw_tma(const void *x, const float *w, const float *scale, const float *shift, void *y,
-                         float *se_sum, int B, int H, int W, int C, int act, cudaStream_t st) {
+                         float *se_sum, float *stats, int B, int H, int W, int C, int act, cudaStream_t st) {
     using Cfg = DwCfg<K, S, CP>;
     EncodeTiledFn encode = get_encode();
     if (!encode) return fail(EFFDET_E_CUDA, "effdet_dwconv: cuTensorMapEncodeTiled unavailable%s", "");
@@ -204,7 +211,7 @@ static int launch_dw_tma(const void *x, const float *w, const float *scale, cons
     p.tiles_x = (Wo + Cfg::TW - 1) / Cfg::TW; p.tiles_y = (Ho + Cfg::TH - 1) / Cfg::TH;
     p.cblocks = (C + Cfg::CB - 1) / Cfg::CB;
     p.total_tiles = p.tiles_x * p.tiles_y * p.cblocks * B;
-    p.scale = scale; p.shift = shift; p.y = static_cast<__nv_bfloat16 *>(y); p.se_sum = se_sum;
+    p.scale = scale; p.shift = shift; p.y = static_cast<__nv_bfloat16 *>(y); p.se_sum = se_sum; p.stats = stats;
     {
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
@@ -427,13 +434,13 @@ int dwconv_bf16_tma_se_blocks(int H, int W, int stride) {
 
 // bf16 entry used by effdet_dwconv (dwconv.cu)
 int dwconv_bf16_tma(const void *x, const float *w, const float *scale, const float *shift, void *y, float *se_sum,
-                    int B, int H, int W, int C, int k, int stride, int act, cudaStream_t st) {
+                    int B, int H, int W, int C, int k, int stride, int act, cudaStream_t st, float *stats) {
     const int cp = pick_cp(C);
 #define DWT_CASE(K_, S_)                                                                                   \
     if (k == K_ && stride == S_) {                                                                         \
-        if (cp == 32) return launch_dw_tma<K_, S_, 32>(x, w, scale, shift, y, se_sum, B, H, W, C, act, st); \
-        if (cp == 24) return launch_dw_tma<K_, S_, 24>(x, w, scale, shift, y, se_sum, B, H, W, C, act, st); \
-        return launch_dw_tma<K_, S_, 16>(x, w, scale, shift, y, se_sum, B, H, W, C, act, st);              \
+        if (cp == 32) return launch_dw_tma<K_, S_, 32>(x, w, scale, shift, y, se_sum, stats, B, H, W, C, act, st); \
+        if (cp == 24) return launch_dw_tma<K_, S_, 24>(x, w, scale, shift, y, se_sum, stats, B, H, W, C, act, st); \
+        return launch_dw_tma<K_, S_, 16>(x, w, scale, shift, y, se_sum, stats, B, H, W, C, act, st);              \
     }
     DWT_CASE(3, 1) DWT_CASE(5, 1) DWT_CASE(3, 2) DWT_CASE(5, 2)
 #undef DWT_CASE

@@ -615,6 +615,36 @@ extern "C" int effdet_bn_train_stats(const void *z, size_t rows, int C, const fl
     return EFFDET_OK;
 }
 
+/* Depthwise conv (raw output z, no activation) + the batch statistics of the BatchNormalization that follows
+ * it, in one pass over the data: the depthwise kernel emits per-tile sums / sums of squares of its outputs
+ * and only the finalize step of effdet_bn_train_stats runs afterwards (model.py:48-68 DepthwiseConvBlock in
+ * training mode).  bf16 only.  partial: 2*C*nblk floats, nblk = B * effdet_dwconv_se_blocks(...). */
+namespace effdet {
+int dwconv_bf16_tma(const void *x, const float *w, const float *scale, const float *shift, void *y, float *se_sum,
+                    int B, int H, int W, int C, int k, int stride, int act, cudaStream_t st, float *stats);
+}
+extern "C" int effdet_dwconv_bn_stats(const void *x, const float *kernel, const float *ones, const float *zeros,
+                                      void *z, int B, int H, int W, int C, int k, int stride, const float *gamma,
+                                      const float *beta, float eps, float momentum, float *moving_mean,
+                                      float *moving_var, float *scale, float *shift, float *save_mean,
+                                      float *save_invstd, float *partial, int nblk, int dtype, void *stream) {
+    EFFDET_REQUIRE(x && kernel && ones && zeros && z && gamma && beta && scale && shift && save_mean && save_invstd &&
+                       partial, "null pointer");
+    EFFDET_REQUIRE(dtype == EFFDET_BF16, "bf16 only");
+    EFFDET_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (k == 3 || k == 5) && (stride == 1 || stride == 2),
+                   "bad sizes");
+    EFFDET_REQUIRE(nblk == B * effdet_dwconv_se_blocks(B, H, W, C, stride, dtype), "nblk must be B * effdet_dwconv_se_blocks()");
+    cudaStream_t st = as_stream(stream);
+    const int rc = dwconv_bf16_tma(x, kernel, ones, zeros, z, nullptr, B, H, W, C, k, stride, EFFDET_ACT_NONE, st, partial);
+    if (rc) return rc;
+    const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
+    bn_train_finalize_kernel<<<cdiv((size_t)C * 32, 256), 256, 0, st>>>(partial, nblk, (double)B * Ho * Wo, gamma, beta,
+                                                                      eps, momentum, moving_mean, moving_var, scale,
+                                                                      shift, save_mean, save_invstd, C);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
 extern "C" int effdet_scale_shift_act(const void *z, const float *scale, const float *shift, void *y,
                                       size_t rows, int C, int act, int dtype, void *stream) {
     EFFDET_REQUIRE(z && scale && shift && y && C > 0 && C % 8 == 0, "bad arguments");

@@ -482,7 +482,7 @@ __global__ void dw_flip_kernel(const float *__restrict__ w, float *__restrict__ 
 
 // dwconv_tma.cu
 int dwconv_bf16_tma(const void *x, const float *w, const float *scale, const float *shift, void *y, float *se_sum,
-                    int B, int H, int W, int C, int k, int stride, int act, cudaStream_t st);
+                    int B, int H, int W, int C, int k, int stride, int act, cudaStream_t st, float *stats = nullptr);
 int dw_wgrad_bf16_splits(int B, int H, int W, int C, int stride);
 int dw_wgrad_bf16_tma(const void *x, const void *dz, float *partial, int nsplit, int B, int H, int W, int C, int k,
                       int stride, cudaStream_t st);

@@ -52,13 +52,42 @@ class TrainPlan(engine.Plan):
     def bn_is_training(self, bn_name):
         return not (self.net.freeze_bn or bn_name in self.net.frozen_layers)
 
-    def _bn_train(self, z, y, bn_name, C, rows, act):
-        """z -> y = act(BN_batch(z)); returns the record needed by the backward pass."""
+    def _bn_train(self, z, y, bn_name, C, rows, act, dw_from=None):
+        """z -> y = act(BN_batch(z)); returns the record needed by the backward pass.
+        dw_from = (f, kernel_key, H): z is the raw 3x3 stride-1 depthwise conv of f, not computed yet --
+        in bf16 mode with a trainable BN the depthwise kernel then also emits the batch statistics."""
         lib = _lib.load()
         is_bifpn = bn_name.startswith("BiFPN_")
         eps = BN_EPS_BIFPN if is_bifpn else BN_EPS_BACKBONE
         mom = BN_MOMENTUM_BIFPN if is_bifpn else BN_MOMENTUM_BACKBONE
         rec = dict(bn=bn_name, C=C, rows=rows, train=self.bn_is_training(bn_name), act=act)
+        if dw_from is not None:
+            f, kkey, H = dw_from
+            B = self.B
+            ones, zeros = self.net.const_ones(C), self.net.const_zeros(C)
+            if rec["train"] and self.dtype == BF16:
+                nblk = B * lib.effdet_dwconv_se_blocks(B, H, H, C, 1, self.dtype)
+                sc, sh = self.fvec(C, bn_name + "/scale_t"), self.fvec(C, bn_name + "/shift_t")
+                mu, iv = self.fvec(C, bn_name + "/mean_t"), self.fvec(C, bn_name + "/invstd_t")
+                part = self._scratch(2 * C * nblk, bn_name + "/partial")
+                w = self.w
+                self.add("dwconv", [f], [z, sc, sh, mu, iv, part],
+                         lambda: _call("effdet_dwconv_bn_stats", f.ptr, w(kkey).data_ptr(), ones.data_ptr(),
+                                       zeros.data_ptr(), z.ptr, B, H, H, C, 3, 1, w(bn_name + "/gamma").data_ptr(),
+                                       w(bn_name + "/beta").data_ptr(), eps, mom,
+                                       w(bn_name + "/moving_mean").data_ptr(),
+                                       w(bn_name + "/moving_variance").data_ptr(), sc.ptr, sh.ptr, mu.ptr, iv.ptr,
+                                       part.ptr, nblk, self.dtype), bn_name[:-3] + "_dconv+stats",
+                         flops=18 * B * H * H * C)
+                self.add("bn_apply", [z, sc, sh], [y],
+                         lambda: _call("effdet_scale_shift_act", z.ptr, sc.ptr, sh.ptr, y.ptr, rows, C, act,
+                                       self.dtype), bn_name + "_apply")
+                rec.update(mean=mu, invstd=iv, nblk=lib.effdet_colreduce_blocks(rows, C, self.dtype), ua=sc, ub=sh)
+                return rec
+            self.add("dwconv", [f], [z],
+                     lambda: _call("effdet_dwconv", f.ptr, self.w(kkey).data_ptr(), ones.data_ptr(),
+                                   zeros.data_ptr(), z.ptr, None, 0, B, H, H, C, 3, 1, ACT_NONE, self.dtype),
+                     bn_name[:-3] + "_dconv", flops=18 * B * H * H * C)
         if rec["train"]:
             nblk = lib.effdet_colreduce_blocks(rows, C, self.dtype)
             sc, sh = self.fvec(C, bn_name + "/scale_t"), self.fvec(C, bn_name + "/shift_t")
@@ -125,12 +154,8 @@ class TrainPlan(engine.Plan):
                  lambda: _call("effdet_resample_fuse", in0.ptr, mode0, in1.ptr,
                                in2.ptr if in2 is not None else None, fwp, 1e-4, f.ptr, B, H, H, C,
                                self.dtype), dw_name + "_fuse")
-        ones, zeros = net.const_ones(C), net.const_zeros(C)
-        self.add("dwconv", [f], [z],
-                 lambda: _call("effdet_dwconv", f.ptr, self.w(dw_name + "_dconv/depthwise_kernel").data_ptr(),
-                               ones.data_ptr(), zeros.data_ptr(), z.ptr, None, 0, B, H, H, C, 3, 1,
-                               ACT_NONE, self.dtype), dw_name + "_dconv", flops=18 * B * H * H * C)
-        rec = self._bn_train(z, y, dw_name + "_bn", C, B * H * H, ACT_RELU)
+        rec = self._bn_train(z, y, dw_name + "_bn", C, B * H * H, ACT_RELU,
+                             dw_from=(f, dw_name + "_dconv/depthwise_kernel", H))
         rec.update(kind="node", in0=in0, mode0=mode0, in1=in1, in2=in2, f=f, z=z, y=y, fuse=fuse_name,
                    name=dw_name, H=H)
         self.tape.append(rec)

@@ -252,6 +252,16 @@ int effdet_bn_train_stats(const void *z, size_t rows, int C, const float *gamma,
                           float eps, float momentum, float *moving_mean, float *moving_var,
                           float *scale, float *shift, float *save_mean, float *save_invstd,
                           float *partial, int nblk, int dtype, void *stream);
+/* Depthwise conv with raw output z (no activation) + the batch statistics of the BatchNormalization that
+ * follows it (model.py:48-68 DepthwiseConvBlock, trainable BN), one pass over the data: the depthwise kernel
+ * emits per-tile sums / sums of squares and only the finalize step of effdet_bn_train_stats runs afterwards.
+ * bf16 only; ones / zeros: C floats each; partial: 2*C*nblk floats, nblk = B * effdet_dwconv_se_blocks(). */
+int effdet_dwconv_bn_stats(const void *x, const float *kernel, const float *ones, const float *zeros, void *z,
+                           int B, int H, int W, int C, int k, int stride, const float *gamma, const float *beta,
+                           float eps, float momentum, float *moving_mean, float *moving_var, float *scale,
+                           float *shift, float *save_mean, float *save_invstd, float *partial, int nblk,
+                           int dtype, void *stream);
+
 /* y = act(z*scale + shift) over a (rows,C) matrix. */
 int effdet_scale_shift_act(const void *z, const float *scale, const float *shift, void *y,
                            size_t rows, int C, int act, int dtype, void *stream);
