@@ -62,7 +62,24 @@ __global__ void bn_act_bwd_reduce_kernel(const T *__restrict__ z, const T *__res
     ldv<CV>(ua + c, a); ldv<CV>(ub + c, b); ldv<CV>(mean + c, mu); ldv<CV>(invstd + c, is);
 #pragma unroll
     for (int k = 0; k < CV; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
-    for (size_t r = r0 + py; r < r1; r += PY) {
+    size_t r = r0 + py;
+    for (; r + PY < r1; r += 2 * PY) {          // two independent rows in flight
+        float zz[CV], g[CV], zz1[CV], g1[CV];
+        VecB<T, CV>::load(z + r * C + c, zz);
+        VecB<T, CV>::load(dy + r * C + c, g);
+        VecB<T, CV>::load(z + (r + PY) * C + c, zz1);
+        VecB<T, CV>::load(dy + (r + PY) * C + c, g1);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) {
+            const float gm = g[k] * act_grad_io<T>(fmaf(zz[k], a[k], b[k]), act);
+            s1[k] += gm;
+            s2[k] = fmaf(gm, (zz[k] - mu[k]) * is[k], s2[k]);
+            const float gm1 = g1[k] * act_grad_io<T>(fmaf(zz1[k], a[k], b[k]), act);
+            s1[k] += gm1;
+            s2[k] = fmaf(gm1, (zz1[k] - mu[k]) * is[k], s2[k]);
+        }
+    }
+    for (; r < r1; r += PY) {
         float zz[CV], g[CV];
         VecB<T, CV>::load(z + r * C + c, zz);
         VecB<T, CV>::load(dy + r * C + c, g);
@@ -112,23 +129,44 @@ __global__ void bn_act_bwd_finalize_kernel(const float *__restrict__ partial, in
     if (dbeta) dbeta[c] = (float)s1;
 }
 // pass 2: dz = k1*(dy*act'(u)) + k2*z + k3
+// block = nvec channel vectors x PY rows; a thread keeps the seven per-channel coefficient vectors of
+// ITS channels in registers and walks rows (the flat-index version re-read them from L1 for every
+// 16-byte vector: 10 extra load instructions per 8 elements, LSU-bound at ~1.5 TB/s).
 template <typename T, int CV>
-__global__ void __launch_bounds__(256)
-bn_act_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ z, const float *__restrict__ ua,
+__global__ void bn_act_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ z, const float *__restrict__ ua,
                         const float *__restrict__ ub, const float *__restrict__ k123, T *__restrict__ dz,
-                        size_t nvec_total, int C, int act) {
-    const unsigned nvec = C / CV;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
-        const int c = (int)((unsigned)i % nvec) * CV;
-        float g[CV], zz[CV], a[CV], b[CV], k1[CV], k2[CV], k3[CV];
-        VecB<T, CV>::load(dy + i * CV, g);
-        VecB<T, CV>::load(z + i * CV, zz);
-        ldv<CV>(ua + c, a); ldv<CV>(ub + c, b);
-        ldv<CV>(k123 + c, k1); ldv<CV>(k123 + C + c, k2); ldv<CV>(k123 + 2 * C + c, k3);
+                        size_t rows, int C, int rows_per_block, int act) {
+    const int nvec = C / CV, PY = blockDim.x / nvec;
+    const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec, c = cv * CV;
+    if (py >= PY) return;
+    float a[CV], b[CV], k1[CV], k2[CV], k3[CV];
+    ldv<CV>(ua + c, a); ldv<CV>(ub + c, b);
+    ldv<CV>(k123 + c, k1); ldv<CV>(k123 + C + c, k2); ldv<CV>(k123 + 2 * C + c, k3);
+    const size_t r0 = (size_t)blockIdx.x * rows_per_block;
+    const size_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+    size_t r = r0 + py;
+    for (; r + PY < r1; r += 2 * PY) {          // two independent rows in flight
+        float g0[CV], z0[CV], g1[CV], z1[CV];
+        VecB<T, CV>::load(dy + r * C + c, g0);
+        VecB<T, CV>::load(z + r * C + c, z0);
+        VecB<T, CV>::load(dy + (r + PY) * C + c, g1);
+        VecB<T, CV>::load(z + (r + PY) * C + c, z1);
+#pragma unroll
+        for (int k = 0; k < CV; ++k) {
+            g0[k] = k1[k] * (g0[k] * act_grad_io<T>(fmaf(z0[k], a[k], b[k]), act)) + k2[k] * z0[k] + k3[k];
+            g1[k] = k1[k] * (g1[k] * act_grad_io<T>(fmaf(z1[k], a[k], b[k]), act)) + k2[k] * z1[k] + k3[k];
+        }
+        VecB<T, CV>::store(dz + r * C + c, g0);
+        VecB<T, CV>::store(dz + (r + PY) * C + c, g1);
+    }
+    for (; r < r1; r += PY) {
+        float g0[CV], z0[CV];
+        VecB<T, CV>::load(dy + r * C + c, g0);
+        VecB<T, CV>::load(z + r * C + c, z0);
 #pragma unroll
         for (int k = 0; k < CV; ++k)
-            g[k] = k1[k] * (g[k] * act_grad_io<T>(fmaf(zz[k], a[k], b[k]), act)) + k2[k] * zz[k] + k3[k];
-        VecB<T, CV>::store(dz + i * CV, g);
+            g0[k] = k1[k] * (g0[k] * act_grad_io<T>(fmaf(z0[k], a[k], b[k]), act)) + k2[k] * z0[k] + k3[k];
+        VecB<T, CV>::store(dz + r * C + c, g0);
     }
 }
 
@@ -605,12 +643,22 @@ extern "C" int effdet_bn_act_backward(const void *dy, const void *z, size_t rows
                                                                             dbeta, C);
         EFFDET_LAUNCHED();
     }
-    DISPATCH_TB(dtype,
-        (bn_act_bwd_apply_kernel<float, 4><<<grid_for_n(rows * C / 4), 256, 0, st>>>(
-            (const float *)dy, (const float *)z, ua, ub, k123, (float *)dz, rows * C / 4, C, act)),
-        (bn_act_bwd_apply_kernel<__nv_bfloat16, 8><<<grid_for_n(rows * C / 8), 256, 0, st>>>(
-            (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)z, ua, ub, k123, (__nv_bfloat16 *)dz, rows * C / 8, C,
-            act)))
+    {
+        const int CVa = dtype == EFFDET_BF16 ? 8 : 4;
+        const int nva = C / CVa;
+        EFFDET_REQUIRE(nva <= 1024, "C too large");
+        int PYa = 256 / nva; if (PYa < 1) PYa = 1;
+        // ~8 blocks per SM, each thread at least 2 rows
+        size_t rpb = (size_t)PYa * 2;
+        while (cdiv(rows, rpb) > (unsigned)kNumSMs * 8) rpb *= 2;
+        const unsigned nb = cdiv(rows, rpb);
+        DISPATCH_TB(dtype,
+            (bn_act_bwd_apply_kernel<float, 4><<<nb, nva * PYa, 0, st>>>(
+                (const float *)dy, (const float *)z, ua, ub, k123, (float *)dz, rows, C, (int)rpb, act)),
+            (bn_act_bwd_apply_kernel<__nv_bfloat16, 8><<<nb, nva * PYa, 0, st>>>(
+                (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)z, ua, ub, k123, (__nv_bfloat16 *)dz, rows, C,
+                (int)rpb, act)))
+    }
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }

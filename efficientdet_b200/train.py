@@ -62,23 +62,25 @@ class TrainPlan(engine.Plan):
         mom = BN_MOMENTUM_BIFPN if is_bifpn else BN_MOMENTUM_BACKBONE
         rec = dict(bn=bn_name, C=C, rows=rows, train=self.bn_is_training(bn_name), act=act)
         if dw_from is not None:
-            f, kkey, H = dw_from
+            f, kkey, H = dw_from[:3]
+            dk, ds = (dw_from[3], dw_from[4]) if len(dw_from) > 3 else (3, 1)
+            dHo = -(-H // ds)
             B = self.B
             ones, zeros = self.net.const_ones(C), self.net.const_zeros(C)
             if rec["train"] and self.dtype == BF16:
-                nblk = B * lib.effdet_dwconv_se_blocks(B, H, H, C, 1, self.dtype)
+                nblk = B * lib.effdet_dwconv_se_blocks(B, H, H, C, ds, self.dtype)
                 sc, sh = self.fvec(C, bn_name + "/scale_t"), self.fvec(C, bn_name + "/shift_t")
                 mu, iv = self.fvec(C, bn_name + "/mean_t"), self.fvec(C, bn_name + "/invstd_t")
                 part = self._scratch(2 * C * nblk, bn_name + "/partial")
                 w = self.w
                 self.add("dwconv", [f], [z, sc, sh, mu, iv, part],
                          lambda: _call("effdet_dwconv_bn_stats", f.ptr, w(kkey).data_ptr(), ones.data_ptr(),
-                                       zeros.data_ptr(), z.ptr, B, H, H, C, 3, 1, w(bn_name + "/gamma").data_ptr(),
+                                       zeros.data_ptr(), z.ptr, B, H, H, C, dk, ds, w(bn_name + "/gamma").data_ptr(),
                                        w(bn_name + "/beta").data_ptr(), eps, mom,
                                        w(bn_name + "/moving_mean").data_ptr(),
                                        w(bn_name + "/moving_variance").data_ptr(), sc.ptr, sh.ptr, mu.ptr, iv.ptr,
                                        part.ptr, nblk, self.dtype), bn_name[:-3] + "_dconv+stats",
-                         flops=18 * B * H * H * C)
+                         flops=2 * dk * dk * B * dHo * dHo * C)
                 self.add("bn_apply", [z, sc, sh], [y],
                          lambda: _call("effdet_scale_shift_act", z.ptr, sc.ptr, sh.ptr, y.ptr, rows, C, act,
                                        self.dtype), bn_name + "_apply")
@@ -86,8 +88,8 @@ class TrainPlan(engine.Plan):
                 return rec
             self.add("dwconv", [f], [z],
                      lambda: _call("effdet_dwconv", f.ptr, self.w(kkey).data_ptr(), ones.data_ptr(),
-                                   zeros.data_ptr(), z.ptr, None, 0, B, H, H, C, 3, 1, ACT_NONE, self.dtype),
-                     bn_name[:-3] + "_dconv", flops=18 * B * H * H * C)
+                                   zeros.data_ptr(), z.ptr, None, 0, B, H, H, C, dk, ds, ACT_NONE, self.dtype),
+                     bn_name[:-3] + "_dconv", flops=2 * dk * dk * B * dHo * dHo * C)
         if rec["train"]:
             nblk = lib.effdet_colreduce_blocks(rows, C, self.dtype)
             sc, sh = self.fvec(C, bn_name + "/scale_t"), self.fvec(C, bn_name + "/shift_t")
@@ -537,13 +539,9 @@ class TrainPlan(engine.Plan):
         Ho = (H + blk.stride - 1) // blk.stride
         z_d = self.val((B, Ho, Ho, cmid), name=p + "dw_z", keep=True)
         y_d = self.val((B, Ho, Ho, cmid), name=p + "dw", keep=True)
-        ones, zeros = net.const_ones(cmid), net.const_zeros(cmid)
-        self.add("dwconv", [xin], [z_d],
-                 lambda: _call("effdet_dwconv", xin.ptr, self.w(p + "dwconv/depthwise_kernel").data_ptr(),
-                               ones.data_ptr(), zeros.data_ptr(), z_d.ptr, None, 0, B, H, H, cmid,
-                               blk.kernel_size, blk.stride, ACT_NONE, self.dtype), p + "dwconv",
-                 flops=2 * blk.kernel_size ** 2 * B * Ho * Ho * cmid)
-        rec["bn_d"] = self._bn_train(z_d, y_d, p + "bn", cmid, B * Ho * Ho, ACT_SWISH)
+        # depthwise conv (raw) + batch statistics of its BN in one pass (bf16), then BN-apply + swish
+        rec["bn_d"] = self._bn_train(z_d, y_d, p + "bn", cmid, B * Ho * Ho, ACT_SWISH,
+                                     dw_from=(xin, p + "dwconv/depthwise_kernel", H, blk.kernel_size, blk.stride))
         HW = Ho * Ho
         nblk = lib.effdet_se_backward_blocks(HW, cmid, self.dtype)
         part = self.val((B, nblk, cmid), F32, name=p + "se_partial", keep=True)
