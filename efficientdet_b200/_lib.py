@@ -78,6 +78,7 @@ _SIGNATURES = {
                                 c_void_p, c_int, c_int, c_void_p],
     "effdet_colsum": [c_void_p, c_size_t, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
                       c_void_p],
+    "effdet_colsum_tail": [c_void_p, c_size_t, c_int, c_int, c_void_p, c_int, c_void_p],
     "effdet_dw_wgrad": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                         c_int, c_void_p],
     "effdet_fuse_backward_input": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_float,

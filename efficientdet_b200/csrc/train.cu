@@ -696,6 +696,27 @@ extern "C" int effdet_bn_relu_backward(const void *dy, const void *y, const void
     return EFFDET_OK;
 }
 
+/* out[c] += sum over rows [row0, row0 + nrows) of x[r][c] for a dense (*, C) matrix: scalar tail of
+ * effdet_colsum for the few rows that do not fill a whole vector-aligned fold. */
+template <typename T>
+__global__ void colsum_tail_kernel(const T *__restrict__ x, size_t row0, int nrows, int C, float *__restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float t = 0.f;
+    for (int r = 0; r < nrows; ++r) t += to_f<T>(x[(row0 + r) * (size_t)C + c]);
+    out[c] += t;
+}
+extern "C" int effdet_colsum_tail(const void *x, size_t row0, int nrows, int C, float *out, int dtype, void *stream) {
+    EFFDET_REQUIRE(x && out && C > 0 && nrows >= 0, "bad arguments");
+    if (nrows == 0) return EFFDET_OK;
+    cudaStream_t st = as_stream(stream);
+    DISPATCH_T(dtype,
+        (colsum_tail_kernel<float><<<cdiv(C, 128), 128, 0, st>>>((const float *)x, row0, nrows, C, out)),
+        (colsum_tail_kernel<__nv_bfloat16><<<cdiv(C, 128), 128, 0, st>>>((const __nv_bfloat16 *)x, row0, nrows, C, out)))
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
 /* column sum of a dense (rows*fold, C/fold) matrix -> out[C/fold] (bias gradients); the caller
  * passes it viewed as (rows, C) with C a multiple of the vector width. */
 extern "C" int effdet_colsum(const void *x, size_t rows, int C, int fold, float *out, int accumulate,

@@ -435,15 +435,32 @@ class Model:
             raise RuntimeError("compile() the model before training")
         return self._trainer.step(x, y)
 
-    def fit(self, x=None, y=None, epochs=1, steps_per_epoch=None, batch_size=None, verbose=0, **kw):
-        """x: iterable of (images, (regression_targets, class_targets)) batches, or arrays."""
+    def fit(self, x=None, y=None, epochs=1, steps_per_epoch=None, batch_size=None, verbose=0, callbacks=None,
+            initial_epoch=0, **kw):
+        """x: iterable of (images, (regression_targets, class_targets)) batches, or arrays.
+        callbacks: keras-style objects with optional set_model / on_epoch_begin / on_epoch_end
+        (utils.lr_schedule.LearningRateScheduler, utils.train.CheckpointSaver; train.py:377-388)."""
+        callbacks = list(callbacks or [])
+        for cb in callbacks:
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
         hist = []
-        for _ in range(epochs):
+        for epoch in range(initial_epoch, epochs):
+            for cb in callbacks:
+                if hasattr(cb, "on_epoch_begin"):
+                    cb.on_epoch_begin(epoch, {})
             it = iter(x) if y is None else iter([(x, y)])
+            last = None
             for step, (xb, yb) in enumerate(it):
                 if steps_per_epoch is not None and step >= steps_per_epoch:
                     break
-                hist.append(self.train_on_batch(xb, yb))
+                last = self.train_on_batch(xb, yb)
+                hist.append(last)
+            logs = {} if last is None else {"loss": last[0], "regression_loss": last[1],
+                                            "classification_loss": last[2]}
+            for cb in callbacks:
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(epoch, logs)
         return hist
 
 

@@ -339,14 +339,18 @@ class TrainPlan(engine.Plan):
         fold = 1
         while (C * fold) % vec:
             fold *= 2
-        assert rows % fold == 0
         prow, pC = rows // fold, C * fold
+        tail = rows - prow * fold            # < fold rows that do not fill a vector-aligned fold
         nblk = lib.effdet_colreduce_blocks(prow, pC, dtype)
         part = self._scratch(2 * pC * nblk, key + "_bg_partial")
         g = self.gw(key)
         self.add("bias_grad", [dz], [part],
                  lambda: _call("effdet_colsum", dz.ptr + byte_off, prow, pC, fold, g.data_ptr(), accumulate,
                                part.ptr, nblk, dtype), name)
+        if tail:
+            self.add("bias_grad", [dz], [part],
+                     lambda: _call("effdet_colsum_tail", dz.ptr + byte_off, prow * fold, tail, C, g.data_ptr(),
+                                   dtype), name + "_tail")
 
     # backward ------------------------------------------------------------------------
     def _build_backward(self):

@@ -276,6 +276,10 @@ int effdet_bn_relu_backward(const void *dy, const void *y, const void *z, size_t
  * rows were packed into one physical row to keep rows vectorisable). */
 int effdet_colsum(const void *x, size_t rows, int C, int fold, float *out, int accumulate,
                   float *partial, int nblk, int dtype, void *stream);
+/* out[c] += sum over rows [row0, row0 + nrows) of the dense (*, C) matrix x: the scalar tail for the few rows
+ * that do not fill a whole fold of effdet_colsum. */
+int effdet_colsum_tail(const void *x, size_t row0, int nrows, int C, float *out, int dtype, void *stream);
+
 
 /* Depthwise 3x3 stride-1 SAME weight gradient (model.py:48-55 DepthwiseConv2D backward-filter).
  * partial: 9*C*blocks floats with blocks = effdet_dw_wgrad_blocks(). */

@@ -591,3 +591,38 @@ def test_fit_prefetched_matches_stepwise_training():
         losses[mode] = out
     for a, b in zip(losses["stepwise"], losses["prefetched"]):
         assert abs(a[0] - b[0]) / max(abs(a[0]), 1e-9) < 1e-4 and abs(a[1] - b[1]) / max(abs(a[1]), 1e-9) < 1e-4, losses
+
+
+def test_checkpoint_saver_round_trip_and_lr_schedule_in_fit(tmp_path):
+    """utils/train.py:66-92 CheckpointSaver + utils/lr_schedule.py callback driven by Model.fit: the
+    checkpoint restores weights, SGD velocity and the iteration count exactly."""
+    from efficientdet_b200.model import efficientdet
+    from efficientdet_b200.optimizers import SGD
+    from efficientdet_b200.utils.lr_schedule import get_cosine_decay_with_linear_warmup
+    from efficientdet_b200.utils.train import CheckpointSaver, restore_checkpoint
+    size, C, B = 128, 3, 2
+    anchors, ann, reg_t, lab_t = _targets(size, B, C)
+    img = np.random.default_rng(2).standard_normal((B, size, size, 3)).astype(np.float32)
+
+    def build():
+        m = efficientdet(0, num_classes=C, image_size=size, dtype="fp32", drop_connect_rate=0,
+                         just_training_model=True)
+        perturb_weights(m)
+        m.freeze_backbone()
+        m.compile(optimizer=SGD(lr=0.01, decay=4e-5, momentum=0.9))
+        return m
+    m1 = build()
+    sched = get_cosine_decay_with_linear_warmup(total_epochs=4, learning_rate_max=0.02, warmup_percent=0.5)
+    saver = CheckpointSaver(str(tmp_path / "ckpt_{epoch:02d}_{loss:.3f}"))
+    hist = m1.fit([(img, [reg_t, lab_t])] * 2, epochs=2, callbacks=[sched, saver])
+    assert len(hist) == 4 and m1.optimizer.lr == pytest.approx(0.02) and m1.optimizer.iterations == 4
+    files = sorted(tmp_path.glob("ckpt_01_*.npz"))
+    assert len(files) == 1
+    m2 = build()
+    restore_checkpoint(m2, str(tmp_path))                  # newest checkpoint of the directory
+    assert m2.optimizer.iterations == 4 and m2.optimizer.lr == pytest.approx(0.02)
+    w1, w2 = m1.get_weights_dict(), m2.get_weights_dict()
+    assert all(np.array_equal(w1[k], w2[k]) for k in w1)
+    assert torch.equal(m1.net.velocity, m2.net.velocity)
+    a, b = m1.train_on_batch(img, [reg_t, lab_t]), m2.train_on_batch(img, [reg_t, lab_t])
+    assert a == b                                          # the restored model continues identically
