@@ -370,14 +370,31 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                         if (lane == 0)
                             tma_store_4d(&p.out_map[tc.gi], my_stage + (size_t)sbuf * kStageBytes, nbase, sx, sy, sb);
                         sbuf ^= 1;
-                    } else if (nvalid == 32 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
+                    } else {
+                        // rows whose byte stride is not a multiple of 16 (9*C floats, C = 90: the class head's
+                        // concatenated output) cannot go through TMA: transpose through the warp's staging
+                        // buffer and let the 32 lanes write 32 consecutive floats of one row per instruction
+                        // (one 128-byte segment instead of 32 scattered 4-byte stores)
+                        (void)Y;
+                        __syncwarp();
+                        uint8_t *dst = my_stage + lane * 128;
 #pragma unroll
                         for (int j4 = 0; j4 < 8; ++j4)
-                            *reinterpret_cast<float4 *>(Y + 4 * j4) =
+                            *reinterpret_cast<float4 *>(dst + ((j4 ^ (lane & 7)) << 4)) =
                                 make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (j < nvalid) Y[j] = v[j];
+                        __syncwarp();
+                        const unsigned ok_mask = __ballot_sync(0xffffffffu, row_ok);
+                        const unsigned long long row_off = (unsigned long long)base + (unsigned long long)nbase;
+                        float *Yb = static_cast<float *>(G.y);
+#pragma unroll 4
+                        for (int rr = 0; rr < 32; ++rr) {
+                            const unsigned long long off = __shfl_sync(0xffffffffu, row_off, rr);
+                            if (((ok_mask >> rr) & 1u) && lane < ncols) {
+                                const float val = *reinterpret_cast<const float *>(
+                                    my_stage + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2)));
+                                Yb[off + lane] = val;
+                            }
+                        }
                     }
                 } else {
                     __nv_bfloat16 *Y = static_cast<__nv_bfloat16 *>(G.y) + base + nbase;
@@ -720,21 +737,27 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 using namespace effdet;
 
-extern "C" int effdet_conv_tc_block_n(int n) {
-    // N tile <= 128 columns: two accumulators of <= 128 TMEM columns each leave room for two CTAs
-    // (16 epilogue warps) per SM; N is split into equal tiles rounded up to 16.
-    // up to 256 columns: one N tile (the activations are read once); the launcher picks one or two
-    // TMEM accumulators per CTA from the K extent
+// N tile of the tensor-core convolution for an (N = Cout) x (num_k = taps * ceil(K / 64)) problem.
+// Up to 256 columns in one tile (the activations are then read once).  Wider N is split into equal
+// tiles that are multiples of 32 (no 32-column epilogue chunk straddles two tiles): <= 256 columns
+// for deep reductions (tensor-bound 3x3 head convolutions: the activation tile is re-read from L2 once
+// per N tile, so wide tiles cut the shared-memory fill traffic), <= 128 columns for shallow ones
+// (HBM-bound expand convolutions: two TMEM accumulators and two CTAs per SM hide the epilogue).
+static int tc_block_n(int n, int num_k) {
     const int n16 = round_up(n, 16);
     if (n16 <= 256) return n16;
-    // several N tiles: multiples of 32 so that no 32-column epilogue chunk straddles two tiles
-    const int tiles = (n16 + 127) / 128;
+    const int cap = num_k >= 8 ? 256 : 128;
+    const int tiles = (n16 + cap - 1) / cap;
     return round_up((n16 + tiles - 1) / tiles, 32);
 }
 
+extern "C" int effdet_conv_tc_block_n(int n) { return tc_block_n(n, 1); }
+
 extern "C" size_t effdet_conv_weight_panel_elems(int taps_or_samples, int K, int N) {
-    const int bn = effdet_conv_tc_block_n(N);
-    return (size_t)taps_or_samples * round_up(N, bn) * round_up(K, kTileK);
+    // large enough for either tiling rule (the caller does not say whether the first argument counts
+    // taps or samples)
+    const int a = round_up(N, tc_block_n(N, 1)), b = round_up(N, tc_block_n(N, 8));
+    return (size_t)taps_or_samples * (a > b ? a : b) * round_up(K, kTileK);
 }
 
 extern "C" int effdet_conv_weight_panel(const float *w, void *panel, int taps, int Cin, int Cout, int mode,
@@ -743,8 +766,9 @@ extern "C" int effdet_conv_weight_panel(const float *w, void *panel, int taps, i
     EFFDET_REQUIRE(mode == 0 || mode == 1, "mode 0 (forward) or 1 (data gradient)");
     EFFDET_REQUIRE(!gate || (mode == 0 && taps == 1 && B > 0), "gate only for forward 1x1");
     const int K = mode == 0 ? Cin : Cout, N = mode == 0 ? Cout : Cin;
-    const int bn = effdet_conv_tc_block_n(N);
-    const int Kpad = round_up(K, kTileK), Npad = round_up(N, bn);
+    const int Kpad = round_up(K, kTileK);
+    const int bn = tc_block_n(N, (gate ? 1 : taps) * (Kpad / kTileK));
+    const int Npad = round_up(N, bn);
     const size_t total = (size_t)(gate ? B : taps) * Npad * Kpad;
     EFFDET_REQUIRE(total < 0xffffffffull, "panel too large");
     if (gate) {
@@ -774,8 +798,9 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     if (!encode) return fail(EFFDET_E_CUDA, "effdet_conv2d: cuTensorMapEncodeTiled unavailable%s", "");
     static TcParams p;      // large; filled per call (single-threaded use per the ABI contract)
     memset(&p, 0, sizeof(p));
-    const int bn = effdet_conv_tc_block_n(d->Cout);
-    const int Kpad = round_up(d->Cin, kTileK), Npad = round_up(d->Cout, bn);
+    const int Kpad = round_up(d->Cin, kTileK);
+    const int bn = tc_block_n(d->Cout, d->kh * d->kw * (Kpad / kTileK));
+    const int Npad = round_up(d->Cout, bn);
     p.n_groups = d->n_groups; p.B = d->B; p.Cout = d->Cout; p.ksize = d->kh; p.stride = d->stride;
     p.kblocks_per_tap = Kpad / kTileK; p.block_n = bn;
     const int num_k = d->kh * d->kw * p.kblocks_per_tap;

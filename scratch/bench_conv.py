@@ -3,7 +3,8 @@ sys.path.insert(0,'.'); sys.path.insert(0,'tests')
 from efficientdet_b200 import _lib
 from test_gpu_conv_tc import _panel, _d
 cases={"expand2a":(32,256,16,96,1,2),"expand3a":(32,128,24,144,1,2),"project2b":(32,128,144,24,1,0),"head":(32,64,64,64,3,1),"project7a":(32,16,1152,320,1,0),
-"expand3b":(32,64,40,240,1,2),"expand4b":(32,32,80,480,1,2),"expand5b":(32,32,112,672,1,2),"project5b":(32,32,672,112,1,0),"expand6b":(32,16,192,1152,1,2),"project1a":(32,256,32,16,1,0)}
+"expand3b":(32,64,40,240,1,2),"expand4b":(32,32,80,480,1,2),"expand5b":(32,32,112,672,1,2),"project5b":(32,32,672,112,1,0),"expand6b":(32,16,192,1152,1,2),"project1a":(32,256,32,16,1,0),
+"d2cls":(16,96,112,810,3,3),"d2trunk":(16,96,112,112,3,1),"d0cls":(32,64,64,180,3,3),"d6exp":(4,44,576,3456,1,2),"d4trunk":(8,128,224,224,3,1)}
 name=sys.argv[1] if len(sys.argv)>1 else "expand2a"
 B,H,cin,cout,k,act=cases[name]
 rng=np.random.default_rng(0)
