@@ -564,6 +564,9 @@ static int launch_dw(const void *x, const float *w, const float *scale, const fl
 int dwconv_bf16_tma(const void *x, const float *w, const float *scale, const float *shift, void *y, float *se_sum,
                     int B, int H, int W, int C, int k, int stride, int act, cudaStream_t st, float *stats = nullptr);
 int dwconv_bf16_tma_se_blocks(int H, int W, int stride);
+int bifpn_node_bf16_tma(const void *in0, int mode0, const void *in1, const void *in2, const float *fw, float eps,
+                        const float *dw, const float *scale, const float *shift, void *out, int B, int H, int W,
+                        int C, cudaStream_t st);
 
 }  // namespace effdet
 
@@ -676,6 +679,8 @@ extern "C" int effdet_bifpn_node(const void *in0, int mode0, const void *in1, co
             static_cast<const float *>(in0), mode0, static_cast<const float *>(in1),
             static_cast<const float *>(in2), w, eps, dw_kernel, scale, shift,
             static_cast<float *>(out), H, W, C, tx);
+    else if (dtype == EFFDET_BF16 && (mode0 == 1 || mode0 == 2))
+        return bifpn_node_bf16_tma(in0, mode0, in1, in2, w, eps, dw_kernel, scale, shift, out, B, H, W, C, st);
     else if (dtype == EFFDET_BF16)
         bifpn_node_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(
             static_cast<const __nv_bfloat16 *>(in0), mode0, static_cast<const __nv_bfloat16 *>(in1),

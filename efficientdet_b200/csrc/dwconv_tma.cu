@@ -412,6 +412,239 @@ static int launch_dw_wgrad_tma(const void *x, const void *dz, float *partial, in
     return EFFDET_OK;
 }
 
+// ------------------------------------------------------------------ fused BiFPN node
+// out = ReLU(BN(DW3x3( fuse(resample(in0), in1 [, in2]) )))    (model.py:154-194 / :226-266, layers.py:26-31)
+// resample = nearest x2 upsampling of the coarser level (MODE0 = 1) or 2x2 / stride-2 max pooling of the
+// finer level (MODE0 = 2), applied while the tile is read.  Same persistent TMA pipeline as the
+// depthwise kernel: per tile the halo patches of in1 / in2, the matching patch of in0 (half or double
+// resolution) and the 9 x CB weights land in shared memory (zero fill outside the images: the fused
+// tensor is zero there too, which is exactly the SAME padding of the depthwise conv); one cooperative
+// pass writes the fused bf16 patch over in1's patch, then every thread runs its 2 x 4 register tile.
+// HBM traffic: each input once, the output once (the fused tensor never leaves the SM).
+struct alignas(64) NodeParams {
+    CUtensorMap in0_map, in1_map, in2_map;  // (C, W*, H*, B) bf16
+    CUtensorMap w_map;                      // (C, 9) f32
+    const float *fw;                        // fusion weights (2 or 3) or NULL (plain Add)
+    const float *scale, *shift;
+    __nv_bfloat16 *y;
+    float eps;
+    int has_in2, H, W, C, tiles_x, tiles_y, cblocks, total_tiles;
+};
+
+template <int MODE0, int CP> struct NodeCfg {
+    static constexpr int TH = 8, TW = MODE0 == 2 ? 8 : 16;
+    static constexpr int CB = CP * 2;
+    static constexpr int FH = TH + 2, FW = TW + 2;                       // fused patch (halo 1)
+    static constexpr int SH = MODE0 == 1 ? TH / 2 + 2 : 2 * FH;          // in0 patch
+    static constexpr int SW = MODE0 == 1 ? TW / 2 + 2 : 2 * FW;
+    static constexpr int NRT = (TH / kRtH) * (TW / kRtW);
+    static constexpr int PASSES = NRT / 8;
+    static constexpr int NT = CP * 8;
+    static constexpr int F_BYTES = FH * FW * CB * 2;
+    static constexpr int F_PAD = ((F_BYTES + 127) / 128) * 128;
+    static constexpr int S_BYTES = SH * SW * CB * 2;
+    static constexpr int S_PAD = ((S_BYTES + 127) / 128) * 128;
+    static constexpr int W_BYTES = 9 * CB * 4;
+    static constexpr int STAGE_BYTES = ((2 * F_PAD + S_PAD + W_BYTES + 127) / 128) * 128;   // in1 | in2 | in0 | w
+    static constexpr size_t SMEM = 2 * (size_t)STAGE_BYTES + 64 + 128;
+};
+
+template <int MODE0, int CP>
+__global__ void __launch_bounds__(NodeCfg<MODE0, CP>::NT, 2)
+bifpn_node_tma_kernel(const __grid_constant__ NodeParams p) {
+    using Cfg = NodeCfg<MODE0, CP>;
+    constexpr int CB = Cfg::CB, TH = Cfg::TH, TW = Cfg::TW, FH = Cfg::FH, FW = Cfg::FW, SW = Cfg::SW;
+    extern __shared__ uint8_t dsm_raw[];
+    uint8_t *dsm = dsm_raw + ((128u - (smem_u32(dsm_raw) & 127u)) & 127u);
+    uint64_t *full = reinterpret_cast<uint64_t *>(dsm + 2 * Cfg::STAGE_BYTES);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int t, int stage) {
+        int r = t;
+        const int tx = r % p.tiles_x; r /= p.tiles_x;
+        const int ty = r % p.tiles_y; r /= p.tiles_y;
+        const int cb = r % p.cblocks; const int b = r / p.cblocks;
+        uint8_t *dst = dsm + (size_t)stage * Cfg::STAGE_BYTES;
+        const int x0 = tx * TW - 1, y0 = ty * TH - 1;
+        mbar_expect_tx(&full[stage], (uint32_t)(Cfg::F_BYTES * (p.has_in2 ? 2 : 1) + Cfg::S_BYTES + Cfg::W_BYTES));
+        tma_load_4d(dst, &p.in1_map, &full[stage], cb * CB, x0, y0, b);
+        if (p.has_in2) tma_load_4d(dst + Cfg::F_PAD, &p.in2_map, &full[stage], cb * CB, x0, y0, b);
+        if (MODE0 == 1) tma_load_4d(dst + 2 * Cfg::F_PAD, &p.in0_map, &full[stage], cb * CB, tx * TW / 2 - 1, ty * TH / 2 - 1, b);
+        else tma_load_4d(dst + 2 * Cfg::F_PAD, &p.in0_map, &full[stage], cb * CB, 2 * x0, 2 * y0, b);
+        tma_load_2d(dst + 2 * Cfg::F_PAD + Cfg::S_PAD, &p.w_map, &full[stage], cb * CB, 0);
+    };
+
+    float w0 = 1.f, w1 = 1.f, w2 = 1.f, rinv = 1.f;
+    const bool weighted = p.fw != nullptr;
+    if (weighted) {
+        w0 = fmaxf(p.fw[0], 0.f); w1 = fmaxf(p.fw[1], 0.f); w2 = p.has_in2 ? fmaxf(p.fw[2], 0.f) : 0.f;
+        rinv = 1.f / (w0 + w1 + w2 + p.eps);
+    }
+    const int pair = tid % CP, slot = tid / CP;
+    auto unpack = [](uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); };
+
+    if (tid == 0 && (int)blockIdx.x < p.total_tiles) issue(blockIdx.x, 0);
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const int stage = it & 1;
+        if (tid == 0 && t + (int)gridDim.x < p.total_tiles) issue(t + gridDim.x, stage ^ 1);
+        int r = t;
+        const int tx = r % p.tiles_x; r /= p.tiles_x;
+        const int ty = r % p.tiles_y; r /= p.tiles_y;
+        const int cb = r % p.cblocks; const int b = r / p.cblocks;
+        const int c = cb * CB + pair * 2;
+        const bool c_ok = c < p.C;
+        float2 sc = make_float2(0.f, 0.f), sh = make_float2(0.f, 0.f);
+        if (c_ok) {
+            sc = *reinterpret_cast<const float2 *>(p.scale + c);
+            sh = *reinterpret_cast<const float2 *>(p.shift + c);
+        }
+        uint8_t *s1 = dsm + (size_t)stage * Cfg::STAGE_BYTES;
+        const uint8_t *s2 = s1 + Cfg::F_PAD, *s0 = s1 + 2 * Cfg::F_PAD;
+        const float *sW = reinterpret_cast<const float *>(s1 + 2 * Cfg::F_PAD + Cfg::S_PAD);
+        mbar_wait(&full[stage], (it >> 1) & 1);
+
+        // ---- fusion pass: fused patch (bf16) written over in1's patch
+        for (int px = slot; px < FH * FW; px += 8) {
+            const int hy = px / FW, hx = px - hy * FW;
+            const size_t off = ((size_t)px * CB + pair * 2) * 2;
+            float2 a;
+            if (MODE0 == 1) {
+                a = unpack(*reinterpret_cast<const uint32_t *>(
+                    s0 + ((size_t)(((hy + 1) >> 1) * SW + ((hx + 1) >> 1)) * CB + pair * 2) * 2));
+            } else {
+                const uint8_t *q = s0 + ((size_t)((2 * hy) * SW + 2 * hx) * CB + pair * 2) * 2;
+                const float2 q0 = unpack(*reinterpret_cast<const uint32_t *>(q));
+                const float2 q1 = unpack(*reinterpret_cast<const uint32_t *>(q + CB * 2));
+                const float2 q2 = unpack(*reinterpret_cast<const uint32_t *>(q + (size_t)SW * CB * 2));
+                const float2 q3 = unpack(*reinterpret_cast<const uint32_t *>(q + (size_t)SW * CB * 2 + CB * 2));
+                a = make_float2(fmaxf(fmaxf(q0.x, q1.x), fmaxf(q2.x, q3.x)), fmaxf(fmaxf(q0.y, q1.y), fmaxf(q2.y, q3.y)));
+            }
+            const float2 bb = unpack(*reinterpret_cast<const uint32_t *>(s1 + off));
+            float2 f;
+            if (weighted) { f.x = w0 * a.x + w1 * bb.x; f.y = w0 * a.y + w1 * bb.y; }
+            else { f.x = a.x + bb.x; f.y = a.y + bb.y; }
+            if (p.has_in2) {
+                const float2 cc = unpack(*reinterpret_cast<const uint32_t *>(s2 + off));
+                if (weighted) { f.x += w2 * cc.x; f.y += w2 * cc.y; }
+                else { f.x += cc.x; f.y += cc.y; }
+            }
+            if (weighted) { f.x *= rinv; f.y *= rinv; }
+            *reinterpret_cast<__nv_bfloat162 *>(s1 + off) = __floats2bfloat162_rn(f.x, f.y);
+        }
+        __syncthreads();
+
+        // ---- depthwise 3x3 + BN + ReLU on the fused patch
+        float2 wk[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) wk[i] = *reinterpret_cast<const float2 *>(sW + i * CB + pair * 2);
+#pragma unroll 1
+        for (int pass = 0; pass < Cfg::PASSES; ++pass) {
+            const int rt = pass * 8 + slot;
+            const int ry = (rt / (TW / kRtW)) * kRtH, rx = (rt % (TW / kRtW)) * kRtW;
+            float2 acc[kRtH][kRtW];
+#pragma unroll
+            for (int i = 0; i < kRtH; ++i)
+#pragma unroll
+                for (int j = 0; j < kRtW; ++j) acc[i][j] = make_float2(0.f, 0.f);
+            const uint8_t *base = s1 + ((size_t)(ry * FW + rx) * CB + pair * 2) * 2;
+#pragma unroll
+            for (int rr = 0; rr < kRtH + 2; ++rr) {
+                float2 in[kRtW + 2];
+#pragma unroll
+                for (int j = 0; j < kRtW + 2; ++j)
+                    in[j] = unpack(*reinterpret_cast<const uint32_t *>(base + (size_t)(rr * FW + j) * CB * 2));
+#pragma unroll
+                for (int orow = 0; orow < kRtH; ++orow) {
+                    const int ky = rr - orow;
+                    if (ky < 0 || ky >= 3) continue;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                        for (int oc = 0; oc < kRtW; ++oc)
+                            acc[orow][oc] = __ffma2_rn(in[oc + kx], wk[ky * 3 + kx], acc[orow][oc]);
+                }
+            }
+            if (c_ok) {
+#pragma unroll
+                for (int orow = 0; orow < kRtH; ++orow) {
+                    const int oy = ty * TH + ry + orow;
+                    if (oy >= p.H) continue;
+                    __nv_bfloat16 *yrow = p.y + (((size_t)b * p.H + oy) * p.W) * p.C + c;
+#pragma unroll
+                    for (int oc = 0; oc < kRtW; ++oc) {
+                        const int ox = tx * TW + rx + oc;
+                        if (ox < p.W) {
+                            const float2 z = __ffma2_rn(acc[orow][oc], sc, sh);
+                            *reinterpret_cast<__nv_bfloat162 *>(yrow + (size_t)ox * p.C) =
+                                __floats2bfloat162_rn(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f));
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();        // everyone is done with this stage before it is refilled
+    }
+}
+
+template <int MODE0, int CP>
+static int launch_node_tma(const void *in0, const void *in1, const void *in2, const float *fw, float eps,
+                           const float *dw, const float *scale, const float *shift, void *out, int B, int H, int W,
+                           int C, cudaStream_t st) {
+    using Cfg = NodeCfg<MODE0, CP>;
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return fail(EFFDET_E_CUDA, "effdet_bifpn_node: cuTensorMapEncodeTiled unavailable%s", "");
+    NodeParams p;
+    memset(&p, 0, sizeof(p));
+    p.fw = fw; p.eps = eps; p.scale = scale; p.shift = shift; p.y = static_cast<__nv_bfloat16 *>(out);
+    p.has_in2 = in2 != nullptr; p.H = H; p.W = W; p.C = C;
+    p.tiles_x = (W + Cfg::TW - 1) / Cfg::TW; p.tiles_y = (H + Cfg::TH - 1) / Cfg::TH;
+    p.cblocks = (C + Cfg::CB - 1) / Cfg::CB;
+    p.total_tiles = p.tiles_x * p.tiles_y * p.cblocks * B;
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    auto enc4 = [&](CUtensorMap *m, const void *ptr, int w, int h, int bw, int bh) -> CUresult {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * w, (cuuint64_t)C * 2 * w * h};
+        cuuint32_t box[4] = {(cuuint32_t)Cfg::CB, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+        return encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    const int H0 = MODE0 == 1 ? H / 2 : H * 2, W0 = MODE0 == 1 ? W / 2 : W * 2;
+    CUresult r = enc4(&p.in1_map, in1, W, H, Cfg::FW, Cfg::FH);
+    if (r == CUDA_SUCCESS && in2) r = enc4(&p.in2_map, in2, W, H, Cfg::FW, Cfg::FH);
+    if (r == CUDA_SUCCESS) r = enc4(&p.in0_map, in0, W0, H0, Cfg::SW, Cfg::SH);
+    if (r == CUDA_SUCCESS) {
+        cuuint64_t dims[2] = {(cuuint64_t)C, 9};
+        cuuint64_t strides[1] = {(cuuint64_t)C * 4};
+        cuuint32_t box[2] = {(cuuint32_t)Cfg::CB, 9};
+        cuuint32_t es2[2] = {1, 1};
+        r = encode(&p.w_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(dw), dims, strides, box, es2,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_bifpn_node: cuTensorMapEncodeTiled failed %s(%lld)", "", (long long)r);
+    auto kern = bifpn_node_tma_kernel<MODE0, CP>;
+    static int per_sm = 0;
+    if (!per_sm) {
+        EFFDET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        int nb = 0;
+        EFFDET_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::NT, Cfg::SMEM));
+        per_sm = nb < 1 ? 1 : nb;
+    }
+    int grid = kNumSMs * per_sm;
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    kern<<<grid, Cfg::NT, Cfg::SMEM, st>>>(p);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
 // channel pairs per block: the largest of 32 / 24 / 16 (64 / 48 / 32 channels) that divides C,
 // else the one wasting the fewest lanes
 static int pick_cp(int C) {
@@ -472,6 +705,20 @@ int dw_wgrad_bf16_tma(const void *x, const void *dz, float *partial, int nsplit,
     DWW_CASE(3, 1) DWW_CASE(5, 1) DWW_CASE(3, 2) DWW_CASE(5, 2)
 #undef DWW_CASE
     return fail(EFFDET_E_INVALID, "effdet_dw_backward: bad kernel / stride%s", "");
+}
+
+// bf16 entry used by effdet_bifpn_node (dwconv.cu): mode0 1 = upsample in0, 2 = max-pool in0
+int bifpn_node_bf16_tma(const void *in0, int mode0, const void *in1, const void *in2, const float *fw, float eps,
+                        const float *dw, const float *scale, const float *shift, void *out, int B, int H, int W,
+                        int C, cudaStream_t st) {
+    if (mode0 == 1) {
+        const int cp = pick_cp(C);
+        if (cp == 32) return launch_node_tma<1, 32>(in0, in1, in2, fw, eps, dw, scale, shift, out, B, H, W, C, st);
+        if (cp == 24) return launch_node_tma<1, 24>(in0, in1, in2, fw, eps, dw, scale, shift, out, B, H, W, C, st);
+        return launch_node_tma<1, 16>(in0, in1, in2, fw, eps, dw, scale, shift, out, B, H, W, C, st);
+    }
+    // max-pool mode: the in0 patch is 4x the tile, 32-channel blocks keep two stages + two blocks per SM
+    return launch_node_tma<2, 16>(in0, in1, in2, fw, eps, dw, scale, shift, out, B, H, W, C, st);
 }
 
 }  // namespace effdet
