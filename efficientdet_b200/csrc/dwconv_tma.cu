@@ -648,7 +648,14 @@ static int launch_node_tma(const void *in0, const void *in1, const void *in2, co
 // channel pairs per block: the largest of 32 / 24 / 16 (64 / 48 / 32 channels) that divides C,
 // else the one wasting the fewest lanes
 static int pick_cp(int C) {
+    // 32 pairs (64 channels) = one warp per register-tile slot: shared-memory reads are conflict free.
+    // 24 / 16 pairs put lanes of two slots into one warp; their pixel offsets are multiples of four
+    // pixels = multiples of 32 words, so those reads are 2-way bank conflicted -- only worth it when
+    // 64-channel blocks would idle more than ~1/8 of the lanes.
+    if (const char *e = getenv("EFFDET_DW_CP")) { const int v = atoi(e); if (v == 32 || v == 24 || v == 16) return v; }
     const int cand[3] = {32, 24, 16};
+    const long w64 = (long)((C + 63) / 64) * 64 - C;
+    if (w64 * 8 <= C) return 32;
     for (int cp : cand) if (C % (2 * cp) == 0) return cp;
     int best = 32; long waste = -1;
     for (int cp : cand) {
