@@ -702,6 +702,163 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
     }
 }
 
+
+// ------------------------------------------------------------------ 3x3 weight gradient, Cin <= 64: halo version
+// The per-tap kernel above moves every activation tile through L2 -> shared memory once per tap
+// (9 x 16 KiB per 128 pixels); measured, the 64-channel head convolutions sit at the L2 bandwidth
+// (profiles/).  Here ONE CTA handles all nine taps of its pixel tiles.  Per tile it loads three
+// copies of the activation patch with one row of halo above / below, shifted by kx = 0, 1, 2 columns
+// (box (64 ch, Wt, Ht + 2, Bt), out-of-image = zero = SAME padding) and the dz tile once.  Inside copy
+// kx, tap (ky, kx) is the dense pixel range starting ky rows in: with Wt in {8, 16, 32} every
+// 16-pixel K step starts on an 8-pixel (1024-byte swizzle atom) boundary, so plain MN-major
+// descriptors address it.  Two taps share one M = 128 instruction (LBO = distance between their
+// two 64-channel operands); the ninth tap is paired with a block of ones, which yields the bias
+// gradient.  Five accumulators of 64 columns live in TMEM.  ~76 KiB instead of 240 KiB per tile.
+struct WgHaloGroup { int Wt, Ht, Bt, lw, lh, tiles_x, tiles_y, n_tiles, split_begin, tiles_per_split, box_bytes; };
+struct alignas(64) WgHaloParams {
+    CUtensorMap x_map[kTcMaxGroups];
+    CUtensorMap z_map[kTcMaxGroups];
+    WgHaloGroup g[kTcMaxGroups];
+    int n_groups, Cin, Cout, stages, box_stride;      // box_stride: bytes reserved per activation copy
+    float *partial, *bias_partial;
+};
+
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int stage_bytes = 3 * p.box_stride + kATileBytes;          // 3 activation copies + dz tile
+    uint8_t *sOnes = smem + (size_t)p.stages * stage_bytes;          // box_stride bytes of bf16 1.0
+    uint64_t *full = reinterpret_cast<uint64_t *>(sOnes + p.box_stride);
+    uint64_t *empty = full + p.stages;
+    uint64_t *tmem_full = empty + p.stages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int gi = 0;
+#pragma unroll
+    for (int i = 1; i < kTcMaxGroups; ++i)
+        if (i < p.n_groups && (int)blockIdx.x >= p.g[i].split_begin) gi = i;
+    const WgHaloGroup &G = p.g[gi];
+    const int t_begin = ((int)blockIdx.x - G.split_begin) * G.tiles_per_split;
+    const int t_end = min(t_begin + G.tiles_per_split, G.n_tiles);
+    const int num_k = t_end - t_begin;
+    const int n0 = blockIdx.y * 64;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512u);
+    for (int i = threadIdx.x; i < p.box_stride / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(sOnes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % p.stages, ph = (kb / p.stages) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                int t = t_begin + kb;
+                const int tx = t % G.tiles_x; t /= G.tiles_x;
+                const int ty = t % G.tiles_y; t /= G.tiles_y;
+                const int x0 = tx * G.Wt, y0 = ty * G.Ht, b0 = t * G.Bt;
+                uint8_t *st = smem + (size_t)s * stage_bytes;
+                mbar_expect_tx(&full[s], (uint32_t)(3 * G.box_bytes + kATileBytes));
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+                    tma_load_4d(st + (size_t)kx * p.box_stride, &p.x_map[gi], &full[s], 0, x0 - 1 + kx, y0 - 1, b0);
+                tma_load_4d(st + 3 * (size_t)p.box_stride, &p.z_map[gi], &full[s], n0, x0, y0, b0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // M = 128 (two taps x 64 channels), N = 64, both operands MN-major
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t ones_addr = smem_u32(sOnes);
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % p.stages, ph = (kb / p.stages) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t zb = st + 3u * (uint32_t)p.box_stride;
+#pragma unroll 1
+                for (int k = 0; k < 8; ++k) {                 // 16-pixel K steps of the 128-pixel tile
+                    const int pix = 16 * k;
+                    const int xx = pix & (G.Wt - 1), yy = (pix >> G.lw) & (G.Ht - 1), bb = pix >> (G.lw + G.lh);
+                    const uint32_t row0 = (uint32_t)((bb * (G.Ht + 2) + yy) * G.Wt + xx) * 128u;   // tap ky = 0
+                    const uint64_t db = make_mnmajor_sw128_desc(zb + (uint32_t)k * 2048u, kATileBytes);
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        // operand slots u = kx * 3 + ky are ordered by shared-memory address (copy kx, then
+                        // ky rows in), so the second half of a pair always lies above the first (LBO > 0)
+                        const int ua = 2 * j, ub = 2 * j + 1;
+                        const uint32_t aa = st + (uint32_t)(ua / 3) * (uint32_t)p.box_stride + row0 +
+                                            (uint32_t)((ua % 3) * G.Wt) * 128u;
+                        // second half: slot ub, or (j == 4) the block of ones at the same relative offset
+                        const uint32_t ab = ub < 9 ? st + (uint32_t)(ub / 3) * (uint32_t)p.box_stride + row0 +
+                                                         (uint32_t)((ub % 3) * G.Wt) * 128u
+                                                   : ones_addr + row0;
+                        const uint64_t da = make_mnmajor_sw128_desc(aa, ab - aa);
+                        umma_bf16(tmem_base + (uint32_t)(j * 64), da, db, idesc, (kb | k) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[s]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        if (num_k > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        const int ci = row & 63;
+        for (int j = 0; j < 5; ++j) {
+            const int u = 2 * j + (row >> 6);                       // operand slot kx * 3 + ky; 9 = ones
+            const int tap = u < 9 ? (u % 3) * 3 + u / 3 : 9;        // HWIO tap index ky * 3 + kx
+            float *out = p.partial + ((size_t)blockIdx.x * 9 + min(tap, 8)) * p.Cin * p.Cout;
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t r[32];
+                __syncwarp();
+                if (num_k > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 64 + c0), r);
+                const int nv = min(32, p.Cout - (n0 + c0));
+                float *o = nullptr;
+                if (tap < 9 && ci < p.Cin) o = out + (size_t)ci * p.Cout + n0 + c0;
+                else if (tap == 9 && row == 64 && p.bias_partial) o = p.bias_partial + (size_t)blockIdx.x * p.Cout + n0 + c0;
+                if (o) {
+                    if (num_k == 0) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) r[jj] = 0u;
+                    }
+                    if (nv == 32 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4)
+                            reinterpret_cast<uint4 *>(o)[j4] = make_uint4(r[4 * j4], r[4 * j4 + 1], r[4 * j4 + 2], r[4 * j4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj)
+                            if (jj < nv) o[jj] = __uint_as_float(r[jj]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512u);
+    }
+}
+
 __global__ void wgrad_tc_reduce_kernel(const float *__restrict__ partial, int nsplit, size_t n,
                                        float *__restrict__ out, int accumulate,
                                        const float *__restrict__ bias_partial, int n_bias,
@@ -927,20 +1084,38 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     return EFFDET_OK;
 }
 
+static bool wg_halo(const effdet_wgrad_desc *d) {
+    return d->kh == 3 && d->kw == 3 && d->stride == 1 && d->Cin <= 64 && getenv("EFFDET_NO_WGRAD_HALO") == nullptr;
+}
+// tiles of the halo kernel: Wt in {8, 16, 32} (16-pixel K steps start on swizzle-atom boundaries)
+static void pick_tile_halo(int W, int H, int B, int *Wt, int *Ht, int *Bt) {
+    static const int cand[][3] = {{16, 8, 1}, {8, 16, 1}, {32, 4, 1}, {8, 8, 2}, {16, 4, 2}, {8, 4, 4}, {16, 2, 4},
+                                  {8, 2, 8}, {16, 1, 8}};     // Wt * Ht >= 16: a K step never straddles images
+    long best = -1;
+    for (auto &c : cand) {
+        long n = (long)cdiv(W, c[0]) * cdiv(H, c[1]) * cdiv(B, c[2]);
+        if (best < 0 || n < best) { best = n; *Wt = c[0]; *Ht = c[1]; *Bt = c[2]; }
+    }
+}
+
 static int wg_tc_plan(const effdet_wgrad_desc *d, int *tiles_per_split_out, int *n_tiles_out, int *Wt, int *Ht,
                       int *Bt, int *block_n_out, int *m_tiles_out) {
     const int taps = d->kh * d->kw;
     const int bn = d->Cout <= 256 ? round_up(d->Cout, 64) : 256;
     const int m_tiles = (d->Cin + 127) / 128, n_tiles_n = (d->Cout + bn - 1) / bn;
     long total_tiles = 0;
+    const bool halo = wg_halo(d);
     for (int i = 0; i < d->n_groups; ++i) {
-        pick_tile(d->W[i], d->H[i], d->B, &Wt[i], &Ht[i], &Bt[i]);
+        if (halo) pick_tile_halo(d->W[i], d->H[i], d->B, &Wt[i], &Ht[i], &Bt[i]);
+        else pick_tile(d->W[i], d->H[i], d->B, &Wt[i], &Ht[i], &Bt[i]);
         n_tiles_out[i] = (int)(cdiv(d->W[i], Wt[i]) * cdiv(d->H[i], Ht[i]) * cdiv(d->B, Bt[i]));
         total_tiles += n_tiles_out[i];
     }
-    // ~2 CTAs per SM in flight; at least 8 pixel tiles per CTA so the pipeline has work
-    const long yz = (long)((d->Cin <= 64 && taps > 1) ? (taps + 1) / 2 : taps * m_tiles) * n_tiles_n;
-    long want = ((long)kNumSMs * 2 + yz - 1) / yz;
+    // ~2 CTAs per SM in flight (halo kernel: one CTA per SM, all taps in it; N tiles of 64);
+    // at least 8 pixel tiles per CTA so the pipeline has work
+    const long yz = halo ? (long)(d->Cout + 63) / 64
+                         : (long)((d->Cin <= 64 && taps > 1) ? (taps + 1) / 2 : taps * m_tiles) * n_tiles_n;
+    long want = ((long)kNumSMs * (halo ? 1 : 2) + yz - 1) / yz;
     if (want < 1) want = 1;
     long tps = (total_tiles + want - 1) / want;
     if (tps < 8) tps = 8;
@@ -978,6 +1153,69 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
     int tps, nt[kTcMaxGroups], Wt[kTcMaxGroups], Ht[kTcMaxGroups], Bt[kTcMaxGroups], bn, mt;
     const int splits = wg_tc_plan(d, &tps, nt, Wt, Ht, Bt, &bn, &mt);
     EFFDET_REQUIRE(splits == d->n_splits, "n_splits must be effdet_conv_wgrad_tc_splits()");
+    if (wg_halo(d)) {
+        static WgHaloParams hp;
+        memset(&hp, 0, sizeof(hp));
+        hp.n_groups = d->n_groups; hp.Cin = d->Cin; hp.Cout = d->Cout; hp.partial = d->partial;
+        hp.bias_partial = d->dbias ? d->partial + (size_t)splits * 9 * d->Cin * d->Cout : nullptr;
+        int box_max = 0, zs = 0;
+        for (int i = 0; i < d->n_groups; ++i) {
+            WgHaloGroup &g = hp.g[i];
+            g.Wt = Wt[i]; g.Ht = Ht[i]; g.Bt = Bt[i];
+            g.lw = 31 - __builtin_clz(g.Wt); g.lh = 31 - __builtin_clz(g.Ht);
+            g.tiles_x = cdiv(d->W[i], g.Wt); g.tiles_y = cdiv(d->H[i], g.Ht);
+            g.n_tiles = nt[i]; g.split_begin = zs; g.tiles_per_split = tps;
+            zs += (int)cdiv(nt[i], tps);
+            g.box_bytes = g.Wt * (g.Ht + 2) * g.Bt * 128;
+            if (g.box_bytes > box_max) box_max = g.box_bytes;
+            const long long ldz = d->dz_ld[i] ? d->dz_ld[i] : d->Cout;
+            const long long zbs = d->dz_batch_stride[i] ? d->dz_batch_stride[i] : (long long)d->H[i] * d->W[i] * ldz;
+            EFFDET_REQUIRE((ldz * 2) % 16 == 0 && (zbs * 2) % 16 == 0, "dz strides must be multiples of 16 bytes");
+            EFFDET_REQUIRE(((reinterpret_cast<uintptr_t>(d->x[i]) | reinterpret_cast<uintptr_t>(d->dz[i])) & 15) == 0,
+                           "operands must be 16-byte aligned");
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            {
+                cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W[i], (cuuint64_t)d->H[i], (cuuint64_t)d->B};
+                cuuint64_t stx[3] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * d->W[i],
+                                     (cuuint64_t)d->Cin * 2 * d->W[i] * d->H[i]};
+                cuuint32_t box[4] = {64, (cuuint32_t)g.Wt, (cuuint32_t)(g.Ht + 2), (cuuint32_t)g.Bt};
+                CUresult r = encode(&hp.x_map[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d->x[i]), dims,
+                                    stx, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_conv_wgrad_tc: encode(x halo) failed %s(%lld)", "", (long long)r);
+            }
+            {
+                cuuint64_t dims[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->W[i], (cuuint64_t)d->H[i], (cuuint64_t)d->B};
+                cuuint64_t stz[3] = {(cuuint64_t)ldz * 2, (cuuint64_t)ldz * 2 * d->W[i], (cuuint64_t)zbs * 2};
+                cuuint32_t box[4] = {64, (cuuint32_t)g.Wt, (cuuint32_t)g.Ht, (cuuint32_t)g.Bt};
+                CUresult r = encode(&hp.z_map[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d->dz[i]), dims,
+                                    stz, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_conv_wgrad_tc: encode(dz) failed %s(%lld)", "", (long long)r);
+            }
+        }
+        hp.box_stride = round_up(box_max, 1024);
+        const int stage_bytes = 3 * hp.box_stride + kATileBytes;
+        hp.stages = (int)((220 * 1024 - hp.box_stride - 2048) / stage_bytes);
+        if (hp.stages > 3) hp.stages = 3;
+        EFFDET_REQUIRE(hp.stages >= 1, "tile does not fit shared memory");
+        const size_t hsmem = (size_t)hp.stages * stage_bytes + hp.box_stride + (2 * hp.stages + 1) * 8 + 16 + 1024;
+        static bool hattr = false;
+        if (!hattr) {
+            EFFDET_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            hattr = true;
+        }
+        cudaStream_t hst = as_stream(stream);
+        dim3 hgrid(zs, (d->Cout + 63) / 64);
+        conv_wgrad_halo_kernel<<<hgrid, 192, hsmem, hst>>>(hp);
+        EFFDET_LAUNCHED();
+        const size_t hn = (size_t)9 * d->Cin * d->Cout;
+        const int hn_bias = d->dbias ? d->Cout : 0;
+        wgrad_tc_reduce_kernel<<<cdiv(hn + hn_bias, 256), 256, 0, hst>>>(d->partial, zs, hn, d->dweight, d->accumulate,
+                                                                        hp.bias_partial, hn_bias, d->dbias);
+        EFFDET_LAUNCHED();
+        return EFFDET_OK;
+    }
     p.n_groups = d->n_groups; p.B = d->B; p.Cin = d->Cin; p.Cout = d->Cout; p.ksize = d->kh;
     p.m_tiles = mt; p.block_n = bn; p.partial = d->partial;
     p.bias_partial = d->dbias ? d->partial + (size_t)splits * d->kh * d->kw * d->Cin * d->Cout : nullptr;
