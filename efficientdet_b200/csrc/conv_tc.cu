@@ -96,6 +96,10 @@ struct alignas(64) TcParams {
     TcGroup g[kTcMaxGroups];
     int n_groups, B, Cout, ksize, kblocks_per_tap, block_n, stages, tmem_cols;
     int act, out_f32, b_per_sample, total_tiles, n_tiles, any_tma_store;
+    // halo mode (3x3, stride 1, Cin <= 64, weights resident): one ring stage = three kx-shifted copies of
+    // the activation patch with a halo row above / below; tap (ky, kx) is the 128-pixel range of copy kx
+    // that starts ky rows in (see conv_wgrad_halo_kernel).  60 KiB instead of 9 x 16 KiB per tile.
+    int halo, a_stage_bytes, box_stride, stage_bufs, box_bytes[kTcMaxGroups];
     int acc_bufs;        // TMEM accumulators per CTA: 2 (epilogue of tile i overlaps the MMAs of i+1) or 1
     int b_resident;      // all K blocks of the (single) weight tile stay in shared memory for the CTA's lifetime
     int stride, pad_t[kTcMaxGroups], pad_l[kTcMaxGroups];   // stride 2: TMA element strides sample every other pixel
@@ -186,7 +190,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int b_tile_bytes = p.block_n * kTileK * 2;
     uint8_t *sA = smem;
-    uint8_t *sB = smem + (size_t)p.stages * kATileBytes;
+    uint8_t *sB = smem + (size_t)p.stages * p.a_stage_bytes;
     // ring B tiles, or (b_resident) one slot per K block filled once
     const int num_k_all = p.ksize * p.ksize * p.kblocks_per_tap;
     float *sScale = reinterpret_cast<float *>(sB + (size_t)(p.b_resident ? num_k_all : p.stages) * b_tile_bytes);   // [256]
@@ -237,6 +241,17 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             for (int t = t_begin; t < t_end; ++t, ti_.next(p)) {
                 const TileCoord c = ti_.coord(p);
                 const CUtensorMap *amap = &p.a_map[c.gi];
+                if (p.halo) {
+                    const int s = it % p.stages, ph = (it / p.stages) & 1;
+                    mbar_wait_backoff(&empty[s], ph ^ 1, 256);
+                    mbar_expect_tx(&full[s], (uint32_t)(3 * p.box_bytes[c.gi]));
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+                        tma_load_4d(sA + (size_t)s * p.a_stage_bytes + (size_t)kx * p.box_stride, amap, &full[s], 0,
+                                    c.x0 - 1 + kx, c.y0 - 1, c.b0);
+                    ++it;
+                    continue;
+                }
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
                     const int s = it % p.stages, ph = (it / p.stages) & 1;
                     mbar_wait_backoff(&empty[s], ph ^ 1, 256);
@@ -258,11 +273,33 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                                    ((uint32_t)(kTileM >> 4) << 24);
             int it = 0, ti = 0;
             if (p.b_resident && t_begin < t_end) { mbar_wait(b_full, 0); tc_fence_after(); }
-            for (int t = t_begin; t < t_end; ++t, ++ti) {
+            TileIter mit;
+            mit.init(p, t_begin);
+            for (int t = t_begin; t < t_end; ++t, ++ti, mit.next(p)) {
                 const int acc = two_acc ? (ti & 1) : 0, aph = (two_acc ? (ti >> 1) : ti) & 1;
                 mbar_wait(&tmem_empty[acc], aph ^ 1);        // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols;
+                if (p.halo) {
+                    const int s = it % p.stages, ph = (it / p.stages) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA + (size_t)s * p.a_stage_bytes);
+                    const uint32_t row_bytes = (uint32_t)p.g[mit.gi].Wt * 128u;
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        const uint64_t da = make_kmajor_sw128_desc(a0 + (uint32_t)kx * (uint32_t)p.box_stride + (uint32_t)ky * row_bytes);
+                        const uint64_t db = make_kmajor_sw128_desc(smem_u32(sB + (size_t)tap * b_tile_bytes));
+#pragma unroll
+                        for (int k = 0; k < kTileK / 16; ++k)
+                            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (tap | k) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);
+                    ++it;
+                    umma_commit(&tmem_full[acc]);
+                    continue;
+                }
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
                     const int s = it % p.stages, ph = (it / p.stages) & 1;
                     mbar_wait(&full[s], ph);
@@ -286,7 +323,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         const int et = threadIdx.x - 64;                    // 0..255
         constexpr bool kHalfIn = (ACT == EFFDET_ACT_SWISH) && !OUT_F32;
         int ti = 0, cur_n0 = -1, sbuf = 0;
-        uint8_t *my_stage = sStage + (size_t)ew * 2 * kStageBytes;
+        uint8_t *my_stage = sStage + (size_t)ew * p.stage_bufs * kStageBytes;
         TileIter tit;
         tit.init(p, t_begin);
         for (int t = t_begin; t < t_end; ++t, ++ti, tit.next(p)) {
@@ -358,7 +395,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                     }
                     if (tma_out) {
                         // [32 rows][128 B] SWIZZLE_128B: 16-byte chunk index ^= row & 7 (bank-conflict free)
-                        tma_store_wait_read<1>();           // the store that last read this buffer is done
+                        if (p.stage_bufs == 2) tma_store_wait_read<1>();   // the store that last read this buffer is done
+                        else tma_store_wait_read<0>();
                         __syncwarp();
                         uint8_t *dst = my_stage + (size_t)sbuf * kStageBytes + lane * 128;
 #pragma unroll
@@ -369,7 +407,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                         __syncwarp();
                         if (lane == 0)
                             tma_store_4d(&p.out_map[tc.gi], my_stage + (size_t)sbuf * kStageBytes, nbase, sx, sy, sb);
-                        sbuf ^= 1;
+                        sbuf = (sbuf + 1) & (p.stage_bufs - 1);
                     } else {
                         // rows whose byte stride is not a multiple of 16 (9*C floats, C = 90: the class head's
                         // concatenated output) cannot go through TMA: transpose through the warp's staging
@@ -437,7 +475,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                     }
                     if (tma_out) {
                         // [32 rows][64 B] SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3 (bank-conflict free)
-                        tma_store_wait_read<1>();
+                        if (p.stage_bufs == 2) tma_store_wait_read<1>();
+                        else tma_store_wait_read<0>();
                         __syncwarp();
                         uint8_t *dst = my_stage + (size_t)sbuf * kStageBytes + lane * 64;
 #pragma unroll
@@ -453,7 +492,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                         __syncwarp();
                         if (lane == 0)
                             tma_store_4d(&p.out_map[tc.gi], my_stage + (size_t)sbuf * kStageBytes, nbase, sx, sy, sb);
-                        sbuf ^= 1;
+                        sbuf = (sbuf + 1) & (p.stage_bufs - 1);
                     } else if (nvalid == 32 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
 #pragma unroll
                         for (int j8 = 0; j8 < 4; ++j8) {
@@ -971,15 +1010,27 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     p.act = d->act; p.out_f32 = d->out_dtype == EFFDET_F32; p.b_per_sample = d->weight_per_sample ? 1 : 0;
     p.scale = d->scale; p.shift = d->shift; p.keep = d->keep;
     const int b_tile_bytes = bn * kTileK * 2;
+    // halo mode: 3x3 stride 1, one K block per tap, one N tile, all nine weight tiles resident (<= 80 KiB)
+    p.halo = (d->kh == 3 && d->stride == 1 && Kpad == kTileK && Npad == bn && !d->weight_per_sample &&
+              9 * b_tile_bytes <= 80 * 1024 && getenv("EFFDET_NO_CONV_HALO") == nullptr) ? 1 : 0;
+    p.box_stride = 20 * 1024;                         // (16, 8+2) or (8, 16+2) pixels x 128 bytes
+    p.a_stage_bytes = p.halo ? 3 * p.box_stride : kATileBytes;
+    p.stage_bufs = 2;
+    if (p.halo) { p.b_resident = 1; p.acc_bufs = 2; p.tmem_cols = 2 * acc_pow2; }
     // <= 4 stages: with 64..128-wide N tiles two CTAs stay resident per SM, so one CTA's
     // epilogue overlaps the other's main loop
     // small tiles: 2 resident CTAs per SM (<= ~100 KiB each); wide tiles: 1
-    const int stage_out_bytes = kEpiWarps * 2 * 32 * 32 * (p.out_f32 ? 4 : 2);
-    const int two_ctas = p.tmem_cols <= 256;
-    const int ring_bytes = kATileBytes + (p.b_resident ? 0 : b_tile_bytes);
+    int stage_out_bytes = kEpiWarps * 2 * 32 * 32 * (p.out_f32 ? 4 : 2);
+    if (p.halo && 9 * b_tile_bytes + 2 * p.a_stage_bytes + stage_out_bytes + 6 * 1024 > 226 * 1024) {
+        p.stage_bufs = 1;                             // one staging buffer per epilogue warp
+        stage_out_bytes /= 2;
+    }
+    const int two_ctas = p.tmem_cols <= 256 && !p.halo;
+    const int ring_bytes = p.halo ? p.a_stage_bytes : kATileBytes + (p.b_resident ? 0 : b_tile_bytes);
     const int fixed_bytes = stage_out_bytes + (p.b_resident ? num_k * b_tile_bytes : 0) + 6 * 1024;
     int stages = ((two_ctas ? 113 : 226) * 1024 - fixed_bytes) / ring_bytes;
     if (stages > (p.b_resident ? 6 : 4)) stages = p.b_resident ? 6 : 4;
+    if (p.halo && stages > 2) stages = 2;
     // persistent kernel: the ring runs ahead ACROSS tiles, so its depth does not depend on the
     // number of K blocks of one tile (a 1x1 convolution with Cin <= 64 has a single K block)
     if (stages < 2) stages = 2;
@@ -998,7 +1049,14 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
         p.pad_l[i] = max((g.W - 1) * sd + d->kw - Win, 0) / 2;
         g.ldc = d->ldc[i] ? d->ldc[i] : d->Cout;
         g.y_batch_stride = d->y_batch_stride[i] ? d->y_batch_stride[i] : (long long)g.H * g.W * g.ldc;
-        if (d->weight_per_sample) { g.Bt = 1; pick_tile(g.W, g.H, 1, &g.Wt, &g.Ht, &g.Bt); if (g.Bt != 1) { g.Wt = 16; g.Ht = 8; g.Bt = 1; } }
+        if (p.halo) {
+            // one image per tile; 16 x 8 or 8 x 16 pixels (the tap offsets stay swizzle-atom aligned)
+            const long n_a = (long)cdiv(g.W, 16) * cdiv(g.H, 8), n_b = (long)cdiv(g.W, 8) * cdiv(g.H, 16);
+            g.Bt = 1;
+            if (n_a <= n_b) { g.Wt = 16; g.Ht = 8; } else { g.Wt = 8; g.Ht = 16; }
+            p.box_bytes[i] = g.Wt * (g.Ht + 2) * 128;
+        }
+        else if (d->weight_per_sample) { g.Bt = 1; pick_tile(g.W, g.H, 1, &g.Wt, &g.Ht, &g.Bt); if (g.Bt != 1) { g.Wt = 16; g.Ht = 8; g.Bt = 1; } }
         else pick_tile(g.W, g.H, d->B, &g.Wt, &g.Ht, &g.Bt);
         g.tiles_x = cdiv(g.W, g.Wt); g.tiles_y = cdiv(g.H, g.Ht); g.tiles_b = cdiv(d->B, g.Bt);
         g.lw = 31 - __builtin_clz(g.Wt); g.lh = 31 - __builtin_clz(g.Ht);
@@ -1010,7 +1068,8 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
         if (g.Wt * sd > 256 || g.Ht * sd > 256) return EFFDET_E_UNSUPPORTED;
         cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)d->B};
         cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * Win, (cuuint64_t)xbs * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kTileK, (cuuint32_t)(g.Wt * sd), (cuuint32_t)(g.Ht * sd), (cuuint32_t)g.Bt};
+        cuuint32_t box[4] = {(cuuint32_t)kTileK, (cuuint32_t)(g.Wt * sd), (cuuint32_t)((g.Ht + (p.halo ? 2 : 0)) * sd),
+                             (cuuint32_t)g.Bt};
         cuuint32_t es_in[4] = {1, (cuuint32_t)sd, (cuuint32_t)sd, 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = encode(&p.a_map[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d->x[i]), dims,
@@ -1052,7 +1111,7 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     }
     p.n_tiles = Npad / bn;
     p.total_tiles = tiles * p.n_tiles;
-    const int ctas_per_sm = (smem <= 113 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
+    const int ctas_per_sm = (smem <= 113 * 1024 && p.tmem_cols <= 256 && !p.halo) ? 2 : 1;
     int grid = kNumSMs * ctas_per_sm;
     if (grid > p.total_tiles) grid = p.total_tiles;
     static bool attr_set = false;
