@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#define EFFDET_PDL_TU_LEVEL 2
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -222,6 +223,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // Programmatic dependent launch: everything above (barriers, TMEM, tensor-map fetch) overlaps the
+    // tail of the previous kernel in the stream; nothing below may touch global memory before the
+    // previous grid has completed.  The next PDL kernel may start ITS prologue as soon as our CTAs
+    // have reached this point and an SM has room for it.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t acc_cols = (uint32_t)p.tmem_cols / (uint32_t)p.acc_bufs;
     const int two_acc = p.acc_bufs == 2;
@@ -531,6 +538,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
 __global__ void __launch_bounds__(256)
 weight_panel_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ panel, int taps, int Cin,
                     int Cout, int Kpad, int Npad, int mode, const float *__restrict__ gate, int nb) {
+    EFFDET_PDL_SYNC();
     const unsigned per = (unsigned)Npad * Kpad;
     const unsigned total = (unsigned)(gate ? nb : taps) * per;
     for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
@@ -555,6 +563,7 @@ weight_panel_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ pan
 __global__ void __launch_bounds__(256)
 gated_panel_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ panel, int Cin, int Cout,
                    int Kpad, int Npad, const float *__restrict__ gate, int nb) {
+    EFFDET_PDL_SYNC();
     __shared__ float tile[32][33];
     const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
@@ -610,6 +619,7 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint
 
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
+    EFFDET_PDL_SYNC();
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int n_boxes = p.block_n / 64;
@@ -764,6 +774,7 @@ struct alignas(64) WgHaloParams {
 
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
+    EFFDET_PDL_SYNC();
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int stage_bytes = 3 * p.box_stride + kATileBytes;          // 3 activation copies + dz tile
@@ -902,6 +913,7 @@ __global__ void wgrad_tc_reduce_kernel(const float *__restrict__ partial, int ns
                                        float *__restrict__ out, int accumulate,
                                        const float *__restrict__ bias_partial, int n_bias,
                                        float *__restrict__ dbias) {
+    EFFDET_PDL_SYNC();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         float t = 0.f;
@@ -970,15 +982,15 @@ extern "C" int effdet_conv_weight_panel(const float *w, void *panel, int taps, i
     if (gate) {
         int zs = B < 8 ? B : 8;             // samples per block column: enough blocks to fill the machine
         dim3 grid(Kpad / 32, (Npad + 31) / 32, zs);
-        gated_panel_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, static_cast<__nv_bfloat16 *>(panel), Cin, Cout,
-                                                                Kpad, Npad, gate, B);
+        EFFDET_CUDA(launch_pdl(gated_panel_kernel, dim3(grid), dim3(256), 0, as_stream(stream), w, static_cast<__nv_bfloat16 *>(panel), Cin, Cout,
+                                                                Kpad, Npad, gate, B));
         EFFDET_LAUNCHED();
         return EFFDET_OK;
     }
     unsigned blocks = cdiv(total, 256);
     if (blocks > (unsigned)kNumSMs * 16) blocks = kNumSMs * 16;
-    weight_panel_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, static_cast<__nv_bfloat16 *>(panel), taps, Cin,
-                                                               Cout, Kpad, Npad, mode, gate, B);
+    EFFDET_CUDA(launch_pdl(weight_panel_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), w, static_cast<__nv_bfloat16 *>(panel), taps, Cin,
+                                                               Cout, Kpad, Npad, mode, gate, B));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -1129,10 +1141,18 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     }
 #undef TC_INST
     cudaStream_t st = as_stream(stream);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = pdl_level() >= 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
 #define TC_LAUNCH(A)                                                                      \
     case A:                                                                               \
-        if (p.out_f32) conv_tc_kernel<A, true><<<grid, kTcThreads, smem, st>>>(p);        \
-        else conv_tc_kernel<A, false><<<grid, kTcThreads, smem, st>>>(p);                 \
+        if (p.out_f32) EFFDET_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<A, true>, p)); \
+        else EFFDET_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<A, false>, p));          \
         break;
     switch (d->act) {
         TC_LAUNCH(EFFDET_ACT_NONE) TC_LAUNCH(EFFDET_ACT_RELU) TC_LAUNCH(EFFDET_ACT_SWISH) TC_LAUNCH(EFFDET_ACT_SIGMOID)
@@ -1266,12 +1286,12 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
         }
         cudaStream_t hst = as_stream(stream);
         dim3 hgrid(zs, (d->Cout + 63) / 64);
-        conv_wgrad_halo_kernel<<<hgrid, 192, hsmem, hst>>>(hp);
+        EFFDET_CUDA(launch_pdl(conv_wgrad_halo_kernel, dim3(hgrid), dim3(192), hsmem, hst, hp));
         EFFDET_LAUNCHED();
         const size_t hn = (size_t)9 * d->Cin * d->Cout;
         const int hn_bias = d->dbias ? d->Cout : 0;
-        wgrad_tc_reduce_kernel<<<cdiv(hn + hn_bias, 256), 256, 0, hst>>>(d->partial, zs, hn, d->dweight, d->accumulate,
-                                                                        hp.bias_partial, hn_bias, d->dbias);
+        EFFDET_CUDA(launch_pdl(wgrad_tc_reduce_kernel, dim3(cdiv(hn + hn_bias, 256)), dim3(256), 0, hst, d->partial, zs, hn, d->dweight, d->accumulate,
+                                                                        hp.bias_partial, hn_bias, d->dbias));
         EFFDET_LAUNCHED();
         return EFFDET_OK;
     }
@@ -1328,12 +1348,12 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
     const int taps = d->kh * d->kw;
     dim3 grid(z, p.pair_taps ? (taps + 1) / 2 : taps * mt, (d->Cout + bn - 1) / bn);
     cudaStream_t st = as_stream(stream);
-    conv_wgrad_tc_kernel<<<grid, 192, smem, st>>>(p);
+    EFFDET_CUDA(launch_pdl(conv_wgrad_tc_kernel, dim3(grid), dim3(192), smem, st, p));
     EFFDET_LAUNCHED();
     const size_t n = (size_t)taps * d->Cin * d->Cout;
     const int n_bias = d->dbias ? d->Cout : 0;
-    wgrad_tc_reduce_kernel<<<cdiv(n + n_bias, 256), 256, 0, st>>>(d->partial, z, n, d->dweight, d->accumulate,
-                                                                 p.bias_partial, n_bias, d->dbias);
+    EFFDET_CUDA(launch_pdl(wgrad_tc_reduce_kernel, dim3(cdiv(n + n_bias, 256)), dim3(256), 0, st, d->partial, z, n, d->dweight, d->accumulate,
+                                                                 p.bias_partial, n_bias, d->dbias));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }

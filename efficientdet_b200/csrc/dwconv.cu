@@ -6,6 +6,7 @@
 //   wbifpn_add_kernel  layers.py:26-31          fast normalised fusion / keras Add
 //   bifpn_node_kernel  model.py:154-194, :226-266  upsample|maxpool-on-load + fusion +
 //                      DepthwiseConv3x3 + BN + ReLU in one pass (shared-memory halo tile)
+#define EFFDET_PDL_TU_LEVEL 2
 #include "common.cuh"
 
 namespace effdet {
@@ -299,6 +300,7 @@ se_gate_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_hw,
                const float *__restrict__ w1, const float *__restrict__ b1,
                const float *__restrict__ w2, const float *__restrict__ b2,
                float *__restrict__ gate, int C, int R) {
+    EFFDET_PDL_SYNC();
     extern __shared__ float sm[];      // mean[C] | r[R] | part[4 * kSeThreads]
     float *mean = sm, *r = sm + C, *part = sm + C + R;
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -625,8 +627,8 @@ extern "C" int effdet_se_gate(const float *se_sum, int se_blocks, float inv_hw, 
                      reinterpret_cast<uintptr_t>(gate)) & 15) == 0, "w2 / b2 / gate must be 16B aligned");
     const size_t sm = (size_t)(C + R + 4 * kSeThreads) * sizeof(float);
     EFFDET_REQUIRE(sm <= 48 * 1024, "C + R too large");
-    se_gate_kernel<<<B, kSeThreads, sm, as_stream(stream)>>>(se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate,
-                                                      C, R);
+    EFFDET_CUDA(launch_pdl(se_gate_kernel, dim3(B), dim3(kSeThreads), sm, as_stream(stream), se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate,
+                                                      C, R));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }

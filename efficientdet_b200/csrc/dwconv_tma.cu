@@ -16,6 +16,7 @@
 // along the channel pairs: a warp reads / writes whole 64..128-byte pixel rows.
 // SE partial sums are reduced in a fixed order (registers -> shared rows -> one (image, tile,
 // channel) partial) so the result is bit-reproducible run to run.
+#define EFFDET_PDL_TU_LEVEL 2
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -80,6 +81,7 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    EFFDET_PDL_SYNC();
 
     auto issue = [&](int t, int stage) {
         int r = t;
@@ -244,7 +246,7 @@ static int launch_dw_tma(const void *x, const float *w, const float *scale, cons
         }                                                                                                  \
         int grid = kNumSMs * per_sm;                                                                       \
         if (grid > p.total_tiles) grid = p.total_tiles;                                                    \
-        kern<<<grid, Cfg::NT, Cfg::SMEM, st>>>(p);                                                         \
+        EFFDET_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::NT), Cfg::SMEM, st, p));                        \
     }
     if (act == EFFDET_ACT_SWISH) DWT_LAUNCH(EFFDET_ACT_SWISH)
     else if (act == EFFDET_ACT_RELU) DWT_LAUNCH(EFFDET_ACT_RELU)
@@ -288,6 +290,7 @@ dw_wgrad_tma_kernel(const __grid_constant__ DwWgParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    EFFDET_PDL_SYNC();
     const int cb = blockIdx.y;
     auto issue = [&](int t, int stage) {
         int r = t;
@@ -407,7 +410,7 @@ static int launch_dw_wgrad_tma(const void *x, const void *dz, float *partial, in
         attr = true;
     }
     dim3 grid(nsplit, (C + Cfg::CB - 1) / Cfg::CB);
-    kern<<<grid, Cfg::NT, SMEM, st>>>(p);
+    EFFDET_CUDA(launch_pdl(kern, grid, dim3(Cfg::NT), SMEM, st, p));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -464,6 +467,7 @@ bifpn_node_tma_kernel(const __grid_constant__ NodeParams p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    EFFDET_PDL_SYNC();
 
     auto issue = [&](int t, int stage) {
         int r = t;
@@ -640,7 +644,7 @@ static int launch_node_tma(const void *in0, const void *in1, const void *in2, co
     }
     int grid = kNumSMs * per_sm;
     if (grid > p.total_tiles) grid = p.total_tiles;
-    kern<<<grid, Cfg::NT, Cfg::SMEM, st>>>(p);
+    EFFDET_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::NT), Cfg::SMEM, st, p));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }

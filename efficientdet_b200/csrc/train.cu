@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256)
 resample_fuse_kernel(const T *__restrict__ in0, int mode0, const T *__restrict__ in1,
                      const T *__restrict__ in2, const float *__restrict__ fw, float eps,
                      T *__restrict__ out, int B, int H, int W, int C) {
+    EFFDET_PDL_SYNC();
     const int nvec = C / CV;
     const size_t total = (size_t)B * H * W * nvec;
     const FuseCoef fc = fuse_coef(fw, in2 ? 3 : 2, eps);
@@ -130,6 +131,7 @@ __global__ void colreduce_kernel(const T *__restrict__ x, const T *__restrict__ 
                                  const T *__restrict__ dy, const float *__restrict__ mean,
                                  const float *__restrict__ invstd, size_t rows, int C,
                                  int rows_per_block, float *__restrict__ partial) {
+    EFFDET_PDL_SYNC();
     extern __shared__ float sred[];      // PY * 2 * C
     const int nvec = C / CV, PY = blockDim.x / nvec;
     const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec, c = cv * CV;
@@ -197,6 +199,7 @@ __global__ void bn_train_finalize_kernel(const float *__restrict__ partial, int 
                                          float *__restrict__ moving_var, float *__restrict__ scale,
                                          float *__restrict__ shift, float *__restrict__ save_mean,
                                          float *__restrict__ save_invstd, int C) {
+    EFFDET_PDL_SYNC();
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per channel
     if (c >= C) return;
     const double s1 = warp_block_sum(partial, nblk, 2 * (size_t)C, c);
@@ -222,6 +225,7 @@ __global__ void bn_train_finalize_kernel(const float *__restrict__ partial, int 
 // C = fold * Cout: the matrix was viewed as (rows/fold, fold*Cout) to get vectorisable rows
 __global__ void colsum_finalize_kernel(const float *__restrict__ partial, int nblk, int C, int fold,
                                        float *__restrict__ out, int accumulate) {
+    EFFDET_PDL_SYNC();
     const int Cout = C / fold;
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per channel
     if (c >= Cout) return;
@@ -237,6 +241,7 @@ __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partial, int nb
                                        const float *__restrict__ mean,
                                        const float *__restrict__ invstd, float *__restrict__ k123,
                                        float *__restrict__ dgamma, float *__restrict__ dbeta, int C) {
+    EFFDET_PDL_SYNC();
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per channel
     if (c >= C) return;
     const double s1 = warp_block_sum(partial, nblk, 2 * (size_t)C, c);
@@ -256,6 +261,7 @@ __global__ void __launch_bounds__(256)
 scale_shift_act_kernel(const T *__restrict__ z, const float *__restrict__ scale,
                        const float *__restrict__ shift, T *__restrict__ y, size_t nvec_total,
                        int C, int act) {
+    EFFDET_PDL_SYNC();
     const unsigned nvec = C / CV;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
         const int c = (int)((unsigned)i % nvec) * CV;        // nvec_total < 2^32 (checked by the launcher)
@@ -274,6 +280,7 @@ template <typename T, int CV>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ y, const T *__restrict__ z,
                     const float *__restrict__ k123, T *__restrict__ dz, size_t nvec_total, int C) {
+    EFFDET_PDL_SYNC();
     const unsigned nvec = C / CV;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
         const int c = (int)((unsigned)i % nvec) * CV;
@@ -295,6 +302,7 @@ bn_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ y, const T *
 template <typename T, int CV>
 __global__ void dw_wgrad_kernel(const T *__restrict__ f, const T *__restrict__ dz, int B, int H, int W,
                                 int C, int pix_per_block, float *__restrict__ partial) {
+    EFFDET_PDL_SYNC();
     extern __shared__ float sred[];      // PY * 9 * C
     const int nvec = C / CV, PY = blockDim.x / nvec;
     const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec, c = cv * CV;
@@ -339,6 +347,7 @@ __global__ void dw_wgrad_kernel(const T *__restrict__ f, const T *__restrict__ d
 }
 __global__ void sum_partials_kernel(const float *__restrict__ partial, int nblk, int n,
                                     float *__restrict__ out, int accumulate) {
+    EFFDET_PDL_SYNC();
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per element
     if (i >= n) return;
     const double t = warp_block_sum(partial, nblk, (size_t)n, (size_t)i);
@@ -353,6 +362,7 @@ __global__ void __launch_bounds__(256)
 fuse_bwd_kernel(const T *__restrict__ df, int which, int mode0, const T *__restrict__ in0,
                 const float *__restrict__ fw, int n_in, float eps, T *__restrict__ dst,
                 int accumulate, int B, int H, int W, int C) {
+    EFFDET_PDL_SYNC();
     // H, W = resolution of df (the node's resolution)
     const FuseCoef fc = fuse_coef(fw, n_in, eps);
     const float coef = fw ? fc.c[which] / fc.inv : 1.f;
@@ -426,6 +436,7 @@ __global__ void __launch_bounds__(256)
 fuse_wgrad_kernel(const T *__restrict__ df, const T *__restrict__ f, const T *__restrict__ in0,
                   int mode0, const T *__restrict__ in1, const T *__restrict__ in2, int B, int H,
                   int W, int C, float *__restrict__ partial) {
+    EFFDET_PDL_SYNC();
     __shared__ float sh[4][8];
     const int nvec = C / CV;
     const size_t total = (size_t)B * H * W * nvec;
@@ -469,6 +480,7 @@ fuse_wgrad_kernel(const T *__restrict__ df, const T *__restrict__ f, const T *__
 __global__ void fuse_wgrad_finalize_kernel(const float *__restrict__ partial, int nblk,
                                            const float *__restrict__ fw, int n_in, float eps,
                                            float *__restrict__ dw) {
+    EFFDET_PDL_SYNC();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double s[4] = {0, 0, 0, 0};
     for (int b = 0; b < nblk; ++b)
@@ -482,6 +494,7 @@ __global__ void fuse_wgrad_finalize_kernel(const float *__restrict__ partial, in
 __global__ void __launch_bounds__(256)
 sgd_momentum_kernel(float *__restrict__ w, const float *__restrict__ g, float *__restrict__ v,
                     size_t n, float lr_t, float momentum, float grad_scale) {
+    EFFDET_PDL_SYNC();
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
         const float vel = momentum * v[i] - lr_t * (g[i] * grad_scale);
         v[i] = vel;
@@ -491,6 +504,7 @@ sgd_momentum_kernel(float *__restrict__ w, const float *__restrict__ g, float *_
 
 // flips a depthwise kernel (k,k,C) spatially: out[k*k-1-t][c] = in[t][c]
 __global__ void flip_taps_kernel(const float *__restrict__ in, float *__restrict__ out, int taps, int n) {
+    EFFDET_PDL_SYNC();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= taps * n) return;
     const int t = i / n, r = i - t * n;
@@ -499,6 +513,7 @@ __global__ void flip_taps_kernel(const float *__restrict__ in, float *__restrict
 // dense conv weight (taps,Cin,Cout) -> (taps flipped, Cout, Cin)   (data-gradient kernel)
 __global__ void conv_weight_transpose_kernel(const float *__restrict__ in, float *__restrict__ out,
                                              int taps, int Cin, int Cout) {
+    EFFDET_PDL_SYNC();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)taps * Cin * Cout) return;
     const int co = (int)(i % Cout), ci = (int)((i / Cout) % Cin), t = (int)(i / ((size_t)Cout * Cin));
@@ -512,6 +527,7 @@ template <typename T, int CV>
 __global__ void __launch_bounds__(256)
 zero_insert_kernel(const T *__restrict__ dz, T *__restrict__ out, int B, int Ho, int Wo, int C, int H, int W,
                    int ay, int ax) {
+    EFFDET_PDL_SYNC();
     const int nvec = C / CV;
     const size_t total = (size_t)B * H * W * nvec;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
@@ -552,9 +568,9 @@ extern "C" int effdet_resample_fuse(const void *in0, int mode0, const void *in1,
     EFFDET_REQUIRE(a16(in0) && a16(in1) && (!in2 || a16(in2)) && a16(out), "16B alignment");
     cudaStream_t st = as_stream(stream);
     DISPATCH_T(dtype,
-        (resample_fuse_kernel<float, 4><<<grid_for((size_t)B * H * W * C / 4), 256, 0, st>>>(
+        ((void)launch_pdl(resample_fuse_kernel<float, 4>, dim3(grid_for((size_t)B * H * W * C / 4)), dim3(256), 0, st, 
             (const float *)in0, mode0, (const float *)in1, (const float *)in2, w, eps, (float *)out, B, H, W, C)),
-        (resample_fuse_kernel<__nv_bfloat16, 8><<<grid_for((size_t)B * H * W * C / 8), 256, 0, st>>>(
+        ((void)launch_pdl(resample_fuse_kernel<__nv_bfloat16, 8>, dim3(grid_for((size_t)B * H * W * C / 8)), dim3(256), 0, st, 
             (const __nv_bfloat16 *)in0, mode0, (const __nv_bfloat16 *)in1, (const __nv_bfloat16 *)in2, w,
             eps, (__nv_bfloat16 *)out, B, H, W, C)))
     EFFDET_LAUNCHED();
@@ -588,8 +604,8 @@ static int launch_colreduce(const void *x, const void *y, const void *dy, const 
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return fail(EFFDET_E_CUDA, "colreduce: smem attribute: %s", cudaGetErrorString(e));
     }
-    colreduce_kernel<T, CV, MODE><<<nblk, nvec * PY, sm, st>>>(
-        (const T *)x, (const T *)y, (const T *)dy, mean, invstd, rows, C, rpb, partial);
+    EFFDET_CUDA(launch_pdl(colreduce_kernel<T, CV, MODE>, dim3(nblk), dim3(nvec * PY), sm, st, 
+        (const T *)x, (const T *)y, (const T *)dy, mean, invstd, rows, C, rpb, partial));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -608,9 +624,9 @@ extern "C" int effdet_bn_train_stats(const void *z, size_t rows, int C, const fl
         rc = (launch_colreduce<float, 4, RED_STATS>(z, nullptr, nullptr, nullptr, nullptr, rows, C, nblk, partial, st)),
         rc = (launch_colreduce<__nv_bfloat16, 8, RED_STATS>(z, nullptr, nullptr, nullptr, nullptr, rows, C, nblk, partial, st)))
     if (rc) return rc;
-    bn_train_finalize_kernel<<<cdiv((size_t)C * 32, 256), 256, 0, st>>>(partial, nblk, (double)rows, gamma, beta, eps,
+    EFFDET_CUDA(launch_pdl(bn_train_finalize_kernel, dim3(cdiv((size_t)C * 32, 256)), dim3(256), 0, st, partial, nblk, (double)rows, gamma, beta, eps,
                                                            momentum, moving_mean, moving_var, scale,
-                                                           shift, save_mean, save_invstd, C);
+                                                           shift, save_mean, save_invstd, C));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -638,9 +654,9 @@ extern "C" int effdet_dwconv_bn_stats(const void *x, const float *kernel, const 
     const int rc = dwconv_bf16_tma(x, kernel, ones, zeros, z, nullptr, B, H, W, C, k, stride, EFFDET_ACT_NONE, st, partial);
     if (rc) return rc;
     const int Ho = (H + stride - 1) / stride, Wo = (W + stride - 1) / stride;
-    bn_train_finalize_kernel<<<cdiv((size_t)C * 32, 256), 256, 0, st>>>(partial, nblk, (double)B * Ho * Wo, gamma, beta,
+    EFFDET_CUDA(launch_pdl(bn_train_finalize_kernel, dim3(cdiv((size_t)C * 32, 256)), dim3(256), 0, st, partial, nblk, (double)B * Ho * Wo, gamma, beta,
                                                                       eps, momentum, moving_mean, moving_var, scale,
-                                                                      shift, save_mean, save_invstd, C);
+                                                                      shift, save_mean, save_invstd, C));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -652,9 +668,9 @@ extern "C" int effdet_scale_shift_act(const void *z, const float *scale, const f
     if (rows == 0) return EFFDET_OK;
     cudaStream_t st = as_stream(stream);
     DISPATCH_T(dtype,
-        (scale_shift_act_kernel<float, 4><<<grid_for(rows * C / 4), 256, 0, st>>>(
+        ((void)launch_pdl(scale_shift_act_kernel<float, 4>, dim3(grid_for(rows * C / 4)), dim3(256), 0, st, 
             (const float *)z, scale, shift, (float *)y, rows * C / 4, C, act)),
-        (scale_shift_act_kernel<__nv_bfloat16, 8><<<grid_for(rows * C / 8), 256, 0, st>>>(
+        ((void)launch_pdl(scale_shift_act_kernel<__nv_bfloat16, 8>, dim3(grid_for(rows * C / 8)), dim3(256), 0, st, 
             (const __nv_bfloat16 *)z, scale, shift, (__nv_bfloat16 *)y, rows * C / 8, C, act)))
     EFFDET_LAUNCHED();
     return EFFDET_OK;
@@ -682,14 +698,14 @@ extern "C" int effdet_bn_relu_backward(const void *dy, const void *y, const void
             rc = (launch_colreduce<float, 4, RED_BNBWD>(z, y, dy, save_mean, save_invstd, rows, C, nblk, partial, st)),
             rc = (launch_colreduce<__nv_bfloat16, 8, RED_BNBWD>(z, y, dy, save_mean, save_invstd, rows, C, nblk, partial, st)))
         if (rc) return rc;
-        bn_bwd_finalize_kernel<<<cdiv((size_t)C * 32, 256), 256, 0, st>>>(partial, nblk, (double)rows, gamma, save_mean,
-                                                             save_invstd, k123, dgamma, dbeta, C);
+        EFFDET_CUDA(launch_pdl(bn_bwd_finalize_kernel, dim3(cdiv((size_t)C * 32, 256)), dim3(256), 0, st, partial, nblk, (double)rows, gamma, save_mean,
+                                                             save_invstd, k123, dgamma, dbeta, C));
         EFFDET_LAUNCHED();
     }
     DISPATCH_T(dtype,
-        (bn_bwd_apply_kernel<float, 4><<<grid_for(rows * C / 4), 256, 0, st>>>(
+        ((void)launch_pdl(bn_bwd_apply_kernel<float, 4>, dim3(grid_for(rows * C / 4)), dim3(256), 0, st, 
             (const float *)dy, (const float *)y, (const float *)z, k123, (float *)dz, rows * C / 4, C)),
-        (bn_bwd_apply_kernel<__nv_bfloat16, 8><<<grid_for(rows * C / 8), 256, 0, st>>>(
+        ((void)launch_pdl(bn_bwd_apply_kernel<__nv_bfloat16, 8>, dim3(grid_for(rows * C / 8)), dim3(256), 0, st, 
             (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)y, (const __nv_bfloat16 *)z, k123,
             (__nv_bfloat16 *)dz, rows * C / 8, C)))
     EFFDET_LAUNCHED();
@@ -700,6 +716,7 @@ extern "C" int effdet_bn_relu_backward(const void *dy, const void *y, const void
  * effdet_colsum for the few rows that do not fill a whole vector-aligned fold. */
 template <typename T>
 __global__ void colsum_tail_kernel(const T *__restrict__ x, size_t row0, int nrows, int C, float *__restrict__ out) {
+    EFFDET_PDL_SYNC();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float t = 0.f;
@@ -711,8 +728,8 @@ extern "C" int effdet_colsum_tail(const void *x, size_t row0, int nrows, int C, 
     if (nrows == 0) return EFFDET_OK;
     cudaStream_t st = as_stream(stream);
     DISPATCH_T(dtype,
-        (colsum_tail_kernel<float><<<cdiv(C, 128), 128, 0, st>>>((const float *)x, row0, nrows, C, out)),
-        (colsum_tail_kernel<__nv_bfloat16><<<cdiv(C, 128), 128, 0, st>>>((const __nv_bfloat16 *)x, row0, nrows, C, out)))
+        ((void)launch_pdl(colsum_tail_kernel<float>, dim3(cdiv(C, 128)), dim3(128), 0, st, (const float *)x, row0, nrows, C, out)),
+        ((void)launch_pdl(colsum_tail_kernel<__nv_bfloat16>, dim3(cdiv(C, 128)), dim3(128), 0, st, (const __nv_bfloat16 *)x, row0, nrows, C, out)))
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -730,7 +747,7 @@ extern "C" int effdet_colsum(const void *x, size_t rows, int C, int fold, float 
         rc = (launch_colreduce<float, 4, RED_SUM>(x, nullptr, nullptr, nullptr, nullptr, rows, C, nblk, partial, st)),
         rc = (launch_colreduce<__nv_bfloat16, 8, RED_SUM>(x, nullptr, nullptr, nullptr, nullptr, rows, C, nblk, partial, st)))
     if (rc) return rc;
-    colsum_finalize_kernel<<<cdiv((size_t)(C / fold) * 32, 256), 256, 0, st>>>(partial, nblk, C, fold, out, accumulate);
+    EFFDET_CUDA(launch_pdl(colsum_finalize_kernel, dim3(cdiv((size_t)(C / fold) * 32, 256)), dim3(256), 0, st, partial, nblk, C, fold, out, accumulate));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -763,7 +780,7 @@ extern "C" int effdet_dw_wgrad(const void *f, const void *dz, int B, int H, int 
         EFFDET_REQUIRE(nblk == effdet_dw_wgrad_blocks(B, H, W, C, dtype), "nblk must come from effdet_dw_wgrad_blocks");
         const int rc = dw_wgrad_bf16_tma(f, dz, partial, nblk, B, H, W, C, 3, 1, st);
         if (rc) return rc;
-        sum_partials_kernel<<<cdiv((size_t)9 * C * 32, 256), 256, 0, st>>>(partial, nblk, 9 * C, dkernel, 0);
+        EFFDET_CUDA(launch_pdl(sum_partials_kernel, dim3(cdiv((size_t)9 * C * 32, 256)), dim3(256), 0, st, partial, nblk, 9 * C, dkernel, 0));
         EFFDET_LAUNCHED();
         return EFFDET_OK;
     }
@@ -777,15 +794,15 @@ extern "C" int effdet_dw_wgrad(const void *f, const void *dz, int B, int H, int 
     const size_t sm = (size_t)PY * 9 * C * sizeof(float);
     if (dtype == EFFDET_F32) {
         if (sm > 48 * 1024) EFFDET_CUDA(cudaFuncSetAttribute(dw_wgrad_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        dw_wgrad_kernel<float, 4><<<nblk, nvec * PY, sm, st>>>((const float *)f, (const float *)dz, B, H, W, C, ppb, partial);
+        EFFDET_CUDA(launch_pdl(dw_wgrad_kernel<float, 4>, dim3(nblk), dim3(nvec * PY), sm, st, (const float *)f, (const float *)dz, B, H, W, C, ppb, partial));
     } else if (dtype == EFFDET_BF16) {
         if (sm > 48 * 1024) EFFDET_CUDA(cudaFuncSetAttribute(dw_wgrad_kernel<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        dw_wgrad_kernel<__nv_bfloat16, 8><<<nblk, nvec * PY, sm, st>>>((const __nv_bfloat16 *)f, (const __nv_bfloat16 *)dz, B, H, W, C, ppb, partial);
+        EFFDET_CUDA(launch_pdl(dw_wgrad_kernel<__nv_bfloat16, 8>, dim3(nblk), dim3(nvec * PY), sm, st, (const __nv_bfloat16 *)f, (const __nv_bfloat16 *)dz, B, H, W, C, ppb, partial));
     } else {
         return fail(EFFDET_E_INVALID, "effdet_dw_wgrad: bad dtype%s", "");
     }
     EFFDET_LAUNCHED();
-    sum_partials_kernel<<<cdiv((size_t)9 * C * 32, 256), 256, 0, st>>>(partial, nblk, 9 * C, dkernel, 0);
+    EFFDET_CUDA(launch_pdl(sum_partials_kernel, dim3(cdiv((size_t)9 * C * 32, 256)), dim3(256), 0, st, partial, nblk, 9 * C, dkernel, 0));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -804,9 +821,9 @@ extern "C" int effdet_fuse_backward_input(const void *df, int which, int mode0, 
     if (which == 0 && mode0 == 1) n /= 4;
     if (which == 0 && mode0 == 2) n *= 4;
     DISPATCH_T(dtype,
-        (fuse_bwd_kernel<float, 4><<<grid_for(n / 4), 256, 0, st>>>(
+        ((void)launch_pdl(fuse_bwd_kernel<float, 4>, dim3(grid_for(n / 4)), dim3(256), 0, st, 
             (const float *)df, which, mode0, (const float *)in0, w, n_inputs, eps, (float *)dst, accumulate, B, H, W, C)),
-        (fuse_bwd_kernel<__nv_bfloat16, 8><<<grid_for(n / 8), 256, 0, st>>>(
+        ((void)launch_pdl(fuse_bwd_kernel<__nv_bfloat16, 8>, dim3(grid_for(n / 8)), dim3(256), 0, st, 
             (const __nv_bfloat16 *)df, which, mode0, (const __nv_bfloat16 *)in0, w, n_inputs, eps,
             (__nv_bfloat16 *)dst, accumulate, B, H, W, C)))
     EFFDET_LAUNCHED();
@@ -825,14 +842,14 @@ extern "C" int effdet_fuse_backward_weights(const void *df, const void *f, const
     const size_t n = (size_t)B * H * W * C;
     unsigned nblk;
     DISPATCH_T(dtype,
-        (nblk = grid_for(n / 4), fuse_wgrad_kernel<float, 4><<<nblk, 256, 0, st>>>(
+        (nblk = grid_for(n / 4), (void)launch_pdl(fuse_wgrad_kernel<float, 4>, dim3(nblk), dim3(256), 0, st, 
             (const float *)df, (const float *)f, (const float *)in0, mode0, (const float *)in1,
             (const float *)in2, B, H, W, C, partial)),
-        (nblk = grid_for(n / 8), fuse_wgrad_kernel<__nv_bfloat16, 8><<<nblk, 256, 0, st>>>(
+        (nblk = grid_for(n / 8), (void)launch_pdl(fuse_wgrad_kernel<__nv_bfloat16, 8>, dim3(nblk), dim3(256), 0, st, 
             (const __nv_bfloat16 *)df, (const __nv_bfloat16 *)f, (const __nv_bfloat16 *)in0, mode0,
             (const __nv_bfloat16 *)in1, (const __nv_bfloat16 *)in2, B, H, W, C, partial)))
     EFFDET_LAUNCHED();
-    fuse_wgrad_finalize_kernel<<<1, 32, 0, st>>>(partial, (int)nblk, w, n_in, eps, dw);
+    EFFDET_CUDA(launch_pdl(fuse_wgrad_finalize_kernel, dim3(1), dim3(32), 0, st, partial, (int)nblk, w, n_in, eps, dw));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -848,8 +865,8 @@ extern "C" int effdet_zero_insert(const void *dz, void *out, int B, int Ho, int 
     cudaStream_t st = as_stream(stream);
     const size_t n = (size_t)B * H * W * C;
     DISPATCH_T(dtype,
-        (zero_insert_kernel<float, 4><<<grid_for(n / 4), 256, 0, st>>>((const float *)dz, (float *)out, B, Ho, Wo, C, H, W, ay, ax)),
-        (zero_insert_kernel<__nv_bfloat16, 8><<<grid_for(n / 8), 256, 0, st>>>((const __nv_bfloat16 *)dz, (__nv_bfloat16 *)out, B, Ho, Wo, C, H, W, ay, ax)))
+        ((void)launch_pdl(zero_insert_kernel<float, 4>, dim3(grid_for(n / 4)), dim3(256), 0, st, (const float *)dz, (float *)out, B, Ho, Wo, C, H, W, ay, ax)),
+        ((void)launch_pdl(zero_insert_kernel<__nv_bfloat16, 8>, dim3(grid_for(n / 8)), dim3(256), 0, st, (const __nv_bfloat16 *)dz, (__nv_bfloat16 *)out, B, Ho, Wo, C, H, W, ay, ax)))
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -858,14 +875,14 @@ extern "C" int effdet_sgd_momentum_step(float *w, const float *g, float *v, size
                                         float momentum, float grad_scale, void *stream) {
     if (n == 0) return EFFDET_OK;
     EFFDET_REQUIRE(w && g && v, "null pointer");
-    sgd_momentum_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(w, g, v, n, lr_t, momentum, grad_scale);
+    EFFDET_CUDA(launch_pdl(sgd_momentum_kernel, dim3(grid_for(n)), dim3(256), 0, as_stream(stream), w, g, v, n, lr_t, momentum, grad_scale));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
 
 extern "C" int effdet_flip_taps(const float *in, float *out, int taps, int n, void *stream) {
     EFFDET_REQUIRE(in && out && taps > 0 && n > 0, "bad arguments");
-    flip_taps_kernel<<<cdiv((size_t)taps * n, 256), 256, 0, as_stream(stream)>>>(in, out, taps, n);
+    EFFDET_CUDA(launch_pdl(flip_taps_kernel, dim3(cdiv((size_t)taps * n, 256)), dim3(256), 0, as_stream(stream), in, out, taps, n));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -873,8 +890,8 @@ extern "C" int effdet_flip_taps(const float *in, float *out, int taps, int n, vo
 extern "C" int effdet_conv_weight_transpose(const float *in, float *out, int taps, int Cin, int Cout,
                                             void *stream) {
     EFFDET_REQUIRE(in && out && taps > 0 && Cin > 0 && Cout > 0, "bad arguments");
-    conv_weight_transpose_kernel<<<cdiv((size_t)taps * Cin * Cout, 256), 256, 0, as_stream(stream)>>>(
-        in, out, taps, Cin, Cout);
+    EFFDET_CUDA(launch_pdl(conv_weight_transpose_kernel, dim3(cdiv((size_t)taps * Cin * Cout, 256)), dim3(256), 0, as_stream(stream), 
+        in, out, taps, Cin, Cout));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
