@@ -46,6 +46,19 @@ def peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def measured_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes) of `kernel` from the committed ncu --set full capture of this workload
+    (profiles/traffic.json), or None when no capture of that kernel has been taken."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        e = json.load(open(p)).get(workload)
+    except (OSError, ValueError):
+        return None
+    if not e or e.get("kernel") != kernel:
+        return None
+    return e["bytes_per_launch"]
+
+
 class Clocks:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -192,7 +205,7 @@ def run_ours(args, rank, world):
     else:
         roof = dict(bound="hbm", achieved=dom["bytes"] / (dom["ms"] * 1e-3) / 1e9, peak=hbm, unit="GB/s")
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof.update(traffic=None, kernel=dom_kind, launches=dom["n"], share_of_step=dom["ms"] / total_ms,
+    roof.update(traffic=measured_traffic(args.workload, dom_kind), kernel=dom_kind, launches=dom["n"], share_of_step=dom["ms"] / total_ms,
                 peak_source=peak_src,
                 per_kind_ms={k_: round(v["ms"], 4) for k_, v in sorted(by_kind.items())})
 

@@ -101,6 +101,8 @@ _SIGNATURES = {
                                c_int, c_int, c_void_p],
     "effdet_spatial_sum": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "effdet_se_apply": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "effdet_drop_connect_scales": [c_void_p, c_int, c_int, ctypes.c_ulonglong, c_void_p, c_void_p, c_void_p],
+    "effdet_sample_scale_add": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_size_t, c_int, c_void_p],
     "effdet_se_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                            c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],

@@ -28,15 +28,29 @@ __global__ void bn_fold_kernel(const float *__restrict__ gamma, const float *__r
 
 // ------------------------------------------------------------------ stem
 // one thread = one output pixel x all C0 channels (C0 <= 64); weights broadcast from smem
-template <typename TO, int C0>
+// TI = float: normalised pixels; TI = uint8_t: raw letterboxed RGB bytes, normalised on the fly through
+// lut[c][byte] = ((byte / 255) - mean_c) / std_c (train_tpu.py:135-140, generators/common.py:418-429), computed
+// by the host in float32 exactly as the reference does -> bit-identical to feeding the normalised image
+template <typename TI> struct StemPix;
+template <> struct StemPix<float> {
+    static __device__ __forceinline__ float get(const float *p, const float *, int) { return *p; }
+};
+template <> struct StemPix<uint8_t> {
+    static __device__ __forceinline__ float get(const uint8_t *p, const float *lut, int c) { return lut[c * 256 + *p]; }
+};
+
+template <typename TI, typename TO, int C0>
 __global__ void __launch_bounds__(128)
-stem_conv_kernel(const float *__restrict__ img, const float *__restrict__ w,
+stem_conv_kernel(const TI *__restrict__ img, const float *__restrict__ lut, const float *__restrict__ w,
                  const float *__restrict__ scale, const float *__restrict__ shift,
                  TO *__restrict__ out, int B, int H, int W, int Ho, int Wo, int pad_t, int pad_l) {
     __shared__ float sw[27 * C0];
     __shared__ float ss[C0], sb[C0];
+    __shared__ float slut[sizeof(TI) == 1 ? 768 : 1];
     for (int i = threadIdx.x; i < 27 * C0; i += blockDim.x) sw[i] = w[i];
     for (int i = threadIdx.x; i < C0; i += blockDim.x) { ss[i] = scale[i]; sb[i] = shift[i]; }
+    if (sizeof(TI) == 1)
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) slut[i] = lut[i];
     __syncthreads();
     const size_t total = (size_t)B * Ho * Wo;
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -53,8 +67,9 @@ stem_conv_kernel(const float *__restrict__ img, const float *__restrict__ w,
         for (int kx = 0; kx < 3; ++kx) {
             const int ix = ox * 2 - pad_l + kx;
             if (ix < 0 || ix >= W) continue;
-            const float *px = img + (((size_t)b * H + iy) * W + ix) * 3;
-            const float v0 = px[0], v1 = px[1], v2 = px[2];
+            const TI *px = img + (((size_t)b * H + iy) * W + ix) * 3;
+            const float v0 = StemPix<TI>::get(px, slut, 0), v1 = StemPix<TI>::get(px + 1, slut, 1),
+                        v2 = StemPix<TI>::get(px + 2, slut, 2);
             const float *wk = sw + (ky * 3 + kx) * 3 * C0;
 #pragma unroll
             for (int c = 0; c < C0; ++c)
@@ -75,9 +90,9 @@ stem_conv_kernel(const float *__restrict__ img, const float *__restrict__ w,
 constexpr int kStemTW = 32, kStemTH = 4, kStemStrip = 4;
 constexpr int kStemIW = 2 * kStemTW + 1, kStemIH = 2 * kStemTH + 1;
 
-template <int C0, int ACT>
+template <typename TI, int C0, int ACT>
 __global__ void __launch_bounds__((C0 / 8) * (kStemTW / kStemStrip) * kStemTH)
-stem_conv_tiled_kernel(const float *__restrict__ img, const float *__restrict__ w,
+stem_conv_tiled_kernel(const TI *__restrict__ img, const float *__restrict__ lut, const float *__restrict__ w,
                        const float *__restrict__ scale, const float *__restrict__ shift,
                        __nv_bfloat16 *__restrict__ out, int H, int W, int Ho, int Wo, int pad_t, int pad_l,
                        int tiles_x) {
@@ -86,16 +101,23 @@ stem_conv_tiled_kernel(const float *__restrict__ img, const float *__restrict__ 
     constexpr int ROW = kStemIW * 3;
     __shared__ __align__(16) float sw[27 * C0];
     __shared__ float sin_[kStemIH * ROW];
+    __shared__ float slut[sizeof(TI) == 1 ? 768 : 1];
+    if (sizeof(TI) == 1) {
+        for (int i = threadIdx.x; i < 768; i += NT) slut[i] = lut[i];
+        __syncthreads();
+    }
     const int b = blockIdx.y;
     const int ty0 = (blockIdx.x / tiles_x) * kStemTH, tx0 = (blockIdx.x % tiles_x) * kStemTW;
     const int iy0 = ty0 * 2 - pad_t, ix0 = tx0 * 2 - pad_l;
     for (int i = threadIdx.x; i < 27 * C0 / 4; i += NT)
         reinterpret_cast<float4 *>(sw)[i] = reinterpret_cast<const float4 *>(w)[i];
-    const float *ib = img + (size_t)b * H * W * 3;
+    const TI *ib = img + (size_t)b * H * W * 3;
     for (int i = threadIdx.x; i < kStemIH * ROW; i += NT) {
         const int r = i / ROW, cidx = i - r * ROW;
         const int gy = iy0 + r, g3 = ix0 * 3 + cidx;
-        sin_[i] = (gy >= 0 && gy < H && g3 >= 0 && g3 < W * 3) ? ib[(size_t)gy * W * 3 + g3] : 0.f;
+        // outside the image: zero in NORMALISED space (TF SAME padding acts on the network input)
+        sin_[i] = (gy >= 0 && gy < H && g3 >= 0 && g3 < W * 3)
+                      ? StemPix<TI>::get(ib + (size_t)gy * W * 3 + g3, slut, cidx % 3) : 0.f;
     }
     __syncthreads();
     const int oct = threadIdx.x % NO, strip = threadIdx.x / NO;
@@ -327,8 +349,8 @@ extern "C" int effdet_bn_fold(const float *gamma, const float *beta, const float
     return EFFDET_OK;
 }
 
-template <typename TO>
-static int launch_stem(const float *img, const float *w, const float *scale, const float *shift,
+template <typename TI, typename TO>
+static int launch_stem(const TI *img, const float *lut, const float *w, const float *scale, const float *shift,
                        void *out, int B, int H, int W, int C0, cudaStream_t st) {
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     const int pad_t = ((Ho - 1) * 2 + 3 - H > 0 ? (Ho - 1) * 2 + 3 - H : 0) / 2;
@@ -337,7 +359,7 @@ static int launch_stem(const float *img, const float *w, const float *scale, con
     dim3 grid(cdiv(total, 128));
 #define STEM_CASE(C)                                                                             \
     case C:                                                                                      \
-        stem_conv_kernel<TO, C><<<grid, 128, 0, st>>>(img, w, scale, shift, static_cast<TO *>(out), \
+        stem_conv_kernel<TI, TO, C><<<grid, 128, 0, st>>>(img, lut, w, scale, shift, static_cast<TO *>(out), \
                                                       B, H, W, Ho, Wo, pad_t, pad_l);           \
         break;
     switch (C0) {
@@ -350,7 +372,8 @@ static int launch_stem(const float *img, const float *w, const float *scale, con
     return EFFDET_OK;
 }
 
-static int launch_stem_bf16(const float *img, const float *w, const float *scale, const float *shift,
+template <typename TI>
+static int launch_stem_bf16(const TI *img, const float *lut, const float *w, const float *scale, const float *shift,
                             void *out, int B, int H, int W, int C0, int act, cudaStream_t st) {
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     const int pad_t = ((Ho - 1) * 2 + 3 - H > 0 ? (Ho - 1) * 2 + 3 - H : 0) / 2;
@@ -360,17 +383,17 @@ static int launch_stem_bf16(const float *img, const float *w, const float *scale
 #define STEM_T(C)                                                                                          \
     case C:                                                                                                \
         if (act == EFFDET_ACT_SWISH)                                                                       \
-            stem_conv_tiled_kernel<C, EFFDET_ACT_SWISH><<<grid, (C / 8) * (kStemTW / kStemStrip) * kStemTH, 0, st>>>( \
-                img, w, scale, shift, static_cast<__nv_bfloat16 *>(out), H, W, Ho, Wo, pad_t, pad_l, tx);  \
+            stem_conv_tiled_kernel<TI, C, EFFDET_ACT_SWISH><<<grid, (C / 8) * (kStemTW / kStemStrip) * kStemTH, 0, st>>>( \
+                img, lut, w, scale, shift, static_cast<__nv_bfloat16 *>(out), H, W, Ho, Wo, pad_t, pad_l, tx);  \
         else                                                                                               \
-            stem_conv_tiled_kernel<C, EFFDET_ACT_NONE><<<grid, (C / 8) * (kStemTW / kStemStrip) * kStemTH, 0, st>>>( \
-                img, w, scale, shift, static_cast<__nv_bfloat16 *>(out), H, W, Ho, Wo, pad_t, pad_l, tx);  \
+            stem_conv_tiled_kernel<TI, C, EFFDET_ACT_NONE><<<grid, (C / 8) * (kStemTW / kStemStrip) * kStemTH, 0, st>>>( \
+                img, lut, w, scale, shift, static_cast<__nv_bfloat16 *>(out), H, W, Ho, Wo, pad_t, pad_l, tx);  \
         break;
     switch (C0) {
         STEM_T(32) STEM_T(40) STEM_T(48) STEM_T(56) STEM_T(64)
         default:
             if (act != EFFDET_ACT_SWISH) return fail(EFFDET_E_UNSUPPORTED, "effdet_stem_conv_act: %sunsupported C0=%lld", "", C0);
-            return launch_stem<__nv_bfloat16>(img, w, scale, shift, out, B, H, W, C0, st);
+            return launch_stem<TI, __nv_bfloat16>(img, lut, w, scale, shift, out, B, H, W, C0, st);
     }
 #undef STEM_T
     EFFDET_LAUNCHED();
@@ -383,10 +406,69 @@ extern "C" int effdet_stem_conv(const float *images, const float *kernel, const 
     EFFDET_REQUIRE(images && kernel && scale && shift && out, "null pointer");
     EFFDET_REQUIRE(B > 0 && H > 0 && W > 0, "bad sizes");
     if (out_dtype == EFFDET_F32)
-        return launch_stem<float>(images, kernel, scale, shift, out, B, H, W, C0, as_stream(stream));
+        return launch_stem<float, float>(images, nullptr, kernel, scale, shift, out, B, H, W, C0, as_stream(stream));
     if (out_dtype == EFFDET_BF16)
-        return launch_stem_bf16(images, kernel, scale, shift, out, B, H, W, C0, EFFDET_ACT_SWISH, as_stream(stream));
+        return launch_stem_bf16<float>(images, nullptr, kernel, scale, shift, out, B, H, W, C0, EFFDET_ACT_SWISH,
+                                       as_stream(stream));
     return fail(EFFDET_E_INVALID, "effdet_stem_conv: bad dtype%s", "");
+}
+
+/* Stem fed with the raw letterboxed uint8 RGB image (what train_tpu.py:170-183 decodes from the TFRecord PNG and
+ * what generators/common.py:406-417 builds before dividing by 255): normalize_image (train_tpu.py:135-140 ==
+ * generators/common.py:418-429) is applied on the fly through lut (3 x 256 floats, lut[c][v] = ((v/255) - mean_c)
+ * / std_c evaluated in float32 by the caller), so the float image (12 B/pixel) is never uploaded or stored.
+ * act: EFFDET_ACT_SWISH (folded BN in scale/shift) or, bf16 only, EFFDET_ACT_NONE (raw z for training). */
+extern "C" int effdet_stem_conv_u8(const unsigned char *images, const float *lut, const float *kernel,
+                                   const float *scale, const float *shift, void *out, int B, int H, int W, int C0,
+                                   int act, int out_dtype, void *stream) {
+    EFFDET_REQUIRE(images && lut && kernel && scale && shift && out, "null pointer");
+    EFFDET_REQUIRE(B > 0 && H > 0 && W > 0, "bad sizes");
+    EFFDET_REQUIRE(act == EFFDET_ACT_SWISH || (act == EFFDET_ACT_NONE && out_dtype == EFFDET_BF16),
+                   "act must be swish (or none with bf16 output)");
+    if (out_dtype == EFFDET_F32)
+        return launch_stem<uint8_t, float>(images, lut, kernel, scale, shift, out, B, H, W, C0, as_stream(stream));
+    if (out_dtype == EFFDET_BF16)
+        return launch_stem_bf16<uint8_t>(images, lut, kernel, scale, shift, out, B, H, W, C0, act, as_stream(stream));
+    return fail(EFFDET_E_INVALID, "effdet_stem_conv_u8: bad dtype%s", "");
+}
+
+/* out[p][c] = lut[c][in[p][c]]: normalize_image on the device for callers that need the float image itself
+ * (weight gradient of a trainable stem). */
+__global__ void __launch_bounds__(256)
+normalize_u8_kernel(const unsigned char *__restrict__ in, const float *__restrict__ lut, float *__restrict__ out,
+                    size_t n) {
+    __shared__ float slut[768];
+    for (int i = threadIdx.x; i < 768; i += 256) slut[i] = lut[i];
+    __syncthreads();
+    // 12 bytes = 4 pixels per thread: 3 x 4-byte loads, 3 x 16-byte stores
+    const size_t ngrp = n / 12;
+    for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < ngrp; g += (size_t)gridDim.x * 256) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(in) + g * 3;
+        float4 *dst = reinterpret_cast<float4 *>(out) + g * 3;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const uint32_t w = src[q];
+            float4 o;
+            o.x = slut[((q * 4 + 0) % 3) * 256 + (w & 0xff)];
+            o.y = slut[((q * 4 + 1) % 3) * 256 + ((w >> 8) & 0xff)];
+            o.z = slut[((q * 4 + 2) % 3) * 256 + ((w >> 16) & 0xff)];
+            o.w = slut[((q * 4 + 3) % 3) * 256 + (w >> 24)];
+            dst[q] = o;
+        }
+    }
+    if (blockIdx.x == 0)
+        for (size_t i = ngrp * 12 + threadIdx.x; i < n; i += 256) out[i] = slut[(i % 3) * 256 + in[i]];
+}
+extern "C" int effdet_normalize_u8(const unsigned char *images, const float *lut, float *out, size_t n_values,
+                                   void *stream) {
+    EFFDET_REQUIRE(images && lut && out && n_values > 0 && n_values % 3 == 0, "bad arguments");
+    EFFDET_REQUIRE((reinterpret_cast<uintptr_t>(images) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                   "unaligned buffers");
+    size_t nb = cdiv(n_values / 12 + 1, 256);
+    if (nb > (size_t)148 * 16) nb = (size_t)148 * 16;
+    normalize_u8_kernel<<<(unsigned)nb, 256, 0, as_stream(stream)>>>(images, lut, out, n_values);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
 }
 
 /* bf16 stem with a selectable epilogue: act = EFFDET_ACT_SWISH (inference, folded BN in scale/shift) or
@@ -397,7 +479,7 @@ extern "C" int effdet_stem_conv_act(const float *images, const float *kernel, co
     EFFDET_REQUIRE(images && kernel && scale && shift && out, "null pointer");
     EFFDET_REQUIRE(B > 0 && H > 0 && W > 0, "bad sizes");
     EFFDET_REQUIRE(act == EFFDET_ACT_SWISH || act == EFFDET_ACT_NONE, "act must be swish or none");
-    return launch_stem_bf16(images, kernel, scale, shift, out, B, H, W, C0, act, as_stream(stream));
+    return launch_stem_bf16<float>(images, nullptr, kernel, scale, shift, out, B, H, W, C0, act, as_stream(stream));
 }
 
 int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream);     // conv_tc.cu

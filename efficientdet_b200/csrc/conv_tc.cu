@@ -917,7 +917,15 @@ __global__ void wgrad_tc_reduce_kernel(const float *__restrict__ partial, int ns
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         float t = 0.f;
-        for (int s = 0; s < nsplit; ++s) t += partial[(size_t)s * n + i];
+        int s = 0;
+        for (; s + 7 < nsplit; s += 8) {          // eight loads in flight, same summation order
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(partial + (size_t)(s + u) * n + i);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t += v[u];
+        }
+        for (; s < nsplit; ++s) t += __ldcg(partial + (size_t)s * n + i);
         out[i] = accumulate ? out[i] + t : t;
     } else if (i < n + (size_t)n_bias) {
         const size_t j = i - n;

@@ -46,38 +46,60 @@ template <int CV> __device__ __forceinline__ void ldv(const float *p, float *v) 
 
 // ------------------------------------------------------------------ BN + activation backward
 // u = z*a + b with a = gamma*invstd, b = beta - mean*a (training) or the folded inference scale/shift.
-// pass 1: partial[blk][0][c] = sum dy*act'(u), partial[blk][1][c] = sum dy*act'(u)*xhat
-template <typename T, int CV>
+// pass 1: partial[blk][0][c] = sum dy*act'(u), partial[blk][1][c] = sum dy*act'(u)*(z - mean)
+// (the finalize kernel multiplies the second sum by invstd).
+// Both passes are pure streaming kernels, so what matters is bytes in flight per SM: a thread owns CV = 4
+// channels (8-byte bf16 / 16-byte fp32 vectors) and keeps U = 4 rows of both tensors in flight; the
+// per-channel coefficients then cost 20 registers instead of 48 and four blocks fit an SM (the 8-channel /
+// 2-row version needed 100 registers: two blocks per SM, ~32 KB in flight, ~2.4 TB/s).
+template <> struct VecB<__nv_bfloat16, 4> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float *v) {
+        const uint2 t = *reinterpret_cast<const uint2 *>(p);
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float *v) {
+        uint2 t;
+        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&t);
+        h[0] = __floats2bfloat162_rn(v[0], v[1]);
+        h[1] = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2 *>(p) = t;
+    }
+};
+template <typename T, int ACT> __device__ __forceinline__ float act_grad_t(float u) {
+    return act_grad_io<T>(u, ACT);
+}
+constexpr int kBnU = 4;       // rows in flight per thread
+template <typename T, int CV, int ACT>
 __global__ void bn_act_bwd_reduce_kernel(const T *__restrict__ z, const T *__restrict__ dy,
                                          const float *__restrict__ ua, const float *__restrict__ ub,
-                                         const float *__restrict__ mean, const float *__restrict__ invstd,
-                                         size_t rows, int C, int rows_per_block, int act,
-                                         float *__restrict__ partial) {
+                                         const float *__restrict__ mean, size_t rows, int C,
+                                         int rows_per_block, float *__restrict__ partial) {
     extern __shared__ float sred[];
     const int nvec = C / CV, PY = blockDim.x / nvec;
     const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec, c = cv * CV;
     const size_t r0 = (size_t)blockIdx.x * rows_per_block;
     const size_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-    float s1[CV], s2[CV], a[CV], b[CV], mu[CV], is[CV];
-    ldv<CV>(ua + c, a); ldv<CV>(ub + c, b); ldv<CV>(mean + c, mu); ldv<CV>(invstd + c, is);
+    float s1[CV], s2[CV], a[CV], b[CV], mu[CV];
+    ldv<CV>(ua + c, a); ldv<CV>(ub + c, b); ldv<CV>(mean + c, mu);
 #pragma unroll
     for (int k = 0; k < CV; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
     size_t r = r0 + py;
-    for (; r + PY < r1; r += 2 * PY) {          // two independent rows in flight
-        float zz[CV], g[CV], zz1[CV], g1[CV];
-        VecB<T, CV>::load(z + r * C + c, zz);
-        VecB<T, CV>::load(dy + r * C + c, g);
-        VecB<T, CV>::load(z + (r + PY) * C + c, zz1);
-        VecB<T, CV>::load(dy + (r + PY) * C + c, g1);
+    for (; r + (size_t)(kBnU - 1) * PY < r1; r += (size_t)kBnU * PY) {
+        float zz[kBnU][CV], g[kBnU][CV];
 #pragma unroll
-        for (int k = 0; k < CV; ++k) {
-            const float gm = g[k] * act_grad_io<T>(fmaf(zz[k], a[k], b[k]), act);
-            s1[k] += gm;
-            s2[k] = fmaf(gm, (zz[k] - mu[k]) * is[k], s2[k]);
-            const float gm1 = g1[k] * act_grad_io<T>(fmaf(zz1[k], a[k], b[k]), act);
-            s1[k] += gm1;
-            s2[k] = fmaf(gm1, (zz1[k] - mu[k]) * is[k], s2[k]);
+        for (int u = 0; u < kBnU; ++u) {
+            VecB<T, CV>::load(z + (r + (size_t)u * PY) * C + c, zz[u]);
+            VecB<T, CV>::load(dy + (r + (size_t)u * PY) * C + c, g[u]);
         }
+#pragma unroll
+        for (int u = 0; u < kBnU; ++u)
+#pragma unroll
+            for (int k = 0; k < CV; ++k) {
+                const float gm = g[u][k] * act_grad_t<T, ACT>(fmaf(zz[u][k], a[k], b[k]));
+                s1[k] += gm;
+                s2[k] = fmaf(gm, zz[u][k] - mu[k], s2[k]);
+            }
     }
     for (; r < r1; r += PY) {
         float zz[CV], g[CV];
@@ -85,9 +107,9 @@ __global__ void bn_act_bwd_reduce_kernel(const T *__restrict__ z, const T *__res
         VecB<T, CV>::load(dy + r * C + c, g);
 #pragma unroll
         for (int k = 0; k < CV; ++k) {
-            const float gm = g[k] * act_grad_io<T>(fmaf(zz[k], a[k], b[k]), act);
+            const float gm = g[k] * act_grad_t<T, ACT>(fmaf(zz[k], a[k], b[k]));
             s1[k] += gm;
-            s2[k] = fmaf(gm, (zz[k] - mu[k]) * is[k], s2[k]);
+            s2[k] = fmaf(gm, zz[k] - mu[k], s2[k]);
         }
     }
 #pragma unroll
@@ -98,7 +120,7 @@ __global__ void bn_act_bwd_reduce_kernel(const T *__restrict__ z, const T *__res
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
         float t = 0.f;
-        for (int r = 0; r < PY; ++r) t += sred[(size_t)r * 2 * C + i];
+        for (int q = 0; q < PY; ++q) t += sred[(size_t)q * 2 * C + i];
         partial[(size_t)blockIdx.x * 2 * C + i] = t;
     }
 }
@@ -110,9 +132,21 @@ __global__ void bn_act_bwd_finalize_kernel(const float *__restrict__ partial, in
     if (c >= C) return;
     const int lane = threadIdx.x & 31;
     double s1 = 0.0, s2 = 0.0;
-    for (int b = lane; b < nblk; b += 32) {
-        s1 += (double)partial[(size_t)b * 2 * C + c];
-        s2 += (double)partial[(size_t)b * 2 * C + C + c];
+    int b = lane;
+    for (; b + 7 * 32 < nblk; b += 8 * 32) {      // sixteen loads in flight, same summation order
+        float v[8], q[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float *row = partial + (size_t)(b + 32 * u) * 2 * C;
+            v[u] = __ldcg(row + c);
+            q[u] = __ldcg(row + C + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s1 += (double)v[u]; s2 += (double)q[u]; }
+    }
+    for (; b < nblk; b += 32) {
+        s1 += (double)__ldcg(partial + (size_t)b * 2 * C + c);
+        s2 += (double)__ldcg(partial + (size_t)b * 2 * C + C + c);
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
@@ -121,6 +155,7 @@ __global__ void bn_act_bwd_finalize_kernel(const float *__restrict__ partial, in
     }
     if (lane) return;
     const float g = gamma[c], is = invstd[c], mu = mean[c];
+    s2 *= (double)is;                       // the reduce pass accumulated dy*act'*(z - mean)
     const float m1 = (float)(s1 / count), m2 = (float)(s2 / count);
     k123[c] = g * is;
     k123[C + c] = -g * is * is * m2;
@@ -132,10 +167,10 @@ __global__ void bn_act_bwd_finalize_kernel(const float *__restrict__ partial, in
 // block = nvec channel vectors x PY rows; a thread keeps the seven per-channel coefficient vectors of
 // ITS channels in registers and walks rows (the flat-index version re-read them from L1 for every
 // 16-byte vector: 10 extra load instructions per 8 elements, LSU-bound at ~1.5 TB/s).
-template <typename T, int CV>
+template <typename T, int CV, int ACT>
 __global__ void bn_act_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ z, const float *__restrict__ ua,
                         const float *__restrict__ ub, const float *__restrict__ k123, T *__restrict__ dz,
-                        size_t rows, int C, int rows_per_block, int act) {
+                        size_t rows, int C, int rows_per_block) {
     const int nvec = C / CV, PY = blockDim.x / nvec;
     const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec, c = cv * CV;
     if (py >= PY) return;
@@ -145,19 +180,20 @@ __global__ void bn_act_bwd_apply_kernel(const T *__restrict__ dy, const T *__res
     const size_t r0 = (size_t)blockIdx.x * rows_per_block;
     const size_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
     size_t r = r0 + py;
-    for (; r + PY < r1; r += 2 * PY) {          // two independent rows in flight
-        float g0[CV], z0[CV], g1[CV], z1[CV];
-        VecB<T, CV>::load(dy + r * C + c, g0);
-        VecB<T, CV>::load(z + r * C + c, z0);
-        VecB<T, CV>::load(dy + (r + PY) * C + c, g1);
-        VecB<T, CV>::load(z + (r + PY) * C + c, z1);
+    for (; r + (size_t)(kBnU - 1) * PY < r1; r += (size_t)kBnU * PY) {
+        float g[kBnU][CV], zz[kBnU][CV];
 #pragma unroll
-        for (int k = 0; k < CV; ++k) {
-            g0[k] = k1[k] * (g0[k] * act_grad_io<T>(fmaf(z0[k], a[k], b[k]), act)) + k2[k] * z0[k] + k3[k];
-            g1[k] = k1[k] * (g1[k] * act_grad_io<T>(fmaf(z1[k], a[k], b[k]), act)) + k2[k] * z1[k] + k3[k];
+        for (int u = 0; u < kBnU; ++u) {
+            VecB<T, CV>::load(dy + (r + (size_t)u * PY) * C + c, g[u]);
+            VecB<T, CV>::load(z + (r + (size_t)u * PY) * C + c, zz[u]);
         }
-        VecB<T, CV>::store(dz + r * C + c, g0);
-        VecB<T, CV>::store(dz + (r + PY) * C + c, g1);
+#pragma unroll
+        for (int u = 0; u < kBnU; ++u) {
+#pragma unroll
+            for (int k = 0; k < CV; ++k)
+                g[u][k] = k1[k] * (g[u][k] * act_grad_t<T, ACT>(fmaf(zz[u][k], a[k], b[k]))) + k2[k] * zz[u][k] + k3[k];
+            VecB<T, CV>::store(dz + (r + (size_t)u * PY) * C + c, g[u]);
+        }
     }
     for (; r < r1; r += PY) {
         float g0[CV], z0[CV];
@@ -165,7 +201,7 @@ __global__ void bn_act_bwd_apply_kernel(const T *__restrict__ dy, const T *__res
         VecB<T, CV>::load(z + r * C + c, z0);
 #pragma unroll
         for (int k = 0; k < CV; ++k)
-            g0[k] = k1[k] * (g0[k] * act_grad_io<T>(fmaf(z0[k], a[k], b[k]), act)) + k2[k] * z0[k] + k3[k];
+            g0[k] = k1[k] * (g0[k] * act_grad_t<T, ACT>(fmaf(z0[k], a[k], b[k]))) + k2[k] * z0[k] + k3[k];
         VecB<T, CV>::store(dz + r * C + c, g0);
     }
 }
@@ -440,7 +476,15 @@ __global__ void sum_partials_warp_kernel(const float *__restrict__ partial, int 
     if (i >= n) return;
     const int lane = threadIdx.x & 31;
     double s = 0.0;
-    for (int b = lane; b < nblk; b += 32) s += (double)partial[(size_t)b * n + i];
+    int b = lane;
+    for (; b + 7 * 32 < nblk; b += 8 * 32) {      // eight loads in flight, same summation order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(partial + (size_t)(b + 32 * u) * n + i);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)v[u];
+    }
+    for (; b < nblk; b += 32) s += (double)__ldcg(partial + (size_t)b * n + i);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
     if (lane == 0) out[i] = (float)s;
@@ -624,19 +668,23 @@ extern "C" int effdet_bn_act_backward(const void *dy, const void *z, size_t rows
         EFFDET_CUDA(cudaMemcpyAsync(k123, ua, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else {
         EFFDET_REQUIRE(gamma && save_mean && save_invstd && partial, "null statistics");
-        const int CV = dtype == EFFDET_BF16 ? 8 : 4;
-        const int nvec = C / CV;
+        const int nvec = C / 4;
         EFFDET_REQUIRE(nvec <= 1024, "C too large");
         int PY = 256 / nvec; if (PY < 1) PY = 1;
         const int rpb = (int)cdiv(rows, nblk);
         EFFDET_REQUIRE((int)cdiv(rows, rpb) == nblk, "nblk must come from effdet_colreduce_blocks");
         const size_t sm = (size_t)PY * 2 * C * sizeof(float);
-        DISPATCH_TB(dtype,
-            (bn_act_bwd_reduce_kernel<float, 4><<<nblk, nvec * PY, sm, st>>>(
-                (const float *)z, (const float *)dy, ua, ub, save_mean, save_invstd, rows, C, rpb, act, partial)),
-            (bn_act_bwd_reduce_kernel<__nv_bfloat16, 8><<<nblk, nvec * PY, sm, st>>>(
-                (const __nv_bfloat16 *)z, (const __nv_bfloat16 *)dy, ua, ub, save_mean, save_invstd, rows, C, rpb,
-                act, partial)))
+#define BN_RED(A)                                                                                              \
+        DISPATCH_TB(dtype,                                                                                     \
+            (bn_act_bwd_reduce_kernel<float, 4, A><<<nblk, nvec * PY, sm, st>>>(                                \
+                (const float *)z, (const float *)dy, ua, ub, save_mean, rows, C, rpb, partial)),                \
+            (bn_act_bwd_reduce_kernel<__nv_bfloat16, 4, A><<<nblk, nvec * PY, sm, st>>>(                        \
+                (const __nv_bfloat16 *)z, (const __nv_bfloat16 *)dy, ua, ub, save_mean, rows, C, rpb, partial)))
+        if (act == EFFDET_ACT_SWISH) { BN_RED(EFFDET_ACT_SWISH) }
+        else if (act == EFFDET_ACT_RELU) { BN_RED(EFFDET_ACT_RELU) }
+        else if (act == EFFDET_ACT_NONE) { BN_RED(EFFDET_ACT_NONE) }
+        else return fail(EFFDET_E_UNSUPPORTED, "%s: unsupported activation", __func__);
+#undef BN_RED
         EFFDET_LAUNCHED();
         bn_act_bwd_finalize_kernel<<<cdiv((size_t)C * 32, 256), 256, 0, st>>>(partial, nblk, (double)rows, gamma,
                                                                             save_mean, save_invstd, k123, dgamma,
@@ -644,20 +692,25 @@ extern "C" int effdet_bn_act_backward(const void *dy, const void *z, size_t rows
         EFFDET_LAUNCHED();
     }
     {
-        const int CVa = dtype == EFFDET_BF16 ? 8 : 4;
-        const int nva = C / CVa;
+        const int nva = C / 4;
         EFFDET_REQUIRE(nva <= 1024, "C too large");
         int PYa = 256 / nva; if (PYa < 1) PYa = 1;
-        // ~8 blocks per SM, each thread at least 2 rows
-        size_t rpb = (size_t)PYa * 2;
+        // ~8 blocks per SM, each thread at least kBnU rows
+        size_t rpb = (size_t)PYa * kBnU;
         while (cdiv(rows, rpb) > (unsigned)kNumSMs * 8) rpb *= 2;
         const unsigned nb = cdiv(rows, rpb);
-        DISPATCH_TB(dtype,
-            (bn_act_bwd_apply_kernel<float, 4><<<nb, nva * PYa, 0, st>>>(
-                (const float *)dy, (const float *)z, ua, ub, k123, (float *)dz, rows, C, (int)rpb, act)),
-            (bn_act_bwd_apply_kernel<__nv_bfloat16, 8><<<nb, nva * PYa, 0, st>>>(
-                (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)z, ua, ub, k123, (__nv_bfloat16 *)dz, rows, C,
-                (int)rpb, act)))
+#define BN_APP(A)                                                                                              \
+        DISPATCH_TB(dtype,                                                                                     \
+            (bn_act_bwd_apply_kernel<float, 4, A><<<nb, nva * PYa, 0, st>>>(                                    \
+                (const float *)dy, (const float *)z, ua, ub, k123, (float *)dz, rows, C, (int)rpb)),            \
+            (bn_act_bwd_apply_kernel<__nv_bfloat16, 4, A><<<nb, nva * PYa, 0, st>>>(                            \
+                (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)z, ua, ub, k123, (__nv_bfloat16 *)dz, rows, C, \
+                (int)rpb)))
+        if (act == EFFDET_ACT_SWISH) { BN_APP(EFFDET_ACT_SWISH) }
+        else if (act == EFFDET_ACT_RELU) { BN_APP(EFFDET_ACT_RELU) }
+        else if (act == EFFDET_ACT_NONE) { BN_APP(EFFDET_ACT_NONE) }
+        else return fail(EFFDET_E_UNSUPPORTED, "%s: unsupported activation", __func__);
+#undef BN_APP
     }
     EFFDET_LAUNCHED();
     return EFFDET_OK;
@@ -672,6 +725,74 @@ extern "C" int effdet_se_apply(const void *y, const float *gate, void *out, int 
         (se_apply_kernel<float, 4><<<grid_for_n(n / 4), 256, 0, st>>>((const float *)y, gate, (float *)out, HW, C, n / 4)),
         (se_apply_kernel<__nv_bfloat16, 8><<<grid_for_n(n / 8), 256, 0, st>>>(
             (const __nv_bfloat16 *)y, gate, (__nv_bfloat16 *)out, HW, C, n / 8)))
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+/* Stochastic depth (FixedDropout with noise shape (None,1,1,1): efficientnet.py:147-188, applied to the
+ * projected branch of every skip block when drop_rate > 0, efficientnet.py:300-304).  Keras dropout in the
+ * training phase: keep = uniform[0,1) >= rate per (block, image); the kept branch is scaled by 1/(1-rate).
+ * scales (nblocks, B) f32 holds keep/(1-rate).  The uniform numbers come from a counter-based generator
+ * (splitmix64 of seed, step, block, image -- TensorFlow's own stream cannot be reproduced, only its
+ * distribution); *step_counter is read and incremented on the device, so a captured graph draws a fresh
+ * mask at every replay. */
+__global__ void __launch_bounds__(256)
+drop_connect_scales_kernel(const float *__restrict__ rates, int nblocks, int B, unsigned long long seed,
+                           unsigned long long *__restrict__ step_counter, float *__restrict__ scales) {
+    const unsigned long long step = *step_counter;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nblocks * B; i += blockDim.x) {
+        const int blk = i / B;
+        unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (step * (unsigned long long)(nblocks * B) + i + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        const float u = (float)(z >> 40) * (1.0f / 16777216.0f);      // 24 random bits -> [0, 1)
+        const float rate = rates[blk];
+        scales[i] = u >= rate ? 1.0f / (1.0f - rate) : 0.0f;
+    }
+    if (threadIdx.x == 0) *step_counter = step + 1;
+}
+extern "C" int effdet_drop_connect_scales(const float *rates, int nblocks, int B, unsigned long long seed,
+                                          unsigned long long *step_counter, float *scales, void *stream) {
+    EFFDET_REQUIRE(rates && step_counter && scales && nblocks > 0 && B > 0, "bad arguments");
+    drop_connect_scales_kernel<<<1, 256, 0, as_stream(stream)>>>(rates, nblocks, B, seed, step_counter, scales);
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+// out = y * scale[b] (+ res): forward of the dropped skip branch (res = block input) and, with res == NULL,
+// its backward (d y = d out * scale[b])
+template <typename T, int CV>
+__global__ void __launch_bounds__(256)
+sample_scale_add_kernel(const T *__restrict__ y, const float *__restrict__ scale, const T *__restrict__ res,
+                        T *__restrict__ out, size_t vec_per_image, size_t nvec_total) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
+        const float s = scale[i / vec_per_image];
+        float v[CV];
+        VecB<T, CV>::load(y + i * CV, v);
+        if (res) {
+            float r[CV];
+            VecB<T, CV>::load(res + i * CV, r);
+#pragma unroll
+            for (int k = 0; k < CV; ++k) v[k] = v[k] * s + r[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < CV; ++k) v[k] *= s;
+        }
+        VecB<T, CV>::store(out + i * CV, v);
+    }
+}
+extern "C" int effdet_sample_scale_add(const void *y, const float *scale, const void *res, void *out, int B,
+                                       size_t per_image, int dtype, void *stream) {
+    EFFDET_REQUIRE(y && scale && out && B > 0 && per_image > 0 && per_image % 8 == 0, "bad arguments");
+    cudaStream_t st = as_stream(stream);
+    const size_t n = (size_t)B * per_image;
+    DISPATCH_TB(dtype,
+        (sample_scale_add_kernel<float, 4><<<grid_for_n(n / 4), 256, 0, st>>>(
+            (const float *)y, scale, (const float *)res, (float *)out, per_image / 4, n / 4)),
+        (sample_scale_add_kernel<__nv_bfloat16, 8><<<grid_for_n(n / 8), 256, 0, st>>>(
+            (const __nv_bfloat16 *)y, scale, (const __nv_bfloat16 *)res, (__nv_bfloat16 *)out, per_image / 8, n / 8)))
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }

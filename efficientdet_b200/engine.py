@@ -202,6 +202,11 @@ class Plan:
                  "stem_conv")
         return x, H
 
+    def drop_keep(self, blk):
+        """(B,) f32 scale of the projected branch of a skip block, or None.  Inference: FixedDropout is the
+        identity (efficientnet.py:300-303 only acts in the training phase)."""
+        return self.net.drop_scale.get(blk.prefix) if blk.has_skip else None
+
     def _mbconv(self, x, blk, H):
         """One MBConv block (efficientnet.py:210-306), inference form: BN folded into the conv /
         depthwise epilogues, SE gate folded into the project conv."""
@@ -233,7 +238,7 @@ class Plan:
                                gate.ptr, B, cmid, blk.se_filters), p + "se")
         y = self.val((B, Ho, Ho, cout), name=p + "out")
         s3, b3 = self.folded(p + "project_bn")
-        keep = self.net.drop_scale.get(p) if blk.has_skip else None
+        keep = self.drop_keep(blk)
         self.conv([d], [y], p + "project_conv/kernel", cmid, cout, scale=s3, shift=b3,
                   gate=gate, keep=keep, residuals=[inp] if blk.has_skip else None,
                   name=p + "project_conv")

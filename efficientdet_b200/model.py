@@ -57,6 +57,7 @@ class Network:
         self.frozen_layers = set()
         self.plans = {}
         self._staged = collections.OrderedDict()
+        self.seed = seed
         self._init_weights(seed)
         self._materialize()
         self.refresh()

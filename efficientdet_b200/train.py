@@ -37,6 +37,19 @@ class TrainPlan(engine.Plan):
         self.bb_tape = []
         self.gvals = {}            # id(Val) -> gradient Val
         net.ensure_grad_buffers()
+        # stochastic depth (efficientnet.py:300-304): one (B,) scale vector per skip block with drop_rate > 0,
+        # redrawn on the device at the start of every step
+        self.drop_blocks = [b for b in net.backbone.blocks if b.has_skip and b.drop_rate and b.drop_rate > 0]
+        self.drop_index = {b.prefix: i for i, b in enumerate(self.drop_blocks)}
+        if self.drop_blocks:
+            dev = net.device
+            self.drop_rates = torch.tensor([float(b.drop_rate) for b in self.drop_blocks], dtype=torch.float32,
+                                           device=dev)
+            self.drop_scales = torch.ones((len(self.drop_blocks), int(batch)), dtype=torch.float32, device=dev)
+            self.drop_step = torch.zeros((1,), dtype=torch.int64, device=dev)
+            rank = torch.distributed.get_rank() if (torch.distributed.is_available() and
+                                                    torch.distributed.is_initialized()) else 0
+            self.drop_seed = (int(getattr(net, "seed", 0) or 0) * 1000003 + 7919 * rank + 12345) & (2 ** 63 - 1)
         super().__init__(net, batch, reuse_buffers=reuse_buffers)
 
     # ------------------------------------------------------------------ small helpers
@@ -501,7 +514,17 @@ class TrainPlan(engine.Plan):
 
 
     # ------------------------------------------------------------------ backbone in training mode
+    def drop_keep(self, blk):
+        i = self.drop_index.get(blk.prefix)
+        return None if i is None else self.drop_scales[i]
+
     def _stem(self):
+        if self.drop_blocks:
+            nb = len(self.drop_blocks)
+            self.add("drop_mask", [], [],
+                     lambda: _call("effdet_drop_connect_scales", self.drop_rates.data_ptr(), nb, self.B,
+                                   self.drop_seed, self.drop_step.data_ptr(), self.drop_scales.data_ptr()),
+                     "drop_connect_scales")
         if not self.train_backbone:
             return super()._stem()
         net, B, S = self.net, self.B, self.net.image_size
@@ -575,7 +598,13 @@ class TrainPlan(engine.Plan):
                 arr = ptrs()
                 self._keepalive.append(arr)
                 return _call("effdet_wbifpn_add", arr, 2, None, 0.0, out.ptr, B * HW * cout, self.dtype)
-            self.add("add", [y_p, inp], [out], make_add, p + "add")
+            keep = self.drop_keep(blk)
+            if keep is not None:        # y_p * keep[b] / (1 - rate) + inp  (FixedDropout on the projected branch)
+                self.add("add", [y_p, inp], [out],
+                         lambda: _call("effdet_sample_scale_add", y_p.ptr, keep.data_ptr(), inp.ptr, out.ptr, B,
+                                       HW * cout, self.dtype), p + "drop_add")
+            else:
+                self.add("add", [y_p, inp], [out], make_add, p + "add")
         rec.update(xin=xin, z_d=z_d, y_d=y_d, part=part, nblk=nblk, gate=gate, yg=yg, z_p=z_p, y_p=y_p,
                    out=out, Ho=Ho)
         self.bb_tape.append(rec)
@@ -615,7 +644,14 @@ class TrainPlan(engine.Plan):
             return
         # project BN (linear) -> project conv
         bn_p = dict(rec["bn_p"]); bn_p["z"] = rec["z_p"]
-        dz_p = self._bn_act_backward(bn_p, d_out, p + "project")
+        d_yp = d_out
+        keep = self.drop_keep(blk) if blk.has_skip else None
+        if keep is not None:            # backward of the dropped branch: d y_p = d out * keep[b] / (1 - rate)
+            d_yp = self.val(rec["y_p"].shape, name=p + "drop_grad")
+            self.add("add", [d_out], [d_yp],
+                     lambda: _call("effdet_sample_scale_add", d_out.ptr, keep.data_ptr(), None, d_yp.ptr, B,
+                                   HW * cout, self.dtype), p + "drop_bwd")
+        dz_p = self._bn_act_backward(bn_p, d_yp, p + "project")
         pkey = p + "project_conv/kernel"
         yg = rec["yg"]
         self._wgrad([yg], [dz_p], pkey, cmid, cout, 1, 1, name=p + "project_wgrad")
@@ -826,10 +862,6 @@ class Trainer:
                     "partially frozen backbones are not supported: freeze all of it "
                     "(model.freeze_backbone(), train_tpu.py --freeze-backbone) or none of it")
             self.train_backbone = n_frozen == 0
-            if self.train_backbone and any(b.drop_rate and b.drop_rate > 0 and b.has_skip
-                                           for b in net.backbone.blocks):
-                raise NotImplementedError("stochastic depth while training the backbone is not "
-                                          "implemented: build with drop_connect_rate=0")
             self.plans[key] = TrainPlan(net, B, self.focal.alpha, self.focal.gamma, self.sl1.lambda_,
                                         dense_labels=dense,
                                         reuse_buffers=os.environ.get("EFFDET_NO_REUSE") != "1",
@@ -1084,7 +1116,7 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev, freeze_backb
     else:
         roof = dict(bound="hbm", achieved=dom["bytes"] / (dom["ms"] * 1e-3) / 1e9, peak=hbm, unit="GB/s")
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof.update(traffic=None, kernel=dom_kind, launches=dom["n"], share_of_step=dom["ms"] / total_ms,
+    roof.update(traffic=bench_mod.measured_traffic(args.workload, dom_kind), kernel=dom_kind, launches=dom["n"], share_of_step=dom["ms"] / total_ms,
                 peak_source=peak_src,
                 per_kind_ms={k_: round(v["ms"], 4) for k_, v in sorted(by_kind.items())})
     cpu = cpu_baseline_train(phi, C, weighted, S, freeze_backbone=freeze_backbone) if rank == 0 else None

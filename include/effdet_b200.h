@@ -371,6 +371,17 @@ int effdet_spatial_sum(const void *y, float *partial, int nblk, int B, int HW, i
 /* out = y * gate[b][c]  (efficientnet.py:286 se_excite, materialised in training mode). */
 int effdet_se_apply(const void *y, const float *gate, void *out, int B, int HW, int C, int dtype,
                     void *stream);
+/* Stochastic depth = FixedDropout(drop_rate, noise_shape=(None,1,1,1)) on the projected branch of the skip
+ * blocks in the training phase (efficientnet.py:147-188, :300-304; drop_rate per block :466-467).
+ * effdet_drop_connect_scales draws scales[blk][b] = (uniform >= rates[blk]) / (1 - rates[blk]) for all
+ * blocks of one step (Keras dropout semantics); the generator is counter based (seed, *step_counter, blk, b)
+ * and increments *step_counter on the device, so every replay of a captured graph draws a new mask.
+ * effdet_sample_scale_add: out = y * scale[b] (+ res), per image of `per_image` elements: the forward of the
+ * dropped branch (res = block input) and, with res == NULL, its backward. */
+int effdet_drop_connect_scales(const float *rates, int nblocks, int B, unsigned long long seed,
+                               unsigned long long *step_counter, float *scales, void *stream);
+int effdet_sample_scale_add(const void *y, const float *scale, const void *res, void *out, int B,
+                            size_t per_image, int dtype, void *stream);
 /* Squeeze-excite backward (efficientnet.py:255-286): dy (gradient of the SE input, both the direct
  * path and the path through GlobalAveragePooling), gradients of se_reduce / se_expand. */
 int effdet_se_backward_blocks(int HW, int C, int dtype);

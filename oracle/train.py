@@ -28,8 +28,10 @@ def trainable_keys(W, freeze_backbone=True, freeze_bn=False):
 
 
 def loss_and_grads(W, images, reg_t, lab_t, phi, num_classes, weighted=False, freeze_bn=False,
-                   alpha=0.25, gamma=1.5, dtype=torch.float64, freeze_backbone=True):
-    """-> (focal, smooth_l1, grads dict, bn batch stats dict name -> (mean, unbiased var))."""
+                   alpha=0.25, gamma=1.5, dtype=torch.float64, freeze_backbone=True, drop_scale=None):
+    """-> (focal, smooth_l1, grads dict, bn batch stats dict name -> (mean, unbiased var)).
+    drop_scale: {block prefix: (B,) keep/(1-rate)} = the FixedDropout draw of this step
+    (efficientnet.py:300-304), or None for drop_connect_rate=0."""
     keys = trainable_keys(W, freeze_backbone, freeze_bn)
     Wt = {k: torch.tensor(np.asarray(v), dtype=dtype) for k, v in W.items()}
     for k in keys:
@@ -37,7 +39,8 @@ def loss_and_grads(W, images, reg_t, lab_t, phi, num_classes, weighted=False, fr
     stats = {}
     reg, cls = graph.forward(Wt, images, phi, num_classes, weighted, dtype=dtype,
                              bn_train_bifpn=not freeze_bn,
-                             bn_train_backbone=(not freeze_backbone) and (not freeze_bn), stats=stats)
+                             bn_train_backbone=(not freeze_backbone) and (not freeze_bn), stats=stats,
+                             drop_scale=drop_scale)
     fl = losses.focal(torch.as_tensor(lab_t).to(dtype), cls, alpha, gamma)
     sl = losses.smooth_l1(torch.as_tensor(reg_t).to(dtype), reg)
     (fl + sl).backward()

@@ -531,7 +531,7 @@ def test_stem_weight_gradient_bf16(C0, H, B):
     assert rel_err(dw.cpu().numpy(), w.grad.permute(2, 3, 1, 0).numpy()) < 2e-5
 
 
-def test_partial_backbone_freeze_and_stochastic_depth_are_rejected():
+def test_partial_backbone_freeze_is_rejected():
     from efficientdet_b200.model import efficientdet
     z = lambda *s: np.zeros(s, np.float32)
     model = efficientdet(0, num_classes=3, image_size=128, just_training_model=True, drop_connect_rate=0)
@@ -539,10 +539,78 @@ def test_partial_backbone_freeze_and_stochastic_depth_are_rejected():
     model.compile()
     with pytest.raises(NotImplementedError):
         model.train_on_batch(z(1, 128, 128, 3), [z(1, 3069, 5), z(1, 3069, 4)])
-    model = efficientdet(0, num_classes=3, image_size=128, just_training_model=True)   # drop_connect 0.2
-    model.compile()
-    with pytest.raises(NotImplementedError):
-        model.train_on_batch(z(1, 128, 128, 3), [z(1, 3069, 5), z(1, 3069, 4)])
+
+
+def test_drop_connect_scales_distribution_and_fresh_draws():
+    """effdet_drop_connect_scales: Keras dropout semantics (keep = u >= rate, kept branch * 1/(1-rate)),
+    a new draw per launch (device-side step counter), reproducible from (seed, step)."""
+    from efficientdet_b200 import _lib
+    DEV = torch.device("cuda")
+    lib = _lib.load()
+    nb, B = 9, 4096
+    rates = torch.tensor([0.0125 * (i + 1) for i in range(nb)], dtype=torch.float32, device=DEV)
+    step = torch.zeros(1, dtype=torch.int64, device=DEV)
+    a, b = torch.empty((nb, B), device=DEV), torch.empty((nb, B), device=DEV)
+    _lib.check(lib.effdet_drop_connect_scales(rates.data_ptr(), nb, B, 77, step.data_ptr(), a.data_ptr(), None))
+    _lib.check(lib.effdet_drop_connect_scales(rates.data_ptr(), nb, B, 77, step.data_ptr(), b.data_ptr(), None))
+    assert int(step.item()) == 2
+    a, b, r = a.cpu().numpy(), b.cpu().numpy(), rates.cpu().numpy()
+    assert not np.array_equal(a, b)
+    for i in range(nb):
+        keep = np.float32(1.0) / (np.float32(1.0) - r[i])
+        assert set(np.unique(a[i])) <= {np.float32(0.0), keep}
+        frac = float((a[i] == 0).mean())
+        assert abs(frac - r[i]) < 4 * np.sqrt(r[i] * (1 - r[i]) / B) + 1e-3, (i, frac, r[i])
+    step.zero_()
+    c = torch.empty((nb, B), device=DEV)
+    _lib.check(lib.effdet_drop_connect_scales(rates.data_ptr(), nb, B, 77, step.data_ptr(), c.data_ptr(), None))
+    assert np.array_equal(c.cpu().numpy(), a)
+
+
+@pytest.mark.parametrize("freeze_backbone", [False, True])
+def test_training_step_with_stochastic_depth(freeze_backbone):
+    """drop_connect_rate = 0.2 (the reference default, efficientnet.py:318): the training step draws a
+    per-(block, image) keep mask on the device; with the SAME mask the fp64 oracle gives the same losses
+    and gradients (forward scale + residual, backward through the dropped branch), and a second step
+    draws a different mask.  Frozen backbone: Keras dropout ignores `trainable`, so the mask still acts."""
+    from efficientdet_b200.model import efficientdet
+    from efficientdet_b200.optimizers import SGD
+    from oracle import train as otrain
+    from util_model import rel_l2
+    size, C, B, phi = 256, 5, 8, 0
+    model = efficientdet(phi, num_classes=C, weighted_bifpn=False, image_size=size, dtype="fp32",
+                         drop_connect_rate=0.6, just_training_model=True)     # high rate: drops do happen at B=8
+    W0 = perturb_weights(model)
+    if freeze_backbone:
+        model.freeze_backbone()
+    model.compile(optimizer=SGD(lr=0.01, decay=4e-5, momentum=0.9))
+    anchors, ann, reg_t, lab_t = _targets(size, B, C)
+    img = np.random.default_rng(5).standard_normal((B, size, size, 3)).astype(np.float32)
+    total, l_reg, l_cls = model.train_on_batch(img, [reg_t, lab_t])
+    plan = model._trainer.plan(B, dense=True)
+    assert len(plan.drop_blocks) == 9            # B0: 16 blocks, 9 of them skip blocks
+    scales = plan.drop_scales.cpu().numpy().copy()
+    drop = {b.prefix: scales[i] for i, b in enumerate(plan.drop_blocks)}
+    for i, b in enumerate(plan.drop_blocks):
+        keep = np.float32(1.0) / (np.float32(1.0) - np.float32(b.drop_rate))
+        assert set(np.unique(scales[i])) <= {np.float32(0.0), keep}
+    assert (scales == 0).any() and (scales != 0).any()
+    fl, sl, grads, _ = otrain.loss_and_grads(W0, img, reg_t, lab_t, phi, C, False, False,
+                                             freeze_backbone=freeze_backbone, drop_scale=drop)
+    assert abs(l_cls - fl) / fl < 2e-4, (l_cls, fl)
+    assert abs(l_reg - sl) / max(sl, 1e-9) < 2e-4, (l_reg, sl)
+    bad = {}
+    for k, g in grads.items():
+        if np.abs(g).max() < 1e-12:
+            continue
+        e = rel_l2(model.net.grads[k].cpu().numpy(), g)
+        if not e < 8e-2:
+            bad[k] = float(e)
+    assert not bad, bad
+    model.train_on_batch(img, [reg_t, lab_t])
+    assert not np.array_equal(plan.drop_scales.cpu().numpy(), scales)
+    # inference is unaffected by the mask (FixedDropout only acts in the training phase)
+    assert model.net.drop_scale == {}
 
 
 def test_fit_prefetched_matches_stepwise_training():
