@@ -48,6 +48,9 @@ _SIGNATURES = {
                          c_int, c_int, c_void_p],
     "effdet_stem_conv_act": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                              c_int, c_int, c_void_p],
+    "effdet_stem_conv_u8": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                            c_int, c_int, c_int, c_void_p],
+    "effdet_normalize_u8": [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "effdet_conv2d": [c_void_p, c_void_p],
     "effdet_conv_weight_panel": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                  c_void_p],

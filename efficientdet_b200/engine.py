@@ -16,7 +16,8 @@ import torch
 from . import _lib
 from ._lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SWISH, BF16, F32
 
-TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16, "i8": torch.int8, "i32": torch.int32}
+TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16, "i8": torch.int8, "i32": torch.int32,
+               "u8": torch.uint8}
 BN_EPS_BACKBONE = 1e-3            # keras default (efficientnet.py:233-236 passes no epsilon)
 BN_EPS_BIFPN = 1e-4               # model.py:42-45
 BN_MOMENTUM_BIFPN = 0.997
@@ -40,7 +41,7 @@ class Val:
         n = 1
         for s in self.shape:
             n *= s
-        return n * {BF16: 2, F32: 4, "i8": 1, "i32": 4}[self.dtype]
+        return n * {BF16: 2, F32: 4, "i8": 1, "i32": 4, "u8": 1}[self.dtype]
 
     @property
     def ptr(self):
@@ -68,8 +69,9 @@ def _call(name, *args):
 
 
 class Plan:
-    def __init__(self, net, batch, reuse_buffers=True, keep_taps=False):
+    def __init__(self, net, batch, reuse_buffers=True, keep_taps=False, u8_input=False):
         self.net = net
+        self.u8_input = bool(u8_input)     # images are raw letterboxed uint8 RGB; normalised inside the stem
         self.B = int(batch)
         self.dev = net.device
         self.dtype = net.dtype
@@ -84,6 +86,11 @@ class Plan:
         self._assign_buffers()
         for op in self.ops:
             op.fn = op.make()
+
+    @property
+    def input_images(self):
+        """The Val the caller's images are copied into (uint8 for a u8_input plan)."""
+        return getattr(self, "images_u8", None) or self.images
 
     # -------------------------------------------------------------- helpers
     def val(self, shape, dtype=None, name=None, keep=False):
@@ -178,7 +185,7 @@ class Plan:
     def _build(self):
         net, B, S = self.net, self.B, self.net.image_size
         bb = net.backbone
-        self.images = self.val((B, S, S, 3), F32, "images", keep=True)
+        self.images = self.val((B, S, S, 3), "u8" if self.u8_input else F32, "images", keep=True)
         x, H = self._stem()
         feats = []
         for bi, blk in enumerate(bb.blocks):
@@ -196,10 +203,17 @@ class Plan:
         c0 = net.backbone.stem_filters
         x = self.val((B, H, H, c0), name="stem")
         sc, sh = self.folded("stem_bn")
-        self.add("stem", [self.images], [x],
-                 lambda: _call("effdet_stem_conv", self.images.ptr, self.w("stem_conv/kernel").data_ptr(),
-                               sc.data_ptr(), sh.data_ptr(), x.ptr, B, S, S, c0, self.dtype),
-                 "stem_conv")
+        if self.u8_input:
+            lut = net.normalization_lut()
+            self.add("stem", [self.images], [x],
+                     lambda: _call("effdet_stem_conv_u8", self.images.ptr, lut.data_ptr(),
+                                   self.w("stem_conv/kernel").data_ptr(), sc.data_ptr(), sh.data_ptr(), x.ptr,
+                                   B, S, S, c0, ACT_SWISH, self.dtype), "stem_conv")
+        else:
+            self.add("stem", [self.images], [x],
+                     lambda: _call("effdet_stem_conv", self.images.ptr, self.w("stem_conv/kernel").data_ptr(),
+                                   sc.data_ptr(), sh.data_ptr(), x.ptr, B, S, S, c0, self.dtype),
+                     "stem_conv")
         return x, H
 
     def drop_keep(self, blk):
@@ -434,7 +448,8 @@ class Plan:
                 for i, op in enumerate(self.ops)]
 
     def forward(self, images):
-        """images: (B,S,S,3) float32 CUDA tensor -> (regression, classification) views."""
-        self.tensor(self.images).copy_(images, non_blocking=True)
+        """images: (B,S,S,3) float32 (or, for a u8_input plan, uint8) CUDA tensor -> (regression,
+        classification) views."""
+        self.tensor(self.input_images).copy_(images, non_blocking=True)
         self.replay()
         return self.tensor(self.regression), self.tensor(self.classification)

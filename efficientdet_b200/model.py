@@ -33,6 +33,11 @@ def _fuse_name(k):
     return "w_bi_fpn_add" if k == 0 else "w_bi_fpn_add_%d" % k
 
 
+def _is_u8(images):
+    return (images.dtype == torch.uint8) if isinstance(images, torch.Tensor) else \
+        (getattr(images, "dtype", None) == np.uint8)
+
+
 class Network:
     """Weights (Keras names, fp32 masters on the device) + derived tensors + plans."""
 
@@ -209,6 +214,14 @@ class Network:
         _lib.call("effdet_conv_weight_panel", self.weights[k[0]].data_ptr(), t.data_ptr(), taps, cin, cout,
                   k[1], None, 0, _lib.stream_ptr(self.device))
 
+    def normalization_lut(self):
+        """(3, 256) f32 on the device: lut[c][v] = ((v / 255) - mean_c) / std_c evaluated in float32 the way the
+        reference does (train_tpu.py:130-140, generators/common.py:418-429) -- see utils.preprocess."""
+        if getattr(self, "_norm_lut", None) is None:
+            from .utils.preprocess import normalization_lut
+            self._norm_lut = torch.from_numpy(normalization_lut()).to(self.device)
+        return self._norm_lut
+
     def plan(self, batch, **kw):
         if getattr(self, "_dirty", False):
             self.refresh()
@@ -300,12 +313,13 @@ class Model:
     # ---------------------------------------------------------------- inference
     def _stage(self, images):
         """host numpy -> pinned staging buffer -> device (async)."""
+        u8 = _is_u8(images)
         if isinstance(images, torch.Tensor):
-            return images.to(self.net.device, torch.float32)
-        a = np.ascontiguousarray(images, np.float32)
-        key = a.shape
+            return images.to(self.net.device, torch.uint8 if u8 else torch.float32)
+        a = np.ascontiguousarray(images, np.uint8 if u8 else np.float32)
+        key = (a.shape, u8)
         if key not in self._pinned:
-            self._pinned[key] = torch.empty(a.shape, dtype=torch.float32).pin_memory()
+            self._pinned[key] = torch.empty(a.shape, dtype=torch.uint8 if u8 else torch.float32).pin_memory()
         self._pinned[key].numpy()[...] = a
         return self._pinned[key].to(self.net.device, non_blocking=True)
 
@@ -321,7 +335,9 @@ class Model:
         if tuple(images.shape[1:]) != (S, S, 3):
             raise ValueError("expected images of shape (B, %d, %d, 3), got %s" % (S, S, tuple(images.shape)))
         B = int(images.shape[0])
-        plan = net.plan(B)
+        # uint8 input = the raw letterboxed RGB image (utils.preprocess.preprocess_image); normalize_image runs
+        # inside the stem kernel
+        plan = net.plan(B, u8_input=True) if _is_u8(images) else net.plan(B)
         reg, cls = plan.forward(self._stage(images))
         if self._outputs == "train":
             return [reg, cls]
@@ -348,8 +364,8 @@ class Model:
         return [o.cpu().numpy() for o in outs]
 
     def predict_generator(self, batches):
-        """keras Model.predict_generator over an iterable of HOST image batches ((B,S,S,3) float32 torch
-        tensors, ideally pinned): the host->device copy of batch i+1 runs on a copy stream while batch i
+        """keras Model.predict_generator over an iterable of HOST image batches ((B,S,S,3) float32 -- or raw
+        uint8 -- torch tensors, ideally pinned): the host->device copy of batch i+1 runs on a copy stream while batch i
         is computed (what the reference gets from keras' generator queue / tf.data prefetch).  Yields
         the outputs of predict_on_batch (numpy) per batch."""
         dev = self.net.device
@@ -361,9 +377,10 @@ class Model:
 
         def stage(slot, xb):
             xb = torch.as_tensor(xb)
-            key = (slot, tuple(xb.shape))
+            dt = torch.uint8 if xb.dtype == torch.uint8 else torch.float32
+            key = (slot, tuple(xb.shape), dt)
             if key not in self._slots:
-                self._slots[key] = torch.empty(xb.shape, dtype=torch.float32, device=dev)
+                self._slots[key] = torch.empty(xb.shape, dtype=dt, device=dev)
             d = self._slots[key]
             with torch.cuda.stream(cs):
                 d.copy_(xb, non_blocking=True)

@@ -29,7 +29,7 @@ class TrainPlan(engine.Plan):
     """Forward (training mode) + losses + backward launch list for a fixed batch."""
 
     def __init__(self, net, batch, alpha=0.25, gamma=1.5, delta=1.0, dense_labels=False,
-                 reuse_buffers=True, train_backbone=False):
+                 reuse_buffers=True, train_backbone=False, u8_input=False):
         self.alpha, self.gamma, self.delta = alpha, gamma, delta
         self.dense_labels = dense_labels
         self.train_backbone = train_backbone
@@ -50,7 +50,7 @@ class TrainPlan(engine.Plan):
             rank = torch.distributed.get_rank() if (torch.distributed.is_available() and
                                                     torch.distributed.is_initialized()) else 0
             self.drop_seed = (int(getattr(net, "seed", 0) or 0) * 1000003 + 7919 * rank + 12345) & (2 ** 63 - 1)
-        super().__init__(net, batch, reuse_buffers=reuse_buffers)
+        super().__init__(net, batch, reuse_buffers=reuse_buffers, u8_input=u8_input)
 
     # ------------------------------------------------------------------ small helpers
     def gw(self, key):
@@ -533,6 +533,15 @@ class TrainPlan(engine.Plan):
         z = self.val((B, H, H, c0), name="stem_z", keep=True)
         y = self.val((B, H, H, c0), name="stem", keep=True)
         ones, zeros = net.const_ones(c0), net.const_zeros(c0)
+        if self.u8_input:
+            # a trainable stem needs the normalised image again for its weight gradient: materialise it once
+            # on the device (the upload stays 3 B/pixel)
+            raw, lut = self.images, net.normalization_lut()
+            self.images_u8 = raw
+            self.images = self.val((B, S, S, 3), F32, "images_f32", keep=True)
+            self.add("stem", [raw], [self.images],
+                     lambda: _call("effdet_normalize_u8", raw.ptr, lut.data_ptr(), self.images.ptr,
+                                   B * S * S * 3), "normalize_image")
         # raw conv: identity scale/shift; swish is applied after the batch-norm pass, so the
         # stem kernel's built-in swish cannot be used -> run it through the generic conv (Cin = 3)
         if self.dtype == BF16 and c0 in (32, 40, 48, 56, 64):
@@ -689,10 +698,20 @@ class TrainPlan(engine.Plan):
         else:
             d_xin, acc = self.grad_of(inp)
             assert acc == 0, "block without expansion must be the only consumer of its input"
-        self.add("dw_bwd", [xin, dz_d], [d_xin, dwp],
-                 lambda: _call("effdet_dw_backward", xin.ptr, dz_d.ptr, w(dkey).data_ptr(), d_xin.ptr,
-                               gw(dkey).data_ptr(), dwp.ptr, nb, B, H, H, cmid, k, st, self.dtype), p + "dw_bwd",
-                 flops=4 * k * k * B * Ho * Ho * cmid)
+        if st == 2 and self.dtype == BF16:
+            # stride-2 data gradient on the TMA tile pipeline: zero-insert dz into an x-sized tensor, then
+            # the stride-1 depthwise kernel with spatially flipped taps (the gather-form kernel that
+            # effdet_dw_backward falls back to runs at 0.5-1.4 TB/s); the weight gradient stays there
+            self.add("dw_bwd", [xin, dz_d], [dwp],
+                     lambda: _call("effdet_dw_backward", xin.ptr, dz_d.ptr, w(dkey).data_ptr(), None,
+                                   gw(dkey).data_ptr(), dwp.ptr, nb, B, H, H, cmid, k, st, self.dtype),
+                     p + "dw_wgrad", flops=2 * k * k * B * Ho * Ho * cmid)
+            self._dw_dgrad_stride2(dz_d, dkey, d_xin, H, Ho, cmid, k, p)
+        else:
+            self.add("dw_bwd", [xin, dz_d], [d_xin, dwp],
+                     lambda: _call("effdet_dw_backward", xin.ptr, dz_d.ptr, w(dkey).data_ptr(), d_xin.ptr,
+                                   gw(dkey).data_ptr(), dwp.ptr, nb, B, H, H, cmid, k, st, self.dtype),
+                     p + "dw_bwd", flops=4 * k * k * B * Ho * Ho * cmid)
         if blk.expand_ratio == 1:
             return
         bn_e = dict(rec["bn_e"]); bn_e["z"] = rec["z_e"]
@@ -710,6 +729,28 @@ class TrainPlan(engine.Plan):
         wt = self._transposed_weight(ekey, 1, cin, cmid)
         self._dgrad(None, [dz_e], wt, cmid, cin, [g], [inp], None, [acc], [inp.shape], name=p + "expand_dgrad",
                     key=ekey, extra_residual=extra)
+
+    def _dw_dgrad_stride2(self, dz, dkey, dx, H, Ho, C, k, p):
+        """dx (B,H,H,C) of a stride-2 SAME depthwise conv (efficientnet.py:242-252).  With the forward
+        iy = 2*oy - pad_t + ky, dx[iy] = sum_ky U[iy + pad_t - ky] w[ky] for U = dz with zeros between samples;
+        the stride-1 SAME conv with flipped taps computes sum_ky V[iy + (k-1)/2 - ky] w[ky], so V is U
+        shifted by (k-1)/2 - pad_t (1 for even H, 0 for odd H)."""
+        B = self.B
+        pad_t = max((Ho - 1) * 2 + k - H, 0) // 2
+        shift = (k - 1) // 2 - pad_t
+        assert shift in (0, 1) and 2 * (Ho - 1) + shift < H
+        U = self.val((B, H, H, C), name=p + "dw_dz_zero_inserted")
+        self.add("zero_insert", [dz], [U],
+                 lambda: _call("effdet_zero_insert", dz.ptr, U.ptr, B, Ho, Ho, C, H, H, shift, shift, self.dtype),
+                 p + "dw_zero_insert")
+        wflip = self._scratch(k * k * C, p + "dw_flip")
+        self.add("wtrans", [], [wflip],
+                 lambda: _call("effdet_flip_taps", self.w(dkey).data_ptr(), wflip.ptr, k * k, C), p + "dw_flip")
+        ones, zeros = self.net.const_ones(C), self.net.const_zeros(C)
+        self.add("dwconv", [U, wflip], [dx],
+                 lambda: _call("effdet_dwconv", U.ptr, wflip.ptr, ones.data_ptr(), zeros.data_ptr(), dx.ptr,
+                               None, 0, B, H, H, C, k, 1, ACT_NONE, self.dtype), p + "dw_dgrad_s2",
+                 flops=2 * k * k * B * H * H * C)
 
     def _stem_backward(self, rec):
         lib = _lib.load()
@@ -850,8 +891,8 @@ class Trainer:
         self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         self.graphs = {}
 
-    def plan(self, B, dense):
-        key = (B, dense)
+    def plan(self, B, dense, u8=False):
+        key = (B, dense, bool(u8))
         if key not in self.plans:
             net = self.net
             names = net.backbone.keras_layer_names()
@@ -865,7 +906,7 @@ class Trainer:
             self.plans[key] = TrainPlan(net, B, self.focal.alpha, self.focal.gamma, self.sl1.lambda_,
                                         dense_labels=dense,
                                         reuse_buffers=os.environ.get("EFFDET_NO_REUSE") != "1",
-                                        train_backbone=self.train_backbone)
+                                        train_backbone=self.train_backbone, u8_input=bool(u8))
         return self.plans[key]
 
     def load_batch(self, plan, images, targets):
@@ -873,8 +914,8 @@ class Trainer:
         (regression_t, state i8, cls i32) device tensors from anchor_targets_device(compact=True)."""
         dev = self.net.device
         img = images if isinstance(images, torch.Tensor) else torch.from_numpy(
-            np.ascontiguousarray(images, np.float32))
-        plan.tensor(plan.images).copy_(img.to(dev, non_blocking=True))
+            np.ascontiguousarray(images, np.uint8 if plan.u8_input else np.float32))
+        plan.tensor(plan.input_images).copy_(img.to(dev, non_blocking=True))
         if plan.dense_labels:
             reg_t, lab_t = targets
             plan.tensor(plan.reg_t).copy_(torch.as_tensor(reg_t).to(dev, non_blocking=True))
@@ -946,7 +987,7 @@ class Trainer:
             self._copy_stream = torch.cuda.Stream(dev)
             self._slots = {}
         cs = self._copy_stream
-        img_buf = plan.tensor(plan.images)
+        img_buf = plan.tensor(plan.input_images)
 
         def stage(slot, batch):
             imgs, gt, kmax = batch
@@ -981,7 +1022,8 @@ class Trainer:
     def step(self, images, targets, sync=True):
         dense = not (isinstance(targets, (tuple, list)) and len(targets) == 3)
         B = int(images.shape[0])
-        plan = self.plan(B, dense)
+        from .model import _is_u8
+        plan = self.plan(B, dense, u8=_is_u8(images))     # uint8 = raw letterboxed RGB (utils.preprocess)
         self.load_batch(plan, images, targets)
         plan.run()
         self.apply_gradients()
@@ -1095,6 +1137,36 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev, freeze_backb
     run_e2e(2)
     ms_e2e = timed_e2e(args.steps)
     clk = clocks.stop() if clocks else {}
+
+    # the same end-to-end loop fed with raw letterboxed uint8 images (what train_tpu.py:170-183 decodes from the
+    # TFRecord PNGs): normalize_image runs on the device, the image upload is 3 B/pixel
+    rng8 = np.random.default_rng(4321 + rank)
+    pinned8 = [torch.from_numpy(rng8.integers(0, 256, (B, S, S, 3), dtype=np.uint8)).pin_memory()
+               for _ in range(n_sets)]
+    plan8 = tr.plan(B, dense=False, u8=True)
+    plan8.tensor(plan8.input_images).copy_(pinned8[0].to(dev))
+    g0 = gts[0]
+    tr.targets_into_plan(plan8, anchors_d, g0["dev"][0], g0["dev"][1], g0["dev"][2], g0["dev"][3], g0["kmax"])
+    plan8.replay()
+    tr.apply_gradients()
+    torch.cuda.synchronize(dev)
+    plan8.capture()
+
+    def run_e2e8(steps):
+        gen = ((pinned8[i % n_sets], gts[i % n_sets]["host"], gts[i % n_sets]["kmax"]) for i in range(steps))
+        for _ in tr.fit_prefetched(plan8, anchors_d, gen):
+            pass
+    run_e2e8(3)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(torch.cuda.current_stream(dev))
+    run_e2e8(args.steps)
+    e1.record(torch.cuda.current_stream(dev))
+    torch.cuda.synchronize(dev)
+    from . import parallel as _par
+    ms_e2e8 = _par.max_over_ranks(e0.elapsed_time(e1), dev)
     losses = plan.tensor(plan.loss_out).cpu().numpy().tolist()
 
     prof = plan.profile(iters=3)
@@ -1142,6 +1214,10 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev, freeze_backb
                    "final_losses": losses[:2]},
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 32},
+        "e2e_uint8": {"value": imgs / (ms_e2e8 * 1e-3), "unit": "images/s",
+                      "h2d_bytes_per_step": int(h2d - B * S * S * 9), "d2h_bytes_per_step": 32,
+                      "note": "same loop, raw letterboxed uint8 RGB input (train_tpu.py TFRecord format; "
+                              "normalize_image on the device)"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
     }

@@ -129,6 +129,20 @@ int effdet_stem_conv(const float *images, const float *kernel, const float *scal
  * statistics, efficientnet.py:413-423 with trainable BN). */
 int effdet_stem_conv_act(const float *images, const float *kernel, const float *scale, const float *shift,
                          void *out, int B, int H, int W, int C0, int act, void *stream);
+/* Same stem fed with the raw letterboxed uint8 RGB image -- what train_tpu.py:170-183 decodes from the
+ * TFRecord PNG and what generators/common.py:406-417 builds before dividing by 255.  normalize_image
+ * (train_tpu.py:135-140 == generators/common.py:418-429: ((v / 255) - mean_c) / std_c in float32) is applied on
+ * the fly through lut (3 x 256 f32, lut[c*256 + v], evaluated by the caller in float32 exactly like the
+ * reference), so the result is bit-identical to effdet_stem_conv on the normalised float image while the
+ * 12 B/pixel float image is never uploaded or stored.  SAME padding is zero in normalised space.
+ * act: EFFDET_ACT_SWISH, or EFFDET_ACT_NONE with bf16 output (training: raw z). */
+int effdet_stem_conv_u8(const unsigned char *images, const float *lut, const float *kernel, const float *scale,
+                        const float *shift, void *out, int B, int H, int W, int C0, int act, int out_dtype,
+                        void *stream);
+/* normalize_image alone: out[i] = lut[(i % 3)*256 + images[i]] over n_values = B*H*W*3 interleaved RGB bytes
+ * (for callers that need the float image itself: the weight gradient of a trainable stem). */
+int effdet_normalize_u8(const unsigned char *images, const float *lut, float *out, size_t n_values,
+                        void *stream);
 
 
 /* Dense convolution as implicit GEMM (1x1 or 3x3, stride 1 or 2, TF SAME padding) with fused

@@ -192,6 +192,75 @@ def test_stem():
     assert rel_err(out.cpu().numpy(), _nhwc(y)) < 1e-5
 
 
+@pytest.mark.parametrize("C0,S,B,dtype,act", [(32, 34, 2, "fp32", 2), (32, 70, 3, "bf16", 2), (48, 33, 2, "bf16", 2),
+                                              (40, 64, 1, "bf16", 0), (16, 20, 2, "fp32", 2), (16, 20, 2, "bf16", 2)])
+def test_stem_uint8_input_is_bit_identical(C0, S, B, dtype, act):
+    """effdet_stem_conv_u8 (raw letterboxed bytes + the per-byte normalisation table) == the float stem on
+    the normalised image (train_tpu.py:135-140), bit for bit; effdet_normalize_u8 == the oracle (pinned on the
+    reference's utils.normalize_image by tests/golden/preprocess.npz)."""
+    from efficientdet_b200 import _lib
+    from efficientdet_b200.utils.preprocess import normalization_lut
+    from oracle import preprocess as op
+    rng = np.random.default_rng(C0 + S)
+    img = rng.integers(0, 256, (B, S, S, 3), dtype=np.uint8)
+    norm = op.normalize_image_ref(img)
+    w = (rng.standard_normal((3, 3, 3, C0)) / 5).astype(np.float32)
+    sc = rng.uniform(0.5, 1.5, C0).astype(np.float32)
+    sh = rng.normal(0, 0.2, C0).astype(np.float32)
+    Ho = (S + 1) // 2
+    tdt = torch.float32 if dtype == "fp32" else torch.bfloat16
+    cdt = _lib.F32 if dtype == "fp32" else _lib.BF16
+    a = torch.full((B, Ho, Ho, C0), float("nan"), dtype=tdt, device="cuda")
+    b = torch.full((B, Ho, Ho, C0), float("nan"), dtype=tdt, device="cuda")
+    u8d = torch.from_numpy(img).cuda()
+    lut = _dev(normalization_lut())
+    xd, wd, scd, shd = _dev(norm), _dev(w), _dev(sc), _dev(sh)
+    st = _lib.stream_ptr()
+    nf = torch.empty((B, S, S, 3), dtype=torch.float32, device="cuda")
+    _lib.call("effdet_normalize_u8", u8d.data_ptr(), lut.data_ptr(), nf.data_ptr(), B * S * S * 3, st)
+    assert np.array_equal(nf.cpu().numpy(), norm)
+    if dtype == "bf16" and C0 in (32, 40, 48, 56, 64):
+        _lib.call("effdet_stem_conv_act", xd.data_ptr(), wd.data_ptr(), scd.data_ptr(), shd.data_ptr(),
+                  a.data_ptr(), B, S, S, C0, act, st)
+    else:
+        _lib.call("effdet_stem_conv", xd.data_ptr(), wd.data_ptr(), scd.data_ptr(), shd.data_ptr(),
+                  a.data_ptr(), B, S, S, C0, cdt, st)
+    _lib.call("effdet_stem_conv_u8", u8d.data_ptr(), lut.data_ptr(), wd.data_ptr(), scd.data_ptr(),
+              shd.data_ptr(), b.data_ptr(), B, S, S, C0, act, cdt, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(a.view(torch.int16 if dtype == "bf16" else torch.int32).cpu().numpy(),
+                          b.view(torch.int16 if dtype == "bf16" else torch.int32).cpu().numpy())
+    assert not torch.isnan(b.float()).any()
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_model_accepts_raw_uint8_images(dtype):
+    """predict_on_batch(uint8 letterboxed image) == predict_on_batch(normalize_image(image)), bit-exact, through
+    FilterDetections; the uint8 image comes from utils.preprocess.preprocess_image (utils/__init__.py:103-138)."""
+    from efficientdet_b200.model import efficientdet
+    from efficientdet_b200.utils.anchors import anchors_for_shape
+    from efficientdet_b200.utils.preprocess import normalize_image, preprocess_image
+    size, classes = 128, 5
+    anchors = anchors_for_shape((size, size))
+    model, pmodel = efficientdet(0, num_classes=classes, image_size=size, score_threshold=0.3, dtype=dtype,
+                                 drop_connect_rate=0, anchors=anchors)
+    perturb_weights(model)
+    rng = np.random.default_rng(3)
+    raw = [rng.integers(0, 256, (97, 150, 3), dtype=np.uint8), rng.integers(0, 256, (200, 131, 3), dtype=np.uint8)]
+    boxed = np.stack([preprocess_image(r, size)[0] for r in raw])
+    assert boxed.dtype == np.uint8 and boxed.shape == (2, size, size, 3)
+    r8, c8 = model.predict_on_batch(boxed)
+    rf, cf = model.predict_on_batch(normalize_image(boxed))
+    assert np.array_equal(r8, rf) and np.array_equal(c8, cf)
+    d8 = pmodel.predict_on_batch([boxed])
+    df = pmodel.predict_on_batch([normalize_image(boxed)])
+    for x, y in zip(d8, df):
+        assert np.array_equal(x, y)
+    g8 = list(pmodel.predict_generator([torch.from_numpy(boxed).pin_memory()]))[0]
+    for x, y in zip(g8, df):
+        assert np.array_equal(x, y)
+
+
 # ------------------------------------------------------------------ whole network
 @pytest.mark.parametrize("phi,size,weighted,dtype,classes", [
     (0, 128, False, "fp32", 20), (0, 256, True, "fp32", 90), (0, 256, True, "bf16", 20),

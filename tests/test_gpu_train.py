@@ -508,6 +508,36 @@ def test_depthwise_backward_bf16_tma(k, stride, C, H, B):
     assert rel_err(dx.float().cpu().numpy(), xr.grad.permute(0, 2, 3, 1).numpy()) < 6e-3
 
 
+@pytest.mark.parametrize("k,C,H,B", [(3, 96, 16, 2), (5, 240, 18, 2), (3, 48, 21, 1), (5, 64, 33, 2)])
+def test_depthwise_stride2_dgrad_by_zero_insertion(k, C, H, B):
+    """The training plan's stride-2 depthwise data gradient (TrainPlan._dw_dgrad_stride2): dz zero-inserted
+    at offset (k-1)/2 - pad_t, then the stride-1 TMA depthwise kernel with flipped taps -- against autograd
+    of the stride-2 SAME depthwise conv (efficientnet.py:242-252), even and odd input sizes."""
+    from efficientdet_b200 import _lib
+    from oracle import graph
+    rng = np.random.default_rng(k * 10 + C + H)
+    Ho = (H + 1) // 2
+    dz = torch.from_numpy(rng.standard_normal((B, Ho, Ho, C)).astype(np.float32)).cuda().to(torch.bfloat16)
+    w = torch.from_numpy((rng.standard_normal((k, k, C)) * 0.3).astype(np.float32)).cuda()
+    pad_t = max((Ho - 1) * 2 + k - H, 0) // 2
+    shift = (k - 1) // 2 - pad_t
+    U = torch.full((B, H, H, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    wflip = torch.empty_like(w)
+    dx = torch.full((B, H, H, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ones, zeros = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+    st = _lib.stream_ptr()
+    _lib.call("effdet_zero_insert", dz.data_ptr(), U.data_ptr(), B, Ho, Ho, C, H, H, shift, shift, _lib.BF16, st)
+    _lib.call("effdet_flip_taps", w.data_ptr(), wflip.data_ptr(), k * k, C, st)
+    _lib.call("effdet_dwconv", U.data_ptr(), wflip.data_ptr(), ones.data_ptr(), zeros.data_ptr(), dx.data_ptr(),
+              None, 0, B, H, H, C, k, 1, _lib.ACT_NONE, _lib.BF16, st)
+    torch.cuda.synchronize()
+    xr = torch.zeros((B, C, H, H), dtype=torch.float64, requires_grad=True)
+    wt = w.cpu().double().permute(2, 0, 1)[:, None]
+    y = torch.nn.functional.conv2d(graph.same_pad(xr, k, 2), wt, None, stride=2, groups=C)
+    y.backward(dz.float().cpu().double().permute(0, 3, 1, 2))
+    assert rel_err(dx.float().cpu().numpy(), xr.grad.permute(0, 2, 3, 1).numpy()) < 6e-3
+
+
 @pytest.mark.parametrize("C0,H,B", [(32, 64, 2), (48, 70, 3), (40, 33, 1)])
 def test_stem_weight_gradient_bf16(C0, H, B):
     """Stem conv (efficientnet.py:413-423: 3x3, stride 2, 3 -> C0) weight gradient from bf16 dz (tiled
@@ -611,6 +641,35 @@ def test_training_step_with_stochastic_depth(freeze_backbone):
     assert not np.array_equal(plan.drop_scales.cpu().numpy(), scales)
     # inference is unaffected by the mask (FixedDropout only acts in the training phase)
     assert model.net.drop_scale == {}
+
+
+@pytest.mark.parametrize("freeze_backbone,dtype", [(True, "bf16"), (False, "bf16"), (False, "fp32")])
+def test_training_step_on_raw_uint8_images(freeze_backbone, dtype):
+    """train_on_batch(uint8 letterboxed images) == train_on_batch(normalize_image(images)): the TFRecord path
+    of the reference decodes uint8 PNGs and normalises them on the fly (train_tpu.py:170-183); here the
+    normalisation runs inside the stem (frozen backbone) or once on the device (trainable stem, whose weight
+    gradient needs the float image).  The step is deterministic, so losses and gradients are bit-identical."""
+    from efficientdet_b200.model import efficientdet
+    from efficientdet_b200.optimizers import SGD
+    from efficientdet_b200.utils.preprocess import normalize_image
+    size, C, B = 128, 4, 4
+    anchors, ann, reg_t, lab_t = _targets(size, B, C)
+    img8 = np.random.default_rng(11).integers(0, 256, (B, size, size, 3), dtype=np.uint8)
+    res = []
+    for images in (img8, normalize_image(img8)):
+        model = efficientdet(0, num_classes=C, image_size=size, dtype=dtype, drop_connect_rate=0,
+                             just_training_model=True, seed=5)
+        if freeze_backbone:
+            model.freeze_backbone()
+        model.compile(optimizer=SGD(lr=0.01, decay=4e-5, momentum=0.9))
+        out = model.train_on_batch(images, [reg_t, lab_t])
+        g = model.net.grads
+        res.append((out, g["class_head/pyramid_classification/kernel"].cpu().numpy().copy(),
+                    g["stem_conv/kernel"].cpu().numpy().copy()))
+    assert res[0][0] == res[1][0]
+    assert np.array_equal(res[0][1], res[1][1])
+    if not freeze_backbone:
+        assert np.abs(res[0][2]).max() > 0 and np.array_equal(res[0][2], res[1][2])
 
 
 def test_fit_prefetched_matches_stepwise_training():
