@@ -257,10 +257,10 @@ static int launch_dw_tiled(const void *x, const float *w, const float *scale, co
 // chains, fixed summation orders (bit-reproducible).
 constexpr int kSeThreads = 512;
 
-template <int VW>
+template <int VW, int NTH = kSeThreads>
 __device__ __forceinline__ void se_fc1(const float *__restrict__ mean, const float *__restrict__ w1, float *part,
                                        int C, int R, int tid) {
-    const int JV = R / VW, G = kSeThreads / JV;
+    const int JV = R / VW, G = NTH / JV;
     const int jv = tid % JV, cg = tid / JV;
     if (cg >= G) return;
     float s[4][VW];
@@ -380,6 +380,156 @@ se_gate_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_hw,
         o.w = activate<EFFDET_ACT_SIGMOID>(bb.w + ((s[0][3] + s[1][3]) + (s[2][3] + s[3][3])));
         *reinterpret_cast<float4 *>(gate + (size_t)b * C + c) = o;
     }
+}
+
+// Thread-block-cluster version: the NC CTAs of a cluster share ONE image.  Each CTA owns a slice of the C
+// channels: it reduces the squeeze partials of its slice, forms the partial FC1 products of that slice for all
+// R hidden units, the cluster exchanges the NC partial vectors through distributed shared memory (summed in
+// rank order: deterministic), and each CTA finishes FC2 + sigmoid for its own slice.  One image then streams
+// its 2*C*R weights through NC SMs with NC-times shorter dependent-load chains -- the single-CTA kernel above
+// is a chain of ~25 L2 round trips per image on one SM (11-35 us per block of the network, 18 % of the
+// batch-1 inference step).
+constexpr int kSeCT = 256;
+template <int NC>
+__global__ void __launch_bounds__(kSeCT)
+se_gate_cluster_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_hw,
+                       const float *__restrict__ w1, const float *__restrict__ b1,
+                       const float *__restrict__ w2, const float *__restrict__ b2,
+                       float *__restrict__ gate, int C, int R, int Cs) {
+    EFFDET_PDL_SYNC();
+    extern __shared__ __align__(16) float smc[];     // mean[Cs] | rpart[Rp] | r[Rp] | part[4 * kSeCT + Cs]
+    const int Rp = (R + 3) & ~3;                     // keeps `part` 16-byte aligned
+    float *mean = smc, *rpart = smc + Cs, *r = rpart + Rp, *part = r + Rp;
+    unsigned rank;
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int b = blockIdx.x / NC, tid = threadIdx.x;
+    const int c0 = (int)rank * Cs;
+    int n = C - c0; n = n > Cs ? Cs : (n < 0 ? 0 : n);
+    // ---- squeeze: mean of this CTA's channel slice (KS thread groups per channel, fixed order)
+    if (n > 0) {
+        const int KS = n >= kSeCT ? 1 : kSeCT / n;
+        const float *src0 = se_sum + (size_t)b * se_blocks * C + c0;
+        for (int idx = tid; idx < n * KS; idx += kSeCT) {
+            const int c = idx % n, sl = idx / n;
+            const float *src = src0 + c;
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+            int k = sl;
+            for (; k + 3 * KS < se_blocks; k += 4 * KS) {
+                t0 += src[(size_t)k * C]; t1 += src[(size_t)(k + KS) * C];
+                t2 += src[(size_t)(k + 2 * KS) * C]; t3 += src[(size_t)(k + 3 * KS) * C];
+            }
+            for (; k < se_blocks; k += KS) t0 += src[(size_t)k * C];
+            part[sl * n + c] = (t0 + t1) + (t2 + t3);
+        }
+        __syncthreads();
+        for (int c = tid; c < n; c += kSeCT) {
+            float t = 0.f;
+            for (int s2 = 0; s2 < KS; ++s2) t += part[s2 * n + c];
+            mean[c] = t * inv_hw;
+        }
+    }
+    __syncthreads();
+    // ---- FC1, partial over the slice
+    const float *w1s = w1 + (size_t)c0 * R;
+    const bool v4 = (R % 4 == 0) && ((reinterpret_cast<uintptr_t>(w1s) & 15) == 0) && R / 4 <= kSeCT;
+    const bool v2 = (R % 2 == 0) && ((reinterpret_cast<uintptr_t>(w1s) & 7) == 0) && R / 2 <= kSeCT;
+    if (n > 0 && R <= kSeCT) {
+        int G;
+        if (v4) { se_fc1<4, kSeCT>(mean, w1s, part, n, R, tid); G = kSeCT / (R / 4); }
+        else if (v2) { se_fc1<2, kSeCT>(mean, w1s, part, n, R, tid); G = kSeCT / (R / 2); }
+        else { se_fc1<1, kSeCT>(mean, w1s, part, n, R, tid); G = kSeCT / R; }
+        __syncthreads();
+        if (tid < R) {
+            float t = 0.f;
+            for (int g = 0; g < G; ++g) t += part[g * R + tid];
+            rpart[tid] = t;
+        }
+    } else {
+        for (int j = tid; j < R; j += kSeCT) {          // R > 256 (not reached by EfficientNet) or empty slice
+            float t = 0.f;
+            for (int c = 0; c < n; ++c) t = fmaf(mean[c], w1s[(size_t)c * R + j], t);
+            rpart[j] = t;
+        }
+    }
+    // ---- exchange: every CTA adds the NC partial vectors in rank order (DSMEM reads)
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    for (int j = tid; j < R; j += kSeCT) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            uint32_t ra;
+            asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra)
+                : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(rpart + j))), "r"(k));
+            float v;
+            asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra));
+            t += v;
+        }
+        r[j] = activate<EFFDET_ACT_SWISH>(t + b1[j]);
+    }
+    // nobody may leave (or reuse rpart) while a peer still reads it; also orders r[] for this CTA
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (n <= 0) return;
+    // ---- FC2 + sigmoid on the slice: thread = (channel quad, r-group); quads along lanes (16-byte loads)
+    const int q = n / 4;
+    int RG = kSeCT / q; if (RG < 1) RG = 1; if (RG > R) RG = R;
+    const float *w2s = w2 + c0;
+    for (int idx = tid; idx < q * RG; idx += kSeCT) {
+        const int quad = idx % q, rg = idx / q;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+        int j = rg;
+        for (; j + 3 * RG < R; j += 4 * RG) {
+            const float4 q0 = *reinterpret_cast<const float4 *>(w2s + (size_t)j * C + quad * 4);
+            const float4 q1 = *reinterpret_cast<const float4 *>(w2s + (size_t)(j + RG) * C + quad * 4);
+            const float4 q2 = *reinterpret_cast<const float4 *>(w2s + (size_t)(j + 2 * RG) * C + quad * 4);
+            const float4 q3 = *reinterpret_cast<const float4 *>(w2s + (size_t)(j + 3 * RG) * C + quad * 4);
+            const float r0 = r[j], r1 = r[j + RG], r2 = r[j + 2 * RG], r3 = r[j + 3 * RG];
+            a0.x = fmaf(r0, q0.x, a0.x); a0.y = fmaf(r0, q0.y, a0.y); a0.z = fmaf(r0, q0.z, a0.z); a0.w = fmaf(r0, q0.w, a0.w);
+            a1.x = fmaf(r1, q1.x, a1.x); a1.y = fmaf(r1, q1.y, a1.y); a1.z = fmaf(r1, q1.z, a1.z); a1.w = fmaf(r1, q1.w, a1.w);
+            a2.x = fmaf(r2, q2.x, a2.x); a2.y = fmaf(r2, q2.y, a2.y); a2.z = fmaf(r2, q2.z, a2.z); a2.w = fmaf(r2, q2.w, a2.w);
+            a3.x = fmaf(r3, q3.x, a3.x); a3.y = fmaf(r3, q3.y, a3.y); a3.z = fmaf(r3, q3.z, a3.z); a3.w = fmaf(r3, q3.w, a3.w);
+        }
+        for (; j < R; j += RG) {
+            const float4 q0 = *reinterpret_cast<const float4 *>(w2s + (size_t)j * C + quad * 4);
+            const float r0 = r[j];
+            a0.x = fmaf(r0, q0.x, a0.x); a0.y = fmaf(r0, q0.y, a0.y); a0.z = fmaf(r0, q0.z, a0.z); a0.w = fmaf(r0, q0.w, a0.w);
+        }
+        float4 o;
+        o.x = (a0.x + a1.x) + (a2.x + a3.x); o.y = (a0.y + a1.y) + (a2.y + a3.y);
+        o.z = (a0.z + a1.z) + (a2.z + a3.z); o.w = (a0.w + a1.w) + (a2.w + a3.w);
+        *reinterpret_cast<float4 *>(part + (size_t)rg * n + quad * 4) = o;
+    }
+    __syncthreads();
+    for (int quad = tid; quad < q; quad += kSeCT) {
+        float4 t = *reinterpret_cast<const float4 *>(b2 + c0 + quad * 4);
+        for (int rg = 0; rg < RG; ++rg) {
+            const float4 v = *reinterpret_cast<const float4 *>(part + (size_t)rg * n + quad * 4);
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        float4 o;
+        o.x = activate<EFFDET_ACT_SIGMOID>(t.x); o.y = activate<EFFDET_ACT_SIGMOID>(t.y);
+        o.z = activate<EFFDET_ACT_SIGMOID>(t.z); o.w = activate<EFFDET_ACT_SIGMOID>(t.w);
+        *reinterpret_cast<float4 *>(gate + (size_t)b * C + c0 + quad * 4) = o;
+    }
+}
+
+template <int NC>
+static cudaError_t launch_se_cluster(cudaStream_t st, const float *se_sum, int se_blocks, float inv_hw, const float *w1,
+                                     const float *b1, const float *w2, const float *b2, float *gate, int B, int C,
+                                     int R) {
+    int Cs = (C + NC - 1) / NC;
+    Cs = (Cs + 3) / 4 * 4;
+    const size_t smem = (size_t)(2 * Cs + 2 * ((R + 3) & ~3) + 4 * kSeCT) * sizeof(float);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(B * NC); cfg.blockDim = dim3(kSeCT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = pdl_level() >= EFFDET_PDL_TU_LEVEL;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, se_gate_cluster_kernel<NC>, se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate, C, R, Cs);
 }
 
 // ------------------------------------------------------------------ fusion (stand-alone layer)
@@ -625,6 +775,19 @@ extern "C" int effdet_se_gate(const float *se_sum, int se_blocks, float inv_hw, 
     EFFDET_REQUIRE(C % 4 == 0 && R <= kSeThreads, "C must be a multiple of 4, R <= 512");
     EFFDET_REQUIRE(((reinterpret_cast<uintptr_t>(w2) | reinterpret_cast<uintptr_t>(b2) |
                      reinterpret_cast<uintptr_t>(gate)) & 15) == 0, "w2 / b2 / gate must be 16B aligned");
+    // clusters of 8 / 4 / 2 CTAs per image (fewer as the batch alone fills the GPU); EFFDET_SE_CLUSTER=0 keeps the
+    // one-CTA-per-image kernel
+    static const bool use_cluster = !(getenv("EFFDET_SE_CLUSTER") && atoi(getenv("EFFDET_SE_CLUSTER")) == 0);
+    if (use_cluster && C >= 32 && R <= kSeCT) {
+        cudaStream_t st = as_stream(stream);
+        cudaError_t ce;
+        if (B <= 18) ce = launch_se_cluster<8>(st, se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate, B, C, R);
+        else if (B <= 74) ce = launch_se_cluster<4>(st, se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate, B, C, R);
+        else ce = launch_se_cluster<2>(st, se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate, B, C, R);
+        EFFDET_CUDA(ce);
+        EFFDET_LAUNCHED();
+        return EFFDET_OK;
+    }
     const size_t sm = (size_t)(C + R + 4 * kSeThreads) * sizeof(float);
     EFFDET_REQUIRE(sm <= 48 * 1024, "C + R too large");
     EFFDET_CUDA(launch_pdl(se_gate_kernel, dim3(B), dim3(kSeThreads), sm, as_stream(stream), se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate,

@@ -63,8 +63,10 @@ template <int K, int S, int CP> struct DwCfg {
     static constexpr size_t SMEM = 2 * (size_t)STAGE_BYTES + 2 * 2 * 8 * CB * 4 + 64 + 128;
 };
 
+// 3x3: three CTAs per SM (the 64-channel block needs <= 80 registers for that; at two CTAs = 16 warps per SM the
+// kernel sat at 53 % issue utilisation with DRAM at 30-37 %, profiles/r1f_dwconv_ncu.txt)
 template <int K, int S, int CP, int ACT>
-__global__ void __launch_bounds__(DwCfg<K, S, CP>::NT, 2)
+__global__ void __launch_bounds__(DwCfg<K, S, CP>::NT, (K == 3 ? 3 : 2))
 dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
     using Cfg = DwCfg<K, S, CP>;
     constexpr int CB = Cfg::CB, IW = Cfg::IW, NIN = Cfg::NIN, IR = Cfg::IR, TW = Cfg::TW, TH = Cfg::TH;

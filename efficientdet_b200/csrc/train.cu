@@ -141,7 +141,23 @@ __global__ void colreduce_kernel(const T *__restrict__ x, const T *__restrict__ 
 #pragma unroll
     for (int k = 0; k < CV; ++k) { s1[k] = 0.f; s2[k] = 0.f; mu[k] = 0.f; is[k] = 1.f; }
     if (MODE == RED_BNBWD) { ldf<CV>(mean + c, mu); ldf<CV>(invstd + c, is); }
-    for (size_t r = r0 + py; r < r1; r += PY) {
+    size_t r = r0 + py;
+    if (MODE != RED_BNBWD) {
+        // four independent rows in flight per thread (one 16-byte load each)
+        for (; r + 3 * (size_t)PY < r1; r += 4 * (size_t)PY) {
+            float v[4][CV];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) VecT<T, CV>::load(x + (r + (size_t)u * PY) * C + c, v[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int k = 0; k < CV; ++k) {
+                    s1[k] += v[u][k];
+                    if (MODE == RED_STATS) s2[k] = fmaf(v[u][k], v[u][k], s2[k]);
+                }
+        }
+    }
+    for (; r < r1; r += PY) {
         float v[CV];
         if (MODE == RED_STATS) {
             VecT<T, CV>::load(x + r * C + c, v);
@@ -586,6 +602,12 @@ zero_insert_kernel(const T *__restrict__ dz, T *__restrict__ out, int B, int Ho,
 }
 
 static bool a16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// grid-stride kernels that need ~40 registers keep 6 x 256 threads per SM resident: 6 blocks per SM is one full
+// wave (8 per SM would run as 1.33 waves)
+static unsigned grid_for6(size_t n) {
+    unsigned b = cdiv(n, 256);
+    return b > (unsigned)kNumSMs * 6 ? kNumSMs * 6 : (b ? b : 1);
+}
 static unsigned grid_for(size_t n) {
     unsigned b = cdiv(n, 256);
     return b > (unsigned)kNumSMs * 8 ? kNumSMs * 8 : (b ? b : 1);
@@ -623,9 +645,12 @@ extern "C" int effdet_colreduce_blocks(size_t rows, int C, int dtype) {
     const int CV = dtype == EFFDET_BF16 ? 8 : 4;
     int nvec = C / CV; if (nvec < 1) nvec = 1;
     int PY = 256 / nvec; if (PY < 1) PY = 1;
-    // up to 64 rows per thread (fewer partial rows for the finalize kernels), but at least ~6 blocks per SM
-    size_t rpb = (size_t)PY * 64;
-    while (rpb > (size_t)PY && cdiv(rows, rpb) < (unsigned)kNumSMs * 6) rpb >>= 1;
+    // ONE balanced wave: at most 4 blocks per SM (every reduction kernel fits 4 x 256 threads per SM), each
+    // thread at least 4 rows.  More, smaller blocks ran as 1.3-2.6 waves whose last, partly filled wave cost
+    // 10-30 % of the pass, and made the finalize kernels walk up to ~2300 partial rows.
+    size_t rpb = cdiv(rows, (size_t)kNumSMs * 4);
+    if (rpb < (size_t)PY * 4) rpb = (size_t)PY * 4;
+    rpb = cdiv(rpb, PY) * PY;
     return (int)cdiv(rows, rpb);
 }
 
@@ -708,9 +733,9 @@ extern "C" int effdet_scale_shift_act(const void *z, const float *scale, const f
     if (rows == 0) return EFFDET_OK;
     cudaStream_t st = as_stream(stream);
     DISPATCH_T(dtype,
-        ((void)launch_pdl(scale_shift_act_kernel<float, 4>, dim3(grid_for(rows * C / 4)), dim3(256), 0, st, 
+        ((void)launch_pdl(scale_shift_act_kernel<float, 4>, dim3(grid_for6(rows * C / 4)), dim3(256), 0, st, 
             (const float *)z, scale, shift, (float *)y, rows * C / 4, C, act)),
-        ((void)launch_pdl(scale_shift_act_kernel<__nv_bfloat16, 8>, dim3(grid_for(rows * C / 8)), dim3(256), 0, st, 
+        ((void)launch_pdl(scale_shift_act_kernel<__nv_bfloat16, 8>, dim3(grid_for6(rows * C / 8)), dim3(256), 0, st, 
             (const __nv_bfloat16 *)z, scale, shift, (__nv_bfloat16 *)y, rows * C / 8, C, act)))
     EFFDET_LAUNCHED();
     return EFFDET_OK;
@@ -743,9 +768,9 @@ extern "C" int effdet_bn_relu_backward(const void *dy, const void *y, const void
         EFFDET_LAUNCHED();
     }
     DISPATCH_T(dtype,
-        ((void)launch_pdl(bn_bwd_apply_kernel<float, 4>, dim3(grid_for(rows * C / 4)), dim3(256), 0, st, 
+        ((void)launch_pdl(bn_bwd_apply_kernel<float, 4>, dim3(grid_for6(rows * C / 4)), dim3(256), 0, st, 
             (const float *)dy, (const float *)y, (const float *)z, k123, (float *)dz, rows * C / 4, C)),
-        ((void)launch_pdl(bn_bwd_apply_kernel<__nv_bfloat16, 8>, dim3(grid_for(rows * C / 8)), dim3(256), 0, st, 
+        ((void)launch_pdl(bn_bwd_apply_kernel<__nv_bfloat16, 8>, dim3(grid_for6(rows * C / 8)), dim3(256), 0, st, 
             (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)y, (const __nv_bfloat16 *)z, k123,
             (__nv_bfloat16 *)dz, rows * C / 8, C)))
     EFFDET_LAUNCHED();

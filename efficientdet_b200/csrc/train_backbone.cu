@@ -69,7 +69,54 @@ template <> struct VecB<__nv_bfloat16, 4> {
 template <typename T, int ACT> __device__ __forceinline__ float act_grad_t(float u) {
     return act_grad_io<T>(u, ACT);
 }
-constexpr int kBnU = 4;       // rows in flight per thread
+// Raw (still packed) 4-channel vectors.  The compiler sinks independent loads next to their uses, which leaves
+// ONE load in flight per thread however the loop is unrolled (seen in the SASS of every streaming kernel
+// here: LDG, math, LDG, math ...); all_loaded() is an empty asm statement that takes every loaded register as
+// an in/out operand, so all loads of a batch must have been issued before the first unpack.
+template <typename T> struct Raw4;
+template <> struct Raw4<__nv_bfloat16> {
+    typedef uint2 type;
+    static __device__ __forceinline__ type load(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint2 *>(p); }
+    static __device__ __forceinline__ void unpack(const type &t, float *v) {
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void all_loaded(type (&a)[4], type (&b)[4]) {
+        asm volatile("" : "+r"(a[0].x), "+r"(a[0].y), "+r"(a[1].x), "+r"(a[1].y), "+r"(a[2].x), "+r"(a[2].y),
+                          "+r"(a[3].x), "+r"(a[3].y), "+r"(b[0].x), "+r"(b[0].y), "+r"(b[1].x), "+r"(b[1].y),
+                          "+r"(b[2].x), "+r"(b[2].y), "+r"(b[3].x), "+r"(b[3].y));
+    }
+};
+template <> struct Raw4<float> {
+    typedef float4 type;
+    static __device__ __forceinline__ type load(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+    static __device__ __forceinline__ void unpack(const type &t, float *v) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    static __device__ __forceinline__ void all_loaded(type (&a)[4], type (&b)[4]) {
+        asm volatile("" : "+f"(a[0].x), "+f"(a[0].y), "+f"(a[0].z), "+f"(a[0].w), "+f"(a[1].x), "+f"(a[1].y),
+                          "+f"(a[1].z), "+f"(a[1].w), "+f"(a[2].x), "+f"(a[2].y), "+f"(a[2].z), "+f"(a[2].w),
+                          "+f"(a[3].x), "+f"(a[3].y), "+f"(a[3].z), "+f"(a[3].w));
+        asm volatile("" : "+f"(b[0].x), "+f"(b[0].y), "+f"(b[0].z), "+f"(b[0].w), "+f"(b[1].x), "+f"(b[1].y),
+                          "+f"(b[1].z), "+f"(b[1].w), "+f"(b[2].x), "+f"(b[2].y), "+f"(b[2].z), "+f"(b[2].w),
+                          "+f"(b[3].x), "+f"(b[3].y), "+f"(b[3].z), "+f"(b[3].w));
+    }
+};
+constexpr int kBnU = 4;       // rows per thread and loop iteration
+// ptxas sinks each load of an unrolled batch next to its first use whatever the source order (SASS: LDG, LDG,
+// math, LDG, LDG, math ...), so a thread never has more than two loads in flight and these passes ran at
+// ~3.5 TB/s.  The bytes in flight are therefore supplied by the TMA engine instead: one thread per block asks
+// for the block's next row ranges with cp.async.bulk.prefetch.L2 (no registers, no shared memory), kBnPD loop
+// iterations ahead, and the register loads then hit L2.
+constexpr int kBnPD = 6;
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, size_t bytes) {
+    if (bytes == 0) return;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((uint32_t)bytes) : "memory");
+}
+// rows [ra, rb) of a dense (rows, C) matrix of T, clipped to r1; row size is a multiple of 16 bytes (C % 8 == 0)
+template <typename T>
+__device__ __forceinline__ void prefetch_rows(const T *base, size_t ra, size_t rb, size_t r1, int C) {
+    if (rb > r1) rb = r1;
+    if (ra < rb) bulk_prefetch_l2(base + ra * C, (rb - ra) * (size_t)C * sizeof(T));
+}
 template <typename T, int CV, int ACT>
 __global__ void bn_act_bwd_reduce_kernel(const T *__restrict__ z, const T *__restrict__ dy,
                                          const float *__restrict__ ua, const float *__restrict__ ub,
@@ -85,21 +132,37 @@ __global__ void bn_act_bwd_reduce_kernel(const T *__restrict__ z, const T *__res
 #pragma unroll
     for (int k = 0; k < CV; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
     size_t r = r0 + py;
-    for (; r + (size_t)(kBnU - 1) * PY < r1; r += (size_t)kBnU * PY) {
-        float zz[kBnU][CV], g[kBnU][CV];
+    const size_t step = (size_t)kBnU * PY;
+    if (threadIdx.x == 0) {
+        prefetch_rows(z, r0, r0 + kBnPD * step, r1, C);
+        prefetch_rows(dy, r0, r0 + kBnPD * step, r1, C);
+    }
+    size_t rq = r0 + kBnPD * step;             // first row not yet requested
+    for (; r + (size_t)(kBnU - 1) * PY < r1; r += step, rq += step) {
+        static_assert(CV == 4 && kBnU == 4, "raw-vector batch is written for 4 channels x 4 rows");
+        if (threadIdx.x == 0) {
+            prefetch_rows(z, rq, rq + step, r1, C);
+            prefetch_rows(dy, rq, rq + step, r1, C);
+        }
+        typename Raw4<T>::type zr[kBnU], gr[kBnU];
 #pragma unroll
         for (int u = 0; u < kBnU; ++u) {
-            VecB<T, CV>::load(z + (r + (size_t)u * PY) * C + c, zz[u]);
-            VecB<T, CV>::load(dy + (r + (size_t)u * PY) * C + c, g[u]);
+            zr[u] = Raw4<T>::load(z + (r + (size_t)u * PY) * C + c);
+            gr[u] = Raw4<T>::load(dy + (r + (size_t)u * PY) * C + c);
         }
+        Raw4<T>::all_loaded(zr, gr);
 #pragma unroll
-        for (int u = 0; u < kBnU; ++u)
+        for (int u = 0; u < kBnU; ++u) {
+            float zz[CV], g[CV];
+            Raw4<T>::unpack(zr[u], zz);
+            Raw4<T>::unpack(gr[u], g);
 #pragma unroll
             for (int k = 0; k < CV; ++k) {
-                const float gm = g[u][k] * act_grad_t<T, ACT>(fmaf(zz[u][k], a[k], b[k]));
+                const float gm = g[k] * act_grad_t<T, ACT>(fmaf(zz[k], a[k], b[k]));
                 s1[k] += gm;
-                s2[k] = fmaf(gm, zz[u][k] - mu[k], s2[k]);
+                s2[k] = fmaf(gm, zz[k] - mu[k], s2[k]);
             }
+        }
     }
     for (; r < r1; r += PY) {
         float zz[CV], g[CV];
@@ -180,19 +243,34 @@ __global__ void bn_act_bwd_apply_kernel(const T *__restrict__ dy, const T *__res
     const size_t r0 = (size_t)blockIdx.x * rows_per_block;
     const size_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
     size_t r = r0 + py;
-    for (; r + (size_t)(kBnU - 1) * PY < r1; r += (size_t)kBnU * PY) {
-        float g[kBnU][CV], zz[kBnU][CV];
-#pragma unroll
-        for (int u = 0; u < kBnU; ++u) {
-            VecB<T, CV>::load(dy + (r + (size_t)u * PY) * C + c, g[u]);
-            VecB<T, CV>::load(z + (r + (size_t)u * PY) * C + c, zz[u]);
+    const size_t step = (size_t)kBnU * PY;
+    if (threadIdx.x == 0) {
+        prefetch_rows(z, r0, r0 + kBnPD * step, r1, C);
+        prefetch_rows(dy, r0, r0 + kBnPD * step, r1, C);
+    }
+    size_t rq = r0 + kBnPD * step;             // first row not yet requested
+    for (; r + (size_t)(kBnU - 1) * PY < r1; r += step, rq += step) {
+        static_assert(CV == 4 && kBnU == 4, "raw-vector batch is written for 4 channels x 4 rows");
+        if (threadIdx.x == 0) {
+            prefetch_rows(z, rq, rq + step, r1, C);
+            prefetch_rows(dy, rq, rq + step, r1, C);
         }
+        typename Raw4<T>::type zr[kBnU], gr[kBnU];
 #pragma unroll
         for (int u = 0; u < kBnU; ++u) {
+            gr[u] = Raw4<T>::load(dy + (r + (size_t)u * PY) * C + c);
+            zr[u] = Raw4<T>::load(z + (r + (size_t)u * PY) * C + c);
+        }
+        Raw4<T>::all_loaded(zr, gr);
+#pragma unroll
+        for (int u = 0; u < kBnU; ++u) {
+            float g[CV], zz[CV];
+            Raw4<T>::unpack(gr[u], g);
+            Raw4<T>::unpack(zr[u], zz);
 #pragma unroll
             for (int k = 0; k < CV; ++k)
-                g[u][k] = k1[k] * (g[u][k] * act_grad_t<T, ACT>(fmaf(zz[u][k], a[k], b[k]))) + k2[k] * zz[u][k] + k3[k];
-            VecB<T, CV>::store(dz + (r + (size_t)u * PY) * C + c, g[u]);
+                g[k] = k1[k] * (g[k] * act_grad_t<T, ACT>(fmaf(zz[k], a[k], b[k]))) + k2[k] * zz[k] + k3[k];
+            VecB<T, CV>::store(dz + (r + (size_t)u * PY) * C + c, g);
         }
     }
     for (; r < r1; r += PY) {
@@ -695,9 +773,10 @@ extern "C" int effdet_bn_act_backward(const void *dy, const void *z, size_t rows
         const int nva = C / 4;
         EFFDET_REQUIRE(nva <= 1024, "C too large");
         int PYa = 256 / nva; if (PYa < 1) PYa = 1;
-        // ~8 blocks per SM, each thread at least kBnU rows
-        size_t rpb = (size_t)PYa * kBnU;
-        while (cdiv(rows, rpb) > (unsigned)kNumSMs * 8) rpb *= 2;
+        // one balanced wave (<= 4 blocks per SM: 48 registers x 256 threads), each thread at least kBnU rows
+        size_t rpb = cdiv(rows, (size_t)kNumSMs * 4);
+        if (rpb < (size_t)PYa * kBnU) rpb = (size_t)PYa * kBnU;
+        rpb = cdiv(rpb, PYa) * PYa;
         const unsigned nb = cdiv(rows, rpb);
 #define BN_APP(A)                                                                                              \
         DISPATCH_TB(dtype,                                                                                     \
