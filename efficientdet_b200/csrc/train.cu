@@ -127,10 +127,11 @@ resample_fuse_kernel(const T *__restrict__ in0, int mode0, const T *__restrict__
 // x is (rows, C).  block = nvec x PY threads; blocks split the rows; partial[(blk)*2*C + s*C + c]
 enum { RED_STATS = 0, RED_BNBWD = 1, RED_SUM = 2 };
 template <typename T, int CV, int MODE>
-__global__ void colreduce_kernel(const T *__restrict__ x, const T *__restrict__ y,
+__global__ void __launch_bounds__(1024, 1)      // <= 64 registers: four 256-thread blocks per SM (blocks grow to C/CV threads)
+colreduce_kernel(const T *__restrict__ x, const T *__restrict__ y,
                                  const T *__restrict__ dy, const float *__restrict__ mean,
                                  const float *__restrict__ invstd, size_t rows, int C,
-                                 int rows_per_block, float *__restrict__ partial) {
+                                 int rows_per_block, float *__restrict__ partial, uint32_t zero) {
     EFFDET_PDL_SYNC();
     extern __shared__ float sred[];      // PY * 2 * C
     const int nvec = C / CV, PY = blockDim.x / nvec;
@@ -143,18 +144,47 @@ __global__ void colreduce_kernel(const T *__restrict__ x, const T *__restrict__ 
     if (MODE == RED_BNBWD) { ldf<CV>(mean + c, mu); ldf<CV>(invstd + c, is); }
     size_t r = r0 + py;
     if (MODE != RED_BNBWD) {
-        // four independent rows in flight per thread (one 16-byte load each)
+        // four rows (one 16-byte load each) in flight per thread
         for (; r + 3 * (size_t)PY < r1; r += 4 * (size_t)PY) {
-            float v[4][CV];
+            uint4 raw[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) VecT<T, CV>::load(x + (r + (size_t)u * PY) * C + c, v[u]);
+            for (int u = 0; u < 4; ++u) raw[u] = ld16(x + (r + (size_t)u * PY) * C + c);
+            tie_loads(raw, zero);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 4; ++u) {
+                float v[CV];
+                Unpack16<T, CV>::run(raw[u], v);
 #pragma unroll
                 for (int k = 0; k < CV; ++k) {
-                    s1[k] += v[u][k];
-                    if (MODE == RED_STATS) s2[k] = fmaf(v[u][k], v[u][k], s2[k]);
+                    s1[k] += v[k];
+                    if (MODE == RED_STATS) s2[k] = fmaf(v[k], v[k], s2[k]);
                 }
+            }
+        }
+    } else {
+        // two rows of the three tensors (six 16-byte loads) in flight per thread
+        for (; r + (size_t)PY < r1; r += 2 * (size_t)PY) {
+            uint4 raw[6];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                raw[3 * u + 0] = ld16(x + (r + (size_t)u * PY) * C + c);
+                raw[3 * u + 1] = ld16(dy + (r + (size_t)u * PY) * C + c);
+                raw[3 * u + 2] = ld16(y + (r + (size_t)u * PY) * C + c);
+            }
+            tie_loads(raw, zero);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                float v[CV], g[CV], yy[CV];
+                Unpack16<T, CV>::run(raw[3 * u + 0], v);
+                Unpack16<T, CV>::run(raw[3 * u + 1], g);
+                Unpack16<T, CV>::run(raw[3 * u + 2], yy);
+#pragma unroll
+                for (int k = 0; k < CV; ++k) {
+                    const float gm = yy[k] > 0.f ? g[k] : 0.f;
+                    s1[k] += gm;
+                    s2[k] = fmaf(gm, (v[k] - mu[k]) * is[k], s2[k]);
+                }
+            }
         }
     }
     for (; r < r1; r += PY) {
@@ -316,10 +346,30 @@ template <typename T, int CV>
 __global__ void __launch_bounds__(256)
 scale_shift_act_kernel(const T *__restrict__ z, const float *__restrict__ scale,
                        const float *__restrict__ shift, T *__restrict__ y, size_t nvec_total,
-                       int C, int act) {
+                       int C, int act, uint32_t zero) {
     EFFDET_PDL_SYNC();
     const unsigned nvec = C / CV;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
+    const size_t stride = (size_t)gridDim.x * 256;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + 3 * stride < nvec_total; i += 4 * stride) {      // four vectors in flight
+        uint4 raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) raw[u] = ld16(z + (i + u * stride) * CV);
+        tie_loads(raw, zero);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const size_t iv = i + u * stride;
+            const int c = (int)((unsigned)iv % nvec) * CV;
+            float v[CV], sc[CV], sh[CV];
+            Unpack16<T, CV>::run(raw[u], v);
+            ldf<CV>(scale + c, sc);
+            ldf<CV>(shift + c, sh);
+#pragma unroll
+            for (int k = 0; k < CV; ++k) v[k] = activate_io<T>(fmaf(v[k], sc[k], sh[k]), act);
+            VecT<T, CV>::store(y + iv * CV, v);
+        }
+    }
+    for (; i < nvec_total; i += stride) {
         const int c = (int)((unsigned)i % nvec) * CV;        // nvec_total < 2^32 (checked by the launcher)
         float v[CV], sc[CV], sh[CV];
         VecT<T, CV>::load(z + i * CV, v);
@@ -333,12 +383,39 @@ scale_shift_act_kernel(const T *__restrict__ z, const float *__restrict__ scale,
 
 // dz = k1*(dy * [y>0]) + k2*z + k3     (frozen BN: k2 = k3 = 0, k1 = scale)
 template <typename T, int CV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bn_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ y, const T *__restrict__ z,
-                    const float *__restrict__ k123, T *__restrict__ dz, size_t nvec_total, int C) {
+                    const float *__restrict__ k123, T *__restrict__ dz, size_t nvec_total, int C, uint32_t zero) {
     EFFDET_PDL_SYNC();
     const unsigned nvec = C / CV;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
+    const size_t stride = (size_t)gridDim.x * 256;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + stride < nvec_total; i += 2 * stride) {      // two vectors of the three tensors in flight
+        uint4 raw[6];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            raw[3 * u + 0] = ld16(dy + (i + u * stride) * CV);
+            raw[3 * u + 1] = ld16(y + (i + u * stride) * CV);
+            raw[3 * u + 2] = ld16(z + (i + u * stride) * CV);
+        }
+        tie_loads(raw, zero);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const size_t iv = i + u * stride;
+            const int c = (int)((unsigned)iv % nvec) * CV;
+            float g[CV], yy[CV], zz[CV], k1[CV], k2[CV], k3[CV];
+            Unpack16<T, CV>::run(raw[3 * u + 0], g);
+            Unpack16<T, CV>::run(raw[3 * u + 1], yy);
+            Unpack16<T, CV>::run(raw[3 * u + 2], zz);
+            ldf<CV>(k123 + c, k1);
+            ldf<CV>(k123 + C + c, k2);
+            ldf<CV>(k123 + 2 * C + c, k3);
+#pragma unroll
+            for (int k = 0; k < CV; ++k) g[k] = k1[k] * (yy[k] > 0.f ? g[k] : 0.f) + k2[k] * zz[k] + k3[k];
+            VecT<T, CV>::store(dz + iv * CV, g);
+        }
+    }
+    for (; i < nvec_total; i += stride) {
         const int c = (int)((unsigned)i % nvec) * CV;
         float g[CV], yy[CV], zz[CV], k1[CV], k2[CV], k3[CV];
         VecT<T, CV>::load(dy + i * CV, g);
@@ -608,6 +685,10 @@ static unsigned grid_for6(size_t n) {
     unsigned b = cdiv(n, 256);
     return b > (unsigned)kNumSMs * 6 ? kNumSMs * 6 : (b ? b : 1);
 }
+static unsigned grid_for4(size_t n) {            // batched-load kernels (<= 64 registers): four blocks per SM, one wave
+    unsigned b = cdiv(n, 256 * 2);
+    return b > (unsigned)kNumSMs * 4 ? kNumSMs * 4 : (b ? b : 1);
+}
 static unsigned grid_for(size_t n) {
     unsigned b = cdiv(n, 256);
     return b > (unsigned)kNumSMs * 8 ? kNumSMs * 8 : (b ? b : 1);
@@ -670,7 +751,7 @@ static int launch_colreduce(const void *x, const void *y, const void *dy, const 
         if (e != cudaSuccess) return fail(EFFDET_E_CUDA, "colreduce: smem attribute: %s", cudaGetErrorString(e));
     }
     EFFDET_CUDA(launch_pdl(colreduce_kernel<T, CV, MODE>, dim3(nblk), dim3(nvec * PY), sm, st, 
-        (const T *)x, (const T *)y, (const T *)dy, mean, invstd, rows, C, rpb, partial));
+        (const T *)x, (const T *)y, (const T *)dy, mean, invstd, rows, C, rpb, partial, 0u));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -733,10 +814,10 @@ extern "C" int effdet_scale_shift_act(const void *z, const float *scale, const f
     if (rows == 0) return EFFDET_OK;
     cudaStream_t st = as_stream(stream);
     DISPATCH_T(dtype,
-        ((void)launch_pdl(scale_shift_act_kernel<float, 4>, dim3(grid_for6(rows * C / 4)), dim3(256), 0, st, 
-            (const float *)z, scale, shift, (float *)y, rows * C / 4, C, act)),
-        ((void)launch_pdl(scale_shift_act_kernel<__nv_bfloat16, 8>, dim3(grid_for6(rows * C / 8)), dim3(256), 0, st, 
-            (const __nv_bfloat16 *)z, scale, shift, (__nv_bfloat16 *)y, rows * C / 8, C, act)))
+        ((void)launch_pdl(scale_shift_act_kernel<float, 4>, dim3(grid_for4(rows * C / 4)), dim3(256), 0, st, 
+            (const float *)z, scale, shift, (float *)y, rows * C / 4, C, act, 0u)),
+        ((void)launch_pdl(scale_shift_act_kernel<__nv_bfloat16, 8>, dim3(grid_for4(rows * C / 8)), dim3(256), 0, st, 
+            (const __nv_bfloat16 *)z, scale, shift, (__nv_bfloat16 *)y, rows * C / 8, C, act, 0u)))
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -768,11 +849,11 @@ extern "C" int effdet_bn_relu_backward(const void *dy, const void *y, const void
         EFFDET_LAUNCHED();
     }
     DISPATCH_T(dtype,
-        ((void)launch_pdl(bn_bwd_apply_kernel<float, 4>, dim3(grid_for6(rows * C / 4)), dim3(256), 0, st, 
-            (const float *)dy, (const float *)y, (const float *)z, k123, (float *)dz, rows * C / 4, C)),
-        ((void)launch_pdl(bn_bwd_apply_kernel<__nv_bfloat16, 8>, dim3(grid_for6(rows * C / 8)), dim3(256), 0, st, 
+        ((void)launch_pdl(bn_bwd_apply_kernel<float, 4>, dim3(grid_for4(rows * C / 4)), dim3(256), 0, st, 
+            (const float *)dy, (const float *)y, (const float *)z, k123, (float *)dz, rows * C / 4, C, 0u)),
+        ((void)launch_pdl(bn_bwd_apply_kernel<__nv_bfloat16, 8>, dim3(grid_for4(rows * C / 8)), dim3(256), 0, st, 
             (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)y, (const __nv_bfloat16 *)z, k123,
-            (__nv_bfloat16 *)dz, rows * C / 8, C)))
+            (__nv_bfloat16 *)dz, rows * C / 8, C, 0u)))
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }

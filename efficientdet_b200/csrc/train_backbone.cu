@@ -69,10 +69,10 @@ template <> struct VecB<__nv_bfloat16, 4> {
 template <typename T, int ACT> __device__ __forceinline__ float act_grad_t(float u) {
     return act_grad_io<T>(u, ACT);
 }
-// Raw (still packed) 4-channel vectors.  The compiler sinks independent loads next to their uses, which leaves
-// ONE load in flight per thread however the loop is unrolled (seen in the SASS of every streaming kernel
-// here: LDG, math, LDG, math ...); all_loaded() is an empty asm statement that takes every loaded register as
-// an in/out operand, so all loads of a batch must have been issued before the first unpack.
+// Raw (still packed) 4-channel vectors.  ptxas sinks independent loads next to their uses, which leaves two
+// loads in flight per thread however the loop is unrolled (seen in the SASS of every streaming kernel here:
+// LDG, LDG, math, LDG, LDG, math ...; ncu: long-scoreboard stalls 11.6 per issue, DRAM at 50 %, 16 KB in
+// flight per SM); all_loaded() ties every value of a batch to all of its loads.
 template <typename T> struct Raw4;
 template <> struct Raw4<__nv_bfloat16> {
     typedef uint2 type;
@@ -81,24 +81,23 @@ template <> struct Raw4<__nv_bfloat16> {
         v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
         v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
     }
-    static __device__ __forceinline__ void all_loaded(type (&a)[4], type (&b)[4]) {
-        asm volatile("" : "+r"(a[0].x), "+r"(a[0].y), "+r"(a[1].x), "+r"(a[1].y), "+r"(a[2].x), "+r"(a[2].y),
-                          "+r"(a[3].x), "+r"(a[3].y), "+r"(b[0].x), "+r"(b[0].y), "+r"(b[1].x), "+r"(b[1].y),
-                          "+r"(b[2].x), "+r"(b[2].y), "+r"(b[3].x), "+r"(b[3].y));
+    // `zero` is a kernel argument that is always 0: every value is OR-ed with (xor of ALL loaded words) & zero,
+    // a data dependence the assembler cannot remove, so the eight loads are in flight together (an empty asm
+    // with in/out operands orders the PTX but ptxas re-sinks the loads)
+    static __device__ __forceinline__ void all_loaded(type (&a)[4], type (&b)[4], uint32_t zero) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t ^= a[i].x ^ a[i].y ^ b[i].x ^ b[i].y;
+        t &= zero;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i].x |= t; a[i].y |= t; b[i].x |= t; b[i].y |= t; }
     }
 };
 template <> struct Raw4<float> {
     typedef float4 type;
     static __device__ __forceinline__ type load(const float *p) { return *reinterpret_cast<const float4 *>(p); }
     static __device__ __forceinline__ void unpack(const type &t, float *v) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-    static __device__ __forceinline__ void all_loaded(type (&a)[4], type (&b)[4]) {
-        asm volatile("" : "+f"(a[0].x), "+f"(a[0].y), "+f"(a[0].z), "+f"(a[0].w), "+f"(a[1].x), "+f"(a[1].y),
-                          "+f"(a[1].z), "+f"(a[1].w), "+f"(a[2].x), "+f"(a[2].y), "+f"(a[2].z), "+f"(a[2].w),
-                          "+f"(a[3].x), "+f"(a[3].y), "+f"(a[3].z), "+f"(a[3].w));
-        asm volatile("" : "+f"(b[0].x), "+f"(b[0].y), "+f"(b[0].z), "+f"(b[0].w), "+f"(b[1].x), "+f"(b[1].y),
-                          "+f"(b[1].z), "+f"(b[1].w), "+f"(b[2].x), "+f"(b[2].y), "+f"(b[2].z), "+f"(b[2].w),
-                          "+f"(b[3].x), "+f"(b[3].y), "+f"(b[3].z), "+f"(b[3].w));
-    }
+    static __device__ __forceinline__ void all_loaded(type (&)[4], type (&)[4], uint32_t) {}   // accuracy mode: as is
 };
 constexpr int kBnU = 4;       // rows per thread and loop iteration
 // ptxas sinks each load of an unrolled batch next to its first use whatever the source order (SASS: LDG, LDG,
@@ -106,7 +105,7 @@ constexpr int kBnU = 4;       // rows per thread and loop iteration
 // ~3.5 TB/s.  The bytes in flight are therefore supplied by the TMA engine instead: one thread per block asks
 // for the block's next row ranges with cp.async.bulk.prefetch.L2 (no registers, no shared memory), kBnPD loop
 // iterations ahead, and the register loads then hit L2.
-constexpr int kBnPD = 6;
+constexpr int kBnPD = 3;
 __device__ __forceinline__ void bulk_prefetch_l2(const void *p, size_t bytes) {
     if (bytes == 0) return;
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((uint32_t)bytes) : "memory");
@@ -118,10 +117,11 @@ __device__ __forceinline__ void prefetch_rows(const T *base, size_t ra, size_t r
     if (ra < rb) bulk_prefetch_l2(base + ra * C, (rb - ra) * (size_t)C * sizeof(T));
 }
 template <typename T, int CV, int ACT>
-__global__ void bn_act_bwd_reduce_kernel(const T *__restrict__ z, const T *__restrict__ dy,
+__global__ void __launch_bounds__(1024, 1)      // <= 64 registers
+bn_act_bwd_reduce_kernel(const T *__restrict__ z, const T *__restrict__ dy,
                                          const float *__restrict__ ua, const float *__restrict__ ub,
                                          const float *__restrict__ mean, size_t rows, int C,
-                                         int rows_per_block, float *__restrict__ partial) {
+                                         int rows_per_block, float *__restrict__ partial, uint32_t zero) {
     extern __shared__ float sred[];
     const int nvec = C / CV, PY = blockDim.x / nvec;
     const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec, c = cv * CV;
@@ -150,7 +150,7 @@ __global__ void bn_act_bwd_reduce_kernel(const T *__restrict__ z, const T *__res
             zr[u] = Raw4<T>::load(z + (r + (size_t)u * PY) * C + c);
             gr[u] = Raw4<T>::load(dy + (r + (size_t)u * PY) * C + c);
         }
-        Raw4<T>::all_loaded(zr, gr);
+        Raw4<T>::all_loaded(zr, gr, zero);
 #pragma unroll
         for (int u = 0; u < kBnU; ++u) {
             float zz[CV], g[CV];
@@ -231,9 +231,10 @@ __global__ void bn_act_bwd_finalize_kernel(const float *__restrict__ partial, in
 // ITS channels in registers and walks rows (the flat-index version re-read them from L1 for every
 // 16-byte vector: 10 extra load instructions per 8 elements, LSU-bound at ~1.5 TB/s).
 template <typename T, int CV, int ACT>
-__global__ void bn_act_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ z, const float *__restrict__ ua,
+__global__ void __launch_bounds__(1024, 1)      // <= 64 registers: four 256-thread blocks per SM (blocks grow to C/4 threads)
+bn_act_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ z, const float *__restrict__ ua,
                         const float *__restrict__ ub, const float *__restrict__ k123, T *__restrict__ dz,
-                        size_t rows, int C, int rows_per_block) {
+                        size_t rows, int C, int rows_per_block, uint32_t zero) {
     const int nvec = C / CV, PY = blockDim.x / nvec;
     const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec, c = cv * CV;
     if (py >= PY) return;
@@ -261,7 +262,7 @@ __global__ void bn_act_bwd_apply_kernel(const T *__restrict__ dy, const T *__res
             gr[u] = Raw4<T>::load(dy + (r + (size_t)u * PY) * C + c);
             zr[u] = Raw4<T>::load(z + (r + (size_t)u * PY) * C + c);
         }
-        Raw4<T>::all_loaded(zr, gr);
+        Raw4<T>::all_loaded(zr, gr, zero);
 #pragma unroll
         for (int u = 0; u < kBnU; ++u) {
             float g[CV], zz[CV];
@@ -306,7 +307,7 @@ se_apply_kernel(const T *__restrict__ y, const float *__restrict__ gate, T *__re
 // y == NULL: plain spatial sum of dyg (the squeeze of the forward pass)
 template <typename T, int CV>
 __global__ void se_bwd_reduce_kernel(const T *__restrict__ dyg, const T *__restrict__ y, int HW, int C,
-                                     int rows_per_block, float *__restrict__ partial) {
+                                     int rows_per_block, float *__restrict__ partial, uint32_t zero) {
     extern __shared__ float sred[];
     const int nvec = C / CV, PY = blockDim.x / nvec;
     const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec, c = cv * CV;
@@ -316,7 +317,41 @@ __global__ void se_bwd_reduce_kernel(const T *__restrict__ dyg, const T *__restr
     float s[CV];
 #pragma unroll
     for (int k = 0; k < CV; ++k) s[k] = 0.f;
-    for (int r = r0 + py; r < r1; r += PY) {
+    int r = r0 + py;
+    if (pb) {
+        for (; r + 3 * PY < r1; r += 4 * PY) {          // four rows of both tensors in flight
+            uint4 raw[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                raw[2 * u] = ld16(pa + (size_t)(r + u * PY) * C + c);
+                raw[2 * u + 1] = ld16(pb + (size_t)(r + u * PY) * C + c);
+            }
+            tie_loads(raw, zero);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float a[CV], v[CV];
+                Unpack16<T, CV>::run(raw[2 * u], a);
+                Unpack16<T, CV>::run(raw[2 * u + 1], v);
+#pragma unroll
+                for (int k = 0; k < CV; ++k) s[k] = fmaf(a[k], v[k], s[k]);
+            }
+        }
+    } else {
+        for (; r + 3 * PY < r1; r += 4 * PY) {
+            uint4 raw[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) raw[u] = ld16(pa + (size_t)(r + u * PY) * C + c);
+            tie_loads(raw, zero);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float a[CV];
+                Unpack16<T, CV>::run(raw[u], a);
+#pragma unroll
+                for (int k = 0; k < CV; ++k) s[k] += a[k];
+            }
+        }
+    }
+    for (; r < r1; r += PY) {
         float a[CV], v[CV];
         VecB<T, CV>::load(pa + (size_t)r * C + c, a);
         if (pb) {
@@ -485,9 +520,30 @@ se_bwd_phase4_kernel(const float *__restrict__ mean, const float *__restrict__ r
 template <typename T, int CV>
 __global__ void __launch_bounds__(256)
 se_bwd_finish_kernel(const T *__restrict__ dyg, const float *__restrict__ gate, const float *__restrict__ dmean,
-                     float inv_hw, T *__restrict__ dy, int HW, int C, size_t nvec_total) {
+                     float inv_hw, T *__restrict__ dy, int HW, int C, size_t nvec_total, uint32_t zero) {
     const int nvec = C / CV;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec_total; i += (size_t)gridDim.x * 256) {
+    const size_t stride = (size_t)gridDim.x * 256;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + 3 * stride < nvec_total; i += 4 * stride) {      // four vectors in flight
+        uint4 raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) raw[u] = ld16(dyg + (i + u * stride) * CV);
+        tie_loads(raw, zero);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const size_t iv = i + u * stride;
+            const int c = (int)(iv % nvec) * CV;
+            const size_t b = iv / ((size_t)nvec * HW);
+            float v[CV], g[CV], m[CV];
+            Unpack16<T, CV>::run(raw[u], v);
+            ldv<CV>(gate + b * C + c, g);
+            ldv<CV>(dmean + b * C + c, m);
+#pragma unroll
+            for (int k = 0; k < CV; ++k) v[k] = fmaf(v[k], g[k], m[k] * inv_hw);
+            VecB<T, CV>::store(dy + iv * CV, v);
+        }
+    }
+    for (; i < nvec_total; i += stride) {
         const int c = (int)(i % nvec) * CV;
         const size_t b = i / ((size_t)nvec * HW);
         float v[CV], g[CV], m[CV];
@@ -717,6 +773,11 @@ stem_wgrad_tiled_kernel(const float *__restrict__ img, const __nv_bfloat16 *__re
     }
 }
 
+// kernels that batch four 16-byte loads per thread need ~56 registers: four 256-thread blocks per SM = one wave
+static unsigned grid_for_n4(size_t n) {
+    unsigned b = cdiv(n, 256 * 4);
+    return b > (unsigned)kNumSMs * 4 ? kNumSMs * 4 : (b ? b : 1);
+}
 static unsigned grid_for_n(size_t n) {
     unsigned b = cdiv(n, 256);
     return b > (unsigned)kNumSMs * 8 ? kNumSMs * 8 : (b ? b : 1);
@@ -755,9 +816,9 @@ extern "C" int effdet_bn_act_backward(const void *dy, const void *z, size_t rows
 #define BN_RED(A)                                                                                              \
         DISPATCH_TB(dtype,                                                                                     \
             (bn_act_bwd_reduce_kernel<float, 4, A><<<nblk, nvec * PY, sm, st>>>(                                \
-                (const float *)z, (const float *)dy, ua, ub, save_mean, rows, C, rpb, partial)),                \
+                (const float *)z, (const float *)dy, ua, ub, save_mean, rows, C, rpb, partial, 0u)),            \
             (bn_act_bwd_reduce_kernel<__nv_bfloat16, 4, A><<<nblk, nvec * PY, sm, st>>>(                        \
-                (const __nv_bfloat16 *)z, (const __nv_bfloat16 *)dy, ua, ub, save_mean, rows, C, rpb, partial)))
+                (const __nv_bfloat16 *)z, (const __nv_bfloat16 *)dy, ua, ub, save_mean, rows, C, rpb, partial, 0u)))
         if (act == EFFDET_ACT_SWISH) { BN_RED(EFFDET_ACT_SWISH) }
         else if (act == EFFDET_ACT_RELU) { BN_RED(EFFDET_ACT_RELU) }
         else if (act == EFFDET_ACT_NONE) { BN_RED(EFFDET_ACT_NONE) }
@@ -781,10 +842,10 @@ extern "C" int effdet_bn_act_backward(const void *dy, const void *z, size_t rows
 #define BN_APP(A)                                                                                              \
         DISPATCH_TB(dtype,                                                                                     \
             (bn_act_bwd_apply_kernel<float, 4, A><<<nb, nva * PYa, 0, st>>>(                                    \
-                (const float *)dy, (const float *)z, ua, ub, k123, (float *)dz, rows, C, (int)rpb)),            \
+                (const float *)dy, (const float *)z, ua, ub, k123, (float *)dz, rows, C, (int)rpb, 0u)),        \
             (bn_act_bwd_apply_kernel<__nv_bfloat16, 4, A><<<nb, nva * PYa, 0, st>>>(                            \
                 (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)z, ua, ub, k123, (__nv_bfloat16 *)dz, rows, C, \
-                (int)rpb)))
+                (int)rpb, 0u)))
         if (act == EFFDET_ACT_SWISH) { BN_APP(EFFDET_ACT_SWISH) }
         else if (act == EFFDET_ACT_RELU) { BN_APP(EFFDET_ACT_RELU) }
         else if (act == EFFDET_ACT_NONE) { BN_APP(EFFDET_ACT_NONE) }
@@ -893,9 +954,9 @@ extern "C" int effdet_spatial_sum(const void *y, float *partial, int nblk, int B
     const size_t sm = (size_t)PY * C * sizeof(float);
     dim3 grid(nblk, B);
     DISPATCH_TB(dtype,
-        (se_bwd_reduce_kernel<float, 4><<<grid, nvec * PY, sm, st>>>((const float *)y, nullptr, HW, C, rpb, partial)),
+        (se_bwd_reduce_kernel<float, 4><<<grid, nvec * PY, sm, st>>>((const float *)y, nullptr, HW, C, rpb, partial, 0u)),
         (se_bwd_reduce_kernel<__nv_bfloat16, 8><<<grid, nvec * PY, sm, st>>>((const __nv_bfloat16 *)y, nullptr, HW, C,
-                                                                              rpb, partial)))
+                                                                              rpb, partial, 0u)))
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
@@ -931,9 +992,9 @@ extern "C" int effdet_se_backward(const void *dyg, const void *y, const float *g
     const size_t sm = (size_t)PY * C * sizeof(float);
     dim3 grid(dg_blocks, B);
     DISPATCH_TB(dtype,
-        (se_bwd_reduce_kernel<float, 4><<<grid, nvec * PY, sm, st>>>((const float *)dyg, (const float *)y, HW, C, rpb, dg_partial)),
+        (se_bwd_reduce_kernel<float, 4><<<grid, nvec * PY, sm, st>>>((const float *)dyg, (const float *)y, HW, C, rpb, dg_partial, 0u)),
         (se_bwd_reduce_kernel<__nv_bfloat16, 8><<<grid, nvec * PY, sm, st>>>(
-            (const __nv_bfloat16 *)dyg, (const __nv_bfloat16 *)y, HW, C, rpb, dg_partial)))
+            (const __nv_bfloat16 *)dyg, (const __nv_bfloat16 *)y, HW, C, rpb, dg_partial, 0u)))
     EFFDET_LAUNCHED();
     {
         EFFDET_REQUIRE(R <= 512, "R too large");
@@ -957,10 +1018,10 @@ extern "C" int effdet_se_backward(const void *dyg, const void *y, const float *g
     }
     const size_t n = (size_t)B * HW * C;
     DISPATCH_TB(dtype,
-        (se_bwd_finish_kernel<float, 4><<<grid_for_n(n / 4), 256, 0, st>>>(
-            (const float *)dyg, gate, dmean, 1.f / (float)HW, (float *)dy, HW, C, n / 4)),
-        (se_bwd_finish_kernel<__nv_bfloat16, 8><<<grid_for_n(n / 8), 256, 0, st>>>(
-            (const __nv_bfloat16 *)dyg, gate, dmean, 1.f / (float)HW, (__nv_bfloat16 *)dy, HW, C, n / 8)))
+        (se_bwd_finish_kernel<float, 4><<<grid_for_n4(n / 4), 256, 0, st>>>(
+            (const float *)dyg, gate, dmean, 1.f / (float)HW, (float *)dy, HW, C, n / 4, 0u)),
+        (se_bwd_finish_kernel<__nv_bfloat16, 8><<<grid_for_n4(n / 8), 256, 0, st>>>(
+            (const __nv_bfloat16 *)dyg, gate, dmean, 1.f / (float)HW, (__nv_bfloat16 *)dy, HW, C, n / 8, 0u)))
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
