@@ -395,7 +395,10 @@ __global__ void __launch_bounds__(kSeCT)
 se_gate_cluster_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_hw,
                        const float *__restrict__ w1, const float *__restrict__ b1,
                        const float *__restrict__ w2, const float *__restrict__ b2,
-                       float *__restrict__ gate, int C, int R, int Cs) {
+                       float *__restrict__ gate, int C, int R, int Cs, float *__restrict__ mean_o,
+                       float *__restrict__ s1_o, float *__restrict__ rr_o) {
+    // mean_o / s1_o / rr_o (optional): squeeze mean (B,C), FC1 pre-activation and its swish (B,R) -- the
+    // forward quantities the SE backward needs; gate == nullptr skips FC2 (backward recompute mode)
     EFFDET_PDL_SYNC();
     extern __shared__ __align__(16) float smc[];     // mean[Cs] | rpart[Rp] | r[Rp] | part[4 * kSeCT + Cs]
     const int Rp = (R + 3) & ~3;                     // keeps `part` 16-byte aligned
@@ -426,6 +429,7 @@ se_gate_cluster_kernel(const float *__restrict__ se_sum, int se_blocks, float in
             float t = 0.f;
             for (int s2 = 0; s2 < KS; ++s2) t += part[s2 * n + c];
             mean[c] = t * inv_hw;
+            if (mean_o) mean_o[(size_t)b * C + c0 + c] = t * inv_hw;
         }
     }
     __syncthreads();
@@ -464,11 +468,13 @@ se_gate_cluster_kernel(const float *__restrict__ se_sum, int se_blocks, float in
             asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra));
             t += v;
         }
-        r[j] = activate<EFFDET_ACT_SWISH>(t + b1[j]);
+        const float pre = t + b1[j];
+        r[j] = activate<EFFDET_ACT_SWISH>(pre);
+        if (s1_o && rank == 0) { s1_o[(size_t)b * R + j] = pre; rr_o[(size_t)b * R + j] = r[j]; }
     }
     // nobody may leave (or reuse rpart) while a peer still reads it; also orders r[] for this CTA
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    if (n <= 0) return;
+    if (n <= 0 || !gate) return;
     // ---- FC2 + sigmoid on the slice: thread = (channel quad, r-group); quads along lanes (16-byte loads)
     const int q = n / 4;
     int RG = kSeCT / q; if (RG < 1) RG = 1; if (RG > R) RG = R;
@@ -515,7 +521,7 @@ se_gate_cluster_kernel(const float *__restrict__ se_sum, int se_blocks, float in
 template <int NC>
 static cudaError_t launch_se_cluster(cudaStream_t st, const float *se_sum, int se_blocks, float inv_hw, const float *w1,
                                      const float *b1, const float *w2, const float *b2, float *gate, int B, int C,
-                                     int R) {
+                                     int R, float *mean_o = nullptr, float *s1_o = nullptr, float *rr_o = nullptr) {
     int Cs = (C + NC - 1) / NC;
     Cs = (Cs + 3) / 4 * 4;
     const size_t smem = (size_t)(2 * Cs + 2 * ((R + 3) & ~3) + 4 * kSeCT) * sizeof(float);
@@ -529,7 +535,20 @@ static cudaError_t launch_se_cluster(cudaStream_t st, const float *se_sum, int s
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     static const bool pdl = pdl_level() >= EFFDET_PDL_TU_LEVEL;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
-    return cudaLaunchKernelEx(&cfg, se_gate_cluster_kernel<NC>, se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate, C, R, Cs);
+    return cudaLaunchKernelEx(&cfg, se_gate_cluster_kernel<NC>, se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate, C, R, Cs,
+                              mean_o, s1_o, rr_o);
+}
+// clusters of 8 / 4 / 2 CTAs per image (fewer as the batch alone fills the GPU)
+cudaError_t se_cluster_launch(cudaStream_t st, const float *se_sum, int se_blocks, float inv_hw, const float *w1,
+                              const float *b1, const float *w2, const float *b2, float *gate, int B, int C, int R,
+                              float *mean_o, float *s1_o, float *rr_o) {
+    if (B <= 18) return launch_se_cluster<8>(st, se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate, B, C, R, mean_o, s1_o, rr_o);
+    if (B <= 74) return launch_se_cluster<4>(st, se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate, B, C, R, mean_o, s1_o, rr_o);
+    return launch_se_cluster<2>(st, se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate, B, C, R, mean_o, s1_o, rr_o);
+}
+bool se_cluster_ok(int C, int R) {
+    static const bool use_cluster = !(getenv("EFFDET_SE_CLUSTER") && atoi(getenv("EFFDET_SE_CLUSTER")) == 0);
+    return use_cluster && C >= 32 && C % 4 == 0 && R <= kSeCT;
 }
 
 // ------------------------------------------------------------------ fusion (stand-alone layer)
@@ -777,13 +796,9 @@ extern "C" int effdet_se_gate(const float *se_sum, int se_blocks, float inv_hw, 
                      reinterpret_cast<uintptr_t>(gate)) & 15) == 0, "w2 / b2 / gate must be 16B aligned");
     // clusters of 8 / 4 / 2 CTAs per image (fewer as the batch alone fills the GPU); EFFDET_SE_CLUSTER=0 keeps the
     // one-CTA-per-image kernel
-    static const bool use_cluster = !(getenv("EFFDET_SE_CLUSTER") && atoi(getenv("EFFDET_SE_CLUSTER")) == 0);
-    if (use_cluster && C >= 32 && R <= kSeCT) {
-        cudaStream_t st = as_stream(stream);
-        cudaError_t ce;
-        if (B <= 18) ce = launch_se_cluster<8>(st, se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate, B, C, R);
-        else if (B <= 74) ce = launch_se_cluster<4>(st, se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate, B, C, R);
-        else ce = launch_se_cluster<2>(st, se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate, B, C, R);
+    if (se_cluster_ok(C, R)) {
+        cudaError_t ce = se_cluster_launch(as_stream(stream), se_sum, se_blocks, inv_hw, w1, b1, w2, b2, gate, B, C, R,
+                                           nullptr, nullptr, nullptr);
         EFFDET_CUDA(ce);
         EFFDET_LAUNCHED();
         return EFFDET_OK;

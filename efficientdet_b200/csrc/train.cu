@@ -731,6 +731,10 @@ extern "C" int effdet_colreduce_blocks(size_t rows, int C, int dtype) {
     // 10-30 % of the pass, and made the finalize kernels walk up to ~2300 partial rows.
     size_t rpb = cdiv(rows, (size_t)kNumSMs * 4);
     if (rpb < (size_t)PY * 4) rpb = (size_t)PY * 4;
+    // a block's partial row is 2*C floats: at least 64 rows per block keeps the partial matrix (written here, read
+    // by the finalize kernel) below 1/16 of the tensor (block7b of D4: 8192 rows x 2688 channels had 586 partial
+    // rows = 12.6 MB for a 44 MB tensor, and a 14-us finalize)
+    if (rpb < 64) rpb = 64;
     rpb = cdiv(rpb, PY) * PY;
     return (int)cdiv(rows, rpb);
 }

@@ -940,6 +940,12 @@ extern "C" int effdet_sample_scale_add(const void *y, const float *scale, const 
 /* Per-(image, block, channel) spatial sums of y (B,HW,C): the SE squeeze when the depthwise
  * output is produced by a separate BN/activation pass (training mode).  partial (B, nblk, C) with
  * nblk = effdet_se_backward_blocks(). */
+namespace effdet {      // dwconv.cu
+cudaError_t se_cluster_launch(cudaStream_t st, const float *se_sum, int se_blocks, float inv_hw, const float *w1,
+                              const float *b1, const float *w2, const float *b2, float *gate, int B, int C, int R,
+                              float *mean_o, float *s1_o, float *rr_o);
+bool se_cluster_ok(int C, int R);
+}
 extern "C" int effdet_se_backward_blocks(int HW, int C, int dtype);
 extern "C" int effdet_spatial_sum(const void *y, float *partial, int nblk, int B, int HW, int C, int dtype,
                                   void *stream) {
@@ -1005,7 +1011,15 @@ extern "C" int effdet_se_backward(const void *dyg, const void *y, const float *g
         float *ds2_g = rr_g + (size_t)B * R, *ds1_g = ds2_g + (size_t)B * C, *ds1p = ds1_g + (size_t)B * R;
         const size_t sm1 = (size_t)(C + 512) * sizeof(float);
         EFFDET_REQUIRE(sm1 <= 48 * 1024, "C too large");
-        se_bwd_phase1_kernel<<<B, 512, sm1, st>>>(se_sum, se_blocks, 1.f / (float)HW, w1, b1, C, R, mean_g, s1_g, rr_g);
+        if (se_cluster_ok(C, R)) {
+            // forward recompute (squeeze mean, FC1) on thread-block clusters: the one-block-per-image kernel
+            // was a 45-us chain of dependent L2 round trips per MBConv block at batch 8
+            cudaError_t ce = se_cluster_launch(st, se_sum, se_blocks, 1.f / (float)HW, w1, b1, w2, b2, nullptr, B, C, R,
+                                               mean_g, s1_g, rr_g);
+            EFFDET_CUDA(ce);
+        } else {
+            se_bwd_phase1_kernel<<<B, 512, sm1, st>>>(se_sum, se_blocks, 1.f / (float)HW, w1, b1, C, R, mean_g, s1_g, rr_g);
+        }
         EFFDET_LAUNCHED();
         dim3 g2(nch, B);
         se_bwd_phase2_kernel<<<g2, 256, (size_t)9 * R * sizeof(float), st>>>(rr_g, dg_partial, dg_blocks, w2, b2, C, R,
