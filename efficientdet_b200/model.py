@@ -417,15 +417,26 @@ class Model:
         return self.net.set_weights_dict(d, strict)
 
     def save_weights(self, path):
+        """`.h5` / `.hdf5`: Keras weight-file layout (one group per layer, `layer_names` / `weight_names`
+        attributes; utils/hdf5.py) so that the reference's `load_weights(path, by_name=True)` (train.py:329-332)
+        can read it; anything else: `.npz` keyed '<layer>/<weight>'."""
+        if str(path).endswith((".h5", ".hdf5")):
+            from .utils import hdf5
+            hdf5.save_keras_weights(path, self.net.get_weights_dict(),
+                                    layer_order=list(dict.fromkeys(k.split("/")[0] for k in self.net.weights)))
+            return
         np.savez(path, **self.net.get_weights_dict())
 
     def load_weights(self, path, by_name=True, skip_mismatch=False):
-        """Loads a .npz written by save_weights (keys = '<keras layer>/<weight>[:0]').
-        Keras .h5 files need h5py, which this image does not ship (SURVEY 8(f) 'next')."""
+        """Keras `.h5` weight files (the reference's exchange format, train.py:329-332, utils/train.py:10-35;
+        read by the built-in HDF5 subset reader utils/hdf5.py -- h5py is not needed) or the `.npz` written by
+        save_weights; keys = '<keras layer>/<weight>[:0]'.  by_name=True ignores unknown / missing names like
+        Keras does; skip_mismatch drops weights whose shape differs."""
         if str(path).endswith((".h5", ".hdf5")):
-            raise NotImplementedError("Keras .h5 reading needs h5py (not installed); export the "
-                                      "weights to .npz keyed '<layer>/<weight>'")
-        d = {(k[:-2] if k.endswith(":0") else k): v for k, v in dict(np.load(path)).items()}
+            from .utils import hdf5
+            d = hdf5.load_keras_weights(path)
+        else:
+            d = {(k[:-2] if k.endswith(":0") else k): v for k, v in dict(np.load(path)).items()}
         if skip_mismatch:
             d = {k: v for k, v in d.items() if k in self.net.weights and
                  tuple(v.shape) == tuple(self.net.weights[k].shape)}

@@ -1,0 +1,545 @@
+"""Minimal HDF5 reader / writer for Keras weight files.
+
+The reference exchanges weights as Keras ``.h5`` files (`model.load_weights(path, by_name=True)`
+train.py:329-332, utils/train.py:15-16; `CheckpointSaver` utils/train.py:66-92 writes them).  h5py / libhdf5
+are not available in this image, so this module implements the subset of the HDF5 file format that h5py's
+default settings (libver 'earliest') produce for such files, from the published format specification
+("HDF5 File Format Specification Version 2.0"):
+
+  superblock version 0/1, version-1 object headers (+ continuation blocks), old-style groups (symbol-table
+  message -> version-1 B-tree of "SNOD" symbol-table nodes + local heap), dataspace message v1/v2, datatype
+  classes 0 (integers), 1 (IEEE floats), 3 (fixed-length strings), 9 (variable-length strings through the
+  global heap), data layout v3 (contiguous / compact; chunked only without filters), attribute message v1-v3.
+
+Not implemented (a clear NotImplementedError is raised): superblock v2/v3 with version-2 object headers
+(libver='latest'), filtered / compressed chunks, dense attribute storage.
+
+PARITY UNPINNED: no file written by libhdf5 exists in this container (no h5py, no network), so the reader is
+tested against this module's own writer plus byte-level known answers derived from the specification
+(tests/test_hdf5.py).  The writer emits only structures the reader (and libhdf5 1.8+) accept for the Keras
+layout: root attributes `layer_names`, `backend`, `keras_version`; one group per layer with a `weight_names`
+attribute and one contiguous little-endian dataset per weight (keras/engine/saving.py save_weights_to_hdf5_group).
+"""
+import struct
+
+import numpy as np
+
+SIGNATURE = b"\x89HDF\r\n\x1a\n"
+UNDEF = 0xFFFFFFFFFFFFFFFF
+
+
+# ====================================================================== reader
+class _Reader:
+    def __init__(self, buf):
+        self.b = memoryview(buf)
+        if bytes(self.b[:8]) != SIGNATURE:
+            raise ValueError("not an HDF5 file (bad signature)")
+        ver = self.b[8]
+        if ver not in (0, 1):
+            raise NotImplementedError("HDF5 superblock version %d (libver='latest' files) is not supported" % ver)
+        self.O, self.L = self.b[13], self.b[14]
+        if self.O != 8 or self.L != 8:
+            raise NotImplementedError("only 8-byte offsets/lengths are supported")
+        self.leaf_k, self.internal_k = struct.unpack_from("<HH", self.b, 16)
+        p = 24 + (4 if ver == 1 else 0)
+        self.base, _free, self.eof, _drv = struct.unpack_from("<QQQQ", self.b, p)
+        p += 32
+        # root group symbol table entry
+        _name_off, self.root_addr, cache, _res = struct.unpack_from("<QQII", self.b, p)
+        self.root_cache = struct.unpack_from("<QQ", self.b, p + 24) if cache == 1 else None
+
+    # ---- object headers
+    def messages(self, addr):
+        """-> list of (type, flags, bytes) of a version-1 object header, continuation blocks followed."""
+        b = self.b
+        addr += self.base
+        if bytes(b[addr:addr + 4]) == b"OHDR":
+            raise NotImplementedError("version-2 object headers are not supported")
+        ver, _r, nmsg, _refc, hsize = struct.unpack_from("<BBHII", b, addr)
+        if ver != 1:
+            raise ValueError("bad object header version %d at %d" % (ver, addr))
+        blocks = [(addr + 16, hsize)]
+        out = []
+        while blocks and len(out) < nmsg:
+            p, size = blocks.pop(0)
+            end = p + size
+            while p + 8 <= end and len(out) < nmsg:
+                mtype, msize, flags = struct.unpack_from("<HHB", b, p)
+                data = bytes(b[p + 8:p + 8 + msize])
+                p += 8 + msize
+                if mtype == 0x0010:                      # continuation: offset, length
+                    off, ln = struct.unpack_from("<QQ", data, 0)
+                    blocks.append((off + self.base, ln))
+                out.append((mtype, flags, data))
+        return out
+
+    # ---- groups
+    def _heap_string(self, heap_addr, off):
+        b = self.b
+        a = heap_addr + self.base
+        if bytes(b[a:a + 4]) != b"HEAP":
+            raise ValueError("bad local heap signature")
+        _size, _free, data_addr = struct.unpack_from("<QQQ", b, a + 8)
+        p = data_addr + self.base + off
+        e = p
+        while b[e] != 0:
+            e += 1
+        return bytes(b[p:e]).decode("utf-8")
+
+    def _btree_group(self, node_addr, heap_addr, out):
+        b = self.b
+        a = node_addr + self.base
+        sig = bytes(b[a:a + 4])
+        if sig == b"SNOD":
+            _ver, _r, nsym = struct.unpack_from("<BBH", b, a + 4)
+            p = a + 8
+            for _ in range(nsym):
+                name_off, obj = struct.unpack_from("<QQ", b, p)
+                out.append((self._heap_string(heap_addr, name_off), obj))
+                p += 40
+            return
+        if sig != b"TREE":
+            raise ValueError("bad B-tree signature %r" % sig)
+        ntype, _level, used = struct.unpack_from("<BBH", b, a + 4)
+        if ntype != 0:
+            raise ValueError("not a group B-tree")
+        p = a + 8 + 16                      # skip siblings
+        for i in range(used):
+            p += 8                          # key i
+            child, = struct.unpack_from("<Q", b, p)
+            p += 8
+            self._btree_group(child, heap_addr, out)
+
+    def links(self, addr):
+        """children of the group whose object header is at addr -> [(name, object header address)]."""
+        for mtype, _f, data in self.messages(addr):
+            if mtype == 0x0011:
+                btree, heap = struct.unpack_from("<QQ", data, 0)
+                out = []
+                self._btree_group(btree, heap, out)
+                return out
+            if mtype in (0x0002, 0x0006):
+                raise NotImplementedError("new-style (link message) groups are not supported")
+        return None                        # not a group
+
+    # ---- datatypes / dataspaces
+    def _dtype(self, data, p=0):
+        cv, b0, _b1, _b2, size = struct.unpack_from("<BBBBI", data, p)
+        cls = cv & 0x0F
+        if cls == 0:
+            order = ">" if b0 & 1 else "<"
+            return np.dtype("%s%s%d" % (order, "i" if b0 & 8 else "u", size)), p + 8 + 4
+        if cls == 1:
+            order = ">" if b0 & 1 else "<"
+            return np.dtype("%sf%d" % (order, size)), p + 8 + 12
+        if cls == 3:
+            return np.dtype("S%d" % size), p + 8
+        if cls == 9:
+            if (b0 & 0x0F) != 1:
+                raise NotImplementedError("variable-length sequences are not supported")
+            _base, q = self._dtype(data, p + 8)
+            return "vlen_str", q
+        raise NotImplementedError("HDF5 datatype class %d is not supported" % cls)
+
+    @staticmethod
+    def _dataspace(data):
+        ver = data[0]
+        rank = data[1]
+        if ver == 1:
+            p = 8
+        elif ver == 2:
+            if data[3] == 2:                # null dataspace
+                return None
+            p = 4
+        else:
+            raise NotImplementedError("dataspace message version %d" % ver)
+        return tuple(struct.unpack_from("<%dQ" % rank, data, p)) if rank else ()
+
+    def _vlen_strings(self, raw, n):
+        out = []
+        for i in range(n):
+            ln, gaddr, idx = struct.unpack_from("<IQI", raw, 16 * i)
+            if ln == 0 and gaddr == 0:
+                out.append("")
+                continue
+            out.append(self._global_heap_object(gaddr, idx)[:ln].decode("utf-8"))
+        return out
+
+    def _global_heap_object(self, addr, index):
+        b = self.b
+        a = addr + self.base
+        if bytes(b[a:a + 4]) != b"GCOL":
+            raise ValueError("bad global heap signature")
+        csize, = struct.unpack_from("<Q", b, a + 8)
+        p, end = a + 16, a + csize
+        while p + 16 <= end:
+            idx, _refc, _r, osize = struct.unpack_from("<HHIQ", b, p)
+            if idx == index:
+                return bytes(b[p + 16:p + 16 + osize])
+            if idx == 0:
+                break
+            p += 16 + (osize + 7) // 8 * 8
+        raise KeyError("global heap object %d not found" % index)
+
+    def _decode(self, dt, shape, raw):
+        n = 1
+        for s in (shape or ()):
+            n *= s
+        if shape is None:
+            return None
+        if isinstance(dt, str):             # variable-length strings
+            v = self._vlen_strings(raw, n)
+            return v[0] if shape == () else np.array(v, dtype=object).reshape(shape)
+        a = np.frombuffer(raw, dtype=dt, count=n).reshape(shape)
+        if dt.kind == "S":
+            return a[()] if shape == () else a
+        return a.astype(dt.newbyteorder("=")) if shape != () else a.astype(dt.newbyteorder("="))[()]
+
+    # ---- attributes / datasets
+    def attributes(self, addr):
+        out = {}
+        for mtype, _f, d in self.messages(addr):
+            if mtype != 0x000C:
+                continue
+            ver = d[0]
+            nsz, tsz, ssz = struct.unpack_from("<HHH", d, 2)
+            p = 8
+            if ver == 3:
+                p = 9
+            pad = (lambda x: (x + 7) // 8 * 8) if ver == 1 else (lambda x: x)
+            name = bytes(d[p:p + nsz]).split(b"\0")[0].decode("utf-8")
+            p += pad(nsz)
+            dt, _ = self._dtype(d, p)
+            p += pad(tsz)
+            shape = self._dataspace(d[p:p + ssz])
+            p += pad(ssz)
+            out[name] = self._decode(dt, shape, d[p:])
+        return out
+
+    def dataset(self, addr):
+        dt = shape = None
+        layout = None
+        for mtype, _f, d in self.messages(addr):
+            if mtype == 0x0003:
+                dt, _ = self._dtype(d)
+            elif mtype == 0x0001:
+                shape = self._dataspace(d)
+            elif mtype == 0x0008:
+                layout = d
+            elif mtype == 0x000B:
+                raise NotImplementedError("filtered (compressed) datasets are not supported")
+        if dt is None or layout is None:
+            raise ValueError("object at %d is not a dataset" % addr)
+        n = 1
+        for s in shape:
+            n *= s
+        nbytes = n * (16 if isinstance(dt, str) else dt.itemsize)
+        ver = layout[0]
+        if ver != 3:
+            raise NotImplementedError("data layout message version %d" % ver)
+        cls = layout[1]
+        if cls == 0:                         # compact
+            sz, = struct.unpack_from("<H", layout, 2)
+            raw = layout[4:4 + sz]
+        elif cls == 1:                       # contiguous
+            a, sz = struct.unpack_from("<QQ", layout, 2)
+            raw = b"" if a == UNDEF else bytes(self.b[a + self.base:a + self.base + nbytes])
+            if a == UNDEF:
+                raw = bytes(nbytes)
+        elif cls == 2:                       # chunked, no filters
+            raw = self._read_chunked(layout, shape, dt)
+        else:
+            raise NotImplementedError("data layout class %d" % cls)
+        return self._decode(dt, shape, raw)
+
+    def _read_chunked(self, layout, shape, dt):
+        ndim = layout[2]                     # rank + 1
+        btree, = struct.unpack_from("<Q", layout, 3)
+        cdims = struct.unpack_from("<%dI" % ndim, layout, 11)
+        chunk = cdims[:-1]
+        out = np.zeros(shape, dtype=dt)
+        if btree == UNDEF:
+            return out.tobytes()
+
+        def walk(node):
+            b = self.b
+            a = node + self.base
+            if bytes(b[a:a + 4]) != b"TREE":
+                raise ValueError("bad chunk B-tree")
+            ntype, level, used = struct.unpack_from("<BBH", b, a + 4)
+            p = a + 24
+            ksz = 8 + 8 * ndim
+            for _ in range(used):
+                csize, fmask = struct.unpack_from("<II", b, p)
+                offs = struct.unpack_from("<%dQ" % ndim, b, p + 8)
+                child, = struct.unpack_from("<Q", b, p + ksz)
+                p += ksz + 8
+                if level > 0:
+                    walk(child)
+                    continue
+                if fmask:
+                    raise NotImplementedError("filtered chunks are not supported")
+                data = np.frombuffer(bytes(b[child + self.base:child + self.base + csize]), dtype=dt).reshape(chunk)
+                sl = tuple(slice(o, min(o + c, s)) for o, c, s in zip(offs[:-1], chunk, shape))
+                out[sl] = data[tuple(slice(0, s.stop - s.start) for s in sl)]
+        walk(btree)
+        return out.tobytes()
+
+
+class Group:
+    """Read-only view of an HDF5 group: `g[name]` -> Group or numpy array, `g.attrs`, `g.keys()`."""
+
+    def __init__(self, reader, addr, name="/"):
+        self._r, self._addr, self.name = reader, addr, name
+        self._links = dict(reader.links(addr) or [])
+
+    @property
+    def attrs(self):
+        return self._r.attributes(self._addr)
+
+    def keys(self):
+        return list(self._links)
+
+    def __contains__(self, k):
+        return k.split("/")[0] in self._links
+
+    def __getitem__(self, key):
+        node = self
+        for part in [p for p in key.split("/") if p]:
+            if not isinstance(node, Group):
+                raise KeyError(key)
+            addr = node._links[part]
+            if node._r.links(addr) is not None:
+                node = Group(node._r, addr, node.name.rstrip("/") + "/" + part)
+            else:
+                node = node._r.dataset(addr)
+        return node
+
+
+def open_file(path):
+    with open(path, "rb") as f:
+        buf = f.read()
+    r = _Reader(buf)
+    return Group(r, r.root_addr)
+
+
+def _names(v):
+    return [(x.decode("utf-8") if isinstance(x, bytes) else str(x)) for x in np.asarray(v).reshape(-1)]
+
+
+def _chunked_attr(attrs, name):
+    """keras saving.load_attributes_from_hdf5_group: `name` or `name0`, `name1`, ... chunks."""
+    if name in attrs:
+        return _names(attrs[name])
+    out, i = [], 0
+    while "%s%d" % (name, i) in attrs:
+        out += _names(attrs["%s%d" % (name, i)])
+        i += 1
+    return out
+
+
+def load_keras_weights(path):
+    """Keras `.h5` weights file (save_weights, or the `model_weights` group of a full-model file) ->
+    {"<weight name without ':0'>": ndarray} keyed like Network.weights ("<layer>/<weight>")."""
+    root = open_file(path)
+    g = root["model_weights"] if "model_weights" in root and "layer_names" not in root.attrs else root
+    out = {}
+    for layer in _chunked_attr(g.attrs, "layer_names"):
+        lg = g[layer]
+        for wn in _chunked_attr(lg.attrs, "weight_names"):
+            key = wn[:-2] if wn.endswith(":0") else wn
+            # weights of a nested Model layer (box_head / class_head, model.py:271-353) are named after their own
+            # inner layer ("regress_head_conv_0/kernel:0"): prefix the outer layer like Network.weights does
+            if not key.startswith(layer + "/"):
+                key = layer + "/" + key
+            out[key] = np.require(lg[wn], requirements="C")
+    return out
+
+
+# ====================================================================== writer
+class _Writer:
+    """Appends HDF5 structures to a byte buffer; every structure is 8-byte aligned."""
+    LEAF_K, INTERNAL_K = 4, 16
+
+    def __init__(self):
+        self.buf = bytearray(b"\0" * 96)     # superblock v0 (56 bytes + root symbol table entry 40)
+
+    def _align(self):
+        while len(self.buf) % 8:
+            self.buf.append(0)
+
+    def _append(self, data):
+        self._align()
+        a = len(self.buf)
+        self.buf += data
+        return a
+
+    # ---- messages
+    @staticmethod
+    def _msg(mtype, data, flags=0):
+        data = bytes(data)
+        data += b"\0" * (-len(data) % 8)
+        return struct.pack("<HHBBBB", mtype, len(data), flags, 0, 0, 0) + data
+
+    @staticmethod
+    def _datatype(dt):
+        dt = np.dtype(dt)
+        if dt.kind == "f":
+            exp_bits, man_bits, bias = {2: (5, 10, 15), 4: (8, 23, 127), 8: (11, 52, 1023)}[dt.itemsize]
+            bits = dt.itemsize * 8
+            # class 1 version 1; byte order LE, pad 0, mantissa normalisation "implied msb" (2 << 4), sign bit pos
+            head = struct.pack("<BBBBI", 0x11, 0x20, bits - 1, 0, dt.itemsize)
+            return head + struct.pack("<HHBBBBI", 0, bits, man_bits, exp_bits, 0, man_bits, bias)
+        if dt.kind in "iu":
+            head = struct.pack("<BBBBI", 0x10, 0x08 if dt.kind == "i" else 0, 0, 0, dt.itemsize)
+            return head + struct.pack("<HH", 0, dt.itemsize * 8)
+        if dt.kind == "S":
+            return struct.pack("<BBBBI", 0x13, 0x01, 0, 0, dt.itemsize)      # null-padded ASCII
+        raise TypeError("unsupported dtype %s" % dt)
+
+    @staticmethod
+    def _dataspace(shape):
+        shape = tuple(shape)
+        return struct.pack("<BBBBI", 1, len(shape), 0, 0, 0) + b"".join(struct.pack("<Q", s) for s in shape)
+
+    def _attribute(self, name, value):
+        if isinstance(value, str):
+            value = np.bytes_(value.encode("utf-8"))
+        if isinstance(value, (list, tuple)):
+            enc = [v.encode("utf-8") if isinstance(v, str) else v for v in value]
+            value = np.array(enc, dtype="S%d" % max(1, max(len(e) for e in enc)))
+        a = np.asarray(value)
+        if a.dtype.kind == "S" and a.dtype.itemsize == 0:
+            a = a.astype("S1")
+        pad = lambda b_: b_ + b"\0" * (-len(b_) % 8)
+        nm = name.encode("utf-8") + b"\0"
+        dt, ds = self._datatype(a.dtype), self._dataspace(a.shape)
+        body = struct.pack("<BBHHH", 1, 0, len(nm), len(dt), len(ds)) + pad(nm) + pad(dt) + pad(ds) + a.tobytes()
+        if len(body) > 64000:
+            raise ValueError("attribute %r too large for a version-1 object header (keras splits such lists "
+                             "into %s0, %s1, ...)" % (name, name, name))
+        return self._msg(0x000C, body)
+
+    def _object_header(self, msgs):
+        body = b"".join(msgs)
+        hdr = struct.pack("<BBHII", 1, 0, len(msgs), 1, len(body)) + b"\0" * 4
+        return self._append(hdr + body)
+
+    # ---- objects
+    def dataset(self, array, attrs=None):
+        a = np.require(np.asarray(array), requirements="C")      # keeps 0-d arrays 0-d
+        if a.dtype.byteorder == ">":
+            a = a.astype(a.dtype.newbyteorder("<"))
+        data_addr = self._append(a.tobytes()) if a.nbytes else UNDEF
+        msgs = [self._msg(0x0001, self._dataspace(a.shape)),
+                self._msg(0x0003, self._datatype(a.dtype), flags=1),
+                self._msg(0x0005, struct.pack("<BBBB", 2, 2, 2, 0)),           # fill value v2: never written, undefined
+                self._msg(0x0008, struct.pack("<BBQQ", 3, 1, data_addr, a.nbytes))]
+        msgs += [self._attribute(k, v) for k, v in (attrs or {}).items()]
+        return self._object_header(msgs)
+
+    def group(self, children, attrs=None):
+        """children: {name: object header address} -> object header address of the new group."""
+        names = sorted(children, key=lambda s: s.encode("utf-8"))
+        # local heap: offset 0 holds the empty string (B-tree key 0)
+        heap_data = bytearray(b"\0" * 8)
+        offs = {}
+        for n in names:
+            offs[n] = len(heap_data)
+            heap_data += n.encode("utf-8") + b"\0"
+            heap_data += b"\0" * (-len(heap_data) % 8)
+        free_off = len(heap_data)
+        heap_data += struct.pack("<QQ", 1, 16)                 # one free block (next = 1 -> last, size 16)
+        data_addr = self._append(bytes(heap_data))
+        heap_addr = self._append(b"HEAP" + struct.pack("<BBBBQQQ", 0, 0, 0, 0, len(heap_data), free_off, data_addr))
+        # symbol table nodes of <= 2K entries each
+        cap = 2 * self.LEAF_K
+        leaves = []
+        for i in range(0, max(len(names), 1), cap):
+            part = names[i:i + cap]
+            body = b"SNOD" + struct.pack("<BBH", 1, 0, len(part))
+            for n in part:
+                body += struct.pack("<QQII", offs[n], children[n], 0, 0) + b"\0" * 16
+            body += b"\0" * (40 * (cap - len(part)))
+            leaves.append((self._append(body), offs[part[-1]] if part else 0))
+        # B-tree levels: nodes of <= 2K' children; key[i+1] = heap offset of the largest name under child i
+        level, nodes = 0, leaves
+        icap = 2 * self.INTERNAL_K
+        while True:
+            parents = []
+            for i in range(0, len(nodes), icap):
+                part = nodes[i:i + icap]
+                body = b"TREE" + struct.pack("<BBHQQ", 0, level, len(part), UNDEF, UNDEF)
+                body += struct.pack("<Q", 0)
+                for addr, maxkey in part:
+                    body += struct.pack("<QQ", addr, maxkey)
+                body += b"\0" * (16 * (icap - len(part)))
+                parents.append((self._append(body), part[-1][1]))
+            if len(parents) == 1:
+                btree_addr = parents[0][0]
+                break
+            nodes, level = parents, level + 1
+        # sibling pointers are left undefined (single traversal from the root suffices for readers)
+        msgs = [self._msg(0x0011, struct.pack("<QQ", btree_addr, heap_addr))]
+        msgs += [self._attribute(k, v) for k, v in (attrs or {}).items()]
+        return self._object_header(msgs), btree_addr, heap_addr
+
+    def finish(self, root):
+        root_addr, btree, heap = root
+        self._align()
+        eof = len(self.buf)
+        sb = SIGNATURE + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, self.LEAF_K, self.INTERNAL_K, 0)
+        sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
+        sb += struct.pack("<QQII", 0, root_addr, 1, 0) + struct.pack("<QQ", btree, heap)
+        assert len(sb) == 96
+        self.buf[:96] = sb
+        return bytes(self.buf)
+
+
+def _split_attr(name, values, limit=60000):
+    """keras saving.save_attributes_to_hdf5_group: lists too large for one object-header message are split."""
+    enc = [v.encode("utf-8") for v in values]
+    width = max([1] + [len(e) for e in enc])
+    if width * max(len(enc), 1) <= limit:
+        return {name: enc}
+    per = max(1, limit // width)
+    return {"%s%d" % (name, i // per): enc[i:i + per] for i in range(0, len(enc), per)}
+
+
+def save_keras_weights(path, weights, layer_order=None, backend="tensorflow", keras_version="2.2.4-tf"):
+    """{"<layer>/<weight>": ndarray} -> Keras `.h5` weights file: one group per layer (the first path
+    component), datasets named "<layer>/<weight>:0" inside it (nested groups, as h5py creates them for names
+    with slashes), `weight_names` per layer and `layer_names` / `backend` / `keras_version` on the root."""
+    w = _Writer()
+    by_layer = {}
+    for k, v in weights.items():
+        by_layer.setdefault(k.split("/")[0], []).append((k, np.asarray(v)))
+    order = [l for l in (layer_order or []) if l in by_layer] + [l for l in by_layer if l not in (layer_order or [])]
+    root_children = {}
+    for layer in order:
+        tree = {}
+        names = []
+        for k, v in by_layer[layer]:
+            full = k + ":0"
+            names.append(full)
+            node = tree
+            parts = full.split("/")
+            for part in parts[:-1]:
+                node = node.setdefault(part, {})
+            node[parts[-1]] = v
+
+        def emit(node):
+            ch = {}
+            for name, sub in node.items():
+                ch[name] = emit(sub)[0] if isinstance(sub, dict) else w.dataset(sub)
+            return w.group(ch)
+        ch = {}
+        for name, sub in tree.items():
+            ch[name] = emit(sub)[0] if isinstance(sub, dict) else w.dataset(sub)
+        root_children[layer] = w.group(ch, attrs=_split_attr("weight_names", names))[0]
+    attrs = dict(_split_attr("layer_names", order))
+    attrs["backend"] = backend
+    attrs["keras_version"] = keras_version
+    data = w.finish(w.group(root_children, attrs=attrs))
+    with open(path, "wb") as f:
+        f.write(data)

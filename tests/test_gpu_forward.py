@@ -340,3 +340,31 @@ def test_predict_generator_matches_predict_on_batch():
     for g, w in zip(got, want):
         for a, b in zip(g, w):
             assert np.array_equal(a, b)
+
+
+def test_keras_h5_weight_file_round_trip_through_the_model(tmp_path):
+    """model.save_weights('x.h5') -> Keras weight-file layout (utils/hdf5.py) -> load_weights(by_name=True) on a
+    freshly initialised model (train.py:329-332): identical weights and identical detections."""
+    from efficientdet_b200.model import efficientdet
+    from efficientdet_b200.utils import hdf5
+    from efficientdet_b200.utils.anchors import anchors_for_shape
+    size = 128
+    anchors = anchors_for_shape((size, size))
+    m1, p1 = efficientdet(0, num_classes=4, weighted_bifpn=True, image_size=size, drop_connect_rate=0,
+                          score_threshold=0.3, anchors=anchors, seed=1)
+    perturb_weights(m1)
+    path = str(tmp_path / "weights.h5")
+    m1.save_weights(path)
+    root = hdf5.open_file(path)
+    layers = [x.decode() for x in root.attrs["layer_names"]]
+    assert "stem_conv" in layers and "box_head" in layers and "w_bi_fpn_add" in layers
+    assert [x.decode() for x in root["stem_bn"].attrs["weight_names"]] == [
+        "stem_bn/gamma:0", "stem_bn/beta:0", "stem_bn/moving_mean:0", "stem_bn/moving_variance:0"]
+    m2, p2 = efficientdet(0, num_classes=4, weighted_bifpn=True, image_size=size, drop_connect_rate=0,
+                          score_threshold=0.3, anchors=anchors, seed=2)
+    m2.load_weights(path, by_name=True)
+    w1, w2 = m1.get_weights_dict(), m2.get_weights_dict()
+    assert set(w1) == set(w2) and all(np.array_equal(w1[k], w2[k]) for k in w1)
+    img = np.random.default_rng(0).standard_normal((2, size, size, 3)).astype(np.float32)
+    for a, b in zip(p1.predict_on_batch([img]), p2.predict_on_batch([img])):
+        assert np.array_equal(a, b)
