@@ -160,12 +160,14 @@ def test_conv_dgrad_via_transposed_weights_and_strided():
             assert rel_err(out.cpu().numpy(), want + prev) < 1e-5
 
 
+@pytest.mark.parametrize("rows,C", [(4 * 12 * 12, 88), (140003, 64), (8 * 16 * 16, 224)])
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-def test_bn_train_forward_backward(dtype):
+def test_bn_train_forward_backward(dtype, rows, C):
+    """(576, 88) and, in bf16, (2048, 224): tensors <= 512 KB take the one-launch thread-block-cluster backward;
+    (140003, 64): the reduce / finalize / apply chain."""
     from efficientdet_b200 import _lib
     lib = _lib.load()
     rng = np.random.default_rng(2)
-    rows, C = 4 * 12 * 12, 88
     tdt = torch.float32 if dtype == "fp32" else torch.bfloat16
     dt = _lib.F32 if dtype == "fp32" else _lib.BF16
     zd = _d(rng.standard_normal((rows, C)).astype(np.float32) * 1.5 + 0.3, tdt)
