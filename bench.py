@@ -124,7 +124,7 @@ def run_ours(args, rank, world):
     torch.cuda.set_device(dev)
     hbm, tflops, peak_src = peaks()
     if kind == "train":
-        from efficientdet_b200 import train as T
+        import bench_train as T
         return T.bench_train(args, rank, world, phi, B, C, dtype, weighted, dev,
                              freeze_backbone=FREEZE_BACKBONE[args.workload])
 
@@ -338,7 +338,7 @@ def run_reference(args, rank, world):
     from oracle import graph, tail, anchors as oa
     torch.set_num_threads(os.cpu_count())
     if kind == "train":
-        from efficientdet_b200 import train as T
+        import bench_train as T
         return T.bench_train_reference(args, phi, B, C, weighted, FREEZE_BACKBONE[args.workload])
     W = _random_weights(phi, C, weighted)
     anchors = oa.anchors_for_shape((S, S)).astype(np.float32)

@@ -521,19 +521,3 @@ def efficientdet(phi, num_classes=20, weighted_bifpn=False, freeze_bn=False, sco
                              anchors=baked, score_threshold=score_threshold,
                              takes_anchors=anchors is None)
     return model, prediction_model
-
-
-def _smoke():
-    """Tiny end-to-end check used by __graft_entry__.smoke(): D0 at 128x128, batch 2, against
-    the torch-CPU oracle (fp32, 1e-4 relative)."""
-    from oracle import graph
-    m, pm = efficientdet(0, num_classes=4, image_size=128, drop_connect_rate=0, score_threshold=0.3)
-    rng = np.random.default_rng(1234)
-    img = rng.standard_normal((2, 128, 128, 3)).astype(np.float32)
-    reg, cls = m.predict_on_batch(img)
-    W = m.get_weights_dict()
-    with torch.no_grad():
-        r0, c0 = graph.forward(W, img, 0, 4)
-    for got, want, nm in ((reg, r0.numpy(), "regression"), (cls, c0.numpy(), "classification")):
-        err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-12)
-        assert err < 1e-4, "%s mismatch vs oracle: %g" % (nm, err)
