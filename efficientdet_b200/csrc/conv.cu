@@ -95,7 +95,7 @@ __global__ void __launch_bounds__((C0 / 8) * (kStemTW / kStemStrip) * kStemTH)
 stem_conv_tiled_kernel(const TI *__restrict__ img, const float *__restrict__ lut, const float *__restrict__ w,
                        const float *__restrict__ scale, const float *__restrict__ shift,
                        __nv_bfloat16 *__restrict__ out, int H, int W, int Ho, int Wo, int pad_t, int pad_l,
-                       int tiles_x) {
+                       int tiles_x, uint32_t zero) {
     constexpr int NO = C0 / 8;
     constexpr int NT = NO * (kStemTW / kStemStrip) * kStemTH;
     constexpr int ROW = kStemIW * 3;
@@ -112,12 +112,35 @@ stem_conv_tiled_kernel(const TI *__restrict__ img, const float *__restrict__ lut
     for (int i = threadIdx.x; i < 27 * C0 / 4; i += NT)
         reinterpret_cast<float4 *>(sw)[i] = reinterpret_cast<const float4 *>(w)[i];
     const TI *ib = img + (size_t)b * H * W * 3;
-    for (int i = threadIdx.x; i < kStemIH * ROW; i += NT) {
-        const int r = i / ROW, cidx = i - r * ROW;
-        const int gy = iy0 + r, g3 = ix0 * 3 + cidx;
-        // outside the image: zero in NORMALISED space (TF SAME padding acts on the network input)
-        sin_[i] = (gy >= 0 && gy < H && g3 >= 0 && g3 < W * 3)
-                      ? StemPix<TI>::get(ib + (size_t)gy * W * 3 + g3, slut, cidx % 3) : 0.f;
+    // patch staging: four loads per thread in flight (tied together: ptxas otherwise sinks each load next to its
+    // shared-memory store and the block waits one global round trip per element, 14 times)
+    for (int i0 = threadIdx.x; i0 < kStemIH * ROW; i0 += 4 * NT) {
+        uint32_t raw[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * NT;
+            const int r = i / ROW, cidx = i - r * ROW;
+            const int gy = iy0 + r, g3 = ix0 * 3 + cidx;
+            // outside the image: zero in NORMALISED space (TF SAME padding acts on the network input)
+            ok[u] = i < kStemIH * ROW && gy >= 0 && gy < H && g3 >= 0 && g3 < W * 3;
+            raw[u] = 0u;
+            if (ok[u]) {
+                const TI *src = ib + (size_t)gy * W * 3 + g3;
+                raw[u] = sizeof(TI) == 1 ? (uint32_t)*reinterpret_cast<const uint8_t *>(src)
+                                         : __float_as_uint(*reinterpret_cast<const float *>(src));
+            }
+        }
+        const uint32_t t = (raw[0] ^ raw[1] ^ raw[2] ^ raw[3]) & zero;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * NT;
+            if (i < kStemIH * ROW) {
+                const uint32_t w = raw[u] | t;
+                const int cidx = i % ROW;
+                sin_[i] = !ok[u] ? 0.f : (sizeof(TI) == 1 ? slut[(cidx % 3) * 256 + w] : __uint_as_float(w));
+            }
+        }
     }
     __syncthreads();
     const int oct = threadIdx.x % NO, strip = threadIdx.x / NO;
@@ -384,10 +407,10 @@ static int launch_stem_bf16(const TI *img, const float *lut, const float *w, con
     case C:                                                                                                \
         if (act == EFFDET_ACT_SWISH)                                                                       \
             stem_conv_tiled_kernel<TI, C, EFFDET_ACT_SWISH><<<grid, (C / 8) * (kStemTW / kStemStrip) * kStemTH, 0, st>>>( \
-                img, lut, w, scale, shift, static_cast<__nv_bfloat16 *>(out), H, W, Ho, Wo, pad_t, pad_l, tx);  \
+                img, lut, w, scale, shift, static_cast<__nv_bfloat16 *>(out), H, W, Ho, Wo, pad_t, pad_l, tx, 0u);  \
         else                                                                                               \
             stem_conv_tiled_kernel<TI, C, EFFDET_ACT_NONE><<<grid, (C / 8) * (kStemTW / kStemStrip) * kStemTH, 0, st>>>( \
-                img, lut, w, scale, shift, static_cast<__nv_bfloat16 *>(out), H, W, Ho, Wo, pad_t, pad_l, tx);  \
+                img, lut, w, scale, shift, static_cast<__nv_bfloat16 *>(out), H, W, Ho, Wo, pad_t, pad_l, tx, 0u);  \
         break;
     switch (C0) {
         STEM_T(32) STEM_T(40) STEM_T(48) STEM_T(56) STEM_T(64)
