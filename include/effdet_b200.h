@@ -206,7 +206,9 @@ int effdet_dwconv(const void *x, const float *kernel, const float *scale, const 
 
 /* Squeeze-excite FCs (efficientnet.py:255-286): mean = sum_blocks(se_sum)/(HW);
  * r = swish(W1^T mean + b1); gate = sigmoid(W2^T r + b2).  se_sum (B,se_blocks,C);
- * w1 (C,R), w2 (R,C) f32 (Keras 1x1 conv kernels). gate (B,C) f32. */
+ * w1 (C,R), w2 (R,C) f32 (Keras 1x1 conv kernels). gate (B,C) f32.  Runs on thread-block clusters of 2-8 CTAs
+ * per image (channel slices, partial FC1 sums exchanged through distributed shared memory in rank order:
+ * deterministic); EFFDET_SE_CLUSTER=0 selects the one-CTA-per-image kernel. */
 int effdet_se_gate(const float *se_sum, int se_blocks, float inv_hw, const float *w1,
                    const float *b1, const float *w2, const float *b2, float *gate, int B, int C,
                    int R, void *stream);
@@ -255,7 +257,8 @@ int effdet_resample_fuse(const void *in0, int mode0, const void *in1, const void
                          void *stream);
 
 /* Row-block count used by the deterministic column reductions below for a (rows, C) matrix;
- * `partial` scratch must hold 2*C*blocks floats. */
+ * `partial` scratch must hold 2*C*blocks floats.  The count is one balanced wave on the 148 SMs (at most 4 blocks
+ * per SM, at least 64 rows per block), so the partial matrix stays below 1/16 of the tensor. */
 int effdet_colreduce_blocks(size_t rows, int C, int dtype);
 
 /* BatchNormalization, training mode (model.py:59-62/81-84 with trainable=True; TF fused BN):
