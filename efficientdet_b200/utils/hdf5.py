@@ -9,16 +9,19 @@ default settings (libver 'earliest') produce for such files, from the published 
   superblock version 0/1, version-1 object headers (+ continuation blocks), old-style groups (symbol-table
   message -> version-1 B-tree of "SNOD" symbol-table nodes + local heap), dataspace message v1/v2, datatype
   classes 0 (integers), 1 (IEEE floats), 3 (fixed-length strings), 9 (variable-length strings through the
-  global heap), data layout v3 (contiguous / compact; chunked only without filters), attribute message v1-v3.
+  global heap), data layout v1-v3 (contiguous / compact; chunked only without filters), attribute message v1-v3,
+  a user block in front of the superblock.
 
 Not implemented (a clear NotImplementedError is raised): superblock v2/v3 with version-2 object headers
 (libver='latest'), filtered / compressed chunks, dense attribute storage.
 
-PARITY UNPINNED: no file written by libhdf5 exists in this container (no h5py, no network), so the reader is
-tested against this module's own writer plus byte-level known answers derived from the specification
-(tests/test_hdf5.py).  The writer emits only structures the reader (and libhdf5 1.8+) accept for the Keras
-layout: root attributes `layer_names`, `backend`, `keras_version`; one group per layer with a `weight_names`
-attribute and one contiguous little-endian dataset per weight (keras/engine/saving.py save_weights_to_hdf5_group).
+Pinning: the reader is checked against the one libhdf5-written file in this image (a MATLAB 7.4 v7.3 MAT-file
+from scipy's test data: user block, superblock v0, symbol-table group, v1 object header, float dataset, layout
+v1/2, string attribute -- tests/test_hdf5.py).  No h5py-written KERAS file is available (no h5py, no network), so
+the Keras conventions (root attributes `layer_names`, `backend`, `keras_version`; one group per layer with a
+`weight_names` attribute and one contiguous little-endian dataset per weight, keras/engine/saving.py
+save_weights_to_hdf5_group) and this module's writer are tested by round trips plus byte-level known answers
+derived from the specification: that part is PARITY UNPINNED.
 """
 import struct
 
@@ -32,16 +35,20 @@ UNDEF = 0xFFFFFFFFFFFFFFFF
 class _Reader:
     def __init__(self, buf):
         self.b = memoryview(buf)
-        if bytes(self.b[:8]) != SIGNATURE:
-            raise ValueError("not an HDF5 file (bad signature)")
-        ver = self.b[8]
+        # the superblock sits at offset 0 or, behind a user block, at 512, 1024, 2048, ... (format spec II.A)
+        sb = 0
+        while bytes(self.b[sb:sb + 8]) != SIGNATURE:
+            sb = 512 if sb == 0 else sb * 2
+            if sb + 8 > len(self.b):
+                raise ValueError("not an HDF5 file (bad signature)")
+        ver = self.b[sb + 8]
         if ver not in (0, 1):
             raise NotImplementedError("HDF5 superblock version %d (libver='latest' files) is not supported" % ver)
-        self.O, self.L = self.b[13], self.b[14]
+        self.O, self.L = self.b[sb + 13], self.b[sb + 14]
         if self.O != 8 or self.L != 8:
             raise NotImplementedError("only 8-byte offsets/lengths are supported")
-        self.leaf_k, self.internal_k = struct.unpack_from("<HH", self.b, 16)
-        p = 24 + (4 if ver == 1 else 0)
+        self.leaf_k, self.internal_k = struct.unpack_from("<HH", self.b, sb + 16)
+        p = sb + 24 + (4 if ver == 1 else 0)
         self.base, _free, self.eof, _drv = struct.unpack_from("<QQQQ", self.b, p)
         p += 32
         # root group symbol table entry
@@ -235,6 +242,26 @@ class _Reader:
             n *= s
         nbytes = n * (16 if isinstance(dt, str) else dt.itemsize)
         ver = layout[0]
+        if ver in (1, 2):                    # libhdf5 <= 1.6: version, rank, class, 5 reserved, [address], dims
+            ndim, cls = layout[1], layout[2]
+            p = 8
+            a = UNDEF
+            if cls != 0:
+                a, = struct.unpack_from("<Q", layout, p)
+                p += 8
+            dims = struct.unpack_from("<%dI" % ndim, layout, p)
+            p += 4 * ndim
+            if cls == 0:
+                sz, = struct.unpack_from("<I", layout, p)
+                raw = layout[p + 4:p + 4 + sz]
+            elif cls == 1:
+                raw = bytes(nbytes) if a == UNDEF else bytes(self.b[a + self.base:a + self.base + nbytes])
+            elif cls == 2:
+                raw = self._read_chunked(bytes([3, 2, ndim]) + struct.pack("<Q", a) +
+                                         struct.pack("<%dI" % ndim, *dims), shape, dt)
+            else:
+                raise NotImplementedError("data layout class %d" % cls)
+            return self._decode(dt, shape, raw)
         if ver != 3:
             raise NotImplementedError("data layout message version %d" % ver)
         cls = layout[1]

@@ -1,7 +1,10 @@
 """CPU: the built-in HDF5 subset (efficientdet_b200/utils/hdf5.py) behind load_weights / save_weights of Keras
-`.h5` weight files (train.py:329-332, utils/train.py:10-35).  PARITY UNPINNED against libhdf5 (no h5py in this
-image): round trips through the module's own writer + byte-level checks of the structures the format
-specification fixes (superblock, object-header / B-tree / heap signatures, message encodings)."""
+`.h5` weight files (train.py:329-332, utils/train.py:10-35).  The READER is pinned on the one file written by
+libhdf5 that exists in this image (a MATLAB 7.4 v7.3 MAT-file = HDF5 behind a 512-byte user block, from scipy's
+test data, BSD licence, copied to tests/golden/): user block + superblock v0, symbol-table group (v1 B-tree,
+SNOD, local heap), v1 object header, dataspace, IEEE float datatype, layout message v1/2, fixed-string attribute.
+No h5py-written Keras file is available, so the Keras LAYOUT (layer_names / weight_names conventions) and the
+writer are checked by round trips + byte-level known answers derived from the format specification."""
 import struct
 
 import numpy as np
@@ -24,6 +27,20 @@ def _weights(n_layers=70, seed=0):
     w["boxes/anchor_boxes_baked"] = rng.uniform(0, 512, (1, 49104, 4)).astype(np.float32)
     w["scalar_layer/step"] = np.array(7, np.int64)
     return w
+
+
+def test_reader_on_a_file_written_by_libhdf5():
+    """scipy/io/matlab/tests/data/testhdf5_7.4_GLNX86.mat: MATLAB 7.4 saved `testdouble = 0:pi/4:2*pi` with
+    libhdf5 (scipy's own tests list this variable's value in test_mio.py)."""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = hdf5.open_file(os.path.join(here, "golden", "libhdf5_matlab74_testdouble.mat"))
+    assert g.keys() == ["testdouble"]
+    v = g["testdouble"]
+    assert v.shape == (9, 1) and v.dtype == np.float64
+    assert np.array_equal(v.ravel(), np.pi / 4 * np.arange(9))
+    assert g._r.attributes(g._links["testdouble"]) == {"MATLAB_class": b"double"}
+    assert g._r.base == 512 and (g._r.leaf_k, g._r.internal_k) == (4, 16)
 
 
 def test_keras_weight_file_round_trip(tmp_path):
