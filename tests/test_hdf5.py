@@ -41,6 +41,15 @@ def test_reader_on_a_file_written_by_libhdf5():
     assert np.array_equal(v.ravel(), np.pi / 4 * np.arange(9))
     assert g._r.attributes(g._links["testdouble"]) == {"MATLAB_class": b"double"}
     assert g._r.base == 512 and (g._r.leaf_k, g._r.internal_k) == (4, 16)
+    # the writer encodes the structures both files share byte for byte like libhdf5 did in that file
+    msgs = {t: d for t, _f, d in g._r.messages(g._links["testdouble"])}
+    assert msgs[0x0003][:20] == hdf5._Writer._datatype(np.float64)
+    assert msgs[0x0001] == hdf5._Writer._dataspace((9, 1))
+    mine = hdf5._Writer()._attribute("MATLAB_class", np.bytes_(b"double"))[8:]      # message body
+    theirs = bytearray(msgs[0x000C])
+    assert theirs[25] == 0x00 and mine[25] == 0x01        # string padding: libhdf5/MATLAB null-terminated, numpy 'S' null-padded
+    theirs[25] = 0x01
+    assert bytes(theirs) == mine
 
 
 def test_keras_weight_file_round_trip(tmp_path):
