@@ -112,6 +112,11 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev, freeze_backb
         from efficientdet_b200 import parallel
         return parallel.max_over_ranks(e0.elapsed_time(e1), dev)
 
+    # the plan is ~10^5 long-lived Python objects (ops, closures, descriptors): keep the cyclic collector from
+    # walking them during the timed loops (a full collection is a 50-150 ms pause = several D4 steps)
+    import gc
+    gc.collect()
+    gc.freeze()
     clocks = bench_mod.Clocks(dev.index) if rank == 0 else None
     ms = timed(step_device, args.steps)
     run_e2e(2)
@@ -137,6 +142,8 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev, freeze_backb
         for _ in tr.fit_prefetched(plan8, anchors_d, gen):
             pass
     run_e2e8(3)
+    gc.collect()
+    gc.freeze()
     if world > 1:
         torch.distributed.barrier()
     torch.cuda.synchronize(dev)
