@@ -89,8 +89,10 @@ class _Reader:
         _size, _free, data_addr = struct.unpack_from("<QQQ", b, a + 8)
         p = data_addr + self.base + off
         e = p
-        while b[e] != 0:
+        while e < len(b) and b[e] != 0:
             e += 1
+        if e >= len(b):
+            raise ValueError("unterminated link name in local heap (truncated file?)")
         return bytes(b[p:e]).decode("utf-8")
 
     def _btree_group(self, node_addr, heap_addr, out):

@@ -188,3 +188,10 @@ def test_unsupported_files_fail_loudly(tmp_path):
     p.write_bytes(hdf5.SIGNATURE + bytes([2]) + b"\0" * 64)
     with pytest.raises(NotImplementedError):
         hdf5.open_file(str(p))
+    # truncated file: structures point past the end -> an exception, never a hang or garbage
+    good = tmp_path / "g.h5"
+    hdf5.save_keras_weights(str(good), {"a/kernel": np.ones((4, 4), np.float32)})
+    data = good.read_bytes()
+    p.write_bytes(data[:len(data) // 2])
+    with pytest.raises((ValueError, struct.error, IndexError, KeyError)):
+        hdf5.load_keras_weights(str(p))
