@@ -101,7 +101,8 @@ class FilterDetections(Layer):
         if not self.nms:
             self.nms_threshold = 0        # FilterDetections.py:170-171
         ob, os_, ol = _run(boxes, classification, self.class_specific_filter, self.score_threshold,
-                           self.max_detections, self.nms_threshold, self.nms)
+                           self.max_detections, self.nms_threshold,
+                           bool(self.nms) and self.nms_threshold > 0)     # iou_threshold <= 0 skips NMS (:11)
         host = hb and hc
         return [give_back(ob, host), give_back(os_, host), give_back(ol, host)]
 

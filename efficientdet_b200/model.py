@@ -319,9 +319,16 @@ class Model:
         a = np.ascontiguousarray(images, np.uint8 if u8 else np.float32)
         key = (a.shape, u8)
         if key not in self._pinned:
-            self._pinned[key] = torch.empty(a.shape, dtype=torch.uint8 if u8 else torch.float32).pin_memory()
-        self._pinned[key].numpy()[...] = a
-        return self._pinned[key].to(self.net.device, non_blocking=True)
+            self._pinned[key] = [torch.empty(a.shape, dtype=torch.uint8 if u8 else torch.float32).pin_memory(),
+                                 None]
+        slot = self._pinned[key]
+        if slot[1] is not None:
+            slot[1].synchronize()       # the previous async copy out of this buffer must have finished
+        slot[0].numpy()[...] = a
+        d = slot[0].to(self.net.device, non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record(torch.cuda.current_stream(self.net.device))
+        return d
 
     def predict_on_batch_device(self, x):
         """Same as predict_on_batch but returns CUDA tensors (no device->host copy)."""
@@ -456,8 +463,9 @@ class Model:
     # ---------------------------------------------------------------- training (train.py)
     def compile(self, optimizer=None, loss=None, **kw):
         from . import train
-        self.optimizer, self.loss = optimizer, loss
+        self.loss = loss
         self._trainer = train.Trainer(self, optimizer, loss)
+        self.optimizer = self._trainer.opt      # the default SGD when none was given (callbacks read .optimizer.lr)
 
     def train_on_batch(self, x, y):
         if self._trainer is None:

@@ -52,6 +52,20 @@ class TrainPlan(engine.Plan):
             self.drop_seed = (int(getattr(net, "seed", 0) or 0) * 1000003 + 7919 * rank + 12345) & (2 ** 63 - 1)
         super().__init__(net, batch, reuse_buffers=reuse_buffers, u8_input=u8_input)
 
+    def capture(self):
+        """Capturing warms the launch list up with one real run (engine.Plan.capture): that run has side effects
+        on a training plan -- it advances the BatchNorm moving averages and the stochastic-depth step counter --
+        so both are snapshotted and restored around it (the captured graph itself does not execute)."""
+        net = self.net
+        snap = net.flat.clone()
+        step = self.drop_step.clone() if self.drop_blocks else None
+        g = super().capture()
+        torch.cuda.current_stream(self.dev).synchronize()
+        net.flat.copy_(snap)
+        if step is not None:
+            self.drop_step.copy_(step)
+        return g
+
     # ------------------------------------------------------------------ small helpers
     def gw(self, key):
         return self.net.grads[key]
@@ -713,6 +727,14 @@ class TrainPlan(engine.Plan):
                                    gw(dkey).data_ptr(), dwp.ptr, nb, B, H, H, cmid, k, st, self.dtype),
                      p + "dw_bwd", flops=4 * k * k * B * Ho * Ho * cmid)
         if blk.expand_ratio == 1:
+            if blk.has_skip:
+                # no expand conv whose data-gradient epilogue could carry the residual branch (block1b.. of
+                # B1-B6): d(inp) = depthwise data gradient + d(out)   (efficientnet.py:297-304)
+                def make_skip_add():
+                    arr = (ctypes.c_void_p * 3)(d_xin.ptr, d_out.ptr, None)
+                    self._keepalive.append(arr)
+                    return _call("effdet_wbifpn_add", arr, 2, None, 0.0, d_xin.ptr, B * H * H * cin, self.dtype)
+                self.add("add", [d_xin, d_out], [d_xin], make_skip_add, p + "skip_grad_add")
             return
         bn_e = dict(rec["bn_e"]); bn_e["z"] = rec["z_e"]
         dz_e = self._bn_act_backward(bn_e, d_xin, p + "expand")
@@ -939,6 +961,7 @@ class Trainer:
                   net.velocity.data_ptr() + 4 * start, n, float(self.opt.current_lr()),
                   float(self.opt.momentum), float(scale), _lib.stream_ptr(net.device))
         self.opt.iterations += 1
+        net.invalidate()            # folded BN / static weight panels of the inference plans are stale now
 
     def _frozen_keys(self):
         net = self.net
@@ -952,19 +975,6 @@ class Trainer:
             if layer in fl or top in fl or (k.startswith("w_bi_fpn_add") and top in fl):
                 keys.append(k)
         return keys
-
-    def run_plan(self, plan, use_graph=True):
-        key = id(plan)
-        if use_graph and key not in self.graphs:
-            plan.run()                                  # eager warm-up (sets func attributes)
-            torch.cuda.synchronize(self.net.device)
-            # the warm-up advanced the BN moving averages once; that is a real (extra) step of
-            # statistics only when the caller discards this run, so restore them
-            self.graphs[key] = plan.capture()
-        if use_graph:
-            plan.graph.replay()
-        else:
-            plan.run()
 
     def targets_into_plan(self, plan, anchors_d, gt_d, gl_d, cnt_d, hw_d, kmax):
         """Row 12 on the device: writes regression / compact class targets straight into the
@@ -1025,9 +1035,13 @@ class Trainer:
         from .model import _is_u8
         plan = self.plan(B, dense, u8=_is_u8(images))     # uint8 = raw letterboxed RGB (utils.preprocess)
         self.load_batch(plan, images, targets)
-        plan.run()
+        if os.environ.get("EFFDET_EAGER_STEP") == "1":
+            plan.run()
+        else:
+            if plan.graph is None:
+                plan.capture()
+            plan.replay()           # the captured graph: the path bench.py times (fit_prefetched)
         self.apply_gradients()
-        self.net.invalidate()
         if not sync:
             return None
         out = plan.tensor(plan.loss_out).cpu().numpy()

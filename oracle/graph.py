@@ -106,6 +106,30 @@ def swish(x):
     return x * torch.sigmoid(x)
 
 
+def forced(x, force, name):
+    """Teacher forcing for the bf16 training-parity test: when `force` holds a tensor for `name` (NHWC, the value
+    the CUDA path stored for this activation), the forward value becomes exactly that tensor while the gradient
+    still flows to x (straight-through).  ReLU masks and max-pool routes of the backward pass are then those of
+    the CUDA forward, so the remaining gradient difference is the backward arithmetic alone (a 2^-9 relative
+    perturbation of a ReLU network's forward otherwise flips ~0.4 % of the masks per layer, which moves the
+    gradients by tens of per cent in L2 -- tests/test_gpu_train.py)."""
+    if force is None or name not in force:
+        return x
+    f = torch.as_tensor(force[name]).to(x.dtype).permute(0, 3, 1, 2)
+    assert f.shape == x.shape, (name, f.shape, x.shape)
+    return x + (f - x).detach()
+
+
+def relu_forced(pre, force, name):
+    """relu(pre); under teacher forcing the ReLU mask is the forced activation's (f > 0)."""
+    if force is None or name not in force:
+        return torch.relu(pre)
+    f = torch.as_tensor(force[name]).to(pre.dtype).permute(0, 3, 1, 2)
+    assert f.shape == pre.shape, (name, f.shape, pre.shape)
+    y = pre * (f > 0).to(pre.dtype)
+    return y + (f - y).detach()
+
+
 def upsample2(x):                                       # UpSampling2D(): nearest x2
     return x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
 
@@ -136,27 +160,27 @@ def mbconv(x, W, blk, bn_train, drop_scale=None, stats=None):
     return x
 
 
-def backbone(x, W, phi, bn_train=False, drop_scale=None, stats=None):
+def backbone(x, W, phi, bn_train=False, drop_scale=None, stats=None, force=None):
     blocks, taps = block_list(phi)
     x = conv2d(x, W["stem_conv/kernel"], 2)
     x = swish(batchnorm(x, W, "stem_bn", BN_EPS_BACKBONE, bn_train, stats))
     feats = []
     for i, blk in enumerate(blocks):
-        x = mbconv(x, W, blk, bn_train, drop_scale, stats)
+        x = forced(mbconv(x, W, blk, bn_train, drop_scale, stats), force, blk["prefix"] + "out")
         if i in taps:
             feats.append(x)
     return feats
 
 
 # ---------------------------------------------------------------- BiFPN
-def conv_block(x, W, name, k=1, s=1, bn_train=False, stats=None):          # model.py:71-90
+def conv_block(x, W, name, k=1, s=1, bn_train=False, stats=None, force=None):          # model.py:71-90
     x = conv2d(x, W[name + "_conv/kernel"], s)
-    return torch.relu(batchnorm(x, W, name + "_bn", BN_EPS_BIFPN, bn_train, stats))
+    return relu_forced(batchnorm(x, W, name + "_bn", BN_EPS_BIFPN, bn_train, stats), force, name)
 
 
-def dw_block(x, W, name, bn_train=False, stats=None):                      # model.py:48-68
+def dw_block(x, W, name, bn_train=False, stats=None, force=None):                      # model.py:48-68
     x = dwconv2d(x, W[name + "_dconv/depthwise_kernel"], 1)
-    return torch.relu(batchnorm(x, W, name + "_bn", BN_EPS_BIFPN, bn_train, stats))
+    return relu_forced(batchnorm(x, W, name + "_bn", BN_EPS_BIFPN, bn_train, stats), force, name)
 
 
 def fuse(inputs, W, weighted, name, eps=1e-4):                             # layers.py:26-31
@@ -172,8 +196,8 @@ def fuse(inputs, W, weighted, name, eps=1e-4):                             # lay
     return x / (w.sum() + eps)
 
 
-def bifpn_layer(feats, W, i, weighted, bn_train=False, stats=None):
-    kw = dict(bn_train=bn_train, stats=stats)
+def bifpn_layer(feats, W, i, weighted, bn_train=False, stats=None, force=None):
+    kw = dict(bn_train=bn_train, stats=stats, force=force)
     pre = "BiFPN_%d_" % i
     if i == 0:
         _, _, C3, C4, C5 = feats
@@ -198,38 +222,38 @@ def bifpn_layer(feats, W, i, weighted, bn_train=False, stats=None):
 
 
 # ---------------------------------------------------------------- heads
-def head(x, W, scope, trunk_fmt, final_name, depth):
+def head(x, W, scope, trunk_fmt, final_name, depth, force=None, level=0):
     for i in range(depth):
         n = scope + "/" + trunk_fmt % i
-        x = torch.relu(conv2d(x, W[n + "/kernel"], 1, W[n + "/bias"]))
+        x = relu_forced(conv2d(x, W[n + "/kernel"], 1, W[n + "/bias"]), force, "%s_%d_l%d" % (scope, i, level))
     n = scope + "/" + final_name
     return conv2d(x, W[n + "/kernel"], 1, W[n + "/bias"])
 
 
 def forward(W, images, phi, num_classes, weighted_bifpn=False, dtype=torch.float32,
             bn_train_bifpn=False, bn_train_backbone=False, drop_scale=None, taps=None,
-            stats=None):
+            stats=None, force=None):
     """images: (B,S,S,3) array/tensor.  W values may be numpy arrays or torch tensors
-    (leaf tensors with requires_grad for the training oracle).
+    (leaf tensors with requires_grad for the training oracle).  `force`: see forced().
     Returns (regression (B,N,4), classification (B,N,C)) torch tensors; `taps`, if a
     dict, receives NHWC copies of C1..C5 and every BiFPN layer's outputs."""
     x = torch.as_tensor(images).to(dtype).permute(0, 3, 1, 2)
-    feats = backbone(x, W, phi, bn_train_backbone, drop_scale, stats)
+    feats = backbone(x, W, phi, bn_train_backbone, drop_scale, stats, force)
     if taps is not None:
         for j, f in enumerate(feats):
             taps["C%d" % (j + 1)] = f.permute(0, 2, 3, 1).detach()
     depth = 3 + phi // 3
     for i in range(2 + phi):
-        feats = bifpn_layer(feats, W, i, weighted_bifpn, bn_train_bifpn, stats)
+        feats = bifpn_layer(feats, W, i, weighted_bifpn, bn_train_bifpn, stats, force)
         if taps is not None:
             for j, f in enumerate(feats):
                 taps["BiFPN_%d_P%d" % (i, j + 3)] = f.permute(0, 2, 3, 1).detach()
     B = x.shape[0]
     regs, clss = [], []
-    for f in feats:
-        r = head(f, W, "box_head", "regress_head_conv_%d", "regress_head_conv_final", depth)
+    for l, f in enumerate(feats):
+        r = head(f, W, "box_head", "regress_head_conv_%d", "regress_head_conv_final", depth, force, l)
         regs.append(r.permute(0, 2, 3, 1).reshape(B, -1, 4))
-        c = head(f, W, "class_head", "class_head_%d", "pyramid_classification", depth)
+        c = head(f, W, "class_head", "class_head_%d", "pyramid_classification", depth, force, l)
         clss.append(torch.sigmoid(c.permute(0, 2, 3, 1).reshape(B, -1, num_classes)))
     return torch.cat(regs, 1), torch.cat(clss, 1)
 

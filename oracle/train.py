@@ -28,7 +28,8 @@ def trainable_keys(W, freeze_backbone=True, freeze_bn=False):
 
 
 def loss_and_grads(W, images, reg_t, lab_t, phi, num_classes, weighted=False, freeze_bn=False,
-                   alpha=0.25, gamma=1.5, dtype=torch.float64, freeze_backbone=True, drop_scale=None):
+                   alpha=0.25, gamma=1.5, dtype=torch.float64, freeze_backbone=True, drop_scale=None,
+                   force=None):
     """-> (focal, smooth_l1, grads dict, bn batch stats dict name -> (mean, unbiased var)).
     drop_scale: {block prefix: (B,) keep/(1-rate)} = the FixedDropout draw of this step
     (efficientnet.py:300-304), or None for drop_connect_rate=0."""
@@ -40,7 +41,7 @@ def loss_and_grads(W, images, reg_t, lab_t, phi, num_classes, weighted=False, fr
     reg, cls = graph.forward(Wt, images, phi, num_classes, weighted, dtype=dtype,
                              bn_train_bifpn=not freeze_bn,
                              bn_train_backbone=(not freeze_backbone) and (not freeze_bn), stats=stats,
-                             drop_scale=drop_scale)
+                             drop_scale=drop_scale, force=force)
     fl = losses.focal(torch.as_tensor(lab_t).to(dtype), cls, alpha, gamma)
     sl = losses.smooth_l1(torch.as_tensor(reg_t).to(dtype), reg)
     (fl + sl).backward()

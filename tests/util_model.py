@@ -35,3 +35,34 @@ def rel_l2(got, want):
     got = np.asarray(got, np.float64)
     want = np.asarray(want, np.float64)
     return float(np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30))
+
+
+def golden_weight(key, shape, seed=0):
+    """Deterministic synthetic value of the Keras weight `key` ("[model/]layer/weight"): a pure function of
+    (key, shape, seed), shared by tests/golden/make_golden_graph.py (which feeds it to the reference's own
+    graph-construction code) and the parity tests (which feed it to the oracle and to the CUDA path), so the
+    fixtures only have to carry the weight manifest (names + shapes) and the outputs.  Scales keep activations
+    O(1) through ~100 layers: N(0, 1/fan_in) kernels, BN gamma~U(.5,1.5), beta / moving_mean~N(0,.1),
+    moving_variance~U(.5,1.5), biases~N(0,.05), fusion weights~U(-.2,1) (some negative: exercises the relu)."""
+    import zlib
+    rng = np.random.default_rng([zlib.crc32(key.encode()), int(seed)])
+    leaf = key.rsplit("/", 1)[1]
+    shape = tuple(int(s) for s in shape)
+    if leaf == "kernel":
+        fan_in = shape[0] * shape[1] * shape[2]
+        v = rng.standard_normal(shape) * np.sqrt(1.0 / fan_in)
+    elif leaf == "depthwise_kernel":
+        v = rng.standard_normal(shape) * np.sqrt(1.0 / (shape[0] * shape[1]))
+    elif leaf == "gamma":
+        v = rng.uniform(0.5, 1.5, shape)
+    elif leaf in ("beta", "moving_mean"):
+        v = rng.normal(0, 0.1, shape)
+    elif leaf == "moving_variance":
+        v = rng.uniform(0.5, 1.5, shape)
+    elif leaf == "bias":
+        v = rng.normal(0, 0.05, shape) - (2.0 if "pyramid_classification" in key else 0.0)
+    elif leaf.startswith("w_bi_fpn_add"):
+        v = rng.uniform(-0.2, 1.0, shape)
+    else:
+        raise KeyError(key)
+    return v.astype(np.float32)
