@@ -125,8 +125,18 @@ def run_ours(args, rank, world):
     hbm, tflops, peak_src = peaks()
     if kind == "train":
         import bench_train as T
-        return T.bench_train(args, rank, world, phi, B, C, dtype, weighted, dev,
-                             freeze_backbone=FREEZE_BACKBONE[args.workload])
+        out = T.bench_train(args, rank, world, phi, B, C, dtype, weighted, dev,
+                            freeze_backbone=FREEZE_BACKBONE[args.workload])
+        if args.workload == DEFAULT_WORKLOAD and not args.no_sub_records:
+            # north_star's SCALING config (BASELINE configs[3]: D4, batch 8 per GPU, nothing frozen, 100 MB of
+            # fp32 gradients all-reduced per step) measured in the same run at the same N, next to the headline
+            k4, phi4, B4, C4, dt4, w4 = WORKLOADS["d4_train_b8"]
+            sub_args = argparse.Namespace(**vars(args))
+            sub_args.steps, sub_args.warmup = max(5, args.steps // 2), max(3, args.warmup // 2)
+            out["d4_train_b8"] = T.bench_train(sub_args, rank, world, phi4, B4, C4, dt4, w4, dev,
+                                               freeze_backbone=False, workload="d4_train_b8", sub_record=True)
+            out["d4_train_b8"]["steps"] = sub_args.steps
+        return out
 
     S = IMAGE_SIZE_OVERRIDE.get(args.workload, [512, 640, 768, 896, 1024, 1280, 1408][phi])
     anchors = anchors_for_shape((S, S))
@@ -227,7 +237,7 @@ def run_ours(args, rank, world):
                 peak_source=peak_src,
                 per_kind_ms={k_: round(v["ms"], 4) for k_, v in sorted(by_kind.items())})
 
-    cpu = cpu_baseline_infer(phi, C, weighted, S, thr) if rank == 0 else None
+    cpu = cpu_baseline_infer(phi, C, weighted, S, thr) if (rank == 0 and world == 1) else None
     imgs = B * world * args.steps
     h2d = B * S * S * 3 * 4
     d2h = B * 300 * (16 + 4 + 4)
@@ -347,20 +357,31 @@ def run_reference(args, rank, world):
         return T.bench_train_reference(args, phi, B, C, weighted, FREEZE_BACKBONE[args.workload])
     W = _random_weights(phi, C, weighted)
     anchors = oa.anchors_for_shape((S, S)).astype(np.float32)
-    sample = max(1, min(B, 2))
-    img = synth_images(sample, S, 1, 1234)[0]
+    # the workload's own batch and the requested step counts when the run fits ~4 minutes; else whole steps of
+    # a smaller batch (the per-image rate of this CPU graph does not depend on the batch beyond ~2 images)
+    budget_s = 240.0
     with torch.no_grad():
-        r, c = graph.forward(W, img, phi, C, weighted)
+        probe = synth_images(1, S, 1, 1234)[0]
+        t0 = time.perf_counter()
+        r, c = graph.forward(W, probe, phi, C, weighted)
+        per_img = time.perf_counter() - t0
         flat = c[0].flatten()
         thr = float(torch.topk(flat, min(5000, flat.numel() - 1) + 1).values[-1])
-
+    warm = max(0, min(args.warmup, 1))
+    sample = B
+    while sample > 1 and per_img * sample * (args.steps + warm) > budget_s:
+        sample //= 2
+    steps = args.steps
+    while steps > 1 and per_img * sample * (steps + warm) > budget_s:
+        steps -= 1
+    img = synth_images(sample, S, 1, 1234)[0]
+    with torch.no_grad():
         def step():
             r, c = graph.forward(W, img, phi, C, weighted)
             boxes = tail.clip_boxes((sample, S, S, 3), tail.apply_bbox_deltas(anchors[None], r.numpy()))
             tail.filter_detections_batch(boxes, c.numpy(), score_threshold=thr)
-        for _ in range(min(args.warmup, 1)):
+        for _ in range(warm):
             step()
-        steps = max(1, min(args.steps, 5))
         t0 = time.perf_counter()
         for _ in range(steps):
             step()
@@ -368,11 +389,11 @@ def run_reference(args, rank, world):
     v = sample * steps / dt
     return {
         "impl": "reference", "metric": "images/sec", "value": v, "unit": "images/s", "n_gpus": world,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / steps * 1e3,
+        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (numpy default_rng images, random-init weights)",
         "config": {"workload": args.workload, "phi": phi, "image_size": S, "batch_per_gpu": B,
-                   "num_classes": C, "weighted_bifpn": weighted},
+                   "num_classes": C, "weighted_bifpn": weighted, "reference_batch": sample},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": "%d-image step(s) of the workload on torch-CPU fp32 (reference "
                                    "graph restated; TensorFlow not installable)" % sample},
@@ -401,6 +422,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-sub-records", action="store_true",
+                    help="headline workload only (skip the d4_train_b8 record inside the default line)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -28,7 +28,10 @@ def _synthetic_gt(B, S, C, seed):
     return ann
 
 
-def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev, freeze_backbone=True):
+def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev, freeze_backbone=True, workload=None,
+                sub_record=False):
+    """sub_record: the secondary workload reported inside the headline line (no uint8 leg, no CPU baseline)."""
+    workload = workload or args.workload
     import bench as bench_mod
     from efficientdet_b200.model import efficientdet
     from efficientdet_b200.optimizers import SGD
@@ -60,8 +63,7 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev, freeze_backb
     def core(i, imgs_dev, gt_dev, kmax):
         img_buf.copy_(imgs_dev, non_blocking=True)
         tr.targets_into_plan(plan, anchors_d, gt_dev[0], gt_dev[1], gt_dev[2], gt_dev[3], kmax)
-        plan.replay()
-        tr.apply_gradients()
+        tr.run_step(plan)
 
     def step_device(i):
         g = gts[i % n_sets]
@@ -123,37 +125,26 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev, freeze_backb
     ms_e2e = timed_e2e(args.steps)
     clk = clocks.stop() if clocks else {}
 
-    # the same end-to-end loop fed with raw letterboxed uint8 images (what train_tpu.py:170-183 decodes from the
-    # TFRecord PNGs): normalize_image runs on the device, the image upload is 3 B/pixel
-    rng8 = np.random.default_rng(4321 + rank)
-    pinned8 = [torch.from_numpy(rng8.integers(0, 256, (B, S, S, 3), dtype=np.uint8)).pin_memory()
-               for _ in range(n_sets)]
-    plan8 = tr.plan(B, dense=False, u8=True)
-    plan8.tensor(plan8.input_images).copy_(pinned8[0].to(dev))
-    g0 = gts[0]
-    tr.targets_into_plan(plan8, anchors_d, g0["dev"][0], g0["dev"][1], g0["dev"][2], g0["dev"][3], g0["kmax"])
-    plan8.replay()
-    tr.apply_gradients()
-    torch.cuda.synchronize(dev)
-    plan8.capture()
-
-    def run_e2e8(steps):
-        gen = ((pinned8[i % n_sets], gts[i % n_sets]["host"], gts[i % n_sets]["kmax"]) for i in range(steps))
-        for _ in tr.fit_prefetched(plan8, anchors_d, gen):
-            pass
-    run_e2e8(3)
-    gc.collect()
-    gc.freeze()
-    if world > 1:
-        torch.distributed.barrier()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(torch.cuda.current_stream(dev))
-    run_e2e8(args.steps)
-    e1.record(torch.cuda.current_stream(dev))
-    torch.cuda.synchronize(dev)
+    # the gradient all-reduce alone (the step's only collective), CUDA events, max over ranks
     from efficientdet_b200 import parallel as _par
-    ms_e2e8 = _par.max_over_ranks(e0.elapsed_time(e1), dev)
+    g_flat = model.net.grad_flat[0 if not freeze_backbone else model.net.backbone_end:]
+    allreduce_us = None
+    if world > 1:
+        for _ in range(3):
+            _par.allreduce_gradients_(g_flat)
+        torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(dev))
+        for _ in range(10):
+            _par.allreduce_gradients_(g_flat)
+        e1.record(torch.cuda.current_stream(dev))
+        torch.cuda.synchronize(dev)
+        allreduce_us = _par.max_over_ranks(e0.elapsed_time(e1), dev) / 10 * 1e3
+        g_flat.zero_()
+    ms_e2e8 = None
+    if not sub_record:
+        ms_e2e8 = _e2e_uint8(args, rank, world, tr, anchors_d, gts, n_sets, B, S, dev)
     losses = plan.tensor(plan.loss_out).cpu().numpy().tolist()
 
     prof = plan.profile(iters=3)
@@ -175,18 +166,21 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev, freeze_backb
     else:
         roof = dict(bound="hbm", achieved=dom["bytes"] / (dom["ms"] * 1e-3) / 1e9, peak=hbm, unit="GB/s")
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof.update(traffic=bench_mod.measured_traffic(args.workload, dom_kind), kernel=dom_kind, launches=dom["n"], share_of_step=dom["ms"] / total_ms,
+    roof.update(traffic=bench_mod.measured_traffic(workload, dom_kind), kernel=dom_kind, launches=dom["n"], share_of_step=dom["ms"] / total_ms,
                 peak_source=peak_src,
                 per_kind_ms={k_: round(v["ms"], 4) for k_, v in sorted(by_kind.items())})
-    cpu = cpu_baseline_train(phi, C, weighted, S, freeze_backbone=freeze_backbone) if rank == 0 else None
+    # the CPU leg runs on rank 0 at N=1 only (at N>1 the other ranks would spin in a barrier for its 12 s)
+    cpu = cpu_baseline_train(phi, C, weighted, S, freeze_backbone=freeze_backbone) \
+        if (rank == 0 and world == 1 and not sub_record) else None
     imgs = B * world * args.steps
     h2d = B * S * S * 3 * 4 + sum(t.numel() * t.element_size() for t in gts[0]["host"])
-    return {
+    grad_mb = 4 * g_flat.numel() / 1e6
+    out = {
         "metric": "images/sec", "value": imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": dtype,
         "data": "synthetic (numpy default_rng images + VOC-shaped boxes, random-init weights)",
-        "config": {"workload": args.workload, "phi": phi, "image_size": S, "batch_per_gpu": B,
+        "config": {"workload": workload, "phi": phi, "image_size": S, "batch_per_gpu": B,
                    "global_batch": B * world, "num_classes": C, "weighted_bifpn": weighted,
                    "freeze_backbone": freeze_backbone, "optimizer": "SGD(lr=.01, decay=4e-5, momentum=.9)",
                    "step": "device anchor targets -> forward (BN batch stats in %s) -> focal + "
@@ -195,19 +189,65 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev, freeze_backb
                               ("every layer", "heads + BiFPN + backbone")),
                    "l2": "inputs rotate over %d image sets (%.0f MB) > 126 MB L2; activations %.0f MB"
                          % (n_sets, n_sets * B * S * S * 12 / 1e6, plan.activation_bytes / 1e6),
-                   "parallelism": "dp%d (NCCL all-reduce of %.1f MB fp32 gradients)"
-                                  % (world, 4 * (model.net.flat.numel() -
-                                                 (model.net.backbone_end if freeze_backbone else 0)) / 1e6),
+                   "parallelism": "dp%d (NCCL all-reduce of %.1f MB fp32 gradients)" % (world, grad_mb),
                    "final_losses": losses[:2]},
+        "allreduce": {"mb": grad_mb, "us": allreduce_us,
+                      "note": "the flat trainable-gradient range, timed alone (10 calls, CUDA events, max over "
+                              "ranks); null at 1 GPU"},
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": 32},
-        "e2e_uint8": {"value": imgs / (ms_e2e8 * 1e-3), "unit": "images/s",
-                      "h2d_bytes_per_step": int(h2d - B * S * S * 9), "d2h_bytes_per_step": 32,
-                      "note": "same loop, raw letterboxed uint8 RGB input (train_tpu.py TFRecord format; "
-                              "normalize_image on the device)"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
     }
+    if ms_e2e8 is not None:
+        out["e2e_uint8"] = {"value": imgs / (ms_e2e8 * 1e-3), "unit": "images/s",
+                            "h2d_bytes_per_step": int(h2d - B * S * S * 9), "d2h_bytes_per_step": 32,
+                            "note": "same loop, raw letterboxed uint8 RGB input (train_tpu.py TFRecord format; "
+                                    "normalize_image on the device)"}
+    if sub_record:
+        for k in ("metric", "unit", "n_gpus", "steps", "warmup", "higher_is_better", "scaling", "vs_baseline",
+                  "data", "cpu_baseline", "clocks"):
+            out.pop(k, None)
+    # free this workload's plans before the next one is built
+    del plan, tr
+    model._trainer = None
+    torch.cuda.empty_cache()
+    return out
+
+
+def _e2e_uint8(args, rank, world, tr, anchors_d, gts, n_sets, B, S, dev):
+    """The same end-to-end loop fed with raw letterboxed uint8 images (what train_tpu.py:170-183 decodes from the
+    TFRecord PNGs): normalize_image runs on the device, the image upload is 3 B/pixel.  -> ms for args.steps."""
+    import gc
+    rng8 = np.random.default_rng(4321 + rank)
+    pinned8 = [torch.from_numpy(rng8.integers(0, 256, (B, S, S, 3), dtype=np.uint8)).pin_memory()
+               for _ in range(n_sets)]
+    plan8 = tr.plan(B, dense=False, u8=True)
+    plan8.tensor(plan8.input_images).copy_(pinned8[0].to(dev))
+    g0 = gts[0]
+    tr.targets_into_plan(plan8, anchors_d, g0["dev"][0], g0["dev"][1], g0["dev"][2], g0["dev"][3], g0["kmax"])
+    plan8.run()
+    tr.apply_gradients()
+    torch.cuda.synchronize(dev)
+    plan8.capture()
+
+    def run_e2e8(steps):
+        gen = ((pinned8[i % n_sets], gts[i % n_sets]["host"], gts[i % n_sets]["kmax"]) for i in range(steps))
+        for _ in tr.fit_prefetched(plan8, anchors_d, gen):
+            pass
+    run_e2e8(3)
+    gc.collect()
+    gc.freeze()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(torch.cuda.current_stream(dev))
+    run_e2e8(args.steps)
+    e1.record(torch.cuda.current_stream(dev))
+    torch.cuda.synchronize(dev)
+    from efficientdet_b200 import parallel as _par
+    return _par.max_over_ranks(e0.elapsed_time(e1), dev)
 
 
 def _cpu_train_step_fn(phi, C, weighted, S, batch, freeze_backbone=True):
@@ -250,11 +290,24 @@ def cpu_baseline_train(phi, C, weighted, S, budget_s=12.0, batch=2, freeze_backb
 def bench_train_reference(args, phi, B, C, weighted, freeze_backbone=True):
     S = [512, 640, 768, 896, 1024, 1280, 1408][phi]
     torch.set_num_threads(os.cpu_count())
-    batch = max(1, min(B, 2))
+    # the workload's own batch and the requested step counts when the run fits ~4 minutes (D0, batch 32: ~2.5 s
+    # per step on 16 cores); else whole steps of a smaller batch
+    budget_s = 240.0
+    probe = _cpu_train_step_fn(phi, C, weighted, S, 2, freeze_backbone)
+    probe()                                  # allocator / oneDNN primitive caches
+    t0 = time.perf_counter()
+    probe()
+    per_img = (time.perf_counter() - t0) / 2
+    warm = max(0, min(args.warmup, 1))
+    batch = B
+    while batch > 1 and per_img * batch * (args.steps + warm) > budget_s:
+        batch //= 2
+    steps = args.steps
+    while steps > 1 and per_img * batch * (steps + warm) > budget_s:
+        steps -= 1
     step = _cpu_train_step_fn(phi, C, weighted, S, batch, freeze_backbone)
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(warm):
         step()
-    steps = max(1, min(args.steps, 4))
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
@@ -262,11 +315,12 @@ def bench_train_reference(args, phi, B, C, weighted, freeze_backbone=True):
     v = batch * steps / dt
     return {
         "impl": "reference", "metric": "images/sec", "value": v, "unit": "images/s", "n_gpus": 1,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / steps * 1e3,
+        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic (numpy default_rng images + VOC-shaped boxes, random-init weights)",
         "config": {"workload": args.workload, "phi": phi, "image_size": S, "batch_per_gpu": B,
-                   "num_classes": C, "weighted_bifpn": weighted, "freeze_backbone": freeze_backbone},
+                   "num_classes": C, "weighted_bifpn": weighted, "freeze_backbone": freeze_backbone,
+                   "reference_batch": batch},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": "%d-image training steps on torch-CPU fp32 (reference graph restated; "
                                    "TensorFlow not installable)" % batch},

@@ -561,10 +561,14 @@ se_bwd_finish_kernel(const T *__restrict__ dyg, const float *__restrict__ gate, 
 template <typename T, int CV, int K>
 __global__ void dw_wgrad_general_kernel(const T *__restrict__ x, const T *__restrict__ dz, int B, int H, int W,
                                         int Ho, int Wo, int C, int stride, int pad_t, int pad_l,
-                                        int pix_per_block, float *__restrict__ partial) {
-    extern __shared__ float sred[];      // PY * K*K * C
-    const int nvec = C / CV, PY = blockDim.x / nvec;
-    const int cv = threadIdx.x % nvec, py = threadIdx.x / nvec, c = cv * CV;
+                                        int pix_per_block, int cvb, float *__restrict__ partial) {
+    // block (x, y): pixel range x, channel-vector chunk y of `cvb` vectors (wide layers -- D4..D6 reach 3456
+    // channels -- would otherwise need > 1024 threads of ~100 registers)
+    extern __shared__ float sred[];      // PY * K*K * cvb*CV
+    const int PY = blockDim.x / cvb, CC = cvb * CV;
+    const int cv = threadIdx.x % cvb, py = threadIdx.x / cvb;
+    const int c = (blockIdx.y * cvb + cv) * CV;
+    const bool active = c < C;
     const size_t total = (size_t)B * Ho * Wo;
     const size_t p0 = (size_t)blockIdx.x * pix_per_block;
     const size_t p1 = p0 + pix_per_block < total ? p0 + pix_per_block : total;
@@ -573,7 +577,7 @@ __global__ void dw_wgrad_general_kernel(const T *__restrict__ x, const T *__rest
     for (int t = 0; t < K * K; ++t)
 #pragma unroll
         for (int k = 0; k < CV; ++k) acc[t][k] = 0.f;
-    for (size_t p = p0 + py; p < p1; p += PY) {
+    for (size_t p = p0 + py; active && p < p1; p += PY) {
         const int ox = (int)(p % Wo), oy = (int)((p / Wo) % Ho);
         const size_t b = p / ((size_t)Wo * Ho);
         float g[CV];
@@ -596,12 +600,15 @@ __global__ void dw_wgrad_general_kernel(const T *__restrict__ x, const T *__rest
 #pragma unroll
     for (int t = 0; t < K * K; ++t)
 #pragma unroll
-        for (int k = 0; k < CV; ++k) sred[((size_t)py * K * K + t) * C + c + k] = acc[t][k];
+        for (int k = 0; k < CV; ++k) sred[((size_t)py * K * K + t) * CC + cv * CV + k] = acc[t][k];
     __syncthreads();
-    for (int i = threadIdx.x; i < K * K * C; i += blockDim.x) {
+    for (int i = threadIdx.x; i < K * K * CC; i += blockDim.x) {
+        const int tap = i / CC, cl = i - tap * CC;
+        const int cg = blockIdx.y * CC + cl;
+        if (cg >= C) continue;
         float t = 0.f;
-        for (int r = 0; r < PY; ++r) t += sred[(size_t)r * K * K * C + i];
-        partial[(size_t)blockIdx.x * K * K * C + i] = t;
+        for (int r = 0; r < PY; ++r) t += sred[(size_t)r * K * K * CC + i];
+        partial[((size_t)blockIdx.x * K * K + tap) * C + cg] = t;
     }
 }
 __global__ void sum_partials_warp_kernel(const float *__restrict__ partial, int nblk, int n,
@@ -1044,6 +1051,7 @@ extern "C" int effdet_dw_backward_blocks(int B, int H, int W, int C, int k, int 
     if (dtype == EFFDET_BF16) return dw_wgrad_bf16_splits(B, H, W, C, stride);
     const int CV = dtype == EFFDET_BF16 ? 8 : 4;
     int nvec = C / CV; if (nvec < 1) nvec = 1;
+    if (nvec > 128) nvec = 128;          // channel-vector chunk per block (see dw_wgrad_general_kernel)
     int PY = (k == 5 ? 64 : 128) / nvec; if (PY < 1) PY = 1;
     const size_t total = (size_t)B * ((H + stride - 1) / stride) * ((W + stride - 1) / stride);
     size_t ppb = (size_t)PY * 32;
@@ -1088,16 +1096,17 @@ extern "C" int effdet_dw_backward(const void *x, const void *dz, const float *ke
     }
     const int CV = dtype == EFFDET_BF16 ? 8 : 4;
     const int nvec = C / CV;
-    EFFDET_REQUIRE(nvec <= 1024, "C too large");
-    int PY = (k == 5 ? 64 : 128) / nvec; if (PY < 1) PY = 1;
+    const int cvb = nvec > 128 ? 128 : nvec;                 // channel vectors per block
+    const int cchunks = (nvec + cvb - 1) / cvb;
+    int PY = (k == 5 ? 64 : 128) / cvb; if (PY < 1) PY = 1;
     const size_t total = (size_t)B * Ho * Wo;
     const int ppb = (int)cdiv(total, nblk);
-    const size_t sm = (size_t)PY * k * k * C * sizeof(float);
+    const size_t sm = (size_t)PY * k * k * cvb * CV * sizeof(float);
 #define DWG(T, CVV, KK)                                                                                        \
     {                                                                                                          \
         auto kern = dw_wgrad_general_kernel<T, CVV, KK>;                                                       \
         if (sm > 48 * 1024) EFFDET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-        kern<<<nblk, nvec * PY, sm, st>>>((const T *)x, (const T *)dz, B, H, W, Ho, Wo, C, stride, pt, pl, ppb, partial); \
+        kern<<<dim3(nblk, cchunks), cvb * PY, sm, st>>>((const T *)x, (const T *)dz, B, H, W, Ho, Wo, C, stride, pt, pl, ppb, cvb, partial); \
     }
     if (dtype == EFFDET_F32) { if (k == 3) DWG(float, 4, 3) else DWG(float, 4, 5) }
     else if (dtype == EFFDET_BF16) { if (k == 3) DWG(__nv_bfloat16, 8, 3) else DWG(__nv_bfloat16, 8, 5) }

@@ -384,29 +384,42 @@ class Plan:
         return v.t[:v.nbytes].view(TORCH_DTYPE[v.dtype]).view(v.shape)
 
     # -------------------------------------------------------------- execution
-    def run(self):
+    def run(self, begin=0, end=None):
         stream = torch.cuda.current_stream(self.dev).cuda_stream
-        for op in self.ops:
+        for op in self.ops[begin:end]:
             op.fn(stream)
 
-    def capture(self):
-        """Capture the launch list in a CUDA graph (replay with .replay())."""
+    def capture(self, bounds=None):
+        """Capture the launch list in a CUDA graph (replay with .replay()).  bounds: ascending launch indices
+        [e0, e1, ..., len(ops)]: one graph per segment [0,e0), [e0,e1), ... (replay_segment(i)) so that the
+        caller can interleave work -- the per-bucket gradient all-reduce -- between them."""
         s = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
             self.run()              # warm-up outside capture
         torch.cuda.current_stream(self.dev).wait_stream(s)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.run()
-        self.graph = g
-        return g
+        bounds = list(bounds) if bounds else [len(self.ops)]
+        assert bounds[-1] == len(self.ops) and all(a < b for a, b in zip(bounds, bounds[1:]))
+        self.segment_graphs = []
+        begin = 0
+        for end in bounds:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run(begin, end)
+            self.segment_graphs.append(g)
+            begin = end
+        self.graph = self.segment_graphs[0] if len(self.segment_graphs) == 1 else self.segment_graphs
+        return self.graph
 
     def replay(self):
         if self.graph is None:
             self.run()
         else:
-            self.graph.replay()
+            for g in self.segment_graphs:
+                g.replay()
+
+    def replay_segment(self, i):
+        self.segment_graphs[i].replay()
 
     def profile(self, iters=3, repeat=8):
         """Per-launch device times -> list of dicts {name, kind, ms, bytes, flops}.

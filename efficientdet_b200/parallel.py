@@ -47,6 +47,31 @@ def allreduce_gradients_(flat_grads):
     return 1.0 / n
 
 
+def plan_buckets(marks, total, min_elems=1 << 20):
+    """Gradient buckets for the overlapped all-reduce.  The flat gradient buffer is laid out in creation
+    order (backbone, BiFPN, heads) and the backward pass produces it from the END: `marks` lists, in
+    backward-production order, (index one past the last launch of a backward segment, lowest flat index that
+    segment completes).  Returns [(launch_end, lo, hi)]: after launches [.., launch_end) have run,
+    flat[lo:hi) is final and can be all-reduced while the next segment computes.  Buckets smaller than
+    `min_elems` are merged into the following one (a collective has a fixed launch cost of tens of
+    microseconds); the last bucket always closes the range."""
+    out, hi = [], int(total)
+    for i, (launch_end, lo) in enumerate(marks):
+        lo = int(lo)
+        if lo > hi:
+            raise ValueError("bucket marks must descend through the flat buffer")
+        last = i == len(marks) - 1
+        if hi - lo >= min_elems or (last and hi > lo):
+            out.append((int(launch_end), lo, hi))
+            hi = lo
+        elif last:                       # nothing left to reduce: the trailing launches join the last bucket
+            if out:
+                out[-1] = (int(launch_end), out[-1][1], out[-1][2])
+            else:
+                out.append((int(launch_end), lo, lo))
+    return out
+
+
 def max_over_ranks(value, device=None):
     """Timing reduction used by bench.py: device time = max over ranks."""
     _, n = world()

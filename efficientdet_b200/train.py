@@ -59,7 +59,12 @@ class TrainPlan(engine.Plan):
         net = self.net
         snap = net.flat.clone()
         step = self.drop_step.clone() if self.drop_blocks else None
-        g = super().capture()
+        from . import parallel
+        self.buckets = None
+        if parallel.world()[1] > 1 or os.environ.get("EFFDET_FORCE_BUCKETS") == "1":
+            min_elems = int(os.environ.get("EFFDET_BUCKET_MIN_ELEMS", 1 << 20))
+            self.buckets = parallel.plan_buckets(self.bucket_marks, net.flat.numel(), min_elems)
+        g = super().capture([b[0] for b in self.buckets] if self.buckets else None)
         torch.cuda.current_stream(self.dev).synchronize()
         net.flat.copy_(snap)
         if step is not None:
@@ -439,18 +444,29 @@ class TrainPlan(engine.Plan):
                             masks=targets if li > 0 else None, accumulate=[a for _, a in gv],
                             shapes=[t.shape for t in targets], name=L["name"] + "_dgrad",
                             key=L["name"] + "/kernel")
+        # gradient buckets (parallel.plan_buckets): (launches done, lowest flat index final) after each segment
+        self.bucket_marks = [(len(self.ops), net.offsets["box_head/regress_head_conv_0/kernel"])]
         # ---- BiFPN (reverse tape)
         for rec in reversed(self.tape):
             if rec["kind"] == "node":
                 self._node_backward(rec)
             else:
                 self._convblock_backward(rec)
-        # ---- backbone (only when it is trained)
+        self.bucket_marks.append((len(self.ops), net.backbone_end))
+        # ---- backbone (only when it is trained): stages 7..5 hold ~85 % of its parameters and are
+        # back-propagated first, so their bucket is reduced under the (long) backward of stages 4..1
+        split = next((b.prefix for b in net.backbone.blocks if b.prefix.startswith("block5a")), None)
         for rec in reversed(self.bb_tape):
             if rec["kind"] == "mbconv":
                 self._mbconv_backward(rec)
+                if rec["blk"].prefix == split:
+                    first = next(k for k in net.offsets if k.startswith(split))
+                    self.bucket_marks.append((len(self.ops), net.offsets[first]))
             else:
                 self._stem_backward(rec)
+        if self.bb_tape:
+            self.bucket_marks.append((len(self.ops), 0))
+        self.bucket_marks[-1] = (len(self.ops), self.bucket_marks[-1][1])
 
     def _dgrad(self, x_single, xs, wt, cin, cout, dsts, targets, masks, accumulate, shapes, x_ld=None,
                x_bs=None, x_off=None, in_dtype=None, name="", key=None, extra_residual=None):
@@ -948,20 +964,60 @@ class Trainer:
             plan.tensor(plan.state_t).copy_(st)
             plan.tensor(plan.cls_t).copy_(cl)
 
+    def _reduce_and_update(self, lo, hi):
+        """flat[lo:hi): zero the gradients of frozen layers, SUM over replicas (NCCL over NVLink; the 1/replicas
+        factor rides in the SGD kernel), SGD-momentum update -- all on the current stream."""
+        net = self.net
+        for k in self._frozen_keys():          # layers.trainable = False outside the backbone
+            if lo <= net.offsets[k] < hi:
+                net.grads[k].zero_()
+        from . import parallel
+        g = net.grad_flat[lo:hi]
+        scale = parallel.allreduce_gradients_(g)
+        _lib.call("effdet_sgd_momentum_step", net.flat.data_ptr() + 4 * lo, g.data_ptr(),
+                  net.velocity.data_ptr() + 4 * lo, hi - lo, float(self.opt.current_lr()),
+                  float(self.opt.momentum), float(scale), _lib.stream_ptr(net.device))
+
     def apply_gradients(self):
         net = self.net
         start = 0 if getattr(self, "train_backbone", False) else net.backbone_end
-        g = net.grad_flat[start:]
-        for k in self._frozen_keys():          # layers.trainable = False outside the backbone
-            net.grads[k].zero_()
-        from . import parallel
-        scale = parallel.allreduce_gradients_(g)      # SUM over replicas (NCCL); 1/replicas below
-        n = g.numel()
-        _lib.call("effdet_sgd_momentum_step", net.flat.data_ptr() + 4 * start, g.data_ptr(),
-                  net.velocity.data_ptr() + 4 * start, n, float(self.opt.current_lr()),
-                  float(self.opt.momentum), float(scale), _lib.stream_ptr(net.device))
+        self._reduce_and_update(start, net.flat.numel())
         self.opt.iterations += 1
         net.invalidate()            # folded BN / static weight panels of the inference plans are stale now
+
+    def run_step(self, plan):
+        """One optimizer step on the batch already loaded into `plan`: forward + losses + backward (captured CUDA
+        graph) -> gradient all-reduce -> SGD.  With several replicas the backward is captured as segments
+        (heads | BiFPN | backbone stages 7-5 | stages 4-1 + stem) and each segment's gradient bucket is
+        all-reduced and applied on a second stream while the next segment computes -- the bucketed, overlapped
+        form of MirroredStrategy's per-step all-reduce (train_tpu.py:233-247)."""
+        if plan.graph is None:
+            plan.capture()
+        buckets = getattr(plan, "buckets", None)
+        if not buckets or len(buckets) == 1:
+            plan.replay()
+            self.apply_gradients()
+            return
+        net, dev = self.net, self.net.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_comm_stream", None) is None:
+            self._comm_stream = torch.cuda.Stream(dev)
+            self._seg_events = [torch.cuda.Event() for _ in range(8)]
+        comm = self._comm_stream
+        start = 0 if getattr(self, "train_backbone", False) else net.backbone_end
+        for i, (_, lo, hi) in enumerate(buckets):
+            plan.replay_segment(i)
+            lo = max(lo, start)
+            if hi <= lo:
+                continue
+            ev = self._seg_events[i]
+            ev.record(main)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev)
+                self._reduce_and_update(lo, hi)
+        main.wait_stream(comm)          # the next forward reads the updated weights
+        self.opt.iterations += 1
+        net.invalidate()
 
     def _frozen_keys(self):
         net = self.net
@@ -1024,8 +1080,7 @@ class Trainer:
             main.wait_event(ev)
             img_buf.copy_(d[0], non_blocking=True)
             self.targets_into_plan(plan, anchors_d, d[1], d[2], d[3], d[4], kmax)
-            plan.replay()
-            self.apply_gradients()
+            self.run_step(plan)
             yield plan.tensor(plan.loss_out).cpu()
             i += 1
 
@@ -1037,11 +1092,9 @@ class Trainer:
         self.load_batch(plan, images, targets)
         if os.environ.get("EFFDET_EAGER_STEP") == "1":
             plan.run()
+            self.apply_gradients()
         else:
-            if plan.graph is None:
-                plan.capture()
-            plan.replay()           # the captured graph: the path bench.py times (fit_prefetched)
-        self.apply_gradients()
+            self.run_step(plan)     # the captured graph(s): the path bench.py times (fit_prefetched)
         if not sync:
             return None
         out = plan.tensor(plan.loss_out).cpu().numpy()
