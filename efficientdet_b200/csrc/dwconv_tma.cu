@@ -27,6 +27,7 @@ constexpr int kRtH = 2, kRtW = 4;          // outputs per thread (register tile)
 struct alignas(64) DwTmaParams {
     CUtensorMap x_map;                     // (C, W, H, B) bf16, box (CB, IW, IH, 1)
     CUtensorMap w_map;                     // (C, K*K) f32,      box (CB, K*K)
+    CUtensorMap y_map;                     // (C, Wo, Ho, B) bf16, box (CB, TW, TH, 1): output tiles leave through TMA
     const float *scale, *shift;
     __nv_bfloat16 *y;
     float *se_sum;                         // [image][tile][C] sums of the outputs (SE squeeze), or NULL
@@ -60,12 +61,22 @@ template <int K, int S, int CP> struct DwCfg {
     static constexpr int IN_PAD = ((IN_BYTES + 127) / 128) * 128;       // TMA destinations are 128-byte aligned
     static constexpr int W_BYTES = K * K * CB * 4;
     static constexpr int STAGE_BYTES = ((IN_PAD + W_BYTES + 127) / 128) * 128;
-    static constexpr size_t SMEM = 2 * (size_t)STAGE_BYTES + 2 * 2 * 8 * CB * 4 + 64 + 128;
+    static constexpr int OUT_BYTES = TH * TW * CB * 2;                  // staged output tile [TH][TW][CB] bf16
+    static constexpr int OUT_PAD = ((OUT_BYTES + 127) / 128) * 128;
+    static constexpr size_t SMEM = 2 * (size_t)STAGE_BYTES + 2 * (size_t)OUT_PAD + 2 * 2 * 8 * CB * 4 + 64 + 128;
 };
 
-// 3x3: three CTAs per SM (the 64-channel block needs <= 80 registers for that; at two CTAs = 16 warps per SM the
-// kernel sat at 53 % issue utilisation with DRAM at 30-37 %, profiles/r1f_dwconv_ncu.txt)
-template <int K, int S, int CP, int ACT>
+enum { DW_SUMS_NONE = 0, DW_SUMS_SE = 1, DW_SUMS_STATS = 2 };
+
+// Epilogue (round 2): folded BN + activation in registers, bf16 pack, ONE 4-byte shared-memory store per output
+// pair into a staged [TH][TW][CB] tile; after the tile barrier one thread hands the tile to the TMA engine
+// (cp.async.bulk.tensor store: full 128-byte bursts, rows / columns / channels outside the tensor are clipped by
+// the tensor map).  The round-1 epilogue stored straight to global memory: per output pair a 64-bit address
+// IMAD chain, two bounds predicates and an STG -- 186 of the 330 issue slots of a 3x3 pass (profiles/
+// r2_dwconv_sass.txt); the kernel was issue-bound at 53 % with DRAM at 30-37 %.  Two staging tiles: the store of
+// tile i drains while tile i+1 is computed.  SUMS selects the per-tile reductions compiled in: none, the SE
+// squeeze sums, or sum + sum of squares (BatchNorm batch statistics of the following layer).
+template <int K, int S, int CP, int ACT, int SUMS>
 __global__ void __launch_bounds__(DwCfg<K, S, CP>::NT, (K == 3 ? 3 : 2))
 dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
     using Cfg = DwCfg<K, S, CP>;
@@ -73,7 +84,8 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
     extern __shared__ uint8_t dsm_raw[];
     // pointer arithmetic on the __shared__ array (not through uintptr_t) keeps LDS/STS addressing
     uint8_t *dsm = dsm_raw + ((128u - (smem_u32(dsm_raw) & 127u)) & 127u);
-    float *sRed = reinterpret_cast<float *>(dsm + 2 * Cfg::STAGE_BYTES);      // [2 parities][2 moments][8][CB]
+    uint8_t *sOut = dsm + 2 * Cfg::STAGE_BYTES;                                // [2][TH][TW][CB] bf16
+    float *sRed = reinterpret_cast<float *>(sOut + 2 * Cfg::OUT_PAD);          // [2 parities][2 moments][8][CB]
     uint64_t *full = reinterpret_cast<uint64_t *>(sRed + 2 * 2 * 8 * CB);
 
     const int tid = threadIdx.x;
@@ -119,6 +131,11 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
         }
         const uint8_t *sIn = dsm + (size_t)stage * Cfg::STAGE_BYTES;
         const float *sW = reinterpret_cast<const float *>(sIn + Cfg::IN_PAD);
+        uint8_t *so = sOut + (size_t)(it & 1) * Cfg::OUT_PAD + (size_t)pair * 4;
+        // rows / columns of this tile inside the output (edge tiles: the sums must skip the rest; the store is
+        // clipped by the tensor map)
+        const int vh = min(TH, p.Ho - ty * TH), vw = min(TW, p.Wo - tx * TW);
+        const bool whole = vh == TH && vw == TW;
         mbar_wait(&full[stage], (it >> 1) & 1);
 
         float2 wk[K * K];
@@ -155,49 +172,51 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
                             acc[orow][oc] = __ffma2_rn(in[oc * S + kx], wk[ky * K + kx], acc[orow][oc]);
                 }
             }
-            if (c_ok) {
+            uint8_t *srow = so + (size_t)(ry * TW + rx) * CB * 2;
 #pragma unroll
-                for (int orow = 0; orow < kRtH; ++orow) {
-                    const int oy = ty * TH + ry + orow;
-                    if (oy >= p.Ho) continue;
-                    __nv_bfloat16 *yrow = p.y + (((size_t)b * p.Ho + oy) * p.Wo) * p.C + c;
+            for (int orow = 0; orow < kRtH; ++orow) {
 #pragma unroll
-                    for (int oc = 0; oc < kRtW; ++oc) {
-                        const int ox = tx * TW + rx + oc;
-                        if (ox < p.Wo) {
-                            float2 z = __ffma2_rn(acc[orow][oc], sc, sh);
-                            if (ACT == EFFDET_ACT_SWISH) {
-                                z.x = fmaf(z.x, tanh_approx_f(z.x), z.x);
-                                z.y = fmaf(z.y, tanh_approx_f(z.y), z.y);
-                            } else if (ACT == EFFDET_ACT_RELU) {
-                                z.x = fmaxf(z.x, 0.f); z.y = fmaxf(z.y, 0.f);
-                            }
-                            tot.x += z.x; tot.y += z.y;
-                            tot2 = __ffma2_rn(z, z, tot2);
-                            *reinterpret_cast<__nv_bfloat162 *>(yrow + (size_t)ox * p.C) = __floats2bfloat162_rn(z.x, z.y);
+                for (int oc = 0; oc < kRtW; ++oc) {
+                    float2 z = __ffma2_rn(acc[orow][oc], sc, sh);
+                    if (ACT == EFFDET_ACT_SWISH) {
+                        z = __ffma2_rn(z, make_float2(tanh_approx_f(z.x), tanh_approx_f(z.y)), z);
+                    } else if (ACT == EFFDET_ACT_RELU) {
+                        z.x = fmaxf(z.x, 0.f); z.y = fmaxf(z.y, 0.f);
+                    }
+                    if (SUMS != DW_SUMS_NONE) {
+                        if (whole || (ry + orow < vh && rx + oc < vw)) {
+                            tot = __fadd2_rn(tot, z);
+                            if (SUMS == DW_SUMS_STATS) tot2 = __ffma2_rn(z, z, tot2);
                         }
                     }
+                    *reinterpret_cast<__nv_bfloat162 *>(srow + (size_t)(orow * TW + oc) * CB * 2) =
+                        __floats2bfloat162_rn(z.x, z.y);
                 }
             }
         }
-        if (p.se_sum || p.stats) {
-            float *red = sRed + (size_t)(it & 1) * 2 * 8 * CB;
+        fence_proxy_async();                       // this thread's staged outputs -> visible to the TMA engine
+        float *red = sRed + (size_t)(it & 1) * 2 * 8 * CB;
+        if (SUMS != DW_SUMS_NONE) {
             *reinterpret_cast<float2 *>(red + slot * CB + pair * 2) = tot;
-            if (p.stats) *reinterpret_cast<float2 *>(red + (8 + slot) * CB + pair * 2) = tot2;
-            __syncthreads();
+            if (SUMS == DW_SUMS_STATS) *reinterpret_cast<float2 *>(red + (8 + slot) * CB + pair * 2) = tot2;
+        }
+        if (tid == 0) tma_store_wait_read<0>();    // the previous tile's store has left the other staging tile
+        __syncthreads();                           // tile staged; everyone is done reading this input stage
+        if (tid == 0)
+            tma_store_4d(&p.y_map, sOut + (size_t)(it & 1) * Cfg::OUT_PAD, cb * CB, tx * TW, ty * TH, b);
+        if (SUMS != DW_SUMS_NONE) {
             const int moment = tid / CB, ch = tid - moment * CB;        // NT = 4 * CB threads
-            if (moment < (p.stats ? 2 : 1) && cb * CB + ch < p.C) {
+            if (moment < (SUMS == DW_SUMS_STATS ? 2 : 1) && cb * CB + ch < p.C) {
                 float s = 0.f;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) s += red[(moment * 8 + w) * CB + ch];
                 const size_t row = (size_t)b * p.tiles_x * p.tiles_y + (size_t)ty * p.tiles_x + tx;
-                if (p.stats) p.stats[(row * 2 + moment) * p.C + cb * CB + ch] = s;
+                if (SUMS == DW_SUMS_STATS) p.stats[(row * 2 + moment) * p.C + cb * CB + ch] = s;
                 else p.se_sum[row * p.C + cb * CB + ch] = s;
             }
-        } else {
-            __syncthreads();        // everyone is done reading this stage before it is refilled
         }
     }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // outstanding stores land before exit
 }
 
 template <int K, int S, int CP>
@@ -236,9 +255,19 @@ static int launch_dw_tma(const void *x, const float *w, const float *scale, cons
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_dwconv: cuTensorMapEncodeTiled(w) failed %s(%lld)", "", (long long)r);
     }
-#define DWT_LAUNCH(A)                                                                                      \
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * Wo, (cuuint64_t)C * 2 * Wo * Ho};
+        cuuint32_t box[4] = {(cuuint32_t)Cfg::CB, (cuuint32_t)Cfg::TW, (cuuint32_t)Cfg::TH, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = encode(&p.y_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, y, dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_dwconv: cuTensorMapEncodeTiled(y) failed %s(%lld)", "", (long long)r);
+    }
+#define DWT_LAUNCH(A, SU)                                                                                  \
     {                                                                                                      \
-        auto kern = dwconv_tma_kernel<K, S, CP, A>;                                                        \
+        auto kern = dwconv_tma_kernel<K, S, CP, A, SU>;                                                    \
         static int per_sm = 0;                                                                             \
         if (!per_sm) {                                                                                     \
             EFFDET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM)); \
@@ -250,10 +279,15 @@ static int launch_dw_tma(const void *x, const float *w, const float *scale, cons
         if (grid > p.total_tiles) grid = p.total_tiles;                                                    \
         EFFDET_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::NT), Cfg::SMEM, st, p));                        \
     }
-    if (act == EFFDET_ACT_SWISH) DWT_LAUNCH(EFFDET_ACT_SWISH)
-    else if (act == EFFDET_ACT_RELU) DWT_LAUNCH(EFFDET_ACT_RELU)
-    else if (act == EFFDET_ACT_NONE) DWT_LAUNCH(EFFDET_ACT_NONE)
-    else return fail(EFFDET_E_UNSUPPORTED, "effdet_dwconv: unsupported activation%s", "");
+    // compiled combinations: swish (+ SE squeeze sums) = MBConv forward; linear (+ BN batch statistics) = raw
+    // convolution of the training step / data gradients; ReLU = stand-alone DepthwiseConvBlock
+    if (stats && se_sum) return fail(EFFDET_E_INVALID, "effdet_dwconv: SE sums and BN statistics are exclusive%s", "");
+    if (act == EFFDET_ACT_SWISH && se_sum) DWT_LAUNCH(EFFDET_ACT_SWISH, DW_SUMS_SE)
+    else if (act == EFFDET_ACT_SWISH && !stats) DWT_LAUNCH(EFFDET_ACT_SWISH, DW_SUMS_NONE)
+    else if (act == EFFDET_ACT_NONE && stats) DWT_LAUNCH(EFFDET_ACT_NONE, DW_SUMS_STATS)
+    else if (act == EFFDET_ACT_NONE && !se_sum) DWT_LAUNCH(EFFDET_ACT_NONE, DW_SUMS_NONE)
+    else if (act == EFFDET_ACT_RELU && !stats && !se_sum) DWT_LAUNCH(EFFDET_ACT_RELU, DW_SUMS_NONE)
+    else return fail(EFFDET_E_UNSUPPORTED, "effdet_dwconv: unsupported activation / reduction combination%s", "");
 #undef DWT_LAUNCH
     EFFDET_LAUNCHED();
     return EFFDET_OK;
