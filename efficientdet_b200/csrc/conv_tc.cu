@@ -61,6 +61,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
 // rows are 128-byte lines (64 bf16), 8-row groups are 1024 bytes apart (SBO), LBO = 1 (unused).
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
@@ -595,14 +605,24 @@ gated_panel_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ pane
 // reduced in a fixed order by wgrad_reduce_kernel (deterministic).
 struct WgTcGroup {
     int H, W, Wt, Ht, Bt, tiles_x, tiles_y, tiles_b;
-    int n_tiles, split_begin, tiles_per_split;
+    int n_tiles, tile_begin;    // this group's pixel tiles are [tile_begin, tile_begin + n_tiles) of the flat list
+    int lw, lh, box_bytes;      // col_taps: log2(Wt), log2(Ht), bytes of one 64-channel activation box (with halo rows)
 };
 struct alignas(64) WgTcParams {
     CUtensorMap x_map[kTcMaxGroups];
     CUtensorMap z_map[kTcMaxGroups];
     WgTcGroup g[kTcMaxGroups];
     int n_groups, B, Cin, Cout, ksize, m_tiles, block_n, stages, tmem_cols;
+    int total_tiles, tiles_per_split;   // split-K over the FLAT list of pixel tiles of all groups: CTA x owns tiles
+                                        // [x * tiles_per_split, ...) -- equal work per CTA, one balanced wave
     int pair_taps;       // Cin <= 64: the two 64-channel halves of the M = 128 tile hold two different taps
+    int col_taps;        // 3x3, Cin > 64: one CTA = one kx and all three ky of a 128-channel block.  The activation
+                         // patch is loaded ONCE with a halo row above / below (box (64 ch, Wt, Ht + 2, Bt), zero fill
+                         // = SAME padding); tap ky is the dense pixel range starting ky rows in (Wt in {8, 16, 32}:
+                         // every 16-pixel K step starts on a swizzle-atom boundary), three accumulators of block_n
+                         // columns in TMEM.  Per 128 pixels 40 + 16 * ceil(bn / 64) KiB of shared-memory fill feed
+                         // 3 x 128 x bn x 128 MACs: 162 FLOP/B at bn = 112 instead of 83 for the per-tap form.
+    int a_box_stride;    // col_taps: bytes reserved per 64-channel activation box
     float *partial;
     float *bias_partial; // [split][Cout] or NULL: the spare half of the last pair multiplies ones -> sum of dz
 };
@@ -622,8 +642,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
     EFFDET_PDL_SYNC();
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int n_boxes = p.block_n / 64;
-    const int a_bytes = 2 * kATileBytes, b_bytes = n_boxes * kATileBytes;
+    const int n_boxes = (p.block_n + 63) / 64;
+    const int a_bytes = p.col_taps ? 2 * p.a_box_stride : 2 * kATileBytes, b_bytes = n_boxes * kATileBytes;
     uint8_t *sA = smem;
     uint8_t *sB = smem + (size_t)p.stages * a_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(sB + (size_t)p.stages * b_bytes);
@@ -632,17 +652,20 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    int gi = 0;
+    const int t_begin = (int)blockIdx.x * p.tiles_per_split;
+    const int t_end = min(t_begin + p.tiles_per_split, p.total_tiles);
+    auto group_of = [&](int T) {
+        int gi = 0;
 #pragma unroll
-    for (int i = 1; i < kTcMaxGroups; ++i)
-        if (i < p.n_groups && (int)blockIdx.x >= p.g[i].split_begin) gi = i;
-    const WgTcGroup &G = p.g[gi];
-    const int t_begin = ((int)blockIdx.x - G.split_begin) * G.tiles_per_split;
-    const int t_end = min(t_begin + G.tiles_per_split, G.n_tiles);
+        for (int i = 1; i < kTcMaxGroups; ++i)
+            if (i < p.n_groups && T >= p.g[i].tile_begin) gi = i;
+        return gi;
+    };
     const int taps_all = p.ksize * p.ksize;
     // pair_taps: rows 0..63 of the accumulator = tap 2*blockIdx.y, rows 64..127 = the next tap (both
     // over input channels 0..63), sharing one dz tile -- halves the operand traffic of the 64-channel
     // head convolutions
+    // col_taps: blockIdx.y = kx * m_tiles + m_tile; `tap` is then the ky = 0 tap of that column (kx)
     const int tap = p.pair_taps ? 2 * (int)blockIdx.y : (int)blockIdx.y / p.m_tiles;
     const int tap2 = p.pair_taps ? min(tap + 1, taps_all - 1) : tap;
     const int ci0 = p.pair_taps ? 0 : ((int)blockIdx.y % p.m_tiles) * 128;
@@ -678,12 +701,23 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
             for (int kb = 0; kb < num_k; ++kb) {
                 const int s = kb % p.stages, ph = (kb / p.stages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
-                int t = t_begin + kb;
+                const int gi = group_of(t_begin + kb);
+                const WgTcGroup &G = p.g[gi];
+                int t = t_begin + kb - G.tile_begin;
                 const int tx = t % G.tiles_x; t /= G.tiles_x;
                 const int ty = t % G.tiles_y; t /= G.tiles_y;
                 const int x0 = tx * G.Wt, y0 = ty * G.Ht, b0 = t * G.Bt;
-                mbar_expect_tx(&full[s], (uint32_t)(a_bytes + b_bytes - (ones_half ? kATileBytes : 0)));
                 uint8_t *a = sA + (size_t)s * a_bytes, *b = sB + (size_t)s * b_bytes;
+                if (p.col_taps) {
+                    // here `tap` = kx (blockIdx.y / m_tiles): column kx - 1, rows y0 - 1 .. y0 + Ht
+                    mbar_expect_tx(&full[s], (uint32_t)(2 * G.box_bytes + b_bytes));
+                    tma_load_4d(a, &p.x_map[gi], &full[s], ci0, x0 + tap - 1, y0 - 1, b0);
+                    tma_load_4d(a + p.a_box_stride, &p.x_map[gi], &full[s], ci0 + 64, x0 + tap - 1, y0 - 1, b0);
+                    for (int j = 0; j < n_boxes; ++j)
+                        tma_load_4d(b + (size_t)j * kATileBytes, &p.z_map[gi], &full[s], n0 + 64 * j, x0, y0, b0);
+                    continue;
+                }
+                mbar_expect_tx(&full[s], (uint32_t)(a_bytes + b_bytes - (ones_half ? kATileBytes : 0)));
                 tma_load_4d(a, &p.x_map[gi], &full[s], ci0, x0 + kx - pad, y0 + ky - pad, b0);
                 if (ones_half) { }
                 else if (p.pair_taps) tma_load_4d(a + kATileBytes, &p.x_map[gi], &full[s], 0, x0 + kx2 - pad, y0 + ky2 - pad, b0);
@@ -702,6 +736,24 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t a = smem_u32(sA + (size_t)s * a_bytes), b = smem_u32(sB + (size_t)s * b_bytes);
+                if (p.col_taps) {
+                    const WgTcGroup &G = p.g[group_of(t_begin + kb)];
+#pragma unroll 1
+                    for (int k = 0; k < 8; ++k) {
+                        const int pix = 16 * k;
+                        const int xx = pix & (G.Wt - 1), yy = (pix >> G.lw) & (G.Ht - 1), bb = pix >> (G.lw + G.lh);
+                        const uint32_t row0 = (uint32_t)((bb * (G.Ht + 2) + yy) * G.Wt + xx) * 128u;      // ky = 0
+                        const uint64_t db = make_mnmajor_sw128_desc(b + (uint32_t)k * 2048u, kATileBytes);
+#pragma unroll
+                        for (int kyy = 0; kyy < 3; ++kyy) {
+                            const uint64_t da = make_mnmajor_sw128_desc(a + row0 + (uint32_t)(kyy * G.Wt) * 128u,
+                                                                        (uint32_t)p.a_box_stride);
+                            umma_bf16(tmem_base + (uint32_t)(kyy * p.block_n), da, db, idesc, (kb | k) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                    continue;
+                }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {   // 128 pixels = 8 x UMMA_K(16); 16 pixel rows = 2048 bytes
                     const uint64_t da = make_mnmajor_sw128_desc(a + k * 2048, kATileBytes);
@@ -721,6 +773,24 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
             mbar_wait(tmem_full, 0);
             tc_fence_after();
         }
+        if (p.col_taps) {
+            // accumulator kyy (columns kyy * block_n ..) = tap (ky = kyy, kx = `tap`)
+            for (int kyy = 0; kyy < 3; ++kyy) {
+                float *o_tap = p.partial + ((size_t)blockIdx.x * taps_all + (kyy * 3 + tap)) * p.Cin * p.Cout;
+                for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+                    uint32_t r[16];
+                    __syncwarp();
+                    if (num_k > 0) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kyy * p.block_n + c0), r);
+                    if (ci < p.Cin) {
+                        float *o = o_tap + (size_t)ci * p.Cout + n0 + c0;
+                        const int nv = min(16, p.Cout - (n0 + c0));
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j < nv) o[j] = num_k > 0 ? __uint_as_float(r[j]) : 0.f;
+                    }
+                }
+            }
+        } else {
         float *out = p.partial + ((size_t)blockIdx.x * taps_all + min(otap, taps_all - 1)) * p.Cin * p.Cout;
         const bool row_ok = ci < p.Cin && otap < taps_all;
         for (int c0 = 0; c0 < p.block_n; c0 += 32) {
@@ -741,6 +811,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
                 for (int j = 0; j < 32; ++j)
                     if (j < nv) o[j] = num_k > 0 ? __uint_as_float(r[j]) : 0.f;
             }
+        }
         }
     }
     tc_fence_before();
@@ -763,12 +834,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
 // descriptors address it.  Two taps share one M = 128 instruction (LBO = distance between their
 // two 64-channel operands); the ninth tap is paired with a block of ones, which yields the bias
 // gradient.  Five accumulators of 64 columns live in TMEM.  ~76 KiB instead of 240 KiB per tile.
-struct WgHaloGroup { int Wt, Ht, Bt, lw, lh, tiles_x, tiles_y, n_tiles, split_begin, tiles_per_split, box_bytes; };
+struct WgHaloGroup { int Wt, Ht, Bt, lw, lh, tiles_x, tiles_y, n_tiles, tile_begin, box_bytes; };
 struct alignas(64) WgHaloParams {
     CUtensorMap x_map[kTcMaxGroups];
     CUtensorMap z_map[kTcMaxGroups];
     WgHaloGroup g[kTcMaxGroups];
     int n_groups, Cin, Cout, stages, box_stride;      // box_stride: bytes reserved per activation copy
+    int total_tiles, tiles_per_split;                 // flat split-K over all groups' tiles (see WgTcParams)
     float *partial, *bias_partial;
 };
 
@@ -785,13 +857,15 @@ conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    int gi = 0;
+    const int t_begin = (int)blockIdx.x * p.tiles_per_split;
+    const int t_end = min(t_begin + p.tiles_per_split, p.total_tiles);
+    auto group_of = [&](int T) {
+        int gi = 0;
 #pragma unroll
-    for (int i = 1; i < kTcMaxGroups; ++i)
-        if (i < p.n_groups && (int)blockIdx.x >= p.g[i].split_begin) gi = i;
-    const WgHaloGroup &G = p.g[gi];
-    const int t_begin = ((int)blockIdx.x - G.split_begin) * G.tiles_per_split;
-    const int t_end = min(t_begin + G.tiles_per_split, G.n_tiles);
+        for (int i = 1; i < kTcMaxGroups; ++i)
+            if (i < p.n_groups && T >= p.g[i].tile_begin) gi = i;
+        return gi;
+    };
     const int num_k = t_end - t_begin;
     const int n0 = blockIdx.y * 64;
 
@@ -814,7 +888,9 @@ conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
             for (int kb = 0; kb < num_k; ++kb) {
                 const int s = kb % p.stages, ph = (kb / p.stages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
-                int t = t_begin + kb;
+                const int gi = group_of(t_begin + kb);
+                const WgHaloGroup &G = p.g[gi];
+                int t = t_begin + kb - G.tile_begin;
                 const int tx = t % G.tiles_x; t /= G.tiles_x;
                 const int ty = t % G.tiles_y; t /= G.tiles_y;
                 const int x0 = tx * G.Wt, y0 = ty * G.Ht, b0 = t * G.Bt;
@@ -836,6 +912,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
                 const int s = kb % p.stages, ph = (kb / p.stages) & 1;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
+                const WgHaloGroup &G = p.g[group_of(t_begin + kb)];
                 const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t zb = st + 3u * (uint32_t)p.box_stride;
 #pragma unroll 1
@@ -1185,15 +1262,27 @@ static void pick_tile_halo(int W, int H, int B, int *Wt, int *Ht, int *Bt) {
     }
 }
 
+// 3x3, Cin > 64: column-of-taps form of conv_wgrad_tc_kernel (WgTcParams::col_taps)
+static bool wg_col(const effdet_wgrad_desc *d) {
+    return d->kh == 3 && d->kw == 3 && d->stride == 1 && d->Cin > 64 && getenv("EFFDET_NO_WGRAD_COL") == nullptr;
+}
+// N tile of the column-of-taps form: three accumulators must fit the 512 TMEM columns (<= 160 each, multiples of
+// 16 = the UMMA N granularity at M = 128); equal tiles so that no CTA is mostly padding
+static int wg_col_block_n(int Cout) {
+    const int nt = (Cout + 159) / 160;
+    return round_up((Cout + nt - 1) / nt, 16);
+}
+
 static int wg_tc_plan(const effdet_wgrad_desc *d, int *tiles_per_split_out, int *n_tiles_out, int *Wt, int *Ht,
                       int *Bt, int *block_n_out, int *m_tiles_out) {
     const int taps = d->kh * d->kw;
-    const int bn = d->Cout <= 256 ? round_up(d->Cout, 64) : 256;
+    const bool col = wg_col(d);
+    const int bn = col ? wg_col_block_n(d->Cout) : (d->Cout <= 256 ? round_up(d->Cout, 64) : 256);
     const int m_tiles = (d->Cin + 127) / 128, n_tiles_n = (d->Cout + bn - 1) / bn;
     long total_tiles = 0;
     const bool halo = wg_halo(d);
     for (int i = 0; i < d->n_groups; ++i) {
-        if (halo) pick_tile_halo(d->W[i], d->H[i], d->B, &Wt[i], &Ht[i], &Bt[i]);
+        if (halo || col) pick_tile_halo(d->W[i], d->H[i], d->B, &Wt[i], &Ht[i], &Bt[i]);
         else pick_tile(d->W[i], d->H[i], d->B, &Wt[i], &Ht[i], &Bt[i]);
         n_tiles_out[i] = (int)(cdiv(d->W[i], Wt[i]) * cdiv(d->H[i], Ht[i]) * cdiv(d->B, Bt[i]));
         total_tiles += n_tiles_out[i];
@@ -1201,16 +1290,17 @@ static int wg_tc_plan(const effdet_wgrad_desc *d, int *tiles_per_split_out, int 
     // ~2 CTAs per SM in flight (halo kernel: one CTA per SM, all taps in it; N tiles of 64);
     // at least 8 pixel tiles per CTA so the pipeline has work
     const long yz = halo ? (long)(d->Cout + 63) / 64
-                         : (long)((d->Cin <= 64 && taps > 1) ? (taps + 1) / 2 : taps * m_tiles) * n_tiles_n;
-    long want = ((long)kNumSMs * (halo ? 1 : 2) + yz - 1) / yz;
+                    : col ? (long)3 * m_tiles * n_tiles_n
+                          : (long)((d->Cin <= 64 && taps > 1) ? (taps + 1) / 2 : taps * m_tiles) * n_tiles_n;
+    // ONE balanced wave: splits * yz <= resident CTAs (1 per SM for the halo / column forms, 2 otherwise); the
+    // splits cut the FLAT tile list of all groups into equal ranges, so no CTA is a short remainder
+    long want = ((long)kNumSMs * ((halo || col) ? 1 : 2)) / yz;
     if (want < 1) want = 1;
     long tps = (total_tiles + want - 1) / want;
     if (tps < 8) tps = 8;
     *tiles_per_split_out = (int)tps;
     *block_n_out = bn; *m_tiles_out = m_tiles;
-    int splits = 0;
-    for (int i = 0; i < d->n_groups; ++i) splits += (int)cdiv(n_tiles_out[i], tps);
-    return splits;
+    return (int)cdiv(total_tiles, tps);
 }
 
 extern "C" int effdet_conv_wgrad_tc_fuses_bias(const effdet_wgrad_desc *d) {
@@ -1251,8 +1341,8 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
             g.Wt = Wt[i]; g.Ht = Ht[i]; g.Bt = Bt[i];
             g.lw = 31 - __builtin_clz(g.Wt); g.lh = 31 - __builtin_clz(g.Ht);
             g.tiles_x = cdiv(d->W[i], g.Wt); g.tiles_y = cdiv(d->H[i], g.Ht);
-            g.n_tiles = nt[i]; g.split_begin = zs; g.tiles_per_split = tps;
-            zs += (int)cdiv(nt[i], tps);
+            g.n_tiles = nt[i]; g.tile_begin = zs;
+            zs += nt[i];
             g.box_bytes = g.Wt * (g.Ht + 2) * g.Bt * 128;
             if (g.box_bytes > box_max) box_max = g.box_bytes;
             const long long ldz = d->dz_ld[i] ? d->dz_ld[i] : d->Cout;
@@ -1281,6 +1371,8 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
                 if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_conv_wgrad_tc: encode(dz) failed %s(%lld)", "", (long long)r);
             }
         }
+        hp.total_tiles = zs; hp.tiles_per_split = tps;
+        zs = splits;                                  // below: number of split rows
         hp.box_stride = round_up(box_max, 1024);
         const int stage_bytes = 3 * hp.box_stride + kATileBytes;
         hp.stages = (int)((220 * 1024 - hp.box_stride - 2048) / stage_bytes);
@@ -1308,9 +1400,15 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
     p.bias_partial = d->dbias ? d->partial + (size_t)splits * d->kh * d->kw * d->Cin * d->Cout : nullptr;
     p.pair_taps = (d->Cin <= 64 && d->kh * d->kw > 1) ? 1 : 0;
     EFFDET_REQUIRE(!d->dbias || effdet_conv_wgrad_tc_fuses_bias(d), "dbias only when effdet_conv_wgrad_tc_fuses_bias()");
-    p.tmem_cols = bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
-    const int stage_bytes = 2 * kATileBytes + (bn / 64) * kATileBytes;
-    int stages = (200 * 1024) / stage_bytes;
+    p.col_taps = wg_col(d) ? 1 : 0;
+    if (p.col_taps) {
+        int box_max = 0;
+        for (int i = 0; i < d->n_groups; ++i) box_max = max(box_max, Wt[i] * (Ht[i] + 2) * Bt[i] * 128);
+        p.a_box_stride = round_up(box_max, 1024);
+    }
+    p.tmem_cols = p.col_taps ? 512 : (bn <= 64 ? 64 : bn <= 128 ? 128 : 256);
+    const int stage_bytes = (p.col_taps ? 2 * p.a_box_stride : 2 * kATileBytes) + ((bn + 63) / 64) * kATileBytes;
+    int stages = ((p.col_taps ? 222 : 200) * 1024) / stage_bytes;
     if (stages > 4) stages = 4;
     if (stages < 1) stages = 1;
     p.stages = stages;
@@ -1320,20 +1418,23 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
         WgTcGroup &g = p.g[i];
         g.H = d->H[i]; g.W = d->W[i]; g.Wt = Wt[i]; g.Ht = Ht[i]; g.Bt = Bt[i];
         g.tiles_x = cdiv(g.W, g.Wt); g.tiles_y = cdiv(g.H, g.Ht); g.tiles_b = cdiv(d->B, g.Bt);
-        g.n_tiles = nt[i]; g.split_begin = z; g.tiles_per_split = tps;
-        z += (int)cdiv(nt[i], tps);
+        g.n_tiles = nt[i]; g.tile_begin = z;
+        g.lw = 31 - __builtin_clz(g.Wt); g.lh = 31 - __builtin_clz(g.Ht);
+        g.box_bytes = g.Wt * (g.Ht + 2) * g.Bt * 128;
+        z += nt[i];
         const long long ldz = d->dz_ld[i] ? d->dz_ld[i] : d->Cout;
         const long long zbs = d->dz_batch_stride[i] ? d->dz_batch_stride[i] : (long long)g.H * g.W * ldz;
         EFFDET_REQUIRE((ldz * 2) % 16 == 0 && (zbs * 2) % 16 == 0, "dz strides must be multiples of 16 bytes");
         EFFDET_REQUIRE(((reinterpret_cast<uintptr_t>(d->x[i]) | reinterpret_cast<uintptr_t>(d->dz[i])) & 15) == 0,
                        "operands must be 16-byte aligned");
         cuuint32_t box[4] = {64, (cuuint32_t)g.Wt, (cuuint32_t)g.Ht, (cuuint32_t)g.Bt};
+        cuuint32_t xbox[4] = {64, (cuuint32_t)g.Wt, (cuuint32_t)(g.Ht + (p.col_taps ? 2 : 0)), (cuuint32_t)g.Bt};
         cuuint32_t es[4] = {1, 1, 1, 1};
         {
             cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)d->B};
             cuuint64_t st[3] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cin * 2 * g.W, (cuuint64_t)d->Cin * 2 * g.W * g.H};
             CUresult r = encode(&p.x_map[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(d->x[i]), dims, st,
-                                box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                xbox, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(EFFDET_E_CUDA, "effdet_conv_wgrad_tc: encode(x) failed %s(%lld)", "", (long long)r);
         }
@@ -1354,7 +1455,9 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
         attr_set = true;
     }
     const int taps = d->kh * d->kw;
-    dim3 grid(z, p.pair_taps ? (taps + 1) / 2 : taps * mt, (d->Cout + bn - 1) / bn);
+    p.total_tiles = z; p.tiles_per_split = tps;
+    z = splits;
+    dim3 grid(z, p.col_taps ? 3 * mt : (p.pair_taps ? (taps + 1) / 2 : taps * mt), (d->Cout + bn - 1) / bn);
     cudaStream_t st = as_stream(stream);
     EFFDET_CUDA(launch_pdl(conv_wgrad_tc_kernel, dim3(grid), dim3(192), smem, st, p));
     EFFDET_LAUNCHED();

@@ -2,7 +2,9 @@ import sys, ctypes, numpy as np, torch
 sys.path.insert(0,'.')
 from efficientdet_b200 import _lib
 lib=_lib.load()
-cases={"d0trunk":(32,[64,32,16,8,4],64,64,64),"d0cls":(32,[64,32,16,8,4],64,180,184),"d0box":(32,[64,32,16,8,4],64,36,40)}
+cases={"d0trunk":(32,[64,32,16,8,4],64,64,64),"d0cls":(32,[64,32,16,8,4],64,180,184),"d0box":(32,[64,32,16,8,4],64,36,40),
+       "d4trunk":(8,[128,64,32,16,8],224,224,224),"d4cls":(8,[128,64,32,16,8],224,810,816),"d4box":(8,[128,64,32,16,8],224,36,40),
+       "d2trunk":(16,[96,48,24,12,6],112,112,112)}
 for name in (sys.argv[1:] or list(cases)):
     B,sizes,cin,cout,ldz=cases[name]
     d=_lib.WgradDesc(); d.n_groups=len(sizes); keep=[]
@@ -16,7 +18,7 @@ for name in (sys.argv[1:] or list(cases)):
     ns=lib.effdet_conv_wgrad_tc_splits(ctypes.byref(d))
     part=torch.empty(ns*(9*cin*cout+cout),device="cuda"); out=torch.empty((3,3,cin,cout),device="cuda"); db=torch.empty(cout,device="cuda")
     d.dweight,d.partial,d.n_splits,d.accumulate=out.data_ptr(),part.data_ptr(),ns,0
-    d.dbias=db.data_ptr()
+    d.dbias=db.data_ptr() if lib.effdet_conv_wgrad_tc_fuses_bias(ctypes.byref(d)) else None
     st=_lib.stream_ptr()
     f=lambda: _lib.call("effdet_conv_wgrad_tc",ctypes.byref(d),st)
     for _ in range(3): f()

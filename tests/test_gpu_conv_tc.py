@@ -191,7 +191,11 @@ def test_conv3x3_dgrad_tc_with_relu_mask_and_accumulate():
 
 @pytest.mark.parametrize("k,cin,cout,ldz,sizes,B", [(3, 64, 64, 64, [16, 8, 4, 2, 1], 4), (1, 112, 64, 64, [16], 2),
                                                       (3, 64, 36, 40, [8, 4], 3), (1, 320, 64, 64, [8], 2),
-                                                      (3, 88, 180, 184, [10, 5], 2), (3, 64, 810, 816, [4], 1)])
+                                                      (3, 88, 180, 184, [10, 5], 2), (3, 64, 810, 816, [4], 1),
+                                                      # D4 / D6 head widths: the column-of-taps form (Cin > 64)
+                                                      (3, 224, 224, 224, [32, 16, 8, 4, 2], 2),
+                                                      (3, 224, 810, 816, [16, 8], 1), (3, 224, 36, 40, [16, 4], 3),
+                                                      (3, 384, 384, 384, [22, 11], 1), (3, 160, 160, 160, [14, 7], 2)])
 def test_conv_wgrad_tc(k, cin, cout, ldz, sizes, B):
     """tcgen05 weight gradient with MN-major TMA-fed operands vs fp64 autograd on the same
     bf16-rounded operands (dz lives in channel-padded per-level buffers)."""
