@@ -116,6 +116,17 @@ _SIGNATURES = {
     "effdet_filter_detections": [c_void_p, c_void_p, c_int, c_size_t, c_int, c_float, c_float,
                                  c_int, c_int, c_int, c_void_p, c_size_t, c_size_t, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    # plan level (csrc/plan.cu)
+    "effdet_plan_create": [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.c_uint, c_void_p],
+    "effdet_plan_destroy": [c_void_p],
+    "effdet_plan_weight_info": [c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "effdet_plan_bind_weights": [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "effdet_plan_bind_weights_host": [c_void_p, c_void_p, c_void_p, c_int],
+    "effdet_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "effdet_plan_buffers": [c_void_p, c_void_p, c_void_p, c_void_p],
+    "effdet_detect": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                      c_void_p],
+    "effdet_detect_host": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p],
 }
 
 
@@ -192,6 +203,12 @@ def load():
     lib.effdet_stem_wgrad_blocks.argtypes = [c_int, c_int, c_int]
     lib.effdet_dwconv_se_blocks.restype = c_int
     lib.effdet_dwconv_se_blocks.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int]
+    lib.effdet_plan_num_anchors.restype = c_size_t
+    lib.effdet_plan_num_anchors.argtypes = [c_void_p]
+    lib.effdet_plan_num_weights.restype = c_int
+    lib.effdet_plan_num_weights.argtypes = [c_void_p]
+    lib.effdet_plan_num_launches.restype = c_int
+    lib.effdet_plan_num_launches.argtypes = [c_void_p]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args

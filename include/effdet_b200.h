@@ -417,6 +417,58 @@ int effdet_stem_wgrad_blocks(int B, int H, int W);
 int effdet_stem_wgrad(const float *images, const void *dz, float *dkernel, float *partial, int nblk, int B,
                       int H, int W, int C0, int dtype, void *stream);
 
+/* ---------------------------------------------------------------- plan level (whole model)
+ * What the reference's callers use: `model, prediction_model = efficientdet(phi, ...)` (model.py:356-452) and
+ * `prediction_model.predict_on_batch([images (, anchors)])` (inference.py:57-59, predict.py:101-105).
+ * A plan is the network lowered for a fixed (phi, image size, batch, classes, BiFPN kind, dtype) into a static
+ * list of this library's launches over plan-owned buffers, captured in a CUDA graph.  Not thread-safe per plan;
+ * one plan per (GPU, stream).  The caller owns every buffer it passes; the library owns the plan's workspace.
+ *
+ *   effdet_plan_create       phi 0..6 (model.py:367); image_size = image_sizes[phi] of model.py:29 or any multiple of
+ *                            128; dtype EFFDET_F32 (accuracy mode) | EFFDET_BF16 (speed mode, tcgen05 convolutions);
+ *                            flags: EFFDET_PLAN_U8_INPUT = images are the raw letterboxed uint8 RGB picture and
+ *                            normalize_image runs inside the stem; EFFDET_PLAN_NO_GRAPH = launch eagerly.
+ *   effdet_plan_weight_info  the weight manifest: Keras names "<layer>/<weight>" (nested heads "box_head/...",
+ *                            "class_head/...") and Keras shapes (conv HWIO, depthwise HWC1, BN vectors), in the
+ *                            creation order of the reference graph -- what `load_weights(by_name=True)` matches
+ *                            (train.py:329-332).
+ *   effdet_plan_bind_weights float32 DEVICE pointers by name (a trailing ":0" is accepted; unknown names are
+ *                            ignored like by_name=True).  The values are COPIED into the plan (asynchronously on
+ *                            `stream`); re-bind after the weights changed.  _host: the same from host memory.
+ *   effdet_forward           images (B,S,S,3) f32 (uint8 with EFFDET_PLAN_U8_INPUT), device -> regression (B,N,4) f32,
+ *                            classification (B,N,C) f32 (model.py:393-407).  Output pointers may be NULL: the
+ *                            results then stay in the plan's own buffers (effdet_plan_buffers).  Every weight must
+ *                            have been bound.  Enqueues only (graph launch).
+ *   effdet_detect            forward + RegressBoxes (mean 0, std 0.2) + ClipBoxes + FilterDetections (model.py:
+ *                            414-450): boxes (B,max_det,4) f32, scores (B,max_det) f32, labels (B,max_det) i32, padded
+ *                            with -1.  anchors (1,N,4) f32 device, or NULL = utils/anchors.py anchors_for_shape of the
+ *                            plan's image size (the `anchors=` baked form, model.py:414-419).  Synchronises the stream
+ *                            once (candidate-capacity word).  _host: host images / anchors / outputs, copies inside.
+ * The training step (losses, backward, optimizer) is lowered on the host side by efficientdet_b200/train.py over the
+ * per-layer entry points above. */
+typedef struct effdet_plan effdet_plan_t;
+#define EFFDET_PLAN_U8_INPUT 1u
+#define EFFDET_PLAN_NO_GRAPH 2u
+int effdet_plan_create(int phi, int image_size, int batch, int num_classes, int weighted_bifpn, int dtype,
+                       unsigned flags, effdet_plan_t **out);
+int effdet_plan_destroy(effdet_plan_t *plan);
+int effdet_plan_num_weights(const effdet_plan_t *plan);
+size_t effdet_plan_num_anchors(const effdet_plan_t *plan);
+int effdet_plan_num_launches(const effdet_plan_t *plan);
+int effdet_plan_weight_info(const effdet_plan_t *plan, int index, const char **name, int *ndim, int dims[4]);
+int effdet_plan_bind_weights(effdet_plan_t *plan, const char *const *names, const void *const *device_ptrs, int n,
+                             void *stream);
+int effdet_plan_bind_weights_host(effdet_plan_t *plan, const char *const *names, const void *const *host_ptrs, int n);
+int effdet_forward(effdet_plan_t *plan, const void *images, float *regression_out, float *classification_out,
+                   void *stream);
+int effdet_plan_buffers(effdet_plan_t *plan, void **images, float **regression, float **classification);
+int effdet_detect(effdet_plan_t *plan, const void *images, const float *anchors, float score_threshold,
+                  float iou_threshold, int max_detections, float *boxes_out, float *scores_out,
+                  int32_t *labels_out, void *stream);
+int effdet_detect_host(effdet_plan_t *plan, const void *images_host, const float *anchors_host,
+                       float score_threshold, float iou_threshold, int max_detections, float *boxes_host,
+                       float *scores_host, int32_t *labels_host);
+
 #ifdef __cplusplus
 }
 #endif
