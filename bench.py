@@ -23,7 +23,9 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (kind, phi, per-GPU batch, classes, dtype, weighted_bifpn)
-    "d0_infer_b1": ("infer", 0, 1, 90, "bf16", False),
+    "d0_infer_b1": ("infer", 0, 1, 90, "bf16", False),             # BASELINE configs[0] (speed mode)
+    "d0_infer_b1_fp32": ("infer", 0, 1, 90, "fp32", False),        # BASELINE configs[0] in the reference's precision
+    "d2_infer_b64_fp32": ("infer", 2, 64, 90, "fp32", False),      # BASELINE configs[2], fp32 leg
     "d0_infer_b32": ("infer", 0, 32, 20, "bf16", False),
     "d2_infer_b64": ("infer", 2, 64, 90, "bf16", False),
     "d0_train_b32": ("train", 0, 32, 20, "bf16", False),          # BASELINE configs[1] (frozen backbone)
@@ -136,9 +138,24 @@ def run_ours(args, rank, world):
             out["d4_train_b8"] = T.bench_train(sub_args, rank, world, phi4, B4, C4, dt4, w4, dev,
                                                freeze_backbone=False, workload="d4_train_b8", sub_record=True)
             out["d4_train_b8"]["steps"] = sub_args.steps
+            if world == 1:
+                # the other BASELINE configs (inference: replicas only, so 1 GPU says it all), same run, same box
+                for wl in ("d0_infer_b1", "d0_infer_b1_fp32", "d2_infer_b64", "d2_infer_b64_fp32", "d6_infer_b16"):
+                    out[wl] = bench_infer(sub_args, rank, world, wl, dev, sub_record=True)
         return out
+    return bench_infer(args, rank, world, args.workload, dev)
 
-    S = IMAGE_SIZE_OVERRIDE.get(args.workload, [512, 640, 768, 896, 1024, 1280, 1408][phi])
+
+def bench_infer(args, rank, world, workload, dev, sub_record=False):
+    import gc
+    import numpy as np
+    import torch
+    from efficientdet_b200 import _lib
+    from efficientdet_b200.model import efficientdet
+    from efficientdet_b200.utils.anchors import anchors_for_shape
+    kind, phi, B, C, dtype, weighted = WORKLOADS[workload]
+    hbm, tflops, peak_src = peaks()
+    S = IMAGE_SIZE_OVERRIDE.get(workload, [512, 640, 768, 896, 1024, 1280, 1408][phi])
     anchors = anchors_for_shape((S, S))
     model, pmodel = efficientdet(phi, num_classes=C, weighted_bifpn=weighted, dtype=dtype,
                                  anchors=anchors, drop_connect_rate=0, seed=2024 + rank, image_size=S)
@@ -193,29 +210,20 @@ def run_ours(args, rank, world):
         for _ in pmodel.predict_generator(pinned[i % n_sets] for i in range(steps)):
             pass
 
-    import gc                                  # see bench_train.py: no full collections inside the timed loops
-    gc.collect()
+    gc.collect()                               # see bench_train.py: no full collections inside the timed loops
     gc.freeze()
     clocks = Clocks(dev.index) if rank == 0 else None
     ms = timed(step_device, args.steps)
     run_e2e(steps=2)
     ms_e2e = timed(lambda i: run_e2e(steps=args.steps) if i == 0 else None, args.steps)
     clk = clocks.stop() if clocks else {}
+    # the network forward alone (graph replay): the difference to the full step is the detection tail
+    # (decode + clip + score threshold + per-class NMS + top-k, launched eagerly after the graph)
+    ms_fwd = timed(lambda i: plan.forward(dev_imgs[i % n_sets]), args.steps)
 
-    # the same end-to-end call fed with raw letterboxed uint8 images (utils.preprocess_image's output /
-    # the TFRecord PNGs of train_tpu.py): normalize_image runs inside the stem, the upload is 3 B/pixel
-    rng8 = np.random.default_rng(4321 + rank)
-    pinned8 = [torch.from_numpy(rng8.integers(0, 256, (B, S, S, 3), dtype=np.uint8)).pin_memory()
-               for _ in range(n_sets)]
-    net.plan(B, u8_input=True).capture()
-
-    def run_e2e8(steps):
-        for _ in pmodel.predict_generator(pinned8[i % n_sets] for i in range(steps)):
-            pass
-    run_e2e8(3)
-    gc.collect()
-    gc.freeze()
-    ms_e2e8 = timed(lambda i: run_e2e8(args.steps) if i == 0 else None, args.steps)
+    ms_e2e8 = None
+    if not sub_record:
+        ms_e2e8 = _infer_e2e_uint8(args, rank, net, pmodel, B, S, n_sets, timed)
 
     # dominant kernel (by share of the step) + its roofline, timed live with CUDA events
     prof = plan.profile(iters=3)
@@ -233,32 +241,65 @@ def run_ours(args, rank, world):
     else:
         roof = dict(bound="hbm", achieved=dom["bytes"] / (dom["ms"] * 1e-3) / 1e9, peak=hbm, unit="GB/s")
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof.update(traffic=measured_traffic(args.workload, dom_kind), kernel=dom_kind, launches=dom["n"], share_of_step=dom["ms"] / total_ms,
+    roof.update(traffic=measured_traffic(workload, dom_kind), kernel=dom_kind, launches=dom["n"], share_of_step=dom["ms"] / total_ms,
                 peak_source=peak_src,
                 per_kind_ms={k_: round(v["ms"], 4) for k_, v in sorted(by_kind.items())})
+    roof["per_kind_ms"]["tail_decode_clip_nms_topk"] = round(max(ms - ms_fwd, 0.0) / args.steps, 4)
 
-    cpu = cpu_baseline_infer(phi, C, weighted, S, thr) if (rank == 0 and world == 1) else None
+    cpu = cpu_baseline_infer(phi, C, weighted, S, thr) if (rank == 0 and world == 1 and not sub_record and not os.environ.get('EFFDET_BENCH_NO_CPU')) else None
     imgs = B * world * args.steps
     h2d = B * S * S * 3 * 4
     d2h = B * 300 * (16 + 4 + 4)
-    return {
+    out = {
         "metric": "images/sec", "value": imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
         "data": "synthetic (numpy default_rng images, random-init weights)",
-        "config": {"workload": args.workload, "phi": phi, "image_size": S, "batch_per_gpu": B,
+        "config": {"workload": workload, "phi": phi, "image_size": S, "batch_per_gpu": B,
                    "num_classes": C, "weighted_bifpn": weighted, "score_threshold": thr,
                    "l2": "inputs rotate over %d image sets (%.0f MB) > 126 MB L2; activations "
                          "%.0f MB" % (n_sets, n_sets * h2d / 1e6, plan.activation_bytes / 1e6),
                    "parallelism": "replicas only (batch sharded, no collective)"},
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
-        "e2e_uint8": {"value": imgs / (ms_e2e8 * 1e-3), "unit": "images/s", "h2d_bytes_per_step": B * S * S * 3,
-                      "d2h_bytes_per_step": d2h,
-                      "note": "same call, raw letterboxed uint8 RGB input (normalize_image fused into the stem)"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
     }
+    if ms_e2e8 is not None:
+        out["e2e_uint8"] = {"value": imgs / (ms_e2e8 * 1e-3), "unit": "images/s", "h2d_bytes_per_step": B * S * S * 3,
+                            "d2h_bytes_per_step": d2h,
+                            "note": "same call, raw letterboxed uint8 RGB input (normalize_image fused into the stem)"}
+    if sub_record:
+        for k in ("metric", "unit", "n_gpus", "warmup", "higher_is_better", "scaling", "vs_baseline", "data",
+                  "cpu_baseline", "clocks"):
+            out.pop(k, None)
+    del plan, pmodel, model, net, dev_imgs, pinned
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def _infer_e2e_uint8(args, rank, net, pmodel, B, S, n_sets, timed):
+    """The same end-to-end call fed with raw letterboxed uint8 images (utils.preprocess_image's output / the
+    TFRecord PNGs of train_tpu.py): normalize_image runs inside the stem, the upload is 3 B/pixel."""
+    import gc
+    import numpy as np
+    import torch
+    rng8 = np.random.default_rng(4321 + rank)
+    pinned8 = [torch.from_numpy(rng8.integers(0, 256, (B, S, S, 3), dtype=np.uint8)).pin_memory()
+               for _ in range(n_sets)]
+    net.plan(B, u8_input=True).capture()
+
+    def run_e2e8(steps):
+        for _ in pmodel.predict_generator(pinned8[i % n_sets] for i in range(steps)):
+            pass
+    run_e2e8(3)
+    gc.collect()
+    gc.freeze()
+    return timed(lambda i: run_e2e8(args.steps) if i == 0 else None, args.steps)
+
+
+
 
 
 def cpu_baseline_infer(phi, C, weighted, S, thr, budget_s=12.0, batch=1):

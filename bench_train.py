@@ -171,7 +171,7 @@ def bench_train(args, rank, world, phi, B, C, dtype, weighted, dev, freeze_backb
                 per_kind_ms={k_: round(v["ms"], 4) for k_, v in sorted(by_kind.items())})
     # the CPU leg runs on rank 0 at N=1 only (at N>1 the other ranks would spin in a barrier for its 12 s)
     cpu = cpu_baseline_train(phi, C, weighted, S, freeze_backbone=freeze_backbone) \
-        if (rank == 0 and world == 1 and not sub_record) else None
+        if (rank == 0 and world == 1 and not sub_record and not os.environ.get('EFFDET_BENCH_NO_CPU')) else None
     imgs = B * world * args.steps
     h2d = B * S * S * 3 * 4 + sum(t.numel() * t.element_size() for t in gts[0]["host"])
     grad_mb = 4 * g_flat.numel() / 1e6

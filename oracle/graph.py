@@ -1,7 +1,10 @@
 """Oracle: the reference Keras graph restated on torch-CPU (TEST INFRASTRUCTURE --
-see oracle/__init__.py).  PARITY UNPINNED for the network body: TensorFlow cannot
-run here, the reference ships no forward-pass fixtures; fidelity rests on the
-cited lines + SURVEY.md Appendix A (each TF behaviour sits behind one function).
+see oracle/__init__.py).  WIRING PINNED: tests/test_oracle_graph_golden.py checks
+this file against outputs of the reference's own model.py / efficientnet.py /
+layers.py executed unmodified under a torch-backed Keras stand-in (D0, D0 weighted,
+D1, D3 weighted: C3-C5, every BiFPN level, regression, classification to 2e-6).
+The arithmetic inside TensorFlow's kernels is restated from SURVEY.md Appendix A
+(each TF behaviour sits behind one function); TensorFlow itself cannot run here.
 
 Follows
   /root/reference/efficientnet.py:99-114 (block table) :191-207 (rounding)

@@ -1,5 +1,7 @@
 """Oracle: training losses + optimiser on torch-CPU (TEST INFRASTRUCTURE -- see
-oracle/__init__.py).  PARITY UNPINNED (no reference fixtures; TF not runnable).
+oracle/__init__.py).  PINNED for focal / smooth-L1 values and gradients on fixtures produced by
+executing the reference's utils/tpu.py (tests/golden/make_golden_losses.py, tests/
+test_oracle_losses_golden.py); the SGD step is parity unpinned (TF semantics, App. A.9).
 
 Restates /root/reference/utils/tpu.py:26-81 (tpu_smooth_l1, delta = lambda_ = 1),
 :84-155 (tpu_focal; call site train_tpu.py:259 uses alpha=.25, gamma=1.5) and the

@@ -1,5 +1,5 @@
 import sys, ctypes, numpy as np, torch
-sys.path.insert(0,'.')
+sys.path.insert(0,'.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 from efficientdet_b200 import _lib
 lib=_lib.load()
 cases={"b2":(8*256*256,144),"b3":(8*128*128,192),"b5":(8*64*64,672),"b6":(8*32*32,960),"b7":(8*32*32,1632)}

@@ -1,5 +1,5 @@
 import sys, ctypes, numpy as np, torch
-sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+sys.path.insert(0,'.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))); sys.path.insert(0,'tests')
 from efficientdet_b200 import _lib
 from test_gpu_conv_tc import _panel, _d
 cases={"expand2a":(32,256,16,96,1,2),"expand3a":(32,128,24,144,1,2),"project2b":(32,128,144,24,1,0),"head":(32,64,64,64,3,1),"project7a":(32,16,1152,320,1,0),

@@ -1,5 +1,5 @@
 import sys, ctypes, numpy as np, torch
-sys.path.insert(0,'.')
+sys.path.insert(0,'.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 from efficientdet_b200 import _lib
 cases={"b2a":(32,256,96,3,2),"b2b":(32,128,144,3,1),"b3a":(32,128,144,5,2),"b3b":(32,64,240,5,1),"b4b":(32,32,480,3,1),
        "b5b":(32,32,672,5,1),"b6a":(32,32,672,5,2),"b6b":(32,16,1152,5,1),"b1a":(32,256,32,3,1),"b7a":(32,16,1152,3,1)}

@@ -1,5 +1,5 @@
 import sys, ctypes, numpy as np, torch
-sys.path.insert(0,'.')
+sys.path.insert(0,'.'); sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 from efficientdet_b200 import _lib
 lib=_lib.load()
 cases={"d0trunk":(32,[64,32,16,8,4],64,64,64),"d0cls":(32,[64,32,16,8,4],64,180,184),"d0box":(32,[64,32,16,8,4],64,36,40),

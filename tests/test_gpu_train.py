@@ -304,7 +304,7 @@ def test_training_step_gradients(weighted, freeze_bn):
     """End to end against the fp64 autograd oracle.  Per-tensor relative L2 <= 5e-2: the oracle
     itself moves by up to ~1e-2 (L2) between fp32 and fp64 on this network because a handful of the
     ~10^7 ReLU units sit within rounding distance of zero and the detection gradients are carried
-    by few positive anchors (measured in scratch/dbg_cond.py); the kernels themselves are pinned
+    by few positive anchors (measured with the oracle alone, see tests/test_gpu_whole_model.py); the kernels themselves are pinned
     much tighter by the single-kernel tests above, which share the ReLU masks."""
     from efficientdet_b200.model import efficientdet, EFFICIENTNET_DEPTHS
     from efficientdet_b200.optimizers import SGD
