@@ -23,6 +23,9 @@
 namespace effdet {
 
 constexpr int kRtH = 2, kRtW = 4;          // outputs per thread (register tile)
+#ifndef EFFDET_DW_RTH
+#define EFFDET_DW_RTH 4
+#endif
 
 struct alignas(64) DwTmaParams {
     CUtensorMap x_map;                     // (C, W, H, B) bf16, box (CB, IW, IH, 1)
@@ -34,6 +37,7 @@ struct alignas(64) DwTmaParams {
     float *stats;                          // [image*tile][2][C] sum / sum of squares of the outputs (BN batch
                                            // statistics of the following BatchNormalization), or NULL
     int Ho, Wo, C, pad_t, pad_l, tiles_x, tiles_y, cblocks, total_tiles;
+    int run;                               // tiles a block takes in a row before it strides by gridDim.x runs
 };
 
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
@@ -48,15 +52,43 @@ __device__ __forceinline__ float tanh_approx_f(float x) {
     float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
 
+// Strided walk over tiles t = first, first + stride, ... with coordinates (x, y, c, b) = t decomposed over the
+// extents (nx, ny, nc): the stride is decomposed once and added with carries -- no integer division per tile
+// (a division per coordinate is an I2F / MUFU.RCP / IMAD.HI chain of ~35 dependent instructions).
+struct TileWalk {
+    int t, x, y, c, b;
+    int jx, jy, jc, jb, stride;
+    __device__ __forceinline__ void init(int first, int stride_, int nx, int ny, int nc) {
+        stride = stride_;
+        int r = stride_;
+        jx = r % nx; r /= nx; jy = r % ny; r /= ny; jc = r % nc; jb = r / nc;
+        t = first; r = first;
+        x = r % nx; r /= nx; y = r % ny; r /= ny; c = r % nc; b = r / nc;
+    }
+    __device__ __forceinline__ void next(int nx, int ny, int nc) {
+        t += stride;
+        x += jx; int carry = x >= nx; x -= carry ? nx : 0;
+        y += jy + carry; carry = y >= ny; y -= carry ? ny : 0;
+        c += jc + carry; carry = c >= nc; c -= carry ? nc : 0;
+        b += jb + carry;
+    }
+};
+
 // S = 1: 8 x 16 output tile, two register-tile passes per thread; S = 2: 8 x 8 tile, one pass
-template <int K, int S, int CP> struct DwCfg {
+// register-tile height of the forward kernel: 4 rows for the stride-1 kernels (a 4 x 4 tile reads (3+K)^2 words
+// for 16 outputs instead of (1+K)(3+K) for 8: 5x5 goes from 18 to 12 shared-memory load + unpack instructions per
+// output pair, below its 12.5 FFMA2, so the FMA pipe -- 2 cycles per FFMA2 -- becomes the limiter)
+template <int K, int S> struct FwdRt { static constexpr int H = S == 1 ? EFFDET_DW_RTH : 2; };
+
+template <int K, int S, int CP, int RTH = kRtH> struct DwCfg {
+    static constexpr int RT_H = RTH;
     static constexpr int TH = 8, TW = S == 1 ? 16 : 8;
     static constexpr int CB = CP * 2;
     static constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
-    static constexpr int NRT = (TH / kRtH) * (TW / kRtW);              // register tiles per tile
+    static constexpr int NRT = (TH / RTH) * (TW / kRtW);               // register tiles per tile
     static constexpr int PASSES = NRT / 8;
     static constexpr int NT = CP * 8;
-    static constexpr int IR = (kRtH - 1) * S + K, NIN = (kRtW - 1) * S + K;
+    static constexpr int IR = (RTH - 1) * S + K, NIN = (kRtW - 1) * S + K;
     static constexpr int IN_BYTES = IH * IW * CB * 2;
     static constexpr int IN_PAD = ((IN_BYTES + 127) / 128) * 128;       // TMA destinations are 128-byte aligned
     static constexpr int W_BYTES = K * K * CB * 4;
@@ -77,9 +109,10 @@ enum { DW_SUMS_NONE = 0, DW_SUMS_SE = 1, DW_SUMS_STATS = 2 };
 // tile i drains while tile i+1 is computed.  SUMS selects the per-tile reductions compiled in: none, the SE
 // squeeze sums, or sum + sum of squares (BatchNorm batch statistics of the following layer).
 template <int K, int S, int CP, int ACT, int SUMS>
-__global__ void __launch_bounds__(DwCfg<K, S, CP>::NT, (K == 3 ? 3 : 2))
+__global__ void __launch_bounds__(DwCfg<K, S, CP, FwdRt<K, S>::H>::NT, (K == 3 ? 3 : 2))
 dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
-    using Cfg = DwCfg<K, S, CP>;
+    using Cfg = DwCfg<K, S, CP, FwdRt<K, S>::H>;
+    constexpr int RTH = Cfg::RT_H;
     constexpr int CB = Cfg::CB, IW = Cfg::IW, NIN = Cfg::NIN, IR = Cfg::IR, TW = Cfg::TW, TH = Cfg::TH;
     extern __shared__ uint8_t dsm_raw[];
     // pointer arithmetic on the __shared__ array (not through uintptr_t) keeps LDS/STS addressing
@@ -97,11 +130,15 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
     __syncthreads();
     EFFDET_PDL_SYNC();
 
-    auto issue = [&](int t, int stage) {
-        int r = t;
-        const int tx = r % p.tiles_x; r /= p.tiles_x;
-        const int ty = r % p.tiles_y; r /= p.tiles_y;
-        const int cb = r % p.cblocks; const int b = r / p.cblocks;
+    // Tile order: x, y, channel block, image.  Block i takes runs of p.run consecutive tiles: run i, i + grid, ...
+    // (block-cyclic), so the tiles in flight at any time are neighbours -- halo rows and the 128-byte lines two
+    // channel blocks share are L2 hits (a contiguous range per block measured 2.3x the algorithmic DRAM reads on
+    // 48-channel blocks) -- while a block still sees the same channel block for a whole run.  Tile coordinates
+    // advance by add-with-carry of a pre-decomposed step: round 1 decomposed every tile index with three integer
+    // divisions, twice (once for the TMA issue): 195 of the instructions of a 5x5 tile but 31 % of its stall
+    // samples (profiles/r2_dwconv_ncu.txt: I2F / MUFU.RCP / IMAD.HI chains ahead of the barrier wait).  The K*K
+    // weights and the folded-BN constants are re-read into registers only when the channel block changes.
+    auto issue = [&](int tx, int ty, int cb, int b, int stage) {
         uint8_t *dst = dsm + (size_t)stage * Cfg::STAGE_BYTES;
         mbar_expect_tx(&full[stage], (uint32_t)(Cfg::IN_BYTES + Cfg::W_BYTES));
         tma_load_4d(dst, &p.x_map, &full[stage], cb * CB, tx * TW * S - p.pad_l, ty * TH * S - p.pad_t, b);
@@ -109,26 +146,44 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
     };
 
     const int pair = tid % CP, slot = tid / CP;        // slot 0..7: which register tile of a pass
-
-    if (tid == 0 && (int)blockIdx.x < p.total_tiles) issue(blockIdx.x, 0);
-    int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    const int run = p.run;
+    // step from the last tile of a run to the first tile of this block's next run, decomposed once
+    int jx, jy, jc, jb;
+    {
+        int r = (int)(gridDim.x - 1) * run + 1;
+        jx = r % p.tiles_x; r /= p.tiles_x;
+        jy = r % p.tiles_y; r /= p.tiles_y;
+        jc = r % p.cblocks; jb = r / p.cblocks;
+    }
+    int tx, ty, cb, b;                                 // current tile
+    int nt = blockIdx.x * run, ntx, nty, ncb, nb, nk = 0;   // next tile to issue: index, coordinates, position in run
+    {
+        int r = nt;
+        ntx = r % p.tiles_x; r /= p.tiles_x;
+        nty = r % p.tiles_y; r /= p.tiles_y;
+        ncb = r % p.cblocks; nb = r / p.cblocks;
+    }
+    auto advance = [&]() {
+        const bool hop = ++nk == run;
+        if (hop) nk = 0;
+        nt += hop ? (int)(gridDim.x - 1) * run + 1 : 1;
+        ntx += hop ? jx : 1;
+        int carry = ntx >= p.tiles_x; ntx -= carry ? p.tiles_x : 0;
+        nty += (hop ? jy : 0) + carry;
+        carry = nty >= p.tiles_y; nty -= carry ? p.tiles_y : 0;
+        ncb += (hop ? jc : 0) + carry;
+        carry = ncb >= p.cblocks; ncb -= carry ? p.cblocks : 0;
+        nb += (hop ? jb : 0) + carry;
+    };
+    if (tid == 0 && nt < p.total_tiles) issue(ntx, nty, ncb, nb, 0);
+    int it = 0, cur_cb = -1;
+    float2 wk[K * K];
+    float2 sc = make_float2(0.f, 0.f), sh = make_float2(0.f, 0.f);
+    while (nt < p.total_tiles) {
         const int stage = it & 1;
-        if (tid == 0 && t + (int)gridDim.x < p.total_tiles) issue(t + gridDim.x, stage ^ 1);
-        int r = t;
-        const int tx = r % p.tiles_x; r /= p.tiles_x;
-        const int ty = r % p.tiles_y; r /= p.tiles_y;
-        const int cb = r % p.cblocks; const int b = r / p.cblocks;
-        const int c = cb * CB + pair * 2;
-        const bool c_ok = c < p.C;
-        // per-channel epilogue constants (swish: the 1/2 of z/2 * (1 + tanh(z/2)) is folded in)
-        float2 sc = make_float2(0.f, 0.f), sh = make_float2(0.f, 0.f);
-        if (c_ok) {
-            const float pre = ACT == EFFDET_ACT_SWISH ? 0.5f : 1.f;
-            sc = *reinterpret_cast<const float2 *>(p.scale + c);
-            sh = *reinterpret_cast<const float2 *>(p.shift + c);
-            sc.x *= pre; sc.y *= pre; sh.x *= pre; sh.y *= pre;
-        }
+        tx = ntx; ty = nty; cb = ncb; b = nb;
+        advance();
+        if (tid == 0 && nt < p.total_tiles) issue(ntx, nty, ncb, nb, stage ^ 1);
         const uint8_t *sIn = dsm + (size_t)stage * Cfg::STAGE_BYTES;
         const float *sW = reinterpret_cast<const float *>(sIn + Cfg::IN_PAD);
         uint8_t *so = sOut + (size_t)(it & 1) * Cfg::OUT_PAD + (size_t)pair * 4;
@@ -136,20 +191,33 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
         // clipped by the tensor map)
         const int vh = min(TH, p.Ho - ty * TH), vw = min(TW, p.Wo - tx * TW);
         const bool whole = vh == TH && vw == TW;
+        const bool new_cb = cb != cur_cb;
+        if (new_cb) {
+            cur_cb = cb;
+            const int c = cb * CB + pair * 2;
+            // per-channel epilogue constants (swish: the 1/2 of z/2 * (1 + tanh(z/2)) is folded in)
+            sc = make_float2(0.f, 0.f); sh = make_float2(0.f, 0.f);
+            if (c < p.C) {
+                const float pre = ACT == EFFDET_ACT_SWISH ? 0.5f : 1.f;
+                sc = *reinterpret_cast<const float2 *>(p.scale + c);
+                sh = *reinterpret_cast<const float2 *>(p.shift + c);
+                sc.x *= pre; sc.y *= pre; sh.x *= pre; sh.y *= pre;
+            }
+        }
         mbar_wait(&full[stage], (it >> 1) & 1);
-
-        float2 wk[K * K];
+        if (new_cb) {
 #pragma unroll
-        for (int i = 0; i < K * K; ++i) wk[i] = *reinterpret_cast<const float2 *>(sW + i * CB + pair * 2);
+            for (int i = 0; i < K * K; ++i) wk[i] = *reinterpret_cast<const float2 *>(sW + i * CB + pair * 2);
+        }
 
         float2 tot = make_float2(0.f, 0.f), tot2 = make_float2(0.f, 0.f);
 #pragma unroll 1
         for (int pass = 0; pass < Cfg::PASSES; ++pass) {
             const int rt = pass * 8 + slot;
-            const int ry = (rt / (TW / kRtW)) * kRtH, rx = (rt % (TW / kRtW)) * kRtW;   // output origin in the tile
-            float2 acc[kRtH][kRtW];
+            const int ry = (rt / (TW / kRtW)) * RTH, rx = (rt % (TW / kRtW)) * kRtW;   // output origin in the tile
+            float2 acc[RTH][kRtW];
 #pragma unroll
-            for (int i = 0; i < kRtH; ++i)
+            for (int i = 0; i < RTH; ++i)
 #pragma unroll
                 for (int j = 0; j < kRtW; ++j) acc[i][j] = make_float2(0.f, 0.f);
             const uint8_t *base = sIn + ((size_t)((ry * S) * IW + rx * S) * CB + pair * 2) * 2;
@@ -162,7 +230,7 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
                     in[j] = make_float2(__uint_as_float(w2 << 16), __uint_as_float(w2 & 0xffff0000u));
                 }
 #pragma unroll
-                for (int orow = 0; orow < kRtH; ++orow) {
+                for (int orow = 0; orow < RTH; ++orow) {
                     const int ky = rr - orow * S;
                     if (ky < 0 || ky >= K) continue;
 #pragma unroll
@@ -174,7 +242,7 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
             }
             uint8_t *srow = so + (size_t)(ry * TW + rx) * CB * 2;
 #pragma unroll
-            for (int orow = 0; orow < kRtH; ++orow) {
+            for (int orow = 0; orow < RTH; ++orow) {
 #pragma unroll
                 for (int oc = 0; oc < kRtW; ++oc) {
                     float2 z = __ffma2_rn(acc[orow][oc], sc, sh);
@@ -215,6 +283,7 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
                 else p.se_sum[row * p.C + cb * CB + ch] = s;
             }
         }
+        ++it;
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // outstanding stores land before exit
 }
@@ -222,7 +291,7 @@ dwconv_tma_kernel(const __grid_constant__ DwTmaParams p) {
 template <int K, int S, int CP>
 static int launch_dw_tma(const void *x, const float *w, const float *scale, const float *shift, void *y,
                          float *se_sum, float *stats, int B, int H, int W, int C, int act, cudaStream_t st) {
-    using Cfg = DwCfg<K, S, CP>;
+    using Cfg = DwCfg<K, S, CP, FwdRt<K, S>::H>;
     EncodeTiledFn encode = get_encode();
     if (!encode) return fail(EFFDET_E_CUDA, "effdet_dwconv: cuTensorMapEncodeTiled unavailable%s", "");
     DwTmaParams p;
@@ -277,6 +346,10 @@ static int launch_dw_tma(const void *x, const float *w, const float *scale, cons
         }                                                                                                  \
         int grid = kNumSMs * per_sm;                                                                       \
         if (grid > p.total_tiles) grid = p.total_tiles;                                                    \
+        /* runs: at least ~4 per block (balance), at most 8 tiles long */                                  \
+        p.run = p.total_tiles / (grid * 4);                                                                \
+        if (const char *e = getenv("EFFDET_DW_RUN")) p.run = atoi(e);                                      \
+        p.run = p.run < 1 ? 1 : (p.run > 8 ? 8 : p.run);                                                   \
         EFFDET_CUDA(launch_pdl(kern, dim3(grid), dim3(Cfg::NT), Cfg::SMEM, st, p));                        \
     }
     // compiled combinations: swish (+ SE squeeze sums) = MBConv forward; linear (+ BN batch statistics) = raw
@@ -328,10 +401,7 @@ dw_wgrad_tma_kernel(const __grid_constant__ DwWgParams p) {
     __syncthreads();
     EFFDET_PDL_SYNC();
     const int cb = blockIdx.y;
-    auto issue = [&](int t, int stage) {
-        int r = t;
-        const int tx = r % p.tiles_x; r /= p.tiles_x;
-        const int ty = r % p.tiles_y; const int b = r / p.tiles_y;
+    auto issue = [&](int tx, int ty, int b, int stage) {
         uint8_t *dst = dsm + (size_t)stage * STAGE;
         mbar_expect_tx(&full[stage], (uint32_t)(Cfg::IN_BYTES + Z_BYTES));
         tma_load_4d(dst, &p.x_map, &full[stage], cb * CB, tx * TW * S - p.pad_l, ty * TH * S - p.pad_t, b);
@@ -342,11 +412,14 @@ dw_wgrad_tma_kernel(const __grid_constant__ DwWgParams p) {
 #pragma unroll
     for (int i = 0; i < K * K; ++i) acc[i] = make_float2(0.f, 0.f);
 
-    if (tid == 0 && (int)blockIdx.x < p.spatial_tiles) issue(blockIdx.x, 0);
+    TileWalk nxt;                                      // the tile to issue next (x, y, image; c unused)
+    nxt.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y, 1 << 30);
+    if (tid == 0 && nxt.t < p.spatial_tiles) issue(nxt.x, nxt.y, nxt.c, 0);
     int it = 0;
-    for (int t = blockIdx.x; t < p.spatial_tiles; t += gridDim.x, ++it) {
+    for (; nxt.t < p.spatial_tiles; ++it) {
         const int stage = it & 1;
-        if (tid == 0 && t + (int)gridDim.x < p.spatial_tiles) issue(t + gridDim.x, stage ^ 1);
+        nxt.next(p.tiles_x, p.tiles_y, 1 << 30);
+        if (tid == 0 && nxt.t < p.spatial_tiles) issue(nxt.x, nxt.y, nxt.c, stage ^ 1);
         const uint8_t *sIn = dsm + (size_t)stage * STAGE;
         const uint8_t *sZ = sIn + Cfg::IN_PAD;
         mbar_wait(&full[stage], (it >> 1) & 1);
@@ -505,11 +578,7 @@ bifpn_node_tma_kernel(const __grid_constant__ NodeParams p) {
     __syncthreads();
     EFFDET_PDL_SYNC();
 
-    auto issue = [&](int t, int stage) {
-        int r = t;
-        const int tx = r % p.tiles_x; r /= p.tiles_x;
-        const int ty = r % p.tiles_y; r /= p.tiles_y;
-        const int cb = r % p.cblocks; const int b = r / p.cblocks;
+    auto issue = [&](int tx, int ty, int cb, int b, int stage) {
         uint8_t *dst = dsm + (size_t)stage * Cfg::STAGE_BYTES;
         const int x0 = tx * TW - 1, y0 = ty * TH - 1;
         mbar_expect_tx(&full[stage], (uint32_t)(Cfg::F_BYTES * (p.has_in2 ? 2 : 1) + Cfg::S_BYTES + Cfg::W_BYTES));
@@ -529,15 +598,15 @@ bifpn_node_tma_kernel(const __grid_constant__ NodeParams p) {
     const int pair = tid % CP, slot = tid / CP;
     auto unpack = [](uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); };
 
-    if (tid == 0 && (int)blockIdx.x < p.total_tiles) issue(blockIdx.x, 0);
+    TileWalk nxt;
+    nxt.init(blockIdx.x, gridDim.x, p.tiles_x, p.tiles_y, p.cblocks);
+    if (tid == 0 && nxt.t < p.total_tiles) issue(nxt.x, nxt.y, nxt.c, nxt.b, 0);
     int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    for (; nxt.t < p.total_tiles; ++it) {
         const int stage = it & 1;
-        if (tid == 0 && t + (int)gridDim.x < p.total_tiles) issue(t + gridDim.x, stage ^ 1);
-        int r = t;
-        const int tx = r % p.tiles_x; r /= p.tiles_x;
-        const int ty = r % p.tiles_y; r /= p.tiles_y;
-        const int cb = r % p.cblocks; const int b = r / p.cblocks;
+        const int tx = nxt.x, ty = nxt.y, cb = nxt.c, b = nxt.b;
+        nxt.next(p.tiles_x, p.tiles_y, p.cblocks);
+        if (tid == 0 && nxt.t < p.total_tiles) issue(nxt.x, nxt.y, nxt.c, nxt.b, stage ^ 1);
         const int c = cb * CB + pair * 2;
         const bool c_ok = c < p.C;
         float2 sc = make_float2(0.f, 0.f), sh = make_float2(0.f, 0.f);
