@@ -56,9 +56,11 @@ def measured_traffic(workload, kernel):
         e = json.load(open(p)).get(workload)
     except (OSError, ValueError):
         return None
-    if not e or e.get("kernel") != kernel:
+    if not e:
         return None
-    return e["bytes_per_launch"]
+    if e.get("kernel") == kernel:                 # round-1 layout: one kernel per workload
+        return e["bytes_per_launch"]
+    return (e.get(kernel) or {}).get("bytes_per_launch")
 
 
 class Clocks:

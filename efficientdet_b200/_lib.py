@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libeffdet_b200.so")
+# EFFDET_B200_LIB: another build of the same library (A/B timing of two kernel versions inside one GPU job)
+LIB_PATH = os.environ.get("EFFDET_B200_LIB") or os.path.join(HERE, "libeffdet_b200.so")
 
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED = 0, -1, -2, -3, -4
 F32, BF16 = 0, 1

@@ -840,8 +840,10 @@ struct alignas(64) WgHaloParams {
     CUtensorMap z_map[kTcMaxGroups];
     WgHaloGroup g[kTcMaxGroups];
     int n_groups, Cin, Cout, stages, box_stride;      // box_stride: bytes reserved per activation copy
+    int ksteps, z_bytes;                              // 16-pixel K steps per tile (4 or 8), bytes of the dz tile
     int total_tiles, tiles_per_split;                 // flat split-K over all groups' tiles (see WgTcParams)
     float *partial, *bias_partial;
+    int dbg;                                          // EFFDET_WG_DBG: 1 no MMAs, 2 one activation copy, 4 no partial stores (timing experiments)
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -849,7 +851,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
     EFFDET_PDL_SYNC();
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int stage_bytes = 3 * p.box_stride + kATileBytes;          // 3 activation copies + dz tile
+    const int stage_bytes = 3 * p.box_stride + p.z_bytes;            // 3 activation copies + dz tile
     uint8_t *sOnes = smem + (size_t)p.stages * stage_bytes;          // box_stride bytes of bf16 1.0
     uint64_t *full = reinterpret_cast<uint64_t *>(sOnes + p.box_stride);
     uint64_t *empty = full + p.stages;
@@ -895,10 +897,12 @@ conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
                 const int ty = t % G.tiles_y; t /= G.tiles_y;
                 const int x0 = tx * G.Wt, y0 = ty * G.Ht, b0 = t * G.Bt;
                 uint8_t *st = smem + (size_t)s * stage_bytes;
-                mbar_expect_tx(&full[s], (uint32_t)(3 * G.box_bytes + kATileBytes));
+                const int ncopy = (p.dbg & 2) ? 1 : 3;
+                mbar_expect_tx(&full[s], (uint32_t)(ncopy * G.box_bytes + p.z_bytes));
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx)
-                    tma_load_4d(st + (size_t)kx * p.box_stride, &p.x_map[gi], &full[s], 0, x0 - 1 + kx, y0 - 1, b0);
+                    if (kx < ncopy)
+                        tma_load_4d(st + (size_t)kx * p.box_stride, &p.x_map[gi], &full[s], 0, x0 - 1 + kx, y0 - 1, b0);
                 tma_load_4d(st + 3 * (size_t)p.box_stride, &p.z_map[gi], &full[s], n0, x0, y0, b0);
             }
         }
@@ -915,25 +919,40 @@ conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
                 const WgHaloGroup &G = p.g[group_of(t_begin + kb)];
                 const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t zb = st + 3u * (uint32_t)p.box_stride;
-#pragma unroll 1
-                for (int k = 0; k < 8; ++k) {                 // 16-pixel K steps of the 128-pixel tile
-                    const int pix = 16 * k;
-                    const int xx = pix & (G.Wt - 1), yy = (pix >> G.lw) & (G.Ht - 1), bb = pix >> (G.lw + G.lh);
-                    const uint32_t row0 = (uint32_t)((bb * (G.Ht + 2) + yy) * G.Wt + xx) * 128u;   // tap ky = 0
-                    const uint64_t db = make_mnmajor_sw128_desc(zb + (uint32_t)k * 2048u, kATileBytes);
+                // Descriptors are built once per tile: the five tap-pair operands differ from K step to K step only
+                // in their start address, i.e. by an addition to the descriptor's 14-bit address field (the sums stay
+                // below 256 KiB, so nothing carries into the LBO field).  Measured (EFFDET_WG_DBG experiments, D0
+                // trunk gradient): the 400 MMAs of a CTA cost 11.5 us = ~56 cycles each whether N is 32, 64 or 128 and
+                // whether the issue loop has 9 or 30 instructions per MMA -- a per-instruction floor of the tensor
+                // pipe at M = 128, K = 16; the other 21 us are loads (7.5), partial stores (5.7), the split-K
+                // reduction and the prologue.
+                const uint32_t wt128 = (uint32_t)G.Wt * 128u;
+                uint64_t da0[5];
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) {
-                        // operand slots u = kx * 3 + ky are ordered by shared-memory address (copy kx, then
-                        // ky rows in), so the second half of a pair always lies above the first (LBO > 0)
-                        const int ua = 2 * j, ub = 2 * j + 1;
-                        const uint32_t aa = st + (uint32_t)(ua / 3) * (uint32_t)p.box_stride + row0 +
-                                            (uint32_t)((ua % 3) * G.Wt) * 128u;
-                        // second half: slot ub, or (j == 4) the block of ones at the same relative offset
-                        const uint32_t ab = ub < 9 ? st + (uint32_t)(ub / 3) * (uint32_t)p.box_stride + row0 +
-                                                         (uint32_t)((ub % 3) * G.Wt) * 128u
-                                                   : ones_addr + row0;
-                        const uint64_t da = make_mnmajor_sw128_desc(aa, ab - aa);
-                        umma_bf16(tmem_base + (uint32_t)(j * 64), da, db, idesc, (kb | k) ? 1u : 0u);
+                for (int j = 0; j < 5; ++j) {
+                    // operand slots u = kx * 3 + ky are ordered by shared-memory address (copy kx, then
+                    // ky rows in), so the second half of a pair always lies above the first (LBO > 0)
+                    const int ua = 2 * j, ub = 2 * j + 1;
+                    const uint32_t aa = st + (uint32_t)(ua / 3) * (uint32_t)p.box_stride + (uint32_t)(ua % 3) * wt128;
+                    // second half: slot ub, or (j == 4) the block of ones at the same relative offset
+                    const uint32_t ab = ub < 9 ? st + (uint32_t)(ub / 3) * (uint32_t)p.box_stride + (uint32_t)(ub % 3) * wt128
+                                               : ones_addr;
+                    da0[j] = make_mnmajor_sw128_desc(aa, ab - aa);
+                }
+                const uint64_t db0 = make_mnmajor_sw128_desc(zb, (uint32_t)p.z_bytes);
+                const int ht2 = G.Ht + 2, wm = G.Wt - 1, hm = G.Ht - 1, lw = G.lw, lwh = G.lw + G.lh, wt = G.Wt;
+                const bool first_tile = kb == 0;
+                const bool no_mma = (p.dbg & 1) != 0;
+#pragma unroll 1
+                for (int k = 0; k < p.ksteps; ++k) {          // 16-pixel K steps of the tile
+                    const int pix = 16 * k;
+                    const int xx = pix & wm, yy = (pix >> lw) & hm, bb = pix >> lwh;
+                    const uint64_t r4 = (uint64_t)(((uint32_t)((bb * ht2 + yy) * wt + xx) * 128u) >> 4);   // tap ky = 0
+                    const uint64_t db = db0 + (uint64_t)(k * (2048 >> 4));
+                    const uint32_t acc = (first_tile && k == 0) ? 0u : 1u;
+                    if (!no_mma) {
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) umma_bf16(tmem_base + (uint32_t)(j * 64), da0[j] + r4, db, idesc, acc);
                     }
                 }
                 umma_commit(&empty[s]);
@@ -958,7 +977,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
                 if (num_k > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 64 + c0), r);
                 const int nv = min(32, p.Cout - (n0 + c0));
                 float *o = nullptr;
-                if (tap < 9 && ci < p.Cin) o = out + (size_t)ci * p.Cout + n0 + c0;
+                if (tap < 9 && ci < p.Cin && !(p.dbg & 4)) o = out + (size_t)ci * p.Cout + n0 + c0;
                 else if (tap == 9 && row == 64 && p.bias_partial) o = p.bias_partial + (size_t)blockIdx.x * p.Cout + n0 + c0;
                 if (o) {
                     if (num_k == 0) {
@@ -986,31 +1005,46 @@ conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
     }
 }
 
-__global__ void wgrad_tc_reduce_kernel(const float *__restrict__ partial, int nsplit, size_t n,
-                                       float *__restrict__ out, int accumulate,
-                                       const float *__restrict__ bias_partial, int n_bias,
-                                       float *__restrict__ dbias) {
+// Split-K reduction.  A block of 256 threads owns 256 / S consecutive outputs; slice q of its S slices sums the split
+// rows q, q + S, ... (coalesced reads, eight independent rows in flight per thread), then the S slice sums are
+// combined in a fixed order: deterministic.  S = 8 for the many-row reductions of the D0 heads (137 rows x 147 KB:
+// the thread-per-output form was a chain of 19 dependent L2 round trips, 11 us), S = 1 for few rows / many outputs.
+__global__ void __launch_bounds__(256)
+wgrad_tc_reduce_kernel(const float *__restrict__ partial, int nsplit, size_t n,
+                       float *__restrict__ out, int accumulate,
+                       const float *__restrict__ bias_partial, int n_bias,
+                       float *__restrict__ dbias, int S) {
     EFFDET_PDL_SYNC();
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        float t = 0.f;
-        int s = 0;
-        for (; s + 7 < nsplit; s += 8) {          // eight loads in flight, same summation order
+    __shared__ float sred[256];
+    const int per = 256 / S;
+    const int e = threadIdx.x % per, slice = threadIdx.x / per;
+    const size_t i = (size_t)blockIdx.x * per + e;
+    const bool is_w = i < n, is_b = !is_w && i < n + (size_t)n_bias;
+    const float *src = is_w ? partial + i : bias_partial + (i - n);
+    const size_t stride = is_w ? n : (size_t)n_bias;
+    float t = 0.f;
+    if (is_w || is_b) {
+        int s = slice;
+        for (; s + 7 * S < nsplit; s += 8 * S) {
             float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldcg(partial + (size_t)(s + u) * n + i);
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (size_t)(s + u * S) * stride);
 #pragma unroll
             for (int u = 0; u < 8; ++u) t += v[u];
         }
-        for (; s < nsplit; ++s) t += __ldcg(partial + (size_t)s * n + i);
-        out[i] = accumulate ? out[i] + t : t;
-    } else if (i < n + (size_t)n_bias) {
-        const size_t j = i - n;
-        float t = 0.f;
-        for (int s = 0; s < nsplit; ++s) t += bias_partial[(size_t)s * n_bias + j];
-        dbias[j] = t;
+        for (; s < nsplit; s += S) t += __ldcg(src + (size_t)s * stride);
     }
+    if (S > 1) {
+        sred[threadIdx.x] = t;
+        __syncthreads();
+        if (slice != 0) return;
+        t = 0.f;
+        for (int q = 0; q < S; ++q) t += sred[q * per + e];
+    }
+    if (is_w) out[i] = accumulate ? out[i] + t : t;
+    else if (is_b) dbias[i - n] = t;
 }
+static int wg_reduce_slices(int nsplit) { return nsplit >= 64 ? 8 : nsplit >= 32 ? 4 : nsplit >= 16 ? 2 : 1; }
 
 // picks (Wt, Ht, Bt) with Wt*Ht*Bt == 128 minimising the number of tiles
 static void pick_tile(int W, int H, int B, int *Wt, int *Ht, int *Bt) {
@@ -1252,11 +1286,22 @@ static bool wg_halo(const effdet_wgrad_desc *d) {
     return d->kh == 3 && d->kw == 3 && d->stride == 1 && d->Cin <= 64 && getenv("EFFDET_NO_WGRAD_HALO") == nullptr;
 }
 // tiles of the halo kernel: Wt in {8, 16, 32} (16-pixel K steps start on swizzle-atom boundaries)
-static void pick_tile_halo(int W, int H, int B, int *Wt, int *Ht, int *Bt) {
-    static const int cand[][3] = {{16, 8, 1}, {8, 16, 1}, {32, 4, 1}, {8, 8, 2}, {16, 4, 2}, {8, 4, 4}, {16, 2, 4},
-                                  {8, 2, 8}, {16, 1, 8}};     // Wt * Ht >= 16: a K step never straddles images
+// EFFDET_WG_HALO_PX=64: half-size tiles of the Cin <= 64 halo kernel (four 44 KiB ring stages instead of two of
+// 76 KiB).  Measured 4-10 % SLOWER than 128-pixel tiles on the D0 heads (A/B in one job): the main loop is not
+// starved by load latency; kept as a switch for the experiment.
+static int wg_halo_px() {
+    static const int px = getenv("EFFDET_WG_HALO_PX") ? atoi(getenv("EFFDET_WG_HALO_PX")) : 128;
+    return px == 128 ? 128 : 64;
+}
+static void pick_tile_halo(int W, int H, int B, int *Wt, int *Ht, int *Bt, int px = 128) {
+    static const int cand128[][3] = {{16, 8, 1}, {8, 16, 1}, {32, 4, 1}, {8, 8, 2}, {16, 4, 2}, {8, 4, 4}, {16, 2, 4},
+                                     {8, 2, 8}, {16, 1, 8}};  // Wt * Ht >= 16: a K step never straddles images
+    static const int cand64[][3] = {{16, 4, 1}, {8, 8, 1}, {32, 2, 1}, {8, 4, 2}, {16, 2, 2}, {8, 2, 4}, {16, 1, 4},
+                                    {8, 8, 1}, {8, 8, 1}};
+    const int (*cand)[3] = px == 64 ? cand64 : cand128;
     long best = -1;
-    for (auto &c : cand) {
+    for (int q = 0; q < 9; ++q) {
+        const int *c = cand[q];
         long n = (long)cdiv(W, c[0]) * cdiv(H, c[1]) * cdiv(B, c[2]);
         if (best < 0 || n < best) { best = n; *Wt = c[0]; *Ht = c[1]; *Bt = c[2]; }
     }
@@ -1282,7 +1327,7 @@ static int wg_tc_plan(const effdet_wgrad_desc *d, int *tiles_per_split_out, int 
     long total_tiles = 0;
     const bool halo = wg_halo(d);
     for (int i = 0; i < d->n_groups; ++i) {
-        if (halo || col) pick_tile_halo(d->W[i], d->H[i], d->B, &Wt[i], &Ht[i], &Bt[i]);
+        if (halo || col) pick_tile_halo(d->W[i], d->H[i], d->B, &Wt[i], &Ht[i], &Bt[i], halo ? wg_halo_px() : 128);
         else pick_tile(d->W[i], d->H[i], d->B, &Wt[i], &Ht[i], &Bt[i]);
         n_tiles_out[i] = (int)(cdiv(d->W[i], Wt[i]) * cdiv(d->H[i], Ht[i]) * cdiv(d->B, Bt[i]));
         total_tiles += n_tiles_out[i];
@@ -1297,7 +1342,7 @@ static int wg_tc_plan(const effdet_wgrad_desc *d, int *tiles_per_split_out, int 
     long want = ((long)kNumSMs * ((halo || col) ? 1 : 2)) / yz;
     if (want < 1) want = 1;
     long tps = (total_tiles + want - 1) / want;
-    if (tps < 8) tps = 8;
+    if (tps < (halo && wg_halo_px() == 64 ? 16 : 8)) tps = halo && wg_halo_px() == 64 ? 16 : 8;
     *tiles_per_split_out = (int)tps;
     *block_n_out = bn; *m_tiles_out = m_tiles;
     return (int)cdiv(total_tiles, tps);
@@ -1372,11 +1417,13 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
             }
         }
         hp.total_tiles = zs; hp.tiles_per_split = tps;
+        { static const int dbg = getenv("EFFDET_WG_DBG") ? atoi(getenv("EFFDET_WG_DBG")) : 0; hp.dbg = dbg; }
         zs = splits;                                  // below: number of split rows
         hp.box_stride = round_up(box_max, 1024);
-        const int stage_bytes = 3 * hp.box_stride + kATileBytes;
+        hp.ksteps = wg_halo_px() / 16; hp.z_bytes = wg_halo_px() * 128;
+        const int stage_bytes = 3 * hp.box_stride + hp.z_bytes;
         hp.stages = (int)((220 * 1024 - hp.box_stride - 2048) / stage_bytes);
-        if (hp.stages > 3) hp.stages = 3;
+        if (hp.stages > 4) hp.stages = 4;
         EFFDET_REQUIRE(hp.stages >= 1, "tile does not fit shared memory");
         const size_t hsmem = (size_t)hp.stages * stage_bytes + hp.box_stride + (2 * hp.stages + 1) * 8 + 16 + 1024;
         static bool hattr = false;
@@ -1390,8 +1437,8 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
         EFFDET_LAUNCHED();
         const size_t hn = (size_t)9 * d->Cin * d->Cout;
         const int hn_bias = d->dbias ? d->Cout : 0;
-        EFFDET_CUDA(launch_pdl(wgrad_tc_reduce_kernel, dim3(cdiv(hn + hn_bias, 256)), dim3(256), 0, hst, d->partial, zs, hn, d->dweight, d->accumulate,
-                                                                        hp.bias_partial, hn_bias, d->dbias));
+        EFFDET_CUDA(launch_pdl(wgrad_tc_reduce_kernel, dim3(cdiv(hn + hn_bias, 256 / wg_reduce_slices(zs))), dim3(256), 0, hst, d->partial, zs, hn, d->dweight, d->accumulate,
+                                                                        hp.bias_partial, hn_bias, d->dbias, wg_reduce_slices(zs)));
         EFFDET_LAUNCHED();
         return EFFDET_OK;
     }
@@ -1463,8 +1510,8 @@ extern "C" int effdet_conv_wgrad_tc(const effdet_wgrad_desc *d, void *stream) {
     EFFDET_LAUNCHED();
     const size_t n = (size_t)taps * d->Cin * d->Cout;
     const int n_bias = d->dbias ? d->Cout : 0;
-    EFFDET_CUDA(launch_pdl(wgrad_tc_reduce_kernel, dim3(cdiv(n + n_bias, 256)), dim3(256), 0, st, d->partial, z, n, d->dweight, d->accumulate,
-                                                                 p.bias_partial, n_bias, d->dbias));
+    EFFDET_CUDA(launch_pdl(wgrad_tc_reduce_kernel, dim3(cdiv(n + n_bias, 256 / wg_reduce_slices(z))), dim3(256), 0, st, d->partial, z, n, d->dweight, d->accumulate,
+                                                                 p.bias_partial, n_bias, d->dbias, wg_reduce_slices(z)));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }

@@ -11,6 +11,8 @@ efficientnet.py:309-470 (call stack SURVEY.md section 3 (B)).
 import ctypes
 
 import numpy as np
+import os
+
 import torch
 
 from . import _lib
@@ -430,8 +432,18 @@ class Plan:
         kernel would mostly measure.  Large launches stream more bytes than L2 holds; small ones
         are L2-resident here as they are in the real step (their producer just wrote their input)."""
         stream = torch.cuda.current_stream(self.dev)
+        # EFFDET_PROFILE_KINDS=dwconv,conv1x1_tc: the eager warm-up pass brackets the launches of those kinds with
+        # cudaProfilerStart / Stop, so `ncu --profile-from-start off` captures exactly one launch per op, in plan
+        # order (profiles/tools/traffic_from_ncu.py turns that capture into profiles/traffic.json)
+        kinds = set(filter(None, os.environ.get("EFFDET_PROFILE_KINDS", "").split(",")))
         for op in self.ops:                      # warm (kernel attributes, lazy allocations)
+            if op.kind in kinds:
+                torch.cuda.synchronize(self.dev)
+                torch.cuda.profiler.start()
             op.fn(stream.cuda_stream)
+            if op.kind in kinds:
+                torch.cuda.synchronize(self.dev)
+                torch.cuda.profiler.stop()
         torch.cuda.synchronize(self.dev)
         graphs = []
         side = torch.cuda.Stream(self.dev)
