@@ -52,6 +52,8 @@ _SIGNATURES = {
     "effdet_stem_conv_u8": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                             c_int, c_int, c_int, c_void_p],
     "effdet_normalize_u8": [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
+    "effdet_letterbox_geometry": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "effdet_letterbox_u8": [c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, c_int, c_void_p],
     "effdet_conv2d": [c_void_p, c_void_p],
     "effdet_conv_weight_panel": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                  c_void_p],

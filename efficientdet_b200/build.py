@@ -23,6 +23,7 @@ SOURCES = {
     "core.cu": [],
     "tail.cu": ["-fmad=false"],
     "targets.cu": ["-fmad=false"],
+    "preprocess.cu": ["-fmad=false"],
 }
 
 

@@ -1,6 +1,8 @@
 """Host-side image preparation either side of the stem, with the reference's names.
 
   resize_image / preprocess_image   utils/__init__.py:103-138 (letterbox into a grey 128 square, uint8 kept)
+  preprocess_images_device          the same letterbox on the GPU (effdet_letterbox_u8: bit-exact with cv2's 8-bit
+                                    bilinear resize), so a raw decoded image goes host -> device once, as bytes
   normalize_image                   utils/__init__.py:87-100, train_tpu.py:130-140,
                                     generators/common.py:418-429 ((v/255 - mean) / std per RGB channel)
   normalization_lut                 the same arithmetic tabulated per byte value: what the device stem
@@ -60,3 +62,41 @@ def resize_image(image, image_size):
 def preprocess_image(image, image_size):
     """utils/__init__.py:135-138.  The uint8 result can be passed to the model as is."""
     return resize_image(image, image_size)
+
+
+def preprocess_images_device(images, image_size, out=None, device=None):
+    """Letterbox a list of raw uint8 RGB images (each (h, w, 3), numpy or CUDA tensor, any sizes) on the GPU.
+    -> (batch (B, image_size, image_size, 3) uint8 CUDA tensor, [(scale, offset_h, offset_w), ...]) with the values
+    utils.preprocess_image (utils/__init__.py:135-138) returns per image.  The batch can be passed to
+    predict_on_batch / train_on_batch as is (the stem normalises)."""
+    import ctypes
+    import torch
+    from .. import _lib
+    lib = _lib.load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    B = len(images)
+    if out is None:
+        out = torch.empty((B, image_size, image_size, 3), dtype=torch.uint8, device=device)
+    assert out.shape == (B, image_size, image_size, 3) and out.dtype == torch.uint8 and out.is_cuda
+    meta, keep = [], []
+    st = _lib.stream_ptr(device)
+    for i, img in enumerate(images):
+        if not isinstance(img, torch.Tensor):
+            a = np.ascontiguousarray(img)
+            if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+                raise ValueError("images must be (h, w, 3) uint8, got %s %s" % (a.shape, a.dtype))
+            img = torch.from_numpy(a).to(device, non_blocking=True)
+        elif img.dtype != torch.uint8 or img.dim() != 3 or img.shape[2] != 3 or not img.is_cuda:
+            raise ValueError("tensor images must be (h, w, 3) uint8 CUDA tensors")
+        img = img.contiguous()
+        keep.append(img)
+        h, w = int(img.shape[0]), int(img.shape[1])
+        rh, rw, oh, ow = (ctypes.c_int() for _ in range(4))
+        sc = ctypes.c_double()
+        _lib.call("effdet_letterbox_geometry", h, w, image_size, ctypes.byref(rh), ctypes.byref(rw),
+                  ctypes.byref(oh), ctypes.byref(ow), ctypes.byref(sc))
+        _lib.call("effdet_letterbox_u8", img.data_ptr(), h, w, 0, out[i].data_ptr(), image_size, st)
+        s = sc.value
+        meta.append((0 if s == 0.0 else s, oh.value, ow.value))
+    torch.cuda.current_stream(device).synchronize()      # the staged source tensors may be freed now
+    return out, meta

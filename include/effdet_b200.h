@@ -144,6 +144,17 @@ int effdet_stem_conv_u8(const unsigned char *images, const float *lut, const flo
 int effdet_normalize_u8(const unsigned char *images, const float *lut, float *out, size_t n_values,
                         void *stream);
 
+/* Letterbox resize of one raw uint8 RGB image (src_h, src_w, 3; rows src_row_stride bytes apart, 0 = dense) into
+ * out (image_size, image_size, 3) uint8: utils/__init__.py:103-132 resize_image == generators/common.py:406-417
+ * (cv2.resize bilinear to (resized_w, resized_h), pasted into the centre of a grey 128 square).  Bit-exact with
+ * OpenCV's 8-bit INTER_LINEAR (fixed-point, 11-bit weights); the output feeds effdet_stem_conv_u8 directly.
+ * effdet_letterbox_geometry is the host arithmetic of the same function: resized extent, paste offsets and the
+ * scale the reference returns (0 when the image already is image_size x image_size, as the reference does). */
+int effdet_letterbox_geometry(int src_h, int src_w, int image_size, int *resized_h, int *resized_w,
+                              int *offset_h, int *offset_w, double *scale);
+int effdet_letterbox_u8(const unsigned char *image, int src_h, int src_w, long long src_row_stride,
+                        unsigned char *out, int image_size, void *stream);
+
 
 /* Dense convolution as implicit GEMM (1x1 or 3x3, stride 1 or 2, TF SAME padding) with fused
  * epilogue  y = act(conv(x * gate) * scale + shift) [* keep[b] + residual].

@@ -15,7 +15,9 @@ import utils as ref_utils  # noqa: E402  (reference package)
 
 rng = np.random.default_rng(20261018)
 out = {}
-cases = [(37, 53, 64), (80, 45, 64), (64, 64, 64), (21, 96, 96)]
+cases = [(37, 53, 64), (80, 45, 64), (64, 64, 64), (21, 96, 96),
+         # larger / up- and down-scaling / already-long-side cases for the letterbox resize itself
+         (120, 160, 128), (375, 500, 128), (50, 33, 160), (300, 128, 128), (7, 9, 96), (128, 200, 64)]
 out["cases"] = np.array(cases)
 for i, (h, w, size) in enumerate(cases):
     img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)

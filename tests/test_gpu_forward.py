@@ -368,3 +368,26 @@ def test_keras_h5_weight_file_round_trip_through_the_model(tmp_path):
     img = np.random.default_rng(0).standard_normal((2, size, size, 3)).astype(np.float32)
     for a, b in zip(p1.predict_on_batch([img]), p2.predict_on_batch([img])):
         assert np.array_equal(a, b)
+
+
+def test_letterbox_resize_on_device_bit_exact():
+    """effdet_letterbox_u8 (utils.preprocess.preprocess_images_device) == the reference's utils.resize_image
+    (cv2.resize bilinear + grey canvas): the golden vectors produced by executing the reference, then random image
+    sizes at the model's input sizes against the oracle restatement (itself pinned on the same vectors)."""
+    import os
+    from efficientdet_b200.utils.preprocess import preprocess_images_device
+    from oracle import preprocess as op
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "preprocess.npz"))
+    for i, (h, w, size) in enumerate(gold["cases"]):
+        out, meta = preprocess_images_device([gold["img_%d" % i]], int(size))
+        assert np.array_equal(out[0].cpu().numpy(), gold["boxed_%d" % i]), (i, h, w, size)
+        assert np.array_equal(np.array(meta[0], np.float64), gold["meta_%d" % i])
+    rng = np.random.default_rng(99)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            for h, w in [(480, 640), (375, 500), (1080, 1920), (333, 500), (512, 512), (640, 427), (97, 1400), (512, 300)]]
+    for size in (512, 768):
+        out, meta = preprocess_images_device(imgs, size)
+        for j, img in enumerate(imgs):
+            want, scale, oh, ow = op.resize_image_ref(img, size)
+            assert np.array_equal(out[j].cpu().numpy(), want), (size, img.shape)
+            assert meta[j] == (scale, oh, ow)

@@ -38,3 +38,15 @@ def test_host_preprocess_and_lut_bit_exact(gold):
         # the table lookup the device stem performs
         got = np.stack([lut[c][boxed[..., c]] for c in range(3)], -1)
         assert np.array_equal(got, want)
+
+
+def test_oracle_letterbox_resize_matches_reference(gold):
+    """oracle.preprocess.resize_image_ref (cv2's 8-bit bilinear resize restated + the reference's letterbox) against
+    outputs of the reference's own utils.resize_image (which calls cv2.resize): bit-exact, including the returned
+    (scale, offset_h, offset_w)."""
+    from oracle import preprocess as op
+    for i, (h, w, size) in enumerate(gold["cases"]):
+        boxed, scale, oh, ow = op.resize_image_ref(gold["img_%d" % i], int(size))
+        assert boxed.dtype == np.uint8
+        assert np.array_equal(boxed, gold["boxed_%d" % i]), (i, h, w, size)
+        assert np.array_equal(np.array([scale, oh, ow], np.float64), gold["meta_%d" % i])
