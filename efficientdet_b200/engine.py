@@ -403,15 +403,114 @@ class Plan:
         bounds = list(bounds) if bounds else [len(self.ops)]
         assert bounds[-1] == len(self.ops) and all(a < b for a, b in zip(bounds, bounds[1:]))
         self.segment_graphs = []
+        lanes = self.graph_lanes()
         begin = 0
+        import gc
         for end in bounds:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.run(begin, end)
+                # no cyclic garbage collection inside the capture: collecting an older plan (CUDA graphs, streams,
+                # device buffers in reference cycles) calls cudaFree / cudaGraphExecDestroy, which invalidates a
+                # capture in progress (run_lanes allocates enough Python objects to trigger a collection)
+                was_on = gc.isenabled()
+                gc.disable()
+                try:
+                    if lanes > 1:
+                        self.run_lanes(begin, end, lanes)
+                    else:
+                        self.run(begin, end)
+                finally:
+                    if was_on:
+                        gc.enable()
             self.segment_graphs.append(g)
             begin = end
         self.graph = self.segment_graphs[0] if len(self.segment_graphs) == 1 else self.segment_graphs
         return self.graph
+
+    def graph_lanes(self):
+        """Streams the launch list is captured on.  1 = the plan order as one chain.  More: independent chains
+        (the two heads, the BiFPN lateral convolutions, weight-panel preparation) become parallel branches of the
+        CUDA graph -- what a batch-1 step, a chain of ~120 launches of 3-9 us, is short of is not bandwidth but
+        things to run side by side.  Default: 4 for small inference batches, EFFDET_GRAPH_LANES overrides."""
+        env = os.environ.get("EFFDET_GRAPH_LANES")
+        if env:
+            return max(1, int(env))
+        return 4 if (type(self) is Plan and self.B <= 2) else 1
+
+    def lane_hint(self, op, n_lanes):
+        return None
+
+    def dependencies(self):
+        """Per launch: the earlier launches it must follow -- last writer of every buffer it reads (RAW), last
+        writer and the readers since of every buffer it writes (WAW / WAR; buffers are recycled between values,
+        so hazards are tracked per BUFFER, not per value).  Launches only touch memory through their declared
+        inputs / outputs; weights and static panels are read-only inside a plan."""
+        last_w, readers, deps = {}, {}, []
+        for i, op in enumerate(self.ops):
+            d = set()
+            rb = {v.t.data_ptr() for v in op.inputs if v.t is not None}
+            wb = {v.t.data_ptr() for v in op.outputs if v.t is not None}
+            for b in rb:
+                if b in last_w:
+                    d.add(last_w[b])
+            for b in wb:
+                if b in last_w:
+                    d.add(last_w[b])
+                d.update(readers.get(b, ()))
+            d.discard(i)
+            deps.append(sorted(d))
+            for b in rb - wb:
+                readers.setdefault(b, set()).add(i)
+            for b in wb:
+                last_w[b] = i
+                readers[b] = set()
+        return deps
+
+    def run_lanes(self, begin, end, n_lanes):
+        """Enqueue launches [begin, end) on up to n_lanes streams, joined by events according to dependencies().
+        Called inside a stream capture (the fork / join events become graph edges); launch order within a lane is
+        plan order."""
+        origin = torch.cuda.current_stream(self.dev)
+        deps = self.dependencies()
+        if not hasattr(self, "_lane_streams") or len(self._lane_streams) < n_lanes - 1:
+            self._lane_streams = [torch.cuda.Stream(self.dev) for _ in range(n_lanes - 1)]
+        streams = [origin] + self._lane_streams[:n_lanes - 1]
+        start = torch.cuda.Event()
+        start.record(origin)
+        joined = [True] + [False] * (n_lanes - 1)        # lane has forked from the capturing stream
+        lane_last = [None] * n_lanes                     # last launch index enqueued on the lane
+        lane_of, done_ev = {}, {}
+        for i in range(begin, end):
+            d = [j for j in deps[i] if j >= begin]
+            lane = self.lane_hint(self.ops[i], n_lanes)  # fixed assignment (training plans), or None = by dependencies
+            if lane is None:
+                for j in sorted(d, reverse=True):        # continue the lane of the latest dependency if it is its tail
+                    if lane_last[lane_of[j]] == j:
+                        lane = lane_of[j]
+                        break
+            if lane is None:                             # else an unused lane, else the one idle longest
+                unused = [l for l in range(n_lanes) if lane_last[l] is None]
+                lane = unused[0] if unused else min(range(n_lanes), key=lambda l: lane_last[l])
+            st = streams[lane]
+            if not joined[lane]:
+                st.wait_event(start)
+                joined[lane] = True
+            for j in d:
+                if lane_of[j] != lane:
+                    st.wait_event(done_ev[j])
+            self.ops[i].fn(st.cuda_stream)
+            if os.environ.get("EFFDET_LANE_DEBUG"):      # which launch invalidated the capture?
+                try:
+                    torch.cuda.is_current_stream_capturing()
+                except Exception as e:
+                    raise RuntimeError("capture invalidated by launch %d (%s, %s) on lane %d: %s" % (
+                        i, self.ops[i].kind, self.ops[i].name, lane, e))
+            ev = torch.cuda.Event()
+            ev.record(st)
+            done_ev[i], lane_of[i], lane_last[lane] = ev, lane, i
+        for l in range(1, n_lanes):                      # join: the capture ends on the origin stream
+            if lane_last[l] is not None:
+                origin.wait_event(done_ev[lane_last[l]])
 
     def replay(self):
         if self.graph is None:

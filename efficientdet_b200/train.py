@@ -71,6 +71,28 @@ class TrainPlan(engine.Plan):
             self.drop_step.copy_(step)
         return g
 
+    # Weight gradients are the leaves of the backward pass: nothing in the step reads them before the optimizer, and
+    # they write only their own scratch partials and the (untracked) gradient buffers.  Captured on a second lane
+    # they run beside the data-gradient chain, whose BiFPN / head kernels at the coarse pyramid levels are a few
+    # microseconds on a handful of SMs (engine.Plan.run_lanes; hazards on recycled buffers are tracked per buffer).
+    WGRAD_KINDS = frozenset(("conv_wgrad_tc", "conv_wgrad", "dw_wgrad", "fuse_wgrad", "bias_grad", "stem_wgrad"))
+
+    # Operand preparation that depends on the weights alone (bf16 panels of the trainable convolutions, transposed /
+    # flipped kernels for the data gradients): ready when the step starts, so a third lane runs it beside the
+    # backbone forward instead of in front of each consumer.
+    PREP_KINDS = frozenset(("panel", "wtrans"))
+
+    def graph_lanes(self):
+        env = os.environ.get("EFFDET_GRAPH_LANES")
+        return max(1, int(env)) if env else 3
+
+    def lane_hint(self, op, n_lanes):
+        if op.kind in self.WGRAD_KINDS and n_lanes > 1:
+            return 1
+        if op.kind in self.PREP_KINDS and not op.inputs and n_lanes > 2:
+            return 2
+        return 0
+
     # ------------------------------------------------------------------ small helpers
     def gw(self, key):
         return self.net.grads[key]
