@@ -443,11 +443,19 @@ class Plan:
     def dependencies(self):
         """Per launch: the earlier launches it must follow -- last writer of every buffer it reads (RAW), last
         writer and the readers since of every buffer it writes (WAW / WAR; buffers are recycled between values,
-        so hazards are tracked per BUFFER, not per value).  Launches only touch memory through their declared
-        inputs / outputs; weights and static panels are read-only inside a plan."""
+        so hazards are tracked per BUFFER, not per value).  Launches exchange data only through their declared
+        inputs / outputs; weights and static panels are read-only inside a plan; per-layer state outside the values
+        (BatchNorm moving statistics, parameter gradients) has exactly one writer per step, or writers that
+        lane_hint() keeps on one lane.  A launch that declares neither inputs nor outputs is a barrier."""
         last_w, readers, deps = {}, {}, []
+        barrier = None
         for i, op in enumerate(self.ops):
             d = set()
+            if barrier is not None:
+                d.add(barrier)
+            if not op.inputs and not op.outputs:     # declares nothing: pure side effect (the stochastic-depth
+                d.update(range(0 if barrier is None else barrier, i))     # mask draw) -> ordered against everything
+                barrier = i
             rb = {v.t.data_ptr() for v in op.inputs if v.t is not None}
             wb = {v.t.data_ptr() for v in op.outputs if v.t is not None}
             for b in rb:
@@ -482,15 +490,19 @@ class Plan:
         lane_of, done_ev = {}, {}
         for i in range(begin, end):
             d = [j for j in deps[i] if j >= begin]
-            lane = self.lane_hint(self.ops[i], n_lanes)  # fixed assignment (training plans), or None = by dependencies
+            # fixed lane (training plans: weight gradients, operand preparation), or a set of lanes to choose from
+            # by dependencies (None = all)
+            hint = self.lane_hint(self.ops[i], n_lanes)
+            lane = hint if isinstance(hint, int) else None
+            allowed = list(hint) if isinstance(hint, (list, tuple)) else list(range(n_lanes))
             if lane is None:
                 for j in sorted(d, reverse=True):        # continue the lane of the latest dependency if it is its tail
-                    if lane_last[lane_of[j]] == j:
+                    if lane_of[j] in allowed and lane_last[lane_of[j]] == j:
                         lane = lane_of[j]
                         break
             if lane is None:                             # else an unused lane, else the one idle longest
-                unused = [l for l in range(n_lanes) if lane_last[l] is None]
-                lane = unused[0] if unused else min(range(n_lanes), key=lambda l: lane_last[l])
+                unused = [l for l in allowed if lane_last[l] is None]
+                lane = unused[0] if unused else min(allowed, key=lambda l: lane_last[l])
             st = streams[lane]
             if not joined[lane]:
                 st.wait_event(start)

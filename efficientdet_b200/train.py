@@ -84,13 +84,15 @@ class TrainPlan(engine.Plan):
 
     def graph_lanes(self):
         env = os.environ.get("EFFDET_GRAPH_LANES")
-        return max(1, int(env)) if env else 3
+        return max(1, int(env)) if env else 4
 
     def lane_hint(self, op, n_lanes):
         if op.kind in self.WGRAD_KINDS and n_lanes > 1:
             return 1
         if op.kind in self.PREP_KINDS and not op.inputs and n_lanes > 2:
             return 2
+        if n_lanes > 3:                       # the data path itself over lanes 0, 3, 4, ... by dependencies
+            return [0] + list(range(3, n_lanes))
         return 0
 
     # ------------------------------------------------------------------ small helpers
