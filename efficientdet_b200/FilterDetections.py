@@ -11,42 +11,69 @@ from .keras_compat import Layer
 _ws_cache = {}
 
 
-def _run(boxes, classification, class_specific, score_threshold, max_detections, iou_threshold,
-         nms, cand_capacity=None, want_indices=False):
-    """boxes (B,N,4) f32 cuda, classification (B,N,C) f32 cuda -> (boxes, scores, labels) cuda."""
+def _launch(boxes, classification, class_specific, score_threshold, max_detections, iou_threshold, nms, cap,
+            want_indices=False):
+    """One attempt with candidate capacity `cap`: enqueues the tail, no synchronisation.
+    -> (out_boxes, out_scores, out_labels, out_indices | None, status (4,) i32 device tensor);
+    status[0] != 0: the candidates did not fit, status[1] = capacity needed."""
     B, N, C = classification.shape
     dev = boxes.device
     out_b = torch.empty((B, max_detections, 4), dtype=torch.float32, device=dev)
     out_s = torch.empty((B, max_detections), dtype=torch.float32, device=dev)
     out_l = torch.empty((B, max_detections), dtype=torch.int32, device=dev)
     out_i = torch.empty((B, max_detections), dtype=torch.int32, device=dev) if want_indices else None
-    if B == 0:
-        return (out_b, out_s, out_l, out_i) if want_indices else (out_b, out_s, out_l)
-    S = C if class_specific else 1
+    lib = _lib.load()
+    nbytes = lib.effdet_filter_detections_workspace_size(B, N, C, cap, max_detections)
+    key = (dev.index, "ws")
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=dev)
+        _ws_cache[key] = ws
+    status = torch.zeros(4, dtype=torch.int32, device=dev)
+    _lib.call("effdet_filter_detections", boxes.data_ptr(), classification.data_ptr(), B, N, C,
+              float(score_threshold), float(iou_threshold), int(max_detections),
+              int(bool(class_specific)), int(bool(nms)), ws.data_ptr(), ws.numel(), cap,
+              out_b.data_ptr(), out_s.data_ptr(), out_l.data_ptr(), _lib.ptr(out_i),
+              status.data_ptr(), _lib.stream_ptr())
+    return out_b, out_s, out_l, out_i, status
+
+
+def _capacity(B, N, C, S, cand_capacity=None):
     worst = B * N * S
     cap = cand_capacity if cand_capacity is not None else _ws_cache.get(
         ("cap", B, N, C, S), min(worst, max(1 << 16, B * 8192)))
-    cap = max(1, min(cap, worst))
-    lib = _lib.load()
+    return max(1, min(cap, worst)), worst
+
+
+def _grow_capacity(B, N, C, S, status_host):
+    """Remembers the capacity a failed attempt asked for; returns it."""
+    worst = B * N * S
+    need = int(status_host[1])
+    cap = worst if need >= 0x7fffffff else min(worst, need + need // 8 + 1024)
+    _ws_cache[("cap", B, N, C, S)] = cap
+    return cap
+
+
+def _run(boxes, classification, class_specific, score_threshold, max_detections, iou_threshold,
+         nms, cand_capacity=None, want_indices=False):
+    """boxes (B,N,4) f32 cuda, classification (B,N,C) f32 cuda -> (boxes, scores, labels) cuda."""
+    B, N, C = classification.shape
+    dev = boxes.device
+    if B == 0:
+        out_b = torch.empty((B, max_detections, 4), dtype=torch.float32, device=dev)
+        out_s = torch.empty((B, max_detections), dtype=torch.float32, device=dev)
+        out_l = torch.empty((B, max_detections), dtype=torch.int32, device=dev)
+        out_i = torch.empty((B, max_detections), dtype=torch.int32, device=dev) if want_indices else None
+        return (out_b, out_s, out_l, out_i) if want_indices else (out_b, out_s, out_l)
+    S = C if class_specific else 1
+    cap, _ = _capacity(B, N, C, S, cand_capacity)
     while True:
-        nbytes = lib.effdet_filter_detections_workspace_size(B, N, C, cap, max_detections)
-        key = (dev.index, "ws")
-        ws = _ws_cache.get(key)
-        if ws is None or ws.numel() < nbytes:
-            ws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=dev)
-            _ws_cache[key] = ws
-        status = torch.zeros(4, dtype=torch.int32, device=dev)
-        _lib.call("effdet_filter_detections", boxes.data_ptr(), classification.data_ptr(), B, N, C,
-                  float(score_threshold), float(iou_threshold), int(max_detections),
-                  int(bool(class_specific)), int(bool(nms)), ws.data_ptr(), ws.numel(), cap,
-                  out_b.data_ptr(), out_s.data_ptr(), out_l.data_ptr(), _lib.ptr(out_i),
-                  status.data_ptr(), _lib.stream_ptr())
+        out_b, out_s, out_l, out_i, status = _launch(boxes, classification, class_specific, score_threshold,
+                                                     max_detections, iou_threshold, nms, cap, want_indices)
         st = status.cpu()
         if int(st[0]) == 0:
             return (out_b, out_s, out_l, out_i) if want_indices else (out_b, out_s, out_l)
-        need = int(st[1])
-        cap = worst if need >= 0x7fffffff else min(worst, need + need // 8 + 1024)
-        _ws_cache[("cap", B, N, C, S)] = cap
+        cap = _grow_capacity(B, N, C, S, st)
 
 
 def filter_detections(boxes, classification, class_specific_filter=True, score_threshold=0.01,

@@ -330,7 +330,7 @@ class Model:
         slot[1].record(torch.cuda.current_stream(self.net.device))
         return d
 
-    def predict_on_batch_device(self, x):
+    def predict_on_batch_device(self, x, defer_status=False):
         """Same as predict_on_batch but returns CUDA tensors (no device->host copy)."""
         if isinstance(x, (list, tuple)):
             images = x[0]
@@ -363,6 +363,11 @@ class Model:
                   boxes.data_ptr(), _lib.stream_ptr(net.device))
         if self._outputs == "boxes":
             return [boxes, cls]
+        if defer_status:        # predict_generator: no host synchronisation here; the caller checks `status` later
+            from .FilterDetections import _capacity, _launch
+            cap, _ = _capacity(B, plan.N, int(cls.shape[2]), int(cls.shape[2]))
+            ob, os_, ol, _, status = _launch(boxes, cls, True, self.score_threshold, 300, 0.5, True, cap)
+            return [ob, os_, ol], status
         from .FilterDetections import _run
         return list(_run(boxes, cls, True, self.score_threshold, 300, 0.5, True))
 
@@ -394,19 +399,65 @@ class Model:
                 ev = torch.cuda.Event()
                 ev.record(cs)
             return d, ev
+        # Outputs (and the tail's overflow status) of batch i are copied to pinned host buffers behind batch i on the
+        # main stream and waited for one iteration later, when batch i+1 is already enqueued -- the GPU no longer
+        # idles while the host launches the next batch (17 % of a 0.74 ms batch-1 step, 6 % at D2 / batch 64).  A
+        # staging slot is rewritten only after the batch that used it has consumed it (`consumed` events).  If the
+        # candidate workspace overflowed (rare: the capacity is learned), that batch is redone synchronously.
+        detect = self._outputs not in ("train", "boxes")
+        consumed = [None, None]
         it = iter(batches)
         first = next(it, None)
         nxt = stage(0, first) if first is not None else None
+        host_cur = first
         i = 0
+        pending = None
+
+        def finish(p):
+            host_outs, status_h, lev, host_batch = p
+            lev.synchronize()
+            if status_h is not None and int(status_h[0]) != 0:
+                from .FilterDetections import _grow_capacity
+                B, N, C = int(host_outs[0].shape[0]), self.net.plan(int(host_outs[0].shape[0])).N, self.net.num_classes
+                _grow_capacity(B, N, C, C, status_h)
+                return self.predict_on_batch([host_batch])
+            return [o.numpy().copy() for o in host_outs]
         while nxt is not None:
             cur, ev = nxt
             b = next(it, None)
-            # slot (i+1)%2 was last read by batch i-1, which has completed (its outputs were copied out)
-            nxt = stage((i + 1) % 2, b) if b is not None else None
+            if b is not None:
+                slot = (i + 1) % 2
+                if consumed[slot] is not None:
+                    cs.wait_event(consumed[slot])
+                nxt = stage(slot, b)
+            else:
+                nxt = None
             main.wait_event(ev)
-            outs = self.predict_on_batch_device([cur])
-            yield [o.cpu().numpy() for o in outs]
+            if detect:
+                outs, status = self.predict_on_batch_device([cur], defer_status=True)
+            else:
+                outs, status = self.predict_on_batch_device([cur]), None
+            cev = torch.cuda.Event()
+            cev.record(main)
+            consumed[i % 2] = cev
+            key = ("out", i % 2, tuple(tuple(o.shape) for o in outs))
+            if key not in self._slots:
+                self._slots[key] = ([torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs],
+                                    torch.empty(4, dtype=torch.int32).pin_memory())
+            host_outs, status_h = self._slots[key]
+            for h, o in zip(host_outs, outs):
+                h.copy_(o, non_blocking=True)
+            if status is not None:
+                status_h.copy_(status, non_blocking=True)
+            lev = torch.cuda.Event()
+            lev.record(main)
+            if pending is not None:
+                yield finish(pending)
+            pending = (host_outs, status_h if status is not None else None, lev, host_cur)
+            host_cur = b
             i += 1
+        if pending is not None:
+            yield finish(pending)
 
     def predict(self, x, batch_size=32, **kw):
         images = x[0] if isinstance(x, (list, tuple)) else x
