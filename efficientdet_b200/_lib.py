@@ -51,6 +51,10 @@ _SIGNATURES = {
                              c_int, c_int, c_void_p],
     "effdet_stem_conv_u8": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                             c_int, c_int, c_int, c_void_p],
+    "effdet_replay_load": [ctypes.c_char_p, c_int, c_void_p],
+    "effdet_replay_region": [c_void_p, ctypes.c_char_p, c_void_p, c_void_p],
+    "effdet_replay_step": [c_void_p, c_double, c_void_p],
+    "effdet_replay_destroy": [c_void_p],
     "effdet_normalize_u8": [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     "effdet_letterbox_geometry": [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "effdet_letterbox_u8": [c_void_p, c_int, c_int, ctypes.c_longlong, c_void_p, c_int, c_void_p],
@@ -102,6 +106,7 @@ _SIGNATURES = {
                            c_void_p],
     "effdet_sgd_momentum_step": [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float,
                                  c_void_p],
+    "effdet_sgd_momentum_step_dev_lr": [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_float, c_float, c_void_p],
     "effdet_bn_act_backward": [c_void_p, c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int, c_int, c_void_p],
@@ -212,6 +217,8 @@ def load():
     lib.effdet_plan_num_weights.argtypes = [c_void_p]
     lib.effdet_plan_num_launches.restype = c_int
     lib.effdet_plan_num_launches.argtypes = [c_void_p]
+    lib.effdet_replay_num_launches.restype = c_int
+    lib.effdet_replay_num_launches.argtypes = [c_void_p]
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args

@@ -800,6 +800,20 @@ sgd_momentum_kernel(float *__restrict__ w, const float *__restrict__ g, float *_
     }
 }
 
+// the same update with the learning rate read from device memory: a CUDA graph holding this launch stays valid
+// while the schedule changes lr_t every step (keras `decay`, cosine schedules)
+__global__ void __launch_bounds__(256)
+sgd_momentum_dev_lr_kernel(float *__restrict__ w, const float *__restrict__ g, float *__restrict__ v,
+                           size_t n, const float *__restrict__ lr_dev, float momentum, float grad_scale) {
+    EFFDET_PDL_SYNC();
+    const float lr_t = *lr_dev;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const float vel = momentum * v[i] - lr_t * (g[i] * grad_scale);
+        v[i] = vel;
+        w[i] += vel;
+    }
+}
+
 // flips a depthwise kernel (k,k,C) spatially: out[k*k-1-t][c] = in[t][c]
 __global__ void flip_taps_kernel(const float *__restrict__ in, float *__restrict__ out, int taps, int n) {
     EFFDET_PDL_SYNC();
@@ -1199,6 +1213,15 @@ extern "C" int effdet_zero_insert(const void *dz, void *out, int B, int Ho, int 
     DISPATCH_T(dtype,
         ((void)launch_pdl(zero_insert_kernel<float, 4>, dim3(grid_for(n / 4)), dim3(256), 0, st, (const float *)dz, (float *)out, B, Ho, Wo, C, H, W, ay, ax)),
         ((void)launch_pdl(zero_insert_kernel<__nv_bfloat16, 8>, dim3(grid_for(n / 8)), dim3(256), 0, st, (const __nv_bfloat16 *)dz, (__nv_bfloat16 *)out, B, Ho, Wo, C, H, W, ay, ax)))
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+extern "C" int effdet_sgd_momentum_step_dev_lr(float *w, const float *g, float *v, size_t n, const float *lr_dev,
+                                               float momentum, float grad_scale, void *stream) {
+    if (n == 0) return EFFDET_OK;
+    EFFDET_REQUIRE(w && g && v && lr_dev, "null pointer");
+    EFFDET_CUDA(launch_pdl(sgd_momentum_dev_lr_kernel, dim3(grid_for(n)), dim3(256), 0, as_stream(stream), w, g, v, n, lr_dev, momentum, grad_scale));
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }

@@ -67,6 +67,7 @@ def _call(name, *args):
         rc = fn(*args, stream)
         if rc != 0:
             _lib.check(rc)
+    run.call = (name, args)          # what plan_export.py serialises: entry point + arguments (stream excluded)
     return run
 
 
@@ -474,55 +475,59 @@ class Plan:
                 readers[b] = set()
         return deps
 
+    def lane_schedule(self, begin, end, n_lanes):
+        """[(lane, [launch indices on OTHER lanes to wait for])] for launches [begin, end): the multi-lane order
+        run_lanes() enqueues and plan_export.py writes into a compiled plan.  A launch continues the lane of its
+        latest dependency when that launch is the lane's tail, else takes an unused lane, else the lane idle
+        longest; lane_hint() can pin it (training plans) or restrict the choice."""
+        deps = self.dependencies()
+        lane_last = [None] * n_lanes                     # last launch index enqueued on the lane
+        lane_of, out = {}, []
+        for i in range(begin, end):
+            d = [j for j in deps[i] if j >= begin]
+            hint = self.lane_hint(self.ops[i], n_lanes)
+            lane = hint if isinstance(hint, int) else None
+            allowed = list(hint) if isinstance(hint, (list, tuple)) else list(range(n_lanes))
+            if lane is None:
+                for j in sorted(d, reverse=True):
+                    if lane_of[j] in allowed and lane_last[lane_of[j]] == j:
+                        lane = lane_of[j]
+                        break
+            if lane is None:
+                unused = [l for l in allowed if lane_last[l] is None]
+                lane = unused[0] if unused else min(allowed, key=lambda l: lane_last[l])
+            out.append((lane, [j for j in d if lane_of[j] != lane]))
+            lane_of[i], lane_last[lane] = lane, i
+        return out
+
     def run_lanes(self, begin, end, n_lanes):
-        """Enqueue launches [begin, end) on up to n_lanes streams, joined by events according to dependencies().
+        """Enqueue launches [begin, end) on up to n_lanes streams, joined by events according to lane_schedule().
         Called inside a stream capture (the fork / join events become graph edges); launch order within a lane is
         plan order."""
         origin = torch.cuda.current_stream(self.dev)
-        deps = self.dependencies()
+        sched = self.lane_schedule(begin, end, n_lanes)
         if not hasattr(self, "_lane_streams") or len(self._lane_streams) < n_lanes - 1:
             self._lane_streams = [torch.cuda.Stream(self.dev) for _ in range(n_lanes - 1)]
         streams = [origin] + self._lane_streams[:n_lanes - 1]
         start = torch.cuda.Event()
         start.record(origin)
         joined = [True] + [False] * (n_lanes - 1)        # lane has forked from the capturing stream
-        lane_last = [None] * n_lanes                     # last launch index enqueued on the lane
-        lane_of, done_ev = {}, {}
-        for i in range(begin, end):
-            d = [j for j in deps[i] if j >= begin]
-            # fixed lane (training plans: weight gradients, operand preparation), or a set of lanes to choose from
-            # by dependencies (None = all)
-            hint = self.lane_hint(self.ops[i], n_lanes)
-            lane = hint if isinstance(hint, int) else None
-            allowed = list(hint) if isinstance(hint, (list, tuple)) else list(range(n_lanes))
-            if lane is None:
-                for j in sorted(d, reverse=True):        # continue the lane of the latest dependency if it is its tail
-                    if lane_of[j] in allowed and lane_last[lane_of[j]] == j:
-                        lane = lane_of[j]
-                        break
-            if lane is None:                             # else an unused lane, else the one idle longest
-                unused = [l for l in allowed if lane_last[l] is None]
-                lane = unused[0] if unused else min(allowed, key=lambda l: lane_last[l])
+        lane_tail = [None] * n_lanes
+        done_ev = {}
+        for i, (lane, waits) in zip(range(begin, end), sched):
             st = streams[lane]
             if not joined[lane]:
                 st.wait_event(start)
                 joined[lane] = True
-            for j in d:
-                if lane_of[j] != lane:
-                    st.wait_event(done_ev[j])
+            for j in waits:
+                st.wait_event(done_ev[j])
             self.ops[i].fn(st.cuda_stream)
-            if os.environ.get("EFFDET_LANE_DEBUG"):      # which launch invalidated the capture?
-                try:
-                    torch.cuda.is_current_stream_capturing()
-                except Exception as e:
-                    raise RuntimeError("capture invalidated by launch %d (%s, %s) on lane %d: %s" % (
-                        i, self.ops[i].kind, self.ops[i].name, lane, e))
             ev = torch.cuda.Event()
             ev.record(st)
-            done_ev[i], lane_of[i], lane_last[lane] = ev, lane, i
+            done_ev[i], lane_tail[lane] = ev, i
         for l in range(1, n_lanes):                      # join: the capture ends on the origin stream
-            if lane_last[l] is not None:
-                origin.wait_event(done_ev[lane_last[l]])
+            if lane_tail[l] is not None:
+                origin.wait_event(done_ev[lane_tail[l]])
 
     def replay(self):
         if self.graph is None:

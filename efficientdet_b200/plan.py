@@ -75,3 +75,58 @@ class CPlan:
                   float(score_threshold), float(iou_threshold), int(max_detections), boxes.ctypes.data,
                   scores.ctypes.data, labels.ctypes.data)
         return [boxes, scores, labels]
+
+
+class CReplay:
+    """ctypes caller of the compiled-plan training API (csrc/replay.cu): effdet_replay_load / region / step.
+    Only numpy host arrays cross this boundary (copies through the CUDA runtime, not torch) -- the binding a
+    non-Python host would write.  The plan file comes from plan_export.export_train_plan()."""
+
+    def __init__(self, path, graph=True):
+        _lib.load()
+        h = ctypes.c_void_p()
+        _lib.call("effdet_replay_load", str(path).encode(), 0 if graph else 1, ctypes.byref(h))
+        self._h = h
+        self.num_launches = int(_lib.load().effdet_replay_num_launches(h))
+
+    def close(self):
+        if self._h:
+            _lib.call("effdet_replay_destroy", self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def region(self, name):
+        ptr, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _lib.call("effdet_replay_region", self._h, name.encode(), ctypes.byref(ptr), ctypes.byref(n))
+        return ptr.value, n.value
+
+    @staticmethod
+    def _memcpy(dst, src, nbytes, to_device):
+        from cuda.bindings import runtime as cudart
+        kind = cudart.cudaMemcpyKind.cudaMemcpyHostToDevice if to_device else cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost
+        err, = cudart.cudaMemcpy(dst, src, nbytes, kind)
+        if int(err) != 0:
+            raise RuntimeError("cudaMemcpy failed: %s" % err)
+
+    def write(self, name, array):
+        a = np.ascontiguousarray(array)
+        ptr, n = self.region(name)
+        if a.nbytes > n:
+            raise ValueError("%s: %d bytes into a region of %d" % (name, a.nbytes, n))
+        self._memcpy(ptr, a.ctypes.data, a.nbytes, True)
+
+    def read(self, name, dtype, shape=None, offset_bytes=0):
+        ptr, n = self.region(name)
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape)) if shape is not None else (n - offset_bytes) // dtype.itemsize
+        out = np.empty(count, dtype)
+        self._memcpy(out.ctypes.data, ptr + offset_bytes, out.nbytes, False)
+        return out.reshape(shape) if shape is not None else out
+
+    def step(self, learning_rate, stream=None):
+        _lib.call("effdet_replay_step", self._h, float(learning_rate), stream)

@@ -381,6 +381,10 @@ int effdet_zero_insert(const void *dz, void *out, int B, int Ho, int Wo, int C, 
  * v = momentum*v - lr_t*(g*grad_scale); w += v, lr_t = lr/(1+decay*iterations) from the caller. */
 int effdet_sgd_momentum_step(float *w, const float *g, float *v, size_t n, float lr_t,
                              float momentum, float grad_scale, void *stream);
+/* Same update, lr_t read from device memory (one float): the launch can sit in a CUDA graph while the schedule
+ * changes the rate every step (compiled plans, effdet_replay_step). */
+int effdet_sgd_momentum_step_dev_lr(float *w, const float *g, float *v, size_t n, const float *lr_dev,
+                                    float momentum, float grad_scale, void *stream);
 
 /* ---------------------------------------------------------------- training the backbone
  * (train_tpu.py without --freeze-backbone; BASELINE config 4).
@@ -479,6 +483,25 @@ int effdet_detect(effdet_plan_t *plan, const void *images, const float *anchors,
 int effdet_detect_host(effdet_plan_t *plan, const void *images_host, const float *anchors_host,
                        float score_threshold, float iou_threshold, int max_detections, float *boxes_host,
                        float *scores_host, int32_t *labels_host);
+
+/* ---------------------------------------------------------------- plan level, training: compiled plans
+ * The training step the reference runs per replica (train_tpu.py:249-346: anchor targets -> forward in training
+ * mode -> focal + smooth-L1 -> backward -> SGD) as ONE call from any host language.  The launch list is lowered by
+ * efficientdet_b200/train.py and written by efficientdet_b200.plan_export.export_train_plan(model, batch, path)
+ * ("compile once"); this library loads it, owns the device regions and a CUDA graph of the launches, and replays
+ * them ("run anywhere") -- same launches, same arguments, bit-identical results to Trainer.train_on_batch.
+ * Named regions (effdet_replay_region): "images" (B,S,S,3) f32 (u8 for a uint8 plan), "gt_boxes" (B,kmax,4) f64
+ * x1,y1,x2,y2, "gt_labels" (B,kmax) i32, "gt_counts" (B,) i32, "image_hw" (B,2) f64, "anchors" (N,4) f64,
+ * "losses" (8,) f32 ([0] focal, [1] smooth-L1), "weights" (the flat fp32 parameter buffer; the .json sidecar of
+ * the plan file lists offset and shape of every Keras weight), "lr" (one f32, written by effdet_replay_step).  The caller copies a batch into the input regions,
+ * calls effdet_replay_step with the step's learning rate (keras: lr / (1 + decay * iterations)) and reads
+ * "losses".  flags: 1 = no CUDA graph (launch eagerly). */
+typedef struct effdet_replay effdet_replay_t;
+int effdet_replay_load(const char *path, int flags, effdet_replay_t **out);
+int effdet_replay_num_launches(const effdet_replay_t *plan);
+int effdet_replay_region(effdet_replay_t *plan, const char *name, void **device_ptr, size_t *bytes);
+int effdet_replay_step(effdet_replay_t *plan, double learning_rate, void *stream);
+int effdet_replay_destroy(effdet_replay_t *plan);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,8 @@ def test_python_binding_covers_header():
                                      "effdet_conv_tc_block_n", "effdet_conv_weight_panel_elems",
                                      "effdet_se_backward_blocks", "effdet_dw_backward_blocks",
                                      "effdet_stem_wgrad_blocks", "effdet_plan_num_weights",
-                                     "effdet_plan_num_anchors", "effdet_plan_num_launches"}
+                                     "effdet_plan_num_anchors", "effdet_plan_num_launches",
+                                     "effdet_replay_num_launches"}
     missing = [n for n in _declared() if n not in bound]
     assert not missing, missing
 
@@ -64,3 +65,11 @@ def test_invalid_arguments_raise_without_gpu():
     with pytest.raises(ValueError):
         _lib.call("effdet_anchors_for_shape_host", None, one.ctypes.data, one.ctypes.data,
                   1, r.ctypes.data, 1, s.ctypes.data, 1, out.ctypes.data, 1)
+
+
+def test_replay_thunks_are_up_to_date():
+    """csrc/replay_thunks.inc (dispatch table of the compiled-plan replayer) is generated from the ctypes signature
+    table; the committed file must be what the generator produces now."""
+    from efficientdet_b200 import _gen_replay_thunks as g
+    assert open(g.OUT).read() == g.generate()
+    assert "thunk_effdet_conv2d" in g.generate() and "thunk_effdet_sgd_momentum_step_dev_lr" in g.generate()
