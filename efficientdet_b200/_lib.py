@@ -61,6 +61,8 @@ _SIGNATURES = {
     "effdet_conv2d": [c_void_p, c_void_p],
     "effdet_conv_weight_panel": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                  c_void_p],
+    "effdet_split_bf16": [c_void_p, c_void_p, c_size_t, c_int, c_void_p],
+    "effdet_conv_weight_panel_split": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "effdet_dwconv": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                       c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "effdet_se_gate": [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -157,6 +159,7 @@ class ConvDesc(ctypes.Structure):
         ("keep", c_void_p),
         ("act", c_int), ("in_dtype", c_int), ("out_dtype", c_int),
         ("weight_bf16", c_void_p), ("allow_tensor_core", c_int), ("weight_per_sample", c_int),
+        ("split_planes", c_int),
     ]
 
 
@@ -203,6 +206,8 @@ def load():
     lib.effdet_conv_tc_block_n.argtypes = [c_int]
     lib.effdet_conv_weight_panel_elems.restype = c_size_t
     lib.effdet_conv_weight_panel_elems.argtypes = [c_int, c_int, c_int]
+    lib.effdet_conv_weight_panel_split_elems.restype = c_size_t
+    lib.effdet_conv_weight_panel_split_elems.argtypes = [c_int, c_int, c_int]
     lib.effdet_se_backward_blocks.restype = c_int
     lib.effdet_se_backward_blocks.argtypes = [c_int, c_int, c_int]
     lib.effdet_dw_backward_blocks.restype = c_int

@@ -518,6 +518,7 @@ extern "C" int effdet_conv2d(const effdet_conv_desc *d, void *stream) {
         const int rc = effdet_conv2d_tc(d, stream);
         if (rc != EFFDET_E_UNSUPPORTED) return rc;
     }
+    EFFDET_REQUIRE(!d->split_planes, "split_planes descriptors run on the tensor-core path only (shape not supported)");
     EFFDET_REQUIRE(d->weight, "shape not supported by the tensor-core path and no fp32 weight given");
     ConvParams p;
     memset(&p, 0, sizeof(p));

@@ -106,6 +106,7 @@ struct alignas(64) TcParams {
     CUtensorMap b_map;
     TcGroup g[kTcMaxGroups];
     int n_groups, B, Cout, ksize, kblocks_per_tap, block_n, stages, tmem_cols;
+    int split, kb_plane, plane_stride;   // split-bf16 fp32 mode: K blocks per plane segment, channels between planes
     int act, out_f32, b_per_sample, total_tiles, n_tiles, any_tma_store;
     // halo mode (3x3, stride 1, Cin <= 64, weights resident): one ring stage = three kx-shifted copies of
     // the activation patch with a halo row above / below; tap (ky, kx) is the 128-pixel range of copy kx
@@ -272,10 +273,17 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                 for (int kb = 0; kb < num_k; ++kb, ++it) {
                     const int s = it % p.stages, ph = (it / p.stages) & 1;
                     mbar_wait_backoff(&empty[s], ph ^ 1, 256);
-                    const int tap = kb / p.kblocks_per_tap, kc = (kb - tap * p.kblocks_per_tap) * kTileK;
+                    const int tap = kb / p.kblocks_per_tap, kbt = kb - tap * p.kblocks_per_tap, kc = kbt * kTileK;
                     const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+                    // split-bf16 fp32 mode: the K extent is [hi | lo | hi] against [Whi | Whi | Wlo]; the activation
+                    // tensor holds the two planes side by side (plane_stride channels apart)
+                    int ka = kc;
+                    if (p.split) {
+                        const int seg = kbt / p.kb_plane;
+                        ka = (kbt - seg * p.kb_plane) * kTileK + (seg == 1 ? p.plane_stride : 0);
+                    }
                     mbar_expect_tx(&full[s], (uint32_t)(kATileBytes + (p.b_resident ? 0 : b_tile_bytes)));
-                    tma_load_4d(sA + (size_t)s * kATileBytes, amap, &full[s], kc, c.x0 * p.stride + kx - p.pad_l[c.gi],
+                    tma_load_4d(sA + (size_t)s * kATileBytes, amap, &full[s], ka, c.x0 * p.stride + kx - p.pad_l[c.gi],
                                 c.y0 * p.stride + ky - p.pad_t[c.gi], c.b0);
                     if (!p.b_resident)
                         tma_load_3d(sB + (size_t)s * b_tile_bytes, &p.b_map, &full[s], kc, c.n0,
@@ -1114,6 +1122,87 @@ extern "C" int effdet_conv_weight_panel(const float *w, void *panel, int taps, i
     return EFFDET_OK;
 }
 
+// ------------------------------------------------------------------ fp32 accuracy mode on the tensor cores
+// x = hi + lo + O(2^-18 |x|) with hi = bf16(x), lo = bf16(x - hi).  The convolution of an fp32 tensor by fp32
+// weights becomes ONE bf16 GEMM over the K extent [hi | lo | hi] x [Whi | Whi | Wlo] with fp32 accumulation in
+// TMEM (the lo * Wlo term, ~2^-18 of the product, is dropped): three times the MMAs of the bf16 speed mode instead
+// of the SIMT fp32 kernel (78 of the 145 ms of a D2 / batch-64 forward were its head convolutions).
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ out, size_t n_vec, int C4) {
+    // thread = 4 consecutive channels of one row: one 16-byte load, two 8-byte stores (hi plane, lo plane)
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * 256) {
+        const size_t row = i / (size_t)C4;
+        const int c4 = (int)(i - row * (size_t)C4);
+        const float4 v = *reinterpret_cast<const float4 *>(x + i * 4);
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y),
+                            h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+        __nv_bfloat162 hi[2] = {__halves2bfloat162(h0, h1), __halves2bfloat162(h2, h3)};
+        __nv_bfloat162 lo[2] = {__floats2bfloat162_rn(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1)),
+                                __floats2bfloat162_rn(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3))};
+        __nv_bfloat16 *o = out + row * (size_t)(8 * C4) + (size_t)c4 * 4;
+        *reinterpret_cast<uint2 *>(o) = *reinterpret_cast<uint2 *>(hi);
+        *reinterpret_cast<uint2 *>(o + 4 * C4) = *reinterpret_cast<uint2 *>(lo);
+    }
+}
+
+// panel[z][n][3 * Kp]: k in [0, Kp) = Whi, [Kp, 2 Kp) = Whi again, [2 Kp, 3 Kp) = Wlo of w[z][k][n] (* gate[z][k])
+__global__ void __launch_bounds__(256)
+weight_panel_split_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ panel, int taps, int Cin,
+                          int Cout, int Kp, int Npad, const float *__restrict__ gate, int nb) {
+    EFFDET_PDL_SYNC();
+    const unsigned per = (unsigned)Npad * Kp;
+    const unsigned total = (unsigned)(gate ? nb : taps) * per;
+    for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+        const unsigned z = i / per, rem = i - z * per;
+        const int n = (int)(rem / Kp), k = (int)(rem - (unsigned)n * Kp);
+        float v = 0.f;
+        if (k < Cin && n < Cout) {
+            if (gate) v = w[(size_t)k * Cout + n] * gate[(size_t)z * Cin + k];
+            else v = w[((size_t)z * Cin + k) * Cout + n];
+        }
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        __nv_bfloat16 *row = panel + ((size_t)z * Npad + n) * (size_t)(3 * Kp);
+        row[k] = hi; row[Kp + k] = hi; row[2 * Kp + k] = lo;
+    }
+}
+
+extern "C" int effdet_split_bf16(const float *x, void *out, size_t rows, int C, void *stream) {
+    EFFDET_REQUIRE(x && out && C > 0 && C % 4 == 0, "C must be a multiple of 4");
+    EFFDET_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "16-byte alignment");
+    const size_t n_vec = rows * (size_t)(C / 4);
+    if (n_vec == 0) return EFFDET_OK;
+    unsigned blocks = cdiv(n_vec, 256);
+    if (blocks > (unsigned)kNumSMs * 16) blocks = kNumSMs * 16;
+    split_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, static_cast<__nv_bfloat16 *>(out), n_vec, C / 4);
+    EFFDET_CUDA(cudaGetLastError());
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
+extern "C" size_t effdet_conv_weight_panel_split_elems(int taps_or_samples, int Cin, int Cout) {
+    const int K3 = 3 * round_up(Cin, kTileK);
+    const int a = round_up(Cout, tc_block_n(Cout, 3)), b = round_up(Cout, tc_block_n(Cout, 8));
+    return (size_t)taps_or_samples * (a > b ? a : b) * K3;
+}
+
+extern "C" int effdet_conv_weight_panel_split(const float *w, void *panel, int taps, int Cin, int Cout,
+                                              const float *gate, int B, void *stream) {
+    EFFDET_REQUIRE(w && panel && taps > 0 && Cin > 0 && Cout > 0, "bad arguments");
+    EFFDET_REQUIRE(!gate || (taps == 1 && B > 0), "gate only for 1x1");
+    const int Kp = round_up(Cin, kTileK);
+    const int bn = tc_block_n(Cout, (gate ? 1 : taps) * 3 * (Kp / kTileK));
+    const int Npad = round_up(Cout, bn);
+    const size_t total = (size_t)(gate ? B : taps) * Npad * Kp;
+    EFFDET_REQUIRE(total < 0xffffffffull, "panel too large");
+    unsigned blocks = cdiv(total, 256);
+    if (blocks > (unsigned)kNumSMs * 16) blocks = kNumSMs * 16;
+    EFFDET_CUDA(launch_pdl(weight_panel_split_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), w,
+                           static_cast<__nv_bfloat16 *>(panel), taps, Cin, Cout, Kp, Npad, gate, B));
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}
+
 // Called by effdet_conv2d when the descriptor qualifies.  Returns EFFDET_E_UNSUPPORTED (without
 // touching the error string of a real failure) when the shape cannot take this path.
 int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
@@ -1125,11 +1214,15 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     if (!encode) return fail(EFFDET_E_CUDA, "effdet_conv2d: cuTensorMapEncodeTiled unavailable%s", "");
     static TcParams p;      // large; filled per call (single-threaded use per the ABI contract)
     memset(&p, 0, sizeof(p));
-    const int Kpad = round_up(d->Cin, kTileK);
+    const int split = d->split_planes ? 1 : 0;       // fp32 accuracy mode: [hi | lo | hi] x [Whi | Whi | Wlo]
+    if (split && (d->out_dtype != EFFDET_F32 || d->relu_mask[0])) return EFFDET_E_UNSUPPORTED;
+    const int Kplane = round_up(d->Cin, kTileK);
+    const int Kpad = (split ? 3 : 1) * Kplane;       // K extent of the GEMM = of the weight panel
     const int bn = tc_block_n(d->Cout, d->kh * d->kw * (Kpad / kTileK));
     const int Npad = round_up(d->Cout, bn);
     p.n_groups = d->n_groups; p.B = d->B; p.Cout = d->Cout; p.ksize = d->kh; p.stride = d->stride;
     p.kblocks_per_tap = Kpad / kTileK; p.block_n = bn;
+    p.split = split; p.kb_plane = Kplane / kTileK; p.plane_stride = d->Cin;
     const int num_k = d->kh * d->kw * p.kblocks_per_tap;
     const int acc_pow2 = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
     // two accumulators (epilogue of tile i overlaps the MMAs of tile i+1) unless the tile is wide
@@ -1142,7 +1235,7 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     p.scale = d->scale; p.shift = d->shift; p.keep = d->keep;
     const int b_tile_bytes = bn * kTileK * 2;
     // halo mode: 3x3 stride 1, one K block per tap, one N tile, all nine weight tiles resident (<= 80 KiB)
-    p.halo = (d->kh == 3 && d->stride == 1 && Kpad == kTileK && Npad == bn && !d->weight_per_sample &&
+    p.halo = (d->kh == 3 && d->stride == 1 && Kpad == kTileK && !split && Npad == bn && !d->weight_per_sample &&
               9 * b_tile_bytes <= 80 * 1024 && getenv("EFFDET_NO_CONV_HALO") == nullptr) ? 1 : 0;
     p.box_stride = 20 * 1024;                         // (16, 8+2) or (8, 16+2) pixels x 128 bytes
     p.a_stage_bytes = p.halo ? 3 * p.box_stride : kATileBytes;
@@ -1193,11 +1286,11 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
         g.lw = 31 - __builtin_clz(g.Wt); g.lh = 31 - __builtin_clz(g.Ht);
         g.tile_begin = tiles;
         tiles += g.tiles_x * g.tiles_y * g.tiles_b;
-        const long long ldx = d->ldx[i] ? d->ldx[i] : d->Cin;
+        const long long ldx = d->ldx[i] ? d->ldx[i] : (split ? 2 : 1) * (long long)d->Cin;
         const long long xbs = d->x_batch_stride[i] ? d->x_batch_stride[i] : (long long)Hin * Win * ldx;
         if ((ldx * 2) % 16 || (xbs * 2) % 16 || (reinterpret_cast<uintptr_t>(d->x[i]) & 15)) return EFFDET_E_UNSUPPORTED;
         if (g.Wt * sd > 256 || g.Ht * sd > 256) return EFFDET_E_UNSUPPORTED;
-        cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)d->B};
+        cuuint64_t dims[4] = {(cuuint64_t)((split ? 2 : 1) * d->Cin), (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)d->B};
         cuuint64_t strides[3] = {(cuuint64_t)ldx * 2, (cuuint64_t)ldx * 2 * Win, (cuuint64_t)xbs * 2};
         cuuint32_t box[4] = {(cuuint32_t)kTileK, (cuuint32_t)(g.Wt * sd), (cuuint32_t)((g.Ht + (p.halo ? 2 : 0)) * sd),
                              (cuuint32_t)g.Bt};

@@ -81,7 +81,7 @@ struct effdet_plan {
     struct Folded { float *scale, *shift; int C; float eps; std::string bn; };
     std::vector<Folded> folded;
     std::map<std::string, int> folded_index;
-    struct Panel { std::string key; int taps, cin, cout; void *ptr; };
+    struct Panel { std::string key; int taps, cin, cout; void *ptr; bool split; };
     std::vector<Panel> panels;
     float *lut = nullptr;                  // (3,256) normalisation table of the uint8 stem
     // launch list
@@ -220,10 +220,12 @@ void add_op(effdet_plan *p, std::vector<int> ins, std::vector<int> outs, std::fu
     Op op; op.ins = std::move(ins); op.outs = std::move(outs); op.run = std::move(run);
     p->ops.push_back(std::move(op));
 }
-void *static_panel(effdet_plan *p, const std::string &key, int taps, int cin, int cout) {
+void *static_panel(effdet_plan *p, const std::string &key, int taps, int cin, int cout, bool split = false) {
     for (auto &q : p->panels) if (q.key == key) return q.ptr;
-    effdet_plan::Panel q; q.key = key; q.taps = taps; q.cin = cin; q.cout = cout; q.ptr = nullptr;
-    if (dev_alloc(p, &q.ptr, effdet_conv_weight_panel_elems(taps, cin, cout) * 2) != EFFDET_OK) return nullptr;
+    effdet_plan::Panel q; q.key = key; q.taps = taps; q.cin = cin; q.cout = cout; q.ptr = nullptr; q.split = split;
+    const size_t elems = split ? effdet_conv_weight_panel_split_elems(taps, cin, cout)
+                               : effdet_conv_weight_panel_elems(taps, cin, cout);
+    if (dev_alloc(p, &q.ptr, elems * 2) != EFFDET_OK) return nullptr;
     p->panels.push_back(q);
     return q.ptr;
 }
@@ -245,10 +247,37 @@ struct ConvArgs {
 int emit_conv(effdet_plan *p, const ConvArgs &a) {
     const int n = (int)a.xs.size();
     const int in_dt = a.in_dtype < 0 ? p->dtype : a.in_dtype, out_dt = a.out_dtype < 0 ? p->dtype : a.out_dtype;
-    const bool use_tc = in_dt == EFFDET_BF16 && a.cin % 8 == 0 && (a.stride == 1 || (a.stride == 2 && a.gate < 0));
+    bool use_tc = in_dt == EFFDET_BF16 && a.cin % 8 == 0 && (a.stride == 1 || (a.stride == 2 && a.gate < 0));
+    // fp32 accuracy mode: the tensor-core kernel on the bf16 hi | lo split of the fp32 activations (engine.py
+    // Plan.conv `split`; EFFDET_FP32_TC=0 keeps the exact SIMT kernel)
+    static const bool fp32_tc = !(getenv("EFFDET_FP32_TC") && atoi(getenv("EFFDET_FP32_TC")) == 0);
+    const bool split = fp32_tc && in_dt == EFFDET_F32 && out_dt == EFFDET_F32 && a.cin % 8 == 0 &&
+                       (a.stride == 1 || (a.stride == 2 && a.gate < 0));
     int gate_panel = -1;
     void *panel = nullptr;
-    if (use_tc && a.gate >= 0) {
+    std::vector<int> xs_used = a.xs;
+    if (split) {
+        for (int i = 0; i < n; ++i) {
+            const int xf = a.xs[i], H = a.H[i], Wd = a.Wd[i], cin = a.cin, B = p->B;
+            const int xv = new_val(p, (size_t)B * H * Wd * 2 * cin * 2);
+            xs_used[i] = xv;
+            add_op(p, {xf}, {xv}, [=](cudaStream_t st) {
+                return effdet_split_bf16((const float *)p->vals[xf].ptr, p->vals[xv].ptr, (size_t)B * H * Wd, cin, st);
+            });
+        }
+        if (a.gate >= 0) {
+            gate_panel = new_val(p, effdet_conv_weight_panel_split_elems(p->B, a.cin, a.cout) * 2);
+            const int gv = a.gate, gp = gate_panel, cin = a.cin, cout = a.cout, B = p->B;
+            const std::string wk = a.weight;
+            add_op(p, {gv}, {gp}, [=](cudaStream_t st) {
+                return effdet_conv_weight_panel_split(p->w(wk), p->vals[gp].ptr, 1, cin, cout, (const float *)p->vals[gv].ptr, B, st);
+            });
+        } else {
+            panel = static_panel(p, a.weight, a.k * a.k, a.cin, a.cout, true);
+            if (!panel) return EFFDET_E_CUDA;
+        }
+        use_tc = true;
+    } else if (use_tc && a.gate >= 0) {
         gate_panel = new_val(p, effdet_conv_weight_panel_elems(p->B, a.cin, a.cout) * 2);
         const int gv = a.gate, gp = gate_panel, cin = a.cin, cout = a.cout, B = p->B;
         const std::string wk = a.weight;
@@ -269,10 +298,12 @@ int emit_conv(effdet_plan *p, const ConvArgs &a) {
         d->y_batch_stride[i] = a.ybs.empty() ? 0 : a.ybs[i];
     }
     d->B = p->B; d->Cin = a.cin; d->Cout = a.cout; d->kh = d->kw = a.k; d->stride = a.stride;
-    d->scale = a.scale; d->shift = a.shift; d->act = a.act; d->in_dtype = in_dt; d->out_dtype = out_dt;
+    d->scale = a.scale; d->shift = a.shift; d->act = a.act; d->in_dtype = split ? EFFDET_BF16 : in_dt; d->out_dtype = out_dt;
     d->allow_tensor_core = use_tc ? 1 : 0;
-    const ConvArgs args = a;
-    std::vector<int> ins = a.xs, outs;
+    d->split_planes = split ? 1 : 0;
+    ConvArgs args = a;
+    args.xs = xs_used;
+    std::vector<int> ins = xs_used, outs;
     for (int r : a.residuals) if (r >= 0) ins.push_back(r);
     if (a.gate >= 0) ins.push_back(a.gate);
     if (gate_panel >= 0) ins.push_back(gate_panel);
@@ -510,7 +541,8 @@ int finalize(effdet_plan *p, cudaStream_t st) {
         if (rc) return rc;
     }
     for (auto &q : p->panels) {
-        int rc = effdet_conv_weight_panel(p->w(q.key), q.ptr, q.taps, q.cin, q.cout, 0, nullptr, 0, st);
+        int rc = q.split ? effdet_conv_weight_panel_split(p->w(q.key), q.ptr, q.taps, q.cin, q.cout, nullptr, 0, st)
+                         : effdet_conv_weight_panel(p->w(q.key), q.ptr, q.taps, q.cin, q.cout, 0, nullptr, 0, st);
         if (rc) return rc;
     }
     if (!p->graph && !(p->flags & EFFDET_PLAN_NO_GRAPH)) {

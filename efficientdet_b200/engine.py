@@ -131,8 +131,32 @@ class Plan:
         # (BiFPN P6/P7 laterals) samples every other pixel through the tensor map's element strides
         use_tc = (self.net.use_tensor_cores and in_dt == BF16 and cin % 8 == 0 and
                   (stride == 1 or (stride == 2 and gate is None)))
+        # fp32 accuracy mode of an INFERENCE plan: the same tensor-core kernel on the bf16 hi | lo split of the fp32
+        # activations, three-term product accumulated in fp32 (effdet_conv_desc.split_planes); training plans keep
+        # the exact SIMT kernel (their fp32 tests pin gradients to 1e-5)
+        split = (self.fp32_tensor_cores() and in_dt == F32 and out_dt == F32 and cin % 8 == 0 and
+                 (stride == 1 or (stride == 2 and gate is None)))
         panel = gate_panel = None
-        if use_tc and gate is not None:
+        if split:
+            lib = _lib.load()
+            xs_f32 = xs
+            xs = [self.val(tuple(x.shape[:3]) + (2 * cin,), BF16, name + "_split%d" % i) for i, x in enumerate(xs_f32)]
+            for xf, xv in zip(xs_f32, xs):
+                rows = xf.shape[0] * xf.shape[1] * xf.shape[2]
+                self.add("split", [xf], [xv],
+                         (lambda xf=xf, xv=xv, rows=rows: _call("effdet_split_bf16", xf.ptr, xv.ptr, rows, cin)),
+                         name + "_split")
+            if gate is not None:
+                gate_panel = self.val((lib.effdet_conv_weight_panel_split_elems(self.B, cin, cout),), BF16,
+                                      name + "_gated_panel")
+                self.add("panel", [gate], [gate_panel],
+                         lambda: _call("effdet_conv_weight_panel_split", wt.data_ptr(), gate_panel.ptr, 1, cin, cout,
+                                       gate.ptr, self.B), name + "_panel")
+            else:
+                panel = self.net.static_panel(weight_key, k * k, cin, cout, "split")
+            in_dt = BF16
+            use_tc = True
+        elif use_tc and gate is not None:
             lib = _lib.load()
             gate_panel = self.val((lib.effdet_conv_weight_panel_elems(self.B, cin, cout),), BF16,
                                   name + "_gated_panel")
@@ -159,6 +183,7 @@ class Plan:
             d.gate = gate.ptr if gate is not None else None
             d.keep = keep.data_ptr() if keep is not None else None
             d.act, d.in_dtype, d.out_dtype = act, in_dt, out_dt
+            d.split_planes = 1 if split else 0
             if gate_panel is not None:
                 d.weight_bf16, d.weight_per_sample = gate_panel.ptr, 1
             elif panel is not None:
@@ -440,6 +465,12 @@ class Plan:
 
     def lane_hint(self, op, n_lanes):
         return None
+
+    def fp32_tensor_cores(self):
+        """fp32 accuracy mode: run the dense convolutions on the tensor cores through the split-bf16 form
+        (inference plans; EFFDET_FP32_TC=0 keeps the exact SIMT kernel)."""
+        return (type(self) is Plan and self.net.use_tensor_cores and self.dtype == F32 and
+                os.environ.get("EFFDET_FP32_TC", "1") != "0")
 
     def dependencies(self):
         """Per launch: the earlier launches it must follow -- last writer of every buffer it reads (RAW), last

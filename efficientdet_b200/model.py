@@ -54,7 +54,7 @@ class Network:
         self.w_bifpn = w_bifpns[phi]
         self.d_bifpn = 2 + phi
         self.head_depth = 3 + int(phi / 3)
-        self.use_tensor_cores = bool(tensor_cores)   # bf16 mode: tcgen05 convolutions
+        self.use_tensor_cores = bool(tensor_cores)   # bf16 mode: tcgen05 convolutions; fp32 mode: split-bf16 (3 terms)
         self.weights = collections.OrderedDict()
         self.bn_layers = collections.OrderedDict()     # bn layer name -> (C, eps)
         self.folded = {}
@@ -202,8 +202,11 @@ class Network:
             self._panels = {}
         k = (key, mode)
         if k not in self._panels:
-            n = _lib.load().effdet_conv_weight_panel_elems(taps, cin if mode == 0 else cout,
-                                                           cout if mode == 0 else cin)
+            if mode == "split":
+                n = _lib.load().effdet_conv_weight_panel_split_elems(taps, cin, cout)
+            else:
+                n = _lib.load().effdet_conv_weight_panel_elems(taps, cin if mode == 0 else cout,
+                                                               cout if mode == 0 else cin)
             t = torch.empty(n, dtype=torch.bfloat16, device=self.device)
             self._panels[k] = (t, taps, cin, cout)
             self._build_panel(k)
@@ -211,6 +214,10 @@ class Network:
 
     def _build_panel(self, k):
         t, taps, cin, cout = self._panels[k]
+        if k[1] == "split":       # fp32 accuracy mode on the tensor cores: [Whi | Whi | Wlo]
+            _lib.call("effdet_conv_weight_panel_split", self.weights[k[0]].data_ptr(), t.data_ptr(), taps, cin,
+                      cout, None, 0, _lib.stream_ptr(self.device))
+            return
         _lib.call("effdet_conv_weight_panel", self.weights[k[0]].data_ptr(), t.data_ptr(), taps, cin, cout,
                   k[1], None, 0, _lib.stream_ptr(self.device))
 

@@ -189,6 +189,11 @@ typedef struct effdet_conv_desc {
     const void *weight_bf16; /* optional bf16 panel from effdet_conv_weight_panel for the tcgen05 path */
     int allow_tensor_core;   /* 0 = force the SIMT fp32-accumulate kernel */
     int weight_per_sample;   /* weight_bf16 holds one panel per image (SE gate folded in) */
+    int split_planes;        /* fp32 accuracy mode on the tensor cores: x is the (B,H,W,2*Cin) bf16 hi | lo split of an
+                                fp32 tensor (effdet_split_bf16), weight_bf16 a panel from
+                                effdet_conv_weight_panel_split, out_dtype EFFDET_F32.  The convolution is then the
+                                three-term product hi*Whi + lo*Whi + hi*Wlo accumulated in fp32 (one GEMM with 3x the
+                                K extent): ~2^-18 relative per product. */
 } effdet_conv_desc;
 int effdet_conv2d(const effdet_conv_desc *desc, void *stream);
 
@@ -203,6 +208,13 @@ int effdet_conv_tc_block_n(int n);
 size_t effdet_conv_weight_panel_elems(int taps_or_samples, int K, int N);
 int effdet_conv_weight_panel(const float *kernel, void *panel, int taps, int Cin, int Cout, int mode,
                              const float *gate, int B, void *stream);
+/* fp32 accuracy mode on the tensor cores (split_planes in the descriptor).  effdet_split_bf16: out (rows, 2*C) bf16
+ * = [hi | lo] with hi = bf16(x), lo = bf16(x - hi) for x (rows, C) f32.  effdet_conv_weight_panel_split: forward
+ * panel[tap or image][Cout_pad][3 * Cin_pad] = [Whi | Whi | Wlo] of the (gated) kernel; _elems gives its size. */
+int effdet_split_bf16(const float *x, void *out, size_t rows, int C, void *stream);
+size_t effdet_conv_weight_panel_split_elems(int taps_or_samples, int Cin, int Cout);
+int effdet_conv_weight_panel_split(const float *kernel, void *panel, int taps, int Cin, int Cout,
+                                   const float *gate, int B, void *stream);
 
 /* Depthwise kxk (k = 3 or 5, stride 1 or 2, SAME) + BN + activation; optionally writes
  * per-(image, block, channel) partial spatial SUMS of the activated output into se_sum

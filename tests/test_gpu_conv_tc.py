@@ -235,3 +235,102 @@ def test_conv_wgrad_tc(k, cin, cout, ldz, sizes, B):
         # bias gradient from the same launch (ones block in the spare half of the last tap pair)
         want = sum(keep[2 * i + 1][..., :cout].double().sum((0, 1, 2)) for i in range(len(sizes))).cpu().numpy()
         assert rel_err(dbias.cpu().numpy(), want) < 1e-4
+
+
+# ------------------------------------------------------------------ fp32 accuracy mode on the tensor cores
+def _split(x):
+    """fp32 (B,H,W,C) cuda -> bf16 (B,H,W,2C) hi | lo planes (effdet_split_bf16)."""
+    from efficientdet_b200 import _lib
+    B, H, W, C = x.shape
+    out = torch.empty((B, H, W, 2 * C), dtype=torch.bfloat16, device="cuda")
+    _lib.call("effdet_split_bf16", x.data_ptr(), out.data_ptr(), B * H * W, C, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    return out
+
+
+def _panel_split(w, gate=None, B=0):
+    from efficientdet_b200 import _lib
+    lib = _lib.load()
+    k = w.shape[0]
+    taps, cin, cout = k * k, w.shape[2], w.shape[3]
+    n = lib.effdet_conv_weight_panel_split_elems(B if gate is not None else taps, cin, cout)
+    panel = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    wd = _d(w)
+    gd = _d(gate) if gate is not None else None
+    _lib.call("effdet_conv_weight_panel_split", wd.data_ptr(), panel.data_ptr(), taps, cin, cout,
+              gd.data_ptr() if gate is not None else None, B, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    return panel
+
+
+def _run_split(xs, panel, cin, cout, k, B, stride=1, act=0, scale=None, shift=None, res=None, per_sample=False):
+    from efficientdet_b200 import _lib
+    d = _lib.ConvDesc()
+    d.n_groups = len(xs)
+    outs = []
+    for i, x in enumerate(xs):
+        H = x.shape[1]
+        Ho = -(-H // stride)
+        y = torch.full((B, Ho, Ho, cout), float("nan"), device="cuda", dtype=torch.float32)
+        outs.append(y)
+        d.x[i], d.y[i] = x.data_ptr(), y.data_ptr()
+        d.residual[i] = res[i].data_ptr() if res else None
+        d.H[i] = d.W[i] = H
+    d.B, d.Cin, d.Cout, d.kh, d.kw, d.stride = B, cin, cout, k, k, stride
+    d.scale = scale.data_ptr() if scale is not None else None
+    d.shift = shift.data_ptr() if shift is not None else None
+    d.act, d.in_dtype, d.out_dtype = act, _lib.BF16, _lib.F32
+    d.weight_bf16, d.allow_tensor_core, d.weight_per_sample, d.split_planes = panel.data_ptr(), 1, int(per_sample), 1
+    _lib.call("effdet_conv2d", ctypes.byref(d), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    return outs
+
+
+def test_split_bf16_planes():
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal((2, 5, 7, 24)) * np.exp(rng.normal(0, 3, (2, 5, 7, 24)))).astype(np.float32)
+    s = _split(_d(x)).float().cpu().numpy()
+    hi, lo = s[..., :24], s[..., 24:]
+    assert np.array_equal(hi, _bf(x))
+    assert np.abs(x.astype(np.float64) - (hi.astype(np.float64) + lo)).max() <= 2.0 ** -17 * np.abs(x).max()
+    assert (np.abs(x - (hi + lo)) <= 2.0 ** -16 * np.abs(x) + 1e-38).all()
+
+
+@pytest.mark.parametrize("cin,cout,H,B,k,stride,act", [
+    (24, 144, 16, 3, 1, 1, 2), (1152, 320, 4, 2, 1, 1, 0), (40, 240, 20, 1, 1, 1, 2), (64, 64, 16, 2, 3, 1, 1),
+    (112, 112, 12, 2, 3, 1, 1), (320, 64, 16, 3, 3, 2, 0), (88, 36, 10, 2, 3, 1, 0)])
+def test_conv_fp32_on_tensor_cores(cin, cout, H, B, k, stride, act):
+    """split_planes: fp32 activations and weights through the bf16 tensor-core kernel as the three-term product
+    hi*Whi + lo*Whi + hi*Wlo, fp32 accumulate -- against the fp64 convolution of the UNROUNDED fp32 operands.
+    Bound 2e-5 (max-normalised; each product is good to ~2^-18, the epilogue's swish to ~2^-21)."""
+    rng = np.random.default_rng(cin * 7 + cout + k)
+    x = rng.standard_normal((B, H, H, cin)).astype(np.float32)
+    w = (rng.standard_normal((k, k, cin, cout)) / np.sqrt(cin * k * k)).astype(np.float32)
+    sc = rng.uniform(0.5, 1.5, cout).astype(np.float32); sh = rng.normal(0, 0.2, cout).astype(np.float32)
+    Ho = -(-H // stride)
+    res = rng.standard_normal((B, Ho, Ho, cout)).astype(np.float32)
+    y, = _run_split([_split(_d(x))], _panel_split(w), cin, cout, k, B, stride, act, _d(sc), _d(sh), res=[_d(res)])
+    from oracle import graph
+    r = graph.conv2d(torch.from_numpy(x).double().permute(0, 3, 1, 2), w.astype(np.float64), stride)
+    r = r * torch.from_numpy(sc).double().view(1, -1, 1, 1) + torch.from_numpy(sh).double().view(1, -1, 1, 1)
+    r = [lambda v: v, torch.relu, graph.swish, torch.sigmoid][act](r).permute(0, 2, 3, 1).numpy() + res
+    assert rel_err(y.cpu().numpy(), r) < 2e-5
+
+
+def test_conv_fp32_on_tensor_cores_gated_and_grouped():
+    """per-sample split panels (squeeze-excite gate folded in) and five pyramid levels in one launch."""
+    rng = np.random.default_rng(5)
+    B, cin, cout = 3, 144, 24
+    x = rng.standard_normal((B, 12, 12, cin)).astype(np.float32)
+    w = (rng.standard_normal((1, 1, cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    gate = rng.uniform(0, 1, (B, cin)).astype(np.float32)
+    y, = _run_split([_split(_d(x))], _panel_split(w, gate, B), cin, cout, 1, B, per_sample=True)
+    want = np.einsum("bhwc,bc,co->bhwo", x.astype(np.float64), gate.astype(np.float64), w[0, 0].astype(np.float64))
+    assert rel_err(y.cpu().numpy(), want) < 2e-5
+    from oracle import graph
+    w3 = (rng.standard_normal((3, 3, 64, 64)) / 24).astype(np.float32)
+    xs = [rng.standard_normal((2, h, h, 64)).astype(np.float32) for h in (16, 8, 4, 2, 1)]
+    ys = _run_split([_split(_d(v)) for v in xs], _panel_split(w3), 64, 64, 3, 2, act=1)
+    for v, y in zip(xs, ys):
+        r = torch.relu(graph.conv2d(torch.from_numpy(v).double().permute(0, 3, 1, 2), w3.astype(np.float64), 1))
+        assert rel_err(y.cpu().numpy(), r.permute(0, 2, 3, 1).numpy()) < 2e-5
