@@ -62,6 +62,8 @@ _SIGNATURES = {
     "effdet_conv_weight_panel": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                  c_void_p],
     "effdet_split_bf16": [c_void_p, c_void_p, c_size_t, c_int, c_void_p],
+    "effdet_dwconv_split_out": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_int, c_int, c_int, c_int, c_int, c_void_p],
     "effdet_conv_weight_panel_split": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "effdet_dwconv": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                       c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],

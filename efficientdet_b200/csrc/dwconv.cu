@@ -124,7 +124,10 @@ __device__ __forceinline__ void cp_async16_zfill(void *dst, const void *src, boo
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
 }
 
-template <typename T, int CV, int K, int S, int NCV, int ACT>
+// PLANES (fp32 only): the output is written as the bf16 hi | lo split (B, Ho, Wo, 2*C) that the tensor-core
+// convolution of the fp32 accuracy mode reads (effdet_split_bf16's layout) instead of the fp32 tensor: same bytes,
+// and the separate split pass over the widest tensors of the network (6x expanded) disappears.
+template <typename T, int CV, int K, int S, int NCV, int ACT, bool PLANES = false>
 __global__ void __launch_bounds__(NCV * (kDwTW / kDwStrip) * kDwTH)
 dwconv_tiled_kernel(const T *__restrict__ x, const float *__restrict__ w, const float *__restrict__ scale,
                     const float *__restrict__ shift, T *__restrict__ y, float *__restrict__ se_sum, int H,
@@ -201,7 +204,24 @@ dwconv_tiled_kernel(const T *__restrict__ x, const float *__restrict__ w, const 
                     acc[o][k] = activate<ACT>(acc[o][k] * sc[k] + sh[k]);
                     tot[k] += acc[o][k];
                 }
-                Vec<T, CV>::store(yb + ((size_t)oy * Wo + ox) * C + c, acc[o]);
+                if (PLANES) {
+                    static_assert(!PLANES || CV == 4, "split output is written for 4-channel fp32 threads");
+                    __nv_bfloat16 *yp = reinterpret_cast<__nv_bfloat16 *>(y) +
+                                        ((size_t)b * Ho * Wo + (size_t)oy * Wo + ox) * (size_t)(2 * C) + c;
+                    __nv_bfloat16 h[4];
+                    float l[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        h[k] = __float2bfloat16_rn(acc[o][k]);
+                        l[k] = acc[o][k] - __bfloat162float(h[k]);
+                    }
+                    __nv_bfloat162 hi[2] = {__halves2bfloat162(h[0], h[1]), __halves2bfloat162(h[2], h[3])};
+                    __nv_bfloat162 lo[2] = {__floats2bfloat162_rn(l[0], l[1]), __floats2bfloat162_rn(l[2], l[3])};
+                    *reinterpret_cast<uint2 *>(yp) = *reinterpret_cast<uint2 *>(hi);
+                    *reinterpret_cast<uint2 *>(yp + C) = *reinterpret_cast<uint2 *>(lo);
+                } else {
+                    Vec<T, CV>::store(yb + ((size_t)oy * Wo + ox) * C + c, acc[o]);
+                }
             }
         }
     }
@@ -222,7 +242,7 @@ dwconv_tiled_kernel(const T *__restrict__ x, const float *__restrict__ w, const 
     }
 }
 
-template <typename T, int CV, int K, int S, int NCV>
+template <typename T, int CV, int K, int S, int NCV, bool PLANES = false>
 static int launch_dw_tiled(const void *x, const float *w, const float *scale, const float *shift, void *y,
                            float *se_sum, int B, int H, int W, int C, int act, cudaStream_t st) {
     constexpr int CB = NCV * CV;
@@ -236,7 +256,7 @@ static int launch_dw_tiled(const void *x, const float *w, const float *scale, co
     dim3 grid(tx * ty, (C + CB - 1) / CB, B);
 #define DW_LAUNCH(A)                                                                                       \
     {                                                                                                      \
-        auto kern = dwconv_tiled_kernel<T, CV, K, S, NCV, A>;                                              \
+        auto kern = dwconv_tiled_kernel<T, CV, K, S, NCV, A, PLANES>;                                      \
         if (smem > 48 * 1024) EFFDET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, NT, smem, st>>>(static_cast<const T *>(x), w, scale, shift, static_cast<T *>(y), se_sum, H, W, \
                                      Ho, Wo, C, pt, pl, tx);                                               \
@@ -784,6 +804,26 @@ extern "C" int effdet_dwconv(const void *x, const float *kernel, const float *sc
     }
 #undef DW_CASE
     return fail(EFFDET_E_INVALID, "effdet_dwconv: bad dtype%s", "");
+}
+
+/* fp32 depthwise convolution whose output is the bf16 hi | lo split (B, Ho, Wo, 2*C) -- see effdet_split_bf16 */
+extern "C" int effdet_dwconv_split_out(const float *x, const float *kernel, const float *scale, const float *shift,
+                                       void *y_planes, float *se_sum, int se_blocks, int B, int H, int W, int C,
+                                       int k, int stride, int act, void *stream) {
+    EFFDET_REQUIRE(x && kernel && scale && shift && y_planes, "null pointer");
+    EFFDET_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad sizes");
+    EFFDET_REQUIRE((k == 3 || k == 5) && (stride == 1 || stride == 2), "kernel 3 or 5, stride 1 or 2");
+    EFFDET_REQUIRE(al16(x) && al16(y_planes) && al16(kernel) && al16(scale) && al16(shift), "16B alignment");
+    if (se_sum)
+        EFFDET_REQUIRE(se_blocks == effdet_dwconv_se_blocks(B, H, W, C, stride, EFFDET_F32),
+                       "se_blocks must come from effdet_dwconv_se_blocks");
+    cudaStream_t st = as_stream(stream);
+#define DWP_CASE(K, S, NCV) return launch_dw_tiled<float, 4, K, S, NCV, true>(x, kernel, scale, shift, y_planes, se_sum, B, H, W, C, act, st)
+    if (k == 3 && stride == 1) DWP_CASE(3, 1, 8);
+    if (k == 5 && stride == 1) DWP_CASE(5, 1, 8);
+    if (k == 3 && stride == 2) DWP_CASE(3, 2, 4);
+    DWP_CASE(5, 2, 4);
+#undef DWP_CASE
 }
 
 extern "C" int effdet_se_gate(const float *se_sum, int se_blocks, float inv_hw, const float *w1,

@@ -241,6 +241,7 @@ struct ConvArgs {
     const float *scale = nullptr, *shift = nullptr;
     int act = EFFDET_ACT_NONE, gate = -1;
     int in_dtype = -1, out_dtype = -1;
+    bool pre_split = false;                 // xs already are the (B,H,W,2*cin) bf16 hi | lo planes of an fp32 tensor
 };
 
 // engine.Plan.conv: effdet_conv2d over 1..5 groups sharing the weights; tcgen05 path for bf16 activations
@@ -251,13 +252,13 @@ int emit_conv(effdet_plan *p, const ConvArgs &a) {
     // fp32 accuracy mode: the tensor-core kernel on the bf16 hi | lo split of the fp32 activations (engine.py
     // Plan.conv `split`; EFFDET_FP32_TC=0 keeps the exact SIMT kernel)
     static const bool fp32_tc = !(getenv("EFFDET_FP32_TC") && atoi(getenv("EFFDET_FP32_TC")) == 0);
-    const bool split = fp32_tc && in_dt == EFFDET_F32 && out_dt == EFFDET_F32 && a.cin % 8 == 0 &&
-                       (a.stride == 1 || (a.stride == 2 && a.gate < 0));
+    const bool split = a.pre_split || (fp32_tc && in_dt == EFFDET_F32 && out_dt == EFFDET_F32 && a.cin % 8 == 0 &&
+                                       (a.stride == 1 || (a.stride == 2 && a.gate < 0)));
     int gate_panel = -1;
     void *panel = nullptr;
     std::vector<int> xs_used = a.xs;
     if (split) {
-        for (int i = 0; i < n; ++i) {
+        for (int i = 0; i < n && !a.pre_split; ++i) {
             const int xf = a.xs[i], H = a.H[i], Wd = a.Wd[i], cin = a.cin, B = p->B;
             const int xv = new_val(p, (size_t)B * H * Wd * 2 * cin * 2);
             xs_used[i] = xv;
@@ -387,13 +388,21 @@ int build_ops(effdet_plan *p) {
             x = e;
         }
         const int Ho = (H + b.stride - 1) / b.stride;
-        const int dwv = act_val(p, Ho, Ho, b.cmid);
+        // fp32 accuracy mode on the tensor cores: the depthwise kernel writes the hi | lo planes the project
+        // convolution reads (engine.py _mbconv dw_split)
+        static const bool fp32_tc = !(getenv("EFFDET_FP32_TC") && atoi(getenv("EFFDET_FP32_TC")) == 0);
+        const bool dw_split = fp32_tc && dt == EFFDET_F32 && b.cmid % 8 == 0;
+        const int dwv = dw_split ? new_val(p, (size_t)B * Ho * Ho * 2 * b.cmid * 2) : act_val(p, Ho, Ho, b.cmid);
         const int nblk = effdet_dwconv_se_blocks(B, H, H, b.cmid, b.stride, dt);
         const int part = new_val(p, (size_t)B * nblk * b.cmid * 4);
         {
             const effdet_plan::Folded &f = p->folded[p->folded_index.at(q + "bn")];
             const int xi = x, Hi = H, cm = b.cmid, k = b.k, s = b.stride;
             add_op(p, {xi}, {dwv, part}, [=](cudaStream_t st) {
+                if (dw_split)
+                    return effdet_dwconv_split_out((const float *)p->vals[xi].ptr, p->w(q + "dwconv/depthwise_kernel"),
+                                                   f.scale, f.shift, p->vals[dwv].ptr, (float *)p->vals[part].ptr, nblk, B,
+                                                   Hi, Hi, cm, k, s, EFFDET_ACT_SWISH, st);
                 return effdet_dwconv(p->vals[xi].ptr, p->w(q + "dwconv/depthwise_kernel"), f.scale, f.shift, p->vals[dwv].ptr,
                                      (float *)p->vals[part].ptr, nblk, B, Hi, Hi, cm, k, s, EFFDET_ACT_SWISH, dt, st);
             });
@@ -414,7 +423,7 @@ int build_ops(effdet_plan *p) {
             ConvArgs a;
             a.xs = {dwv}; a.ys = {y}; a.H = {Ho}; a.Wd = {Ho};
             a.weight = q + "project_conv/kernel"; a.cin = b.cmid; a.cout = b.cout;
-            a.scale = f.scale; a.shift = f.shift; a.gate = gate;
+            a.scale = f.scale; a.shift = f.shift; a.gate = gate; a.pre_split = dw_split;
             a.residuals = {b.skip ? inp : -1};               // FixedDropout is the identity at inference (:300-303)
             if ((rc = emit_conv(p, a))) return rc;
         }

@@ -120,7 +120,7 @@ class Plan:
     # -------------------------------------------------------------- op emitters
     def conv(self, xs, ys, weight_key, cin, cout, k=1, stride=1, scale=None, shift=None, act=ACT_NONE,
              gate=None, keep=None, residuals=None, ldc=None, ybs=None, y_offsets=None,
-             in_dtype=None, out_dtype=None, name=""):
+             in_dtype=None, out_dtype=None, name="", pre_split=False):
         """xs / ys: lists of Vals (one per group).  y_offsets: byte offsets into ys[i]."""
         n = len(xs)
         residuals = residuals or [None] * n
@@ -134,18 +134,20 @@ class Plan:
         # fp32 accuracy mode of an INFERENCE plan: the same tensor-core kernel on the bf16 hi | lo split of the fp32
         # activations, three-term product accumulated in fp32 (effdet_conv_desc.split_planes); training plans keep
         # the exact SIMT kernel (their fp32 tests pin gradients to 1e-5)
-        split = (self.fp32_tensor_cores() and in_dt == F32 and out_dt == F32 and cin % 8 == 0 and
-                 (stride == 1 or (stride == 2 and gate is None)))
+        split = pre_split or (self.fp32_tensor_cores() and in_dt == F32 and out_dt == F32 and cin % 8 == 0 and
+                              (stride == 1 or (stride == 2 and gate is None)))
         panel = gate_panel = None
         if split:
             lib = _lib.load()
-            xs_f32 = xs
-            xs = [self.val(tuple(x.shape[:3]) + (2 * cin,), BF16, name + "_split%d" % i) for i, x in enumerate(xs_f32)]
-            for xf, xv in zip(xs_f32, xs):
-                rows = xf.shape[0] * xf.shape[1] * xf.shape[2]
-                self.add("split", [xf], [xv],
-                         (lambda xf=xf, xv=xv, rows=rows: _call("effdet_split_bf16", xf.ptr, xv.ptr, rows, cin)),
-                         name + "_split")
+            if not pre_split:            # pre_split: the producer already wrote the (B,H,W,2*cin) hi | lo planes
+                xs_f32 = xs
+                xs = [self.val(tuple(x.shape[:3]) + (2 * cin,), BF16, name + "_split%d" % i)
+                      for i, x in enumerate(xs_f32)]
+                for xf, xv in zip(xs_f32, xs):
+                    rows = xf.shape[0] * xf.shape[1] * xf.shape[2]
+                    self.add("split", [xf], [xv],
+                             (lambda xf=xf, xv=xv, rows=rows: _call("effdet_split_bf16", xf.ptr, xv.ptr, rows, cin)),
+                             name + "_split")
             if gate is not None:
                 gate_panel = self.val((lib.effdet_conv_weight_panel_split_elems(self.B, cin, cout),), BF16,
                                       name + "_gated_panel")
@@ -263,15 +265,26 @@ class Plan:
                       act=ACT_SWISH, name=p + "expand_conv")
             x = e
         Ho = (H + blk.stride - 1) // blk.stride
-        d = self.val((B, Ho, Ho, cmid), name=p + "dw")
         s2, b2 = self.folded(p + "bn")
         nblk = lib.effdet_dwconv_se_blocks(B, H, H, cmid, blk.stride, self.dtype)
         part = self.val((B, nblk, cmid), F32, name=p + "se_partial")
-        self.add("dwconv", [x], [d, part],
-                 lambda: _call("effdet_dwconv", x.ptr, self.w(p + "dwconv/depthwise_kernel").data_ptr(),
-                               s2.data_ptr(), b2.data_ptr(), d.ptr, part.ptr, nblk, B, H, H, cmid,
-                               blk.kernel_size, blk.stride, ACT_SWISH, self.dtype), p + "dwconv",
-                 flops=2 * blk.kernel_size ** 2 * B * Ho * Ho * cmid)
+        # fp32 accuracy mode on the tensor cores: the depthwise output feeds only the project convolution, so the
+        # kernel writes it as the bf16 hi | lo split that convolution reads (no fp32 copy, no separate split pass)
+        dw_split = self.fp32_tensor_cores() and cmid % 8 == 0 and not self.keep_taps
+        if dw_split:
+            d = self.val((B, Ho, Ho, 2 * cmid), BF16, name=p + "dw_split")
+            self.add("dwconv", [x], [d, part],
+                     lambda: _call("effdet_dwconv_split_out", x.ptr, self.w(p + "dwconv/depthwise_kernel").data_ptr(),
+                                   s2.data_ptr(), b2.data_ptr(), d.ptr, part.ptr, nblk, B, H, H, cmid,
+                                   blk.kernel_size, blk.stride, ACT_SWISH), p + "dwconv",
+                     flops=2 * blk.kernel_size ** 2 * B * Ho * Ho * cmid)
+        else:
+            d = self.val((B, Ho, Ho, cmid), name=p + "dw")
+            self.add("dwconv", [x], [d, part],
+                     lambda: _call("effdet_dwconv", x.ptr, self.w(p + "dwconv/depthwise_kernel").data_ptr(),
+                                   s2.data_ptr(), b2.data_ptr(), d.ptr, part.ptr, nblk, B, H, H, cmid,
+                                   blk.kernel_size, blk.stride, ACT_SWISH, self.dtype), p + "dwconv",
+                     flops=2 * blk.kernel_size ** 2 * B * Ho * Ho * cmid)
         gate = self.val((B, cmid), F32, name=p + "gate")
         self.add("se", [part], [gate],
                  lambda: _call("effdet_se_gate", part.ptr, nblk, 1.0 / float(Ho * Ho),
@@ -283,7 +296,7 @@ class Plan:
         keep = self.drop_keep(blk)
         self.conv([d], [y], p + "project_conv/kernel", cmid, cout, scale=s3, shift=b3,
                   gate=gate, keep=keep, residuals=[inp] if blk.has_skip else None,
-                  name=p + "project_conv")
+                  name=p + "project_conv", pre_split=dw_split)
         return y, Ho
 
     def _build_neck_and_heads(self, feats):

@@ -212,6 +212,11 @@ int effdet_conv_weight_panel(const float *kernel, void *panel, int taps, int Cin
  * = [hi | lo] with hi = bf16(x), lo = bf16(x - hi) for x (rows, C) f32.  effdet_conv_weight_panel_split: forward
  * panel[tap or image][Cout_pad][3 * Cin_pad] = [Whi | Whi | Wlo] of the (gated) kernel; _elems gives its size. */
 int effdet_split_bf16(const float *x, void *out, size_t rows, int C, void *stream);
+/* effdet_dwconv for fp32 tensors with the OUTPUT written directly as that hi | lo split (B,Ho,Wo,2*C) bf16: the
+ * depthwise convolution of an MBConv block feeds only the project convolution (efficientnet.py:242-296). */
+int effdet_dwconv_split_out(const float *x, const float *kernel, const float *scale, const float *shift,
+                            void *y_planes, float *se_sum, int se_blocks, int B, int H, int W, int C, int k,
+                            int stride, int act, void *stream);
 size_t effdet_conv_weight_panel_split_elems(int taps_or_samples, int Cin, int Cout);
 int effdet_conv_weight_panel_split(const float *kernel, void *panel, int taps, int Cin, int Cout,
                                    const float *gate, int B, void *stream);

@@ -391,3 +391,33 @@ def test_letterbox_resize_on_device_bit_exact():
             want, scale, oh, ow = op.resize_image_ref(img, size)
             assert np.array_equal(out[j].cpu().numpy(), want), (size, img.shape)
             assert meta[j] == (scale, oh, ow)
+
+
+@pytest.mark.parametrize("k,stride,C,H", [(3, 1, 48, 20), (5, 1, 96, 17), (3, 2, 144, 22), (5, 2, 40, 19)])
+def test_dwconv_split_output_equals_dwconv_then_split(k, stride, C, H):
+    """fp32 accuracy mode on the tensor cores: the depthwise kernel writing the bf16 hi | lo planes directly
+    (effdet_dwconv_split_out) == effdet_dwconv followed by effdet_split_bf16, bit for bit, SE partial sums included."""
+    from efficientdet_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(k * 100 + C)
+    B = 2
+    Ho = -(-H // stride)
+    x = torch.from_numpy(rng.standard_normal((B, H, H, C)).astype(np.float32)).cuda()
+    w = torch.from_numpy((rng.standard_normal((k, k, C)) * 0.3).astype(np.float32)).cuda()
+    sc = torch.from_numpy(rng.uniform(0.5, 1.5, C).astype(np.float32)).cuda()
+    sh = torch.from_numpy(rng.normal(0, 0.2, C).astype(np.float32)).cuda()
+    nblk = lib.effdet_dwconv_se_blocks(B, H, H, C, stride, _lib.F32)
+    y = torch.empty((B, Ho, Ho, C), device="cuda")
+    p1 = torch.empty((B, nblk, C), device="cuda")
+    p2 = torch.empty((B, nblk, C), device="cuda")
+    st = _lib.stream_ptr()
+    _lib.call("effdet_dwconv", x.data_ptr(), w.data_ptr(), sc.data_ptr(), sh.data_ptr(), y.data_ptr(), p1.data_ptr(),
+              nblk, B, H, H, C, k, stride, _lib.ACT_SWISH, _lib.F32, st)
+    want = torch.empty((B, Ho, Ho, 2 * C), device="cuda", dtype=torch.bfloat16)
+    _lib.call("effdet_split_bf16", y.data_ptr(), want.data_ptr(), B * Ho * Ho, C, st)
+    got = torch.full((B, Ho, Ho, 2 * C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.call("effdet_dwconv_split_out", x.data_ptr(), w.data_ptr(), sc.data_ptr(), sh.data_ptr(), got.data_ptr(),
+              p2.data_ptr(), nblk, B, H, H, C, k, stride, _lib.ACT_SWISH, st)
+    torch.cuda.synchronize()
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+    assert torch.equal(p1, p2)
