@@ -80,7 +80,10 @@ def _ref(x_bf, w, act=0, scale=None, shift=None):
 
 
 @pytest.mark.parametrize("cin,cout,H,B,act", [(64, 64, 16, 2, 1), (24, 144, 16, 3, 2), (320, 64, 8, 2, 1),
-                                              (1152, 320, 4, 2, 0), (40, 240, 20, 1, 2), (88, 88, 10, 5, 1)])
+                                              (1152, 320, 4, 2, 0), (40, 240, 20, 1, 2), (88, 88, 10, 5, 1),
+                                              # D4 / D6 backbone widths (block 7: 448 -> 2688 -> 448, 576 -> 3456 -> 576)
+                                              (2688, 448, 8, 2, 0), (448, 2688, 8, 1, 2), (3456, 576, 6, 1, 0),
+                                              (576, 3456, 5, 2, 2), (1632, 272, 16, 2, 0)])
 def test_conv1x1_tc(cin, cout, H, B, act):
     from efficientdet_b200 import _lib
     rng = np.random.default_rng(cin + cout)
@@ -147,7 +150,12 @@ def test_conv1x1_tc_per_sample_gate():
 @pytest.mark.parametrize("W,cout,out_f32,B,sizes", [(64, 64, False, 4, [16, 8, 4, 2, 1]),
                                                     (64, 36, True, 2, [16, 8, 4, 2, 1]),
                                                     (88, 180, True, 2, [20, 10, 5]),
-                                                    (112, 810, True, 1, [12, 6, 3])])
+                                                    (112, 810, True, 1, [12, 6, 3]),
+                                                    # D4 (W 224, head depth 4) and D6 / D7 (W 384) head widths
+                                                    (224, 224, False, 2, [32, 16, 8, 4, 2]),
+                                                    (224, 810, True, 1, [16, 8, 4, 2, 1]),
+                                                    (384, 384, False, 1, [22, 11, 6, 3, 2]),
+                                                    (384, 36, True, 2, [11, 6, 3])])
 def test_conv3x3_head_tc_grouped(W, cout, out_f32, B, sizes):
     """All pyramid levels in one launch; fp32 outputs land in the concatenated (B, N, per) layout."""
     from efficientdet_b200 import _lib
