@@ -1218,8 +1218,26 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     if (split && (d->out_dtype != EFFDET_F32 || d->relu_mask[0])) return EFFDET_E_UNSUPPORTED;
     const int Kplane = round_up(d->Cin, kTileK);
     const int Kpad = (split ? 3 : 1) * Kplane;       // K extent of the GEMM = of the weight panel
-    const int bn = tc_block_n(d->Cout, d->kh * d->kw * (Kpad / kTileK));
-    const int Npad = round_up(d->Cout, bn);
+    const int bn_panel = tc_block_n(d->Cout, d->kh * d->kw * (Kpad / kTileK));      // N tile the weight panel was padded for
+    const int Npad = round_up(d->Cout, bn_panel);
+    // Few M tiles (batch 1, coarse pyramid levels): a 16 x 16 x 1152 -> 192 project convolution is TWO tiles, i.e. two
+    // SMs pulling 720 KB each through their TMA units while 146 idle (13 us; the batch-1 step is a chain of such
+    // launches).  Narrower N tiles (still multiples of 32, dividing the panel's padding) spread the weight stream
+    // over more SMs; the activation tile is re-read from L2 by each of them.  Not for the halo form (weights resident).
+    int bn = bn_panel;
+    {
+        const bool halo_ok = d->kh == 3 && d->stride == 1 && Kpad == kTileK && !split && Npad == bn_panel &&
+                             !d->weight_per_sample && 9 * bn_panel * kTileK * 2 <= 80 * 1024 &&
+                             getenv("EFFDET_NO_CONV_HALO") == nullptr;
+        static const int min_ctas = getenv("EFFDET_TC_MIN_CTAS") ? atoi(getenv("EFFDET_TC_MIN_CTAS")) : 64;
+        long m_est = 0;
+        for (int i = 0; i < d->n_groups; ++i) {
+            const long Ho = (d->H[i] + d->stride - 1) / d->stride, Wo = (d->W[i] + d->stride - 1) / d->stride;
+            m_est += ((long)d->B * Ho * Wo + kTileM - 1) / kTileM;
+        }
+        for (int c = (bn - 1) / 32 * 32; !halo_ok && c >= 32 && m_est * (Npad / bn) < min_ctas; c -= 32)
+            if (Npad % c == 0) bn = c;      // multiples of 32: no 32-column epilogue chunk straddles two tiles
+    }
     p.n_groups = d->n_groups; p.B = d->B; p.Cout = d->Cout; p.ksize = d->kh; p.stride = d->stride;
     p.kblocks_per_tap = Kpad / kTileK; p.block_n = bn;
     p.split = split; p.kb_plane = Kplane / kTileK; p.plane_stride = d->Cin;
