@@ -86,10 +86,10 @@ constexpr int kScanThreads = 256;
 constexpr int kScanElems = 4096;   // floats per block
 
 // class-specific scan.  One block = kScanElems consecutive floats of image blockIdx.y
-// (coalesced); class of element e is e % C.  FILL=false: per-(image,class) counts, plus ONE BIT per score
-// (score > thr) into `mask` (a warp's ballot == one 32-bit word; kScanElems is a multiple of 32).
+// (coalesced); class of element e is e % C.  FILL=false: per-(image,class) counts, plus ONE BIT per passing score
+// (score > thr) into the zero-filled `mask`.
 // FILL=true: reads only the mask -- 1/32 of the bytes of the scores; the second full pass over the (B, N, C)
-// scores was 0.69 ms of the 1.2 ms tail at D2 / batch 64 / 90 classes (profiles/r2_tail_ncu.txt) -- fetches the
+// scores was 0.69 ms of the 1.2 ms tail at D2 / batch 64 / 90 classes (profiles/r2_tail_ncu.txt; 0.25 ms now) -- fetches the
 // few passing scores and writes their keys at offsets[seg] + (block-reserved range); the order inside a segment
 // is arbitrary, the sort restores (score desc, index asc).
 template <bool FILL>
@@ -113,25 +113,22 @@ scan_scores_kernel(const float *__restrict__ cls, uint32_t NC, int C, float thr,
     uint32_t c = (e0 + tid) % C;
     uint32_t bits = 0;                                   // bit j: element j of this thread passes
     if constexpr (!FILL) {
-        // the streaming loop stays as plain as it can be (load, compare, rare shared-memory atomics): the compiler
-        // pipelines it to 6.5 TB/s; gathering the bits with a ballot per iteration (4.9 TB/s) or from a batch of
-        // tied loads (4.3 TB/s) measured slower.  The block's 4096 mask bits are collected in shared memory.
-        uint32_t *smask = sh + 2 * C;
-        for (int w = tid; w < kScanElems / 32; w += kScanThreads) smask[w] = 0;
-        __syncthreads();
+        // the streaming loop stays exactly the round-1 loop (load, compare, a rare atomic): it runs at the DRAM
+        // rate.  The mask is zero-filled by the launcher (cudaMemsetAsync, 1/32 of the scores' bytes) and the few
+        // passing scores set their bit with a global atomicOr.  Collecting the bits per block in shared memory slowed
+        // this pass from 0.39 to ~0.6 ms (the fill pass gained 0.44: same-box A/B of the whole tail 1.19 -> 0.98 ms;
+        // with this form 1.19 -> 0.77 ms); by warp ballot or from batches of tied loads it was slower still.
         for (uint32_t e = e0 + tid; e < e1; e += kScanThreads) {
             const float sc = p[e];
             if (sc > thr) {
                 atomicAdd(&hist[c], 1u);
-                atomicOr(&smask[(e - e0) >> 5], 1u << ((e - e0) & 31u));
+                atomicOr(&m[e >> 5], 1u << (e & 31u));
             }
             c += step; if (c >= (uint32_t)C) c -= C;
         }
         __syncthreads();
         for (int k = tid; k < C; k += kScanThreads)
             if (hist[k]) atomicAdd(&counts[(size_t)b * C + k], hist[k]);
-        for (int w = tid; w < kScanElems / 32; w += kScanThreads)
-            if (e0 + (uint32_t)w * 32u < e1) m[(e0 >> 5) + w] = smask[w];
         return;
     } else {
         // lane j loads the warp's j-th mask word; a shuffle hands it to the other lanes (one round trip)
@@ -548,9 +545,10 @@ extern "C" int effdet_filter_detections(const float *boxes, const float *classif
         if (class_specific) {
             const uint32_t NC = (uint32_t)(N * C);
             dim3 grid(cdiv(NC, kScanElems), B);
-            size_t sm = (2 * (size_t)C + kScanElems / 32) * sizeof(uint32_t);
+            size_t sm = 2 * (size_t)C * sizeof(uint32_t);
             EFFDET_REQUIRE(sm <= 48 * 1024, "too many classes");
             uint32_t *mask = reinterpret_cast<uint32_t *>(ws + L.mask);
+            EFFDET_CUDA(cudaMemsetAsync(mask, 0, 4 * L.mask_words * (size_t)B, st));
             scan_scores_kernel<false><<<grid, kScanThreads, sm, st>>>(
                 classification, NC, C, score_threshold, counts, offsets, cursor, keys, status, mask, (uint32_t)L.mask_words);
             EFFDET_LAUNCHED();
