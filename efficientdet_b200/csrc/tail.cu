@@ -5,7 +5,7 @@
 //
 // Replaces (reference file:line):
 //   RegressBoxes.py:126-164, ClipBoxes.py:9-24               -> boxes_kernel
-//   FilterDetections.py:9 (tf.where over score>thr)          -> scan_scores_kernel<false/true>
+//   FilterDetections.py:9 (tf.where over score>thr)          -> scan_scores_kernel + fill_keys_kernel (scan_rows_kernel)
 //   FilterDetections.py:16-21 (tf.image.non_max_suppression) -> sort_nms_{small,large}_kernel
 //   FilterDetections.py:85-111 (concat, top_k, gather, pad)  -> merge_topk_kernel
 #include "common.cuh"
@@ -85,84 +85,89 @@ __device__ __forceinline__ float key_score(u64 k) { return unorderable(~(uint32_
 constexpr int kScanThreads = 256;
 constexpr int kScanElems = 4096;   // floats per block
 
-// class-specific scan.  One block = kScanElems consecutive floats of image blockIdx.y
-// (coalesced); class of element e is e % C.  FILL=false: per-(image,class) counts, plus ONE BIT per passing score
-// (score > thr) into the zero-filled `mask`.
-// FILL=true: reads only the mask -- 1/32 of the bytes of the scores; the second full pass over the (B, N, C)
-// scores was 0.69 ms of the 1.2 ms tail at D2 / batch 64 / 90 classes (profiles/r2_tail_ncu.txt; 0.25 ms now) -- fetches the
-// few passing scores and writes their keys at offsets[seg] + (block-reserved range); the order inside a segment
-// is arbitrary, the sort restores (score desc, index asc).
-template <bool FILL>
+// Count pass of the class-specific scan.  One block = kScanElems consecutive floats of image blockIdx.y (coalesced);
+// class of element e is e % C.  Writes per-(image,class) counts and ONE BIT per passing score (score > thr) into the
+// zero-filled `mask` (cudaMemsetAsync by the launcher, 1/32 of the scores' bytes; a rare global atomicOr).  The loop
+// is the plain round-1 loop (load, compare, rare atomics) and runs at the DRAM rate (6.5 TB/s); collecting the bits
+// per block in shared memory slowed it from 0.39 to ~0.6 ms, by warp ballot or from tied load batches more still.
+// The fill pass (fill_keys_kernel) then never touches the (B, N, C) scores again except for the passing ones: the
+// second full pass over them was 0.69 ms of the 1.2 ms tail at D2 / batch 64 / 90 classes (profiles/r2_tail_ncu.txt).
 __global__ void __launch_bounds__(kScanThreads)
-scan_scores_kernel(const float *__restrict__ cls, uint32_t NC, int C, float thr,
-                   uint32_t *__restrict__ counts, const uint32_t *__restrict__ offsets,
-                   uint32_t *__restrict__ cursor, u64 *__restrict__ keys,
-                   const int32_t *__restrict__ status, uint32_t *__restrict__ mask, uint32_t mask_words) {
+scan_scores_kernel(const float *__restrict__ cls, uint32_t NC, int C, float thr, uint32_t *__restrict__ counts,
+                   uint32_t *__restrict__ mask, uint32_t mask_words) {
     extern __shared__ uint32_t sh[];
-    uint32_t *hist = sh, *base = sh + C;
-    if (FILL && status[0]) return;
-    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    uint32_t *hist = sh;
+    const int b = blockIdx.y, tid = threadIdx.x;
     const float *p = cls + (size_t)b * NC;
     uint32_t *m = mask + (size_t)b * mask_words;
     const uint32_t e0 = blockIdx.x * (uint32_t)kScanElems;
     const uint32_t e1 = min(e0 + (uint32_t)kScanElems, NC);
     for (int c = tid; c < C; c += kScanThreads) hist[c] = 0;
     __syncthreads();
-    constexpr int kPer = kScanElems / kScanThreads;      // 16 elements per thread: e = e0 + j * 256 + tid
     const uint32_t step = kScanThreads % C;
     uint32_t c = (e0 + tid) % C;
-    uint32_t bits = 0;                                   // bit j: element j of this thread passes
-    if constexpr (!FILL) {
-        // the streaming loop stays exactly the round-1 loop (load, compare, a rare atomic): it runs at the DRAM
-        // rate.  The mask is zero-filled by the launcher (cudaMemsetAsync, 1/32 of the scores' bytes) and the few
-        // passing scores set their bit with a global atomicOr.  Collecting the bits per block in shared memory slowed
-        // this pass from 0.39 to ~0.6 ms (the fill pass gained 0.44: same-box A/B of the whole tail 1.19 -> 0.98 ms;
-        // with this form 1.19 -> 0.77 ms); by warp ballot or from batches of tied loads it was slower still.
-        for (uint32_t e = e0 + tid; e < e1; e += kScanThreads) {
-            const float sc = p[e];
-            if (sc > thr) {
-                atomicAdd(&hist[c], 1u);
-                atomicOr(&m[e >> 5], 1u << (e & 31u));
-            }
-            c += step; if (c >= (uint32_t)C) c -= C;
+    for (uint32_t e = e0 + tid; e < e1; e += kScanThreads) {
+        const float sc = p[e];
+        if (sc > thr) {
+            atomicAdd(&hist[c], 1u);
+            atomicOr(&m[e >> 5], 1u << (e & 31u));
         }
-        __syncthreads();
-        for (int k = tid; k < C; k += kScanThreads)
-            if (hist[k]) atomicAdd(&counts[(size_t)b * C + k], hist[k]);
-        return;
-    } else {
-        // lane j loads the warp's j-th mask word; a shuffle hands it to the other lanes (one round trip)
-        const uint32_t ebl = e0 + (uint32_t)(lane & (kPer - 1)) * kScanThreads + (tid - lane);
-        const uint32_t mine = ebl < e1 ? m[ebl >> 5] : 0u;
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-            const uint32_t word = __shfl_sync(0xffffffffu, mine, j);
-            bits |= ((word >> lane) & 1u) << j;
-        }
-    }
-    for (uint32_t t = bits, cc = c; t; ) {               // histogram of this thread's passing elements
-        const int j = __ffs(t) - 1;
-        t &= t - 1;
-        atomicAdd(&hist[(cc + (uint32_t)j * step) % (uint32_t)C], 1u);
+        c += step; if (c >= (uint32_t)C) c -= C;
     }
     __syncthreads();
-    if constexpr (FILL) {
+    for (int k = tid; k < C; k += kScanThreads)
+        if (hist[k]) atomicAdd(&counts[(size_t)b * C + k], hist[k]);
+}
+
+// Fill pass of the class-specific scan, reading only the mask: a block owns kFillWords mask words (32768 scores),
+// a thread four of them; the work is one coalesced load per 32 scores plus a loop over the few set bits.  (The first
+// mask-reading version kept one block per 4096 scores and rebuilt per-thread bit vectors with 16 shuffles: 155 000
+// blocks at the block-launch rate, issue-bound, 245 us for 80 MB at D2 / batch 64; this one: 19 us.)
+constexpr int kFillWords = 1024;
+__global__ void __launch_bounds__(kScanThreads)
+fill_keys_kernel(const float *__restrict__ cls, uint32_t NC, int C, const uint32_t *__restrict__ offsets,
+                 uint32_t *__restrict__ cursor, u64 *__restrict__ keys, const int32_t *__restrict__ status,
+                 const uint32_t *__restrict__ mask, uint32_t mask_words) {
+    extern __shared__ uint32_t sh[];
+    uint32_t *hist = sh, *base = sh + C;
+    if (status[0]) return;
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const float *p = cls + (size_t)b * NC;
+    const uint32_t *m = mask + (size_t)b * mask_words;
+    const uint32_t w0 = blockIdx.x * (uint32_t)kFillWords;
+    constexpr int kPerT = kFillWords / kScanThreads;
+    uint32_t wd[kPerT];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < kPerT; ++j) {
+        const uint32_t wi = w0 + (uint32_t)j * kScanThreads + tid;
+        wd[j] = wi < mask_words ? m[wi] : 0u;
+        any |= wd[j] != 0u;
+    }
+    for (int c = tid; c < C; c += kScanThreads) hist[c] = 0;
+    if (!__syncthreads_or(any)) return;                  // no candidate in these 32768 scores
+#pragma unroll
+    for (int j = 0; j < kPerT; ++j)
+        for (uint32_t t = wd[j]; t; t &= t - 1) {
+            const uint32_t e = (w0 + (uint32_t)j * kScanThreads + tid) * 32u + (uint32_t)(__ffs(t) - 1);
+            atomicAdd(&hist[e % (uint32_t)C], 1u);
+        }
+    __syncthreads();
     for (int k = tid; k < C; k += kScanThreads) {
-        uint32_t h = hist[k];
+        const uint32_t h = hist[k];
         base[k] = h ? offsets[(size_t)b * C + k] + atomicAdd(&cursor[(size_t)b * C + k], h) : 0u;
         hist[k] = 0;
     }
     __syncthreads();
-    for (uint32_t t = bits; t; ) {
-        const int j = __ffs(t) - 1;
-        t &= t - 1;
-        const uint32_t e = e0 + (uint32_t)j * kScanThreads + tid;
-        const uint32_t cj = (c + (uint32_t)j * step) % (uint32_t)C;
-        const float sc = p[e];
-        const uint32_t r = atomicAdd(&hist[cj], 1u);
-        keys[base[cj] + r] = make_key(sc, e / (uint32_t)C);
-    }
-    }
+#pragma unroll
+    for (int j = 0; j < kPerT; ++j)
+        for (uint32_t t = wd[j]; t; t &= t - 1) {
+            const uint32_t e = (w0 + (uint32_t)j * kScanThreads + tid) * 32u + (uint32_t)(__ffs(t) - 1);
+            const uint32_t cj = e % (uint32_t)C;
+            const float sc = p[e];
+            const uint32_t r = atomicAdd(&hist[cj], 1u);
+            keys[base[cj] + r] = make_key(sc, e / (uint32_t)C);
+        }
 }
 
 // class-agnostic scan (class_specific_filter=False, FilterDetections.py:86-92): score = row max.
@@ -549,14 +554,14 @@ extern "C" int effdet_filter_detections(const float *boxes, const float *classif
             EFFDET_REQUIRE(sm <= 48 * 1024, "too many classes");
             uint32_t *mask = reinterpret_cast<uint32_t *>(ws + L.mask);
             EFFDET_CUDA(cudaMemsetAsync(mask, 0, 4 * L.mask_words * (size_t)B, st));
-            scan_scores_kernel<false><<<grid, kScanThreads, sm, st>>>(
-                classification, NC, C, score_threshold, counts, offsets, cursor, keys, status, mask, (uint32_t)L.mask_words);
+            scan_scores_kernel<<<grid, kScanThreads, sm, st>>>(classification, NC, C, score_threshold, counts, mask,
+                                                               (uint32_t)L.mask_words);
             EFFDET_LAUNCHED();
             offsets_kernel<<<1, 1024, 0, st>>>(counts, (uint32_t)nseg, offsets, cursor,
                                                (u64)cand_capacity, status);
             EFFDET_LAUNCHED();
-            scan_scores_kernel<true><<<grid, kScanThreads, sm, st>>>(
-                classification, NC, C, score_threshold, counts, offsets, cursor, keys, status, mask, (uint32_t)L.mask_words);
+            fill_keys_kernel<<<dim3(cdiv(L.mask_words, kFillWords), B), kScanThreads, sm, st>>>(
+                classification, NC, C, offsets, cursor, keys, status, mask, (uint32_t)L.mask_words);
             EFFDET_LAUNCHED();
         } else {
             dim3 grid(cdiv(N, kScanThreads), B);
