@@ -399,11 +399,112 @@ sort_nms_large_kernel(const float4 *__restrict__ boxes, size_t N, u64 *__restric
 }
 
 // ------------------------------------------------------------------ cross-class top-k + pad
+// One block per image: S-way merge of the per-segment kept lists (each already score-desc).
+// tf.nn.top_k tie rule = lower position in the class-major concatenation = lower class first.
+// Three phases.  (1) all threads stage the score words (high halves of the keys) of the first min(kept, max_det)
+// entries of every list in shared memory; (2) warp 0 merges on those words alone -- a lane owns lists lane,
+// lane + 32, ..., keeps their current heads in registers, the warp takes the minimum by shuffles, the owner advances
+// in shared memory -- and records the picks (list, position); (3) all threads gather boxes / scores / labels of the
+// picks.  The round-1 kernel did all of it in the merge loop of one warp per image: two dependent global loads per
+// pick (the next key of the list that won, then its box), ~0.9 us x 300 picks = 270 us whatever the batch.
+constexpr int kMergeThreads = 128;
+constexpr int kMergeMaxLists = 256;          // lists per image on the staged path (NQ = 1, 3 or 8 lists per lane)
+template <int NQ>
+__global__ void __launch_bounds__(kMergeThreads)
+merge_topk_kernel(const float4 *__restrict__ boxes, const float *__restrict__ cls, int B, size_t N,
+                  int C, int S, const u64 *__restrict__ keys, const uint32_t *__restrict__ offsets,
+                  const uint32_t *__restrict__ kept, int max_det, float4 *__restrict__ out_boxes,
+                  float *__restrict__ out_scores, int32_t *__restrict__ out_labels,
+                  int32_t *__restrict__ out_indices, const int32_t *__restrict__ status) {
+    extern __shared__ uint32_t msh[];
+    uint32_t *words = msh;                              // [S][max_det] score words of the staged entries
+    uint32_t *picks = msh + (size_t)S * max_det;        // [max_det] (list << 16) | position
+    __shared__ int produced_sh;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x;
+    int produced = 0;
+    if (!status[0]) {
+        const uint32_t *off = offsets + (size_t)b * S, *kp = kept + (size_t)b * S;
+        // ---- (1) stage
+        for (int s = warp; s < S; s += kMergeThreads / 32) {
+            const uint32_t n = min(kp[s], (uint32_t)max_det);
+            const u64 *src = keys + off[s];
+            for (uint32_t i = lane; i < n; i += 32) words[(size_t)s * max_det + i] = (uint32_t)(src[i] >> 32);
+        }
+        __syncthreads();
+        // ---- (2) merge (warp 0).  Per pick: the lane's best score word over its lists, one REDUX for the warp's
+        // best word, one more for the lowest class among the lanes that hold it (ties: lower class first), then the
+        // owner advances that list in shared memory.  (With 64-bit keys and five shuffle rounds a pick cost ~660
+        // cycles: 111 us per 300 detections.)
+        if (warp == 0) {
+            uint32_t hw[NQ];                            // current score word of list lane + 32 q, 0xffffffff = exhausted
+            uint32_t pos[NQ], cnt[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int sidx = lane + 32 * q;
+                pos[q] = 0;
+                cnt[q] = sidx < S ? min(kp[sidx], (uint32_t)max_det) : 0u;
+                hw[q] = cnt[q] ? words[(size_t)sidx * max_det] : 0xffffffffu;
+            }
+            for (; produced < max_det; ++produced) {
+                uint32_t mw = hw[0];
+#pragma unroll
+                for (int q = 1; q < NQ; ++q) mw = min(mw, hw[q]);
+                const uint32_t best = __reduce_min_sync(0xffffffffu, mw);
+                if (best == 0xffffffffu) break;
+                uint32_t myc = 0xffffffffu;             // lowest class of this lane whose head has the best word
+#pragma unroll
+                for (int q = NQ - 1; q >= 0; --q)
+                    if (hw[q] == best) myc = (uint32_t)(lane + 32 * q);
+                const uint32_t sidx = NQ == 1 ? (uint32_t)(__ffs(__ballot_sync(0xffffffffu, myc != 0xffffffffu)) - 1)
+                                              : __reduce_min_sync(0xffffffffu, myc);
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+                    if (sidx == (uint32_t)(lane + 32 * q)) {
+                        picks[produced] = (sidx << 16) | pos[q];
+                        ++pos[q];
+                        hw[q] = pos[q] < cnt[q] ? words[(size_t)sidx * max_det + pos[q]] : 0xffffffffu;
+                    }
+            }
+            if (lane == 0) produced_sh = produced;
+        }
+        __syncthreads();
+        produced = produced_sh;
+        // ---- (3) gather
+        for (int j = tid; j < produced; j += kMergeThreads) {
+            const uint32_t pk = picks[j];
+            const int sidx = (int)(pk >> 16);
+            const u64 k = keys[off[sidx] + (pk & 0xffffu)];
+            const uint32_t idx = (uint32_t)k;
+            int label = sidx;
+            if (S != C) {    // class-agnostic: label = first argmax of the row
+                const float *row = cls + ((size_t)b * N + idx) * C;
+                float mx = row[0]; label = 0;
+                for (int c = 1; c < C; ++c) if (row[c] > mx) { mx = row[c]; label = c; }
+            }
+            const size_t o = (size_t)b * max_det + j;
+            out_boxes[o] = boxes[(size_t)b * N + idx];
+            out_scores[o] = key_score(k);
+            out_labels[o] = label;
+            if (out_indices) out_indices[o] = (int32_t)idx;
+        }
+    }
+    for (int j = produced + tid; j < max_det; j += kMergeThreads) {
+        size_t o = (size_t)b * max_det + j;
+        out_boxes[o] = make_float4(-1.f, -1.f, -1.f, -1.f);
+        out_scores[o] = -1.f;
+        out_labels[o] = -1;
+        if (out_indices) out_indices[o] = -1;
+    }
+}
+
+// Fallback of the cross-class merge for shapes the staged kernel above does not take (very large max_detections
+// without NMS, more than 256 lists): the round-1 kernel.
 // One warp per image: S-way merge of the per-segment kept lists (each already score-desc).
 // tf.nn.top_k tie rule = lower position in the class-major concatenation = lower class first.
 constexpr int kMergeWarps = 4;
 __global__ void __launch_bounds__(kMergeWarps * 32)
-merge_topk_kernel(const float4 *__restrict__ boxes, const float *__restrict__ cls, int B, size_t N,
+merge_topk_warp_kernel(const float4 *__restrict__ boxes, const float *__restrict__ cls, int B, size_t N,
                   int C, int S, const u64 *__restrict__ keys, const uint32_t *__restrict__ offsets,
                   const uint32_t *__restrict__ kept, int max_det, float4 *__restrict__ out_boxes,
                   float *__restrict__ out_scores, int32_t *__restrict__ out_labels,
@@ -587,9 +688,29 @@ extern "C" int effdet_filter_detections(const float *boxes, const float *classif
     sort_nms_large_kernel<<<(unsigned)nseg, kLargeThreads, sel_bytes, st>>>(
         b4, N, keys, offsets, counts, kept, S, iou_threshold, (uint32_t)max_det, do_nms, status);
     EFFDET_LAUNCHED();
-    merge_topk_kernel<<<cdiv(B, kMergeWarps), kMergeWarps * 32, (size_t)kMergeWarps * S * 4, st>>>(
-        b4, classification, B, N, C, S, keys, offsets, kept, max_det,
-        reinterpret_cast<float4 *>(out_boxes), out_scores, out_labels, out_indices, status);
+    const size_t merge_smem = ((size_t)S * max_det + max_det) * 4;
+    if (merge_smem <= 200 * 1024 && max_det <= 65535 && S <= kMergeMaxLists) {
+#define MERGE_LAUNCH(NQ)                                                                                          \
+        {                                                                                                         \
+            static bool attr = false;                                                                             \
+            if (!attr) {                                                                                          \
+                EFFDET_CUDA(cudaFuncSetAttribute(merge_topk_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                 200 * 1024));                                                    \
+                attr = true;                                                                                      \
+            }                                                                                                     \
+            merge_topk_kernel<NQ><<<B, kMergeThreads, merge_smem, st>>>(                                          \
+                b4, classification, B, N, C, S, keys, offsets, kept, max_det,                                     \
+                reinterpret_cast<float4 *>(out_boxes), out_scores, out_labels, out_indices, status);              \
+        }
+        if (S <= 32) MERGE_LAUNCH(1)
+        else if (S <= 96) MERGE_LAUNCH(3)
+        else MERGE_LAUNCH(8)
+#undef MERGE_LAUNCH
+    } else {
+        merge_topk_warp_kernel<<<cdiv(B, kMergeWarps), kMergeWarps * 32, (size_t)kMergeWarps * S * 4, st>>>(
+            b4, classification, B, N, C, S, keys, offsets, kept, max_det,
+            reinterpret_cast<float4 *>(out_boxes), out_scores, out_labels, out_indices, status);
+    }
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
