@@ -300,7 +300,7 @@ __device__ uint32_t greedy_nms(const u64 *sorted, uint32_t len, const float4 *__
     __shared__ float4 tb[kNmsTile];
     __shared__ u64 tk[kNmsTile];
     __shared__ u64 tmask[kNmsTile];
-    __shared__ u64 dead;
+    __shared__ u64 dead, sel_mask;
     __shared__ uint32_t nsel_sh;
     const int tid = threadIdx.x, i = tid & (kNmsTile - 1), q = tid / kNmsTile;
     constexpr int Q = T / kNmsTile;
@@ -332,18 +332,29 @@ __device__ uint32_t greedy_nms(const u64 *sorted, uint32_t len, const float4 *__
             if (bits) atomicOr(&tmask[i], bits);
         }
         __syncthreads();
+        // The greedy pass over the tile is sequential only in the `selected` mask: thread 0 runs it as a register
+        // loop (the tmask loads do not depend on it and are issued ahead by the unrolling), then 64 threads scatter
+        // the selected candidates by popcount rank.  (Round 1 also did the stores inside the one-thread loop: with
+        // ~18 tiles per segment that loop was 37 % of the kernel's stall samples, 255 threads waiting at the barrier.)
+        // Candidates ranked past max_det are dropped; they are the last of the tile and the loop ends after it.
         if (tid == 0) {
-            u64 selected = 0, dd = dead;
-            uint32_t n = nsel;
-            for (uint32_t c = 0; c < tn && n < max_det; ++c) {
-                if (((dd >> c) & 1ull) == 0 && (tmask[c] & selected) == 0) {
-                    selected |= 1ull << c;
-                    sel[n] = tb[c];
-                    out[n] = tk[c];
-                    ++n;
-                }
+            u64 selected = 0;
+            const u64 dd = dead;
+#pragma unroll 8
+            for (uint32_t c = 0; c < tn; ++c) {
+                const u64 mk = tmask[c];
+                if (((dd >> c) & 1ull) == 0 && (mk & selected) == 0) selected |= 1ull << c;
             }
-            nsel_sh = n;
+            sel_mask = selected;
+        }
+        __syncthreads();
+        {
+            const u64 selected = sel_mask;
+            if (tid < kNmsTile && ((selected >> tid) & 1ull)) {
+                const uint32_t pos = nsel + (uint32_t)__popcll(selected & ((1ull << tid) - 1ull));
+                if (pos < max_det) { sel[pos] = tb[tid]; out[pos] = tk[tid]; }
+            }
+            if (tid == 0) nsel_sh = min(nsel + (uint32_t)__popcll(selected), max_det);
         }
         __syncthreads();
     }
