@@ -188,6 +188,16 @@ template <int ACT, bool HALF_IN> __device__ __forceinline__ float fast_act(float
     return x;
 }
 
+// Packed fp32 FMA (FFMA2): two IEEE fma.rn results per issue slot -- bit-identical to two FFMAs.  The
+// epilogue is issue-bound (r3a capture: ~390 warp-instructions per 32-column chunk), not FMA-pipe bound.
+__device__ __forceinline__ void ffma2(float &d0, float &d1, float a0, float a1, float b0, float b1, float c0,
+                                      float c1) {
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+
 constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter, alternating column chunks
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 
@@ -245,7 +255,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     const int two_acc = p.acc_bufs == 2;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== TMA producer
             int it = 0;
             if (p.b_resident && t_begin < t_end) {
@@ -292,7 +302,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ===== MMA issuer (single thread)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                                    ((uint32_t)(kTileM >> 4) << 24);
@@ -369,6 +379,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             // per-row addressing is only needed for direct stores / residual / mask reads: the TMA
             // store clips rows outside the tensor by itself
             const bool tma_out = G.tma_store != 0;
+            const bool has_rm = G.res != nullptr || G.mask != nullptr;
             bool row_ok = true;
             size_t base = 0;
             float kp = 1.f;
@@ -387,22 +398,45 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(q * 32) << 16);
             // 32-column chunks alternate between the two warps of a lane quarter; the starting warp
             // flips every tile so that an odd chunk count (N = 96: 3 chunks) balances over two tiles
-            for (int c0 = ((half ^ ti) & 1) * 32; c0 < p.block_n; c0 += 64) {
+            // columns of this tile that exist (warp-uniform); the accumulator goes back to the MMA warp as soon
+            // as this warp's LAST chunk is in registers, so the next tile's MMAs (and, with one accumulator, the
+            // whole wait -> MMA -> commit round trip) overlap that chunk's math, packing and store.  r3a capture
+            // of block3a_expand (one accumulator, two CTAs per SM): 23 % of the epilogue warps' samples were
+            // waits for tmem_full.
+            const int c_end = min(p.block_n, p.Cout - n0);
+            const int c_first = ((half ^ ti) & 1) * 32;
+            bool released = false;
+            for (int c0 = c_first; c0 < c_end; c0 += 64) {
                 const int nbase = n0 + c0;
-                const int ncols = min(32, min(p.Cout, n0 + p.block_n) - nbase);   // warp-uniform
-                if (ncols <= 0) break;
+                const int ncols = min(32, c_end - c0);      // warp-uniform, >= 1
                 uint32_t r[32];
                 __syncwarp();                               // tcgen05.ld is warp-collective
                 tmem_ld32(d_tmem + (uint32_t)c0, r);
+                if (c0 + 64 >= c_end) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    released = true;
+                }
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 sc = *reinterpret_cast<const float4 *>(sScale + c0 + j);
                     const float4 sh = *reinterpret_cast<const float4 *>(sShift + c0 + j);
-                    v[j] = fast_act<ACT, kHalfIn>(fmaf(__uint_as_float(r[j]), sc.x, sh.x));
-                    v[j + 1] = fast_act<ACT, kHalfIn>(fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y));
-                    v[j + 2] = fast_act<ACT, kHalfIn>(fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z));
-                    v[j + 3] = fast_act<ACT, kHalfIn>(fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w));
+                    ffma2(v[j], v[j + 1], __uint_as_float(r[j]), __uint_as_float(r[j + 1]), sc.x, sc.y, sh.x, sh.y);
+                    ffma2(v[j + 2], v[j + 3], __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]), sc.z, sc.w, sh.z, sh.w);
+                    if (ACT == EFFDET_ACT_SWISH && kHalfIn) {
+                        // swish(z) = h + h * tanh(h), h = z / 2 (the 1/2 is folded into scale / shift)
+                        const float t0 = tanh_approx(v[j]), t1 = tanh_approx(v[j + 1]);
+                        const float t2 = tanh_approx(v[j + 2]), t3 = tanh_approx(v[j + 3]);
+                        ffma2(v[j], v[j + 1], v[j], v[j + 1], t0, t1, v[j], v[j + 1]);
+                        ffma2(v[j + 2], v[j + 3], v[j + 2], v[j + 3], t2, t3, v[j + 2], v[j + 3]);
+                    } else {
+                        v[j] = fast_act<ACT, kHalfIn>(v[j]);
+                        v[j + 1] = fast_act<ACT, kHalfIn>(v[j + 1]);
+                        v[j + 2] = fast_act<ACT, kHalfIn>(v[j + 2]);
+                        v[j + 3] = fast_act<ACT, kHalfIn>(v[j + 3]);
+                    }
                 }
                 const int nvalid = row_ok ? ncols : 0;
                 if (OUT_F32) {
@@ -430,7 +464,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                                 make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
                         fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0)
+                        if (elect_one())
                             tma_store_4d(&p.out_map[tc.gi], my_stage + (size_t)sbuf * kStageBytes, nbase, sx, sy, sb);
                         sbuf = (sbuf + 1) & (p.stage_bufs - 1);
                     } else {
@@ -460,10 +494,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                         }
                     }
                 } else {
-                    __nv_bfloat16 *Y = static_cast<__nv_bfloat16 *>(G.y) + base + nbase;
-                    const __nv_bfloat16 *R = G.res ? static_cast<const __nv_bfloat16 *>(G.res) + base + nbase : nullptr;
-                    const __nv_bfloat16 *MK = G.mask ? static_cast<const __nv_bfloat16 *>(G.mask) + base + nbase : nullptr;
-                    if ((R || MK) && nvalid > 0) {
+                    if (has_rm && nvalid > 0) {       // (pointer arithmetic only on this path: expand convolutions skip it)
+                        const __nv_bfloat16 *R = G.res ? static_cast<const __nv_bfloat16 *>(G.res) + base + nbase : nullptr;
+                        const __nv_bfloat16 *MK = G.mask ? static_cast<const __nv_bfloat16 *>(G.mask) + base + nbase : nullptr;
                         const bool vec = nvalid == 32 && (!R || (reinterpret_cast<uintptr_t>(R) & 15) == 0) &&
                                          (!MK || (reinterpret_cast<uintptr_t>(MK) & 15) == 0);
                         if (vec) {
@@ -515,10 +548,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                         }
                         fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0)
+                        if (elect_one())
                             tma_store_4d(&p.out_map[tc.gi], my_stage + (size_t)sbuf * kStageBytes, nbase, sx, sy, sb);
                         sbuf = (sbuf + 1) & (p.stage_bufs - 1);
-                    } else if (nvalid == 32 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0) {
+                    } else if (nvalid == 32 && (reinterpret_cast<uintptr_t>(static_cast<__nv_bfloat16 *>(G.y) + base + nbase) & 15) == 0) {
+                        __nv_bfloat16 *Y = static_cast<__nv_bfloat16 *>(G.y) + base + nbase;
 #pragma unroll
                         for (int j8 = 0; j8 < 4; ++j8) {
                             uint4 ov;
@@ -528,15 +562,18 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                             *reinterpret_cast<uint4 *>(Y + 8 * j8) = ov;
                         }
                     } else {
+                        __nv_bfloat16 *Y = static_cast<__nv_bfloat16 *>(G.y) + base + nbase;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) if (j < nvalid) Y[j] = __float2bfloat16_rn(v[j]);
                     }
                 }
             }
-            // accumulator drained: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            // a warp without a chunk in this tile (narrow N) still owes its arrival
+            if (!released) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
         }
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // outstanding TMA stores land before exit
     }

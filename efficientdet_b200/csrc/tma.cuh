@@ -78,6 +78,14 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void 
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+// One lane of a converged warp.  Unlike `lane == 0` this tells the compiler that exactly one thread runs the
+// guarded code, so the operands of TMA / tcgen05 instructions (uniform registers) are produced on the uniform
+// datapath instead of a per-lane "waterfall" loop (R2UR.OR + BRA.U.ANY, ~22 instructions per TMA store).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // generic-proxy shared-memory writes -> visible to the async proxy (TMA)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -5,25 +5,33 @@ from test_gpu_conv_tc import _panel, _d
 cases={"expand2a":(32,256,16,96,1,2),"expand3a":(32,128,24,144,1,2),"project2b":(32,128,144,24,1,0),"head":(32,64,64,64,3,1),"project7a":(32,16,1152,320,1,0),
 "expand3b":(32,64,40,240,1,2),"expand4b":(32,32,80,480,1,2),"expand5b":(32,32,112,672,1,2),"project5b":(32,32,672,112,1,0),"expand6b":(32,16,192,1152,1,2),"project1a":(32,256,32,16,1,0),
 "d2cls":(16,96,112,810,3,3),"d2trunk":(16,96,112,112,3,1),"d0cls":(32,64,64,180,3,3),"d6exp":(4,44,576,3456,1,2),"d4trunk":(8,128,224,224,3,1)}
-name=sys.argv[1] if len(sys.argv)>1 else "expand2a"
-B,H,cin,cout,k,act=cases[name]
-rng=np.random.default_rng(0)
-x=torch.randn((B,H,H,cin),device="cuda").to(torch.bfloat16)
-w=(rng.standard_normal((k,k,cin,cout))/np.sqrt(k*k*cin)).astype(np.float32)
-panel=_panel(w,0)
-sc=torch.ones(cout,device="cuda"); sh=torch.zeros(cout,device="cuda")
-y=torch.empty((B,H,H,cout),device="cuda",dtype=torch.bfloat16)
-d=_lib.ConvDesc(); d.n_groups=1; d.x[0]=x.data_ptr(); d.y[0]=y.data_ptr(); d.H[0]=d.W[0]=H
-d.B,d.Cin,d.Cout,d.kh,d.kw,d.stride=B,cin,cout,k,k,1
-d.scale=sc.data_ptr(); d.shift=sh.data_ptr(); d.act=act; d.in_dtype=d.out_dtype=_lib.BF16
-d.weight_bf16=panel.data_ptr(); d.allow_tensor_core=1
-st=_lib.stream_ptr()
-for _ in range(3): _lib.call("effdet_conv2d",ctypes.byref(d),st)
-torch.cuda.synchronize()
-e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(10): _lib.call("effdet_conv2d",ctypes.byref(d),st)
-e1.record(); torch.cuda.synchronize()
-ms=e0.elapsed_time(e1)/10
-byt=B*H*H*(cin+cout)*2
-print(name,"ms",ms,"GB/s",byt/ms/1e6,"TF/s",2*B*H*H*cin*cout*k*k/ms/1e9)
+import hashlib
+names=sys.argv[1:] or ["expand2a"]
+if names==["all"]: names=list(cases)
+for name in names:
+    B,H,cin,cout,k,act=cases[name]
+    rng=np.random.default_rng(0)
+    torch.manual_seed(0)
+    x=torch.randn((B,H,H,cin),device="cuda").to(torch.bfloat16)
+    w=(rng.standard_normal((k,k,cin,cout))/np.sqrt(k*k*cin)).astype(np.float32)
+    panel=_panel(w,0)
+    sc=(torch.rand(cout,device="cuda")+0.5); sh=torch.randn(cout,device="cuda")*0.1
+    y=torch.empty((B,H,H,cout),device="cuda",dtype=torch.bfloat16)
+    d=_lib.ConvDesc(); d.n_groups=1; d.x[0]=x.data_ptr(); d.y[0]=y.data_ptr(); d.H[0]=d.W[0]=H
+    d.B,d.Cin,d.Cout,d.kh,d.kw,d.stride=B,cin,cout,k,k,1
+    d.scale=sc.data_ptr(); d.shift=sh.data_ptr(); d.act=act; d.in_dtype=d.out_dtype=_lib.BF16
+    d.weight_bf16=panel.data_ptr(); d.allow_tensor_core=1
+    st=_lib.stream_ptr()
+    for _ in range(3): _lib.call("effdet_conv2d",ctypes.byref(d),st)
+    torch.cuda.synchronize()
+    e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
+    best=1e9
+    for rep in range(3):
+        e0.record()
+        for _ in range(10): _lib.call("effdet_conv2d",ctypes.byref(d),st)
+        e1.record(); torch.cuda.synchronize()
+        best=min(best,e0.elapsed_time(e1)/10)
+    ms=best
+    byt=B*H*H*(cin+cout)*2
+    digest=hashlib.sha1(y.view(torch.int16).cpu().numpy().tobytes()).hexdigest()[:12]
+    print("%-10s ms %.5f GB/s %7.1f TF/s %7.1f sha %s" % (name,ms,byt/ms/1e6,2*B*H*H*cin*cout*k*k/ms/1e9,digest), flush=True)
