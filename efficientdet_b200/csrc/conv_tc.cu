@@ -215,9 +215,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
     uint8_t *sB = smem + (size_t)p.stages * p.a_stage_bytes;
     // ring B tiles, or (b_resident) one slot per K block filled once
     const int num_k_all = p.ksize * p.ksize * p.kblocks_per_tap;
-    float *sScale = reinterpret_cast<float *>(sB + (size_t)(p.b_resident ? num_k_all : p.stages) * b_tile_bytes);   // [256]
-    float *sShift = sScale + 256;                                                          // [256]
-    uint64_t *full = reinterpret_cast<uint64_t *>(sShift + 256);
+    float *sScale = reinterpret_cast<float *>(sB + (size_t)(p.b_resident ? num_k_all : p.stages) * b_tile_bytes);   // [2][256]
+    float *sShift = sScale + 512;                                                          // [2][256] each: see the epilogue
+    uint64_t *full = reinterpret_cast<uint64_t *>(sShift + 512);
     uint64_t *empty = full + p.stages;
     uint64_t *tmem_full = empty + p.stages;      // [2]
     uint64_t *tmem_empty = tmem_full + 2;        // [2]
@@ -357,8 +357,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
         const int row = q * 32 + lane;                      // tile row == TMEM lane
         const int et = threadIdx.x - 64;                    // 0..255
         constexpr bool kHalfIn = (ACT == EFFDET_ACT_SWISH) && !OUT_F32;
-        int ti = 0, cur_n0 = -1, sbuf = 0;
+        int ti = 0, cur_n0 = -1, sbuf = 0, ss_par = 256;
         uint8_t *my_stage = sStage + (size_t)ew * p.stage_bufs * kStageBytes;
+        const uint32_t stage_s = smem_u32(my_stage);
+        // bf16 staging row of this lane: 64 bytes, 16-byte chunk index ^= (row >> 1) & 3 (SWIZZLE_64B); the
+        // XOR with j8 << 4 touches only bits 4-5, so it commutes with adding the row offset
+        const uint32_t st_row = (uint32_t)lane * 64u + ((((uint32_t)lane >> 1) & 3u) << 4);
         TileIter tit;
         tit.init(p, t_begin);
         for (int t = t_begin; t < t_end; ++t, ++ti, tit.next(p)) {
@@ -366,15 +370,19 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             const TcGroup &G = p.g[tc.gi];
             const int x0 = tc.x0, y0 = tc.y0, b0 = tc.b0, n0 = tc.n0;
             const int acc = two_acc ? (ti & 1) : 0, aph = (two_acc ? (ti >> 1) : ti) & 1;
-            if (n0 != cur_n0) {
-                // per-column scale / shift of this N tile -> shared memory (uniform across the CTA)
-                asm volatile("bar.sync 1, 256;" ::: "memory");       // previous tile's readers are done
+            // Per-column scale / shift of this N tile -> shared memory (uniform across the CTA).  With several N
+            // tiles (n varies fastest) EVERY tile restages them: the loads are issued here, ahead of the wait for
+            // the accumulator, and land in the buffer the previous tile did not use, so one barrier per tile
+            // (after the accumulator wait) orders both the new values and the reuse of the other buffer.  (r3b
+            // capture of block4b_expand: the former barrier -> global load -> barrier chain of each tile held a
+            // quarter of the epilogue warps' samples.)
+            const bool restage = n0 != cur_n0;
+            float st_scale = 1.f, st_shift = 0.f;
+            if (restage) {
                 const int n = n0 + et;
                 const float pre = kHalfIn ? 0.5f : 1.f;
-                sScale[et] = pre * ((p.scale && n < p.Cout) ? p.scale[n] : 1.f);
-                sShift[et] = pre * ((p.shift && n < p.Cout) ? p.shift[n] : 0.f);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                cur_n0 = n0;
+                st_scale = pre * ((p.scale && n < p.Cout) ? p.scale[n] : 1.f);
+                st_shift = pre * ((p.shift && n < p.Cout) ? p.shift[n] : 0.f);
             }
             // per-row addressing is only needed for direct stores / residual / mask reads: the TMA
             // store clips rows outside the tensor by itself
@@ -393,8 +401,16 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
             // origin of this warp's 32-row box (rows 32q .. 32q+31 of the tile) for the TMA store
             const int r0 = q * 32;
             const int sx = x0 + (r0 & (G.Wt - 1)), sy = y0 + ((r0 >> G.lw) & (G.Ht - 1)), sb = b0 + (r0 >> (G.lw + G.lh));
+            if (restage) {
+                ss_par ^= 256;
+                sScale[ss_par + et] = st_scale;
+                sShift[ss_par + et] = st_shift;
+                cur_n0 = n0;
+            }
             mbar_wait(&tmem_full[acc], aph);
             tc_fence_after();
+            if (restage) asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float *cScale = sScale + ss_par, *cShift = sShift + ss_par;
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(q * 32) << 16);
             // 32-column chunks alternate between the two warps of a lane quarter; the starting warp
             // flips every tile so that an odd chunk count (N = 96: 3 chunks) balances over two tiles
@@ -421,8 +437,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 sc = *reinterpret_cast<const float4 *>(sScale + c0 + j);
-                    const float4 sh = *reinterpret_cast<const float4 *>(sShift + c0 + j);
+                    const float4 sc = *reinterpret_cast<const float4 *>(cScale + c0 + j);
+                    const float4 sh = *reinterpret_cast<const float4 *>(cShift + c0 + j);
                     ffma2(v[j], v[j + 1], __uint_as_float(r[j]), __uint_as_float(r[j + 1]), sc.x, sc.y, sh.x, sh.y);
                     ffma2(v[j + 2], v[j + 3], __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]), sc.z, sc.w, sh.z, sh.w);
                     if (ACT == EFFDET_ACT_SWISH && kHalfIn) {
@@ -536,20 +552,21 @@ conv_tc_kernel(const __grid_constant__ TcParams p) {
                         if (p.stage_bufs == 2) tma_store_wait_read<1>();
                         else tma_store_wait_read<0>();
                         __syncwarp();
-                        uint8_t *dst = my_stage + (size_t)sbuf * kStageBytes + lane * 64;
+                        // 32-bit shared-window addresses computed once per warp (stage_s, st_row): no generic ->
+                        // shared conversion and no address IMAD chain per chunk
+                        const uint32_t sbase = stage_s + (uint32_t)sbuf * (uint32_t)kStageBytes;
 #pragma unroll
                         for (int j8 = 0; j8 < 4; ++j8) {
-                            uint4 ov;
-                            ov.x = pack_bf16x2(v[8 * j8], v[8 * j8 + 1]);
-                            ov.y = pack_bf16x2(v[8 * j8 + 2], v[8 * j8 + 3]);
-                            ov.z = pack_bf16x2(v[8 * j8 + 4], v[8 * j8 + 5]);
-                            ov.w = pack_bf16x2(v[8 * j8 + 6], v[8 * j8 + 7]);
-                            *reinterpret_cast<uint4 *>(dst + ((j8 ^ ((lane >> 1) & 3)) << 4)) = ov;
+                            const uint32_t o0 = pack_bf16x2(v[8 * j8], v[8 * j8 + 1]);
+                            const uint32_t o1 = pack_bf16x2(v[8 * j8 + 2], v[8 * j8 + 3]);
+                            const uint32_t o2 = pack_bf16x2(v[8 * j8 + 4], v[8 * j8 + 5]);
+                            const uint32_t o3 = pack_bf16x2(v[8 * j8 + 6], v[8 * j8 + 7]);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                                         ::"r"(sbase + (st_row ^ (uint32_t)(j8 << 4))), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
                         }
                         fence_proxy_async();
                         __syncwarp();
-                        if (elect_one())
-                            tma_store_4d(&p.out_map[tc.gi], my_stage + (size_t)sbuf * kStageBytes, nbase, sx, sy, sb);
+                        if (elect_one()) tma_store_4d_s(&p.out_map[tc.gi], sbase, nbase, sx, sy, sb);
                         sbuf = (sbuf + 1) & (p.stage_bufs - 1);
                     } else if (nvalid == 32 && (reinterpret_cast<uintptr_t>(static_cast<__nv_bfloat16 *>(G.y) + base + nbase) & 15) == 0) {
                         __nv_bfloat16 *Y = static_cast<__nv_bfloat16 *>(G.y) + base + nbase;
@@ -1300,13 +1317,13 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     // epilogue overlaps the other's main loop
     // small tiles: 2 resident CTAs per SM (<= ~100 KiB each); wide tiles: 1
     int stage_out_bytes = kEpiWarps * 2 * 32 * 32 * (p.out_f32 ? 4 : 2);
-    if (p.halo && 9 * b_tile_bytes + 2 * p.a_stage_bytes + stage_out_bytes + 6 * 1024 > 226 * 1024) {
+    if (p.halo && 9 * b_tile_bytes + 2 * p.a_stage_bytes + stage_out_bytes + 7 * 1024 > 226 * 1024) {
         p.stage_bufs = 1;                             // one staging buffer per epilogue warp
         stage_out_bytes /= 2;
     }
     const int two_ctas = p.tmem_cols <= 256 && !p.halo;
     const int ring_bytes = p.halo ? p.a_stage_bytes : kATileBytes + (p.b_resident ? 0 : b_tile_bytes);
-    const int fixed_bytes = stage_out_bytes + (p.b_resident ? num_k * b_tile_bytes : 0) + 6 * 1024;
+    const int fixed_bytes = stage_out_bytes + (p.b_resident ? num_k * b_tile_bytes : 0) + 7 * 1024;
     int stages = ((two_ctas ? 113 : 226) * 1024 - fixed_bytes) / ring_bytes;
     if (stages > (p.b_resident ? 6 : 4)) stages = p.b_resident ? 6 : 4;
     if (p.halo && stages > 2) stages = 2;
@@ -1314,7 +1331,7 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     // number of K blocks of one tile (a 1x1 convolution with Cin <= 64 has a single K block)
     if (stages < 2) stages = 2;
     p.stages = stages;
-    const size_t smem = (size_t)stages * ring_bytes + (p.b_resident ? (size_t)num_k * b_tile_bytes : 0) + 2048 +
+    const size_t smem = (size_t)stages * ring_bytes + (p.b_resident ? (size_t)num_k * b_tile_bytes : 0) + 4096 +
                         (2 * stages + 5) * 8 + 16 + 1024 + 1024 + stage_out_bytes;
     p.any_tma_store = 0;
     int tiles = 0;

@@ -75,6 +75,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void 
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 // at most n of this thread's bulk stores may still be READING their shared-memory source
+// same, source given as a 32-bit shared-window address
+__device__ __forceinline__ void tma_store_4d_s(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
