@@ -759,7 +759,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < num_k; ++kb) {
                 const int s = kb % p.stages, ph = (kb / p.stages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
@@ -789,7 +789,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // a_major = b_major = MN (bits 15, 16)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -948,7 +948,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < num_k; ++kb) {
                 const int s = kb % p.stages, ph = (kb / p.stages) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
@@ -969,7 +969,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ WgHaloParams p) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // M = 128 (two taps x 64 channels), N = 64, both operands MN-major
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
