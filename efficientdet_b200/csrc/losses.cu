@@ -89,19 +89,41 @@ __device__ __forceinline__ LevelPos level_pos(const LevelGrads &L, unsigned b, u
     return q;
 }
 
+// log(1 - x) for 0 <= x <= 1/4: x' = -x, log1p(x') = x' + x'^2 P(x'), P = degree-7 minimax fit of
+// (log1p(x') - x') / x'^2 on [-1/4, 0] (max relative error 7e-8 in fp32 arithmetic, i.e. rounding level --
+// checked against float64 on 2e5 log-spaced points).  Nine FMA-pipe instructions instead of log1pf's ~30.
+__device__ __forceinline__ float log1m_small(float x) {
+    const float f = -x;
+    float t = 0.3018442392349243f;
+    t = fmaf(t, f, -0.0319586880505085f);
+    t = fmaf(t, f, 0.16445574164390564f);
+    t = fmaf(t, f, -0.1639823168516159f);
+    t = fmaf(t, f, 0.2001783549785614f);
+    t = fmaf(t, f, -0.2499942183494568f);
+    t = fmaf(t, f, 0.33333340287208557f);
+    t = fmaf(t, f, -0.5f);
+    return fmaf(f * f, t, f);
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+
 // focal loss of one element + its gradient w.r.t. the logit.  t in {0, 1}:
-//   keras binary_crossentropy (clip -> logit -> sigmoid CE) == -log(pc) | -log(1 - pc), evaluated
-//   with logf / log1pf (the three-transcendental form max(z,0) - z t + log1p(exp(-|z|)) of
-//   utils/tpu.py:135 is the same number); (1-p_t)^gamma by sqrt for the reference's gamma = 1.5.
+//   keras binary_crossentropy (clip -> logit -> sigmoid CE) == -log(pc) | -log(1 - pc) (the
+//   three-transcendental form max(z,0) - z t + log1p(exp(-|z|)) of utils/tpu.py:135 is the same number);
+//   (1-p_t)^gamma by sqrt for the reference's gamma = 1.5.  `lg` = log(pc) (foreground) or log(1 - pc)
+//   (background), supplied by the caller: almost every element is a background anchor with a small score,
+//   for which log(1 - pc) is the short polynomial above; the kernel takes the logf path only for warps that
+//   hold a foreground element or a score above 1/4 (r2 capture: the kernel was issue-bound at 2.6 TB/s on
+//   logf + log1pf + sqrtf evaluated for every element).
 template <int GMODE>   // 0: generic gamma, 1: gamma == 1.5, 2: gamma == 2
-__device__ __forceinline__ float focal_elem(float p, bool fg, float mask, float alpha, float gamma,
+__device__ __forceinline__ float focal_elem(float p, bool fg, float lg, float mask, float alpha, float gamma,
                                             float gscale, float &loss_acc) {
     const float af = fg ? alpha : 1.f - alpha;
     const float fw = fg ? 1.f - p : p;
-    const float pc = fminf(fmaxf(p, 1e-7f), 1.f - 1e-7f);
-    const float bce = fg ? -logf(pc) : -log1pf(-pc);
+    const float bce = -lg;
     float fwg, dfwg_abs;                       // fw^gamma, gamma * fw^(gamma-1)
-    if (GMODE == 1) { const float sq = sqrtf(fw); fwg = fw * sq; dfwg_abs = 1.5f * sq; }
+    if (GMODE == 1) { const float sq = sqrt_approx(fw); fwg = fw * sq; dfwg_abs = 1.5f * sq; }
     else if (GMODE == 2) { fwg = fw * fw; dfwg_abs = 2.f * fw; }
     else { fwg = powf(fw, gamma); dfwg_abs = fw > 0.f ? gamma * powf(fw, gamma - 1.f) : 0.f; }
     loss_acc += af * fwg * bce * mask;
@@ -144,13 +166,28 @@ focal_kernel(const float *__restrict__ p_, const float *__restrict__ labels_t,
             st = (float)state[r];
         }
         const float mask = st != -1.f ? 1.f : 0.f;
-        float g[VEC];
+        float g[VEC], pc[VEC], lg[VEC];
+        bool slow = false;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) g[k] = focal_elem<GMODE>(p[k], t[k] == 1.f, mask, alpha, gamma, gscale, acc);
-        float *dst = dlogit + (size_t)r * C + c0;
-        if (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(g[0], g[1], g[2], g[3]);
-        else if (VEC == 2) *reinterpret_cast<float2 *>(dst) = make_float2(g[0], g[1]);
-        else dst[0] = g[0];
+        for (int k = 0; k < VEC; ++k) {
+            pc[k] = fminf(fmaxf(p[k], 1e-7f), 1.f - 1e-7f);
+            lg[k] = log1m_small(pc[k]);                         // right for background elements with pc <= 1/4
+            slow |= (t[k] == 1.f) | (pc[k] > 0.25f);
+        }
+        if (__any_sync(__activemask(), slow)) {                 // warp-level branch: rare
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+                if ((t[k] == 1.f) | (pc[k] > 0.25f)) lg[k] = t[k] == 1.f ? logf(pc[k]) : logf(1.f - pc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+            g[k] = focal_elem<GMODE>(p[k], t[k] == 1.f, lg[k], mask, alpha, gamma, gscale, acc);
+        if (dlogit) {                                           // (optional fp32 copy: see effdet_detection_losses)
+            float *dst = dlogit + (size_t)r * C + c0;
+            if (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(g[0], g[1], g[2], g[3]);
+            else if (VEC == 2) *reinterpret_cast<float2 *>(dst) = make_float2(g[0], g[1]);
+            else dst[0] = g[0];
+        }
         if (L.n_levels) {
             const unsigned b = r / L.N;
             const LevelPos q = level_pos(L, b, r - b * L.N);
@@ -192,7 +229,7 @@ smooth_l1_kernel(const float *__restrict__ pred, const float *__restrict__ reg_t
             acc += fg ? l : 0.f;
             g[k] = fg ? gd * inv_norm * grad_scale : 0.f;
         }
-        *reinterpret_cast<float4 *>(dreg + (size_t)r * 4) = make_float4(g[0], g[1], g[2], g[3]);
+        if (dreg) *reinterpret_cast<float4 *>(dreg + (size_t)r * 4) = make_float4(g[0], g[1], g[2], g[3]);
         if (L.n_levels) {
             const unsigned b = r / L.N;
             const LevelPos q = level_pos(L, b, r - b * L.N);
@@ -240,12 +277,14 @@ extern "C" int effdet_detection_losses(const float *classification, const float 
                                        void *const *dcls_levels_host, void *const *dreg_levels_host,
                                        const int *level_cells_host, int n_levels, int cpad_cls,
                                        int cpad_reg, void *stream) {
-    EFFDET_REQUIRE(classification && regression && regression_t && dcls_logits && dreg && out8 &&
-                       workspace, "null pointer");
+    EFFDET_REQUIRE(classification && regression && regression_t && out8 && workspace, "null pointer");
+    // the concatenated fp32 gradients are optional when the per-level bf16 copies are requested (the tensor-core
+    // gradient kernels read only those; D0 training: 150 MB of dead stores per step otherwise)
+    EFFDET_REQUIRE((dcls_logits && dreg) || n_levels > 0, "dcls_logits / dreg may be NULL only with level outputs");
     EFFDET_REQUIRE(labels_t || (state && cls), "need dense labels or compact (state, cls) targets");
     EFFDET_REQUIRE(B > 0 && N > 0 && C > 0, "bad sizes");
     EFFDET_REQUIRE((reinterpret_cast<uintptr_t>(regression) & 15) == 0 &&
-                       (reinterpret_cast<uintptr_t>(dreg) & 15) == 0, "16B alignment");
+                       (reinterpret_cast<uintptr_t>(dreg) & 15) == 0, "16B alignment");   // (NULL passes)
     if (workspace_bytes < effdet_detection_losses_workspace_size())
         return fail(EFFDET_E_CAPACITY, "effdet_detection_losses: workspace too small%s", "");
     cudaStream_t st = as_stream(stream);

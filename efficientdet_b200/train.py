@@ -282,14 +282,17 @@ class TrainPlan(engine.Plan):
                              for i, f in enumerate(feats)]
             outs += self.lvl_dcls + self.lvl_dreg
             cells = (ctypes.c_int * 5)(*[f.shape[1] * f.shape[2] for f in feats])
+        # the concatenated fp32 gradients have one reader left in tensor-core mode: the bias gradient of the two
+        # final head convolutions, and only when the weight-gradient kernel does not produce it (Cin > 64)
+        self.fp32_head_grads = not (self.use_tc_grads and self.wgrad_fuses_bias(self.net.w_bifpn, 3))
 
         def make():
             args = [self.classification.ptr, self.regression.ptr,
                     self.reg_t.ptr, self.lab_t.ptr if self.lab_t is not None else None,
                     self.state_t.ptr if self.state_t is not None else None,
                     self.cls_t.ptr if self.cls_t is not None else None, B, N, C, self.alpha,
-                    self.gamma, self.delta, 1.0, self.dcls.ptr, self.dreg.ptr,
-                    self.loss_out.ptr, ws.ptr, ws_bytes]
+                    self.gamma, self.delta, 1.0, self.dcls.ptr if self.fp32_head_grads else None,
+                    self.dreg.ptr if self.fp32_head_grads else None, self.loss_out.ptr, ws.ptr, ws_bytes]
             if self.use_tc_grads:
                 for v in self.lvl_dcls + self.lvl_dreg:      # zero the padding channels once
                     self.tensor(v).zero_()

@@ -267,7 +267,9 @@ int effdet_bifpn_node(const void *in0, int mode0, const void *in1, const void *i
  * [1] smooth-L1 loss, [2]/[3] #positive anchors, [4]/[5] 1/normaliser.
  * Optional (n_levels > 0): a second, bf16 copy of both gradients in per-pyramid-level dense
  * buffers (B, cells_l, cpad) with channel = anchor*per + k (what the TMA-fed tensor-core
- * gradient kernels read); level_cells_host[l] = H_l*W_l; padding channels are not written. */
+ * gradient kernels read); level_cells_host[l] = H_l*W_l; padding channels are not written.
+ * With n_levels > 0, dcls_logits and / or dreg may be NULL: the concatenated fp32 copies are then not
+ * written (a caller whose backward reads only the level buffers saves their 4*N*(C+4) bytes per image). */
 size_t effdet_detection_losses_workspace_size(void);
 int effdet_detection_losses(const float *classification, const float *regression,
                             const float *regression_t, const float *labels_t, const int8_t *state,

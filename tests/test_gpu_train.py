@@ -72,6 +72,55 @@ def test_losses_fwd_bwd():
         assert rel_err(dreg.cpu().numpy(), rt.grad.numpy()) < 1e-5
 
 
+def test_losses_level_outputs_without_fp32_copies():
+    """effdet_detection_losses with per-level bf16 gradient buffers: dcls_logits / dreg may be NULL (the
+    tensor-core backward reads only the level buffers); losses and level buffers are bit-identical to the call
+    that also writes the fp32 copies, and the level buffers hold bf16(fp32 gradient) at (image, cell, anchor*per+k)."""
+    from efficientdet_b200 import _lib
+    import ctypes
+    lib = _lib.load()
+    B, C, cells = 2, 8, [16, 4]
+    N = 9 * sum(cells)
+    cpad_cls, cpad_reg = 9 * C, 40
+    rng = np.random.default_rng(3)
+    p = rng.uniform(0.001, 0.999, (B, N, C)).astype(np.float32)
+    reg = rng.normal(0, 1.2, (B, N, 4)).astype(np.float32)
+    state = rng.choice([-1, 0, 1], (B, N), p=[0.1, 0.7, 0.2]).astype(np.float32)
+    clsid = rng.integers(0, C, (B, N))
+    reg_t = np.concatenate([rng.normal(0, 1, (B, N, 4)), state[..., None]], -1).astype(np.float32)
+    d = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dt)
+    pd, rd, rtd = d(p), d(reg), d(reg_t)
+    st, cl = d(state, torch.int8), d(np.where(state == 1, clsid, -1), torch.int32)
+    wsb = lib.effdet_detection_losses_workspace_size()
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    res = []
+    for with_fp32 in (True, False):
+        dcls = torch.zeros((B, N, C), device="cuda"); dreg = torch.zeros((B, N, 4), device="cuda")
+        out8 = torch.zeros(8, device="cuda")
+        lc = [torch.zeros((B, c, cpad_cls), device="cuda", dtype=torch.bfloat16) for c in cells]
+        lr = [torch.zeros((B, c, cpad_reg), device="cuda", dtype=torch.bfloat16) for c in cells]
+        pc = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in lc]); pr = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in lr])
+        cc = (ctypes.c_int * 5)(*cells)
+        _lib.call("effdet_detection_losses", pd.data_ptr(), rd.data_ptr(), rtd.data_ptr(), None, st.data_ptr(),
+                  cl.data_ptr(), B, N, C, 0.25, 1.5, 1.0, 1.0, dcls.data_ptr() if with_fp32 else None,
+                  dreg.data_ptr() if with_fp32 else None, out8.data_ptr(), ws.data_ptr(), wsb, pc, pr, cc,
+                  len(cells), cpad_cls, cpad_reg, _lib.stream_ptr())
+        torch.cuda.synchronize()
+        res.append((out8.cpu(), [t.cpu() for t in lc], [t.cpu() for t in lr], dcls.cpu(), dreg.cpu()))
+    a, b = res
+    assert torch.equal(a[0], b[0])
+    for x, y in zip(a[1] + a[2], b[1] + b[2]):
+        assert torch.equal(x.view(torch.int16), y.view(torch.int16))
+    assert float(b[3].abs().max()) == 0.0 and float(b[4].abs().max()) == 0.0      # untouched
+    off = 0
+    for l, c in enumerate(cells):
+        want = a[3][:, off:off + 9 * c].reshape(B, c, 9 * C).to(torch.bfloat16)
+        assert torch.equal(a[1][l][:, :, :9 * C].view(torch.int16), want.view(torch.int16))
+        wantr = a[4][:, off:off + 9 * c].reshape(B, c, 36).to(torch.bfloat16)
+        assert torch.equal(a[2][l][:, :, :36].view(torch.int16), wantr.view(torch.int16))
+        off += 9 * c
+
+
 def _d(a, dt=torch.float32):
     return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dt)
 
