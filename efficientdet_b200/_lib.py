@@ -121,6 +121,8 @@ _SIGNATURES = {
     "effdet_se_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                            c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "effdet_se_bn_backward": [c_void_p] * 4 + [c_int] + [c_void_p] * 8 + [c_void_p] * 5 + [c_void_p] * 2 +
+                             [c_void_p] * 2 + [c_void_p] * 3 + [c_int] + [c_void_p] * 2 + [c_int] * 5 + [c_void_p],
     "effdet_dw_backward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                            c_int, c_int, c_int, c_int, c_int, c_void_p],
     "effdet_stem_wgrad": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -212,6 +214,8 @@ def load():
     lib.effdet_conv_weight_panel_split_elems.argtypes = [c_int, c_int, c_int]
     lib.effdet_se_backward_blocks.restype = c_int
     lib.effdet_se_backward_blocks.argtypes = [c_int, c_int, c_int]
+    lib.effdet_se_bn_backward_blocks.restype = c_int
+    lib.effdet_se_bn_backward_blocks.argtypes = [c_int, c_int, c_int, c_int]
     lib.effdet_dw_backward_blocks.restype = c_int
     lib.effdet_dw_backward_blocks.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, c_int]
     lib.effdet_stem_wgrad_blocks.restype = c_int

@@ -1166,3 +1166,375 @@ extern "C" int effdet_stem_wgrad(const float *images, const void *dz, float *dke
     EFFDET_LAUNCHED();
     return EFFDET_OK;
 }
+
+// ------------------------------------------------------------------ fused squeeze-excite + BN/swish backward
+// MBConv backward between the project data gradient and the depthwise backward (efficientnet.py:242-286):
+//   y = swish(u), u = a z + b  (BatchNorm in training mode),  yg = y * gate[b][c],  gate = SE(mean_hw y)
+//   given dyg:  dy = dyg * gate + dmean / HW,   dz = BN^T( dy * swish'(u) )
+// The separate entry points (effdet_se_backward, then effdet_bn_act_backward) read dyg + y, read dyg and
+// write dy, read dy + z, read dy + z and write dz: NINE passes over (B, HW, Cmid) tensors.  Every sum the
+// two reductions need is linear in per-(image, channel) constants:
+//   dgate            = sum dyg y
+//   sum dy s'        = gate * sum dyg s'        + (dmean/HW) * sum s'
+//   sum dy s' (z-mu) = gate * sum dyg s' (z-mu) + (dmean/HW) * sum s' (z-mu)
+// so ONE reduction pass over (dyg, z) produces five per-(image, block, channel) partial sums (y and s' are
+// recomputed from z), the tiny SE fully-connected backward and a per-(image, channel) combine follow, and ONE
+// apply pass reads (dyg, z) and writes dz: five passes; dy is never materialised.
+namespace effdet {
+
+template <typename T> __device__ __forceinline__ void swish_and_grad(float u, float &y, float &g);
+template <> __device__ __forceinline__ void swish_and_grad<float>(float u, float &y, float &g) {
+    const float s = 1.f / (1.f + __expf(-u));
+    y = u * s;
+    g = s * (1.f + u * (1.f - s));
+}
+template <> __device__ __forceinline__ void swish_and_grad<__nv_bfloat16>(float u, float &y, float &g) {
+    const float s = fmaf(0.5f, tanh_fast(0.5f * u), 0.5f);
+    y = u * s;
+    g = s * fmaf(u, 1.f - s, 1.f);
+}
+
+// dgp (B, nblk, C): sum dyg*y ; bnp (B, nblk, 4, C): sum dyg s', sum dyg s' z, sum s', sum s' z
+// Blocks of <= 256 threads (85 registers: 20 accumulators + 8 constants + 16 words of loads in flight do not fit
+// the 64 of a 1024-thread block): wide layers are cut into channel chunks along grid.z (nvb vectors per block).
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
+se_bn_bwd_reduce_kernel(const T *__restrict__ dyg, const T *__restrict__ z, const float *__restrict__ ua,
+                        const float *__restrict__ ub, int HW, int C, int nvb,
+                        int rows_per_block, float *__restrict__ dgp, float *__restrict__ bnp, uint32_t zero) {
+    constexpr int CV = 4;
+    extern __shared__ float sred[];
+    const int PY = blockDim.x / nvb;
+    const int cv = threadIdx.x % nvb, py = threadIdx.x / nvb, c = (blockIdx.z * nvb + cv) * CV;
+    const int cl = cv * CV, CL = nvb * CV;            // channel index / count inside the block's chunk
+    const bool live = py < PY && c < C;
+    const int b = blockIdx.y;
+    const size_t r0 = (size_t)blockIdx.x * rows_per_block;
+    const size_t r1 = r0 + rows_per_block < (size_t)HW ? r0 + rows_per_block : (size_t)HW;
+    const T *pg = dyg + (size_t)b * HW * C, *pz = z + (size_t)b * HW * C;
+    // (the z-weighted sums are taken about zero here; the combine kernel shifts them by the batch mean: 64
+    // registers leave no room for a fourth per-channel constant next to the 20 accumulators)
+    float s[5][CV], a[CV], bb[CV];
+#pragma unroll
+    for (int k = 0; k < CV; ++k) { a[k] = 0.f; bb[k] = 0.f; }
+    if (live) { ldv<CV>(ua + c, a); ldv<CV>(ub + c, bb); }
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+#pragma unroll
+        for (int k = 0; k < CV; ++k) s[j][k] = 0.f;
+    auto accumulate = [&](const float *zz, const float *g) {
+#pragma unroll
+        for (int k = 0; k < CV; ++k) {
+            float y, ag;
+            swish_and_grad<T>(fmaf(zz[k], a[k], bb[k]), y, ag);
+            const float ga = g[k] * ag;
+            s[0][k] = fmaf(g[k], y, s[0][k]);
+            s[1][k] += ga;
+            s[2][k] = fmaf(ga, zz[k], s[2][k]);
+            s[3][k] += ag;
+            s[4][k] = fmaf(ag, zz[k], s[4][k]);
+        }
+    };
+    size_t r = r0 + py;
+    const size_t step = (size_t)kBnU * PY;
+    const bool pf = threadIdx.x == 0 && blockIdx.z == 0;      // whole rows: one chunk asks for them
+    if (live) {
+        if (pf) {
+            prefetch_rows(pz, r0, r0 + kBnPD * step, r1, C);
+            prefetch_rows(pg, r0, r0 + kBnPD * step, r1, C);
+        }
+        size_t rq = r0 + kBnPD * step;             // first row not yet requested
+        for (; r + (size_t)(kBnU - 1) * PY < r1; r += step, rq += step) {
+            if (pf) {
+                prefetch_rows(pz, rq, rq + step, r1, C);
+                prefetch_rows(pg, rq, rq + step, r1, C);
+            }
+            typename Raw4<T>::type zr[kBnU], gr[kBnU];
+#pragma unroll
+            for (int u = 0; u < kBnU; ++u) {
+                zr[u] = Raw4<T>::load(pz + (r + (size_t)u * PY) * C + c);
+                gr[u] = Raw4<T>::load(pg + (r + (size_t)u * PY) * C + c);
+            }
+            Raw4<T>::all_loaded(zr, gr, zero);
+#pragma unroll
+            for (int u = 0; u < kBnU; ++u) {
+                float zz[CV], g[CV];
+                Raw4<T>::unpack(zr[u], zz);
+                Raw4<T>::unpack(gr[u], g);
+                accumulate(zz, g);
+            }
+        }
+        for (; r < r1; r += PY) {
+            float zz[CV], g[CV];
+            VecB<T, CV>::load(pz + r * C + c, zz);
+            VecB<T, CV>::load(pg + r * C + c, g);
+            accumulate(zz, g);
+        }
+    }
+    const size_t row = (size_t)b * gridDim.x + blockIdx.x;
+    if (PY == 1) {                                  // one thread per channel vector: its sums are the block's
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < CV; ++k) {
+                dgp[row * C + c + k] = s[0][k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bnp[(row * 4 + j) * C + c + k] = s[j + 1][k];
+            }
+        }
+        return;
+    }
+    if (py < PY) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+#pragma unroll
+            for (int k = 0; k < CV; ++k) sred[((size_t)py * 5 + j) * CL + cl + k] = s[j][k];
+    }
+    __syncthreads();
+    const int c_base = blockIdx.z * CL;
+    for (int i = threadIdx.x; i < 5 * CL; i += blockDim.x) {
+        float t = 0.f;
+        for (int q = 0; q < PY; ++q) t += sred[(size_t)q * 5 * CL + i];      // fixed order
+        const int j = i / CL, cc = c_base + (i - j * CL);
+        if (cc >= C) continue;
+        if (j == 0) dgp[row * C + cc] = t;
+        else bnp[(row * 4 + (j - 1)) * C + cc] = t;
+    }
+}
+
+// Sums of the block partials per (image, channel): block = 32 channels x 16 slices of the block index; a slice adds
+// its blocks k = slice, slice + 16, ... in order, the slices are added in order (deterministic).  One thread per
+// channel walking all nblk rows (as the SE phase-2 kernel does for dgate) is a chain of nblk dependent L2 round
+// trips: 60 us for the 107 row blocks of a 256 x 256 image.  tot_dg (B, C), tot_bn (B, 4, C).
+__global__ void __launch_bounds__(512)
+se_bn_partial_sum_kernel(const float *__restrict__ dgp, const float *__restrict__ bnp, int nblk, int C,
+                         float *__restrict__ tot_dg, float *__restrict__ tot_bn) {
+    __shared__ float red[16][5][32];
+    const int cx = threadIdx.x & 31, ky = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx, b = blockIdx.y;
+    float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c < C) {
+        const float *pd = dgp + (size_t)b * nblk * C + c;
+        const float *pb = bnp + (size_t)b * nblk * 4 * C + c;
+#pragma unroll 2
+        for (int k = ky; k < nblk; k += 16) {
+            const float v0 = __ldcg(pd + (size_t)k * C);
+            const float v1 = __ldcg(pb + ((size_t)k * 4 + 0) * C), v2 = __ldcg(pb + ((size_t)k * 4 + 1) * C);
+            const float v3 = __ldcg(pb + ((size_t)k * 4 + 2) * C), v4 = __ldcg(pb + ((size_t)k * 4 + 3) * C);
+            t[0] += v0; t[1] += v1; t[2] += v2; t[3] += v3; t[4] += v4;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) red[ky][j][cx] = t[j];
+    __syncthreads();
+    if (ky < 5 && c < C) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) a += red[q][ky][cx];
+        if (ky == 0) tot_dg[(size_t)b * C + c] = a;
+        else tot_bn[((size_t)b * 4 + (ky - 1)) * C + c] = a;
+    }
+}
+
+// per (image, channel): block partials summed in order, folded with gate and dmean/HW into the two sums of the
+// BatchNorm backward: out (B, 2, C) = the `partial` matrix bn_act_bwd_finalize_kernel reduces (one row per image)
+__global__ void __launch_bounds__(256)
+se_bn_bwd_combine_kernel(const float *__restrict__ bnp, int nblk, const float *__restrict__ gate,
+                         const float *__restrict__ dmean, const float *__restrict__ mean, float inv_hw, int C,
+                         float *__restrict__ out) {
+    const int c = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+    if (c >= C) return;
+    double t[4] = {0.0, 0.0, 0.0, 0.0};
+    const float *p = bnp + (size_t)b * nblk * 4 * C + c;
+    for (int k = 0; k < nblk; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] += (double)__ldcg(p + ((size_t)k * 4 + j) * C);
+    }
+    // sums about the batch mean (what bn_act_bwd_finalize_kernel expects), in double: sum w z - mu sum w
+    const double mu = (double)mean[c];
+    const double t1 = t[1] - mu * t[0], t3 = t[3] - mu * t[2];
+    const double g = (double)gate[(size_t)b * C + c], m = (double)dmean[(size_t)b * C + c] * (double)inv_hw;
+    out[((size_t)b * 2 + 0) * C + c] = (float)(g * t[0] + m * t[2]);
+    out[((size_t)b * 2 + 1) * C + c] = (float)(g * t1 + m * t3);
+}
+
+// dz = k1 * ((dyg * gate + dmean/HW) * swish'(u)) + k2 * z + k3
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
+se_bn_bwd_apply_kernel(const T *__restrict__ dyg, const T *__restrict__ z, const float *__restrict__ ua,
+                       const float *__restrict__ ub, const float *__restrict__ k123,
+                       const float *__restrict__ gate, const float *__restrict__ dmean, float inv_hw,
+                       T *__restrict__ dz, int HW, int C, int nvb, int rows_per_block, uint32_t zero) {
+    constexpr int CV = 4;
+    const int PY = blockDim.x / nvb;
+    const int cv = threadIdx.x % nvb, py = threadIdx.x / nvb, c = (blockIdx.z * nvb + cv) * CV;
+    if (py >= PY || c >= C) return;
+    const int b = blockIdx.y;
+    float a[CV], bb[CV], k1g[CV], k1m[CV], k2[CV], k3[CV];      // k1 * gate, k1 * dmean / HW
+    ldv<CV>(ua + c, a); ldv<CV>(ub + c, bb);
+    ldv<CV>(k123 + c, k2);
+    ldv<CV>(gate + (size_t)b * C + c, k1g); ldv<CV>(dmean + (size_t)b * C + c, k1m);
+#pragma unroll
+    for (int k = 0; k < CV; ++k) { k1g[k] *= k2[k]; k1m[k] *= k2[k] * inv_hw; }
+    ldv<CV>(k123 + C + c, k2); ldv<CV>(k123 + 2 * C + c, k3);
+    const size_t r0 = (size_t)blockIdx.x * rows_per_block;
+    const size_t r1 = r0 + rows_per_block < (size_t)HW ? r0 + rows_per_block : (size_t)HW;
+    const T *pg = dyg + (size_t)b * HW * C, *pz = z + (size_t)b * HW * C;
+    T *po = dz + (size_t)b * HW * C;
+    auto apply = [&](float *gg, const float *zz) {
+#pragma unroll
+        for (int k = 0; k < CV; ++k) {
+            float y, ag;
+            swish_and_grad<T>(fmaf(zz[k], a[k], bb[k]), y, ag);
+            gg[k] = fmaf(fmaf(gg[k], k1g[k], k1m[k]), ag, fmaf(k2[k], zz[k], k3[k]));
+        }
+    };
+    size_t r = r0 + py;
+    const size_t step = (size_t)kBnU * PY;
+    const bool pf = threadIdx.x == 0 && blockIdx.z == 0;
+    if (pf) {
+        prefetch_rows(pz, r0, r0 + kBnPD * step, r1, C);
+        prefetch_rows(pg, r0, r0 + kBnPD * step, r1, C);
+    }
+    size_t rq = r0 + kBnPD * step;
+    for (; r + (size_t)(kBnU - 1) * PY < r1; r += step, rq += step) {
+        if (pf) {
+            prefetch_rows(pz, rq, rq + step, r1, C);
+            prefetch_rows(pg, rq, rq + step, r1, C);
+        }
+        typename Raw4<T>::type zr[kBnU], gr[kBnU];
+#pragma unroll
+        for (int u = 0; u < kBnU; ++u) {
+            gr[u] = Raw4<T>::load(pg + (r + (size_t)u * PY) * C + c);
+            zr[u] = Raw4<T>::load(pz + (r + (size_t)u * PY) * C + c);
+        }
+        Raw4<T>::all_loaded(zr, gr, zero);
+#pragma unroll
+        for (int u = 0; u < kBnU; ++u) {
+            float gg[CV], zz[CV];
+            Raw4<T>::unpack(gr[u], gg);
+            Raw4<T>::unpack(zr[u], zz);
+            apply(gg, zz);
+            VecB<T, CV>::store(po + (r + (size_t)u * PY) * C + c, gg);
+        }
+    }
+    for (; r < r1; r += PY) {
+        float gg[CV], zz[CV];
+        VecB<T, CV>::load(pg + r * C + c, gg);
+        VecB<T, CV>::load(pz + r * C + c, zz);
+        apply(gg, zz);
+        VecB<T, CV>::store(po + r * C + c, gg);
+    }
+}
+
+}  // namespace effdet
+
+/* Row blocks per image of the fused reduction (grid = blocks x B). */
+// Block shape: nvb channel vectors x PY rows, <= 256 threads.  The channel range is cut into the number of
+// chunks (grid.z) that fills the block best (C = 672: one chunk would be 168 threads, two chunks are 84 x 3 =
+// 252), then rows_per_block is a multiple of kBnU * PY (no one-row-at-a-time tail except in an image's last
+// block) sized for about two waves of three blocks per SM over (blocks, B, chunks).
+static void se_bn_geometry(int C, int *chunks, int *nvb, int *PY) {
+    int nvec = C / 4; if (nvec < 1) nvec = 1;
+    int best_t = 0;
+    for (int ch = 1; ch <= 8; ++ch) {
+        const int v = (nvec + ch - 1) / ch;
+        if (v > 256) continue;
+        int py = 256 / v; if (py < 1) py = 1;
+        if (v * py > best_t + 8) { best_t = v * py; *chunks = ch; *nvb = v; *PY = py; }
+    }
+}
+static int se_bn_rows_per_block(int B, int HW, int chunks, int PY) {
+    const int unit = kBnU * PY;
+    long want = ((long)kNumSMs * 3 * 2 + (long)B * chunks - 1) / ((long)B * chunks);     // blocks per (image, chunk)
+    if (want < 1) want = 1;
+    long rpb = ((long)HW + want - 1) / want;
+    rpb = (rpb + unit - 1) / unit * unit;
+    if (rpb < 4L * unit) rpb = 4L * unit;
+    return (int)rpb;
+}
+extern "C" int effdet_se_bn_backward_blocks(int B, int HW, int C, int dtype) {
+    (void)dtype;
+    int chunks = 1, nvb = 1, PY = 1;
+    se_bn_geometry(C, &chunks, &nvb, &PY);
+    return (int)cdiv((size_t)HW, (size_t)se_bn_rows_per_block(B, HW, chunks, PY));
+}
+
+/* Fused backward of the squeeze-excite gate and of the depthwise BatchNorm (training statistics) + swish of an
+ * MBConv block (efficientnet.py:242-286): dyg (B,HW,C) gradient of y*gate, z (B,HW,C) the raw depthwise output
+ * -> dz (B,HW,C) gradient of z, gradients of the SE kernels / biases and of gamma / beta.  Same results as
+ * effdet_se_backward followed by effdet_bn_act_backward(act = swish) up to rounding (dy stays in fp32 here),
+ * in five instead of nine passes over the tensors.  Scratch (floats): dg_partial B*(nblk+1)*C, bn_partial
+ * B*(nblk+1)*4*C, bn_rows B*2*C, fc_scratch B*(2*C*R + R + C), dmean B*C, k123 3*C; nblk =
+ * effdet_se_bn_backward_blocks(). */
+extern "C" int effdet_se_bn_backward(const void *dyg, const void *z, const float *gate, const float *se_sum,
+                                     int se_blocks, const float *w1, const float *b1, const float *w2,
+                                     const float *b2, float *dw1, float *db1, float *dw2, float *db2,
+                                     const float *gamma, const float *save_mean, const float *save_invstd,
+                                     const float *ua, const float *ub, float *dgamma, float *dbeta, void *dz,
+                                     float *k123, float *dg_partial, float *bn_partial, float *bn_rows, int nblk,
+                                     float *fc_scratch, float *dmean, int B, int HW, int C, int R, int dtype,
+                                     void *stream) {
+    EFFDET_REQUIRE(dyg && z && gate && se_sum && w1 && b1 && w2 && b2 && dw1 && db1 && dw2 && db2 && gamma &&
+                       save_mean && save_invstd && ua && ub && dz && k123 && dg_partial && bn_partial && bn_rows &&
+                       fc_scratch && dmean, "null pointer");
+    EFFDET_REQUIRE(B > 0 && HW > 0 && C > 0 && C % 8 == 0 && R > 0 && R <= 512 && se_blocks > 0, "bad sizes");
+    EFFDET_REQUIRE(nblk == effdet_se_bn_backward_blocks(B, HW, C, dtype), "nblk must come from effdet_se_bn_backward_blocks");
+    cudaStream_t st = as_stream(stream);
+    int chunks = 1, nvb = 1, PY = 1;
+    se_bn_geometry(C, &chunks, &nvb, &PY);
+    const int rpb = se_bn_rows_per_block(B, HW, chunks, PY);
+    const size_t sm = PY > 1 ? (size_t)PY * 5 * nvb * 4 * sizeof(float) : 0;
+    EFFDET_REQUIRE(sm <= 48 * 1024, "reduction scratch too large");
+    dim3 grid(nblk, B, chunks);
+    DISPATCH_TB(dtype,
+        (se_bn_bwd_reduce_kernel<float><<<grid, nvb * PY, sm, st>>>((const float *)dyg, (const float *)z, ua, ub,
+                                                                    HW, C, nvb, rpb, dg_partial, bn_partial, 0u)),
+        (se_bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, nvb * PY, sm, st>>>(
+            (const __nv_bfloat16 *)dyg, (const __nv_bfloat16 *)z, ua, ub, HW, C, nvb, rpb, dg_partial, bn_partial, 0u)))
+    EFFDET_LAUNCHED();
+    float *tot_dg = dg_partial + (size_t)B * nblk * C, *tot_bn = bn_partial + (size_t)B * nblk * 4 * C;
+    se_bn_partial_sum_kernel<<<dim3(cdiv((size_t)C, 32), B), 512, 0, st>>>(dg_partial, bn_partial, nblk, C, tot_dg, tot_bn);
+    EFFDET_LAUNCHED();
+    {   // SE fully-connected backward: the launches of effdet_se_backward between its two tensor passes
+        const int nch = (C + 255) / 256;
+        const size_t per = (size_t)2 * C * R + R + C;
+        EFFDET_REQUIRE((size_t)B * (2 * C + 3 * R + (size_t)nch * R) <= (size_t)B * per, "fc_scratch too small");
+        float *mean_g = fc_scratch, *s1_g = mean_g + (size_t)B * C, *rr_g = s1_g + (size_t)B * R;
+        float *ds2_g = rr_g + (size_t)B * R, *ds1_g = ds2_g + (size_t)B * C, *ds1p = ds1_g + (size_t)B * R;
+        const size_t sm1 = (size_t)(C + 512) * sizeof(float);
+        EFFDET_REQUIRE(sm1 <= 48 * 1024, "C too large");
+        if (se_cluster_ok(C, R)) {
+            EFFDET_CUDA(se_cluster_launch(st, se_sum, se_blocks, 1.f / (float)HW, w1, b1, w2, b2, nullptr, B, C, R,
+                                          mean_g, s1_g, rr_g));
+        } else {
+            se_bwd_phase1_kernel<<<B, 512, sm1, st>>>(se_sum, se_blocks, 1.f / (float)HW, w1, b1, C, R, mean_g, s1_g, rr_g);
+        }
+        EFFDET_LAUNCHED();
+        dim3 g2(nch, B);
+        se_bwd_phase2_kernel<<<g2, 256, (size_t)9 * R * sizeof(float), st>>>(rr_g, tot_dg, 1, w2, b2, C, R, ds2_g, ds1p);
+        EFFDET_LAUNCHED();
+        se_bwd_phase3_kernel<<<g2, 256, (size_t)R * sizeof(float), st>>>(ds1p, nch, s1_g, w1, C, R, ds1_g, dmean);
+        EFFDET_LAUNCHED();
+        se_bwd_phase4_kernel<<<cdiv(per, 256), 256, 0, st>>>(mean_g, rr_g, ds2_g, ds1_g, B, C, R, dw1, dw2, db1, db2);
+        EFFDET_LAUNCHED();
+    }
+    se_bn_bwd_combine_kernel<<<dim3(cdiv((size_t)C, 256), B), 256, 0, st>>>(tot_bn, 1, gate, dmean, save_mean,
+                                                                           1.f / (float)HW, C, bn_rows);
+    EFFDET_LAUNCHED();
+    bn_act_bwd_finalize_kernel<<<cdiv((size_t)C * 32, 256), 256, 0, st>>>(bn_rows, B, (double)B * (double)HW, gamma,
+                                                                        save_mean, save_invstd, k123, dgamma, dbeta, C);
+    EFFDET_LAUNCHED();
+    {
+        const size_t rpa = (size_t)rpb;
+        dim3 ga(cdiv((size_t)HW, rpa), B, chunks);
+        DISPATCH_TB(dtype,
+            (se_bn_bwd_apply_kernel<float><<<ga, nvb * PY, 0, st>>>((const float *)dyg, (const float *)z, ua, ub, k123,
+                                                                    gate, dmean, 1.f / (float)HW, (float *)dz, HW, C,
+                                                                    nvb, (int)rpa, 0u)),
+            (se_bn_bwd_apply_kernel<__nv_bfloat16><<<ga, nvb * PY, 0, st>>>(
+                (const __nv_bfloat16 *)dyg, (const __nv_bfloat16 *)z, ua, ub, k123, gate, dmean, 1.f / (float)HW,
+                (__nv_bfloat16 *)dz, HW, C, nvb, (int)rpa, 0u)))
+    }
+    EFFDET_LAUNCHED();
+    return EFFDET_OK;
+}

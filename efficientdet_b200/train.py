@@ -725,25 +725,48 @@ class TrainPlan(engine.Plan):
         wt = self._transposed_weight(pkey, 1, cmid, cout)
         self._dgrad(None, [dz_p], wt, cout, cmid, [dyg], [yg], None, [0], [yg.shape], name=p + "project_dgrad",
                     key=pkey)
-        # squeeze-excite
+        # squeeze-excite, then depthwise BN + swish
         y_d, gate, part, nblk = rec["y_d"], rec["gate"], rec["part"], rec["nblk"]
         R = blk.se_filters
-        dy_d = self.val(y_d.shape, name=p + "dw_grad")
-        dgb = lib.effdet_se_backward_blocks(HW, cmid, self.dtype)
-        dgp = self._scratch(B * dgb * cmid, p + "se_dg_partial")
         fcs = self._scratch(B * (2 * cmid * R + R + cmid), p + "se_fc_scratch")
         dmean = self._scratch(B * cmid, p + "se_dmean")
         w, gw = self.w, self.gw
-        self.add("se_bwd", [dyg, y_d, gate, part], [dy_d, dgp, fcs, dmean],
-                 lambda: _call("effdet_se_backward", dyg.ptr, y_d.ptr, gate.ptr, part.ptr, nblk,
-                               w(p + "se_reduce/kernel").data_ptr(), w(p + "se_reduce/bias").data_ptr(),
-                               w(p + "se_expand/kernel").data_ptr(), w(p + "se_expand/bias").data_ptr(),
-                               dy_d.ptr, gw(p + "se_reduce/kernel").data_ptr(), gw(p + "se_reduce/bias").data_ptr(),
-                               gw(p + "se_expand/kernel").data_ptr(), gw(p + "se_expand/bias").data_ptr(),
-                               dgp.ptr, dgb, fcs.ptr, dmean.ptr, B, HW, cmid, R, self.dtype), p + "se_bwd")
-        # depthwise BN + swish -> depthwise conv
         bn_d = dict(rec["bn_d"]); bn_d["z"] = rec["z_d"]
-        dz_d = self._bn_act_backward(bn_d, dy_d, p + "dw")
+        if bn_d["train"] and bn_d["act"] == ACT_SWISH and os.environ.get("EFFDET_SE_BN_FUSED", "1") != "0":
+            # SE gate backward + depthwise BN / swish backward in one reduction and one apply pass over
+            # (dyg, z_d): y_d and swish' are recomputed from z_d, dy_d is never written (effdet_se_bn_backward:
+            # five instead of nine passes over the expanded tensors)
+            z_d, bn = rec["z_d"], bn_d["bn"]
+            dz_d = self.val(z_d.shape, name=p + "dw_dz")
+            nb2 = lib.effdet_se_bn_backward_blocks(B, HW, cmid, self.dtype)
+            dgp2 = self._scratch(B * (nb2 + 1) * cmid, p + "se_dg_partial")
+            bnp = self._scratch(B * (nb2 + 1) * 4 * cmid, p + "se_bn_partial")
+            bnr = self._scratch(B * 2 * cmid, p + "se_bn_rows")
+            k123 = self._scratch(3 * cmid, bn + "/k123")
+            mu, iv, ua, ub = bn_d["mean"], bn_d["invstd"], bn_d["ua"], bn_d["ub"]
+            self.add("se_bn_bwd", [dyg, z_d, gate, part, mu, iv, ua, ub], [dz_d, k123, dgp2, bnp, bnr, fcs, dmean],
+                     lambda: _call("effdet_se_bn_backward", dyg.ptr, z_d.ptr, gate.ptr, part.ptr, nblk,
+                                   w(p + "se_reduce/kernel").data_ptr(), w(p + "se_reduce/bias").data_ptr(),
+                                   w(p + "se_expand/kernel").data_ptr(), w(p + "se_expand/bias").data_ptr(),
+                                   gw(p + "se_reduce/kernel").data_ptr(), gw(p + "se_reduce/bias").data_ptr(),
+                                   gw(p + "se_expand/kernel").data_ptr(), gw(p + "se_expand/bias").data_ptr(),
+                                   w(bn + "/gamma").data_ptr(), mu.ptr, iv.ptr, ua.ptr, ub.ptr,
+                                   gw(bn + "/gamma").data_ptr(), gw(bn + "/beta").data_ptr(), dz_d.ptr, k123.ptr,
+                                   dgp2.ptr, bnp.ptr, bnr.ptr, nb2, fcs.ptr, dmean.ptr, B, HW, cmid, R, self.dtype),
+                     p + "se_bn_bwd")
+        else:
+            dy_d = self.val(y_d.shape, name=p + "dw_grad")
+            dgb = lib.effdet_se_backward_blocks(HW, cmid, self.dtype)
+            dgp = self._scratch(B * dgb * cmid, p + "se_dg_partial")
+            self.add("se_bwd", [dyg, y_d, gate, part], [dy_d, dgp, fcs, dmean],
+                     lambda: _call("effdet_se_backward", dyg.ptr, y_d.ptr, gate.ptr, part.ptr, nblk,
+                                   w(p + "se_reduce/kernel").data_ptr(), w(p + "se_reduce/bias").data_ptr(),
+                                   w(p + "se_expand/kernel").data_ptr(), w(p + "se_expand/bias").data_ptr(),
+                                   dy_d.ptr, gw(p + "se_reduce/kernel").data_ptr(),
+                                   gw(p + "se_reduce/bias").data_ptr(), gw(p + "se_expand/kernel").data_ptr(),
+                                   gw(p + "se_expand/bias").data_ptr(), dgp.ptr, dgb, fcs.ptr, dmean.ptr, B, HW,
+                                   cmid, R, self.dtype), p + "se_bwd")
+            dz_d = self._bn_act_backward(bn_d, dy_d, p + "dw")
         xin = rec["xin"]
         k, st = blk.kernel_size, blk.stride
         nb = lib.effdet_dw_backward_blocks(B, H, H, cmid, k, st, self.dtype)

@@ -441,6 +441,22 @@ int effdet_se_backward(const void *dyg, const void *y, const float *gate, const 
                        void *dy, float *dw1, float *db1, float *dw2, float *db2, float *dg_partial,
                        int dg_blocks, float *fc_scratch, float *dmean, int B, int HW, int C, int R,
                        int dtype, void *stream);
+
+/* Fused backward of the squeeze-excite gate and of the depthwise BatchNorm (training statistics) + swish of an
+ * MBConv block (efficientnet.py:242-286): dyg (B,HW,C) gradient of y*gate, z (B,HW,C) the raw depthwise output
+ * -> dz (B,HW,C) gradient of z, the gradients of the SE kernels / biases and of gamma / beta.  Same results as
+ * effdet_se_backward followed by effdet_bn_act_backward(act = swish) up to rounding, in five instead of nine
+ * passes over the tensors (y and swish' are recomputed from z; dy is never materialised).  ua / ub: the affine
+ * map u = z*ua + ub of the forward pass.  Scratch (floats): dg_partial B*(nblk+1)*C, bn_partial B*(nblk+1)*4*C,
+ * bn_rows B*2*C, fc_scratch B*(2*C*R + R + C), dmean B*C, k123 3*C; nblk = effdet_se_bn_backward_blocks(). */
+int effdet_se_bn_backward_blocks(int B, int HW, int C, int dtype);
+int effdet_se_bn_backward(const void *dyg, const void *z, const float *gate, const float *se_sum, int se_blocks,
+                          const float *w1, const float *b1, const float *w2, const float *b2, float *dw1,
+                          float *db1, float *dw2, float *db2, const float *gamma, const float *save_mean,
+                          const float *save_invstd, const float *ua, const float *ub, float *dgamma,
+                          float *dbeta, void *dz, float *k123, float *dg_partial, float *bn_partial,
+                          float *bn_rows, int nblk, float *fc_scratch, float *dmean, int B, int HW, int C, int R,
+                          int dtype, void *stream);
 /* Depthwise conv backward, k in {3,5}, stride in {1,2}: dkernel (k,k,C) and (optional) dx. */
 int effdet_dw_backward_blocks(int B, int H, int W, int C, int k, int stride, int dtype);
 int effdet_dw_backward(const void *x, const void *dz, const float *kernel, void *dx, float *dkernel,

@@ -33,7 +33,7 @@ def test_python_binding_covers_header():
                                      "effdet_colreduce_blocks", "effdet_dw_wgrad_blocks",
                                      "effdet_conv_wgrad_splits", "effdet_conv_wgrad_tc_splits", "effdet_conv_wgrad_tc_fuses_bias", "effdet_dwconv_se_blocks",
                                      "effdet_conv_tc_block_n", "effdet_conv_weight_panel_elems", "effdet_conv_weight_panel_split_elems",
-                                     "effdet_se_backward_blocks", "effdet_dw_backward_blocks",
+                                     "effdet_se_backward_blocks", "effdet_se_bn_backward_blocks", "effdet_dw_backward_blocks",
                                      "effdet_stem_wgrad_blocks", "effdet_plan_num_weights",
                                      "effdet_plan_num_anchors", "effdet_plan_num_launches",
                                      "effdet_replay_num_launches"}

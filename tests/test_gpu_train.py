@@ -129,6 +129,78 @@ def _nchw(a):
     return torch.from_numpy(np.ascontiguousarray(a)).permute(0, 3, 1, 2).contiguous().double()
 
 
+@pytest.mark.parametrize("dtype,B,H,C,R", [("f32", 2, 12, 48, 4), ("bf16", 3, 9, 144, 6), ("bf16", 2, 8, 2688, 112),
+                                            ("f32", 2, 6, 1152, 48)])
+def test_fused_se_bn_backward_matches_separate_passes(dtype, B, H, C, R):
+    """effdet_se_bn_backward (one reduction + one apply pass over dyg / z) against effdet_se_backward followed by
+    effdet_bn_act_backward (swish), the pair the whole-step oracle tests validate: same dz, gamma / beta gradients
+    and SE weight gradients (fp32 to 2e-5; bf16 to the rounding of the dy tensor the separate form stores)."""
+    from efficientdet_b200 import _lib
+    lib = _lib.load()
+    dt = _lib.F32 if dtype == "f32" else _lib.BF16
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    HW = H * H
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    rnd = lambda *shape, s=1.0: torch.randn(*shape, device="cuda", generator=g) * s
+    z = (rnd(B, HW, C) * 1.5 + rnd(C) * 0.5).to(tdt)
+    dyg = (rnd(B, HW, C) * 0.1).to(tdt)
+    gamma, beta = rnd(C) * 0.3 + 1.0, rnd(C) * 0.2
+    zf = z.float().reshape(-1, C)
+    mean, var = zf.mean(0), zf.var(0, unbiased=False)
+    invstd = 1.0 / torch.sqrt(var + 1e-3)
+    ua = (gamma * invstd).contiguous(); ub = (beta - mean * ua).contiguous()
+    u = z.float() * ua + ub
+    y = (u * torch.sigmoid(u)).to(tdt)
+    w1, b1, w2, b2 = rnd(C, R, s=0.2), rnd(R, s=0.1), rnd(R, C, s=0.2), rnd(C, s=0.1)
+    sblk = lib.effdet_se_backward_blocks(HW, C, dt)
+    se_sum = torch.empty((B, sblk, C), device="cuda")
+    st = _lib.stream_ptr()
+    _lib.call("effdet_spatial_sum", y.data_ptr(), se_sum.data_ptr(), sblk, B, HW, C, dt, st)
+    gate = torch.empty((B, C), device="cuda")
+    _lib.call("effdet_se_gate", se_sum.data_ptr(), sblk, 1.0 / HW, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+              b2.data_ptr(), gate.data_ptr(), B, C, R, st)
+    fcs_n = B * (2 * C * R + R + C)
+
+    def grads():
+        return [torch.zeros_like(t) for t in (w1, b1, w2, b2, gamma, beta)]
+    # ---- separate passes
+    dw1a, db1a, dw2a, db2a, dga, dba = grads()
+    dy = torch.empty_like(z); dza = torch.empty_like(z)
+    dgb = lib.effdet_se_backward_blocks(HW, C, dt)
+    dgp = torch.empty(B * dgb * C, device="cuda"); fcs = torch.empty(fcs_n, device="cuda")
+    dmean = torch.empty(B * C, device="cuda")
+    _lib.call("effdet_se_backward", dyg.data_ptr(), y.data_ptr(), gate.data_ptr(), se_sum.data_ptr(), sblk,
+              w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), dy.data_ptr(), dw1a.data_ptr(),
+              db1a.data_ptr(), dw2a.data_ptr(), db2a.data_ptr(), dgp.data_ptr(), dgb, fcs.data_ptr(),
+              dmean.data_ptr(), B, HW, C, R, dt, st)
+    rows = B * HW
+    nblk = lib.effdet_colreduce_blocks(rows, C, dt)
+    part = torch.empty(2 * C * nblk, device="cuda"); k123 = torch.empty(3 * C, device="cuda")
+    _lib.call("effdet_bn_act_backward", dy.data_ptr(), z.data_ptr(), rows, C, gamma.data_ptr(), mean.data_ptr(),
+              invstd.data_ptr(), ua.data_ptr(), ub.data_ptr(), 0, _lib.ACT_SWISH, dga.data_ptr(), dba.data_ptr(),
+              dza.data_ptr(), k123.data_ptr(), part.data_ptr(), nblk, dt, st)
+    # ---- fused
+    dw1b, db1b, dw2b, db2b, dgbb, dbb = grads()
+    dzb = torch.empty_like(z)
+    nb2 = lib.effdet_se_bn_backward_blocks(B, HW, C, dt)
+    dgp2 = torch.empty(B * (nb2 + 1) * C, device="cuda"); bnp = torch.empty(B * (nb2 + 1) * 4 * C, device="cuda")
+    bnr = torch.empty(B * 2 * C, device="cuda"); k2 = torch.empty(3 * C, device="cuda")
+    fcs2 = torch.empty(fcs_n, device="cuda"); dmean2 = torch.empty(B * C, device="cuda")
+    _lib.call("effdet_se_bn_backward", dyg.data_ptr(), z.data_ptr(), gate.data_ptr(), se_sum.data_ptr(), sblk,
+              w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), dw1b.data_ptr(), db1b.data_ptr(),
+              dw2b.data_ptr(), db2b.data_ptr(), gamma.data_ptr(), mean.data_ptr(), invstd.data_ptr(), ua.data_ptr(),
+              ub.data_ptr(), dgbb.data_ptr(), dbb.data_ptr(), dzb.data_ptr(), k2.data_ptr(), dgp2.data_ptr(),
+              bnp.data_ptr(), bnr.data_ptr(), nb2, fcs2.data_ptr(), dmean2.data_ptr(), B, HW, C, R, dt, st)
+    torch.cuda.synchronize()
+    tol = 2e-5 if dtype == "f32" else 1.5e-2
+    pairs = [("dz", dza, dzb), ("dgamma", dga, dgbb), ("dbeta", dba, dbb), ("dw1", dw1a, dw1b), ("db1", db1a, db1b),
+             ("dw2", dw2a, dw2b), ("db2", db2a, db2b), ("dmean", dmean, dmean2)]
+    for name, a, b in pairs:
+        a, b = a.float(), b.float()
+        err = float((a - b).norm() / a.norm().clamp_min(1e-20))
+        assert err < tol, (name, err)
+
+
 # ------------------------------------------------------------------ backward kernels, one by one
 def test_conv_wgrad_grouped_and_strided_dz():
     import ctypes
