@@ -437,6 +437,16 @@ se_gate_cluster_kernel(const float *__restrict__ se_sum, int se_blocks, float in
             const float *src = src0 + c;
             float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
             int k = sl;
+            // eight partial rows in flight (a wide slice, n > 256 channels, walks all se_blocks rows with one
+            // thread per channel: 64 rows at four loads in flight were 16 dependent L2 round trips, most of the
+            // 40 us this kernel took at C = 2688 in the r3 launch list)
+            for (; k + 7 * KS < se_blocks; k += 8 * KS) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(k + u * KS) * C];
+                t0 += v[0]; t1 += v[1]; t2 += v[2]; t3 += v[3];
+                t0 += v[4]; t1 += v[5]; t2 += v[6]; t3 += v[7];
+            }
             for (; k + 3 * KS < se_blocks; k += 4 * KS) {
                 t0 += src[(size_t)k * C]; t1 += src[(size_t)(k + KS) * C];
                 t2 += src[(size_t)(k + 2 * KS) * C]; t3 += src[(size_t)(k + 3 * KS) * C];

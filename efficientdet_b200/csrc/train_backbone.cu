@@ -412,27 +412,36 @@ se_bwd_phase1_kernel(const float *__restrict__ se_sum, int se_blocks, float inv_
     }
 }
 // phase 2 (grid nch x B, 256 threads = 256 channels): gate pre-activation, ds2 = dgate * g (1-g),
-// partial sums over the chunk of ds1_pre[j] = sum_c ds2[c] * w2[j][c]
+// partial sums over the chunk of ds1_pre[j] = sum_c ds2[c] * w2[j][c].
+// The gate pre-activation keeps eight loads of w2 in flight per thread; the chunk's part of W2 ds2 is computed
+// with warp w owning the rows j = w, w + 8, ... and its lanes striding over the 256 channels (eight independent
+// coalesced loads, one shuffle reduction per row).  The first form -- every warp reducing every row j over its
+// 32 channels, one dependent load and five shuffles per row and warp -- took 36 us per launch at C = 2688,
+// R = 112 (r3 launch list), as long as a pass over the block's activation tensor.
 __global__ void __launch_bounds__(256)
 se_bwd_phase2_kernel(const float *__restrict__ rr_g, const float *__restrict__ dgate_partial, int dg_blocks,
                      const float *__restrict__ w2, const float *__restrict__ b2, int C, int R,
                      float *__restrict__ ds2_o, float *__restrict__ ds1p) {
-    extern __shared__ float sm[];       // rr[R] | red[8][R]
-    float *rr = sm, *red = sm + R;
+    extern __shared__ float sm[];       // rr[R] (callers allocate 9 R floats)
+    __shared__ float sd[256];           // ds2 of the block's channels
+    float *rr = sm;
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x * 256 + tid;
     for (int j = tid; j < R; j += 256) rr[j] = rr_g[(size_t)b * R + j];
     __syncthreads();
     float d = 0.f;
     if (c < C) {
-        float s4[4] = {b2[c], 0.f, 0.f, 0.f};
+        float s8[8] = {b2[c], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int j = 0;
-        for (; j + 3 < R; j += 4) {
+        for (; j + 7 < R; j += 8) {
+            float q[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) s4[u] = fmaf(rr[j + u], w2[(size_t)(j + u) * C + c], s4[u]);
+            for (int u = 0; u < 8; ++u) q[u] = w2[(size_t)(j + u) * C + c];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s8[u] = fmaf(rr[j + u], q[u], s8[u]);
         }
-        for (; j < R; ++j) s4[0] = fmaf(rr[j], w2[(size_t)j * C + c], s4[0]);
-        const float sg = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        for (; j < R; ++j) s8[0] = fmaf(rr[j], w2[(size_t)j * C + c], s8[0]);
+        const float sg = ((s8[0] + s8[1]) + (s8[2] + s8[3])) + ((s8[4] + s8[5]) + (s8[6] + s8[7]));
         const float g = 1.f / (1.f + __expf(-sg));
         const float *src = dgate_partial + (size_t)b * dg_blocks * C + c;
         float dg = 0.f;
@@ -440,19 +449,21 @@ se_bwd_phase2_kernel(const float *__restrict__ rr_g, const float *__restrict__ d
         d = dg * g * (1.f - g);
         ds2_o[(size_t)b * C + c] = d;
     }
-    // ds1 partial of this chunk: for each j, sum over the block's 256 channels (warp shuffle + 8 rows)
-    for (int j = 0; j < R; ++j) {
-        float v = c < C ? d * w2[(size_t)j * C + c] : 0.f;
+    sd[tid] = d;
+    __syncthreads();
+    const int cbase = blockIdx.x * 256;
+    float *out = ds1p + ((size_t)b * gridDim.x + blockIdx.x) * R;
+    for (int j = warp; j < R; j += 8) {
+        const float *wr = w2 + (size_t)j * C + cbase;
+        float q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = cbase + lane + 32 * i < C ? wr[lane + 32 * i] : 0.f;
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v = fmaf(sd[lane + 32 * i], q[i], v);
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) red[warp * R + j] = v;
-    }
-    __syncthreads();
-    for (int j = tid; j < R; j += 256) {
-        float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) t += red[w * R + j];
-        ds1p[((size_t)b * gridDim.x + blockIdx.x) * R + j] = t;
+        if (lane == 0) out[j] = v;
     }
 }
 // phase 3 (grid nch x B): ds1 = (sum of chunk partials) * swish'(s1); dmean[c] = sum_j w1[c][j] ds1[j]
@@ -477,6 +488,20 @@ se_bwd_phase3_kernel(const float *__restrict__ ds1p, int nch, const float *__res
         const float *wr = w1 + (size_t)c * R;
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
         int j = 0;
+        if ((R & 3) == 0 && (reinterpret_cast<uintptr_t>(w1) & 15) == 0) {
+            // a thread streams its own row of W1: four 16-byte loads in flight (r3 launch list: 15 us per launch
+            // at C = 2688, R = 112 with four scalar loads in flight)
+            for (; j + 15 < R; j += 16) {
+                float4 q[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) q[u] = *reinterpret_cast<const float4 *>(wr + j + 4 * u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    s4[u] = fmaf(q[u].x, ds1[j + 4 * u], s4[u]); s4[u] = fmaf(q[u].y, ds1[j + 4 * u + 1], s4[u]);
+                    s4[u] = fmaf(q[u].z, ds1[j + 4 * u + 2], s4[u]); s4[u] = fmaf(q[u].w, ds1[j + 4 * u + 3], s4[u]);
+                }
+            }
+        }
         for (; j + 3 < R; j += 4) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) s4[u] = fmaf(wr[j + u], ds1[j + u], s4[u]);
