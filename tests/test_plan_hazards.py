@@ -1,14 +1,20 @@
 """Host logic of the launch plans, checked on the CPU on the REAL launch lists (no kernels run: the plan is built
 with the library calls stubbed, which leaves the op list, the declared inputs / outputs and the buffer assignment
-exactly as on the GPU):
+exactly as on the GPU; host addresses stand in for device addresses):
 
 * liveness-based buffer reuse (engine.Plan._assign_buffers): two values never share a buffer while both are live;
 * multi-lane CUDA-graph capture order (engine.Plan.dependencies / lane_schedule, train.TrainPlan.lane_hint): every
   read-after-write, write-after-write and write-after-read hazard between two launches on a (recycled) buffer is
   ordered by the lane order plus the cross-lane waits -- for the inference plan on 4 lanes, the training plans
   (frozen / trained backbone, weighted BiFPN, stochastic depth) on 2..6 lanes, and for the per-bucket segments the
-  data-parallel step captures (a segment may rely on earlier segments being complete, never on later ones).
+  data-parallel step captures (a segment may rely on earlier segments being complete, never on later ones);
+* memory OUTSIDE the planned values (parameter gradients that several launches accumulate into, shared scratch,
+  stochastic-depth scales): found by scanning the bound arguments of every launch for addresses -- any such address
+  two launches share must be ordered as well (engine.Plan.dependencies states this as an assumption; here it is
+  checked).
 """
+import bisect
+import ctypes
 import pytest
 import torch
 
@@ -25,7 +31,9 @@ def cpu_plans():
         self.reuse = reuse_buffers and not keep_taps
         self._keepalive, self.graph = [], None
         self._build()
-        self._assign_buffers()          # op.make() is NOT called: nothing binds or launches a kernel
+        self._assign_buffers()
+        for op in self.ops:             # binds entry point + arguments (op.fn.call); nothing is launched
+            op.fn = op.make()
 
     _lib.stream_ptr = lambda device=None: 0
     _lib.call = lambda *a, **k: 0
@@ -166,3 +174,65 @@ def test_barrier_launches_are_ordered_against_everything(cpu_plans):
         assert hb[b] == (1 << b) - 1
         for i in range(b + 1, len(p.ops)):
             assert hb[i] >> b & 1
+
+
+def _addresses(a, out):
+    if isinstance(a, bool):
+        return
+    if isinstance(a, int):
+        if a > (1 << 24):
+            out.add(a)
+    elif isinstance(a, (list, tuple, ctypes.Array)):
+        for x in a:
+            _addresses(x, out)
+    elif isinstance(a, ctypes.Structure):
+        for f in a._fields_:
+            _addresses(getattr(a, f[0]), out)
+    elif isinstance(a, ctypes.c_void_p):
+        if a.value:
+            out.add(a.value)
+    elif hasattr(a, "_obj"):                # ctypes.byref(...)
+        _addresses(a._obj, out)
+
+
+@pytest.mark.parametrize("n_lanes", [2, 4, 6])
+def test_untracked_memory_shared_by_launches_is_ordered(cpu_plans, n_lanes):
+    for name, p in cpu_plans.items():
+        if not name.startswith("train"):
+            continue
+        size = {}
+        for v in p.vals:
+            size[v.t.data_ptr()] = max(size.get(v.t.data_ptr(), 0), v.t.numel())
+        starts = sorted(size)
+
+        def planned(x):
+            k = bisect.bisect_right(starts, x) - 1
+            return k >= 0 and x < starts[k] + size[starts[k]]
+        flat = p.net.flat
+        w_lo, w_hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()
+        sched = p.lane_schedule(0, len(p.ops), n_lanes)
+        hb = _happens_before(sched, 0)
+        touched, n_bound = {}, 0
+        for i, op in enumerate(p.ops):
+            call = getattr(op.fn, "call", None)
+            assert call is not None, "%s: launch %d (%s) does not expose its bound arguments" % (name, i, op.kind)
+            found = set()
+            _addresses(call[1], found)
+            n_bound += len(found)
+            for x in found:
+                # weights are read-only inside a step (the BatchNorm moving statistics have one writer and no
+                # reader in training mode); planned values are covered by the hazard test above
+                if not planned(x) and not (w_lo <= x < w_hi):
+                    touched.setdefault(x, []).append(i)
+        assert n_bound > 2 * len(p.ops)
+        shared = [ops for ops in touched.values() if len(ops) > 1]
+        assert shared, name
+        for ops in shared:
+            for a, i in enumerate(ops):
+                for j in ops[a + 1:]:
+                    assert hb[j] >> i & 1, (
+                        "%s (%d lanes): launches %d (%s %s, lane %d) and %d (%s %s, lane %d) share memory outside the "
+                        "planned values but are not ordered -- declare it as a value, or pin both to one lane "
+                        "(if it is read-only for both, exempt it here)" % (
+                            name, n_lanes, i, p.ops[i].kind, p.ops[i].name, sched[i][0],
+                            j, p.ops[j].kind, p.ops[j].name, sched[j][0]))
