@@ -1257,6 +1257,17 @@ extern "C" int effdet_conv_weight_panel_split(const float *w, void *panel, int t
     return EFFDET_OK;
 }
 
+// Shared memory of the halo form (two stages of three kx-shifted patches, nine resident weight tiles, barriers and
+// scale / shift staging, ONE output staging buffer per epilogue warp) against the 227 KiB a CTA can have.  fp32
+// outputs with 49..64 output channels (a class head of 6 or 7 classes on a 64-wide BiFPN) do not fit: 230 KiB --
+// they take the ring form (found by examples/detect_host.c; the launch failed with "invalid argument").
+static bool halo_fits(int bn, bool out_f32) {
+    const size_t stage_out_min = (size_t)kEpiWarps * 32 * 32 * (out_f32 ? 4 : 2);
+    const size_t smem = (size_t)2 * 3 * 20 * 1024 + (size_t)9 * bn * kTileK * 2 + 4096 + (2 * 2 + 5) * 8 + 16 + 1024 +
+                        1024 + stage_out_min;
+    return smem <= 227 * 1024;
+}
+
 // Called by effdet_conv2d when the descriptor qualifies.  Returns EFFDET_E_UNSUPPORTED (without
 // touching the error string of a real failure) when the shape cannot take this path.
 int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
@@ -1282,7 +1293,7 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     {
         const bool halo_ok = d->kh == 3 && d->stride == 1 && Kpad == kTileK && !split && Npad == bn_panel &&
                              !d->weight_per_sample && 9 * bn_panel * kTileK * 2 <= 80 * 1024 &&
-                             getenv("EFFDET_NO_CONV_HALO") == nullptr;
+                             halo_fits(bn_panel, d->out_dtype == EFFDET_F32) && getenv("EFFDET_NO_CONV_HALO") == nullptr;
         static const int min_ctas = getenv("EFFDET_TC_MIN_CTAS") ? atoi(getenv("EFFDET_TC_MIN_CTAS")) : 64;
         long m_est = 0;
         for (int i = 0; i < d->n_groups; ++i) {
@@ -1308,7 +1319,7 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     const int b_tile_bytes = bn * kTileK * 2;
     // halo mode: 3x3 stride 1, one K block per tap, one N tile, all nine weight tiles resident (<= 80 KiB)
     p.halo = (d->kh == 3 && d->stride == 1 && Kpad == kTileK && !split && Npad == bn && !d->weight_per_sample &&
-              9 * b_tile_bytes <= 80 * 1024 && getenv("EFFDET_NO_CONV_HALO") == nullptr) ? 1 : 0;
+              9 * b_tile_bytes <= 80 * 1024 && halo_fits(bn, p.out_f32) && getenv("EFFDET_NO_CONV_HALO") == nullptr) ? 1 : 0;
     p.box_stride = 20 * 1024;                         // (16, 8+2) or (8, 16+2) pixels x 128 bytes
     p.a_stage_bytes = p.halo ? 3 * p.box_stride : kATileBytes;
     p.stage_bufs = 2;

@@ -5,7 +5,7 @@
  * for this path (it is tf.keras Python; TensorFlow stock ops do the device work),
  * so each entry point cites the reference *Python* interface it replaces
  * (file:line under the reference tree) -- the host-side mirror in
- * efficientdet_b200/*.py binds these through ctypes; INTEGRATION.md shows the
+ * the efficientdet_b200 Python package binds these through ctypes; INTEGRATION.md shows the
  * stub a reference maintainer would add.
  *
  * Conventions

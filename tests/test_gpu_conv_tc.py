@@ -149,6 +149,11 @@ def test_conv1x1_tc_per_sample_gate():
 
 @pytest.mark.parametrize("W,cout,out_f32,B,sizes", [(64, 64, False, 4, [16, 8, 4, 2, 1]),
                                                     (64, 36, True, 2, [16, 8, 4, 2, 1]),
+                                                    # 6 / 7 classes on a 64-wide BiFPN: fp32 outputs of 49..64
+                                                    # channels exceed the halo form's shared memory (ring form)
+                                                    (64, 54, True, 2, [16, 8, 4, 2, 1]),
+                                                    (64, 63, True, 2, [32, 16, 8, 4, 2]),
+                                                    (64, 48, True, 2, [16, 8, 4, 2, 1]),
                                                     (88, 180, True, 2, [20, 10, 5]),
                                                     (112, 810, True, 1, [12, 6, 3]),
                                                     # D4 (W 224, head depth 4) and D6 / D7 (W 384) head widths
