@@ -693,6 +693,19 @@ extern "C" int effdet_filter_detections(const float *boxes, const float *classif
         EFFDET_LAUNCHED();
     }
     const size_t sel_bytes = do_nms ? (size_t)max_det * sizeof(float4) : 0;
+    if (sel_bytes > 24 * 1024) {
+        // sort_nms_small_kernel holds 19 KiB of static shared memory: with the selected-box list of more than ~1850
+        // detections (max_detections is validated up to 2048) static + dynamic passes the 48 KiB a launch gets
+        // without opting in
+        static bool sel_attr = false;
+        if (!sel_attr) {
+            EFFDET_CUDA(cudaFuncSetAttribute(sort_nms_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             2048 * (int)sizeof(float4)));
+            EFFDET_CUDA(cudaFuncSetAttribute(sort_nms_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             2048 * (int)sizeof(float4)));
+            sel_attr = true;
+        }
+    }
     sort_nms_small_kernel<<<(unsigned)nseg, kSmallThreads, sel_bytes, st>>>(
         b4, N, keys, offsets, counts, kept, S, iou_threshold, (uint32_t)max_det, do_nms, status);
     EFFDET_LAUNCHED();

@@ -127,6 +127,18 @@ def test_filter_detections_large_segments_and_cap():
     _check_fd(boxes, cls, score_threshold=0.5, max_detections=50)
 
 
+def test_filter_detections_max_detections_2048():
+    """The largest max_detections the NMS path accepts: the selected-box list (32 KiB) + the small-segment kernel's
+    static shared memory pass 48 KiB (the launch opts in)."""
+    rng = np.random.default_rng(2048)
+    B, N, C = 1, 2900, 2                  # ~2030 candidates per class: tiny boxes far apart, nearly all survive NMS
+    boxes = np.stack([_boxes(rng, N, 4000, 12)])
+    cls = _distinct_scores(rng, (B, N, C))
+    s = _check_fd(boxes, cls, score_threshold=0.3, max_detections=2048)
+    assert (s >= 0).sum() == 2048
+    _check_fd(boxes, cls, score_threshold=0.3, max_detections=1900)
+
+
 def test_filter_detections_variants():
     rng = np.random.default_rng(5)
     B, N, C = 2, 2500, 7
