@@ -20,9 +20,10 @@ import torch
 
 
 @pytest.fixture(scope="module")
-def cpu_plans():
-    from efficientdet_b200 import _lib, engine, train
-    from efficientdet_b200.model import efficientdet
+def stubbed():
+    """Library calls stubbed for the module: plans are built (values, launches, buffers, bound arguments) but nothing
+    is launched."""
+    from efficientdet_b200 import _lib, engine
     saved = (_lib.stream_ptr, _lib.call, engine.Plan.__init__)
 
     def structure_only(self, net, batch, reuse_buffers=True, keep_taps=False, u8_input=False):
@@ -39,21 +40,28 @@ def cpu_plans():
     _lib.call = lambda *a, **k: 0
     engine.Plan.__init__ = structure_only
     try:
-        plans = {}
-        m0 = efficientdet(0, num_classes=4, image_size=128, drop_connect_rate=0, just_training_model=True,
-                          device="cpu", dtype="bf16")
-        plans["infer_d0_b1"] = engine.Plan(m0.net, 1)
-        plans["infer_d0_b1_u8"] = engine.Plan(m0.net, 1, u8_input=True)
-        plans["train_d0_frozen"] = train.TrainPlan(m0.net, 2, train_backbone=False)
-        m1 = efficientdet(1, num_classes=4, image_size=128, weighted_bifpn=True, just_training_model=True,
-                          device="cpu", dtype="bf16")       # default drop_connect_rate: stochastic depth ops
-        plans["train_d1_full"] = train.TrainPlan(m1.net, 2, train_backbone=True)
-        m32 = efficientdet(0, num_classes=4, image_size=128, drop_connect_rate=0, just_training_model=True,
-                           device="cpu", dtype="fp32")
-        plans["train_d0_fp32_full"] = train.TrainPlan(m32.net, 2, train_backbone=True)
-        yield plans
+        yield True
     finally:
         _lib.stream_ptr, _lib.call, engine.Plan.__init__ = saved
+
+
+@pytest.fixture(scope="module")
+def cpu_plans(stubbed):
+    from efficientdet_b200 import engine, train
+    from efficientdet_b200.model import efficientdet
+    plans = {}
+    m0 = efficientdet(0, num_classes=4, image_size=128, drop_connect_rate=0, just_training_model=True,
+                      device="cpu", dtype="bf16")
+    plans["infer_d0_b1"] = engine.Plan(m0.net, 1)
+    plans["infer_d0_b1_u8"] = engine.Plan(m0.net, 1, u8_input=True)
+    plans["train_d0_frozen"] = train.TrainPlan(m0.net, 2, train_backbone=False)
+    m1 = efficientdet(1, num_classes=4, image_size=128, weighted_bifpn=True, just_training_model=True,
+                      device="cpu", dtype="bf16")       # default drop_connect_rate: stochastic depth ops
+    plans["train_d1_full"] = train.TrainPlan(m1.net, 2, train_backbone=True)
+    m32 = efficientdet(0, num_classes=4, image_size=128, drop_connect_rate=0, just_training_model=True,
+                       device="cpu", dtype="fp32")
+    plans["train_d0_fp32_full"] = train.TrainPlan(m32.net, 2, train_backbone=True)
+    return plans
 
 
 def _buffer(v):
@@ -236,3 +244,25 @@ def test_untracked_memory_shared_by_launches_is_ordered(cpu_plans, n_lanes):
                         "(if it is read-only for both, exempt it here)" % (
                             name, n_lanes, i, p.ops[i].kind, p.ops[i].name, sched[i][0],
                             j, p.ops[j].kind, p.ops[j].name, sched[j][0]))
+
+
+@pytest.mark.parametrize("phi", range(7))
+def test_every_model_size_lowers_and_schedules(stubbed, phi):
+    """D0..D6, weighted and plain BiFPN, bf16 and fp32, inference (float / uint8 input) and training (frozen / trained
+    backbone): the lowering runs to the end (every descriptor is built, every argument bound) and the 4-lane order
+    covers every hazard.  The GPU tests run a subset of these combinations; this is all of them."""
+    from efficientdet_b200 import engine, train
+    from efficientdet_b200.model import efficientdet
+    for weighted in (False, True):
+        for dtype in ("bf16", "fp32"):
+            m = efficientdet(phi, num_classes=3 + phi, image_size=128, weighted_bifpn=weighted,
+                             just_training_model=True, device="cpu", dtype=dtype)
+            for B in (1, 3):
+                p = engine.Plan(m.net, B, u8_input=(B == 3))
+                _check_segment("infer D%d" % phi, p, 0, len(p.ops), 4)
+            n_ops = []
+            for full in (False, True):
+                p = train.TrainPlan(m.net, 2, train_backbone=full, u8_input=full)
+                _check_segment("train D%d" % phi, p, 0, len(p.ops), 4)
+                n_ops.append(len(p.ops))
+            assert n_ops[1] > n_ops[0]          # the trained backbone adds its backward launches
