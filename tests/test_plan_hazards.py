@@ -251,8 +251,12 @@ def test_every_model_size_lowers_and_schedules(stubbed, phi):
     """D0..D6, weighted and plain BiFPN, bf16 and fp32, inference (float / uint8 input) and training (frozen / trained
     backbone): the lowering runs to the end (every descriptor is built, every argument bound) and the 4-lane order
     covers every hazard.  The GPU tests run a subset of these combinations; this is all of them."""
-    from efficientdet_b200 import engine, train
+    from efficientdet_b200 import engine, plan_export, train
     from efficientdet_b200.model import efficientdet
+
+    class _AnyRegion:
+        def locate(self, ptr):
+            return 0, ptr
     for weighted in (False, True):
         for dtype in ("bf16", "fp32"):
             m = efficientdet(phi, num_classes=3 + phi, image_size=128, weighted_bifpn=weighted,
@@ -265,4 +269,11 @@ def test_every_model_size_lowers_and_schedules(stubbed, phi):
                 p = train.TrainPlan(m.net, 2, train_backbone=full, u8_input=full)
                 _check_segment("train D%d" % phi, p, 0, len(p.ops), 4)
                 n_ops.append(len(p.ops))
+                # every launch of a training plan must serialise into a compiled plan (plan_export / csrc/replay.cu):
+                # a plain C-ABI call whose recorded arguments match the signature table the replay thunks are
+                # generated from
+                for op in p.ops:
+                    name, args = op.fn.call
+                    blob = plan_export._encode_call(name, args, _AnyRegion())
+                    assert blob[2:2 + len(name)] == name.encode()
             assert n_ops[1] > n_ops[0]          # the trained backbone adds its backward launches
