@@ -1344,6 +1344,8 @@ int effdet_conv2d_tc(const effdet_conv_desc *d, void *stream) {
     p.stages = stages;
     const size_t smem = (size_t)stages * ring_bytes + (p.b_resident ? (size_t)num_k * b_tile_bytes : 0) + 4096 +
                         (2 * stages + 5) * 8 + 16 + 1024 + 1024 + stage_out_bytes;
+    if (smem > 227 * 1024)       // never for the shapes tc_block_n / halo_fits admit; a launch would fail with "invalid argument"
+        return fail(EFFDET_E_INVALID, "effdet_conv2d: %s%lld bytes of shared memory exceed a CTA's 227 KiB", "", (long long)smem);
     p.any_tma_store = 0;
     int tiles = 0;
     for (int i = 0; i < d->n_groups; ++i) {

@@ -101,6 +101,33 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
+// Stand-in used ONLY when no CUDA driver can be loaded and EFFDET_DRY_RUN is set (the CPU test that walks the
+// launch list of every model size through the entry points' host side, tests/test_plan_hazards.py): it checks the
+// documented argument rules of cuTensorMapEncodeTiled for the tiled, non-interleaved maps this library builds and
+// writes nothing.  The launch that follows fails (no driver), so nothing ever consumes such a map.
+static inline CUresult dry_run_encode_tiled(CUtensorMap *map, CUtensorMapDataType dt, cuuint32_t rank, void *addr,
+                                            const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box,
+                                            const cuuint32_t *estr, CUtensorMapInterleave il, CUtensorMapSwizzle sw,
+                                            CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+    const size_t es = dt == CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 ? 2 : dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT32 ? 4 : 0;
+    if (!map || !addr || es == 0 || rank < 1 || rank > 5 || il != CU_TENSOR_MAP_INTERLEAVE_NONE)
+        return CUDA_ERROR_INVALID_VALUE;
+    if (reinterpret_cast<uintptr_t>(addr) & 15) return CUDA_ERROR_INVALID_VALUE;
+    for (cuuint32_t i = 0; i < rank; ++i) {
+        if (dims[i] == 0 || dims[i] > (1ull << 32)) return CUDA_ERROR_INVALID_VALUE;
+        if (box[i] == 0 || box[i] > 256) return CUDA_ERROR_INVALID_VALUE;
+        if (estr[i] == 0 || estr[i] > 8) return CUDA_ERROR_INVALID_VALUE;
+        if (i + 1 < rank && (strides[i] % 16 != 0 || strides[i] == 0 || strides[i] >= (1ull << 40)))
+            return CUDA_ERROR_INVALID_VALUE;
+    }
+    const size_t inner = (size_t)box[0] * es;
+    if (inner % 16 != 0) return CUDA_ERROR_INVALID_VALUE;
+    const size_t span = sw == CU_TENSOR_MAP_SWIZZLE_128B ? 128 : sw == CU_TENSOR_MAP_SWIZZLE_64B ? 64 :
+                        sw == CU_TENSOR_MAP_SWIZZLE_32B ? 32 : (size_t)-1;
+    if (inner > span) return CUDA_ERROR_INVALID_VALUE;
+    return CUDA_SUCCESS;
+}
+
 static inline EncodeTiledFn get_encode() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -109,6 +136,8 @@ static inline EncodeTiledFn get_encode() {
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
             fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else if (getenv("EFFDET_DRY_RUN"))
+            fn = dry_run_encode_tiled;
     }
     return fn;
 }

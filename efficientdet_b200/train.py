@@ -399,6 +399,14 @@ class TrainPlan(engine.Plan):
         while (C * fold) % vec:
             fold *= 2
         prow, pC = rows // fold, C * fold
+        if pC // vec > 1024:
+            # effdet_colsum gives every thread of a block one column vector (csrc/train.cu launch_colreduce): reject
+            # here, when the plan is built, instead of at the first step.  Reached by the class head of fp32 training
+            # plans (C = 9 * num_classes; bf16 plans take that gradient from the tensor-core weight-gradient launch):
+            # num_classes <= 455 if a multiple of 4, <= 227 if even, <= 113 otherwise
+            raise ValueError("bias gradient of %s: %d columns (x%d rows folded) exceed 1024 %d-wide column vectors "
+                             "per block; for the class head use num_classes <= 113, an even count <= 227 or a "
+                             "multiple of 4 <= 455" % (key, C, fold, vec))
         tail = rows - prow * fold            # < fold rows that do not fill a vector-aligned fold
         nblk = lib.effdet_colreduce_blocks(prow, pC, dtype)
         part = self._scratch(2 * pC * nblk, key + "_bg_partial")
