@@ -401,8 +401,8 @@ class TrainPlan(engine.Plan):
         prow, pC = rows // fold, C * fold
         if pC // vec > 1024:
             # effdet_colsum gives every thread of a block one column vector (csrc/train.cu launch_colreduce): reject
-            # here, when the plan is built, instead of at the first step.  Reached by the class head of fp32 training
-            # plans (C = 9 * num_classes; bf16 plans take that gradient from the tensor-core weight-gradient launch):
+            # here, when the plan is built, instead of at the first step.  Reached by the class head (C = 9 *
+            # num_classes) unless its bias gradient comes out of the tensor-core weight-gradient launch (bf16, W <= 64):
             # num_classes <= 455 if a multiple of 4, <= 227 if even, <= 113 otherwise
             raise ValueError("bias gradient of %s: %d columns (x%d rows folded) exceed 1024 %d-wide column vectors "
                              "per block; for the class head use num_classes <= 113, an even count <= 227 or a "

@@ -104,16 +104,19 @@ def test_class_counts(dry, phi):
 
 
 def test_class_count_limit_is_reported_when_the_plan_is_built(dry):
-    """fp32 training reduces the class-head bias gradient with one column vector per thread (<= 1024 per block; odd
+    """Training reduces the class-head bias gradient with one column vector per thread (<= 1024 per block; odd
     9 * classes rows are folded 2 or 4 times to reach the vector width): larger heads are rejected by the lowering,
-    not at the first step.  bf16 training takes that gradient from the tensor-core weight-gradient launch and
-    inference has no such reduction: no limit there."""
+    not at the first step.  bf16 training on a BiFPN of width <= 64 takes that gradient from the tensor-core
+    weight-gradient launch and inference has no such reduction: no limit there."""
     for classes in (115, 230, 456, 601):
         with pytest.raises(ValueError, match="num_classes"):
             for _ in _plans(0, 128, 2, classes, "fp32", False, "f"):
                 pass
     for name, p in _plans(0, 128, 2, 601, "bf16", False, "if"):
         _issue_all(dry, p, "601 classes " + name)
+    with pytest.raises(ValueError, match="num_classes"):
+        for _ in _plans(1, 128, 2, 601, "bf16", False, "f"):          # D1: W = 88
+            pass
 
 
 @pytest.mark.parametrize("phi", [0, 2, 4])
