@@ -12,10 +12,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBDIR = os.path.join(ROOT, "efficientdet_b200")
 
 
-def _compile(tmp_path, *extra):
-    exe = str(tmp_path / "detect_host")
+def _compile(tmp_path, *extra, name="detect_host"):
+    exe = str(tmp_path / name)
     cmd = ["gcc", "-std=c99", "-O1", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "examples", "detect_host.c"), *extra, "-o", exe]
+           os.path.join(ROOT, "examples", name + ".c"), *extra, "-o", exe]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     return exe
@@ -42,6 +42,25 @@ def test_c_host_links_and_fails_loudly_without_a_gpu(tmp_path):
     r = subprocess.run([exe, "0", "128", "1", "4"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert r.returncode == 3, (r.stdout, r.stderr)
     assert "effdet_plan_create failed" in r.stderr and len(r.stderr.strip().splitlines()) == 1
+
+
+def test_c_training_host_links_and_reports_errors(tmp_path):
+    """examples/train_host.c (compiled plans: effdet_replay_load / region / step from C, CUDA runtime for the copies)
+    compiles as pedantic C99, links, and reports a missing or malformed plan file through effdet_last_error()."""
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("CUDA toolkit headers not found")
+    exe = _compile(tmp_path, "-isystem", os.path.join(cuda, "include"), "-L", LIBDIR, "-leffdet_b200",
+                   "-Wl,-rpath," + LIBDIR, "-L", os.path.join(cuda, "lib64"), "-lcudart",
+                   "-Wl,-rpath," + os.path.join(cuda, "lib64"), name="train_host")
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr
+    r = subprocess.run([exe, str(tmp_path / "missing.efd")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 3 and "cannot open" in r.stderr
+    bad = tmp_path / "bad.efd"
+    bad.write_bytes(b"NOTAPLAN" + bytes(64))
+    r = subprocess.run([exe, str(bad)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 3 and "effdet_replay_load failed (-1)" in r.stderr
 
 
 @pytest.mark.gpu
