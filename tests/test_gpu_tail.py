@@ -214,3 +214,22 @@ def test_anchor_targets_kat_512(golden):
     assert hashlib.sha256(lab.tobytes()).hexdigest() == str(golden["kat_lab_sha"])
     with pytest.raises(AssertionError):
         A.anchor_targets_bbox(a, [], [], 20)
+
+
+# ---------------------------------------------------------------- fixtures from the EXECUTED reference
+@pytest.mark.parametrize("case", ["pad", "topk", "class_cap", "max_class", "no_nms", "no_nms_max_class", "tight_iou",
+                                  "nothing"])
+def test_filter_detections_matches_executed_reference(case):
+    """tests/golden/filter_detections.npz holds the outputs of the reference's own FilterDetections.py, executed
+    unmodified over a numpy stand-in for its TensorFlow ops (tests/golden/make_golden_filter.py): the CUDA tail must
+    reproduce them bit for bit (boxes, scores, labels, padding)."""
+    import ast
+    import os
+    from efficientdet_b200.FilterDetections import FilterDetections
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "filter_detections.npz"))
+    kw = dict(ast.literal_eval(str(z[case + "/kw"])))
+    gb, gs, gl = FilterDetections(**kw)([z[case + "/boxes_in"], z[case + "/cls_in"]])
+    assert gl.dtype == np.int32
+    assert np.array_equal(gl, z[case + "/labels"])
+    assert np.array_equal(gs, z[case + "/scores"])
+    assert np.array_equal(gb, z[case + "/boxes"])

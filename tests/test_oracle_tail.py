@@ -40,3 +40,49 @@ def test_filter_detections_pad_and_order():
     b2, s2, l2 = tail.filter_detections(boxes, cls, score_threshold=0.5, max_detections=200,
                                         iou_threshold=0)
     assert int((s2 >= 0).sum()) == int((cls > 0.5).sum())
+
+
+# ---------------------------------------------------------------- fixtures from the EXECUTED reference
+# tests/golden/filter_detections.npz: outputs of the reference's own FilterDetections.py (layer, filter_detections,
+# filter_by_score_and_nms) run unmodified over a numpy stand-in for its TensorFlow ops
+# (tests/golden/make_golden_filter.py): pins the oracle's thresholding, per-class order, top-k, padding, casts,
+# nms=False and class_specific_filter=False handling on the reference's control flow, bit for bit.
+import ast
+import os
+
+import pytest
+
+FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "filter_detections.npz")
+CASES = ("pad", "topk", "class_cap", "max_class", "no_nms", "no_nms_max_class", "tight_iou", "nothing")
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_filter_detections_layer_matches_executed_reference(case):
+    z = np.load(FIX)
+    kw = dict(ast.literal_eval(str(z[case + "/kw"])))
+    b, s, l = tail.filter_detections_batch(z[case + "/boxes_in"], z[case + "/cls_in"], **kw)
+    assert l.dtype == np.int32 and s.dtype == np.float32 and b.dtype == np.float32
+    np.testing.assert_array_equal(l, z[case + "/labels"])
+    np.testing.assert_array_equal(s, z[case + "/scores"])
+    np.testing.assert_array_equal(b, z[case + "/boxes"])
+
+
+def test_fixture_cases_exercise_what_they_claim():
+    z = np.load(FIX)
+    assert (z["pad/labels"] == -1).any() and (z["pad/labels"] >= 0).any()             # padding present
+    assert (z["topk/labels"] >= 0).all()                                               # top-k cut
+    assert (z["nothing/labels"] == -1).all() and (z["nothing/boxes"] == -1).all()
+    lab = z["class_cap/labels"][0]
+    assert (lab >= 0).all() and len(set(lab.tolist())) == 2
+    assert np.all(np.diff(z["topk/scores"], axis=1) <= 0)                              # descending scores
+
+
+def test_filter_detections_function_and_index_form_match_executed_reference():
+    z = np.load(FIX)
+    b, s, l = tail.filter_detections(z["fn/boxes_in"], z["fn/cls_in"], score_threshold=0.6, max_detections=35,
+                                     iou_threshold=0.4)
+    np.testing.assert_array_equal(l, z["fn/labels"])
+    np.testing.assert_array_equal(s, z["fn/scores"])
+    np.testing.assert_array_equal(b, z["fn/boxes"])
+    idx = tail.filter_by_score_and_nms(z["fn/cls_in"][:, 1], z["fsn/labels_in"], 0.5, z["fn/boxes_in"], 20, 0.45)
+    np.testing.assert_array_equal(idx, z["fsn/indices"])
