@@ -73,5 +73,25 @@ out["fn/boxes"], out["fn/scores"], out["fn/labels"] = (np.asarray(r[0], np.float
 lab = rng.integers(0, 4, 200).astype(np.int64)
 idx = ref.filter_by_score_and_nms(stub.t(c1[:, 1]), stub.t(lab), 0.5, stub.t(b1), 20, 0.45)
 out["fsn/labels_in"], out["fsn/indices"] = lab, np.asarray(idx, np.int64)
+# decode + clip: the reference's own apply_bbox_deltas (RegressBoxes.py:126-164) and ClipBoxes.call (ClipBoxes.py:9-24)
+import contextlib  # noqa: E402
+import io  # noqa: E402
+
+import ClipBoxes as ref_clip  # noqa: E402
+import RegressBoxes as ref_reg  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle.anchors import anchors_for_shape  # noqa: E402  (inputs only: any boxes would do)
+
+anchors = anchors_for_shape((256, 384)).astype(np.float32)[None]
+deltas = rng.normal(0, 0.6, (3, anchors.shape[1], 4)).astype(np.float32)
+dec = ref_reg.apply_bbox_deltas(stub.t(np.broadcast_to(anchors, deltas.shape).copy()), stub.t(deltas))
+mean, std = np.array([0.1, -0.1, 0.05, 0.0], np.float32), np.array([0.1, 0.2, 0.3, 0.25], np.float32)
+dec2 = ref_reg.apply_bbox_deltas(stub.t(np.broadcast_to(anchors, deltas.shape).copy()), stub.t(deltas), mean, std)
+with contextlib.redirect_stdout(io.StringIO()):          # ClipBoxes.call prints its inputs (ClipBoxes.py:12-14)
+    clipped = ref_clip.ClipBoxes().call([stub.t(np.zeros((3, 256, 384, 3), np.float32)), dec])
+out.update({"dc/anchors": anchors, "dc/deltas": deltas, "dc/decoded": np.asarray(dec, np.float32),
+            "dc/mean": mean, "dc/std": std, "dc/decoded_mean_std": np.asarray(dec2, np.float32),
+            "dc/clipped": np.asarray(clipped, np.float32), "dc/image_shape": np.array([3, 256, 384, 3])})
+assert out["dc/decoded"].dtype == np.float32 and (out["dc/clipped"] != out["dc/decoded"]).any()
 np.savez_compressed(os.path.join(HERE, "filter_detections.npz"), **out)
 print("wrote", len(out), "arrays")

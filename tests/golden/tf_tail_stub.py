@@ -1,5 +1,6 @@
-"""numpy stand-in for the slice of `tensorflow` / `tensorflow.keras` that the reference's FilterDetections.py uses, so
-that the reference file can be imported and EXECUTED unmodified in the build container (TensorFlow is not
+"""numpy stand-in for the slice of `tensorflow` / `tensorflow.keras` that the reference's FilterDetections.py uses (and
+RegressBoxes.py / ClipBoxes.py: keras.backend.stack, tf.clip_by_value), so that the reference files can be imported
+and EXECUTED unmodified in the build container (TensorFlow is not
 installable offline; requirements.txt:21).  Test infrastructure only: tests/golden/make_golden_filter.py is its one
 user.  Written independently of oracle/tail.py -- the fixtures it produces are what pins that oracle.
 
@@ -121,7 +122,8 @@ backend = _module(
     max=lambda x, axis=None: t(np.asarray(x).max(axis=axis)),
     argmax=lambda x, axis=-1: t(np.asarray(x).argmax(axis=axis).astype(np.int64)),
     minimum=lambda a, b: np.minimum(a, b), maximum=lambda a, b: np.maximum(a, b),
-    cast=lambda x, dtype: t(np.asarray(x).astype(dtype)))
+    cast=lambda x, dtype: t(np.asarray(x).astype(dtype)),
+    stack=lambda xs, axis=0: t(np.stack([np.asarray(x) for x in xs], axis=axis)))
 layers = _module("tensorflow.keras.layers", Layer=Layer)
 keras = _module("tensorflow.keras", backend=backend, layers=layers)
 image = _module("tensorflow.image", non_max_suppression=_non_max_suppression)
@@ -131,7 +133,8 @@ compat = _module("tensorflow.compat", v1=compat_v1)
 tf = _module("tensorflow", keras=keras, image=image, nn=nn, compat=compat, gather_nd=_gather_nd, gather=_gather,
              stack=lambda xs, axis=0: t(np.stack([np.asarray(x) for x in xs], axis=axis)),
              ones=lambda shape, dtype="float32": t(np.ones(tuple(int(s) for s in shape), dtype=dtype)),
-             pad=_pad, map_fn=_map_fn)
+             pad=_pad, map_fn=_map_fn,
+             clip_by_value=lambda x, lo, hi, name=None: t(np.minimum(np.maximum(np.asarray(x), F(lo)), F(hi))))
 
 
 def install():

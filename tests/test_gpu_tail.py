@@ -233,3 +233,15 @@ def test_filter_detections_matches_executed_reference(case):
     assert np.array_equal(gl, z[case + "/labels"])
     assert np.array_equal(gs, z[case + "/scores"])
     assert np.array_equal(gb, z[case + "/boxes"])
+
+
+def test_decode_and_clip_match_executed_reference():
+    """The reference's own apply_bbox_deltas (RegressBoxes.py:126-164) and ClipBoxes.call (ClipBoxes.py:9-24),
+    executed by tests/golden/make_golden_filter.py on 3 x 18 414 anchors: the CUDA decode / clip reproduce the float32
+    results bit for bit."""
+    import os
+    from efficientdet_b200 import RegressBoxes as RB, ClipBoxes as CB
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "filter_detections.npz"))
+    got = RB.apply_bbox_deltas(z["dc/anchors"], z["dc/deltas"])
+    assert np.array_equal(got, z["dc/decoded"])
+    assert np.array_equal(CB.clip_boxes(tuple(int(v) for v in z["dc/image_shape"]), got), z["dc/clipped"])
