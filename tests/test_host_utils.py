@@ -58,3 +58,18 @@ def test_unletterbox_boxes_matches_reference_arithmetic():
     s = np.array([0.9, 0.2, 0.6], np.float32)
     b, sc, lb = select_detections(got[0, :3], s, np.array([1, 2, 3]), 0.5)
     assert sc.tolist() == pytest.approx([0.9, 0.6]) and lb.tolist() == [1, 3] and b.shape == (2, 4)
+
+
+def test_lr_schedule_matches_executed_reference():
+    """tests/golden/lr_schedule.json: the reference's own get_cosine_decay_with_linear_warmup executed unmodified
+    (tests/golden/make_golden_lr.py; only tf.keras.experimental.CosineDecay is restated): every epoch of five
+    configurations, incl. the epochs around the warm-up / cosine switch and past the end."""
+    import json
+    import os
+    from efficientdet_b200.utils.lr_schedule import get_cosine_decay_with_linear_warmup
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lr_schedule.json")))
+    assert len(cases) == 5
+    for c in cases:
+        f = get_cosine_decay_with_linear_warmup(**c["kwargs"]).schedule
+        got = [f(e, None) for e in range(len(c["lr"]))]
+        assert got == pytest.approx(c["lr"], rel=1e-12, abs=1e-15), c["kwargs"]
