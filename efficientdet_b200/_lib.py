@@ -228,6 +228,8 @@ def load():
     lib.effdet_plan_num_weights.argtypes = [c_void_p]
     lib.effdet_plan_num_launches.restype = c_int
     lib.effdet_plan_num_launches.argtypes = [c_void_p]
+    lib.effdet_plan_dry_run.restype = c_int
+    lib.effdet_plan_dry_run.argtypes = [c_void_p, c_void_p]
     lib.effdet_replay_num_launches.restype = c_int
     lib.effdet_replay_num_launches.argtypes = [c_void_p]
     for name, args in _SIGNATURES.items():

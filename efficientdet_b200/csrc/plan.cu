@@ -12,6 +12,8 @@
 // tests/test_gpu_plan_cabi.py checks that both produce bit-identical outputs.
 // Host code only: no kernels live in this file.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <functional>
 #include <map>
@@ -88,6 +90,8 @@ struct effdet_plan {
     std::vector<Val> vals;
     std::vector<Op> ops;
     std::vector<void *> owned;             // every cudaMalloc of the plan
+    std::vector<void *> owned_host;        // dry run only (no CUDA driver + EFFDET_DRY_RUN): host stand-ins
+    bool host_mem = false;
     std::vector<effdet_conv_desc *> descs;
     int v_images = -1, v_reg = -1, v_cls = -1;
     size_t N = 0;
@@ -113,7 +117,24 @@ namespace {
 
 int dev_alloc(effdet_plan *p, void **out, size_t bytes) {
     void *q = nullptr;
-    EFFDET_CUDA(cudaMalloc(&q, bytes < 16 ? 16 : bytes));
+    const cudaError_t alloc_error = cudaMalloc(&q, bytes < 16 ? 16 : bytes);
+    if (alloc_error != cudaSuccess && getenv("EFFDET_DRY_RUN") != nullptr && (p->host_mem || p->owned.empty())) {
+        // Dry run (tests/test_dry_run_launches.py, machines without a CUDA driver): the lowering is built over host
+        // memory so that effdet_plan_dry_run can walk the launch list through the entry points' host side.  Nothing
+        // can execute: every launch fails at its first CUDA call.
+        (void)cudaGetLastError();
+        if (posix_memalign(&q, 256, (bytes + 255) / 256 * 256 + 256) != 0)
+            return fail(EFFDET_E_CUDA, "effdet_plan: dry-run host allocation of %s%lld bytes failed", "", (long long)bytes);
+        p->owned_host.push_back(q);
+        p->host_mem = true;
+        *out = q;
+        return EFFDET_OK;
+    }
+    if (alloc_error != cudaSuccess) {
+        snprintf(::effdet::g_err, sizeof(::effdet::g_err), "effdet_plan: cudaMalloc(%lld bytes) -> %s", (long long)bytes,
+                 cudaGetErrorString(alloc_error));
+        return EFFDET_E_CUDA;
+    }
     p->owned.push_back(q);
     *out = q;
     return EFFDET_OK;
@@ -588,7 +609,8 @@ int normalization_lut(effdet_plan *p) {
         }
     int rc = dev_alloc(p, (void **)&p->lut, sizeof(h));
     if (rc) return rc;
-    EFFDET_CUDA(cudaMemcpy(p->lut, h, sizeof(h), cudaMemcpyHostToDevice));
+    if (p->host_mem) memcpy(p->lut, h, sizeof(h));           // dry run
+    else EFFDET_CUDA(cudaMemcpy(p->lut, h, sizeof(h), cudaMemcpyHostToDevice));
     return EFFDET_OK;
 }
 
@@ -646,7 +668,8 @@ extern "C" int effdet_plan_create(int phi, int image_size, int batch, int num_cl
     build_manifest(p);
     p->bound.assign(p->winfo.size(), 0);
     int rc = dev_alloc(p, (void **)&p->flat, p->flat_count * 4);
-    if (!rc) rc = cudaMemset(p->flat, 0, p->flat_count * 4) == cudaSuccess ? EFFDET_OK : EFFDET_E_CUDA;
+    if (!rc && p->host_mem) memset(p->flat, 0, p->flat_count * 4);          // dry run
+    else if (!rc) rc = cudaMemset(p->flat, 0, p->flat_count * 4) == cudaSuccess ? EFFDET_OK : EFFDET_E_CUDA;
     for (auto &f : p->folded) {
         if (!rc) rc = dev_alloc(p, (void **)&f.scale, (size_t)f.C * 4);
         if (!rc) rc = dev_alloc(p, (void **)&f.shift, (size_t)f.C * 4);
@@ -664,10 +687,38 @@ extern "C" int effdet_plan_destroy(effdet_plan_t *p) {
     if (p->graph) cudaGraphExecDestroy(p->graph);
     if (p->capture_stream) cudaStreamDestroy(p->capture_stream);
     for (void *q : p->owned) cudaFree(q);
+    for (void *q : p->owned_host) free(q);
     for (auto *d : p->descs) delete d;
     if (p->host_in) cudaFreeHost(p->host_in);
     if (p->host_out) cudaFreeHost(p->host_out);
     delete p;
+    return EFFDET_OK;
+}
+
+extern "C" int effdet_plan_dry_run(effdet_plan_t *p, int *launches) {
+    EFFDET_REQUIRE(p, "null plan");
+    EFFDET_REQUIRE(p->host_mem, "only for a plan built without a CUDA driver under EFFDET_DRY_RUN");
+    int n = 0;
+    // a launch passes when it fails at its first CUDA call and nowhere earlier
+    auto passed = [&](int rc) {
+        ++n;
+        return rc == EFFDET_OK || (rc == EFFDET_E_CUDA && strstr(effdet_last_error(), "driver version is insufficient"));
+    };
+    for (auto &f : p->folded) {
+        const int rc = effdet_bn_fold(p->w(f.bn + "/gamma"), p->w(f.bn + "/beta"), p->w(f.bn + "/moving_mean"),
+                                      p->w(f.bn + "/moving_variance"), f.eps, f.scale, f.shift, f.C, nullptr);
+        if (!passed(rc)) return rc;
+    }
+    for (auto &q : p->panels) {
+        const int rc = q.split ? effdet_conv_weight_panel_split(p->w(q.key), q.ptr, q.taps, q.cin, q.cout, nullptr, 0, nullptr)
+                               : effdet_conv_weight_panel(p->w(q.key), q.ptr, q.taps, q.cin, q.cout, 0, nullptr, 0, nullptr);
+        if (!passed(rc)) return rc;
+    }
+    for (Op &op : p->ops) {
+        const int rc = op.run(nullptr);
+        if (!passed(rc)) return rc;
+    }
+    if (launches) *launches = n;
     return EFFDET_OK;
 }
 

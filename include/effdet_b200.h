@@ -505,6 +505,12 @@ int effdet_plan_destroy(effdet_plan_t *plan);
 int effdet_plan_num_weights(const effdet_plan_t *plan);
 size_t effdet_plan_num_anchors(const effdet_plan_t *plan);
 int effdet_plan_num_launches(const effdet_plan_t *plan);
+/* Test facility for machines WITHOUT a CUDA driver: with the environment variable EFFDET_DRY_RUN set,
+ * effdet_plan_create builds the lowering over host memory and effdet_plan_dry_run issues every launch of the plan
+ * (BatchNorm folds, weight panels, the forward launch list) through its entry point; each must pass that entry
+ * point's validation and launch configuration and fail only at its first CUDA call.  Returns the first other error.
+ * With a driver present plans are never built this way and the call returns EFFDET_E_INVALID. */
+int effdet_plan_dry_run(effdet_plan_t *plan, int *launches_checked);
 int effdet_plan_weight_info(const effdet_plan_t *plan, int index, const char **name, int *ndim, int dims[4]);
 int effdet_plan_bind_weights(effdet_plan_t *plan, const char *const *names, const void *const *device_ptrs, int n,
                              void *stream);

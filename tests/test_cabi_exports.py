@@ -35,7 +35,7 @@ def test_python_binding_covers_header():
                                      "effdet_conv_tc_block_n", "effdet_conv_weight_panel_elems", "effdet_conv_weight_panel_split_elems",
                                      "effdet_se_backward_blocks", "effdet_se_bn_backward_blocks", "effdet_dw_backward_blocks",
                                      "effdet_stem_wgrad_blocks", "effdet_plan_num_weights",
-                                     "effdet_plan_num_anchors", "effdet_plan_num_launches",
+                                     "effdet_plan_num_anchors", "effdet_plan_num_launches", "effdet_plan_dry_run",
                                      "effdet_replay_num_launches"}
     missing = [n for n in _declared() if n not in bound]
     assert not missing, missing

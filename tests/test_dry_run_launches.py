@@ -131,3 +131,63 @@ def test_other_image_sizes(dry):
     for size in (128, 384, 1152):
         for name, p in _plans(1, size, 2, 20, "bf16", True, "it"):
             _issue_all(dry, p, "D1 %d px %s" % (size, name))
+
+
+# ---------------------------------------------------------------- the C++ lowering (csrc/plan.cu)
+def _c_plan(lib, phi, size, batch, classes, weighted, dtype, u8):
+    import ctypes
+    plan = ctypes.c_void_p()
+    rc = lib.effdet_plan_create(phi, size, batch, classes, int(weighted), 1 if dtype == "bf16" else 0,
+                                1 if u8 else 0, ctypes.byref(plan))
+    assert rc == 0, lib.effdet_last_error()
+    return plan
+
+
+@pytest.mark.parametrize("phi", range(7))
+def test_cpp_plan_matches_python_lowering_and_passes_dry_run(dry, phi):
+    """effdet_plan_create (the plan-level C ABI, lowered in C++) against the Python lowering for every model size:
+    the same weight manifest (Keras names, shapes, order -- what load_weights(by_name=True) matches), the same number
+    of launches per forward, and every one of its launches passes its entry point's host side (effdet_plan_dry_run).
+    The GPU test (tests/test_gpu_plan_cabi.py) compares outputs bit for bit on four configurations; this covers the
+    structure of all of them."""
+    import ctypes
+    from efficientdet_b200 import engine
+    from efficientdet_b200.model import efficientdet
+    lib = dry.load()
+    for weighted, classes, size in ((False, 90, IMAGE_SIZES[phi]), (True, 6, 256)):
+        for dtype in ("bf16", "fp32"):
+            m = efficientdet(phi, num_classes=classes, image_size=size, weighted_bifpn=weighted,
+                             just_training_model=True, device="cpu", dtype=dtype)
+            mine = m.get_weights_dict()
+            for u8 in (False, True):
+                plan = _c_plan(lib, phi, size, 1, classes, weighted, dtype, u8)
+                try:
+                    manifest = []
+                    for i in range(lib.effdet_plan_num_weights(plan)):
+                        name, nd, dims = ctypes.c_char_p(), ctypes.c_int(), (ctypes.c_int * 4)()
+                        assert lib.effdet_plan_weight_info(plan, i, ctypes.byref(name), ctypes.byref(nd), dims) == 0
+                        manifest.append((name.value.decode(), tuple(dims[:nd.value])))
+                    want = [(k, tuple(v.shape)) for k, v in mine.items() if not k.startswith("boxes/")]
+                    assert manifest == want
+                    py = engine.Plan(m.net, 1, u8_input=u8)
+                    assert lib.effdet_plan_num_launches(plan) == len(py.ops)
+                    assert lib.effdet_plan_num_anchors(plan) == py.N
+                    n = ctypes.c_int()
+                    rc = lib.effdet_plan_dry_run(plan, ctypes.byref(n))
+                    assert rc == 0, "D%d %s: %s" % (phi, dtype, lib.effdet_last_error().decode())
+                    assert n.value > lib.effdet_plan_num_launches(plan)        # + BatchNorm folds and weight panels
+                finally:
+                    lib.effdet_plan_destroy(plan)
+
+
+def test_cpp_plan_dry_run_class_counts_and_batches(dry):
+    import ctypes
+    lib = dry.load()
+    for phi, size in ((0, 256), (1, 128), (4, 128)):
+        for classes in (1, 2, 3, 5, 6, 7, 9, 20, 91, 200, 601):
+            for batch in (1, 3, 64):
+                plan = _c_plan(lib, phi, size, batch, classes, True, "bf16", True)
+                rc = lib.effdet_plan_dry_run(plan, None)
+                msg = lib.effdet_last_error().decode()
+                lib.effdet_plan_destroy(plan)
+                assert rc == 0, "D%d %d classes batch %d: %s" % (phi, classes, batch, msg)
