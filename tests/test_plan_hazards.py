@@ -206,8 +206,6 @@ def _addresses(a, out):
 @pytest.mark.parametrize("n_lanes", [2, 4, 6])
 def test_untracked_memory_shared_by_launches_is_ordered(cpu_plans, n_lanes):
     for name, p in cpu_plans.items():
-        if not name.startswith("train"):
-            continue
         size = {}
         for v in p.vals:
             size[v.t.data_ptr()] = max(size.get(v.t.data_ptr(), 0), v.t.numel())
@@ -234,7 +232,7 @@ def test_untracked_memory_shared_by_launches_is_ordered(cpu_plans, n_lanes):
                     touched.setdefault(x, []).append(i)
         assert n_bound > 2 * len(p.ops)
         shared = [ops for ops in touched.values() if len(ops) > 1]
-        assert shared, name
+        assert shared or not name.startswith("train"), name
         for ops in shared:
             for a, i in enumerate(ops):
                 for j in ops[a + 1:]:
