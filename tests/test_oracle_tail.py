@@ -97,3 +97,48 @@ def test_decode_and_clip_match_executed_reference():
     np.testing.assert_array_equal(tail.apply_bbox_deltas(np.broadcast_to(a, d.shape), d, z["dc/mean"], z["dc/std"]),
                                   z["dc/decoded_mean_std"])
     np.testing.assert_array_equal(tail.clip_boxes(tuple(z["dc/image_shape"]), z["dc/decoded"]), z["dc/clipped"])
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/FilterDetections.py"),
+                    reason="build container only: executes the reference's FilterDetections.py from where it lies")
+def test_oracle_tail_against_the_reference_executed_live_on_random_cases():
+    """Beyond the committed fixtures: 24 random configurations (classes, sizes, thresholds, nms / class-specific
+    switches, max_detections below and above the candidate count) through the reference's own FilterDetections.py
+    (numpy stand-in for its TensorFlow ops, tests/golden/tf_tail_stub.py) and through the oracle: identical."""
+    import importlib.util
+    import sys
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "tensorflow" or k.startswith("tensorflow.")}
+    sys.path.insert(0, golden)
+    try:
+        import tf_tail_stub as stub
+        stub.install()
+        spec = importlib.util.spec_from_file_location("ref_filter_detections", "/root/reference/FilterDetections.py")
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        rng = np.random.default_rng(20261019)
+        seen_detections = seen_padding = 0
+        for case in range(24):
+            B, N, C = int(rng.integers(1, 4)), int(rng.integers(1, 500)), int(rng.integers(1, 8))
+            span, wmax = float(rng.uniform(50, 600)), float(rng.uniform(5, 200))
+            xy = rng.uniform(0, span, (B, N, 2)).astype(np.float32)
+            boxes = np.concatenate([xy, xy + rng.uniform(1, wmax, (B, N, 2)).astype(np.float32)], -1)
+            v = np.linspace(0, 1, B * N * C + 2, dtype=np.float64)[1:-1].astype(np.float32)
+            cls = rng.permutation(v).reshape(B, N, C)
+            kw = dict(nms=bool(rng.integers(0, 2)), class_specific_filter=bool(rng.integers(0, 2)),
+                      nms_threshold=float(rng.choice([0.05, 0.3, 0.5, 0.8])),
+                      score_threshold=float(rng.choice([0.0, 0.3, 0.7, 0.95])),
+                      max_detections=int(rng.choice([1, 7, 50, 300])))
+            want = ref.FilterDetections(**kw).call([stub.t(boxes), stub.t(cls)])
+            got = tail.filter_detections_batch(boxes, cls, **kw)
+            for g, w, nm in zip(got, want, ("boxes", "scores", "labels")):
+                np.testing.assert_array_equal(g, np.asarray(w), err_msg="case %d %s %r" % (case, nm, kw))
+            seen_detections += int((got[2] >= 0).sum())
+            seen_padding += int((got[2] < 0).sum())
+        assert seen_detections > 500 and seen_padding > 500
+    finally:
+        sys.path.remove(golden)
+        for k in [k for k in sys.modules if k == "tensorflow" or k.startswith("tensorflow.")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
+        sys.modules.pop("tf_tail_stub", None)
