@@ -40,7 +40,7 @@ CASES = [  # (tag, phi, num_classes, weighted, image side, seed)
 ]
 
 
-def run_case(tag, phi, C, weighted, S, seed):
+def run_case(tag, phi, C, weighted, S, seed, out_dir=HERE):
     ks.reset()
     ks.WEIGHTS = lambda key, shape: golden_weight(key, shape, seed)
     rec = {}
@@ -94,7 +94,7 @@ def run_case(tag, phi, C, weighted, S, seed):
     init = ks.INITIALIZERS["class_head/pyramid_classification/bias"]
     out["prior_bias"] = np.float64(float(init((1,))[0]))
     assert np.isfinite(out["regression"]).all() and np.isfinite(out["classification"]).all()
-    np.savez_compressed(os.path.join(HERE, "graph_%s.npz" % tag), **out)
+    np.savez_compressed(os.path.join(out_dir, "graph_%s.npz" % tag), **out)
     print(tag, "layers(backbone)=%d" % rec["n_backbone_layers"], "weights=%d" % len(names),
           "reg", out["regression"].shape, float(np.abs(out["regression"]).max()),
           "cls", out["classification"].shape, float(out["classification"].min()),
@@ -103,5 +103,12 @@ def run_case(tag, phi, C, weighted, S, seed):
 
 
 if __name__ == "__main__":
-    for c in CASES:
-        run_case(*c)
+    # no arguments: regenerate the committed fixtures.  `--out DIR tag:phi:classes:weighted:side:seed ...` writes
+    # further cases elsewhere (tests/test_oracle_graph_golden.py runs the remaining model sizes live this way)
+    if len(sys.argv) > 1 and sys.argv[1] == "--out":
+        for spec in sys.argv[3:]:
+            tag, rest = spec.split(":", 1)
+            run_case(tag, *[int(v) for v in rest.split(":")], out_dir=sys.argv[2])
+    else:
+        for c in CASES:
+            run_case(*c)
