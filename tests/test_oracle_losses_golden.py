@@ -48,3 +48,21 @@ def test_fusion_matches_reference_layer():
         xs = [torch.tensor(x).permute(0, 3, 1, 2) for x in z["fuse%d_x" % n]]
         y = graph.fuse(xs, W, True, "w").permute(0, 2, 3, 1).numpy()
         assert np.abs(y - z["fuse%d_y" % n]).max() < 1e-12
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/utils/tpu.py"),
+                    reason="build container only: executes the reference's utils/tpu.py from where it lies")
+@pytest.mark.parametrize("seed", [1, 2])
+def test_losses_against_the_reference_executed_live_on_random_problems(seed):
+    """Beyond the committed fixture: 16 random problems per seed (batch, anchors, classes, positive / ignore
+    fractions incl. none at all, alpha / gamma / lambda) through the reference's own tpu_focal / tpu_smooth_l1 and
+    through oracle/losses.py -- values and gradients (tests/golden/check_losses_live.py, a subprocess because the
+    Keras stand-in replaces `tensorflow` in sys.modules)."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "check_losses_live.py"), str(seed)],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "16 cases agree" in r.stdout, r.stdout[-2000:]
